@@ -1,0 +1,71 @@
+"""ctypes binding of include/clairs_to_b200.h.  There is no CPU fallback: a missing library is an error."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcto_b200.so")
+
+_lib = None
+
+
+class HostStream(C.Structure):
+    _fields_ = [("code", C.c_void_p), ("bq", C.c_void_p), ("mq", C.c_void_p), ("pos_off", C.c_void_p),
+                ("ref_code", C.c_void_p), ("ind_off", C.c_void_p), ("ind_entry", C.c_void_p),
+                ("win_pos", C.c_void_p), ("n_reads", C.c_int64), ("n_rows", C.c_int64), ("n_ind", C.c_int64)]
+
+
+P, I32, I64, INT = C.c_void_p, C.c_int32, C.c_int64, C.c_int
+
+SIGNATURES = {
+    "cto_abi_version": (INT, []),
+    "cto_last_error": (C.c_char_p, []),
+    "cto_device_check": (INT, [P]),
+    "cto_encode_pileup": (INT, [P, P, P, P, P, P, P, P, I64, INT, P, P, P]),
+    "cto_engine_create": (INT, [P, I64, P, INT, P, I64, P, INT, I64, P]),
+    "cto_engine_destroy": (None, [P]),
+    "cto_engine_heads": (INT, [P]),
+    "cto_engine_set_likelihood": (INT, [P, P, INT]),
+    "cto_rescale": (INT, [P, P, I64, P, P]),
+    "cto_forward_aff": (INT, [P, P, I64, P, P]),
+    "cto_forward_neg": (INT, [P, P, I64, P, P]),
+    "cto_softmax_posterior": (INT, [P, P, P, I64, P, P, P, P]),
+    "cto_strand_counts": (INT, [P, I64, P, P, P]),
+    "cto_predict": (INT, [P, P, P, P, P, I64, P, P, P, P, P, P, P, P]),
+    "cto_run_sites_host": (INT, [P, P, P, I64, INT, P, P, P, P, P, P]),
+    "cto_tokenize_mpileup": (INT, [C.c_char_p, I64, C.c_char_p, I64, I64, P, I64, INT, P]),
+    "cto_tokens_sizes": (INT, [P, P, P, P, P]),
+    "cto_tokens_export": (INT, [P, P, P, P, P, P, P, P, P, P, P]),
+    "cto_tokens_destroy": (None, [P]),
+    "cto_format_tensor_row": (I64, [P, P, I64]),
+    "cto_format_prob_fields": (I64, [P, INT, P, I64]),
+    "cto_parse_tensor_row": (INT, [C.c_char_p, I64, P]),
+}
+
+
+class CtoError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libcto_b200.so (built in-tree by clairs_to_b200.build); raise if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CtoError("%s not found: run `python -m clairs_to_b200.build` (nvcc, sm_100a). "
+                           "There is no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().cto_last_error()
+        raise CtoError("%s failed (%d): %s" % (what or "clairs_to_b200 call", rc, msg.decode() if msg else "?"))

@@ -1,0 +1,275 @@
+// C ABI (include/clairs_to_b200.h) over the CUDA kernels.
+#include "../../include/clairs_to_b200.h"
+#include "engine.cuh"
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+namespace cto {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off,
+                         const uint8_t* ref_code, const int32_t* ind_off, const uint32_t* ind_entry,
+                         const int32_t* win_pos, int64_t n_candidates, int low_bq_cut, int16_t* tensor,
+                         int32_t* depth, cudaStream_t stream);
+
+}  // namespace cto
+
+using namespace cto;
+
+struct cto_engine {
+    Engine e;
+};
+
+namespace {
+struct DevStream {
+    uint8_t *code = nullptr, *bq = nullptr, *mq = nullptr, *ref_code = nullptr;
+    int32_t *pos_off = nullptr, *ind_off = nullptr, *win_pos = nullptr;
+    uint32_t* ind_entry = nullptr;
+};
+
+template <typename T>
+int h2d(T** dst, const T* src, int64_t n, cudaStream_t s) {
+    CTO_CHECK(cudaMallocAsync((void**)dst, std::max<int64_t>(sizeof(T) * n, 16), s));
+    if (n > 0) CTO_CHECK(cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+int upload_stream(const cto_host_stream* hs, int64_t n_cand, DevStream& d, cudaStream_t s) {
+    int rc = 0;
+    rc |= h2d(&d.code, hs->code, hs->n_reads, s);
+    rc |= h2d(&d.bq, hs->bq, hs->n_reads, s);
+    rc |= h2d(&d.mq, hs->mq, hs->n_reads, s);
+    rc |= h2d(&d.pos_off, hs->pos_off, hs->n_rows + 1, s);
+    rc |= h2d(&d.ref_code, hs->ref_code, hs->n_rows, s);
+    rc |= h2d(&d.ind_off, hs->ind_off, hs->n_rows + 1, s);
+    rc |= h2d(&d.ind_entry, hs->ind_entry, hs->n_ind, s);
+    rc |= h2d(&d.win_pos, hs->win_pos, n_cand * N_POS, s);
+    return rc;
+}
+
+void free_stream(DevStream& d, cudaStream_t s) {
+    void* ptrs[] = {d.code, d.bq, d.mq, d.ref_code, d.pos_off, d.ind_off, d.win_pos, d.ind_entry};
+    for (void* p : ptrs)
+        if (p) cudaFreeAsync(p, s);
+}
+}  // namespace
+
+
+extern "C" {
+
+int cto_abi_version(void) { return CTO_ABI_VERSION; }
+const char* cto_last_error(void) { return get_error(); }
+
+int cto_device_check(int* sm_count) {
+    int dev = 0;
+    CTO_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    CTO_CHECK(cudaGetDeviceProperties(&p, dev));
+    CTO_REQUIRE(p.major == 10, "clairs_to_b200 is built for sm_100a only; device %d is sm_%d%d (%s)", dev, p.major,
+                p.minor, p.name);
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    return 0;
+}
+
+int cto_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off,
+                      const uint8_t* ref_code, const int32_t* ind_off, const uint32_t* ind_entry,
+                      const int32_t* win_pos, int64_t n_candidates, int low_bq_cut, int16_t* tensor, int32_t* depth,
+                      void* stream) {
+    CTO_REQUIRE(n_candidates >= 0, "encode_pileup: negative candidate count");
+    CTO_REQUIRE(n_candidates == 0 || (pos_off && ref_code && ind_off && win_pos && tensor),
+                "encode_pileup: NULL array");
+    return launch_encode_pileup(code, bq, mq, pos_off, ref_code, ind_off, ind_entry, win_pos, n_candidates, low_bq_cut,
+                                tensor, depth, (cudaStream_t)stream);
+}
+
+int cto_engine_create(const float* aff_blob, int64_t aff_len, const int32_t* aff_cfg, int aff_cfg_len,
+                      const float* neg_blob, int64_t neg_len, const int32_t* neg_cfg, int neg_cfg_len, int64_t max_batch,
+                      cto_engine** out) {
+    CTO_REQUIRE(out && aff_blob && neg_blob && aff_cfg && neg_cfg, "engine_create: NULL argument");
+    CTO_REQUIRE(max_batch > 0 && max_batch <= (1 << 20), "engine_create: max_batch %lld out of range", (long long)max_batch);
+    if (cto_device_check(nullptr)) return 3;
+    cto_engine* h = new (std::nothrow) cto_engine();
+    CTO_REQUIRE(h, "engine_create: out of host memory");
+    int rc = aff_load(h->e.aff, aff_blob, aff_len, aff_cfg, aff_cfg_len);
+    if (!rc) rc = neg_load(h->e.neg, neg_blob, neg_len, neg_cfg, neg_cfg_len);
+    if (!rc && h->e.aff.n_heads != h->e.neg.n_heads) {
+        set_error("engine_create: AFF has %d heads, NEG has %d", h->e.aff.n_heads, h->e.neg.n_heads);
+        rc = 2;
+    }
+    if (!rc) rc = engine_alloc(h->e, max_batch);
+    if (rc) {
+        engine_free(h->e);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+void cto_engine_destroy(cto_engine* h) {
+    if (!h) return;
+    cudaDeviceSynchronize();
+    engine_free(h->e);
+    delete h;
+}
+
+int cto_engine_heads(const cto_engine* h) { return h ? h->e.aff.n_heads : 0; }
+
+int cto_engine_set_likelihood(cto_engine* h, const double* tables, int n_heads) {
+    CTO_REQUIRE(h && tables, "set_likelihood: NULL argument");
+    CTO_REQUIRE(n_heads == h->e.aff.n_heads, "set_likelihood: tables for %d heads, engine has %d", n_heads,
+                h->e.aff.n_heads);
+    if (!h->e.tables) CTO_CHECK(cudaMalloc(&h->e.tables, sizeof(double) * 122 * 6));
+    CTO_CHECK(cudaMemcpy(h->e.tables, tables, sizeof(double) * 122 * n_heads, cudaMemcpyHostToDevice));
+    h->e.table_heads = n_heads;
+    return 0;
+}
+
+int cto_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, void* stream) {
+    return launch_rescale(x, depth, n, out, (cudaStream_t)stream);
+}
+
+int cto_forward_aff(cto_engine* h, const float* x, int64_t n, float* logits, void* stream) {
+    CTO_REQUIRE(h && (n == 0 || (x && logits)), "forward_aff: NULL argument");
+    const int nh = h->e.aff.n_heads;
+    for (int64_t o = 0; o < n; o += h->e.max_batch) {
+        const int64_t nb = std::min(h->e.max_batch, n - o);
+        if (int rc = aff_forward(h->e, x + o * N_POS * N_CH, nb, logits + o * nh * 2, (cudaStream_t)stream)) return rc;
+    }
+    return 0;
+}
+
+int cto_forward_neg(cto_engine* h, const float* x, int64_t n, float* logits, void* stream) {
+    CTO_REQUIRE(h && (n == 0 || (x && logits)), "forward_neg: NULL argument");
+    const int nh = h->e.neg.n_heads;
+    for (int64_t o = 0; o < n; o += h->e.max_batch) {
+        const int64_t nb = std::min(h->e.max_batch, n - o);
+        if (int rc = neg_forward(h->e, x + o * N_POS * N_CH, nb, logits + o * nh * 2, (cudaStream_t)stream)) return rc;
+    }
+    return 0;
+}
+
+int cto_softmax_posterior(cto_engine* h, const float* la, const float* ln, int64_t n, float* probs, double* post,
+                          int32_t* call, void* stream) {
+    CTO_REQUIRE(h && (n == 0 || (la && ln)), "softmax_posterior: NULL argument");
+    const double* tables = (post || call) ? h->e.tables : nullptr;
+    CTO_REQUIRE(!(post || call) || tables, "softmax_posterior: posterior requested but no likelihood tables set");
+    return launch_softmax_posterior(la, ln, n, h->e.aff.n_heads, tables, probs, post, call, (cudaStream_t)stream);
+}
+
+int cto_strand_counts(const int16_t* x, int64_t n, int32_t* fwd, int32_t* rev, void* stream) {
+    CTO_REQUIRE(n == 0 || (x && fwd && rev), "strand_counts: NULL argument");
+    return launch_strand_counts(x, n, fwd, rev, (cudaStream_t)stream);
+}
+
+int cto_predict(cto_engine* h, const int16_t* x_aff, const int32_t* depth_aff, const int16_t* x_neg,
+                const int32_t* depth_neg, int64_t n, float* logits_aff, float* logits_neg, float* probs, double* post,
+                int32_t* call, int32_t* fwd, int32_t* rev, void* stream) {
+    CTO_REQUIRE(h && (n == 0 || (x_aff && x_neg && depth_aff && depth_neg && logits_aff && logits_neg)),
+                "predict: NULL argument");
+    Engine& e = h->e;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nh = e.aff.n_heads;
+    const int64_t xin = (int64_t)N_POS * N_CH;
+    for (int64_t o = 0; o < n; o += e.max_batch) {
+        const int64_t nb = std::min(e.max_batch, n - o);
+        // fork: NEG on the side stream, AFF on the caller's stream
+        CTO_CHECK(cudaEventRecord(e.ev_fork, s));
+        CTO_CHECK(cudaStreamWaitEvent(e.side, e.ev_fork, 0));
+        if (int rc = launch_rescale(x_neg + o * xin, depth_neg + o, nb, e.x_neg, e.side)) return rc;
+        if (int rc = neg_forward(e, e.x_neg, nb, logits_neg + o * nh * 2, e.side)) return rc;
+        CTO_CHECK(cudaEventRecord(e.ev_join, e.side));
+        if (int rc = launch_rescale(x_aff + o * xin, depth_aff + o, nb, e.x_aff, s)) return rc;
+        if (int rc = aff_forward(e, e.x_aff, nb, logits_aff + o * nh * 2, s)) return rc;
+        CTO_CHECK(cudaStreamWaitEvent(s, e.ev_join, 0));
+    }
+    if (fwd && rev)
+        if (int rc = launch_strand_counts(x_aff, n, fwd, rev, s)) return rc;
+    if (probs || post || call) {
+        const double* tables = (post || call) ? e.tables : nullptr;
+        CTO_REQUIRE(!(post || call) || tables, "predict: posterior requested but no likelihood tables set");
+        if (int rc = launch_softmax_posterior(logits_aff, logits_neg, n, nh, tables, probs, post, call, s)) return rc;
+    }
+    return 0;
+}
+
+int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host_stream* neg, int64_t n, int low_bq_cut,
+                       float* probs_host, double* post_host, int32_t* call_host, int16_t* tensor_aff_host,
+                       int16_t* tensor_neg_host, void* stream) {
+    CTO_REQUIRE(h && aff, "run_sites_host: NULL argument");
+    if (n <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nh = h->e.aff.n_heads;
+    const int64_t xin = (int64_t)N_POS * N_CH;
+    DevStream da, dn;
+    int16_t *ta = nullptr, *tn = nullptr;
+    int32_t *dpa = nullptr, *dpn = nullptr, *call = nullptr;
+    float *la = nullptr, *ln = nullptr, *probs = nullptr;
+    double* post = nullptr;
+    int rc = upload_stream(aff, n, da, s);
+    if (!rc && neg) rc = upload_stream(neg, n, dn, s);
+    auto alloc = [&](void** p, int64_t bytes) { return cudaMallocAsync(p, bytes, s) != cudaSuccess; };
+    if (!rc) {
+        rc |= alloc((void**)&ta, sizeof(int16_t) * n * xin);
+        rc |= alloc((void**)&dpa, sizeof(int32_t) * n);
+        if (neg) {
+            rc |= alloc((void**)&tn, sizeof(int16_t) * n * xin);
+            rc |= alloc((void**)&dpn, sizeof(int32_t) * n);
+        }
+        rc |= alloc((void**)&la, sizeof(float) * n * nh * 2);
+        rc |= alloc((void**)&ln, sizeof(float) * n * nh * 2);
+        rc |= alloc((void**)&probs, sizeof(float) * n * nh * 4);
+        rc |= alloc((void**)&post, sizeof(double) * n * nh);
+        rc |= alloc((void**)&call, sizeof(int32_t) * n);
+        if (rc) set_error("run_sites_host: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc)
+        rc = launch_encode_pileup(da.code, da.bq, da.mq, da.pos_off, da.ref_code, da.ind_off, da.ind_entry, da.win_pos, n,
+                                  low_bq_cut, ta, dpa, s);
+    if (!rc && neg)
+        rc = launch_encode_pileup(dn.code, dn.bq, dn.mq, dn.pos_off, dn.ref_code, dn.ind_off, dn.ind_entry, dn.win_pos, n,
+                                  low_bq_cut, tn, dpn, s);
+    const bool want_post = h->e.tables && (post_host || call_host);
+    if (!rc)
+        rc = cto_predict(h, ta, dpa, neg ? tn : ta, neg ? dpn : dpa, n, la, ln, probs, want_post ? post : nullptr,
+                         want_post ? call : nullptr, nullptr, nullptr, s);
+    if (!rc) {
+        cudaError_t ce = cudaSuccess;
+        if (probs_host) ce = cudaMemcpyAsync(probs_host, probs, sizeof(float) * n * nh * 4, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess && want_post && post_host)
+            ce = cudaMemcpyAsync(post_host, post, sizeof(double) * n * nh, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess && want_post && call_host)
+            ce = cudaMemcpyAsync(call_host, call, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess && tensor_aff_host)
+            ce = cudaMemcpyAsync(tensor_aff_host, ta, sizeof(int16_t) * n * xin, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess && tensor_neg_host)
+            ce = cudaMemcpyAsync(tensor_neg_host, neg ? tn : ta, sizeof(int16_t) * n * xin, cudaMemcpyDeviceToHost, s);
+        if (ce != cudaSuccess) {
+            set_error("run_sites_host: D2H copy failed: %s", cudaGetErrorString(ce));
+            rc = 1;
+        }
+    }
+    free_stream(da, s);
+    free_stream(dn, s);
+    void* ptrs[] = {ta, tn, dpa, dpn, la, ln, probs, post, call};
+    for (void* p : ptrs)
+        if (p) cudaFreeAsync(p, s);
+    cudaError_t se = cudaStreamSynchronize(s);
+    if (!rc && se != cudaSuccess) {
+        set_error("run_sites_host: %s", cudaGetErrorString(se));
+        rc = 1;
+    }
+    return rc;
+}
+
+}  // extern "C"

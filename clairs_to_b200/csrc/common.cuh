@@ -1,0 +1,41 @@
+// Shared helpers for the clairs-to_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+namespace cto {
+
+constexpr int N_POS = 33;     // shared/param.py:60  (2 * flankingBaseNum + 1)
+constexpr int N_CH = 34;      // shared/param.py:56  (len(pileup_channel))
+constexpr int CENTER = 16;    // shared/param.py:59
+constexpr int MIN_MQ = 20;    // literal in src/create_tensor_pileup_calling.py:147-148
+constexpr int QUAL_ABSENT = 254;
+constexpr int MIN_RESCALE_COV = 50;  // shared/param.py:26
+
+// thread-local error string behind cto_last_error()
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define CTO_CHECK(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            cto::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,               \
+                           cudaGetErrorString(_e));                                           \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+#define CTO_REQUIRE(cond, ...)                                                                \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            cto::set_error(__VA_ARGS__);                                                      \
+            return 2;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace cto

@@ -1,0 +1,235 @@
+// Weight blob walking, workspace and layer-by-layer forward of AFF / NEG.
+// Reference structure: clairs/model.py:134-147 (Transformer), 194-198 (stage), 231-261 (CvT.forward),
+// 440-467 (BiGRU_NACGT.forward); hyper-parameters come from the blob's cfg, not from constants.
+#include "engine.cuh"
+#include <algorithm>
+
+namespace cto {
+
+namespace {
+struct Walker {
+    const float* base;
+    int64_t off = 0, total;
+    const float* take(int64_t n) {
+        const float* p = base + off;
+        off += (n + 3) & ~int64_t(3);          // every segment is padded to 4 floats (16 B)
+        return p;
+    }
+};
+
+int upload(const float* host, int64_t n, float** dev) {
+    CTO_CHECK(cudaMalloc(dev, sizeof(float) * n));
+    CTO_CHECK(cudaMemcpy(*dev, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void walk_head(Walker& w, HeadW& h, int feat, int n_heads) {
+    h.fc1_w = w.take((int64_t)FC_DIM * feat);
+    h.fc1_b = w.take(FC_DIM);
+    h.fc2_w = w.take((int64_t)n_heads * FC_DIM * FC_DIM);
+    h.fc2_b = w.take((int64_t)n_heads * FC_DIM);
+    h.fc3_w = w.take((int64_t)n_heads * 2 * FC_DIM);
+    h.fc3_b = w.take((int64_t)n_heads * 2);
+}
+}  // namespace
+
+int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg, int cfg_len) {
+    CTO_REQUIRE(cfg_len >= 2 && cfg_len == 2 + 3 * cfg[1], "aff cfg: expected [n_heads, n_stages, (C, heads, depth)*]");
+    m.n_heads = cfg[0];
+    m.n_stages = cfg[1];
+    CTO_REQUIRE(m.n_stages >= 1 && m.n_stages <= 3, "aff cfg: %d stages unsupported", m.n_stages);
+    CTO_REQUIRE(m.n_heads == 4 || m.n_heads == 6, "aff cfg: %d heads (expected 4 or 6)", m.n_heads);
+    if (upload(host_blob, n, &m.blob)) return 1;
+    Walker w{m.blob, 0, n};
+    int cin = N_CH, win = N_POS;
+    for (int s = 0; s < m.n_stages; ++s) {
+        CvtStage& st = m.st[s];
+        st.c = cfg[2 + 3 * s];
+        st.heads = cfg[3 + 3 * s];
+        st.depth = cfg[4 + 3 * s];
+        CTO_REQUIRE(st.depth <= MAX_DEPTH && st.c <= 128 && st.c % 4 == 0, "aff cfg: stage %d C=%d depth=%d unsupported",
+                    s, st.c, st.depth);
+        st.cin = cin;
+        st.win = win;
+        st.wout = (win + 1) / 2;                 // 3-tap, stride 2, pad 1
+        st.wkv = (st.wout + 1) / 2;
+        const int c = st.c, inner = st.heads * DIM_HEAD;
+        st.embed_w = w.take((int64_t)c * 3 * cin);
+        st.embed_b = w.take(c);
+        st.ln_g = w.take(c);
+        st.ln_b = w.take(c);
+        for (int d = 0; d < st.depth; ++d) {
+            CvtLayer& L = st.layers[d];
+            L.ln1_g = w.take(c);
+            L.ln1_b = w.take(c);
+            L.q_dw = w.take(3 * c);
+            L.q_pw = w.take((int64_t)inner * c);
+            L.q_bias = w.take(inner);
+            L.kv_dw = w.take(3 * c);
+            L.kv_pw = w.take((int64_t)2 * inner * c);
+            L.kv_bias = w.take(2 * inner);
+            L.out_w = w.take((int64_t)c * inner);
+            L.out_b = w.take(c);
+            L.ln2_g = w.take(c);
+            L.ln2_b = w.take(c);
+            L.ff1_w = w.take((int64_t)4 * c * c);
+            L.ff1_b = w.take(4 * c);
+            L.ff2_w = w.take((int64_t)4 * c * c);
+            L.ff2_b = w.take(c);
+        }
+        m.sz_x = std::max<int64_t>(m.sz_x, (int64_t)st.wout * c);
+        m.sz_kvin = std::max<int64_t>(m.sz_kvin, (int64_t)st.wkv * c);
+        m.sz_q = std::max<int64_t>(m.sz_q, (int64_t)st.wout * inner);
+        m.sz_kv = std::max<int64_t>(m.sz_kv, (int64_t)st.wkv * 2 * inner);
+        m.sz_ff = std::max<int64_t>(m.sz_ff, (int64_t)st.wout * 4 * c);
+        cin = c;
+        win = st.wout;
+    }
+    m.feat = cin * win;
+    walk_head(w, m.head, m.feat, m.n_heads);
+    CTO_REQUIRE(w.off == n, "aff blob: %lld floats given, layout needs %lld", (long long)n, (long long)w.off);
+    return 0;
+}
+
+int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg, int cfg_len) {
+    CTO_REQUIRE(cfg_len == 4, "neg cfg: expected [n_heads, in_dim, H1, H2]");
+    m.n_heads = cfg[0];
+    CTO_REQUIRE(m.n_heads == 4 || m.n_heads == 6, "neg cfg: %d heads (expected 4 or 6)", m.n_heads);
+    CTO_REQUIRE(cfg[1] == N_CH, "neg cfg: input dim %d != %d", cfg[1], N_CH);
+    if (upload(host_blob, n, &m.blob)) return 1;
+    Walker w{m.blob, 0, n};
+    int in_dim = cfg[1];
+    for (int l = 0; l < 2; ++l) {
+        GruLayerW& g = m.l[l];
+        g.in_dim = in_dim;
+        g.hidden = cfg[2 + l];
+        const int h = g.hidden;
+        g.wih = w.take((int64_t)6 * h * in_dim);
+        g.bih = w.take(6 * h);
+        g.whh_t = w.take((int64_t)2 * h * 3 * h);
+        g.bhn = w.take(2 * h);
+        in_dim = 2 * h;
+    }
+    walk_head(w, m.head, N_POS * in_dim, m.n_heads);
+    CTO_REQUIRE(w.off == n, "neg blob: %lld floats given, layout needs %lld", (long long)n, (long long)w.off);
+    return 0;
+}
+
+namespace {
+int dev_alloc(Engine& e, float** p, int64_t n_floats) {
+    void* q = nullptr;
+    CTO_CHECK(cudaMalloc(&q, sizeof(float) * std::max<int64_t>(n_floats, 4)));
+    e.allocs.push_back(q);
+    *p = static_cast<float*>(q);
+    return 0;
+}
+}  // namespace
+
+int engine_alloc(Engine& e, int64_t max_batch) {
+    e.max_batch = max_batch;
+    const int64_t b = max_batch;
+    const AffModel& a = e.aff;
+    const NegModel& g = e.neg;
+    const int64_t xin = (int64_t)N_POS * N_CH;
+    int rc = 0;
+    rc |= dev_alloc(e, &e.x_aff, b * xin);
+    rc |= dev_alloc(e, &e.x_neg, b * xin);
+    rc |= dev_alloc(e, &e.a_t0, b * a.sz_x);
+    rc |= dev_alloc(e, &e.a_xs, b * a.sz_x);
+    rc |= dev_alloc(e, &e.a_y, b * a.sz_x);
+    rc |= dev_alloc(e, &e.a_dq, b * a.sz_x);
+    rc |= dev_alloc(e, &e.a_dkv, b * a.sz_kvin);
+    rc |= dev_alloc(e, &e.a_q, b * a.sz_q);
+    rc |= dev_alloc(e, &e.a_kv, b * a.sz_kv);
+    rc |= dev_alloc(e, &e.a_att, b * a.sz_q);
+    rc |= dev_alloc(e, &e.a_ff, b * a.sz_ff);
+    const int64_t xp = (int64_t)N_POS * 6 * std::max(g.l[0].hidden, g.l[1].hidden);
+    rc |= dev_alloc(e, &e.n_xp, b * xp);
+    rc |= dev_alloc(e, &e.n_o1, b * N_POS * 2 * g.l[0].hidden);
+    rc |= dev_alloc(e, &e.n_o2, b * N_POS * 2 * g.l[1].hidden);
+    rc |= dev_alloc(e, &e.f1, b * FC_DIM);
+    rc |= dev_alloc(e, &e.f2, b * 6 * FC_DIM);
+    rc |= dev_alloc(e, &e.f1n, b * FC_DIM);
+    rc |= dev_alloc(e, &e.f2n, b * 6 * FC_DIM);
+    if (rc) return 1;
+    CTO_CHECK(cudaStreamCreateWithFlags(&e.side, cudaStreamNonBlocking));
+    CTO_CHECK(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming));
+    CTO_CHECK(cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming));
+    return 0;
+}
+
+void engine_free(Engine& e) {
+    for (void* p : e.allocs) cudaFree(p);
+    e.allocs.clear();
+    if (e.aff.blob) cudaFree(e.aff.blob);
+    if (e.neg.blob) cudaFree(e.neg.blob);
+    if (e.tables) cudaFree(e.tables);
+    if (e.side) cudaStreamDestroy(e.side);
+    if (e.ev_fork) cudaEventDestroy(e.ev_fork);
+    if (e.ev_join) cudaEventDestroy(e.ev_join);
+}
+
+#define RUN(x) do { if (int _rc = (x)) return _rc; } while (0)
+
+static int run_heads(const HeadW& h, const float* feat, int feat_dim, int n_heads, int64_t n, float* f1, float* f2,
+                     float* logits, cudaStream_t s) {
+    // fc1 -> SELU -> per-head fc2 -> SELU -> fc3 -> SELU  (clairs/model.py:239-253)
+    RUN(launch_gemm_nt(plain_a(feat, feat_dim), h.fc1_w, h.fc1_b, nullptr, 0, f1, FC_DIM, n, FC_DIM, feat_dim, ACT_SELU, s));
+    RUN(launch_gemm_nt(plain_a(f1, FC_DIM), h.fc2_w, h.fc2_b, nullptr, 0, f2, (int64_t)n_heads * FC_DIM, n,
+                       n_heads * FC_DIM, FC_DIM, ACT_SELU, s));
+    RUN(launch_head_fc3(f2, h.fc3_w, h.fc3_b, logits, n, n_heads, s));
+    return 0;
+}
+
+int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {
+    CTO_REQUIRE(n <= e.max_batch, "aff_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
+    const AffModel& m = e.aff;
+    const float* cur = x;
+    for (int si = 0; si < m.n_stages; ++si) {
+        const CvtStage& st = m.st[si];
+        const int c = st.c, inner = st.heads * DIM_HEAD;
+        const int64_t rows = n * st.wout, rows_kv = n * st.wkv;
+        // embed conv (3-tap, stride 2, pad 1) + channel LN  (clairs/model.py:195-196)
+        RUN(launch_gemm_nt(conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows, c,
+                           3 * st.cin, ACT_NONE, s));
+        RUN(launch_channel_ln(e.a_t0, st.ln_g, st.ln_b, e.a_xs, rows, c, s));
+        for (int d = 0; d < st.depth; ++d) {
+            const CvtLayer& L = st.layers[d];
+            // x = Attention(LN(x)) + x   (clairs/model.py:145)
+            RUN(launch_channel_ln(e.a_xs, L.ln1_g, L.ln1_b, e.a_y, rows, c, s));
+            RUN(launch_dwconv3(e.a_y, L.q_dw, e.a_dq, n, st.wout, st.wout, 1, c, s));
+            RUN(launch_dwconv3(e.a_y, L.kv_dw, e.a_dkv, n, st.wout, st.wkv, 2, c, s));
+            RUN(launch_gemm_nt(plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c, ACT_NONE, s));
+            RUN(launch_gemm_nt(plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv, 2 * inner, c,
+                               ACT_NONE, s));
+            RUN(launch_attention(e.a_q, e.a_kv, e.a_att, n, st.wout, st.wkv, st.heads, s));
+            RUN(launch_gemm_nt(plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner, ACT_NONE, s));
+            // x = FF(LN(x)) + x          (clairs/model.py:146)
+            RUN(launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, e.a_y, rows, c, s));
+            RUN(launch_gemm_nt(plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
+            RUN(launch_gemm_nt(plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c, ACT_NONE, s));
+        }
+        // the next stage reads a_xs while writing a_t0, so no copy is needed
+        cur = e.a_xs;
+    }
+    return run_heads(m.head, cur, m.feat, m.n_heads, n, e.f1, e.f2, logits, s);
+}
+
+int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {
+    CTO_REQUIRE(n <= e.max_batch, "neg_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
+    const NegModel& m = e.neg;
+    const float* cur = x;
+    float* outs[2] = {e.n_o1, e.n_o2};
+    for (int l = 0; l < 2; ++l) {
+        const GruLayerW& g = m.l[l];
+        const int h = g.hidden;
+        RUN(launch_gemm_nt(plain_a(cur, g.in_dim), g.wih, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS, 6 * h, g.in_dim,
+                           ACT_NONE, s));
+        RUN(launch_gru_recurrent(e.n_xp, g.whh_t, g.bhn, outs[l], n, h, s));
+        cur = outs[l];
+    }
+    const int feat = N_POS * 2 * m.l[1].hidden;
+    return run_heads(m.head, cur, feat, m.n_heads, n, e.f1n, e.f2n, logits, s);
+}
+
+}  // namespace cto

@@ -1,0 +1,77 @@
+// Weight layout + forward orchestration for the AFF (CvT) and NEG (BiGRU) networks.
+// The flat fp32 weight blobs are produced by clairs_to_b200/weights.py from a reference
+// checkpoint's state_dict; both sides walk the SAME segment order below.
+#pragma once
+#include "nn_kernels.cuh"
+#include <vector>
+
+namespace cto {
+
+constexpr int MAX_DEPTH = 16;
+constexpr int DIM_HEAD = 64;       // clairs/model.py:103
+constexpr int FC_DIM = 128;        // clairs/model.py:214, 419
+
+struct CvtLayer {
+    const float *ln1_g, *ln1_b, *q_dw, *q_pw, *q_bias, *kv_dw, *kv_pw, *kv_bias, *out_w, *out_b;
+    const float *ln2_g, *ln2_b, *ff1_w, *ff1_b, *ff2_w, *ff2_b;
+};
+
+struct CvtStage {
+    int c, cin, heads, depth, win, wout, wkv;
+    const float *embed_w, *embed_b, *ln_g, *ln_b;
+    CvtLayer layers[MAX_DEPTH];
+};
+
+struct HeadW {
+    const float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
+};
+
+struct AffModel {
+    int n_heads = 0, n_stages = 0, feat = 0;
+    CvtStage st[3];
+    HeadW head;
+    float* blob = nullptr;
+    // per-candidate workspace sizes (floats)
+    int64_t sz_x = 0, sz_kvin = 0, sz_q = 0, sz_kv = 0, sz_ff = 0;
+};
+
+struct GruLayerW {
+    int in_dim, hidden;
+    const float *wih, *bih, *whh_t, *bhn;
+};
+
+struct NegModel {
+    int n_heads = 0;
+    GruLayerW l[2];
+    HeadW head;
+    float* blob = nullptr;
+};
+
+struct Engine {
+    AffModel aff;
+    NegModel neg;
+    int64_t max_batch = 0;
+    // workspace (device, fp32)
+    float *x_aff = nullptr, *x_neg = nullptr;                  // rescaled network inputs [chunk, 33, 34]
+    float *a_t0 = nullptr, *a_xs = nullptr, *a_y = nullptr, *a_dq = nullptr, *a_dkv = nullptr;
+    float *a_q = nullptr, *a_kv = nullptr, *a_att = nullptr, *a_ff = nullptr;
+    float *n_xp = nullptr, *n_o1 = nullptr, *n_o2 = nullptr;
+    float *f1 = nullptr, *f2 = nullptr;                        // head activations (shared sizes)
+    float *f1n = nullptr, *f2n = nullptr;
+    double* tables = nullptr;                                  // likelihood tables, n_heads * 122
+    int table_heads = 0;
+    cudaStream_t side = nullptr;                               // NEG runs beside AFF
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::vector<void*> allocs;
+};
+
+int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg, int cfg_len);
+int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg, int cfg_len);
+int engine_alloc(Engine& e, int64_t max_batch);
+void engine_free(Engine& e);
+
+// x: device fp32 [n, 33, 34]; logits: device fp32 [n, n_heads, 2]; n <= max_batch
+int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
+int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
+
+}  // namespace cto

@@ -1,0 +1,344 @@
+// Host side of the C ABI: mpileup tokenizer and chunk-file text codec (no CUDA).
+//
+// Tokenizer semantics follow src/create_tensor_pileup_calling.py:120-144 (token loop), 147-149
+// (positional zip with the quality strings), 158-209 (alt_info), 472-497 (row split); cited as CT.
+#include "../../include/clairs_to_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace cto {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+constexpr uint8_t HAS_INDEL = 0x10;
+constexpr uint8_t QUAL_ABSENT = 254;
+constexpr uint32_t IND_DEL = 1u << 24, IND_REV = 1u << 25, IND_LONG = 1u << 26;
+
+inline int symbol_index(char c) {
+    switch (c) {
+        case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; case 'N': return 4;
+        case 'a': return 5; case 'c': return 6; case 'g': return 7; case 't': return 8; case 'n': return 9;
+        case '*': return 10; case '#': return 11;
+        default: return -1;
+    }
+}
+
+inline char upper(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+
+inline int coerce_ref(char c) {            // evc_base_from + upper (CT:82-92, 485)
+    switch (upper(c)) {
+        case 'C': return 1; case 'G': return 2; case 'T': return 3;
+        default: return 0;                 // A, N and every IUPAC code become A
+    }
+}
+
+struct Entry {
+    char sym;
+    char sign;                             // '+', '-' or 0 when the read carries no indel
+    int32_t seq_begin, seq_len;            // indel sequence as a slice of the row's bases string
+};
+
+}  // namespace
+
+struct cto_tokens {
+    std::vector<uint8_t> code, bq, mq, ref_code;
+    std::vector<int32_t> pos_off, ind_off;
+    std::vector<uint32_t> ind_entry;
+    std::vector<int64_t> row_pos;
+    std::string alt_info;
+    std::vector<int64_t> alt_off;
+};
+
+extern "C" {
+
+int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq, int64_t ref_len, int64_t ref_start,
+                         const int64_t* candidate_pos, int64_t n_candidates, int max_indel_length, cto_tokens** out) {
+    if (!text || !ref_seq || !out) {
+        cto::set_error("tokenize_mpileup: NULL argument");
+        return 2;
+    }
+    std::unordered_set<int64_t> cand;
+    for (int64_t i = 0; i < n_candidates; ++i) cand.insert(candidate_pos[i]);
+    cto_tokens* t = new cto_tokens();
+    t->pos_off.push_back(0);
+    t->ind_off.push_back(0);
+    t->alt_off.push_back(0);
+    std::vector<Entry> entries;
+    std::unordered_map<std::string, uint32_t> allele_ids;
+    std::vector<std::pair<std::string, int>> main_counts;          // first-occurrence ordered Counter
+    std::unordered_map<std::string, size_t> main_index;
+    std::vector<std::pair<std::string, int>> alt;                  // ordered alt_info_dict
+    std::unordered_map<std::string, size_t> alt_index;
+
+    const char* p = text;
+    const char* end = text + text_len;
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', end - p);
+        if (!eol) eol = end;
+        const char* col[8];
+        int col_len[8];
+        int ncol = 0;
+        const char* q = p;
+        while (q <= eol && ncol < 8) {
+            const char* tab = (const char*)memchr(q, '\t', eol - q);
+            if (!tab) tab = eol;
+            col[ncol] = q;
+            col_len[ncol] = (int)(tab - q);
+            ++ncol;
+            q = tab + 1;
+        }
+        const char* next = eol + 1;
+        if (ncol == 0 || (ncol == 1 && col_len[0] == 0)) { p = next; continue; }
+        if (ncol < 7) {
+            cto::set_error("tokenize_mpileup: row with %d columns (need 7: chr pos ref depth bases BQ MQ)", ncol);
+            delete t;
+            return 2;
+        }
+        while (col_len[6] > 0 && (col[6][col_len[6] - 1] == '\r' || col[6][col_len[6] - 1] == ' ')) --col_len[6];   // row.strip()
+        const int64_t pos = strtoll(col[1], nullptr, 10);
+        const int64_t roff = pos - ref_start;
+        if (roff < 0 || roff >= ref_len) {
+            cto::set_error("tokenize_mpileup: position %lld outside the reference window", (long long)pos);
+            delete t;
+            return 2;
+        }
+        const int ref = coerce_ref(ref_seq[roff]);
+        const char* bases = col[4];
+        const int nb = col_len[4];
+
+        entries.clear();
+        for (int i = 0; i < nb;) {                                   // CT:120-144
+            const char ch = bases[i];
+            if (ch == '+' || ch == '-') {
+                int j = i + 1, len = 0;
+                while (j < nb && bases[j] >= '0' && bases[j] <= '9') { len = len * 10 + (bases[j] - '0'); ++j; }
+                if (!entries.empty()) {                              // attaches to (overwrites on) the previous entry
+                    const int avail = nb - j > 0 ? nb - j : 0;
+                    entries.back().sign = ch;
+                    entries.back().seq_begin = j;
+                    entries.back().seq_len = len < avail ? len : avail;
+                }
+                i = j + len;
+                continue;
+            }
+            if (symbol_index(ch) >= 0) entries.push_back(Entry{ch, 0, 0, 0});
+            else if (ch == '^') ++i;
+            ++i;
+        }
+
+        const int n_mq = col_len[6], n_bq = col_len[5];
+        allele_ids.clear();
+        main_counts.clear();
+        main_index.clear();
+        const bool is_cand = cand.count(pos) != 0;
+        for (size_t k = 0; k < entries.size(); ++k) {
+            const Entry& e = entries[k];
+            const uint8_t mqv = (int)k < n_mq ? (uint8_t)(col[6][k] - 33) : QUAL_ABSENT;
+            const uint8_t bqv = (int)k < n_bq ? (uint8_t)(col[5][k] - 33) : QUAL_ABSENT;
+            uint8_t c = (uint8_t)symbol_index(e.sym);
+            std::string key(1, e.sym);
+            if (e.sign) {
+                const bool is_del = e.sign == '-';
+                const int seq_len = e.seq_len;
+                key.push_back(e.sign);
+                key.append(bases + e.seq_begin, seq_len);
+                c |= HAS_INDEL;
+                auto it = allele_ids.find(key);
+                uint32_t id;
+                if (it == allele_ids.end()) {
+                    id = (uint32_t)allele_ids.size();
+                    allele_ids.emplace(key, id);
+                } else {
+                    id = it->second;
+                }
+                uint32_t ent = (id & 0xFFFF) | ((uint32_t)mqv << 16);
+                if (is_del) ent |= IND_DEL;
+                const char s = e.sym;
+                const bool fwd = s == 'A' || s == 'C' || s == 'G' || s == 'T' || s == 'N' || s == '*';   // CT:182, 199
+                if (!fwd) ent |= IND_REV;
+                const int span = is_del ? seq_len + 1 : seq_len;     // CT:174, 189 (deletion counts the sign)
+                if (span > max_indel_length) ent |= IND_LONG;
+                t->ind_entry.push_back(ent);
+            }
+            t->code.push_back(c);
+            t->mq.push_back(mqv);
+            t->bq.push_back(bqv);
+            if (is_cand && mqv != QUAL_ABSENT && mqv >= 20) {        // base_counter, CT:147
+                auto it = main_index.find(key);
+                if (it == main_index.end()) {
+                    main_index.emplace(key, main_counts.size());
+                    main_counts.emplace_back(key, 1);
+                } else {
+                    ++main_counts[it->second].second;
+                }
+            }
+        }
+        t->pos_off.push_back((int32_t)t->code.size());
+        t->ind_off.push_back((int32_t)t->ind_entry.size());
+        t->ref_code.push_back((uint8_t)ref);
+        t->row_pos.push_back(pos);
+
+        if (is_cand) {                                               // CT:153-209
+            alt.clear();
+            alt_index.clear();
+            auto bump = [&](const std::string& k, int n) {
+                auto it = alt_index.find(k);
+                if (it == alt_index.end()) {
+                    alt_index.emplace(k, alt.size());
+                    alt.emplace_back(k, n);
+                } else {
+                    alt[it->second].second += n;
+                }
+            };
+            const char ref_char = "ACGT"[ref];
+            int depth = 0, ref_count = 0;
+            for (const auto& kc : main_counts) {
+                const std::string& key = kc.first;
+                const int count = kc.second;
+                if (key.size() == 1) {
+                    const char u = upper(key[0]);
+                    if (u == 'A' || u == 'C' || u == 'G' || u == 'T') {
+                        if (u != ref_char) bump(std::string("X") + u, count);
+                        else ref_count += count;
+                        depth += count;
+                    } else if (key[0] == '#' || key[0] == '*') {
+                        depth += count;
+                    }
+                } else if (key[1] == '+') {
+                    if ((int)key.size() - 2 > max_indel_length) continue;
+                    depth += count;
+                    std::string name = "I";
+                    name.push_back(upper(key[0]));
+                    for (size_t z = 2; z < key.size(); ++z) name.push_back(upper(key[z]));
+                    bump(name, count);
+                } else {
+                    const int span = (int)key.size() - 1;
+                    if (span > max_indel_length) continue;
+                    depth += count;
+                    std::string name = "D";
+                    for (int z = 0; z < span && z < max_indel_length && roff + z < ref_len; ++z) name.push_back(upper(ref_seq[roff + z]));
+                    bump(name, count);
+                }
+            }
+            if (ref_count > 0) {
+                std::string name = "R";
+                name.push_back(ref_char);
+                auto it = alt_index.find(name);
+                if (it == alt_index.end()) alt.emplace_back(name, ref_count);
+                else alt[it->second].second = ref_count;
+            }
+            char buf[32];
+            snprintf(buf, sizeof(buf), "%d-", depth);
+            t->alt_info += buf;
+            for (size_t z = 0; z < alt.size(); ++z) {
+                if (z) t->alt_info.push_back(' ');
+                t->alt_info += alt[z].first;
+                snprintf(buf, sizeof(buf), " %d", alt[z].second);
+                t->alt_info += buf;
+            }
+            t->alt_info.push_back('-');
+        }
+        t->alt_off.push_back((int64_t)t->alt_info.size());
+        p = next;
+    }
+    *out = t;
+    return 0;
+}
+
+int cto_tokens_sizes(const cto_tokens* t, int64_t* n_reads, int64_t* n_rows, int64_t* n_ind, int64_t* alt_info_bytes) {
+    if (!t) return 2;
+    if (n_reads) *n_reads = (int64_t)t->code.size();
+    if (n_rows) *n_rows = (int64_t)t->ref_code.size();
+    if (n_ind) *n_ind = (int64_t)t->ind_entry.size();
+    if (alt_info_bytes) *alt_info_bytes = (int64_t)t->alt_info.size();
+    return 0;
+}
+
+int cto_tokens_export(const cto_tokens* t, uint8_t* code, uint8_t* bq, uint8_t* mq, int32_t* pos_off, uint8_t* ref_code,
+                      int32_t* ind_off, uint32_t* ind_entry, int64_t* row_pos, char* alt_info, int64_t* alt_info_off) {
+    if (!t) return 2;
+    auto cp = [](void* dst, const void* src, size_t n) { if (dst && n) memcpy(dst, src, n); };
+    cp(code, t->code.data(), t->code.size());
+    cp(bq, t->bq.data(), t->bq.size());
+    cp(mq, t->mq.data(), t->mq.size());
+    cp(pos_off, t->pos_off.data(), t->pos_off.size() * sizeof(int32_t));
+    cp(ref_code, t->ref_code.data(), t->ref_code.size());
+    cp(ind_off, t->ind_off.data(), t->ind_off.size() * sizeof(int32_t));
+    cp(ind_entry, t->ind_entry.data(), t->ind_entry.size() * sizeof(uint32_t));
+    cp(row_pos, t->row_pos.data(), t->row_pos.size() * sizeof(int64_t));
+    cp(alt_info, t->alt_info.data(), t->alt_info.size());
+    cp(alt_info_off, t->alt_off.data(), t->alt_off.size() * sizeof(int64_t));
+    return 0;
+}
+
+void cto_tokens_destroy(cto_tokens* t) { delete t; }
+
+// ---- chunk-file text codec ------------------------------------------------------------------
+
+static inline char* put_int(char* o, int v) {
+    if (v < 0) { *o++ = '-'; v = -v; }
+    char tmp[12];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *o++ = tmp[--n];
+    return o;
+}
+
+int64_t cto_format_tensor_row(const int16_t* row, char* out, int64_t cap) {
+    const int n = CTO_N_POS * CTO_N_CH;
+    if (cap < (int64_t)n * 7 + 1) return -1;                 // "-32768 " is 7 bytes
+    char* o = out;
+    for (int i = 0; i < n; ++i) {
+        if (i) *o++ = ' ';
+        o = put_int(o, row[i]);
+    }
+    *o = 0;
+    return (int64_t)(o - out);
+}
+
+int64_t cto_format_prob_fields(const float* probs, int n_pairs, char* out, int64_t cap) {
+    char* o = out;
+    for (int i = 0; i < n_pairs; ++i) {
+        if (cap - (o - out) < 64) return -1;
+        if (i) *o++ = '\t';
+        // "{:0.8f}".format(np.float32) formats the exact double value of the float (clairs/predict.py:121)
+        o += snprintf(o, 32, "%.8f", (double)probs[2 * i]);
+        *o++ = ' ';
+        o += snprintf(o, 32, "%.8f", (double)probs[2 * i + 1]);
+    }
+    *o = 0;
+    return (int64_t)(o - out);
+}
+
+int cto_parse_tensor_row(const char* text, int64_t len, int16_t* row) {
+    const int n = CTO_N_POS * CTO_N_CH;
+    const char* p = text;
+    const char* end = text + len;
+    for (int i = 0; i < n; ++i) {
+        while (p < end && (*p == ' ' || *p == '\t')) ++p;
+        if (p >= end) {
+            cto::set_error("parse_tensor_row: %d values found, %d expected", i, n);
+            return 2;
+        }
+        bool negv = false;
+        if (*p == '-') { negv = true; ++p; }
+        int v = 0;
+        bool any = false;
+        while (p < end && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); ++p; any = true; }
+        if (!any) {
+            cto::set_error("parse_tensor_row: non-integer token at value %d", i);
+            return 2;
+        }
+        row[i] = (int16_t)(negv ? -v : v);
+    }
+    return 0;
+}
+
+}  // extern "C"

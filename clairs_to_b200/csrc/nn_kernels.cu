@@ -1,0 +1,546 @@
+// fp32 CUDA-core kernels of the AFF / NEG forward passes (exact-parity path) and the fp64
+// posterior combine.  The dense contractions that dominate (GRU projections, fc1, 1x1 convs)
+// are additionally served by the tcgen05 kernels in gemm_tc.cu; this file holds everything
+// that is not a plain GEMM plus the CUDA-core GEMM used for odd shapes.
+//
+// Reference: clairs/model.py (M:line), clairs/predict.py (P:line), clairs/call_variants.py (CV:line).
+#include "nn_kernels.cuh"
+#include <float.h>
+
+namespace cto {
+
+// ------------------------------------------------------------------------------------------
+// activations
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) {           // nn.GELU() default (M:83)
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float selu(float x) {               // nn.SELU (M:226)
+    const float alpha = 1.6732632423543772848170429916717f;
+    const float scale = 1.0507009873554804934193349852946f;
+    return scale * (x > 0.0f ? x : alpha * expm1f(x));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_GELU) return gelu_erf(v);
+    if (act == ACT_SELU) return selu(v);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// int16 tensor -> fp32 network input with the depth rescale of P:179-197, 207
+// ------------------------------------------------------------------------------------------
+__global__ void rescale_kernel(const int16_t* __restrict__ x, const int32_t* __restrict__ depth, int64_t total,
+                               float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t cand = i / (N_POS * N_CH);
+    const int d = depth[cand];
+    const double v = (double)x[i];
+    // python: float(item) * (50.0 / depth) in double, then numpy float32 cast
+    out[i] = d > MIN_RESCALE_COV ? __double2float_rn(__dmul_rn(v, __ddiv_rn(50.0, (double)d))) : (float)v;
+}
+
+int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const int64_t total = n * N_POS * N_CH;
+    rescale_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, depth, total, out);
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// strand-count recovery (P:626-642): centre row, forward cols 0:4, reverse cols 9:13
+__global__ void strand_counts_kernel(const int16_t* __restrict__ x, int64_t n, int32_t* __restrict__ fwd,
+                                     int32_t* __restrict__ rev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 2) return;
+    const int64_t cand = i >> 1;
+    const int which = (int)(i & 1);
+    const int16_t* row = x + (cand * N_POS + CENTER) * N_CH + (which ? 9 : 0);
+    int v[4], sum = 0;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = row[k]; sum += v[k]; }
+    int32_t* dst = (which ? rev : fwd) + cand * 4;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = v[k] < 0 ? -sum : v[k];
+}
+
+int launch_strand_counts(const int16_t* x_aff, int64_t n, int32_t* fwd, int32_t* rev, cudaStream_t s) {
+    if (n <= 0) return 0;
+    strand_counts_kernel<<<ceil_div(n * 2, 128), 128, 0, s>>>(x_aff, n, fwd, rev);
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// CUDA-core GEMM: 128x64 tile, 8x4 micro-tile, 256 threads
+// ------------------------------------------------------------------------------------------
+constexpr int G_BM = 128, G_BN = 64, G_BK = 16;
+
+__device__ __forceinline__ void a_row_info(const AView& a, int64_t m, int k_total, const float*& base, int& k_lo,
+                                           int& k_hi) {
+    if (!a.conv) {
+        base = a.ptr + m * a.lda;
+        k_lo = 0;
+        k_hi = k_total;
+    } else {
+        const int64_t b = m / a.wout;
+        const int w = (int)(m - b * a.wout);
+        const int first = 2 * w - 1;                       // stride 2, pad 1 (M:195)
+        base = a.ptr + (b * a.win + first) * (int64_t)a.cin;
+        k_lo = first < 0 ? a.cin : 0;
+        const int avail = (a.win - first) * a.cin;
+        k_hi = avail < k_total ? avail : k_total;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gemm_nt_kernel(AView a, const float* __restrict__ w, const float* __restrict__ bias,
+               const float* residual, int64_t ldr, float* c, int64_t ldc, int64_t m_total,
+               int n_total, int k_total, int act, int vec_ok) {
+    __shared__ __align__(16) float As[G_BK][G_BM + 4];
+    __shared__ __align__(16) float Ws[G_BK][G_BN + 4];
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * G_BM;
+    const int n0 = blockIdx.y * G_BN;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    // loader roles
+    const int ar = tid >> 1, ak = (tid & 1) * 8;           // A: row ar, k offset ak..ak+7
+    const int wr = tid >> 2, wk = (tid & 3) * 4;           // W: row wr, k offset wk..wk+3
+    const float* a_base = nullptr;
+    int a_lo = 0, a_hi = 0;
+    const bool a_valid = (m0 + ar) < m_total;
+    if (a_valid) a_row_info(a, m0 + ar, k_total, a_base, a_lo, a_hi);
+    const bool w_valid = (n0 + wr) < n_total;
+    const float* w_base = w + (int64_t)(n0 + wr) * k_total;
+
+    float acc[8][4];
+    #pragma unroll
+    for (int i = 0; i < 8; ++i)
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < k_total; k0 += G_BK) {
+        float av[8], wv[4];
+        if (vec_ok && a_valid && k0 + ak + 8 <= k_total) {
+            const float4 v0 = *reinterpret_cast<const float4*>(a_base + k0 + ak);
+            const float4 v1 = *reinterpret_cast<const float4*>(a_base + k0 + ak + 4);
+            av[0] = v0.x; av[1] = v0.y; av[2] = v0.z; av[3] = v0.w;
+            av[4] = v1.x; av[5] = v1.y; av[6] = v1.z; av[7] = v1.w;
+        } else {
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = k0 + ak + i;
+                av[i] = (a_valid && k >= a_lo && k < a_hi) ? a_base[k] : 0.0f;
+            }
+        }
+        if (vec_ok && w_valid && k0 + wk + 4 <= k_total) {
+            const float4 v = *reinterpret_cast<const float4*>(w_base + k0 + wk);
+            wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
+        } else {
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + wk + i;
+                wv[i] = (w_valid && k < k_total) ? w_base[k] : 0.0f;
+            }
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) As[ak + i][ar] = av[i];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) Ws[wk + i][wr] = wv[i];
+        __syncthreads();
+        #pragma unroll
+        for (int kk = 0; kk < G_BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+            const float ar8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float br4[4] = {b0.x, b0.y, b0.z, b0.w};
+            #pragma unroll
+            for (int i = 0; i < 8; ++i)
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar8[i], br4[j], acc[i][j]);
+        }
+    }
+
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + ty * 8 + i;
+        if (m >= m_total) continue;
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= n_total) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.0f);
+            v = apply_act(v, act);
+            if (residual) v += residual[m * ldr + n];
+            c[m * ldc + n] = v;
+        }
+    }
+}
+
+int launch_gemm_nt(const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr, float* c,
+                   int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s) {
+    if (m <= 0 || n <= 0) return 0;
+    const int vec_ok = (!a.conv && (a.lda % 4 == 0) && (k % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0))
+                           ? 1 : 0;
+    dim3 grid(ceil_div(m, G_BM), ceil_div(n, G_BN));
+    gemm_nt_kernel<<<grid, 256, 0, s>>>(a, w, bias, residual, ldr, c, ldc, m, n, k, act, vec_ok);
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// channel LayerNorm (M:57-67): population std, eps added to the std; one warp per (b, w) row
+// ------------------------------------------------------------------------------------------
+__global__ void channel_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                  const float* __restrict__ b, float* __restrict__ y, int64_t rows, int c) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * c;
+    float v[4];
+    float sum = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ch = lane + 32 * i;
+        v[i] = ch < c ? xr[ch] : 0.0f;
+        sum += v[i];
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)c;
+    float sq = 0.0f;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ch = lane + 32 * i;
+        const float d = ch < c ? v[i] - mean : 0.0f;
+        sq += d * d;
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float denom = sqrtf(sq / (float)c) + 1e-5f;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ch = lane + 32 * i;
+        if (ch < c) y[row * c + ch] = (v[i] - mean) / denom * g[ch] + b[ch];
+    }
+}
+
+int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    CTO_REQUIRE(c <= 128, "channel_ln: C=%d > 128 unsupported", c);
+    channel_ln_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, g, b, y, rows, c);
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// depth-wise 3-tap conv along positions, pad 1 (M:93-97).  The eval-mode BatchNorm scale is
+// folded into the taps on the host; its shift is folded into the following 1x1 conv's bias.
+// ------------------------------------------------------------------------------------------
+__global__ void dwconv3_kernel(const float* __restrict__ y, const float* __restrict__ taps, float* __restrict__ out,
+                               int64_t total, int win, int wout, int stride, int c) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ch = (int)(i % c);
+    const int64_t bw = i / c;
+    const int w = (int)(bw % wout);
+    const int64_t b = bw / wout;
+    float acc = 0.0f;
+    #pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int src = w * stride - 1 + t;
+        if (src >= 0 && src < win) acc = fmaf(y[(b * win + src) * c + ch], taps[t * c + ch], acc);
+    }
+    out[i] = acc;
+}
+
+int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch, int win, int wout, int stride, int c,
+                   cudaStream_t s) {
+    const int64_t total = batch * wout * c;
+    if (total <= 0) return 0;
+    dwconv3_kernel<<<ceil_div(total, 256), 256, 0, s>>>(y, taps, out, total, win, wout, stride, c);
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// attention over <= 17 query and <= 9 key positions, dim_head 64 (M:120-132); one warp per
+// (candidate, head).  The 64^-0.5 scale is folded into the q projection on the host.
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_MAXW = 17, ATT_MAXKV = 9, ATT_D = 64, ATT_WARPS = 4;
+
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, int64_t n_bh, int w,
+                 int wkv, int heads) {
+    __shared__ float sq[ATT_WARPS][ATT_MAXW][ATT_D + 1];
+    __shared__ float sk[ATT_WARPS][ATT_MAXKV][ATT_D + 1];
+    __shared__ float sv[ATT_WARPS][ATT_MAXKV][ATT_D + 1];
+    __shared__ float sp[ATT_WARPS][ATT_MAXW][ATT_MAXKV + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t bh = (int64_t)blockIdx.x * ATT_WARPS + wib;
+    if (bh >= n_bh) return;
+    const int64_t b = bh / heads;
+    const int h = (int)(bh - b * heads);
+    const int inner = heads * ATT_D;
+    for (int i = 0; i < w; ++i) {
+        const float* src = q + (b * w + i) * inner + h * ATT_D;
+        sq[wib][i][lane] = src[lane];
+        sq[wib][i][lane + 32] = src[lane + 32];
+    }
+    for (int j = 0; j < wkv; ++j) {
+        const float* src = kv + (b * wkv + j) * (2 * inner) + h * ATT_D;
+        sk[wib][j][lane] = src[lane];
+        sk[wib][j][lane + 32] = src[lane + 32];
+        sv[wib][j][lane] = src[inner + lane];
+        sv[wib][j][lane + 32] = src[inner + lane + 32];
+    }
+    __syncwarp();
+    for (int p = lane; p < w * wkv; p += 32) {
+        const int i = p / wkv, j = p - i * wkv;
+        float acc = 0.0f;
+        #pragma unroll 16
+        for (int d = 0; d < ATT_D; ++d) acc = fmaf(sq[wib][i][d], sk[wib][j][d], acc);
+        sp[wib][i][j] = acc;
+    }
+    __syncwarp();
+    if (lane < w) {
+        float mx = -FLT_MAX;
+        for (int j = 0; j < wkv; ++j) mx = fmaxf(mx, sp[wib][lane][j]);
+        float sum = 0.0f;
+        for (int j = 0; j < wkv; ++j) {
+            const float e = expf(sp[wib][lane][j] - mx);
+            sp[wib][lane][j] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / sum;
+        for (int j = 0; j < wkv; ++j) sp[wib][lane][j] *= inv;
+    }
+    __syncwarp();
+    for (int i = 0; i < w; ++i) {
+        float o0 = 0.0f, o1 = 0.0f;
+        for (int j = 0; j < wkv; ++j) {
+            const float pij = sp[wib][i][j];
+            o0 = fmaf(pij, sv[wib][j][lane], o0);
+            o1 = fmaf(pij, sv[wib][j][lane + 32], o1);
+        }
+        float* dst = out + (b * w + i) * inner + h * ATT_D;
+        dst[lane] = o0;
+        dst[lane + 32] = o1;
+    }
+}
+
+int launch_attention(const float* q, const float* kv, float* out, int64_t batch, int w, int wkv, int heads,
+                     cudaStream_t s) {
+    const int64_t n_bh = batch * heads;
+    if (n_bh <= 0) return 0;
+    CTO_REQUIRE(w <= ATT_MAXW && wkv <= ATT_MAXKV, "attention: W=%d Wkv=%d exceed %d/%d", w, wkv, ATT_MAXW, ATT_MAXKV);
+    attention_kernel<<<ceil_div(n_bh, ATT_WARPS), ATT_WARPS * 32, 0, s>>>(q, kv, out, n_bh, w, wkv, heads);
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// GRU recurrence (torch.nn.GRU semantics, gate order r|z|n; M:412-417, 442-443).
+//   xproj [B, T, 2*3H]  = W_ih x + b_ih (+ b_hh for the r,z gates), direction-major columns
+//   whh_t [2][H][3H]    = W_hh transposed (k-major) per direction
+//   bhn   [2][H]        = b_hn (stays inside r * (.))
+//   out   [B, T, 2H]    = h_t, forward in columns 0..H-1, backward in H..2H-1
+// One CTA = BM candidates x one direction for all 33 steps; h lives in shared memory (k-major),
+// each thread owns one hidden unit for TM candidates and keeps its three gate accumulators in
+// registers.  blockIdx.y = direction.
+// ------------------------------------------------------------------------------------------
+template <int H, int BM, int TM>
+__global__ void __launch_bounds__(H * (BM / TM), 1)
+gru_recurrent_kernel(const float* __restrict__ xproj, const float* __restrict__ whh_t,
+                     const float* __restrict__ bhn, float* __restrict__ out, int64_t batch) {
+    static_assert(TM == 8, "micro-tile is two float4");
+    __shared__ __align__(16) float hT[H][BM + 4];      // +4: spreads the per-unit row stores over banks
+    const int tid = threadIdx.x;
+    const int j = tid % H;
+    const int mg = tid / H;
+    const int dir = blockIdx.y;
+    const int64_t b0 = (int64_t)blockIdx.x * BM + mg * TM;
+    const float* wt = whh_t + (int64_t)dir * H * 3 * H;
+    const float b_hn = bhn[dir * H + j];
+    const int64_t xstride = (int64_t)N_POS * 6 * H;        // per candidate
+    const int64_t ostride = (int64_t)N_POS * 2 * H;
+
+    float hreg[TM];                                    // this thread's h_{t-1}[m, j]
+    #pragma unroll
+    for (int i = 0; i < TM; ++i) { hreg[i] = 0.0f; hT[j][mg * TM + i] = 0.0f; }
+    __syncthreads();
+
+    for (int step = 0; step < N_POS; ++step) {
+        const int t = dir ? (N_POS - 1 - step) : step;
+        float xr[TM], xz[TM], xn[TM];
+        #pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int64_t b = b0 + i;
+            if (b >= batch) b = batch - 1;
+            const float* xp = xproj + b * xstride + (int64_t)t * 6 * H + dir * 3 * H + j;
+            xr[i] = xp[0];
+            xz[i] = xp[H];
+            xn[i] = xp[2 * H];
+        }
+        float ar[TM], az[TM], an[TM];
+        #pragma unroll
+        for (int i = 0; i < TM; ++i) { ar[i] = 0.0f; az[i] = 0.0f; an[i] = 0.0f; }
+        #pragma unroll 4
+        for (int k = 0; k < H; ++k) {
+            const float wr = wt[k * 3 * H + j];
+            const float wz = wt[k * 3 * H + H + j];
+            const float wn = wt[k * 3 * H + 2 * H + j];
+            const float4 h0 = *reinterpret_cast<const float4*>(&hT[k][mg * TM]);
+            const float4 h1 = *reinterpret_cast<const float4*>(&hT[k][mg * TM + 4]);
+            const float hv[TM] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            #pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                ar[i] = fmaf(hv[i], wr, ar[i]);
+                az[i] = fmaf(hv[i], wz, az[i]);
+                an[i] = fmaf(hv[i], wn, an[i]);
+            }
+        }
+        #pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const float r = 1.0f / (1.0f + expf(-(xr[i] + ar[i])));
+            const float z = 1.0f / (1.0f + expf(-(xz[i] + az[i])));
+            const float n = tanhf(xn[i] + r * (an[i] + b_hn));
+            hreg[i] = (1.0f - z) * n + z * hreg[i];
+        }
+        __syncthreads();                               // every thread is done reading h_{t-1}
+        *reinterpret_cast<float4*>(&hT[j][mg * TM]) = make_float4(hreg[0], hreg[1], hreg[2], hreg[3]);
+        *reinterpret_cast<float4*>(&hT[j][mg * TM + 4]) = make_float4(hreg[4], hreg[5], hreg[6], hreg[7]);
+        #pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int64_t b = b0 + i;
+            if (b < batch) out[b * ostride + (int64_t)t * 2 * H + dir * H + j] = hreg[i];
+        }
+        __syncthreads();
+    }
+}
+
+int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bhn, float* out, int64_t batch,
+                         int hidden, cudaStream_t s) {
+    if (batch <= 0) return 0;
+    constexpr int BM = 32, TM = 8;
+    dim3 grid(ceil_div(batch, BM), 2);
+    if (hidden == 128) {
+        gru_recurrent_kernel<128, BM, TM><<<grid, 128 * (BM / TM), 0, s>>>(xproj, whh_t, bhn, out, batch);
+    } else if (hidden == 192) {
+        gru_recurrent_kernel<192, BM, TM><<<grid, 192 * (BM / TM), 0, s>>>(xproj, whh_t, bhn, out, batch);
+    } else {
+        CTO_REQUIRE(false, "gru_recurrent: hidden size %d not built (128 and 192 are, M:403-404)", hidden);
+    }
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-head fc3 (128 -> 2) + SELU (M:250-253): one warp per candidate
+// ------------------------------------------------------------------------------------------
+__global__ void head_fc3_kernel(const float* __restrict__ y, const float* __restrict__ w3, const float* __restrict__ b3,
+                                float* __restrict__ logits, int64_t batch, int n_heads) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= batch) return;
+    for (int h = 0; h < n_heads; ++h) {
+        const float4 yv = *reinterpret_cast<const float4*>(y + (b * n_heads + h) * 128 + lane * 4);
+        #pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            const float4 wv = *reinterpret_cast<const float4*>(w3 + (h * 2 + o) * 128 + lane * 4);
+            float acc = yv.x * wv.x;
+            acc = fmaf(yv.y, wv.y, acc);
+            acc = fmaf(yv.z, wv.z, acc);
+            acc = fmaf(yv.w, wv.w, acc);
+            #pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+            if (lane == 0) logits[(b * n_heads + h) * 2 + o] = selu(acc + b3[h * 2 + o]);
+        }
+    }
+}
+
+int launch_head_fc3(const float* y, const float* w3, const float* b3, float* logits, int64_t batch, int n_heads,
+                    cudaStream_t s) {
+    if (batch <= 0) return 0;
+    head_fc3_kernel<<<ceil_div(batch, 8), 256, 0, s>>>(y, w3, b3, logits, batch, n_heads);
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax (P:574, 659-684) + likelihood-matrix Bayes combine (CV:154-224 / 226-304) in fp64.
+// tables: per head 100 matrix entries (row = AFF bin), 11 AFF edges, 11 NEG edges.
+// The reference re-parses probabilities printed with 8 decimals (P:121-132, CV:803-829); the
+// round trip is reproduced exactly: float32 -> double, x 1e8 (exact), rint, / 1e8.
+// call[n]: bits 0-7 argmax head, bit 8 = some bin index was clamped (reference would raise,
+// SURVEY.md 9.12).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int digitize11(double x, const double* edges) {   // np.digitize(x, edges) - 1
+    int c = 0;
+    #pragma unroll
+    for (int i = 0; i < 11; ++i) c += (edges[i] <= x) ? 1 : 0;
+    return c - 1;
+}
+
+__global__ void softmax_posterior_kernel(const float* __restrict__ la, const float* __restrict__ ln, int64_t n,
+                                         int n_heads, const double* __restrict__ tables, float* __restrict__ probs,
+                                         double* __restrict__ post, int32_t* __restrict__ call) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double best = -1.0;
+    int best_h = 0, clamped = 0;
+    for (int h = 0; h < n_heads; ++h) {
+        float pa[2], pn[2];
+        {
+            const float x0 = la[(i * n_heads + h) * 2], x1 = la[(i * n_heads + h) * 2 + 1];
+            const float mx = fmaxf(x0, x1);
+            const float e0 = expf(x0 - mx), e1 = expf(x1 - mx);
+            const float s = e0 + e1;
+            pa[0] = e0 / s; pa[1] = e1 / s;
+        }
+        {
+            const float x0 = ln[(i * n_heads + h) * 2], x1 = ln[(i * n_heads + h) * 2 + 1];
+            const float mx = fmaxf(x0, x1);
+            const float e0 = expf(x0 - mx), e1 = expf(x1 - mx);
+            const float s = e0 + e1;
+            pn[0] = e0 / s; pn[1] = e1 / s;
+        }
+        if (probs) {
+            float* pr = probs + i * (4 * n_heads);
+            pr[h * 2] = pa[0]; pr[h * 2 + 1] = pa[1];
+            pr[(n_heads + h) * 2] = pn[0]; pr[(n_heads + h) * 2 + 1] = pn[1];
+        }
+        if (!tables) continue;
+        const double p = __ddiv_rn(rint(__dmul_rn((double)pa[1], 1e8)), 1e8);
+        const double q = __ddiv_rn(rint(__dmul_rn((double)pn[1], 1e8)), 1e8);
+        const double* t = tables + h * 122;
+        const double one_minus_q = __dsub_rn(1.0, q);
+        int bi = digitize11(p, t + 100);
+        int bj = digitize11(one_minus_q, t + 111);
+        if (bi < 0 || bi > 9 || bj < 0 || bj > 9) clamped = 1;
+        bi = min(max(bi, 0), 9);
+        bj = min(max(bj, 0), 9);
+        const double wgt = __dadd_rn(t[bi * 10 + bj], DBL_EPSILON);
+        const double num = __dmul_rn(__dmul_rn(p, one_minus_q), wgt);
+        const double alt = __dmul_rn(__dmul_rn(__dsub_rn(1.0, p), q), __dsub_rn(1.0, wgt));
+        const double ps = __ddiv_rn(num, __dadd_rn(num, alt));
+        if (post) post[i * n_heads + h] = ps;
+        if (ps > best) { best = ps; best_h = h; }          // first maximum wins like np.argmax
+    }
+    if (call && tables) call[i] = best_h | (clamped << 8);
+}
+
+int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,
+                             const double* tables, float* probs, double* post, int32_t* call, cudaStream_t s) {
+    if (n <= 0) return 0;
+    softmax_posterior_kernel<<<ceil_div(n, 128), 128, 0, s>>>(logits_aff, logits_neg, n, n_heads, tables, probs, post,
+                                                              call);
+    CTO_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cto

@@ -1,0 +1,40 @@
+// Kernel launchers for the AFF (CvT) / NEG (BiGRU) forward passes and the posterior combine.
+// All activations are channels-last fp32: [candidate, position, channel].
+#pragma once
+#include "common.cuh"
+
+namespace cto {
+
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SELU = 2 };
+
+// A-operand addressing for gemm_nt: plain row-major rows, or the rows of a 3-tap / stride-2 /
+// pad-1 convolution over a channels-last [B, Win, Cin] tensor (clairs/model.py:195 on H=1 maps).
+struct AView {
+    const float* ptr;
+    int64_t lda;      // plain: row stride
+    int conv;         // 0 plain, 1 conv rows
+    int win, wout, cin;
+};
+
+static inline AView plain_a(const float* p, int64_t lda) { return AView{p, lda, 0, 0, 0, 0}; }
+static inline AView conv_a(const float* p, int win, int wout, int cin) { return AView{p, 0, 1, win, wout, cin}; }
+
+// C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual)
+int launch_gemm_nt(const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr,
+                   float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s);
+
+int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, cudaStream_t s);
+int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s);
+int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch, int win, int wout, int stride,
+                   int c, cudaStream_t s);
+int launch_attention(const float* q, const float* kv, float* out, int64_t batch, int w, int wkv, int heads,
+                     cudaStream_t s);
+int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bhn, float* out, int64_t batch,
+                         int hidden, cudaStream_t s);
+int launch_head_fc3(const float* y, const float* w3, const float* b3, float* logits, int64_t batch, int n_heads,
+                    cudaStream_t s);
+int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,
+                             const double* tables, float* probs, double* post, int32_t* call, cudaStream_t s);
+int launch_strand_counts(const int16_t* x_aff, int64_t n, int32_t* fwd, int32_t* rev, cudaStream_t s);
+
+}  // namespace cto

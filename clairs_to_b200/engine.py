@@ -1,0 +1,203 @@
+"""Python face of the CUDA engine: torch tensors are containers for device memory, all arithmetic
+happens in ``libcto_b200.so`` (include/clairs_to_b200.h).  No CPU fallback.
+
+The method names mirror the reference call sites they replace:
+  ``encode``      decode_pileup_bases + window assembly (src/create_tensor_pileup_calling.py:95-229, 537-570)
+  ``forward_aff`` model_aff(x)   (clairs/predict.py:646, clairs/model.py:231)
+  ``forward_neg`` model_neg(x)   (clairs/predict.py:648, clairs/model.py:440)
+  ``predict``     one pass of the predict() mini-batch loop (clairs/predict.py:610-699) + the Bayes
+                  combine of output_vcf_from_probability (clairs/call_variants.py:154-304)
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .pileup_format import N_CH, N_POS, PileupStream
+from .weights import export_aff, export_neg, likelihood_tables, state_dict_from_checkpoint
+
+
+def low_bq_cut_for(platform: str) -> int:
+    """The literal of src/create_tensor_pileup_calling.py:149."""
+    return 30 if platform == 'ont' else 10
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        assert t.is_contiguous()
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        assert t.flags['C_CONTIGUOUS']
+        return C.c_void_p(t.ctypes.data)
+    raise TypeError(type(t))
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_TORCH_VIEW = {np.dtype(np.uint32): np.int32}
+
+
+def stream_to_device(stream: PileupStream, device) -> PileupStream:
+    """numpy PileupStream -> the same arrays in HBM (uint32 carried as int32 bits)."""
+    out = []
+    for a in stream.arrays():
+        a = np.ascontiguousarray(a)
+        if a.dtype in _TORCH_VIEW:
+            a = a.view(_TORCH_VIEW[a.dtype])
+        out.append(torch.from_numpy(a).to(device, non_blocking=True))
+    return PileupStream(*out)
+
+
+class Engine:
+    def __init__(self, aff_state_dict, neg_state_dict, max_batch=8192, device=None, likelihood=None):
+        if not torch.cuda.is_available():
+            raise _lib.CtoError("clairs_to_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        aff_blob, aff_cfg = export_aff(aff_state_dict)
+        neg_blob, neg_cfg = export_neg(neg_state_dict)
+        handle = C.c_void_p()
+        _lib.check(self.lib.cto_engine_create(_ptr(aff_blob), aff_blob.size, _ptr(aff_cfg), aff_cfg.size,
+                                              _ptr(neg_blob), neg_blob.size, _ptr(neg_cfg), neg_cfg.size,
+                                              int(max_batch), C.byref(handle)), "cto_engine_create")
+        self.handle = handle
+        self.n_heads = int(self.lib.cto_engine_heads(handle))
+        self.max_batch = int(max_batch)
+        self.has_likelihood = False
+        if likelihood is not None:
+            self.set_likelihood(likelihood)
+
+    @classmethod
+    def from_checkpoints(cls, chkpnt_fn_acgt, chkpnt_fn_nacgt, **kw):
+        return cls(state_dict_from_checkpoint(chkpnt_fn_acgt, 'model_acgt'),
+                   state_dict_from_checkpoint(chkpnt_fn_nacgt, 'model_nacgt'), **kw)
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.cto_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_likelihood(self, path_or_array):
+        tables = np.ascontiguousarray(likelihood_tables(path_or_array, self.n_heads))
+        _lib.check(self.lib.cto_engine_set_likelihood(self.handle, _ptr(tables), self.n_heads), "set_likelihood")
+        self.has_likelihood = True
+
+    # ---- encoder ----------------------------------------------------------------------------
+    def encode(self, s: PileupStream, low_bq_cut: int):
+        """Device PileupStream -> (int16 [N,33,34], int32 depth [N])."""
+        n = s.win_pos.numel() // N_POS
+        tensor = torch.empty((n, N_POS, N_CH), dtype=torch.int16, device=self.device)
+        depth = torch.empty((n,), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.cto_encode_pileup(_ptr(s.code), _ptr(s.bq), _ptr(s.mq), _ptr(s.pos_off), _ptr(s.ref_code),
+                                              _ptr(s.ind_off), _ptr(s.ind_entry), _ptr(s.win_pos), n, int(low_bq_cut),
+                                              _ptr(tensor), _ptr(depth), _stream_ptr()), "cto_encode_pileup")
+        return tensor, depth
+
+    # ---- networks ---------------------------------------------------------------------------
+    def rescale(self, x_i16, depth):
+        out = torch.empty(x_i16.shape, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cto_rescale(_ptr(x_i16), _ptr(depth), x_i16.shape[0], _ptr(out), _stream_ptr()), "cto_rescale")
+        return out
+
+    def _forward(self, fn, x):
+        x = x.to(self.device, torch.float32).contiguous()
+        assert x.shape[1:] == (N_POS, N_CH), x.shape
+        logits = torch.empty((x.shape[0], self.n_heads, 2), dtype=torch.float32, device=self.device)
+        _lib.check(fn(self.handle, _ptr(x), x.shape[0], _ptr(logits), _stream_ptr()), "forward")
+        return logits
+
+    def forward_aff(self, x):
+        return self._forward(self.lib.cto_forward_aff, x)
+
+    def forward_neg(self, x):
+        return self._forward(self.lib.cto_forward_neg, x)
+
+    def predict(self, x_aff, depth_aff, x_neg=None, depth_neg=None, posterior=None):
+        """int16 tensors [N,33,34] (+ centre depths) -> dict of device tensors."""
+        if x_neg is None:
+            x_neg, depth_neg = x_aff, depth_aff
+        n = x_aff.shape[0]
+        posterior = self.has_likelihood if posterior is None else posterior
+        dev, h = self.device, self.n_heads
+        out = dict(
+            logits_aff=torch.empty((n, h, 2), dtype=torch.float32, device=dev),
+            logits_neg=torch.empty((n, h, 2), dtype=torch.float32, device=dev),
+            probs=torch.empty((n, 2 * h, 2), dtype=torch.float32, device=dev),
+            fwd=torch.empty((n, 4), dtype=torch.int32, device=dev),
+            rev=torch.empty((n, 4), dtype=torch.int32, device=dev),
+            post=torch.empty((n, h), dtype=torch.float64, device=dev) if posterior else None,
+            call=torch.empty((n,), dtype=torch.int32, device=dev) if posterior else None,
+        )
+        _lib.check(self.lib.cto_predict(self.handle, _ptr(x_aff), _ptr(depth_aff), _ptr(x_neg), _ptr(depth_neg), n,
+                                        _ptr(out['logits_aff']), _ptr(out['logits_neg']), _ptr(out['probs']),
+                                        _ptr(out['post']), _ptr(out['call']), _ptr(out['fwd']), _ptr(out['rev']),
+                                        _stream_ptr()), "cto_predict")
+        return out
+
+    def run_sites(self, aff: PileupStream, neg: PileupStream | None, low_bq_cut: int, posterior=None):
+        """Device-resident hot path: encode both streams, then predict."""
+        xa, da = self.encode(aff, low_bq_cut)
+        if neg is None:
+            xn, dn = xa, da
+        else:
+            xn, dn = self.encode(neg, low_bq_cut)
+        out = self.predict(xa, da, xn, dn, posterior=posterior)
+        out.update(tensor_aff=xa, tensor_neg=xn, depth_aff=da, depth_neg=dn)
+        return out
+
+    # ---- end to end from host memory ----------------------------------------------------------
+    @staticmethod
+    def _host_struct(s: PileupStream):
+        hs = _lib.HostStream()
+        keep = []
+        for name in PileupStream.__slots__:
+            a = getattr(s, name)
+            if isinstance(a, torch.Tensor):
+                ptr = a.data_ptr()
+            else:
+                a = np.ascontiguousarray(a)
+                ptr = a.ctypes.data
+            keep.append(a)
+            setattr(hs, name, ptr)
+        hs.n_reads = len(s.code)
+        hs.n_rows = len(s.ref_code)
+        hs.n_ind = len(s.ind_entry)
+        return hs, keep
+
+    def run_sites_host(self, aff: PileupStream, neg: PileupStream | None, low_bq_cut: int, out=None,
+                       want_tensors=False):
+        """Host arrays in -> host results out through ``cto_run_sites_host`` (H2D + D2H inside).
+        ``out`` may carry preallocated (pinned) host tensors 'probs', 'post', 'call'."""
+        n = len(aff.win_pos) // N_POS
+        h = self.n_heads
+        out = dict(out or {})
+        if 'probs' not in out:
+            out['probs'] = torch.empty((n, 2 * h, 2), dtype=torch.float32)
+        if self.has_likelihood:
+            out.setdefault('post', torch.empty((n, h), dtype=torch.float64))
+            out.setdefault('call', torch.empty((n,), dtype=torch.int32))
+        if want_tensors:
+            out['tensor_aff'] = torch.empty((n, N_POS, N_CH), dtype=torch.int16)
+            out['tensor_neg'] = torch.empty((n, N_POS, N_CH), dtype=torch.int16)
+        ha, keep_a = self._host_struct(aff)
+        hn, keep_n = (None, None) if neg is None else self._host_struct(neg)
+        _lib.check(self.lib.cto_run_sites_host(self.handle, C.byref(ha), C.byref(hn) if hn is not None else None, n,
+                                               int(low_bq_cut), _ptr(out['probs']), _ptr(out.get('post')),
+                                               _ptr(out.get('call')), _ptr(out.get('tensor_aff')),
+                                               _ptr(out.get('tensor_neg')), _stream_ptr()), "cto_run_sites_host")
+        return out

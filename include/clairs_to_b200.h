@@ -1,0 +1,158 @@
+/*
+ * clairs_to_b200.h -- C ABI of the B200-native drop-in for the ClairS-TO per-candidate hot path
+ * (pileup tensor encoder -> AFF/NEG forward -> posterior combine).
+ *
+ * The reference (HKU-BAL/ClairS-TO v0.4.4) has NO FFI for this path: it is Python calling
+ * PyTorch/NumPy.  Each entry point below therefore cites the reference
+ * Python function it replaces; INTEGRATION.md shows the ctypes binding a maintainer would add
+ * inside src/create_tensor_pileup_calling.py, clairs/predict.py and clairs/call_variants.py.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; "dev" pointers are CUDA device memory on the
+ *     current device, "host" pointers are ordinary (preferably pinned) host memory;
+ *   - the caller owns every input/output buffer; the library owns weights + workspace only;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     stream-ordered and return without synchronising unless stated;
+ *   - return 0 on success, non-zero on error with a message in cto_last_error() (thread-local).
+ *     The Python shims turn that into sys.exit(msg) like the reference's own error style
+ *     (e.g. src/create_tensor_pileup_calling.py:424).  There is no CPU fallback.
+ */
+#ifndef CLAIRS_TO_B200_H
+#define CLAIRS_TO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTO_N_POS 33       /* shared/param.py:60 */
+#define CTO_N_CH 34        /* shared/param.py:56 */
+#define CTO_ABI_VERSION 1
+
+typedef struct cto_engine cto_engine;
+
+int cto_abi_version(void);
+const char* cto_last_error(void);
+
+/* Checks that the current CUDA device is sm_100 (B200).  Returns 0 and writes the SM count. */
+int cto_device_check(int* sm_count);
+
+/*
+ * Pileup tensor encoder.  Replaces decode_pileup_bases() + the window assembly of create_tensor()
+ * (src/create_tensor_pileup_calling.py:146-229, 461, 513-516, 537-543).  Input layout: see
+ * clairs_to_b200/pileup_format.py.  Output tensor int16 [n_candidates, 33, 34]; depth_dev
+ * (nullable) receives the centre-row depth that leads the reference's alt_info string (ibid. 208).
+ * low_bq_cut is the literal of ibid. 149: 30 if platform == 'ont' else 10.
+ */
+int cto_encode_pileup(const uint8_t* code_dev, const uint8_t* bq_dev, const uint8_t* mq_dev,
+                      const int32_t* pos_off_dev, const uint8_t* ref_code_dev,
+                      const int32_t* ind_off_dev, const uint32_t* ind_entry_dev,
+                      const int32_t* win_pos_dev, int64_t n_candidates, int low_bq_cut,
+                      int16_t* tensor_dev, int32_t* depth_dev, void* stream);
+
+/*
+ * Engine = AFF + NEG weights (flat fp32 blobs in HOST memory, produced by
+ * clairs_to_b200/weights.py from the reference checkpoints that clairs/predict.py:512-568 loads)
+ * plus workspace for `max_batch` candidates per internal chunk.
+ *   aff_cfg = [n_heads, n_stages, (C, heads, depth) per stage]   neg_cfg = [n_heads, 34, H1, H2]
+ */
+int cto_engine_create(const float* aff_blob_host, int64_t aff_len, const int32_t* aff_cfg, int aff_cfg_len,
+                      const float* neg_blob_host, int64_t neg_len, const int32_t* neg_cfg, int neg_cfg_len,
+                      int64_t max_batch, cto_engine** out);
+void cto_engine_destroy(cto_engine* e);
+int cto_engine_heads(const cto_engine* e);   /* 4 (SNV) or 6 (indel) */
+
+/*
+ * Likelihood tables for the posterior (clairs/call_variants.py:655-796): per head 100 matrix
+ * entries (row = AFF bin), then 11 AFF bin edges, then 11 NEG bin edges, as doubles in host memory.
+ */
+int cto_engine_set_likelihood(cto_engine* e, const double* tables_host, int n_heads);
+
+/* int16 tensor -> fp32 network input with the >50x depth rescale of clairs/predict.py:179-197. */
+int cto_rescale(const int16_t* x_dev, const int32_t* depth_dev, int64_t n, float* out_dev, void* stream);
+
+/*
+ * model(x) of clairs/model.py:231 (CvT / CvT_Indel) and :440 (BiGRU_NACGT / _Indel):
+ * x fp32 [n, 33, 34] -> post-SELU "logits" fp32 [n, n_heads, 2].  Any n (chunked internally).
+ */
+int cto_forward_aff(cto_engine* e, const float* x_dev, int64_t n, float* logits_dev, void* stream);
+int cto_forward_neg(cto_engine* e, const float* x_dev, int64_t n, float* logits_dev, void* stream);
+
+/*
+ * Softmax(dim=1) of clairs/predict.py:574, 659-684 and, when the engine has likelihood tables and
+ * post_dev/call_dev are non-NULL, the Bayes combine + argmax of clairs/call_variants.py:154-224
+ * (SNV) / 226-304 (indel) in fp64, on probabilities rounded through the reference's 8-decimal
+ * text round trip.  probs_dev fp32 [n, 2*n_heads, 2] in predict-file order (a c g t [i d] na ...);
+ * post_dev double [n, n_heads]; call_dev int32 [n]: bits 0-7 argmax, bit 8 = bin index clamped.
+ */
+int cto_softmax_posterior(cto_engine* e, const float* logits_aff_dev, const float* logits_neg_dev, int64_t n,
+                          float* probs_dev, double* post_dev, int32_t* call_dev, void* stream);
+
+/* Strand-count recovery of clairs/predict.py:626-642 from the un-rescaled AFF tensor: int32 [n,4] x2. */
+int cto_strand_counts(const int16_t* x_aff_dev, int64_t n, int32_t* fwd_dev, int32_t* rev_dev, void* stream);
+
+/*
+ * The per-mini-batch body of predict() (clairs/predict.py:610-699) for n candidates at once:
+ * rescale both tensors, AFF and NEG forward (concurrently), softmax, strand counts, posterior.
+ * Nullable outputs are skipped.  x_neg_dev == x_aff_dev is allowed (Illumina symlink case,
+ * run_clairs_to:1248-1252).
+ */
+int cto_predict(cto_engine* e, const int16_t* x_aff_dev, const int32_t* depth_aff_dev, const int16_t* x_neg_dev,
+                const int32_t* depth_neg_dev, int64_t n, float* logits_aff_dev, float* logits_neg_dev,
+                float* probs_dev, double* post_dev, int32_t* call_dev, int32_t* fwd_dev, int32_t* rev_dev,
+                void* stream);
+
+/*
+ * One stream of per-site read arrays in HOST memory (see clairs_to_b200/pileup_format.py).
+ */
+typedef struct cto_host_stream {
+    const uint8_t* code;
+    const uint8_t* bq;
+    const uint8_t* mq;
+    const int32_t* pos_off;
+    const uint8_t* ref_code;
+    const int32_t* ind_off;
+    const uint32_t* ind_entry;
+    const int32_t* win_pos;
+    int64_t n_reads, n_rows, n_ind;
+} cto_host_stream;
+
+/*
+ * End-to-end host call: host read arrays in -> host probabilities / posteriors out.  Copies both
+ * streams to the device, encodes, predicts and copies results back; synchronises before returning.
+ * neg == NULL reuses the AFF stream.  Outputs (host, nullable): probs fp32 [n, 2H, 2],
+ * post double [n, H], call int32 [n], tensor_aff / tensor_neg int16 [n, 33, 34].
+ */
+int cto_run_sites_host(cto_engine* e, const cto_host_stream* aff, const cto_host_stream* neg, int64_t n_candidates,
+                       int low_bq_cut, float* probs_host, double* post_host, int32_t* call_host,
+                       int16_t* tensor_aff_host, int16_t* tensor_neg_host, void* stream);
+
+/*
+ * Host tokenizer for `samtools mpileup` text (src/create_tensor_pileup_calling.py:120-144, 472-497):
+ * parses rows "chr pos ref depth bases BQ MQ" into the read arrays above, and builds the alt_info
+ * strings (ibid. 158-209) of candidate rows.  Two-phase: create -> query sizes -> export -> destroy.
+ */
+typedef struct cto_tokens cto_tokens;
+int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq, int64_t ref_len,
+                         int64_t ref_start, const int64_t* candidate_pos, int64_t n_candidates,
+                         int max_indel_length, cto_tokens** out);
+int cto_tokens_sizes(const cto_tokens* t, int64_t* n_reads, int64_t* n_rows, int64_t* n_ind, int64_t* alt_info_bytes);
+int cto_tokens_export(const cto_tokens* t, uint8_t* code, uint8_t* bq, uint8_t* mq, int32_t* pos_off,
+                      uint8_t* ref_code, int32_t* ind_off, uint32_t* ind_entry, int64_t* row_pos,
+                      char* alt_info, int64_t* alt_info_off);
+void cto_tokens_destroy(cto_tokens* t);
+
+/*
+ * Text codec for the chunk files: the 1122-int tensor field of a tensor_can row
+ * (src/create_tensor_pileup_calling.py:551) and the "%0.8f" probability fields of a predict row
+ * (clairs/predict.py:121-132).  Return bytes written (excluding NUL), or -1 if `cap` is too small.
+ */
+int64_t cto_format_tensor_row(const int16_t* tensor_row, char* out, int64_t cap);
+int64_t cto_format_prob_fields(const float* probs, int n_pairs, char* out, int64_t cap);
+int cto_parse_tensor_row(const char* text, int64_t len, int16_t* tensor_row);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLAIRS_TO_B200_H */

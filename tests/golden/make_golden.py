@@ -1,0 +1,208 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference (imported read-only from
+/root/reference) on seeded synthetic inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests or golden vectors, so these files are what pins the
+oracle (and through it the CUDA path) to the reference's behaviour.  Nothing here is needed at
+test time except the written fixtures.
+"""
+
+import argparse
+import gzip
+import json
+import os
+import subprocess
+import sys
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from clairs_to_b200 import synth  # noqa: E402
+from oracle import nn_oracle  # noqa: E402
+
+
+HAND_ROWS = [
+    # (bases, BQ, MQ, ref_base, candidate?, chunk_ref_seq)
+    ("ACGTacgtNn*#", "IIIIIIIIIIII", "]]]]]]]]]]]]", "A", True, "ACGTACGTAC"),
+    ("A+2GTA+2GTa+2gtC-1NC-1Nc-1nG", "I" * 7, "]" * 7, "G", True, "GATTACA"),
+    ("A+2GT-1NA", "II", "]]", "A", True, "AC"),                     # second indel overwrites the first
+    ("^]A$C<>T", "IIIII", "]]5]]", "C", True, "CCCC"),             # '<' '>' shift the qualities (quirk 6)
+    ("A+70" + "G" * 70 + "A+60" + "C" * 60 + "T-60" + "N" * 60 + "T-59" + "N" * 59, "IIII", "]]]]", "T", True, "T" * 60),
+    ("*+1A#+1a*-2NN#-2nnN+1T", "I" * 5, "]" * 5, "A", True, "ACG"),
+    ("AAAAaaaaCCcc", "+5+5+5+5+5+5", "]!]!]!]!]!]!", "A", True, "A"),   # low MQ / low BQ mix
+    ("TTTT", "IIII", "]]", "T", False, "T"),                         # MQ string shorter than reads
+    ("", "", "", "A", True, "A"),
+    ("*", "*", "*", "C", True, "C"),                                 # samtools' empty-column row
+    ("gggGGGg+3acgG+3ACG", "5555555I", "]]]]]]]]", "G", True, "GTT"),
+]
+
+
+def encoder_golden():
+    from src.create_tensor_pileup_calling import decode_pileup_bases
+    args = Namespace(max_indel_length=60)
+    cases = []
+
+    def run(bases, bq, mq, ref, is_cand, chunk_ref, platform):
+        cand = {100: 'snv'} if is_cand else {}
+        vec, _, _, _, _, alt_info = decode_pileup_bases(
+            args=args, pos=100, pileup_bases=bases, reference_base=ref,
+            minimum_snp_af_for_candidate=0.05, minimum_indel_af_for_candidate=0.05,
+            has_pileup_candidates=True, candidates_type_dict=cand, is_tumor=True,
+            mapping_quality=[ord(c) - 33 for c in mq], base_quality=[ord(c) - 33 for c in bq],
+            phasing_info=None, chunk_ref_seq=chunk_ref, platform=platform)
+        cases.append(dict(bases=bases, bq=bq, mq=mq, ref=ref, candidate=is_cand, chunk_ref=chunk_ref,
+                          platform=platform, vec=[int(v) for v in vec], alt_info=alt_info if is_cand else None))
+
+    for row in HAND_ROWS:
+        for platform in ("ont", "ont_r10_dorado_sup_5khz", "ilmn"):
+            run(*row, platform)
+    # seeded synthetic rows rendered to mpileup text (with ^ / $ decorations)
+    for seed, platform in ((11, 'ont'), (12, 'ilmn'), (13, 'hifi')):
+        stream, aux = synth.synth_stream(4, seed, platform, depth_lo=1, depth_hi=90)
+        rows = synth.render_mpileup(stream, aux, decorate_seed=seed)
+        for i, text in enumerate(rows):
+            cols = text.rstrip("\n").split("\t")
+            ref = "ACGT"[int(stream.ref_code[i])]
+            run(cols[4], cols[5], cols[6], ref, i % 3 == 0, (ref + "ACGTTGCA" * 8)[:60],
+                "ont" if platform == 'ont' and i % 2 else {"ont": "ont_r10_dorado_sup_5khz", "ilmn": "ilmn_ssrs",
+                                                           "hifi": "hifi_revio"}[platform])
+    with open(os.path.join(HERE, "encoder_golden.json"), "w") as f:
+        json.dump(cases, f)
+    print("encoder_golden.json: %d cases" % len(cases))
+
+
+CVT_KW = dict(num_classes=2, s1_emb_dim=16, s1_emb_kernel=3, s1_emb_stride=2, s1_proj_kernel=3, s1_kv_proj_stride=2,
+              s1_heads=1, s1_depth=1, s1_mlp_mult=4, s2_emb_dim=64, s2_emb_kernel=3, s2_emb_stride=2, s2_proj_kernel=3,
+              s2_kv_proj_stride=2, s2_heads=3, s2_depth=2, s2_mlp_mult=4, s3_emb_dim=128, s3_emb_kernel=3,
+              s3_emb_stride=2, s3_proj_kernel=3, s3_kv_proj_stride=2, s3_heads=4, s3_depth=3, s3_mlp_mult=4,
+              dropout=0., dropout_fc=0.3, depth=1, width=33, dim=34, apply_softmax=False, model_type="acgt")
+
+
+def build_reference_models(n_heads, seed_aff, seed_neg):
+    from clairs.model import CvT, CvT_Indel, BiGRU_NACGT, BiGRU_NACGT_Indel
+    aff = (CvT if n_heads == 4 else CvT_Indel)(**CVT_KW).eval()
+    neg = (BiGRU_NACGT if n_heads == 4 else BiGRU_NACGT_Indel)(apply_softmax=False, num_classes=2, channel_size=34,
+                                                                 model_type="nacgt").eval()
+    aff.load_state_dict(nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads), seed_aff), strict=False)
+    neg.load_state_dict(nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), seed_neg), strict=False)
+    return aff, neg
+
+
+def synth_tensor(n, seed, deep=False):
+    """Count-like int16 tensors [n,33,34] through the same generator the tests use."""
+    (aff, _), (neg, _) = synth.synth_pair(n, seed, 'ont', depth_mean=120 if deep else 50, depth_hi=200)
+    return aff, neg
+
+
+def nn_golden():
+    torch.set_num_threads(4)
+    out = {}
+    rng = np.random.default_rng(5)
+    for n_heads in (4, 6):
+        aff, neg = build_reference_models(n_heads, 100 + n_heads, 200 + n_heads)
+        x = rng.integers(-60, 61, size=(24, 33, 34)).astype(np.float32)
+        x[12:] *= np.float32(0.37)                     # rescaled (non-integer) inputs as after predict.py:179-197
+        with torch.no_grad():
+            la = torch.stack(aff(torch.from_numpy(x)), 1).numpy()
+            ln = torch.stack(neg(torch.from_numpy(x)), 1).numpy()
+        out["x_%d" % n_heads] = x
+        out["aff_logits_%d" % n_heads] = la
+        out["neg_logits_%d" % n_heads] = ln
+    np.savez_compressed(os.path.join(HERE, "nn_golden.npz"), **out)
+    print("nn_golden.npz:", {k: v.shape for k, v in out.items()})
+
+
+def likelihood_file(path, n_heads, seed):
+    rng = np.random.default_rng(seed)
+    rows = [rng.uniform(0.05, 0.95, size=(10, 10)) for _ in range(n_heads)]
+    edges = [np.sort(rng.uniform(0.02, 0.98, size=10)) for _ in range(2 * n_heads)]
+    np.savetxt(path, np.concatenate(rows + [e[None, :] for e in edges], axis=0), fmt="%.6f")
+
+
+def pipeline_golden():
+    """Unmodified reference CLIs `predict` and `call_variants` on a synthetic tensor_can chunk."""
+    from oracle import pileup_oracle
+    work = os.path.join(HERE, "pipeline")
+    os.makedirs(work, exist_ok=True)
+    ctg = "chr20"
+    for n_heads, tag in ((4, "snv"), (6, "indel")):
+        n = 40
+        (aff, aff_aux), (neg, neg_aux) = synth.synth_pair(n, 300 + n_heads, 'ont', depth_mean=60, depth_hi=160)
+        ref_rng = np.random.default_rng(7)
+        files = {}
+        for name, stream, aux in (("aff", aff, aff_aux), ("neg", neg, neg_aux)):
+            rows = synth.render_mpileup(stream, aux, ctg=ctg, first_pos=1001)
+            # every candidate owns 33 consecutive rows; give candidates far-apart coordinates
+            text_rows = []
+            for c in range(n):
+                centre = 5000 + 200 * c
+                ref33 = ''.join("ACGT"[int(stream.ref_code[c * 33 + j])] for j in range(33))
+                if c == 3:
+                    ref33 = ref33[:16] + 'N' + ref33[17:]        # dropped by predict.py:219-220
+                window, alt_info = [], None
+                for j in range(33):
+                    cols = rows[c * 33 + j].rstrip("\n").split("\t")
+                    rb = "ACGT"[int(stream.ref_code[c * 33 + j])]
+                    vec, ai = pileup_oracle.position_vector(
+                        cols[4], [ord(ch) - 33 for ch in cols[6]], [ord(ch) - 33 for ch in cols[5]], rb,
+                        is_candidate=(j == 16), chunk_ref_seq=(rb + "ACGTTGCA" * 8)[:60],
+                        platform="ont_r10_dorado_sup_5khz")
+                    window.append(vec)
+                    if j == 16:
+                        alt_info = ai
+                flat = " ".join(" ".join("%d" % v for v in vec) for vec in window)
+                text_rows.append("%s\t%d\t%s\t%s\t%s\t%s\t%s\n" % (ctg, centre, ref33, flat, alt_info, "unknown", ref33[16]))
+            path = os.path.join(work, "tensor_can_%s_%s" % (name, tag))
+            with gzip.open(path, "wt") as f:
+                f.writelines(text_rows)
+            files[name] = path
+        aff_m, neg_m = build_reference_models(n_heads, 100 + n_heads, 200 + n_heads)
+        ck_a = os.path.join("/tmp", "golden_aff_%s.pkl" % tag)
+        ck_n = os.path.join("/tmp", "golden_neg_%s.pkl" % tag)
+        torch.save({'model_acgt': aff_m}, ck_a)
+        torch.save({'model_nacgt': neg_m}, ck_n)
+        predict_fn = os.path.join(work, "predict_%s" % tag)
+        env = dict(os.environ, PYTHONPATH=REF)
+        subprocess.run([sys.executable, os.path.join(REF, "clairs_to.py"),
+                        "predict", "--tensor_fn_acgt", files["aff"], "--tensor_fn_nacgt", files["neg"],
+                        "--predict_fn", predict_fn, "--chkpnt_fn_acgt", ck_a, "--chkpnt_fn_nacgt", ck_n,
+                        "--use_gpu", "False", "--platform", "ont_r10_dorado_sup_5khz", "--ctg_name", ctg, "--pileup",
+                        "--disable_indel_calling", "True" if n_heads == 4 else "False"], check=True, env=env)
+        lk = os.path.join(work, "likelihood_%s.txt" % tag)
+        likelihood_file(lk, n_heads, 400 + n_heads)
+        fai = os.path.join(work, "ref.fa.fai")
+        with open(fai, "w") as f:
+            f.write("%s\t64444167\t7\t60\t61\n" % ctg)
+        fa = os.path.join(work, "ref.fa")
+        open(fa, "a").close()
+        for show_ref in (False, True):
+            vcf = os.path.join(work, "call_%s%s.vcf" % (tag, "_showref" if show_ref else ""))
+            cmd = [sys.executable, os.path.join(REF, "clairs_to.py"), "call_variants", "--predict_fn", predict_fn,
+                   "--call_fn", vcf, "--ref_fn", fa, "--platform", "ont_r10_dorado_sup_5khz",
+                   "--likelihood_matrix_data", lk, "--disable_indel_calling", "True" if n_heads == 4 else "False"]
+            if show_ref:
+                cmd.append("--show_ref")
+            subprocess.run(cmd, check=True, env=env)
+            if not os.path.exists(vcf):
+                open(vcf + ".absent", "w").close()
+        print("pipeline golden (%s) written" % tag)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    if a.only in (None, "encoder"):
+        encoder_golden()
+    if a.only in (None, "nn"):
+        nn_golden()
+    if a.only in (None, "pipeline"):
+        pipeline_golden()

@@ -1,0 +1,107 @@
+"""CPU: pin the oracle to the fixtures the reference itself produced (tests/golden/make_golden.py)."""
+
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn_oracle, pileup_oracle, posterior_oracle
+
+
+def test_encoder_oracle_matches_reference_decode(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "encoder_golden.json")))
+    assert len(cases) > 400
+    for c in cases:
+        vec, alt_info = pileup_oracle.position_vector(
+            c["bases"], [ord(ch) - 33 for ch in c["mq"]], [ord(ch) - 33 for ch in c["bq"]], c["ref"],
+            is_candidate=c["candidate"], chunk_ref_seq=c["chunk_ref"], platform=c["platform"])
+        assert vec == c["vec"], c["bases"]
+        assert alt_info == c["alt_info"], c["bases"]
+
+
+@pytest.mark.parametrize("n_heads", [4, 6])
+def test_nn_oracle_matches_reference_forward(golden_dir, n_heads):
+    g = np.load(os.path.join(golden_dir, "nn_golden.npz"))
+    x = g["x_%d" % n_heads]
+    aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads), 100 + n_heads)
+    neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 200 + n_heads)
+    la = nn_oracle.aff_forward(x, aff_sd).numpy()
+    ln = nn_oracle.neg_forward(x, neg_sd).numpy()
+    # same arithmetic (torch CPU fp32) in a different op order: 2e-5 absolute
+    assert np.abs(la - g["aff_logits_%d" % n_heads]).max() < 2e-5
+    assert np.abs(ln - g["neg_logits_%d" % n_heads]).max() < 2e-5
+    assert np.abs(g["aff_logits_%d" % n_heads]).max() > 0.1      # the comparison is not vacuous
+
+
+def _read_rows(path):
+    with gzip.open(path, "rt") as f:
+        return [r.rstrip("\n").split("\t") for r in f]
+
+
+@pytest.mark.parametrize("tag,n_heads", [("snv", 4), ("indel", 6)])
+def test_predict_rows_match_reference_predict(golden_dir, tag, n_heads):
+    """oracle rescale + forward + softmax + strand counts + row format vs the reference's predict file."""
+    pdir = os.path.join(golden_dir, "pipeline")
+    aff_rows = _read_rows(os.path.join(pdir, "tensor_can_aff_" + tag))
+    neg_rows = _read_rows(os.path.join(pdir, "tensor_can_neg_" + tag))
+    ref_rows = _read_rows(os.path.join(pdir, "predict_" + tag))
+    keep = [i for i, r in enumerate(aff_rows) if r[2][16] in "ACGT"]          # predict.py:219-220
+    assert len(keep) == len(ref_rows) == len(aff_rows) - 1
+    aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads), 100 + n_heads)
+    neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 200 + n_heads)
+
+    def tensors(rows):
+        raw = np.array([[int(v) for v in rows[i][3].split()] for i in keep], dtype=np.int32).reshape(-1, 33, 34)
+        scaled = np.stack([posterior_oracle.rescale_tensor(raw[k], posterior_oracle.depth_from_alt_info(rows[i][4]))
+                           for k, i in enumerate(keep)])
+        return raw, scaled
+
+    raw_a, xa = tensors(aff_rows)
+    _, xn = tensors(neg_rows)
+    pa = nn_oracle.softmax_heads(nn_oracle.aff_forward(xa, aff_sd)).numpy()
+    pn = nn_oracle.softmax_heads(nn_oracle.neg_forward(xn, neg_sd)).numpy()
+    fwd, rev = posterior_oracle.strand_counts(raw_a.astype(np.float32))
+    for k, i in enumerate(keep):
+        got = posterior_oracle.format_predict_row(aff_rows[i][0], aff_rows[i][1], aff_rows[i][2][16], aff_rows[i][4],
+                                                  fwd[k].tolist(), rev[k].tolist(),
+                                                  list(pa[k]) + list(pn[k])).rstrip("\n").split("\t")
+        ref = ref_rows[k]
+        assert got[:6] == ref[:6]
+        assert len(got) == len(ref) == 6 + 2 * n_heads + (1 if n_heads == 4 else 0)
+        for a, b in zip(got[6:6 + 2 * n_heads], ref[6:6 + 2 * n_heads]):
+            assert np.allclose([float(v) for v in a.split()], [float(v) for v in b.split()], atol=2e-6)
+
+
+def _vcf_records(path):
+    if not os.path.exists(path):
+        return []
+    return [r.rstrip("\n").split("\t") for r in open(path) if not r.startswith("#")]
+
+
+@pytest.mark.parametrize("tag,n_heads", [("snv", 4), ("indel", 6)])
+def test_posterior_oracle_matches_reference_calls(golden_dir, tag, n_heads):
+    """posterior + QUAL + RefCall/variant decision vs the reference call_variants --show_ref VCF."""
+    pdir = os.path.join(golden_dir, "pipeline")
+    mats, ea, en = posterior_oracle.load_likelihood(os.path.join(pdir, "likelihood_%s.txt" % tag), n_heads)
+    recs = {r[1]: r for r in _vcf_records(os.path.join(pdir, "call_%s_showref.vcf" % tag))}
+    assert recs
+    checked = 0
+    for row in _read_rows(os.path.join(pdir, "predict_" + tag)):
+        pos, ref_base = row[1], row[2]
+        probs = [[float(v) for v in f.split()] for f in row[6:6 + 2 * n_heads]]
+        post = posterior_oracle.posterior([p[1] for p in probs[:n_heads]], [p[1] for p in probs[n_heads:]], mats, ea, en)
+        k, pmax, is_variant = posterior_oracle.decide(post, ref_base, snv_mode=(n_heads == 4))
+        if pos not in recs:
+            continue
+        rec = recs[pos]
+        # QUAL always comes from the arg-max posterior (CV:417-586), for RefCall and variant rows alike
+        assert abs(float(rec[5]) - posterior_oracle.quality_score(pmax)) < 1e-4
+        if rec[6] != "RefCall":
+            assert is_variant
+        elif n_heads == 6:
+            assert not is_variant
+        checked += 1
+    assert checked > 5
