@@ -32,6 +32,11 @@ SIGNATURES = {
     "cto_forward_aff": (INT, [P, P, I64, P, P]),
     "cto_forward_neg": (INT, [P, P, I64, P, P]),
     "cto_softmax_posterior": (INT, [P, P, P, I64, P, P, P, P]),
+    "cto_launch_count": (I64, []),
+    "cto_engine_profile": (INT, [P, INT]),
+    "cto_engine_profile_kinds": (INT, []),
+    "cto_engine_profile_name": (C.c_char_p, [INT]),
+    "cto_engine_profile_read": (INT, [P, P, P, P]),
     "cto_strand_counts": (INT, [P, I64, P, P, P]),
     "cto_predict": (INT, [P, P, P, P, P, I64, P, P, P, P, P, P, P, P]),
     "cto_run_sites_host": (INT, [P, P, P, I64, INT, P, P, P, P, P, P]),

@@ -17,6 +17,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static int64_t g_launches = 0;
+void count_launch(int n) { __atomic_add_fetch(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
+int64_t launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off,
                          const uint8_t* ref_code, const int32_t* ind_off, const uint32_t* ind_entry,
                          const int32_t* win_pos, int64_t n_candidates, int low_bq_cut, int16_t* tensor,
@@ -167,6 +171,25 @@ int cto_softmax_posterior(cto_engine* h, const float* la, const float* ln, int64
     return launch_softmax_posterior(la, ln, n, h->e.aff.n_heads, tables, probs, post, call, (cudaStream_t)stream);
 }
 
+int64_t cto_launch_count(void) { return launches(); }
+
+int cto_engine_profile(cto_engine* h, int enable) {
+    CTO_REQUIRE(h, "engine_profile: NULL engine");
+    h->e.profile = enable != 0;
+    return 0;
+}
+
+int cto_engine_profile_kinds(void) { return PK_COUNT; }
+const char* cto_engine_profile_name(int kind) { return prof_kind_name(kind); }
+
+int cto_engine_profile_read(cto_engine* h, double* ms, int64_t* launches_out, double* flops_per_candidate) {
+    CTO_REQUIRE(h && ms && launches_out, "engine_profile_read: NULL argument");
+    if (int rc = prof_collect(h->e, ms, launches_out)) return rc;
+    if (flops_per_candidate)
+        for (int k = 0; k < PK_COUNT; ++k) flops_per_candidate[k] = prof_kind_flops_per_candidate(h->e, k);
+    return 0;
+}
+
 int cto_strand_counts(const int16_t* x, int64_t n, int32_t* fwd, int32_t* rev, void* stream) {
     CTO_REQUIRE(n == 0 || (x && fwd && rev), "strand_counts: NULL argument");
     return launch_strand_counts(x, n, fwd, rev, (cudaStream_t)stream);
@@ -183,15 +206,11 @@ int cto_predict(cto_engine* h, const int16_t* x_aff, const int32_t* depth_aff, c
     const int64_t xin = (int64_t)N_POS * N_CH;
     for (int64_t o = 0; o < n; o += e.max_batch) {
         const int64_t nb = std::min(e.max_batch, n - o);
-        // fork: NEG on the side stream, AFF on the caller's stream
-        CTO_CHECK(cudaEventRecord(e.ev_fork, s));
-        CTO_CHECK(cudaStreamWaitEvent(e.side, e.ev_fork, 0));
-        if (int rc = launch_rescale(x_neg + o * xin, depth_neg + o, nb, e.x_neg, e.side)) return rc;
-        if (int rc = neg_forward(e, e.x_neg, nb, logits_neg + o * nh * 2, e.side)) return rc;
-        CTO_CHECK(cudaEventRecord(e.ev_join, e.side));
+        // both networks saturate the GPU on their own, so they run back to back on the caller's stream
+        if (int rc = launch_rescale(x_neg + o * xin, depth_neg + o, nb, e.x_neg, s)) return rc;
+        if (int rc = neg_forward(e, e.x_neg, nb, logits_neg + o * nh * 2, s)) return rc;
         if (int rc = launch_rescale(x_aff + o * xin, depth_aff + o, nb, e.x_aff, s)) return rc;
         if (int rc = aff_forward(e, e.x_aff, nb, logits_aff + o * nh * 2, s)) return rc;
-        CTO_CHECK(cudaStreamWaitEvent(s, e.ev_join, 0));
     }
     if (fwd && rev)
         if (int rc = launch_strand_counts(x_aff, n, fwd, rev, s)) return rc;

@@ -38,4 +38,8 @@ const char* get_error();
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
+int64_t launches();
+
 }  // namespace cto

@@ -194,6 +194,7 @@ int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* 
     encode_pileup_kernel<<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(
         code, bq, mq, pos_off, ref_code, ind_off, ind_entry, win_pos, n_slots, low_bq_cut, tensor, depth);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

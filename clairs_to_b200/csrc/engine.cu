@@ -152,9 +152,6 @@ int engine_alloc(Engine& e, int64_t max_batch) {
     rc |= dev_alloc(e, &e.f1n, b * FC_DIM);
     rc |= dev_alloc(e, &e.f2n, b * 6 * FC_DIM);
     if (rc) return 1;
-    CTO_CHECK(cudaStreamCreateWithFlags(&e.side, cudaStreamNonBlocking));
-    CTO_CHECK(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming));
-    CTO_CHECK(cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming));
     return 0;
 }
 
@@ -164,9 +161,71 @@ void engine_free(Engine& e) {
     if (e.aff.blob) cudaFree(e.aff.blob);
     if (e.neg.blob) cudaFree(e.neg.blob);
     if (e.tables) cudaFree(e.tables);
-    if (e.side) cudaStreamDestroy(e.side);
-    if (e.ev_fork) cudaEventDestroy(e.ev_fork);
-    if (e.ev_join) cudaEventDestroy(e.ev_join);
+    for (auto& r : e.prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+    for (cudaEvent_t ev : e.ev_free) cudaEventDestroy(ev);
+    e.prof.clear();
+    e.ev_free.clear();
+}
+
+const char* prof_kind_name(int kind) {
+    static const char* names[PK_COUNT] = {"aff_forward", "neg_proj1_gemm", "neg_gru1_recurrent", "neg_proj2_gemm",
+                                          "neg_gru2_recurrent", "neg_fc1_gemm", "neg_heads"};
+    return (kind >= 0 && kind < PK_COUNT) ? names[kind] : "?";
+}
+
+// multiply-add = 2 FLOP; matches SURVEY.md section 8(d) accounting
+double prof_kind_flops_per_candidate(const Engine& e, int kind) {
+    const GruLayerW* l = e.neg.l;
+    const double t = N_POS;
+    switch (kind) {
+        case PK_NEG_PROJ1: return 2.0 * t * l[0].in_dim * 6 * l[0].hidden;
+        case PK_NEG_GRU1: return 2.0 * t * l[0].hidden * 6 * l[0].hidden;
+        case PK_NEG_PROJ2: return 2.0 * t * l[1].in_dim * 6 * l[1].hidden;
+        case PK_NEG_GRU2: return 2.0 * t * l[1].hidden * 6 * l[1].hidden;
+        case PK_NEG_FC1: return 2.0 * t * 2 * l[1].hidden * FC_DIM;
+        case PK_NEG_HEADS: return 2.0 * e.neg.n_heads * (FC_DIM * FC_DIM + 2 * FC_DIM);
+        default: return 0.0;
+    }
+}
+
+static int take_event(Engine& e, cudaEvent_t* ev) {
+    if (!e.ev_free.empty()) {
+        *ev = e.ev_free.back();
+        e.ev_free.pop_back();
+        return 0;
+    }
+    CTO_CHECK(cudaEventCreate(ev));
+    return 0;
+}
+
+int prof_begin(Engine& e, int kind, cudaStream_t s) {
+    if (!e.profile) return 0;
+    Engine::ProfRec r{kind, nullptr, nullptr};
+    if (take_event(e, &r.start) || take_event(e, &r.stop)) return 1;
+    CTO_CHECK(cudaEventRecord(r.start, s));
+    e.prof.push_back(r);
+    return 0;
+}
+
+int prof_end(Engine& e, cudaStream_t s) {
+    if (!e.profile) return 0;
+    CTO_CHECK(cudaEventRecord(e.prof.back().stop, s));
+    return 0;
+}
+
+int prof_collect(Engine& e, double* ms, int64_t* count) {
+    for (int k = 0; k < PK_COUNT; ++k) { ms[k] = 0.0; count[k] = 0; }
+    for (auto& r : e.prof) {
+        CTO_CHECK(cudaEventSynchronize(r.stop));
+        float t = 0.0f;
+        CTO_CHECK(cudaEventElapsedTime(&t, r.start, r.stop));
+        ms[r.kind] += t;
+        count[r.kind] += 1;
+        e.ev_free.push_back(r.start);
+        e.ev_free.push_back(r.stop);
+    }
+    e.prof.clear();
+    return 0;
 }
 
 #define RUN(x) do { if (int _rc = (x)) return _rc; } while (0)
@@ -185,6 +244,7 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
     CTO_REQUIRE(n <= e.max_batch, "aff_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
     const AffModel& m = e.aff;
     const float* cur = x;
+    RUN(prof_begin(e, PK_AFF, s));
     for (int si = 0; si < m.n_stages; ++si) {
         const CvtStage& st = m.st[si];
         const int c = st.c, inner = st.heads * DIM_HEAD;
@@ -212,7 +272,8 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         // the next stage reads a_xs while writing a_t0, so no copy is needed
         cur = e.a_xs;
     }
-    return run_heads(m.head, cur, m.feat, m.n_heads, n, e.f1, e.f2, logits, s);
+    RUN(run_heads(m.head, cur, m.feat, m.n_heads, n, e.f1, e.f2, logits, s));
+    return prof_end(e, s);
 }
 
 int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {
@@ -223,13 +284,25 @@ int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
     for (int l = 0; l < 2; ++l) {
         const GruLayerW& g = m.l[l];
         const int h = g.hidden;
+        RUN(prof_begin(e, l ? PK_NEG_PROJ2 : PK_NEG_PROJ1, s));
         RUN(launch_gemm_nt(plain_a(cur, g.in_dim), g.wih, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS, 6 * h, g.in_dim,
                            ACT_NONE, s));
+        RUN(prof_end(e, s));
+        RUN(prof_begin(e, l ? PK_NEG_GRU2 : PK_NEG_GRU1, s));
         RUN(launch_gru_recurrent(e.n_xp, g.whh_t, g.bhn, outs[l], n, h, s));
+        RUN(prof_end(e, s));
         cur = outs[l];
     }
     const int feat = N_POS * 2 * m.l[1].hidden;
-    return run_heads(m.head, cur, feat, m.n_heads, n, e.f1n, e.f2n, logits, s);
+    const HeadW& hd = m.head;
+    RUN(prof_begin(e, PK_NEG_FC1, s));
+    RUN(launch_gemm_nt(plain_a(cur, feat), hd.fc1_w, hd.fc1_b, nullptr, 0, e.f1n, FC_DIM, n, FC_DIM, feat, ACT_SELU, s));
+    RUN(prof_end(e, s));
+    RUN(prof_begin(e, PK_NEG_HEADS, s));
+    RUN(launch_gemm_nt(plain_a(e.f1n, FC_DIM), hd.fc2_w, hd.fc2_b, nullptr, 0, e.f2n, (int64_t)m.n_heads * FC_DIM, n,
+                       m.n_heads * FC_DIM, FC_DIM, ACT_SELU, s));
+    RUN(launch_head_fc3(e.f2n, hd.fc3_w, hd.fc3_b, logits, n, m.n_heads, s));
+    return prof_end(e, s);
 }
 
 }  // namespace cto

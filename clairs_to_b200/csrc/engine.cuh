@@ -60,10 +60,21 @@ struct Engine {
     float *f1n = nullptr, *f2n = nullptr;
     double* tables = nullptr;                                  // likelihood tables, n_heads * 122
     int table_heads = 0;
-    cudaStream_t side = nullptr;                               // NEG runs beside AFF
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<void*> allocs;
+    // optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
+    bool profile = false;
+    struct ProfRec { int kind; cudaEvent_t start, stop; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_free;
 };
+
+enum ProfKind { PK_AFF = 0, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
+const char* prof_kind_name(int kind);
+double prof_kind_flops_per_candidate(const Engine& e, int kind);
+int prof_begin(Engine& e, int kind, cudaStream_t s);
+int prof_end(Engine& e, cudaStream_t s);
+// synchronises, sums elapsed ms and launch counts per kind, clears the records
+int prof_collect(Engine& e, double* ms, int64_t* count);
 
 int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg, int cfg_len);
 int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg, int cfg_len);

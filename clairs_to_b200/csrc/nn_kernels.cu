@@ -45,6 +45,7 @@ int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out
     const int64_t total = n * N_POS * N_CH;
     rescale_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, depth, total, out);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -68,6 +69,7 @@ int launch_strand_counts(const int16_t* x_aff, int64_t n, int32_t* fwd, int32_t*
     if (n <= 0) return 0;
     strand_counts_kernel<<<ceil_div(n * 2, 128), 128, 0, s>>>(x_aff, n, fwd, rev);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -189,6 +191,7 @@ int launch_gemm_nt(const AView& a, const float* w, const float* bias, const floa
     dim3 grid(ceil_div(m, G_BM), ceil_div(n, G_BN));
     gemm_nt_kernel<<<grid, 256, 0, s>>>(a, w, bias, residual, ldr, c, ldc, m, n, k, act, vec_ok);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -234,6 +237,7 @@ int launch_channel_ln(const float* x, const float* g, const float* b, float* y, 
     CTO_REQUIRE(c <= 128, "channel_ln: C=%d > 128 unsupported", c);
     channel_ln_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, g, b, y, rows, c);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -264,6 +268,7 @@ int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch,
     if (total <= 0) return 0;
     dwconv3_kernel<<<ceil_div(total, 256), 256, 0, s>>>(y, taps, out, total, win, wout, stride, c);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -340,6 +345,7 @@ int launch_attention(const float* q, const float* kv, float* out, int64_t batch,
     CTO_REQUIRE(w <= ATT_MAXW && wkv <= ATT_MAXKV, "attention: W=%d Wkv=%d exceed %d/%d", w, wkv, ATT_MAXW, ATT_MAXKV);
     attention_kernel<<<ceil_div(n_bh, ATT_WARPS), ATT_WARPS * 32, 0, s>>>(q, kv, out, n_bh, w, wkv, heads);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -436,6 +442,7 @@ int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bh
         CTO_REQUIRE(false, "gru_recurrent: hidden size %d not built (128 and 192 are, M:403-404)", hidden);
     }
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -468,6 +475,7 @@ int launch_head_fc3(const float* y, const float* w3, const float* b3, float* log
     if (batch <= 0) return 0;
     head_fc3_kernel<<<ceil_div(batch, 8), 256, 0, s>>>(y, w3, b3, logits, batch, n_heads);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 
@@ -540,6 +548,7 @@ int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, i
     softmax_posterior_kernel<<<ceil_div(n, 128), 128, 0, s>>>(logits_aff, logits_neg, n, n_heads, tables, probs, post,
                                                               call);
     CTO_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

@@ -1,0 +1,98 @@
+"""Host-side (no GPU) entry points of the C ABI: mpileup tokenizer and chunk-file text codec.
+
+These sit on either side of the CUDA hot path: ``tokenize_mpileup`` turns ``samtools mpileup`` text
+into the encoder's struct-of-arrays input (src/create_tensor_pileup_calling.py:120-149, 472-497)
+and builds the ``alt_info`` strings (ibid. 158-209); the codec reads/writes the tensor_can and
+predict chunk files byte-compatibly (ibid. 551; clairs/predict.py:121-132).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .pileup_format import N_CH, N_POS, PileupStream
+
+
+@dataclass
+class Tokens:
+    stream: PileupStream          # win_pos is empty: the caller maps candidates to rows
+    row_pos: np.ndarray           # genomic position of every pileup row
+    alt_info: list                # per row: alt_info string for candidate rows, '' otherwise
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def tokenize_mpileup(text, ref_seq, ref_start, candidate_pos, max_indel_length=60) -> Tokens:
+    lib = _lib.lib()
+    if isinstance(text, str):
+        text = text.encode()
+    if isinstance(ref_seq, str):
+        ref_seq = ref_seq.encode()
+    cand = np.ascontiguousarray(np.asarray(list(candidate_pos), dtype=np.int64))
+    handle = C.c_void_p()
+    _lib.check(lib.cto_tokenize_mpileup(text, len(text), ref_seq, len(ref_seq), int(ref_start), _p(cand), cand.size,
+                                        int(max_indel_length), C.byref(handle)), "cto_tokenize_mpileup")
+    try:
+        sizes = [C.c_int64() for _ in range(4)]
+        _lib.check(lib.cto_tokens_sizes(handle, *[C.byref(s) for s in sizes]), "cto_tokens_sizes")
+        n_reads, n_rows, n_ind, n_alt = [s.value for s in sizes]
+        code = np.empty(n_reads, np.uint8)
+        bq = np.empty(n_reads, np.uint8)
+        mq = np.empty(n_reads, np.uint8)
+        pos_off = np.empty(n_rows + 1, np.int32)
+        ref_code = np.empty(n_rows, np.uint8)
+        ind_off = np.empty(n_rows + 1, np.int32)
+        ind_entry = np.empty(n_ind, np.uint32)
+        row_pos = np.empty(n_rows, np.int64)
+        alt = np.empty(max(n_alt, 1), np.uint8)
+        alt_off = np.empty(n_rows + 1, np.int64)
+        _lib.check(lib.cto_tokens_export(handle, _p(code), _p(bq), _p(mq), _p(pos_off), _p(ref_code), _p(ind_off),
+                                         _p(ind_entry), _p(row_pos), _p(alt), _p(alt_off)), "cto_tokens_export")
+    finally:
+        lib.cto_tokens_destroy(handle)
+    blob = alt.tobytes()[:n_alt].decode()
+    infos = [blob[alt_off[i]:alt_off[i + 1]] for i in range(n_rows)]
+    stream = PileupStream(code, bq, mq, pos_off, ref_code, ind_off, ind_entry, np.empty(0, np.int32))
+    return Tokens(stream, row_pos, infos)
+
+
+def format_tensor_rows(tensors) -> list:
+    """int16 [n,33,34] -> n strings of 1122 space-separated ints (the 4th tensor_can column)."""
+    lib = _lib.lib()
+    t = np.ascontiguousarray(tensors, dtype=np.int16).reshape(-1, N_POS * N_CH)
+    cap = N_POS * N_CH * 7 + 8
+    buf = C.create_string_buffer(cap)
+    out = []
+    for k in range(t.shape[0]):
+        n = lib.cto_format_tensor_row(_p(t[k]), buf, cap)
+        if n < 0:
+            raise _lib.CtoError("cto_format_tensor_row: buffer too small")
+        out.append(buf.raw[:n].decode())
+    return out
+
+
+def parse_tensor_row(text) -> np.ndarray:
+    lib = _lib.lib()
+    if isinstance(text, str):
+        text = text.encode()
+    row = np.empty(N_POS * N_CH, np.int16)
+    _lib.check(lib.cto_parse_tensor_row(text, len(text), _p(row)), "cto_parse_tensor_row")
+    return row.reshape(N_POS, N_CH)
+
+
+def format_prob_fields(probs) -> str:
+    """float32 [k,2] -> 'p0 p1<TAB>p0 p1...' with 8 decimals, exactly like "{:0.8f}".format."""
+    lib = _lib.lib()
+    p = np.ascontiguousarray(probs, dtype=np.float32).reshape(-1, 2)
+    cap = 64 * p.shape[0] + 64
+    buf = C.create_string_buffer(cap)
+    n = lib.cto_format_prob_fields(_p(p), p.shape[0], buf, cap)
+    if n < 0:
+        raise _lib.CtoError("cto_format_prob_fields: buffer too small")
+    return buf.raw[:n].decode()

@@ -147,6 +147,37 @@ def synth_pair(n_candidates, seed, platform='ont', **kw):
     return (aff, aff_aux), (neg, aux)
 
 
+def concat_streams(streams):
+    """Concatenate disjoint PileupStreams (offsets and window indices are rebased)."""
+    code = np.concatenate([s.code for s in streams])
+    bq = np.concatenate([s.bq for s in streams])
+    mq = np.concatenate([s.mq for s in streams])
+    ref_code = np.concatenate([s.ref_code for s in streams])
+    ind_entry = np.concatenate([s.ind_entry for s in streams])
+    pos_off, ind_off, win_pos = [np.zeros(1, np.int32)], [np.zeros(1, np.int32)], []
+    reads = inds = rows = 0
+    for s in streams:
+        pos_off.append((s.pos_off[1:].astype(np.int64) + reads).astype(np.int32))
+        ind_off.append((s.ind_off[1:].astype(np.int64) + inds).astype(np.int32))
+        win_pos.append(np.where(s.win_pos >= 0, s.win_pos + rows, -1).astype(np.int32))
+        reads += s.n_reads
+        inds += len(s.ind_entry)
+        rows += s.n_rows
+    assert reads < 2 ** 31, "one batch holds at most 2^31 reads"
+    return PileupStream(code, bq, mq, np.concatenate(pos_off), ref_code, np.concatenate(ind_off), ind_entry,
+                        np.concatenate(win_pos))
+
+
+def synth_pair_large(n_candidates, seed, platform='ont', piece=20000, **kw):
+    """synth_pair in bounded-memory pieces (bench-scale batches)."""
+    affs, negs = [], []
+    for k, lo in enumerate(range(0, n_candidates, piece)):
+        (a, _), (n, _) = synth_pair(min(piece, n_candidates - lo), seed * 1000 + k, platform, **kw)
+        affs.append(a)
+        negs.append(n)
+    return concat_streams(affs), concat_streams(negs)
+
+
 _BASES = "ACGT"
 
 

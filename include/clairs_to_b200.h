@@ -89,6 +89,18 @@ int cto_forward_neg(cto_engine* e, const float* x_dev, int64_t n, float* logits_
 int cto_softmax_posterior(cto_engine* e, const float* logits_aff_dev, const float* logits_neg_dev, int64_t n,
                           float* probs_dev, double* post_dev, int32_t* call_dev, void* stream);
 
+/*
+ * Instrumentation for bench.py: kernels launched by this library so far in this process, and
+ * optional CUDA-event timing of the kernel families of the forward passes (events are recorded
+ * on the launching stream; cto_engine_profile_read synchronises and returns, per family, the
+ * summed milliseconds, the number of timed launches and the algorithmic FLOP per candidate).
+ */
+int64_t cto_launch_count(void);
+int cto_engine_profile(cto_engine* e, int enable);
+int cto_engine_profile_kinds(void);
+const char* cto_engine_profile_name(int kind);
+int cto_engine_profile_read(cto_engine* e, double* ms, int64_t* launches, double* flops_per_candidate);
+
 /* Strand-count recovery of clairs/predict.py:626-642 from the un-rescaled AFF tensor: int32 [n,4] x2. */
 int cto_strand_counts(const int16_t* x_aff_dev, int64_t n, int32_t* fwd_dev, int32_t* rev_dev, void* stream);
 

@@ -1,0 +1,98 @@
+"""CPU: the C-ABI library loads, exports every declared symbol, and its HOST-side entry points
+(mpileup tokenizer, chunk-file text codec) agree with the oracle.  No compute call needs a GPU."""
+
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from clairs_to_b200 import _lib, synth
+from clairs_to_b200.host import tokenize_mpileup, format_tensor_rows, parse_tensor_row, format_prob_fields
+from clairs_to_b200.pileup_format import HAS_INDEL, SYMBOLS
+from oracle import pileup_oracle, posterior_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "clairs_to_b200.h")).read()
+    declared = set(re.findall(r"\b(cto_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cto_engine", "cto_tokens", "cto_host_stream"}
+    assert len(declared) >= 20
+    handle = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), "missing export " + name
+    assert set(_lib.SIGNATURES) == declared
+    assert _lib.lib().cto_abi_version() == 1
+
+
+def test_tokenizer_matches_oracle_on_golden_rows(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "encoder_golden.json")))
+    ref_window = "ACGT"
+    for c in cases:
+        if c["platform"] != "ont":          # tokenisation is platform independent; one pass is enough
+            continue
+        chunk_ref = c["chunk_ref"] if c["chunk_ref"] else c["ref"]
+        # a reference window whose first base is the row's reference base and continues with chunk_ref
+        ref_seq = (chunk_ref if chunk_ref[0] == c["ref"] else c["ref"] + chunk_ref[1:]) + "A" * 64
+        row = "chr1\t100\tN\t0\t%s\t%s\t%s\n" % (c["bases"], c["bq"], c["mq"])
+        tok = tokenize_mpileup(row, ref_seq, 100, [100] if c["candidate"] else [], 60)
+        entries = pileup_oracle.tokenize(c["bases"])
+        assert tok.stream.n_reads == len(entries)
+        for i, (sym, indel) in enumerate(entries):
+            code = int(tok.stream.code[i])
+            assert SYMBOLS[code & 0xF] == sym
+            assert bool(code & HAS_INDEL) == bool(indel)
+        if c["candidate"] and chunk_ref[0] == c["ref"]:
+            assert tok.alt_info[0] == c["alt_info"], c["bases"]
+
+
+def test_tokenizer_multi_row_layout():
+    stream, aux = synth.synth_stream(3, 21, 'ont', depth_lo=0, depth_hi=40, depth_mean=12)
+    rows = synth.render_mpileup(stream, aux, decorate_seed=3)
+    ref_seq = ''.join("ACGT"[int(r)] for r in stream.ref_code)
+    tok = tokenize_mpileup(''.join(rows), ref_seq, 1001, [1001 + 16, 1001 + 49], 60)
+    s = tok.stream
+    assert s.n_rows == stream.n_rows
+    assert np.array_equal(tok.row_pos, 1001 + np.arange(stream.n_rows))
+    # rows that were empty in the generator come back as samtools' single '*' placeholder read
+    empty = np.diff(stream.pos_off) == 0
+    expect_depth = np.where(empty, 1, np.diff(stream.pos_off))
+    assert np.array_equal(np.diff(s.pos_off), expect_depth)
+    assert np.array_equal(s.ref_code, stream.ref_code)
+    keep = np.repeat(~empty, expect_depth)
+    assert np.array_equal(s.code[keep], stream.code)
+    assert np.array_equal(s.mq[keep], stream.mq)
+    assert np.array_equal(s.bq[keep], stream.bq)
+    assert np.array_equal(np.diff(s.ind_off), np.diff(stream.ind_off))
+    # allele ids may be numbered differently; everything else in the sparse entries is identical
+    assert np.array_equal(s.ind_entry & 0xFFFF0000, stream.ind_entry & 0xFFFF0000)
+    assert [bool(a) for a in tok.alt_info] == [(p in (1017, 1050)) for p in tok.row_pos]
+
+
+def test_tensor_text_codec_roundtrip():
+    rng = np.random.default_rng(3)
+    t = rng.integers(-300, 300, size=(5, 33, 34)).astype(np.int16)
+    t[0, 0, 0] = -32768
+    t[0, 0, 1] = 32767
+    texts = format_tensor_rows(t)
+    for k in range(5):
+        expect = " ".join(" ".join("%d" % x for x in row) for row in t[k])      # CT:551
+        assert texts[k] == expect
+        assert np.array_equal(parse_tensor_row(texts[k]), t[k])
+    with pytest.raises(_lib.CtoError):
+        parse_tensor_row("1 2 3")
+
+
+def test_prob_field_format_matches_python():
+    rng = np.random.default_rng(4)
+    p = rng.random((6, 8, 2)).astype(np.float32)
+    p[0, 0] = [0.0, 1.0]
+    p[0, 1] = [np.float32(0.123456785), np.float32(1e-9)]
+    for k in range(6):
+        fields = format_prob_fields(p[k]).split("\t")
+        expect = posterior_oracle.format_predict_row("c", 1, "A", "x", [0.0], [0.0], list(p[k])).split("\t")[6:14]
+        assert fields == expect

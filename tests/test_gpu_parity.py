@@ -1,0 +1,257 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars: integer pileup tensor, depths, strand counts and the fp64 posterior (given identical
+probabilities) are BIT-EXACT; AFF/NEG logits, probabilities and end-to-end posteriors are within
+1e-3 absolute (BASELINE.json north_star)."""
+
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from clairs_to_b200 import synth
+from clairs_to_b200.host import tokenize_mpileup
+from clairs_to_b200.pileup_format import N_CH, N_POS, PileupStream
+from oracle import nn_oracle, pileup_oracle, posterior_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _engine(n_heads=4, max_batch=4096, gain=1.0, likelihood=None):
+    from clairs_to_b200.engine import Engine
+    aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads), 100 + n_heads, gain)
+    neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 200 + n_heads, gain)
+    return Engine(aff_sd, neg_sd, max_batch=max_batch, likelihood=likelihood), aff_sd, neg_sd
+
+
+@pytest.fixture(scope="module")
+def eng4():
+    e, a, n = _engine(4)
+    yield e, a, n
+    e.close()
+
+
+def _oracle_tensor(stream, aux, platform_literal):
+    """Render the stream to mpileup text and push every row through the oracle."""
+    rows = synth.render_mpileup(stream, aux, decorate_seed=1)
+    vecs, depths = [], []
+    for i, text in enumerate(rows):
+        pos, bases, bq, mq = pileup_oracle.parse_mpileup_row(text)
+        ref = "ACGT"[int(stream.ref_code[i])]
+        vec, alt = pileup_oracle.position_vector(bases, mq, bq, ref, is_candidate=True, chunk_ref_seq=ref,
+                                                 platform=platform_literal)
+        vecs.append(vec)
+        depths.append(int(alt.split('-')[0]))
+    t = np.array(vecs, dtype=np.int16).reshape(-1, N_POS, N_CH)
+    d = np.array(depths, dtype=np.int32).reshape(-1, N_POS)[:, N_POS // 2]
+    return t, d
+
+
+@pytest.mark.parametrize("platform,literal", [("ont", "ont"), ("ont", "ont_r10_dorado_sup_5khz"),
+                                              ("ilmn", "ilmn_ssrs"), ("hifi", "hifi_revio")])
+def test_encoder_bit_exact_vs_oracle(eng4, platform, literal):
+    from clairs_to_b200.engine import low_bq_cut_for, stream_to_device
+    eng = eng4[0]
+    (aff, aff_aux), (neg, neg_aux) = synth.synth_pair(20, 31, platform, depth_lo=0, depth_hi=150)
+    for stream, aux in ((aff, aff_aux), (neg, neg_aux)):
+        want_t, want_d = _oracle_tensor(stream, aux, literal)
+        got_t, got_d = eng.encode(stream_to_device(stream, eng.device), low_bq_cut_for(literal))
+        assert np.array_equal(got_t.cpu().numpy(), want_t)
+        assert np.array_equal(got_d.cpu().numpy(), want_d)
+
+
+def test_encoder_golden_rows_through_tokenizer(eng4, golden_dir):
+    """reference decode_pileup_bases outputs (golden) == tokenizer (host C++) + encoder (CUDA)."""
+    from clairs_to_b200.engine import low_bq_cut_for, stream_to_device
+    eng = eng4[0]
+    cases = json.load(open(os.path.join(golden_dir, "encoder_golden.json")))
+    for literal in sorted({c["platform"] for c in cases}):
+        group = [c for c in cases if c["platform"] == literal]
+        text = ''.join("chr1\t%d\tN\t0\t%s\t%s\t%s\n" % (100 + i, c["bases"], c["bq"], c["mq"]) for i, c in enumerate(group))
+        ref_seq = ''.join(c["ref"] for c in group)
+        tok = tokenize_mpileup(text, ref_seq, 100, [], 60)
+        s = tok.stream
+        assert s.n_rows == len(group)
+        win = np.full((len(group), N_POS), -1, dtype=np.int32)
+        win[:, N_POS // 2] = np.arange(len(group))
+        s.win_pos = win.reshape(-1)
+        got, depth = eng.encode(stream_to_device(s, eng.device), low_bq_cut_for(literal))
+        got = got.cpu().numpy()
+        want = np.array([c["vec"] for c in group], dtype=np.int16)
+        assert np.array_equal(got[:, N_POS // 2, :], want)
+        assert not got[:, :N_POS // 2].any() and not got[:, N_POS // 2 + 1:].any()     # absent rows are zero rows
+        for c, d in zip(group, depth.cpu().numpy()):
+            if c["alt_info"] is not None:
+                assert int(c["alt_info"].split('-')[0]) == d
+
+
+def test_encoder_edge_cases(eng4):
+    from clairs_to_b200.engine import stream_to_device
+    eng = eng4[0]
+    # empty batch
+    empty = PileupStream(*(np.zeros(0, dt) for dt in (np.uint8, np.uint8, np.uint8)), np.zeros(1, np.int32),
+                         np.zeros(0, np.uint8), np.zeros(1, np.int32), np.zeros(0, np.uint32), np.zeros(0, np.int32))
+    t, d = eng.encode(stream_to_device(empty, eng.device), 10)
+    assert t.shape == (0, N_POS, N_CH) and d.shape == (0,)
+    # one very deep row with many distinct indel alleles (exercises the multi-chunk allele scan)
+    rng = np.random.default_rng(9)
+    reads = []
+    for k in range(3000):
+        sym = "ACGTacgt"[rng.integers(0, 8)]
+        r = rng.random()
+        if r < 0.2:
+            L = int(rng.integers(1, 5))
+            seq = ''.join("ACGT"[rng.integers(0, 2)] for _ in range(L))
+            reads.append(sym + "+%d%s" % (L, seq if sym.isupper() else seq.lower()))
+        elif r < 0.35:
+            L = int(rng.integers(1, 4))
+            reads.append(sym + "-%d%s" % (L, ('N' if sym.isupper() else 'n') * L))
+        else:
+            reads.append(sym)
+    mq = ''.join(chr(33 + int(v)) for v in rng.choice([60, 60, 60, 5], size=3000))
+    bq = ''.join(chr(33 + int(v)) for v in rng.integers(1, 50, size=3000))
+    text = "chr1\t500\tN\t3000\t%s\t%s\t%s\n" % (''.join(reads), bq, mq)
+    tok = tokenize_mpileup(text, "G", 500, [500], 60)
+    s = tok.stream
+    win = np.full(N_POS, -1, dtype=np.int32)
+    win[N_POS // 2] = 0
+    s.win_pos = win
+    got, depth = eng.encode(stream_to_device(s, eng.device), 10)
+    want, alt = pileup_oracle.position_vector(''.join(reads), [ord(c) - 33 for c in mq], [ord(c) - 33 for c in bq], "G",
+                                              is_candidate=True, chunk_ref_seq="G" * 60, platform="x")
+    assert got.cpu().numpy()[0, N_POS // 2].tolist() == want
+    assert int(depth.cpu()[0]) == int(alt.split('-')[0])
+    assert tok.alt_info[0] == alt
+
+
+@pytest.mark.parametrize("n_heads", [4, 6])
+def test_forward_matches_reference_golden(golden_dir, n_heads):
+    eng, _, _ = _engine(n_heads, max_batch=16)          # 24 candidates -> two internal chunks
+    g = np.load(os.path.join(golden_dir, "nn_golden.npz"))
+    x = torch.from_numpy(g["x_%d" % n_heads])
+    la = eng.forward_aff(x).cpu().numpy()
+    ln = eng.forward_neg(x).cpu().numpy()
+    err_a = np.abs(la - g["aff_logits_%d" % n_heads]).max()
+    err_n = np.abs(ln - g["neg_logits_%d" % n_heads]).max()
+    print("max |logit err| vs reference: AFF %.3g NEG %.3g" % (err_a, err_n))
+    assert err_a < TOL and err_n < TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("gain", [0.5, 1.0, 2.0])
+def test_forward_vs_oracle_weight_scales(gain):
+    """Trained weights are unavailable offline: hold the tolerance across weight scales."""
+    eng, aff_sd, neg_sd = _engine(4, max_batch=128, gain=gain)
+    (aff, _), (neg, _) = synth.synth_pair(300, 77, 'ont', depth_mean=70, depth_hi=200)
+    from clairs_to_b200.engine import stream_to_device
+    xa, da = eng.encode(stream_to_device(aff, eng.device), 10)
+    xn, dn = eng.encode(stream_to_device(neg, eng.device), 10)
+    fa = eng.rescale(xa, da)
+    fn = eng.rescale(xn, dn)
+    # rescale is bit-exact against python-double arithmetic (predict.py:179-197)
+    want = np.stack([posterior_oracle.rescale_tensor(t, d) for t, d in zip(xa.cpu().numpy(), da.cpu().numpy())])
+    assert np.array_equal(fa.cpu().numpy(), want)
+    la = eng.forward_aff(fa).cpu().numpy()
+    ln = eng.forward_neg(fn).cpu().numpy()
+    oa = nn_oracle.aff_forward(fa.cpu().numpy(), aff_sd).numpy()
+    on = nn_oracle.neg_forward(fn.cpu().numpy(), neg_sd).numpy()
+    err_a, err_n = np.abs(la - oa).max(), np.abs(ln - on).max()
+    print("gain %.1f: max |logit err| AFF %.3g (max|logit| %.2f) NEG %.3g (max|logit| %.2f)"
+          % (gain, err_a, np.abs(oa).max(), err_n, np.abs(on).max()))
+    assert err_a < TOL and err_n < TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("tag,n_heads", [("snv", 4), ("indel", 6)])
+def test_predict_posterior_against_reference_files(golden_dir, tag, n_heads):
+    """tensor_can chunk files -> CUDA predict -> probabilities vs the reference's predict file;
+    posterior kernel bit-exact vs the oracle on identical probabilities."""
+    pdir = os.path.join(golden_dir, "pipeline")
+    eng, _, _ = _engine(n_heads, max_batch=64, likelihood=os.path.join(pdir, "likelihood_%s.txt" % tag))
+
+    def load(path):
+        rows = [r.rstrip("\n").split("\t") for r in gzip.open(path, "rt")]
+        rows = [r for r in rows if r[2][16] in "ACGT"]
+        t = np.array([[int(v) for v in r[3].split()] for r in rows], dtype=np.int16).reshape(-1, N_POS, N_CH)
+        d = np.array([int(r[4].split('-')[0]) for r in rows], dtype=np.int32)
+        return rows, torch.from_numpy(t).cuda(), torch.from_numpy(d).cuda()
+
+    rows, xa, da = load(os.path.join(pdir, "tensor_can_aff_" + tag))
+    _, xn, dn = load(os.path.join(pdir, "tensor_can_neg_" + tag))
+    out = eng.predict(xa, da, xn, dn)
+    ref_rows = [r.rstrip("\n").split("\t") for r in gzip.open(os.path.join(pdir, "predict_" + tag), "rt")]
+    probs = out['probs'].cpu().numpy()
+    ref_probs = np.array([[[float(v) for v in f.split()] for f in r[6:6 + 2 * n_heads]] for r in ref_rows])
+    assert np.abs(probs - ref_probs).max() < TOL
+    # strand counts: exact ("[0.0, 1.0, 0.0, 35.0]" list reprs in the predict file)
+    fwd = out['fwd'].cpu().numpy().astype(np.float64).tolist()
+    rev = out['rev'].cpu().numpy().astype(np.float64).tolist()
+    for k, r in enumerate(ref_rows):
+        assert str(fwd[k]) == r[4] and str(rev[k]) == r[5]
+    # posterior: identical inputs (the kernel's own probabilities, 8-decimal round trip) -> identical doubles
+    mats, ea, en = posterior_oracle.load_likelihood(os.path.join(pdir, "likelihood_%s.txt" % tag), n_heads)
+    post = out['post'].cpu().numpy()
+    call = out['call'].cpu().numpy()
+    for k in range(len(rows)):
+        p8 = [float("{:0.8f}".format(v)) for v in probs[k, :, 1]]
+        want = posterior_oracle.posterior(p8[:n_heads], p8[n_heads:], mats, ea, en)
+        assert np.array_equal(post[k], want), (k, post[k], want)
+        assert (call[k] & 0xFF) == int(np.argmax(want)) and (call[k] >> 8) == 0
+    eng.close()
+
+
+def test_run_sites_host_equals_device_path(eng4):
+    from clairs_to_b200.engine import stream_to_device
+    eng = eng4[0]
+    (aff, _), (neg, _) = synth.synth_pair(150, 5, 'ont')
+    dev = eng.run_sites(stream_to_device(aff, eng.device), stream_to_device(neg, eng.device), 10, posterior=False)
+    host = eng.run_sites_host(aff, neg, 10, want_tensors=True)
+    assert np.array_equal(host['tensor_aff'].numpy(), dev['tensor_aff'].cpu().numpy())
+    assert np.array_equal(host['tensor_neg'].numpy(), dev['tensor_neg'].cpu().numpy())
+    assert np.array_equal(host['probs'].numpy(), dev['probs'].cpu().numpy())
+    # Illumina-style single stream (NEG symlinked to AFF, run_clairs_to:1248-1252)
+    one = eng.run_sites_host(neg, None, 10)
+    two = eng.run_sites_host(neg, neg, 10)
+    assert np.array_equal(one['probs'].numpy(), two['probs'].numpy())
+
+
+def test_full_size_properties(eng4):
+    """BASELINE config-2 scale slice: size-independent checks without running the python oracle."""
+    from clairs_to_b200.engine import stream_to_device
+    eng = eng4[0]
+    n = 20000
+    (aff, _), (neg, _) = synth.synth_pair(n, 123, 'ont')
+    s = neg
+    t, d = eng.encode(stream_to_device(s, eng.device), 10)
+    t = t.cpu().numpy().astype(np.int64)
+    rows = np.repeat(np.arange(s.n_rows), np.diff(s.pos_off))
+    plain = (s.code & 0x10) == 0
+    hi_mq = s.mq >= 20
+    sym = s.code & 0xF
+    flat = t.reshape(-1, N_CH)
+    # checksum of checksums: '*' and '#' channels, and LMQ/LBQ group sums, against numpy bincounts
+    for symbol, ch in ((10, 8), (11, 17)):
+        want = np.bincount(rows[plain & hi_mq & (sym == symbol)], minlength=s.n_rows)
+        assert np.array_equal(flat[:, ch], want)
+    is_base = plain & (((sym < 4)) | ((sym >= 5) & (sym <= 8)))
+    fwd_base = plain & (sym < 4)
+    want_ref_fwd = -np.bincount(rows[fwd_base & hi_mq], minlength=s.n_rows)
+    ref = s.ref_code.astype(np.int64)
+    assert np.array_equal(flat[np.arange(s.n_rows), ref], want_ref_fwd)          # ref channel = -(A+C+G+T)
+    lbq = np.bincount(rows[is_base & (s.bq < 10)], minlength=s.n_rows)
+    got_lbq = -(flat[np.arange(s.n_rows), 26 + ref] + flat[np.arange(s.n_rows), 30 + ref])
+    assert np.array_equal(got_lbq, lbq)
+    # permutation equivariance of the whole device path
+    perm = np.random.default_rng(0).permutation(n)[:4096]
+    win = s.win_pos.reshape(n, N_POS)[perm].reshape(-1).copy()
+    sp = PileupStream(s.code, s.bq, s.mq, s.pos_off, s.ref_code, s.ind_off, s.ind_entry, win)
+    a = eng.run_sites(stream_to_device(sp, eng.device), None, 10, posterior=False)
+    b = eng.run_sites(stream_to_device(s, eng.device), None, 10, posterior=False)
+    assert np.array_equal(a['tensor_aff'].cpu().numpy(), b['tensor_aff'].cpu().numpy()[perm])
+    assert np.abs(a['probs'].cpu().numpy() - b['probs'].cpu().numpy()[perm]).max() < 1e-5
+    assert np.isfinite(b['probs'].cpu().numpy()).all()
+    assert np.allclose(b['probs'].cpu().numpy().sum(-1), 1.0, atol=1e-5)
