@@ -32,6 +32,8 @@ SIGNATURES = {
     "cto_forward_aff": (INT, [P, P, I64, P, P]),
     "cto_forward_neg": (INT, [P, P, I64, P, P]),
     "cto_softmax_posterior": (INT, [P, P, P, I64, P, P, P, P]),
+    "cto_engine_set_tensor_cores": (INT, [P, INT]),
+    "cto_gemm_nt": (INT, [P, I64, P, P, P, I64, P, I64, I64, INT, INT, INT, INT, P]),
     "cto_launch_count": (I64, []),
     "cto_engine_profile": (INT, [P, INT]),
     "cto_engine_profile_kinds": (INT, []),

@@ -111,6 +111,15 @@ int cto_engine_create(const float* aff_blob, int64_t aff_len, const int32_t* aff
         rc = 2;
     }
     if (!rc) rc = engine_alloc(h->e, max_batch);
+    if (!rc) {
+        // keep stream-ordered allocations of cto_run_sites_host cached between calls
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (rc) {
         engine_free(h->e);
         delete h;
@@ -172,6 +181,19 @@ int cto_softmax_posterior(cto_engine* h, const float* la, const float* ln, int64
 }
 
 int64_t cto_launch_count(void) { return launches(); }
+
+int cto_engine_set_tensor_cores(cto_engine* h, int enable) {
+    CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");
+    h->e.use_tc = enable != 0;
+    return 0;
+}
+
+int cto_gemm_nt(const float* a, int64_t lda, const float* w, const float* bias, const float* residual, int64_t ldr,
+                float* c, int64_t ldc, int64_t m, int n, int k, int act, int use_tensor_cores, void* stream) {
+    if (use_tensor_cores)
+        return launch_gemm_tc(a, lda, w, bias, residual, ldr, c, ldc, m, n, k, act, (cudaStream_t)stream);
+    return launch_gemm_nt(plain_a(a, lda), w, bias, residual, ldr, c, ldc, m, n, k, act, (cudaStream_t)stream);
+}
 
 int cto_engine_profile(cto_engine* h, int enable) {
     CTO_REQUIRE(h, "engine_profile: NULL engine");

@@ -230,11 +230,19 @@ int prof_collect(Engine& e, double* ms, int64_t* count) {
 
 #define RUN(x) do { if (int _rc = (x)) return _rc; } while (0)
 
-static int run_heads(const HeadW& h, const float* feat, int feat_dim, int n_heads, int64_t n, float* f1, float* f2,
+// dense contraction: tcgen05 TF32 when the engine allows it and the shape fits, CUDA-core fp32 otherwise
+static int gemm(const Engine& e, const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr,
+                float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s) {
+    if (e.use_tc && !a.conv && gemm_tc_supported(a.ptr, a.lda, w, m, n, k, c, ldc, residual, ldr))
+        return launch_gemm_tc(a.ptr, a.lda, w, bias, residual, ldr, c, ldc, m, n, k, act, s);
+    return launch_gemm_nt(a, w, bias, residual, ldr, c, ldc, m, n, k, act, s);
+}
+
+static int run_heads(const Engine& e, const HeadW& h, const float* feat, int feat_dim, int n_heads, int64_t n, float* f1, float* f2,
                      float* logits, cudaStream_t s) {
     // fc1 -> SELU -> per-head fc2 -> SELU -> fc3 -> SELU  (clairs/model.py:239-253)
-    RUN(launch_gemm_nt(plain_a(feat, feat_dim), h.fc1_w, h.fc1_b, nullptr, 0, f1, FC_DIM, n, FC_DIM, feat_dim, ACT_SELU, s));
-    RUN(launch_gemm_nt(plain_a(f1, FC_DIM), h.fc2_w, h.fc2_b, nullptr, 0, f2, (int64_t)n_heads * FC_DIM, n,
+    RUN(gemm(e, plain_a(feat, feat_dim), h.fc1_w, h.fc1_b, nullptr, 0, f1, FC_DIM, n, FC_DIM, feat_dim, ACT_SELU, s));
+    RUN(gemm(e, plain_a(f1, FC_DIM), h.fc2_w, h.fc2_b, nullptr, 0, f2, (int64_t)n_heads * FC_DIM, n,
                        n_heads * FC_DIM, FC_DIM, ACT_SELU, s));
     RUN(launch_head_fc3(f2, h.fc3_w, h.fc3_b, logits, n, n_heads, s));
     return 0;
@@ -250,7 +258,7 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         const int c = st.c, inner = st.heads * DIM_HEAD;
         const int64_t rows = n * st.wout, rows_kv = n * st.wkv;
         // embed conv (3-tap, stride 2, pad 1) + channel LN  (clairs/model.py:195-196)
-        RUN(launch_gemm_nt(conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows, c,
+        RUN(gemm(e, conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows, c,
                            3 * st.cin, ACT_NONE, s));
         RUN(launch_channel_ln(e.a_t0, st.ln_g, st.ln_b, e.a_xs, rows, c, s));
         for (int d = 0; d < st.depth; ++d) {
@@ -259,20 +267,20 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
             RUN(launch_channel_ln(e.a_xs, L.ln1_g, L.ln1_b, e.a_y, rows, c, s));
             RUN(launch_dwconv3(e.a_y, L.q_dw, e.a_dq, n, st.wout, st.wout, 1, c, s));
             RUN(launch_dwconv3(e.a_y, L.kv_dw, e.a_dkv, n, st.wout, st.wkv, 2, c, s));
-            RUN(launch_gemm_nt(plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c, ACT_NONE, s));
-            RUN(launch_gemm_nt(plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv, 2 * inner, c,
+            RUN(gemm(e, plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c, ACT_NONE, s));
+            RUN(gemm(e, plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv, 2 * inner, c,
                                ACT_NONE, s));
             RUN(launch_attention(e.a_q, e.a_kv, e.a_att, n, st.wout, st.wkv, st.heads, s));
-            RUN(launch_gemm_nt(plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner, ACT_NONE, s));
+            RUN(gemm(e, plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner, ACT_NONE, s));
             // x = FF(LN(x)) + x          (clairs/model.py:146)
             RUN(launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, e.a_y, rows, c, s));
-            RUN(launch_gemm_nt(plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
-            RUN(launch_gemm_nt(plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c, ACT_NONE, s));
+            RUN(gemm(e, plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
+            RUN(gemm(e, plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c, ACT_NONE, s));
         }
         // the next stage reads a_xs while writing a_t0, so no copy is needed
         cur = e.a_xs;
     }
-    RUN(run_heads(m.head, cur, m.feat, m.n_heads, n, e.f1, e.f2, logits, s));
+    RUN(run_heads(e, m.head, cur, m.feat, m.n_heads, n, e.f1, e.f2, logits, s));
     return prof_end(e, s);
 }
 
@@ -285,7 +293,7 @@ int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         const GruLayerW& g = m.l[l];
         const int h = g.hidden;
         RUN(prof_begin(e, l ? PK_NEG_PROJ2 : PK_NEG_PROJ1, s));
-        RUN(launch_gemm_nt(plain_a(cur, g.in_dim), g.wih, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS, 6 * h, g.in_dim,
+        RUN(gemm(e, plain_a(cur, g.in_dim), g.wih, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS, 6 * h, g.in_dim,
                            ACT_NONE, s));
         RUN(prof_end(e, s));
         RUN(prof_begin(e, l ? PK_NEG_GRU2 : PK_NEG_GRU1, s));
@@ -296,10 +304,10 @@ int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
     const int feat = N_POS * 2 * m.l[1].hidden;
     const HeadW& hd = m.head;
     RUN(prof_begin(e, PK_NEG_FC1, s));
-    RUN(launch_gemm_nt(plain_a(cur, feat), hd.fc1_w, hd.fc1_b, nullptr, 0, e.f1n, FC_DIM, n, FC_DIM, feat, ACT_SELU, s));
+    RUN(gemm(e, plain_a(cur, feat), hd.fc1_w, hd.fc1_b, nullptr, 0, e.f1n, FC_DIM, n, FC_DIM, feat, ACT_SELU, s));
     RUN(prof_end(e, s));
     RUN(prof_begin(e, PK_NEG_HEADS, s));
-    RUN(launch_gemm_nt(plain_a(e.f1n, FC_DIM), hd.fc2_w, hd.fc2_b, nullptr, 0, e.f2n, (int64_t)m.n_heads * FC_DIM, n,
+    RUN(gemm(e, plain_a(e.f1n, FC_DIM), hd.fc2_w, hd.fc2_b, nullptr, 0, e.f2n, (int64_t)m.n_heads * FC_DIM, n,
                        m.n_heads * FC_DIM, FC_DIM, ACT_SELU, s));
     RUN(launch_head_fc3(e.f2n, hd.fc3_w, hd.fc3_b, logits, n, m.n_heads, s));
     return prof_end(e, s);

@@ -61,6 +61,7 @@ struct Engine {
     double* tables = nullptr;                                  // likelihood tables, n_heads * 122
     int table_heads = 0;
     std::vector<void*> allocs;
+    bool use_tc = false;                                       // dense contractions on tcgen05 (TF32) where shapes allow
     // optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
     bool profile = false;
     struct ProfRec { int kind; cudaEvent_t start, stop; };

@@ -23,6 +23,12 @@ static inline AView conv_a(const float* p, int win, int wout, int cin) { return 
 int launch_gemm_nt(const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr,
                    float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s);
 
+// tcgen05 TF32 path (gemm_tc.cu); plain row-major A only
+bool gemm_tc_supported(const float* a, int64_t lda, const float* w, int64_t m, int n, int k, const float* c, int64_t ldc,
+                       const float* residual, int64_t ldr);
+int launch_gemm_tc(const float* a, int64_t lda, const float* w, const float* bias, const float* residual, int64_t ldr,
+                   float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s);
+
 int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, cudaStream_t s);
 int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s);
 int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch, int win, int wout, int stride,

@@ -92,6 +92,10 @@ class Engine:
         except Exception:
             pass
 
+    def set_tensor_cores(self, enable: bool):
+        """TF32 tcgen05 contractions (default) or the exact fp32 CUDA-core kernels everywhere."""
+        _lib.check(self.lib.cto_engine_set_tensor_cores(self.handle, 1 if enable else 0), "set_tensor_cores")
+
     def set_likelihood(self, path_or_array):
         tables = np.ascontiguousarray(likelihood_tables(path_or_array, self.n_heads))
         _lib.check(self.lib.cto_engine_set_likelihood(self.handle, _ptr(tables), self.n_heads), "set_likelihood")
@@ -201,3 +205,18 @@ class Engine:
                                                _ptr(out.get('call')), _ptr(out.get('tensor_aff')),
                                                _ptr(out.get('tensor_neg')), _stream_ptr()), "cto_run_sites_host")
         return out
+
+
+def gemm_nt(a, w, bias=None, residual=None, act=0, tensor_cores=True):
+    """C = act(A @ W^T + bias) (+ residual) through ``cto_gemm_nt``: the dense-contraction building
+    block of both networks, on tcgen05 (TF32) or on the fp32 CUDA-core kernel."""
+    lib = _lib.lib()
+    assert a.is_cuda and a.dtype == torch.float32 and w.dtype == torch.float32
+    m, k = a.shape
+    n = w.shape[0]
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    assert a.stride(1) == 1 and w.is_contiguous()
+    _lib.check(lib.cto_gemm_nt(C.c_void_p(a.data_ptr()), a.stride(0), _ptr(w), _ptr(bias), _ptr(residual),
+                               residual.stride(0) if residual is not None else 0, _ptr(c), n, m, n, k, int(act),
+                               1 if tensor_cores else 0, _stream_ptr()), "cto_gemm_nt")
+    return c

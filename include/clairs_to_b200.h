@@ -90,6 +90,17 @@ int cto_softmax_posterior(cto_engine* e, const float* logits_aff_dev, const floa
                           float* probs_dev, double* post_dev, int32_t* call_dev, void* stream);
 
 /*
+ * Dense contractions run on tcgen05 tensor cores as TF32 (fp32 accumulate) by default; enable = 0
+ * forces the exact fp32 CUDA-core kernels everywhere (used by the parity tests to separate
+ * layout bugs from TF32 rounding).  cto_gemm_nt exposes the building block itself:
+ * C[m,n] = act(A[m,k] * W[n,k]^T + bias) (+ residual), act 0 none / 1 GELU(erf) / 2 SELU.
+ */
+int cto_engine_set_tensor_cores(cto_engine* e, int enable);
+int cto_gemm_nt(const float* a_dev, int64_t lda, const float* w_dev, const float* bias_dev, const float* residual_dev,
+                int64_t ldr, float* c_dev, int64_t ldc, int64_t m, int n, int k, int act, int use_tensor_cores,
+                void* stream);
+
+/*
  * Instrumentation for bench.py: kernels launched by this library so far in this process, and
  * optional CUDA-event timing of the kernel families of the forward passes (events are recorded
  * on the launching stream; cto_engine_profile_read synchronises and returns, per family, the

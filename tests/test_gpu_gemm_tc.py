@@ -1,0 +1,56 @@
+"""GPU: the tcgen05 TF32 GEMM (csrc/gemm_tc.cu) against an fp64 torch reference and against the
+fp32 CUDA-core GEMM it replaces.  Floating point: TF32 keeps 10 mantissa bits per operand, so the
+bound is relative to sum |a||w| (stated below), the CUDA-core path is held to fp32 rounding."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (M, N, K) taken from the two networks plus tails
+    (300, 128, 64), (1000, 1152, 256), (256, 16, 64), (130, 64, 16), (515, 128, 12672),
+    (2 * 33 * 128, 768, 256), (45, 512, 128), (128, 192, 64), (77, 384, 64), (640, 256, 128),
+]
+
+
+def _act(x, act):
+    if act == 1:
+        return torch.nn.functional.gelu(x)
+    if act == 2:
+        return torch.nn.functional.selu(x)
+    return x
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_tf32_vs_fp64(m, n, k, act):
+    from clairs_to_b200.engine import gemm_nt
+    g = torch.Generator(device="cpu").manual_seed(m * 7 + n * 3 + k + act)
+    a = torch.randn(m, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) / np.sqrt(k)).cuda()
+    bias = torch.randn(n, generator=g).cuda()
+    res = torch.randn(m, n, generator=g).cuda() if act == 0 else None
+    want = _act(a.double() @ w.double().t() + bias.double(), act)
+    if res is not None:
+        want = want + res.double()
+    scale = (a.double().abs() @ w.double().abs().t()).max().item()
+    exact = gemm_nt(a, w, bias, res, act, tensor_cores=False)
+    assert (exact.double() - want).abs().max().item() < 1e-5 * max(scale, 1.0)
+    got = gemm_nt(a, w, bias, res, act, tensor_cores=True)
+    err = (got.double() - want).abs().max().item()
+    # two TF32 operands: 2 * 2^-11 relative per product, worst case all aligned
+    assert err < 1.2e-3 * scale, (err, scale)
+    assert torch.isfinite(got).all()
+
+
+def test_gemm_tf32_strided_a_and_inplace_residual():
+    from clairs_to_b200.engine import gemm_nt
+    g = torch.Generator(device="cpu").manual_seed(1)
+    big = torch.randn(500, 96, generator=g).cuda()
+    a = big[:, :64]                                   # lda = 96
+    w = (torch.randn(64, 64, generator=g) / 8).cuda()
+    res = torch.randn(500, 64, generator=g).cuda()
+    want = a.double() @ w.double().t() + res.double()
+    got = gemm_nt(a, w, None, res, 0, tensor_cores=True)
+    assert (got.double() - want).abs().max().item() < 5e-3
