@@ -119,6 +119,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=300, help="CPU baseline: candidates per host process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: allow fewer warm-up steps "
+                                                       "(numbers printed in this mode are NOT bench values)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -127,7 +129,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if args.warmup < 3:
+    if args.warmup < 3 and not args.ncu:
         args.warmup = 3
 
     import numpy as np

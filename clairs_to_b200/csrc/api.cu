@@ -149,7 +149,7 @@ int cto_engine_set_likelihood(cto_engine* h, const double* tables, int n_heads) 
 }
 
 int cto_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, void* stream) {
-    return launch_rescale(x, depth, n, out, (cudaStream_t)stream);
+    return launch_rescale(x, depth, n, out, N_CH, (cudaStream_t)stream);
 }
 
 int cto_forward_aff(cto_engine* h, const float* x, int64_t n, float* logits, void* stream) {
@@ -167,7 +167,9 @@ int cto_forward_neg(cto_engine* h, const float* x, int64_t n, float* logits, voi
     const int nh = h->e.neg.n_heads;
     for (int64_t o = 0; o < n; o += h->e.max_batch) {
         const int64_t nb = std::min(h->e.max_batch, n - o);
-        if (int rc = neg_forward(h->e, x + o * N_POS * N_CH, nb, logits + o * nh * 2, (cudaStream_t)stream)) return rc;
+        if (int rc = launch_pad_rows(x + o * N_POS * N_CH, nb * N_POS, N_CH, h->e.x_neg, NEG_IN_LD, (cudaStream_t)stream))
+            return rc;
+        if (int rc = neg_forward(h->e, h->e.x_neg, nb, logits + o * nh * 2, (cudaStream_t)stream)) return rc;
     }
     return 0;
 }
@@ -190,8 +192,18 @@ int cto_engine_set_tensor_cores(cto_engine* h, int enable) {
 
 int cto_gemm_nt(const float* a, int64_t lda, const float* w, const float* bias, const float* residual, int64_t ldr,
                 float* c, int64_t ldc, int64_t m, int n, int k, int act, int use_tensor_cores, void* stream) {
-    if (use_tensor_cores)
-        return launch_gemm_tc(a, lda, w, bias, residual, ldr, c, ldc, m, n, k, act, (cudaStream_t)stream);
+    if (use_tensor_cores) {
+        // split the weights on the fly (the engine does this once at load time)
+        float *hi = nullptr, *lo = nullptr;
+        cudaStream_t s = (cudaStream_t)stream;
+        CTO_CHECK(cudaMallocAsync((void**)&hi, sizeof(float) * (size_t)n * k, s));
+        CTO_CHECK(cudaMallocAsync((void**)&lo, sizeof(float) * (size_t)n * k, s));
+        int rc = launch_split_tf32(w, hi, lo, (int64_t)n * k, s);
+        if (!rc) rc = launch_gemm_tc(a, lda, hi, lo, bias, residual, ldr, c, ldc, m, n, k, act, s);
+        cudaFreeAsync(hi, s);
+        cudaFreeAsync(lo, s);
+        return rc;
+    }
     return launch_gemm_nt(plain_a(a, lda), w, bias, residual, ldr, c, ldc, m, n, k, act, (cudaStream_t)stream);
 }
 
@@ -229,9 +241,9 @@ int cto_predict(cto_engine* h, const int16_t* x_aff, const int32_t* depth_aff, c
     for (int64_t o = 0; o < n; o += e.max_batch) {
         const int64_t nb = std::min(e.max_batch, n - o);
         // both networks saturate the GPU on their own, so they run back to back on the caller's stream
-        if (int rc = launch_rescale(x_neg + o * xin, depth_neg + o, nb, e.x_neg, s)) return rc;
+        if (int rc = launch_rescale(x_neg + o * xin, depth_neg + o, nb, e.x_neg, NEG_IN_LD, s)) return rc;
         if (int rc = neg_forward(e, e.x_neg, nb, logits_neg + o * nh * 2, s)) return rc;
-        if (int rc = launch_rescale(x_aff + o * xin, depth_aff + o, nb, e.x_aff, s)) return rc;
+        if (int rc = launch_rescale(x_aff + o * xin, depth_aff + o, nb, e.x_aff, N_CH, s)) return rc;
         if (int rc = aff_forward(e, e.x_aff, nb, logits_aff + o * nh * 2, s)) return rc;
     }
     if (fwd && rev)

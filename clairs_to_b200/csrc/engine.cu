@@ -17,10 +17,22 @@ struct Walker {
     }
 };
 
-int upload(const float* host, int64_t n, float** dev) {
-    CTO_CHECK(cudaMalloc(dev, sizeof(float) * n));
-    CTO_CHECK(cudaMemcpy(*dev, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+int upload(const float* host, int64_t n, WeightSet& ws) {
+    ws.n = n;
+    CTO_CHECK(cudaMalloc(&ws.blob, sizeof(float) * n));
+    CTO_CHECK(cudaMalloc(&ws.hi, sizeof(float) * n));
+    CTO_CHECK(cudaMalloc(&ws.lo, sizeof(float) * n));
+    CTO_CHECK(cudaMemcpy(ws.blob, host, sizeof(float) * n, cudaMemcpyHostToDevice));
+    if (int rc = launch_split_tf32(ws.blob, ws.hi, ws.lo, n, nullptr)) return rc;
+    CTO_CHECK(cudaDeviceSynchronize());
     return 0;
+}
+
+void release(WeightSet& ws) {
+    if (ws.blob) cudaFree(ws.blob);
+    if (ws.hi) cudaFree(ws.hi);
+    if (ws.lo) cudaFree(ws.lo);
+    ws = WeightSet();
 }
 
 void walk_head(Walker& w, HeadW& h, int feat, int n_heads) {
@@ -39,8 +51,8 @@ int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
     m.n_stages = cfg[1];
     CTO_REQUIRE(m.n_stages >= 1 && m.n_stages <= 3, "aff cfg: %d stages unsupported", m.n_stages);
     CTO_REQUIRE(m.n_heads == 4 || m.n_heads == 6, "aff cfg: %d heads (expected 4 or 6)", m.n_heads);
-    if (upload(host_blob, n, &m.blob)) return 1;
-    Walker w{m.blob, 0, n};
+    if (upload(host_blob, n, m.ws)) return 1;
+    Walker w{m.ws.blob, 0, n};
     int cin = N_CH, win = N_POS;
     for (int s = 0; s < m.n_stages; ++s) {
         CvtStage& st = m.st[s];
@@ -96,8 +108,8 @@ int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
     m.n_heads = cfg[0];
     CTO_REQUIRE(m.n_heads == 4 || m.n_heads == 6, "neg cfg: %d heads (expected 4 or 6)", m.n_heads);
     CTO_REQUIRE(cfg[1] == N_CH, "neg cfg: input dim %d != %d", cfg[1], N_CH);
-    if (upload(host_blob, n, &m.blob)) return 1;
-    Walker w{m.blob, 0, n};
+    if (upload(host_blob, n, m.ws)) return 1;
+    Walker w{m.ws.blob, 0, n};
     int in_dim = cfg[1];
     for (int l = 0; l < 2; ++l) {
         GruLayerW& g = m.l[l];
@@ -112,6 +124,29 @@ int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
     }
     walk_head(w, m.head, N_POS * in_dim, m.n_heads);
     CTO_REQUIRE(w.off == n, "neg blob: %lld floats given, layout needs %lld", (long long)n, (long long)w.off);
+    {   // K-padded copy of the layer-1 input projection
+        const int rows = 6 * m.l[0].hidden, k = m.l[0].in_dim;
+        std::vector<float> pad((size_t)rows * NEG_IN_LD, 0.0f);
+        const float* src = host_blob + (m.l[0].wih - m.ws.blob);
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < k; ++c) pad[(size_t)r * NEG_IN_LD + c] = src[(size_t)r * k + c];
+        if (upload(pad.data(), (int64_t)pad.size(), m.wih1_pad)) return 1;
+    }
+    for (int l = 0; l < 2; ++l) {   // W_hh rows regrouped as (32-unit block, gate, unit) for the tensor-core recurrence
+        const int h = m.l[l].hidden;
+        if (h % 64 != 0) continue;
+        const float* wt = host_blob + (m.l[l].whh_t - m.ws.blob);      // [2][H (k)][3H (gate*H + unit)]
+        std::vector<float> blk((size_t)2 * 3 * h * h);
+        for (int d = 0; d < 2; ++d)
+            for (int b = 0; b < h / 32; ++b)
+                for (int g = 0; g < 3; ++g)
+                    for (int j = 0; j < 32; ++j) {
+                        const int row = b * 96 + g * 32 + j, col = g * h + b * 32 + j;
+                        for (int k = 0; k < h; ++k)
+                            blk[((size_t)d * 3 * h + row) * h + k] = wt[((size_t)d * h + k) * 3 * h + col];
+                    }
+        if (upload(blk.data(), (int64_t)blk.size(), m.whh_blk[l])) return 1;
+    }
     return 0;
 }
 
@@ -133,7 +168,7 @@ int engine_alloc(Engine& e, int64_t max_batch) {
     const int64_t xin = (int64_t)N_POS * N_CH;
     int rc = 0;
     rc |= dev_alloc(e, &e.x_aff, b * xin);
-    rc |= dev_alloc(e, &e.x_neg, b * xin);
+    rc |= dev_alloc(e, &e.x_neg, b * N_POS * NEG_IN_LD);
     rc |= dev_alloc(e, &e.a_t0, b * a.sz_x);
     rc |= dev_alloc(e, &e.a_xs, b * a.sz_x);
     rc |= dev_alloc(e, &e.a_y, b * a.sz_x);
@@ -158,8 +193,11 @@ int engine_alloc(Engine& e, int64_t max_batch) {
 void engine_free(Engine& e) {
     for (void* p : e.allocs) cudaFree(p);
     e.allocs.clear();
-    if (e.aff.blob) cudaFree(e.aff.blob);
-    if (e.neg.blob) cudaFree(e.neg.blob);
+    release(e.aff.ws);
+    release(e.neg.ws);
+    release(e.neg.wih1_pad);
+    release(e.neg.whh_blk[0]);
+    release(e.neg.whh_blk[1]);
     if (e.tables) cudaFree(e.tables);
     for (auto& r : e.prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
     for (cudaEvent_t ev : e.ev_free) cudaEventDestroy(ev);
@@ -233,8 +271,13 @@ int prof_collect(Engine& e, double* ms, int64_t* count) {
 // dense contraction: tcgen05 TF32 when the engine allows it and the shape fits, CUDA-core fp32 otherwise
 static int gemm(const Engine& e, const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr,
                 float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s) {
-    if (e.use_tc && !a.conv && gemm_tc_supported(a.ptr, a.lda, w, m, n, k, c, ldc, residual, ldr))
-        return launch_gemm_tc(a.ptr, a.lda, w, bias, residual, ldr, c, ldc, m, n, k, act, s);
+    if (e.use_tc && !a.conv && gemm_tc_supported(a.ptr, a.lda, w, m, n, k, c, ldc, residual, ldr)) {
+        const WeightSet* ws = e.aff.ws.owns(w) ? &e.aff.ws : (e.neg.ws.owns(w) ? &e.neg.ws : nullptr);
+        if (ws) {
+            const int64_t off = w - ws->blob;
+            return launch_gemm_tc(a.ptr, a.lda, ws->hi + off, ws->lo + off, bias, residual, ldr, c, ldc, m, n, k, act, s);
+        }
+    }
     return launch_gemm_nt(a, w, bias, residual, ldr, c, ldc, m, n, k, act, s);
 }
 
@@ -293,11 +336,21 @@ int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         const GruLayerW& g = m.l[l];
         const int h = g.hidden;
         RUN(prof_begin(e, l ? PK_NEG_PROJ2 : PK_NEG_PROJ1, s));
-        RUN(gemm(e, plain_a(cur, g.in_dim), g.wih, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS, 6 * h, g.in_dim,
-                           ACT_NONE, s));
+        if (l == 0 && e.use_tc) {
+            // x rows are padded to NEG_IN_LD floats; the zero-padded W_ih copy makes K = NEG_IN_LD exact
+            RUN(launch_gemm_tc(cur, NEG_IN_LD, m.wih1_pad.hi, m.wih1_pad.lo, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS,
+                               6 * h, NEG_IN_LD, ACT_NONE, s));
+        } else {
+            RUN(gemm(e, plain_a(cur, l == 0 ? NEG_IN_LD : g.in_dim), g.wih, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS,
+                     6 * h, g.in_dim, ACT_NONE, s));
+        }
         RUN(prof_end(e, s));
         RUN(prof_begin(e, l ? PK_NEG_GRU2 : PK_NEG_GRU1, s));
-        RUN(launch_gru_recurrent(e.n_xp, g.whh_t, g.bhn, outs[l], n, h, s));
+        if (e.use_tc && m.whh_blk[l].hi) {
+            RUN(launch_gru_tc(e.n_xp, m.whh_blk[l].hi, m.whh_blk[l].lo, g.bhn, outs[l], n, h, s));
+        } else {
+            RUN(launch_gru_recurrent(e.n_xp, g.whh_t, g.bhn, outs[l], n, h, s));
+        }
         RUN(prof_end(e, s));
         cur = outs[l];
     }

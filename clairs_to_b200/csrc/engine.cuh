@@ -26,11 +26,20 @@ struct HeadW {
     const float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
 };
 
+constexpr int NEG_IN_LD = 36;      // NEG input rows are padded 34 -> 36 floats (16-byte row stride for TMA)
+
+// fp32 weights plus their TF32 hi / lo split (same offsets in all three blobs)
+struct WeightSet {
+    float *blob = nullptr, *hi = nullptr, *lo = nullptr;
+    int64_t n = 0;
+    bool owns(const float* w) const { return w >= blob && w < blob + n; }
+};
+
 struct AffModel {
     int n_heads = 0, n_stages = 0, feat = 0;
     CvtStage st[3];
     HeadW head;
-    float* blob = nullptr;
+    WeightSet ws;
     // per-candidate workspace sizes (floats)
     int64_t sz_x = 0, sz_kvin = 0, sz_q = 0, sz_kv = 0, sz_ff = 0;
 };
@@ -44,7 +53,9 @@ struct NegModel {
     int n_heads = 0;
     GruLayerW l[2];
     HeadW head;
-    float* blob = nullptr;
+    WeightSet ws;
+    WeightSet wih1_pad;        // layer-1 W_ih with K padded 34 -> NEG_IN_LD (zeros), for the tensor-core path
+    WeightSet whh_blk[2];      // per layer: W_hh [2 dirs][unit block (32) x gate x unit][H], for gru_tc.cu
 };
 
 struct Engine {
@@ -52,7 +63,7 @@ struct Engine {
     NegModel neg;
     int64_t max_batch = 0;
     // workspace (device, fp32)
-    float *x_aff = nullptr, *x_neg = nullptr;                  // rescaled network inputs [chunk, 33, 34]
+    float *x_aff = nullptr, *x_neg = nullptr;                  // rescaled inputs: AFF [chunk,33,34], NEG [chunk,33,NEG_IN_LD]
     float *a_t0 = nullptr, *a_xs = nullptr, *a_y = nullptr, *a_dq = nullptr, *a_dkv = nullptr;
     float *a_q = nullptr, *a_kv = nullptr, *a_att = nullptr, *a_ff = nullptr;
     float *n_xp = nullptr, *n_o1 = nullptr, *n_o2 = nullptr;
@@ -61,7 +72,7 @@ struct Engine {
     double* tables = nullptr;                                  // likelihood tables, n_heads * 122
     int table_heads = 0;
     std::vector<void*> allocs;
-    bool use_tc = false;                                       // dense contractions on tcgen05 (TF32) where shapes allow
+    bool use_tc = true;                                        // dense contractions on tcgen05 (TF32) where shapes allow
     // optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
     bool profile = false;
     struct ProfRec { int kind; cudaEvent_t start, stop; };
@@ -82,7 +93,8 @@ int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
 int engine_alloc(Engine& e, int64_t max_batch);
 void engine_free(Engine& e);
 
-// x: device fp32 [n, 33, 34]; logits: device fp32 [n, n_heads, 2]; n <= max_batch
+// aff: x device fp32 [n, 33, 34]; neg: x device fp32 [n, 33, NEG_IN_LD] (zero padded);
+// logits: device fp32 [n, n_heads, 2]; n <= max_batch
 int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
 int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
 

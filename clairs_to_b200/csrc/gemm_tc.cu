@@ -1,15 +1,23 @@
-// tcgen05 (5th-gen tensor core) TF32 GEMM for sm_100a:  C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual)
+// tcgen05 (5th-gen tensor core) GEMM for sm_100a with fp32-grade accuracy ("3xTF32"):
 //
-// Both operands are K-major fp32 in global memory and are consumed as TF32 (fp32 accumulate in TMEM):
-//   - a TMA producer warp streams 128 x 32 (A) and BN x 32 (W) fp32 boxes into a multi-stage
-//     shared-memory ring with the 128-byte swizzle the UMMA descriptors expect;
-//   - one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) four times per stage and
-//     releases the stage with tcgen05.commit;
-//   - four epilogue warps read the accumulator with tcgen05.ld (one TMEM lane = one output row),
-//     apply bias / GELU / SELU / residual in fp32 and store rows with 16-byte stores.
-// Used for the dense contractions of the hot path: GRU input projections and fc1 (clairs/model.py:
-// 412-420), the CvT 1x1 convolutions and heads (ibid. 78-118, 214-224).  K and M tails are
-// zero-filled by TMA; N must be a multiple of BN (16, 64 or 128).
+//     C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual)
+//
+// Plain TF32 (10 mantissa bits per operand) moves the AFF/NEG logits by up to 1e-2, ten times the
+// parity contract, so every operand is split into an exactly representable TF32 "hi" part and a
+// "lo" remainder and three MMAs are accumulated per k-step in fp32 TMEM:  hi*hi + lo*hi + hi*lo.
+// Weights are split once at load time (W_hi, W_lo in HBM); activations are split on the fly.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer: A (128x32 fp32), W_hi, W_lo (BN x 32) boxes -> 3-stage smem ring,
+//               128-byte swizzle as the UMMA descriptors expect
+//   warps 2-5   converter: A -> A_hi (in place) + A_lo (second buffer), fence to the async proxy
+//   warp 1      MMA issuer (one elected thread): tcgen05.mma.kind::tf32, M=128, N=BN, K=8;
+//               tcgen05.commit releases smem stages and publishes the accumulator
+//   warps 6-9   epilogue: tcgen05.ld (one TMEM lane = one output row), bias / GELU / SELU /
+//               residual in fp32, swizzled staging in smem, TMA store (full 128-byte lines,
+//               M tail clipped by the tensor map)
+// The accumulator is double buffered in TMEM (2 x 128 columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.  K and M tails are zero-filled by TMA; N must be a multiple of 64.
 #include "nn_kernels.cuh"
 #include <cuda.h>
 
@@ -20,10 +28,13 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                       // fp32 elements = one 128-byte swizzle row
 constexpr int MAX_BN = 128;
-constexpr int A_BYTES = BM * BK * 4;         // 16 KB
-constexpr int W_BYTES = MAX_BN * BK * 4;     // 16 KB
-constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-constexpr int THREADS = 192;                 // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB (A, A_lo; W tiles use BN*128 bytes of theirs)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A | A_lo | W_hi | W_lo
+constexpr int STAGES = 3;
+constexpr int SLAB = 32;                     // epilogue works on 128 x 32 fp32 slabs
+constexpr int STAGING_BYTES = BM * SLAB * 4; // 16 KB, two of them
+constexpr int THREADS = 320;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGING_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -32,6 +43,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -49,6 +63,10 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -59,6 +77,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
 }
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row groups
@@ -85,91 +108,151 @@ __device__ __forceinline__ float selu(float x) {
     return scale * (x > 0.0f ? x : alpha * expm1f(x));
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(THREADS)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-                 const float* __restrict__ bias, const float* residual, int64_t ldr, float* c, int64_t ldc,
-                 int64_t m_total, int k_total, int bn, int act) {
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_whi,
+                   const __grid_constant__ CUtensorMap tma_wlo, const __grid_constant__ CUtensorMap tma_c,
+                   const float* __restrict__ bias, const float* residual, int64_t ldr, int64_t m_total, int n_total,
+                   int k_total, int bn, int act) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
+    uint8_t* staging = base + STAGES * STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(staging + 2 * STAGING_BYTES);
+    uint64_t* conv = full + STAGES;
+    uint64_t* empty = conv + STAGES;
     uint64_t* acc_full = empty + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.x * BM;
-    const int n0 = blockIdx.y * bn;
     const int num_kb = (k_total + BK - 1) / BK;
-    const uint32_t tmem_cols = bn <= 32 ? 32 : (bn <= 64 ? 64 : 128);
+    const int n_tiles = n_total / bn;
+    const int64_t m_tiles = (m_total + BM - 1) / BM;
+    const int64_t num_tiles = m_tiles * n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(acc_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {                                   // ---- TMA producer ----
-            const uint32_t tx = (uint32_t)(BM + bn) * BK * 4;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], tx);
-                uint8_t* st = base + s * STAGE_BYTES;
-                tma_load_2d(&tma_a, &full[s], st, kb * BK, (int)m0);
-                tma_load_2d(&tma_w, &full[s], st + A_BYTES, kb * BK, n0);
+            const uint32_t tx = (uint32_t)(BM + 2 * bn) * BK * 4;
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * bn;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], tx);
+                    uint8_t* st = base + s * STAGE_BYTES;
+                    tma_load_2d(&tma_a, &full[s], st, kb * BK, m0);
+                    tma_load_2d(&tma_whi, &full[s], st + 2 * TILE_BYTES, kb * BK, n0);
+                    tma_load_2d(&tma_wlo, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                   // ---- MMA issuer ----
             const uint32_t idesc = make_idesc_tf32(bn);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            uint32_t it = 0, acc_it = 0;
+            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
+                const uint32_t ab = acc_it & 1, aph = (acc_it >> 1) & 1;
+                mbar_wait(&acc_empty[ab], aph ^ 1);        // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(base + s * STAGE_BYTES);
-                const uint64_t da = make_desc_k_sw128(a_addr);
-                const uint64_t dw = make_desc_k_sw128(a_addr + A_BYTES);
-                #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    // advance 8 tf32 = 32 bytes inside the swizzle row: +2 in the (>>4) address field
-                    mma_tf32(tmem_acc, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                const uint32_t acc = tmem_base + ab * MAX_BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);               // W tiles landed
+                    mbar_wait(&conv[s], ph);               // A split into hi / lo
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(base + s * STAGE_BYTES);
+                    const uint64_t d_ahi = make_desc_k_sw128(a_addr);
+                    const uint64_t d_alo = make_desc_k_sw128(a_addr + TILE_BYTES);
+                    const uint64_t d_whi = make_desc_k_sw128(a_addr + 2 * TILE_BYTES);
+                    const uint64_t d_wlo = make_desc_k_sw128(a_addr + 3 * TILE_BYTES);
+                    #pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        // 8 tf32 = 32 bytes along the swizzle row: +2 in the (>>4) start-address field
+                        const uint64_t o = (uint64_t)(k * 2);
+                        mma_tf32(acc, d_ahi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
+                        mma_tf32(acc, d_alo + o, d_whi + o, idesc, 1u);
+                        mma_tf32(acc, d_ahi + o, d_wlo + o, idesc, 1u);
+                    }
+                    tcgen05_commit(&empty[s]);             // stage reusable once these MMAs retire
                 }
-                tcgen05_commit(&empty[s]);                 // stage reusable once these MMAs retire
+                tcgen05_commit(&acc_full[ab]);             // accumulator complete
             }
-            tcgen05_commit(acc_full);                      // accumulator complete
         }
-    } else {                                               // ---- epilogue: warps 2..5 ----
-        const int quad = warp & 3;                         // TMEM lanes [32*quad, 32*quad+32)
-        const int64_t row = m0 + quad * 32 + lane;
-        mbar_wait(acc_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool row_ok = row < m_total;
-        float* crow = c + row * ldc + n0;
-        const float* rrow = residual ? residual + row * ldr + n0 : nullptr;
-        for (int cb = 0; cb < bn; cb += 16) {
-            uint32_t r[16];
-            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row_ok) {
+    } else if (warp < 6) {                                 // ---- converter: warps 2..5 ----
+        const int ct = threadIdx.x - 64;                   // 0..127
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                float4* a_hi = reinterpret_cast<float4*>(base + s * STAGE_BYTES);
+                float4* a_lo = reinterpret_cast<float4*>(base + s * STAGE_BYTES + TILE_BYTES);
                 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {       // elementwise: the swizzle is irrelevant
+                    const int idx = ct + i * 128;
+                    const float4 v = a_hi[idx];
+                    float4 hi, lo;
+                    hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                    a_hi[idx] = hi;
+                    a_lo[idx] = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> UMMA reads
+                mbar_arrive(&conv[s]);
+            }
+        }
+    } else {                                               // ---- epilogue: warps 6..9 ----
+        const int quad = warp & 3;                         // TMEM lanes [32*quad, 32*quad+32)
+        const int et = threadIdx.x - 192;                  // 0..127
+        const int r_in_tile = quad * 32 + lane;
+        uint32_t acc_it = 0, slab_it = 0;
+        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
+            const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * bn;
+            const uint32_t ab = acc_it & 1, aph = (acc_it >> 1) & 1;
+            mbar_wait(&acc_full[ab], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t row = (int64_t)m0 + r_in_tile;
+            const bool row_ok = row < m_total;
+            for (int cb = 0; cb < bn; cb += SLAB, ++slab_it) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ab * MAX_BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cb + SLAB >= bn) {                     // accumulator fully read: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&acc_empty[ab]);
+                }
+                uint8_t* stg = staging + (slab_it & 1) * STAGING_BYTES;
+                // the TMA store that last read this staging buffer (two slabs ago) must have finished reading it
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const float* rrow = (residual && row_ok) ? residual + row * ldr + n0 + cb : nullptr;
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) {
                     float v[4];
                     #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -180,24 +263,40 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         v[e] = x;
                     }
                     if (rrow) {
-                        const float4 rv = *reinterpret_cast<const float4*>(rrow + cb + q * 4);
+                        const float4 rv = *reinterpret_cast<const float4*>(rrow + q * 4);
                         v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
                     }
-                    *reinterpret_cast<float4*>(crow + cb + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                    // 128-byte swizzle: 16-byte chunk q of row r lives at chunk (q ^ (r % 8))
+                    *reinterpret_cast<float4*>(stg + r_in_tile * 128 + ((q ^ (r_in_tile & 7)) << 4)) =
+                        make_float4(v[0], v[1], v[2], v[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    tma_store_2d(&tma_c, stg, n0 + cb, m0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
     }
 }
 
-constexpr int STAGES = 3;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+// fp32 -> exactly representable TF32 hi (round to nearest) + TF32 lo remainder
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = w[i];
+    const float h = round_tf32(v);
+    hi[i] = h;
+    lo[i] = round_tf32(v - h);
+}
 
 int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -216,9 +315,9 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
         CTO_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
         encode = reinterpret_cast<encode_fn>(fn);
     }
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides,
-                                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
                   (long long)cols, (long long)ld);
@@ -229,34 +328,48 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
 
 }  // namespace tc
 
+int launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    tc::split_tf32_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w, hi, lo, n);
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 bool gemm_tc_supported(const float* a, int64_t lda, const float* w, int64_t m, int n, int k, const float* c, int64_t ldc,
                        const float* residual, int64_t ldr) {
-    if (m <= 0 || n < 16 || n % 16 != 0 || k < 8) return false;
-    if (n > 16 && n % 64 != 0) return false;
+    if (m <= 0 || n < 64 || n % 64 != 0 || k < 8) return false;
     if (lda % 4 != 0 || k % 4 != 0 || ldc % 4 != 0 || (residual && ldr % 4 != 0)) return false;
+    if (m >= (1ll << 31) - tc::BM) return false;
     const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) |
                            reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(residual);
     return (bits & 15) == 0;
 }
 
-int launch_gemm_tc(const float* a, int64_t lda, const float* w, const float* bias, const float* residual, int64_t ldr,
-                   float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s) {
-    CTO_REQUIRE(gemm_tc_supported(a, lda, w, m, n, k, c, ldc, residual, ldr),
+int launch_gemm_tc(const float* a, int64_t lda, const float* w_hi, const float* w_lo, const float* bias,
+                   const float* residual, int64_t ldr, float* c, int64_t ldc, int64_t m, int n, int k, int act,
+                   cudaStream_t s) {
+    CTO_REQUIRE(gemm_tc_supported(a, lda, w_hi, m, n, k, c, ldc, residual, ldr) && w_lo &&
+                    (reinterpret_cast<uintptr_t>(w_lo) & 15) == 0,
                 "gemm_tc: unsupported shape/alignment m=%lld n=%d k=%d lda=%lld ldc=%lld", (long long)m, n, k,
                 (long long)lda, (long long)ldc);
-    const int bn = (n % 128 == 0) ? 128 : (n % 64 == 0 ? 64 : 16);
-    CUtensorMap map_a, map_w;
+    const int bn = (n % 128 == 0) ? 128 : 64;
+    CUtensorMap map_a, map_whi, map_wlo, map_c;
     if (tc::make_map(&map_a, a, m, k, lda, tc::BM)) return 1;
-    if (tc::make_map(&map_w, w, n, k, k, bn)) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_tf32_kernel<tc::STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       tc::SMEM_BYTES));
-        attr_set = true;
+    if (tc::make_map(&map_whi, w_hi, n, k, k, bn)) return 1;
+    if (tc::make_map(&map_wlo, w_lo, n, k, k, bn)) return 1;
+    if (tc::make_map(&map_c, c, m, n, ldc, tc::BM)) return 1;
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        CTO_CHECK(cudaGetDevice(&dev));
+        CTO_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     }
-    dim3 grid(ceil_div(m, tc::BM), n / bn);
-    tc::gemm_tf32_kernel<tc::STAGES><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_w, bias, residual, ldr, c, ldc,
-                                                                              m, k, bn, act);
+    const int64_t tiles = (int64_t)ceil_div(m, tc::BM) * (n / bn);
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    tc::gemm_3xtf32_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_whi, map_wlo, map_c, bias, residual, ldr,
+                                                                    m, n, k, bn, act);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

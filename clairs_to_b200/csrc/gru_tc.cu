@@ -1,0 +1,306 @@
+// GRU recurrence on tcgen05 tensor cores (sm_100a), fp32-grade accuracy via the 3xTF32 split.
+//
+// torch.nn.GRU semantics (clairs/model.py:412-417, 442-443), gate order r|z|n:
+//     r = sigmoid(xr + W_hr h)   z = sigmoid(xz + W_hz h)   n = tanh(xn + r * (W_hn h + b_hn))
+//     h' = (1 - z) * n + z * h
+// xproj = W_ih x + b_ih (+ b_hh for r,z) comes from the projection GEMM (gemm_tc.cu).
+//
+// One CTA = 64 candidates x one direction for all 33 steps:
+//   * h_{t-1} lives in shared memory as two K-major 128-byte-swizzled fp32 tiles (TF32 hi + lo), the
+//     A operand of the MMAs (M = 64);
+//   * W_hh (hi + lo, rows regrouped as blocks of 32 units x {r,z,n} = 96 rows) is streamed from L2
+//     by a TMA producer warp through a 5-stage ring every step;
+//   * one elected thread issues tcgen05.mma.kind::tf32 (M=64, N=96, K=8), three per k-step
+//     (hi*hi + lo*hi + hi*lo); the accumulators of ALL gate columns of the step stay in TMEM:
+//     unit block 2p sits in lanes 0-15 and block 2p+1 in lanes 16-31 of columns [96p, 96p+96);
+//   * four epilogue warps (one TMEM lane = one candidate x one unit block) read the gate
+//     pre-activations with tcgen05.ld, add xproj, apply the gate math in fp32, write h_t to HBM and
+//     the TF32 hi/lo split of h_t back into the shared-memory tiles for the next step.
+#include "nn_kernels.cuh"
+#include <cuda.h>
+
+namespace cto {
+
+namespace tc {
+// helpers shared with gemm_tc.cu (same translation-unit-local definitions)
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(g_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void g_tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(g_smem_u32(dst)), "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void g_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(g_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void g_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float g_round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint64_t g_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void g_tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+constexpr int GM = 64;                       // candidates per CTA (MMA M)
+constexpr int GBLK = 32;                     // hidden units per block
+constexpr int GN = 3 * GBLK;                 // 96 gate columns per block (MMA N)
+constexpr int GK = 32;                       // fp32 per swizzle row
+constexpr int G_HTILE = GM * 128;            // 8 KB: 64 rows x 128 bytes
+constexpr int G_WTILE = GN * 128;            // 12 KB
+constexpr int G_STAGE = 2 * G_WTILE;         // hi | lo
+constexpr int G_STAGES = 5;
+constexpr int G_THREADS = 192;
+
+template <int H>
+struct GruSmem {
+    static constexpr int KB = H / GK;        // k-blocks (and also unit blocks)
+    static constexpr int H_BYTES = 2 * KB * G_HTILE;
+    static constexpr int TOTAL = H_BYTES + G_STAGES * G_STAGE + 1024 + 256;
+};
+
+template <int H>
+__global__ void __launch_bounds__(G_THREADS, 1)
+gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__ CUtensorMap tma_wlo,
+              const float* __restrict__ xproj, const float* __restrict__ bhn, float* __restrict__ out, int64_t batch) {
+    constexpr int KB = H / GK;               // 4 (H=128) or 6 (H=192)
+    constexpr int NB = H / GBLK;             // unit blocks, == KB
+    constexpr int PAIRS = NB / 2;
+    constexpr uint32_t TMEM_COLS = PAIRS * GN <= 256 ? 256 : 512;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* h_hi = base;                                    // KB tiles of 8 KB
+    uint8_t* h_lo = base + KB * G_HTILE;
+    uint8_t* wring = base + 2 * KB * G_HTILE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(wring + G_STAGES * G_STAGE);
+    uint64_t* empty = full + G_STAGES;
+    uint64_t* acc_full = empty + G_STAGES;
+    uint64_t* h_ready = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G_STAGES; ++s) { g_mbar_init(&full[s], 1); g_mbar_init(&empty[s], 1); }
+        g_mbar_init(acc_full, 1);
+        g_mbar_init(h_ready, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer: W_hh blocks, every step ----
+            uint32_t it = 0;
+            for (int step = 0; step < N_POS; ++step) {
+                for (int blk = 0; blk < NB; ++blk) {
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const int s = it % G_STAGES;
+                        const uint32_t ph = (it / G_STAGES) & 1;
+                        g_mbar_wait(&empty[s], ph ^ 1);
+                        g_mbar_expect_tx(&full[s], G_STAGE);
+                        uint8_t* st = wring + s * G_STAGE;
+                        const int row = dir * 3 * H + blk * GN;
+                        g_tma_load_2d(&tma_whi, &full[s], st, kb * GK, row);
+                        g_tma_load_2d(&tma_wlo, &full[s], st + G_WTILE, kb * GK, row);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ---- MMA issuer ----
+            // D=f32, A=B=tf32, K-major, M=64, N=96
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+            uint32_t it = 0;
+            for (int step = 0; step < N_POS; ++step) {
+                g_mbar_wait(h_ready, step & 1);            // h_{t-1} (hi/lo) is in smem, accumulators drained
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int blk = 0; blk < NB; ++blk) {
+                    const uint32_t acc = tmem_base + ((uint32_t)((blk & 1) * 16) << 16) + (uint32_t)((blk >> 1) * GN);
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const int s = it % G_STAGES;
+                        const uint32_t ph = (it / G_STAGES) & 1;
+                        g_mbar_wait(&full[s], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t d_hhi = g_desc_k_sw128(g_smem_u32(h_hi + kb * G_HTILE));
+                        const uint64_t d_hlo = g_desc_k_sw128(g_smem_u32(h_lo + kb * G_HTILE));
+                        const uint32_t w_addr = g_smem_u32(wring + s * G_STAGE);
+                        const uint64_t d_whi = g_desc_k_sw128(w_addr);
+                        const uint64_t d_wlo = g_desc_k_sw128(w_addr + G_WTILE);
+                        #pragma unroll
+                        for (int k = 0; k < GK / 8; ++k) {
+                            const uint64_t o = (uint64_t)(k * 2);
+                            g_mma_tf32(acc, d_hhi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
+                            g_mma_tf32(acc, d_hlo + o, d_whi + o, idesc, 1u);
+                            g_mma_tf32(acc, d_hhi + o, d_wlo + o, idesc, 1u);
+                        }
+                        g_commit(&empty[s]);
+                    }
+                }
+                g_commit(acc_full);
+            }
+        }
+    } else {                                               // ---- gate math: warps 2..5 ----
+        const int quad = warp & 3;
+        const int m = quad * 16 + (lane & 15);             // candidate row inside the CTA
+        const int sub = lane >> 4;                         // which unit block of each pair
+        const int64_t b_raw = (int64_t)blockIdx.x * GM + m;
+        const bool b_ok = b_raw < batch;
+        const int64_t b = b_ok ? b_raw : batch - 1;
+        const uint32_t row_off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+        // h_0 = 0
+        for (int kb = sub; kb < KB; kb += 2) {
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                *reinterpret_cast<float4*>(h_hi + kb * G_HTILE + row_off + j * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(h_lo + kb * G_HTILE + row_off + j * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        g_mbar_arrive(h_ready);
+
+        const float* bhn_d = bhn + dir * H;
+        for (int step = 0; step < N_POS; ++step) {
+            const int t = dir ? (N_POS - 1 - step) : step;
+            const float* xp = xproj + (b * N_POS + t) * (int64_t)(6 * H) + dir * 3 * H;
+            float* op = out + (b * N_POS + t) * (int64_t)(2 * H) + dir * H;
+            g_mbar_wait(acc_full, step & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int p = 0; p < PAIRS; ++p) {
+                const int blk = 2 * p + sub;
+                const int u0 = blk * GBLK;
+                const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p * GN);
+                #pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t ar[16], az[16], an[16];
+                    g_tmem_ld16(tcol + half * 16, ar);
+                    g_tmem_ld16(tcol + GBLK + half * 16, az);
+                    g_tmem_ld16(tcol + 2 * GBLK + half * 16, an);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int uu = u0 + half * 16;
+                    #pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 xr = *reinterpret_cast<const float4*>(xp + uu + q * 4);
+                        const float4 xz = *reinterpret_cast<const float4*>(xp + H + uu + q * 4);
+                        const float4 xn = *reinterpret_cast<const float4*>(xp + 2 * H + uu + q * 4);
+                        const float4 bn = *reinterpret_cast<const float4*>(bhn_d + uu + q * 4);
+                        // previous h of these 4 units: chunk (half*4+q) of k-block blk, row m
+                        const uint32_t chunk = (uint32_t)(((half * 4 + q) ^ (m & 7)) << 4);
+                        float4* p_hi = reinterpret_cast<float4*>(h_hi + blk * G_HTILE + row_off + chunk);
+                        float4* p_lo = reinterpret_cast<float4*>(h_lo + blk * G_HTILE + row_off + chunk);
+                        const float4 ohi = *p_hi, olo = *p_lo;
+                        const float hp[4] = {ohi.x + olo.x, ohi.y + olo.y, ohi.z + olo.z, ohi.w + olo.w};
+                        const float xrv[4] = {xr.x, xr.y, xr.z, xr.w}, xzv[4] = {xz.x, xz.y, xz.z, xz.w};
+                        const float xnv[4] = {xn.x, xn.y, xn.z, xn.w}, bnv[4] = {bn.x, bn.y, bn.z, bn.w};
+                        float hn[4], hh[4], hl[4];
+                        #pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float r = 1.0f / (1.0f + expf(-(xrv[e] + __uint_as_float(ar[q * 4 + e]))));
+                            const float z = 1.0f / (1.0f + expf(-(xzv[e] + __uint_as_float(az[q * 4 + e]))));
+                            const float n = tanhf(xnv[e] + r * (__uint_as_float(an[q * 4 + e]) + bnv[e]));
+                            hn[e] = (1.0f - z) * n + z * hp[e];
+                            hh[e] = g_round_tf32(hn[e]);
+                            hl[e] = hn[e] - hh[e];
+                        }
+                        *p_hi = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                        *p_lo = make_float4(hl[0], hl[1], hl[2], hl[3]);
+                        if (b_ok) *reinterpret_cast<float4*>(op + uu + q * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            g_mbar_arrive(h_ready);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
+}  // namespace tc
+
+// w_hi / w_lo: [2 directions][3H rows regrouped as (unit block, gate, unit)][H] fp32 (TF32 hi / lo)
+int launch_gru_tc(const float* xproj, const float* w_hi, const float* w_lo, const float* bhn, float* out, int64_t batch,
+                  int hidden, cudaStream_t s) {
+    if (batch <= 0) return 0;
+    CUtensorMap map_hi, map_lo;
+    if (tc::make_map(&map_hi, w_hi, 6 * hidden, hidden, hidden, tc::GN)) return 1;
+    if (tc::make_map(&map_lo, w_lo, 6 * hidden, hidden, hidden, tc::GN)) return 1;
+    dim3 grid(ceil_div(batch, tc::GM), 2);
+    static bool attr128 = false, attr192 = false;
+    if (hidden == 128) {
+        if (!attr128) {
+            CTO_CHECK(cudaFuncSetAttribute(tc::gru_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tc::GruSmem<128>::TOTAL));
+            attr128 = true;
+        }
+        tc::gru_tc_kernel<128><<<grid, tc::G_THREADS, tc::GruSmem<128>::TOTAL, s>>>(map_hi, map_lo, xproj, bhn, out, batch);
+    } else if (hidden == 192) {
+        if (!attr192) {
+            CTO_CHECK(cudaFuncSetAttribute(tc::gru_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tc::GruSmem<192>::TOTAL));
+            attr192 = true;
+        }
+        tc::gru_tc_kernel<192><<<grid, tc::G_THREADS, tc::GruSmem<192>::TOTAL, s>>>(map_hi, map_lo, xproj, bhn, out, batch);
+    } else {
+        CTO_REQUIRE(false, "gru_tc: hidden size %d not built (128 and 192 are, clairs/model.py:403-404)", hidden);
+    }
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace cto

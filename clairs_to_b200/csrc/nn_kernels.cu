@@ -29,21 +29,40 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // ------------------------------------------------------------------------------------------
 // int16 tensor -> fp32 network input with the depth rescale of P:179-197, 207
 // ------------------------------------------------------------------------------------------
-__global__ void rescale_kernel(const int16_t* __restrict__ x, const int32_t* __restrict__ depth, int64_t total,
+__global__ void rescale_kernel(const int16_t* __restrict__ x, const int32_t* __restrict__ depth, int64_t rows, int ld_out,
                                float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int64_t cand = i / (N_POS * N_CH);
-    const int d = depth[cand];
-    const double v = (double)x[i];
+    if (i >= rows * ld_out) return;
+    const int64_t row = i / ld_out;                    // (candidate, position)
+    const int ch = (int)(i - row * ld_out);
+    if (ch >= N_CH) { out[i] = 0.0f; return; }
+    const int d = depth[row / N_POS];
+    const double v = (double)x[row * N_CH + ch];
     // python: float(item) * (50.0 / depth) in double, then numpy float32 cast
     out[i] = d > MIN_RESCALE_COV ? __double2float_rn(__dmul_rn(v, __ddiv_rn(50.0, (double)d))) : (float)v;
 }
 
-int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, cudaStream_t s) {
+int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, int ld_out, cudaStream_t s) {
     if (n <= 0) return 0;
-    const int64_t total = n * N_POS * N_CH;
-    rescale_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, depth, total, out);
+    CTO_REQUIRE(ld_out >= N_CH, "rescale: ld_out %d < %d", ld_out, N_CH);
+    const int64_t total = n * N_POS * ld_out;
+    rescale_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, depth, n * N_POS, ld_out, out);
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+__global__ void pad_rows_kernel(const float* __restrict__ x, int64_t rows, int cols, int ld_out, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ld_out) return;
+    const int64_t row = i / ld_out;
+    const int ch = (int)(i - row * ld_out);
+    out[i] = ch < cols ? x[row * cols + ch] : 0.0f;
+}
+
+int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_out, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    pad_rows_kernel<<<ceil_div(rows * ld_out, 256), 256, 0, s>>>(x, rows, cols, ld_out, out);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

@@ -26,10 +26,15 @@ int launch_gemm_nt(const AView& a, const float* w, const float* bias, const floa
 // tcgen05 TF32 path (gemm_tc.cu); plain row-major A only
 bool gemm_tc_supported(const float* a, int64_t lda, const float* w, int64_t m, int n, int k, const float* c, int64_t ldc,
                        const float* residual, int64_t ldr);
-int launch_gemm_tc(const float* a, int64_t lda, const float* w, const float* bias, const float* residual, int64_t ldr,
-                   float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s);
+// w_hi / w_lo: the weight matrix split into TF32 hi + lo parts (launch_split_tf32)
+int launch_gemm_tc(const float* a, int64_t lda, const float* w_hi, const float* w_lo, const float* bias,
+                   const float* residual, int64_t ldr, float* c, int64_t ldc, int64_t m, int n, int k, int act,
+                   cudaStream_t s);
+int launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s);
 
-int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, cudaStream_t s);
+// ld_out >= 34: row stride of the fp32 output (extra columns are zero-filled)
+int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, int ld_out, cudaStream_t s);
+int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_out, cudaStream_t s);
 int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s);
 int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch, int win, int wout, int stride,
                    int c, cudaStream_t s);
@@ -37,6 +42,9 @@ int launch_attention(const float* q, const float* kv, float* out, int64_t batch,
                      cudaStream_t s);
 int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bhn, float* out, int64_t batch,
                          int hidden, cudaStream_t s);
+// tensor-core recurrence (gru_tc.cu): w_hi / w_lo = W_hh regrouped per 32-unit block, TF32 hi / lo
+int launch_gru_tc(const float* xproj, const float* w_hi, const float* w_lo, const float* bhn, float* out, int64_t batch,
+                  int hidden, cudaStream_t s);
 int launch_head_fc3(const float* y, const float* w3, const float* b3, float* logits, int64_t batch, int n_heads,
                     cudaStream_t s);
 int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,

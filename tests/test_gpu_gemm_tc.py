@@ -1,6 +1,6 @@
-"""GPU: the tcgen05 TF32 GEMM (csrc/gemm_tc.cu) against an fp64 torch reference and against the
-fp32 CUDA-core GEMM it replaces.  Floating point: TF32 keeps 10 mantissa bits per operand, so the
-bound is relative to sum |a||w| (stated below), the CUDA-core path is held to fp32 rounding."""
+"""GPU: the tcgen05 3xTF32 GEMM (csrc/gemm_tc.cu) against an fp64 torch reference and against the
+fp32 CUDA-core GEMM it replaces.  Floating point: both paths are held to fp32-rounding level,
+2e-5 relative to sum |a||w| (a single-pass TF32 product would be ~1e-3: the hi/lo split matters)."""
 
 import numpy as np
 import pytest
@@ -37,10 +37,14 @@ def test_gemm_tf32_vs_fp64(m, n, k, act):
     scale = (a.double().abs() @ w.double().abs().t()).max().item()
     exact = gemm_nt(a, w, bias, res, act, tensor_cores=False)
     assert (exact.double() - want).abs().max().item() < 1e-5 * max(scale, 1.0)
+    if n % 64 != 0:
+        from clairs_to_b200._lib import CtoError
+        with pytest.raises(CtoError):        # narrow outputs stay on the CUDA-core kernel
+            gemm_nt(a, w, bias, res, act, tensor_cores=True)
+        return
     got = gemm_nt(a, w, bias, res, act, tensor_cores=True)
     err = (got.double() - want).abs().max().item()
-    # two TF32 operands: 2 * 2^-11 relative per product, worst case all aligned
-    assert err < 1.2e-3 * scale, (err, scale)
+    assert err < 2e-5 * max(scale, 1.0), (err, scale)
     assert torch.isfinite(got).all()
 
 
@@ -53,4 +57,4 @@ def test_gemm_tf32_strided_a_and_inplace_residual():
     res = torch.randn(500, 64, generator=g).cuda()
     want = a.double() @ w.double().t() + res.double()
     got = gemm_nt(a, w, None, res, 0, tensor_cores=True)
-    assert (got.double() - want).abs().max().item() < 5e-3
+    assert (got.double() - want).abs().max().item() < 1e-4
