@@ -115,7 +115,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--candidates", type=int, default=100000, help="candidate sites per GPU per step")
-    ap.add_argument("--max-batch", type=int, default=8192, help="engine chunk (candidates per network pass)")
+    ap.add_argument("--max-batch", type=int, default=9472, help="engine chunk (candidates per network pass)")
     ap.add_argument("--cpu-sample", type=int, default=300, help="CPU baseline: candidates per host process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -13,9 +13,10 @@
 //   * one elected thread issues tcgen05.mma.kind::tf32 (M=64, N=96, K=8), three per k-step
 //     (hi*hi + lo*hi + hi*lo); the accumulators of ALL gate columns of the step stay in TMEM:
 //     unit block 2p sits in lanes 0-15 and block 2p+1 in lanes 16-31 of columns [96p, 96p+96);
-//   * four epilogue warps (one TMEM lane = one candidate x one unit block) read the gate
-//     pre-activations with tcgen05.ld, add xproj, apply the gate math in fp32, write h_t to HBM and
-//     the TF32 hi/lo split of h_t back into the shared-memory tiles for the next step.
+//   * eight gate-math warps (one TMEM lane = one candidate x one unit block, two warps per lane
+//     quadrant) read the gate pre-activations with tcgen05.ld, add the software-prefetched xproj,
+//     apply the gate math in fp32, write h_t to HBM and the TF32 hi/lo split of h_t back into the
+//     shared-memory tiles for the next step.
 #include "nn_kernels.cuh"
 #include <cuda.h>
 
@@ -82,6 +83,15 @@ __device__ __forceinline__ void g_tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 
+__device__ __forceinline__ void g_tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+// gate non-linearities through MUFU.EX2 / MUFU.RCP: absolute error ~1e-7, far inside the 1e-3 contract
+__device__ __forceinline__ float g_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float g_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
 constexpr int GM = 64;                       // candidates per CTA (MMA M)
 constexpr int GBLK = 32;                     // hidden units per block
 constexpr int GN = 3 * GBLK;                 // 96 gate columns per block (MMA N)
@@ -90,7 +100,7 @@ constexpr int G_HTILE = GM * 128;            // 8 KB: 64 rows x 128 bytes
 constexpr int G_WTILE = GN * 128;            // 12 KB
 constexpr int G_STAGE = 2 * G_WTILE;         // hi | lo
 constexpr int G_STAGES = 5;
-constexpr int G_THREADS = 192;
+constexpr int G_THREADS = 320;               // warp 0 TMA, warp 1 MMA, warps 2-9 gate math
 
 template <int H>
 struct GruSmem {
@@ -124,7 +134,7 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_STAGES; ++s) { g_mbar_init(&full[s], 1); g_mbar_init(&empty[s], 1); }
         g_mbar_init(acc_full, 1);
-        g_mbar_init(h_ready, 128);
+        g_mbar_init(h_ready, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -187,72 +197,88 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
                 g_commit(acc_full);
             }
         }
-    } else {                                               // ---- gate math: warps 2..5 ----
+    } else {                                               // ---- gate math: warps 2..9 ----
+        // two warps per TMEM lane quadrant; thread = (candidate row m, unit block parity `sub`, 16-unit half `part`)
         const int quad = warp & 3;
+        const int part = (warp - 2) >> 2;
         const int m = quad * 16 + (lane & 15);             // candidate row inside the CTA
         const int sub = lane >> 4;                         // which unit block of each pair
         const int64_t b_raw = (int64_t)blockIdx.x * GM + m;
         const bool b_ok = b_raw < batch;
         const int64_t b = b_ok ? b_raw : batch - 1;
         const uint32_t row_off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
-        // h_0 = 0
+        // h_0 = 0: this thread owns chunks [4*part, 4*part+4) of row m in the tiles of its blocks
         for (int kb = sub; kb < KB; kb += 2) {
             #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                *reinterpret_cast<float4*>(h_hi + kb * G_HTILE + row_off + j * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(h_lo + kb * G_HTILE + row_off + j * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t chunk = (uint32_t)(((part * 4 + j) ^ (m & 7)) << 4);
+                *reinterpret_cast<float4*>(h_hi + kb * G_HTILE + row_off + chunk) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(h_lo + kb * G_HTILE + row_off + chunk) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         g_mbar_arrive(h_ready);
 
         const float* bhn_d = bhn + dir * H;
+        constexpr int ITERS = PAIRS * 2;                   // 8 units per iteration
+        float4 xq[6];                                      // prefetched xproj: r(2) z(2) n(2) float4
+        auto prefetch = [&](int step, int i) {
+            const int t = dir ? (N_POS - 1 - step) : step;
+            const int uu = (2 * (i >> 1) + sub) * GBLK + part * 16 + (i & 1) * 8;
+            const float* xp = xproj + (b * N_POS + t) * (int64_t)(6 * H) + dir * 3 * H + uu;
+            xq[0] = *reinterpret_cast<const float4*>(xp);
+            xq[1] = *reinterpret_cast<const float4*>(xp + 4);
+            xq[2] = *reinterpret_cast<const float4*>(xp + H);
+            xq[3] = *reinterpret_cast<const float4*>(xp + H + 4);
+            xq[4] = *reinterpret_cast<const float4*>(xp + 2 * H);
+            xq[5] = *reinterpret_cast<const float4*>(xp + 2 * H + 4);
+        };
+        prefetch(0, 0);
         for (int step = 0; step < N_POS; ++step) {
             const int t = dir ? (N_POS - 1 - step) : step;
-            const float* xp = xproj + (b * N_POS + t) * (int64_t)(6 * H) + dir * 3 * H;
             float* op = out + (b * N_POS + t) * (int64_t)(2 * H) + dir * H;
             g_mbar_wait(acc_full, step & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int p = 0; p < PAIRS; ++p) {
+            #pragma unroll 1
+            for (int i = 0; i < ITERS; ++i) {
+                const int p = i >> 1;
                 const int blk = 2 * p + sub;
-                const int u0 = blk * GBLK;
-                const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p * GN);
+                const int uu = blk * GBLK + part * 16 + (i & 1) * 8;       // first of this iteration's 8 units
+                const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p * GN + part * 16 + (i & 1) * 8);
+                uint32_t ar[8], az[8], an[8];
+                g_tmem_ld8(tcol, ar);
+                g_tmem_ld8(tcol + GBLK, az);
+                g_tmem_ld8(tcol + 2 * GBLK, an);
+                float xv[24];
                 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t ar[16], az[16], an[16];
-                    g_tmem_ld16(tcol + half * 16, ar);
-                    g_tmem_ld16(tcol + GBLK + half * 16, az);
-                    g_tmem_ld16(tcol + 2 * GBLK + half * 16, an);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    const int uu = u0 + half * 16;
+                for (int q = 0; q < 6; ++q) { xv[q * 4] = xq[q].x; xv[q * 4 + 1] = xq[q].y; xv[q * 4 + 2] = xq[q].z; xv[q * 4 + 3] = xq[q].w; }
+                // next iteration's xproj (possibly of the next step) flies while this one computes
+                if (i + 1 < ITERS) prefetch(step, i + 1);
+                else if (step + 1 < N_POS) prefetch(step + 1, 0);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float4 bn = *reinterpret_cast<const float4*>(bhn_d + uu + q * 4);
+                    const uint32_t chunk = (uint32_t)(((part * 4 + (i & 1) * 2 + q) ^ (m & 7)) << 4);
+                    float4* p_hi = reinterpret_cast<float4*>(h_hi + blk * G_HTILE + row_off + chunk);
+                    float4* p_lo = reinterpret_cast<float4*>(h_lo + blk * G_HTILE + row_off + chunk);
+                    const float4 ohi = *p_hi, olo = *p_lo;
+                    const float hp[4] = {ohi.x + olo.x, ohi.y + olo.y, ohi.z + olo.z, ohi.w + olo.w};
+                    const float bnv[4] = {bn.x, bn.y, bn.z, bn.w};
+                    float hn[4], hh[4], hl[4];
                     #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 xr = *reinterpret_cast<const float4*>(xp + uu + q * 4);
-                        const float4 xz = *reinterpret_cast<const float4*>(xp + H + uu + q * 4);
-                        const float4 xn = *reinterpret_cast<const float4*>(xp + 2 * H + uu + q * 4);
-                        const float4 bn = *reinterpret_cast<const float4*>(bhn_d + uu + q * 4);
-                        // previous h of these 4 units: chunk (half*4+q) of k-block blk, row m
-                        const uint32_t chunk = (uint32_t)(((half * 4 + q) ^ (m & 7)) << 4);
-                        float4* p_hi = reinterpret_cast<float4*>(h_hi + blk * G_HTILE + row_off + chunk);
-                        float4* p_lo = reinterpret_cast<float4*>(h_lo + blk * G_HTILE + row_off + chunk);
-                        const float4 ohi = *p_hi, olo = *p_lo;
-                        const float hp[4] = {ohi.x + olo.x, ohi.y + olo.y, ohi.z + olo.z, ohi.w + olo.w};
-                        const float xrv[4] = {xr.x, xr.y, xr.z, xr.w}, xzv[4] = {xz.x, xz.y, xz.z, xz.w};
-                        const float xnv[4] = {xn.x, xn.y, xn.z, xn.w}, bnv[4] = {bn.x, bn.y, bn.z, bn.w};
-                        float hn[4], hh[4], hl[4];
-                        #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float r = 1.0f / (1.0f + expf(-(xrv[e] + __uint_as_float(ar[q * 4 + e]))));
-                            const float z = 1.0f / (1.0f + expf(-(xzv[e] + __uint_as_float(az[q * 4 + e]))));
-                            const float n = tanhf(xnv[e] + r * (__uint_as_float(an[q * 4 + e]) + bnv[e]));
-                            hn[e] = (1.0f - z) * n + z * hp[e];
-                            hh[e] = g_round_tf32(hn[e]);
-                            hl[e] = hn[e] - hh[e];
-                        }
-                        *p_hi = make_float4(hh[0], hh[1], hh[2], hh[3]);
-                        *p_lo = make_float4(hl[0], hl[1], hl[2], hl[3]);
-                        if (b_ok) *reinterpret_cast<float4*>(op + uu + q * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = q * 4 + e;
+                        const float r = g_sigmoid(xv[c] + __uint_as_float(ar[c]));
+                        const float z = g_sigmoid(xv[8 + c] + __uint_as_float(az[c]));
+                        const float n = g_tanh(xv[16 + c] + r * (__uint_as_float(an[c]) + bnv[e]));
+                        hn[e] = (1.0f - z) * n + z * hp[e];
+                        hh[e] = g_round_tf32(hn[e]);
+                        hl[e] = hn[e] - hh[e];
                     }
+                    *p_hi = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                    *p_lo = make_float4(hl[0], hl[1], hl[2], hl[3]);
+                    if (b_ok) *reinterpret_cast<float4*>(op + uu + q * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
