@@ -136,7 +136,7 @@ def main():
     import torch
     import torch.distributed as dist
     from clairs_to_b200 import _lib, dist as cdist, synth
-    from clairs_to_b200.engine import Engine, low_bq_cut_for, stream_to_device
+    from clairs_to_b200.engine import PIPELINE_LOW_BQ_CUT, Engine, stream_to_device
     from clairs_to_b200.pileup_format import PileupStream
     from oracle import nn_oracle      # only for the seeded random-init weight generator shared with the tests
 
@@ -148,7 +148,7 @@ def main():
     n = args.candidates
     n_heads = 4
     literal = "ont_r10_dorado_sup_5khz"
-    cut = low_bq_cut_for(literal)
+    cut = PIPELINE_LOW_BQ_CUT
 
     t_gen = time.time()
     aff, neg = synth.synth_pair_large(n, 20241 + rank, 'ont')

@@ -34,6 +34,7 @@ SIGNATURES = {
     "cto_softmax_posterior": (INT, [P, P, P, I64, P, P, P, P]),
     "cto_engine_set_tensor_cores": (INT, [P, INT]),
     "cto_gemm_nt": (INT, [P, I64, P, P, P, I64, P, I64, I64, INT, INT, INT, INT, P]),
+    "cto_posterior_from_probs": (INT, [P, INT, P, P, I64, P, P, P]),
     "cto_launch_count": (I64, []),
     "cto_engine_profile": (INT, [P, INT]),
     "cto_engine_profile_kinds": (INT, []),

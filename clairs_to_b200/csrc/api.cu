@@ -182,6 +182,19 @@ int cto_softmax_posterior(cto_engine* h, const float* la, const float* ln, int64
     return launch_softmax_posterior(la, ln, n, h->e.aff.n_heads, tables, probs, post, call, (cudaStream_t)stream);
 }
 
+int cto_posterior_from_probs(const double* tables_host, int n_heads, const double* p_aff_dev, const double* p_neg_dev,
+                             int64_t n, double* post_dev, int32_t* call_dev, void* stream) {
+    CTO_REQUIRE(tables_host && (n_heads == 4 || n_heads == 6), "posterior_from_probs: bad tables / head count %d", n_heads);
+    CTO_REQUIRE(n == 0 || (p_aff_dev && p_neg_dev && post_dev && call_dev), "posterior_from_probs: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* t = nullptr;
+    CTO_CHECK(cudaMallocAsync((void**)&t, sizeof(double) * 122 * n_heads, s));
+    CTO_CHECK(cudaMemcpyAsync(t, tables_host, sizeof(double) * 122 * n_heads, cudaMemcpyHostToDevice, s));
+    const int rc = launch_posterior_from_probs(p_aff_dev, p_neg_dev, n, n_heads, t, post_dev, call_dev, s);
+    cudaFreeAsync(t, s);
+    return rc;
+}
+
 int64_t cto_launch_count(void) { return launches(); }
 
 int cto_engine_set_tensor_cores(cto_engine* h, int enable) {

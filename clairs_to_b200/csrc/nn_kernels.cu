@@ -561,6 +561,43 @@ __global__ void softmax_posterior_kernel(const float* __restrict__ la, const flo
     if (call && tables) call[i] = best_h | (clamped << 8);
 }
 
+// Bayes combine on probabilities that were already parsed from a predict file (clairs/call_variants.py:798-829):
+// pa / pn = P(positive class) per head as doubles, exactly the python floats the reference combines.
+__global__ void posterior_from_probs_kernel(const double* __restrict__ pa, const double* __restrict__ pn, int64_t n,
+                                            int n_heads, const double* __restrict__ tables, double* __restrict__ post,
+                                            int32_t* __restrict__ call) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double best = -1.0;
+    int best_h = 0, clamped = 0;
+    for (int h = 0; h < n_heads; ++h) {
+        const double p = pa[i * n_heads + h], q = pn[i * n_heads + h];
+        const double* t = tables + h * 122;
+        const double one_minus_q = __dsub_rn(1.0, q);
+        int bi = digitize11(p, t + 100);
+        int bj = digitize11(one_minus_q, t + 111);
+        if (bi < 0 || bi > 9 || bj < 0 || bj > 9) clamped = 1;
+        bi = min(max(bi, 0), 9);
+        bj = min(max(bj, 0), 9);
+        const double wgt = __dadd_rn(t[bi * 10 + bj], DBL_EPSILON);
+        const double num = __dmul_rn(__dmul_rn(p, one_minus_q), wgt);
+        const double alt = __dmul_rn(__dmul_rn(__dsub_rn(1.0, p), q), __dsub_rn(1.0, wgt));
+        const double ps = __ddiv_rn(num, __dadd_rn(num, alt));
+        post[i * n_heads + h] = ps;
+        if (ps > best) { best = ps; best_h = h; }
+    }
+    call[i] = best_h | (clamped << 8);
+}
+
+int launch_posterior_from_probs(const double* pa, const double* pn, int64_t n, int n_heads, const double* tables,
+                                double* post, int32_t* call, cudaStream_t s) {
+    if (n <= 0) return 0;
+    posterior_from_probs_kernel<<<ceil_div(n, 128), 128, 0, s>>>(pa, pn, n, n_heads, tables, post, call);
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,
                              const double* tables, float* probs, double* post, int32_t* call, cudaStream_t s) {
     if (n <= 0) return 0;

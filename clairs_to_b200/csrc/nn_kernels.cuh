@@ -49,6 +49,8 @@ int launch_head_fc3(const float* y, const float* w3, const float* b3, float* log
                     cudaStream_t s);
 int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,
                              const double* tables, float* probs, double* post, int32_t* call, cudaStream_t s);
+int launch_posterior_from_probs(const double* pa, const double* pn, int64_t n, int n_heads, const double* tables,
+                                double* post, int32_t* call, cudaStream_t s);
 int launch_strand_counts(const int16_t* x_aff, int64_t n, int32_t* fwd, int32_t* rev, cudaStream_t s);
 
 }  // namespace cto

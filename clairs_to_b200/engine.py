@@ -22,8 +22,13 @@ from .weights import export_aff, export_neg, likelihood_tables, state_dict_from_
 
 
 def low_bq_cut_for(platform: str) -> int:
-    """The literal of src/create_tensor_pileup_calling.py:149."""
+    """The literal of decode_pileup_bases (src/create_tensor_pileup_calling.py:149).  NOTE: create_tensor()
+    never forwards its --platform to that function (ibid. 499-511), so inside the pipeline the callee's
+    default 'ont' applies and the cut is always ``PIPELINE_LOW_BQ_CUT`` (pinned by tests/golden/create_tensor)."""
     return 30 if platform == 'ont' else 10
+
+
+PIPELINE_LOW_BQ_CUT = low_bq_cut_for('ont')
 
 
 def _ptr(t):
@@ -54,6 +59,20 @@ def stream_to_device(stream: PileupStream, device) -> PileupStream:
             a = a.view(_TORCH_VIEW[a.dtype])
         out.append(torch.from_numpy(a).to(device, non_blocking=True))
     return PileupStream(*out)
+
+
+def encode_pileup(s: PileupStream, low_bq_cut: int, device=None):
+    """Device PileupStream -> (int16 [N,33,34], int32 centre depth [N]) through ``cto_encode_pileup``.
+    Needs no weights, so the create_tensor sub-command uses it without building an Engine."""
+    lib = _lib.lib()
+    device = s.win_pos.device if device is None else device
+    n = s.win_pos.numel() // N_POS
+    tensor = torch.empty((n, N_POS, N_CH), dtype=torch.int16, device=device)
+    depth = torch.empty((n,), dtype=torch.int32, device=device)
+    _lib.check(lib.cto_encode_pileup(_ptr(s.code), _ptr(s.bq), _ptr(s.mq), _ptr(s.pos_off), _ptr(s.ref_code),
+                                     _ptr(s.ind_off), _ptr(s.ind_entry), _ptr(s.win_pos), n, int(low_bq_cut),
+                                     _ptr(tensor), _ptr(depth), _stream_ptr()), "cto_encode_pileup")
+    return tensor, depth
 
 
 class Engine:
@@ -104,13 +123,7 @@ class Engine:
     # ---- encoder ----------------------------------------------------------------------------
     def encode(self, s: PileupStream, low_bq_cut: int):
         """Device PileupStream -> (int16 [N,33,34], int32 depth [N])."""
-        n = s.win_pos.numel() // N_POS
-        tensor = torch.empty((n, N_POS, N_CH), dtype=torch.int16, device=self.device)
-        depth = torch.empty((n,), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.cto_encode_pileup(_ptr(s.code), _ptr(s.bq), _ptr(s.mq), _ptr(s.pos_off), _ptr(s.ref_code),
-                                              _ptr(s.ind_off), _ptr(s.ind_entry), _ptr(s.win_pos), n, int(low_bq_cut),
-                                              _ptr(tensor), _ptr(depth), _stream_ptr()), "cto_encode_pileup")
-        return tensor, depth
+        return encode_pileup(s, low_bq_cut, self.device)
 
     # ---- networks ---------------------------------------------------------------------------
     def rescale(self, x_i16, depth):

@@ -90,9 +90,18 @@ int cto_softmax_posterior(cto_engine* e, const float* logits_aff_dev, const floa
                           float* probs_dev, double* post_dev, int32_t* call_dev, void* stream);
 
 /*
- * Dense contractions run on tcgen05 tensor cores as TF32 (fp32 accumulate) by default; enable = 0
- * forces the exact fp32 CUDA-core kernels everywhere (used by the parity tests to separate
- * layout bugs from TF32 rounding).  cto_gemm_nt exposes the building block itself:
+ * The Bayes combine alone, for the call_variants sub-command whose input is a predict FILE
+ * (clairs/call_variants.py:798-853): p_aff / p_neg = P(positive class) per head as doubles [n, n_heads]
+ * (the python floats parsed from the 8-decimal text), tables as in cto_engine_set_likelihood (host).
+ */
+int cto_posterior_from_probs(const double* tables_host, int n_heads, const double* p_aff_dev, const double* p_neg_dev,
+                             int64_t n, double* post_dev, int32_t* call_dev, void* stream);
+
+/*
+ * Dense contractions and the GRU recurrence run on tcgen05 tensor cores by default, as 3xTF32
+ * (operands split into TF32 hi + lo, three MMAs per k-step, fp32 accumulate in TMEM) because
+ * single-pass TF32 breaks the 1e-3 logit contract; enable = 0 forces the fp32 CUDA-core kernels
+ * everywhere (the parity tests run both).  cto_gemm_nt exposes the building block itself:
  * C[m,n] = act(A[m,k] * W[n,k]^T + bias) (+ residual), act 0 none / 1 GELU(erf) / 2 SELU.
  */
 int cto_engine_set_tensor_cores(cto_engine* e, int enable);
@@ -117,7 +126,7 @@ int cto_strand_counts(const int16_t* x_aff_dev, int64_t n, int32_t* fwd_dev, int
 
 /*
  * The per-mini-batch body of predict() (clairs/predict.py:610-699) for n candidates at once:
- * rescale both tensors, AFF and NEG forward (concurrently), softmax, strand counts, posterior.
+ * rescale both tensors, NEG and AFF forward, softmax, strand counts, posterior.
  * Nullable outputs are skipped.  x_neg_dev == x_aff_dev is allowed (Illumina symlink case,
  * run_clairs_to:1248-1252).
  */

@@ -28,7 +28,7 @@ def _worker(args):
     from clairs_to_b200 import synth
     from oracle import nn_oracle, pileup_oracle, posterior_oracle
     torch.set_num_threads(1)
-    literal = "ont_r10_dorado_sup_5khz"
+    literal = "ont"          # create_tensor() always decodes with the callee default (CT:499-511)
     (aff, aff_aux), (neg, neg_aux) = synth.synth_pair(n, seed, 'ont')
     texts = [synth.render_mpileup(s, a) for s, a in ((aff, aff_aux), (neg, neg_aux))]
     refs = ["ACGT"[int(c)] for c in neg.ref_code]

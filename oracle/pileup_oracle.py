@@ -174,8 +174,10 @@ def encode_windows(mpileup_rows, candidates, reference_sequence, reference_start
         ref_base = coerce_ref_base(reference_sequence[pos - reference_start])
         off = pos - reference_start
         chunk_ref = reference_sequence[off:off + max_indel_length].upper()   # CT:497
+        # create_tensor() never forwards its --platform to decode_pileup_bases (CT:499-511), so the
+        # callee's default platform="ont" applies and the low-BQ cut is ALWAYS 30 in the pipeline
         vec, alt_info = position_vector(bases, mq, bq, ref_base, is_candidate=pos in cand_set,
-                                        chunk_ref_seq=chunk_ref, platform=platform,
+                                        chunk_ref_seq=chunk_ref, platform="ont",
                                         max_indel_length=max_indel_length)
         table[pos - extend_start] = vec                                 # CT:513-514
         if pos in cand_set:

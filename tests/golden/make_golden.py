@@ -154,7 +154,7 @@ def pipeline_golden():
                     vec, ai = pileup_oracle.position_vector(
                         cols[4], [ord(ch) - 33 for ch in cols[6]], [ord(ch) - 33 for ch in cols[5]], rb,
                         is_candidate=(j == 16), chunk_ref_seq=(rb + "ACGTTGCA" * 8)[:60],
-                        platform="ont_r10_dorado_sup_5khz")
+                        platform="ont")
                     window.append(vec)
                     if j == 16:
                         alt_info = ai
@@ -196,6 +196,57 @@ def pipeline_golden():
         print("pipeline golden (%s) written" % tag)
 
 
+def create_tensor_golden():
+    """Unmodified reference `create_tensor_pileup_calling` end to end, with tests/fake_samtools.py
+    answering `samtools faidx` / `samtools mpileup` from fixture files."""
+    work = os.path.join(HERE, "create_tensor")
+    os.makedirs(work, exist_ok=True)
+    rng = np.random.default_rng(77)
+    ctg, length = "chr20", 6000
+    seq = rng.choice(list("ACGT"), size=length)
+    for p in (1190, 1203, 2504):                       # IUPAC / N reference bases inside windows
+        seq[p - 1] = rng.choice(list("NRY"))
+    seq = "".join(seq)
+    fa = os.path.join(work, "ref.fa")
+    with open(fa, "w") as f:
+        f.write(">%s\n" % ctg)
+        for i in range(0, length, 60):
+            f.write(seq[i:i + 60] + "\n")
+    with open(fa + ".fai", "w") as f:
+        f.write("%s\t%d\t%d\t60\t61\n" % (ctg, length, len(ctg) + 2))
+    centres = [10, 1200, 1215, 1300, 2500, 2533, 3100, 4000, 4100]
+    cand_fn = os.path.join(work, "%s.0_0_9_snv" % ctg)
+    with open(cand_fn, "w") as f:
+        for x in centres:
+            f.write("%s\t%d\t%d\n" % (ctg, max(x - 17, 1), x + 17))
+    covered = sorted({p for x in centres for p in range(max(x - 17, 1), x + 18)})
+    dropped = {1290, 1291, 3100, 4012}                  # no pileup row: zero rows / a candidate without alt_info
+    covered = [p for p in covered if p not in dropped]
+    n_c = (len(covered) + 32) // 33
+    neg, aux = synth.synth_stream(n_c, 555, 'ont', depth_lo=0, depth_hi=120, depth_mean=45)
+    aff, aff_aux = synth.filter_min_bq(neg, 20, aux)
+    bam = os.path.join(work, "tumor.bam")
+    open(bam, "w").close()
+    for stream, a, k in ((neg, aux, 0), (aff, aff_aux, 20)):
+        rows = synth.render_mpileup(stream, a, ctg=ctg, first_pos=0, decorate_seed=5)
+        with open("%s.minbq%d.mpileup" % (bam, k), "w") as f:
+            for i, p in enumerate(covered):
+                cols = rows[i].split("\t")
+                cols[1] = str(p)
+                cols[2] = seq[p - 1]
+                f.write("\t".join(cols))
+    shim = os.path.join(ROOT, "tests", "fake_samtools.py")
+    env = dict(os.environ, PYTHONPATH=REF)
+    for k, name in ((20, "aff"), (0, "neg")):
+        out = os.path.join(work, "tensor_can_%s" % name)
+        subprocess.run([sys.executable, os.path.join(REF, "clairs_to.py"), "create_tensor_pileup_calling",
+                        "--tumor_bam_fn", bam, "--ref_fn", fa, "--ctg_name", ctg, "--samtools", shim,
+                        "--min_bq", str(k), "--candidates_bed_regions", cand_fn, "--tensor_can_fn", out,
+                        "--platform", "ont_r10_dorado_sup_5khz"], check=True, env=env)
+        n = sum(1 for _ in gzip.open(out, "rt"))
+        print("create_tensor golden (%s): %d rows" % (name, n))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -206,3 +257,5 @@ if __name__ == "__main__":
         nn_golden()
     if a.only in (None, "pipeline"):
         pipeline_golden()
+    if a.only in (None, "create_tensor"):
+        create_tensor_golden()
