@@ -2,19 +2,37 @@
 //
 // Replaces decode_pileup_bases() + window assembly of the reference
 // (src/create_tensor_pileup_calling.py:146-229, 461, 513-516, 537-543; cited as CT).
-// HBM-bound integer work: one warp per (candidate, flank slot); reads are fetched with
-// coalesced byte loads, classified into at most two packed 8-bit counters per read and
-// summed across the warp with REDUX (no atomics, no shared-memory contention).  The rare
-// indel-carrying reads come from a sparse side list and are resolved exactly (per-allele
-// maximum, CT:184-187, 201-204) with an O(K^2/32) scan that has no table-size limit.
+//
+// HBM-bound integer work.  One CTA encodes a group of 8 candidates = 264 (candidate, flank slot)
+// pairs, one THREAD per slot:
+//   1. the group's rows cover one contiguous span of the read arrays (rows are position-sorted), so the
+//      three byte streams (code, bq, mq) of the span are fetched with three bulk async copies
+//      (cp.async.bulk, completion on an mbarrier) into shared memory - full-line HBM reads, no LSU work;
+//   2. every thread walks the reads of its own row in shared memory and bumps private 16-bit
+//      counters kept field-major in shared memory (bank = thread, so no conflicts and no atomics);
+//   3. the rare indel-carrying reads come from a sparse side list and are resolved exactly (per-allele
+//      maximum, CT:184-187, 201-204) with a K^2 scan that has no table-size limit;
+//   4. the 34 int16 of each slot are staged in shared memory and the group's 17.5 KB output block is
+//      written with 16-byte coalesced stores.
+// Groups whose span does not fit the staging buffers (very deep pileups, scattered rows) take the
+// same code path with the pointers left in global memory.
 #include "common.cuh"
 
 namespace cto {
 
-// fields of the two packed counter sets
-//   set A (exclusive by MQ): 0-3 ACGT, 4-7 acgt, 8 '*', 9 '#', 10-13 ACGT-LMQ, 14-17 acgt-LMQ
-//   set B (BQ < cut):        0-3 ACGT-LBQ, 4-7 acgt-LBQ
-__device__ __forceinline__ int field_to_channel_a(int f) {
+namespace enc {
+
+constexpr int GROUP = 8;                          // candidates per CTA
+constexpr int SLOTS = GROUP * N_POS;              // 264
+constexpr int THREADS = 288;                      // 9 warps
+constexpr int STAGE_CAP = 20 * 1024;              // bytes per staged array
+constexpr int N_FIELDS = 26;                      // 18 set-A + 8 set-B counters
+constexpr int OUT_BYTES = SLOTS * N_CH * 2;       // 17952
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// set-A field -> channel (CT:55-58)
+__device__ __forceinline__ int channel_of_a(int f) {
     if (f < 4) return f;                // A C G T
     if (f < 8) return f + 5;            // a c g t  -> 9..12
     if (f == 8) return 8;               // '*'
@@ -22,166 +40,192 @@ __device__ __forceinline__ int field_to_channel_a(int f) {
     return f + 8;                       // LMQ      -> 18..25
 }
 
-constexpr int WARPS_PER_CTA = 8;
-
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(THREADS)
 encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ bq,
                      const uint8_t* __restrict__ mq, const int32_t* __restrict__ pos_off,
                      const uint8_t* __restrict__ ref_code, const int32_t* __restrict__ ind_off,
                      const uint32_t* __restrict__ ind_entry, const int32_t* __restrict__ win_pos,
                      int64_t n_slots, int low_bq_cut, int16_t* __restrict__ tensor,
                      int32_t* __restrict__ depth_out) {
-    __shared__ int s_cnt[WARPS_PER_CTA][N_CH + 2];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int64_t slot = (int64_t)blockIdx.x * WARPS_PER_CTA + wib;
-    if (slot >= n_slots) return;
-    const int row = win_pos[slot];
-    int16_t* out = tensor + slot * N_CH;
-    const bool is_center = (slot % N_POS) == CENTER;
-    if (row < 0) {                                     // CT:461: no pileup row -> zeros
-        out[lane] = 0;
-        if (lane < N_CH - 32) out[32 + lane] = 0;
-        if (is_center && lane == 0 && depth_out) depth_out[slot / N_POS] = 0;
-        return;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* s_code = smem;
+    uint8_t* s_bq = smem + STAGE_CAP;
+    uint8_t* s_mq = smem + 2 * STAGE_CAP;
+    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + 3 * STAGE_CAP);                 // [N_FIELDS][THREADS]
+    int16_t* s_out = reinterpret_cast<int16_t*>(smem + 3 * STAGE_CAP + N_FIELDS * THREADS * 2);   // [SLOTS][34]
+    __shared__ uint64_t s_bar;
+    __shared__ int s_min_row, s_max_row;
+
+    const int tid = threadIdx.x;
+    const int64_t slot0 = (int64_t)blockIdx.x * SLOTS;
+    const int64_t slot = slot0 + tid;
+    const bool active = tid < SLOTS && slot < n_slots;
+    const int row = active ? win_pos[slot] : -1;
+
+    if (tid == 0) {
+        s_min_row = 0x7fffffff;
+        s_max_row = -1;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const int lo = pos_off[row], hi = pos_off[row + 1];
-    const int ref = ref_code[row];
+    #pragma unroll
+    for (int f = 0; f < N_FIELDS; ++f) s_hist[f * THREADS + tid] = 0;
+    __syncthreads();
+    if (row >= 0) {
+        // warp-aggregated min / max of the rows this group touches
+        const unsigned m = __activemask();
+        const int lo = __reduce_min_sync(m, row), hi = __reduce_max_sync(m, row);
+        if ((tid & 31) == __ffs(m) - 1) {
+            atomicMin(&s_min_row, lo);
+            atomicMax(&s_max_row, hi);
+        }
+    }
+    __syncthreads();
+    const int min_row = s_min_row, max_row = s_max_row;
+    int64_t span_lo = 0, span_hi = 0;
+    if (max_row >= 0) {
+        span_lo = pos_off[min_row];
+        span_hi = pos_off[max_row + 1];
+    }
+    const int64_t a_lo = span_lo & ~int64_t(15);                      // 16-byte aligned superset of the span
+    const int64_t a_hi = (span_hi + 15) & ~int64_t(15);
+    const bool staged = (a_hi - a_lo) <= STAGE_CAP && a_hi > a_lo;
+    if (staged && tid == 0) {
+        const uint32_t bytes = (uint32_t)(a_hi - a_lo);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(3 * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(s_code)), "l"(code + a_lo), "r"(bytes), "r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(s_bq)), "l"(bq + a_lo), "r"(bytes), "r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(s_mq)), "l"(mq + a_lo), "r"(bytes), "r"(smem_u32(&s_bar)) : "memory");
+    }
 
-    // 16-bit-field accumulators, identical in every lane: a_lo/a_hi hold even/odd bytes of
-    // the five set-A words, b_* of the two set-B words.
-    uint32_t a_lo[5] = {0, 0, 0, 0, 0}, a_hi[5] = {0, 0, 0, 0, 0};
-    uint32_t b_lo[2] = {0, 0}, b_hi[2] = {0, 0};
-
-    for (int base = lo; base < hi; base += 32) {
-        const int i = base + lane;
-        int fa = -1, fb = -1;
-        if (i < hi) {
-            const uint32_t c = code[i];
-            const uint32_t q = bq[i];
-            const uint32_t m = mq[i];
-            const uint32_t sym = c & 0xF;
-            if (!(c & 0x10)) {                                  // plain read (CT:160-171)
-                int b8 = -1;
-                if (sym < 4) b8 = sym;
-                else if (sym >= 5 && sym <= 8) b8 = sym - 1;
-                if (m != QUAL_ABSENT) {
-                    if (m >= MIN_MQ) {
-                        if (b8 >= 0) fa = b8;
-                        else if (sym == 10) fa = 8;
-                        else if (sym == 11) fa = 9;
-                    } else if (b8 >= 0) {
-                        fa = 10 + b8;                           // CT:215-217
-                    }
+    // per-slot metadata and the sparse indel list are read while the bulk copies are in flight
+    int lo = 0, hi = 0, ref = 0;
+    int tot[4] = {0, 0, 0, 0}, best[4] = {0, 0, 0, 0};
+    if (row >= 0) {
+        lo = pos_off[row];
+        hi = pos_off[row + 1];
+        ref = ref_code[row];
+        const int ilo = ind_off[row], ihi = ind_off[row + 1];
+        for (int i = ilo; i < ihi; ++i) {
+            const uint32_t e = ind_entry[i];
+            const uint32_t em = (e >> 16) & 0xFF;
+            if ((e & (1u << 26)) || em < MIN_MQ || em == QUAL_ABSENT) continue;     // CT:147, 174-176, 189-191
+            const uint32_t key = e & 0x0300FFFFu;                                   // allele id + class bits
+            int same = 0;
+            for (int j = ilo; j < ihi; ++j) {
+                const uint32_t o = ind_entry[j];
+                const uint32_t om = (o >> 16) & 0xFF;
+                same += (!(o & (1u << 26)) && om >= MIN_MQ && om != QUAL_ABSENT && (o & 0x0300FFFFu) == key) ? 1 : 0;
+            }
+            const int cls = (e >> 24) & 3;                                          // bit0 deletion, bit1 reverse
+            #pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                if (cls == c4) {
+                    tot[c4] += 1;
+                    best[c4] = max(best[c4], same);
                 }
-                if (b8 >= 0 && q != QUAL_ABSENT && (int)q < low_bq_cut) fb = b8;   // CT:149, 219-221
             }
         }
-        const uint32_t one_a = fa >= 0 ? (1u << ((fa & 3) * 8)) : 0u;
-        const int wa = fa >> 2;
-        #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const uint32_t s = __reduce_add_sync(0xffffffffu, wa == k ? one_a : 0u);
-            a_lo[k] += s & 0x00FF00FFu;
-            a_hi[k] += (s >> 8) & 0x00FF00FFu;
-        }
-        const uint32_t one_b = fb >= 0 ? (1u << ((fb & 3) * 8)) : 0u;
-        const int wb = fb >> 2;
-        #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint32_t s = __reduce_add_sync(0xffffffffu, wb == k ? one_b : 0u);
-            b_lo[k] += s & 0x00FF00FFu;
-            b_hi[k] += (s >> 8) & 0x00FF00FFu;
-        }
     }
 
-    // sparse indel list: totals per class (ins/del x fwd/rev) and per-allele maxima
-    const int ilo = ind_off[row], ihi = ind_off[row + 1];
-    int tot[4] = {0, 0, 0, 0}, best[4] = {0, 0, 0, 0};
-    for (int base = ilo; base < ihi; base += 32) {
-        const int i = base + lane;
-        uint32_t e = 0;
-        bool ok = false;
-        if (i < ihi) {
-            e = ind_entry[i];
-            const uint32_t m = (e >> 16) & 0xFF;
-            ok = !(e & (1u << 26)) && m >= MIN_MQ && m != QUAL_ABSENT;    // CT:147, 174-176, 189-191
+    if (staged) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "ENC_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@p bra ENC_DONE;\n\t"
+            "bra ENC_WAIT;\n\t"
+            "ENC_DONE:\n\t"
+            "}" ::"r"(smem_u32(&s_bar)) : "memory");
+    }
+    const uint8_t* p_code = staged ? s_code : code;                  // generic pointers: smem or global
+    const uint8_t* p_bq = staged ? s_bq : bq;
+    const uint8_t* p_mq = staged ? s_mq : mq;
+    const int shift = staged ? (int)a_lo : 0;
+    lo -= shift;
+    hi -= shift;
+
+    uint16_t* my = s_hist + tid;
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t c = p_code[i];
+        if (c & 0x10) continue;                                       // indel-carrying read (CT:160-204)
+        const uint32_t sym = c & 0xF;
+        const uint32_t m = p_mq[i], q = p_bq[i];
+        int b8 = -1;
+        if (sym < 4) b8 = sym;
+        else if (sym >= 5 && sym <= 8) b8 = sym - 1;
+        int fa = -1;
+        if (m != QUAL_ABSENT) {
+            if (m >= MIN_MQ) fa = b8 >= 0 ? b8 : (sym == 10 ? 8 : (sym == 11 ? 9 : -1));
+            else if (b8 >= 0) fa = 10 + b8;                           // CT:215-217
         }
-        const int cls = (e >> 24) & 3;                  // bit0 deletion, bit1 reverse
-        const uint32_t key = e & 0x0300FFFFu;
-        int same = 0;
-        for (int j = ilo; j < ihi; ++j) {               // uniform (broadcast) loads
-            const uint32_t o = ind_entry[j];
-            const uint32_t om = (o >> 16) & 0xFF;
-            const bool ook = !(o & (1u << 26)) && om >= MIN_MQ && om != QUAL_ABSENT;
-            same += (ook && (o & 0x0300FFFFu) == key) ? 1 : 0;
-        }
-        #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            const bool mine = ok && cls == c4;
-            tot[c4] += __popc(__ballot_sync(0xffffffffu, mine));
-            best[c4] = max(best[c4], (int)__reduce_max_sync(0xffffffffu, mine ? (unsigned)same : 0u));
-        }
+        if (fa >= 0) my[fa * THREADS] += 1;
+        if (b8 >= 0 && q != QUAL_ABSENT && (int)q < low_bq_cut) my[(18 + b8) * THREADS] += 1;   // CT:149, 219-221
     }
 
-    int* cnt = s_cnt[wib];
-    // unpack: lane f < 18 owns set-A field f, lanes 18..25 own set-B field f-18
-    {
-        int f = lane, v = 0, ch = -1;
-        if (lane < 18) {
-            uint32_t lo16 = 0, hi16 = 0;
+    if (tid < SLOTS) {
+        int16_t* o = s_out + tid * N_CH;
+        int v[N_CH];
+        #pragma unroll
+        for (int ch = 0; ch < N_CH; ++ch) v[ch] = 0;
+        if (row >= 0) {
             #pragma unroll
-            for (int k = 0; k < 5; ++k) if ((f >> 2) == k) { lo16 = a_lo[k]; hi16 = a_hi[k]; }
-            const uint32_t w = (f & 1) ? hi16 : lo16;
-            v = (f & 2) ? (w >> 16) : (w & 0xFFFF);
-            ch = field_to_channel_a(f);
-        } else if (lane < 26) {
-            f = lane - 18;
-            uint32_t lo16 = 0, hi16 = 0;
+            for (int f = 0; f < 18; ++f) v[channel_of_a(f)] = my[f * THREADS];
             #pragma unroll
-            for (int k = 0; k < 2; ++k) if ((f >> 2) == k) { lo16 = b_lo[k]; hi16 = b_hi[k]; }
-            const uint32_t w = (f & 1) ? hi16 : lo16;
-            v = (f & 2) ? (w >> 16) : (w & 0xFFFF);
-            ch = 26 + f;
-        } else if (lane < 30) {                         // I, D, i, d totals
-            const int c4 = lane - 26;                   // 0 ins fwd, 1 del fwd, 2 ins rev, 3 del rev
-            v = c4 == 0 ? tot[0] : c4 == 1 ? tot[1] : c4 == 2 ? tot[2] : tot[3];
-            ch = (c4 & 2 ? 13 : 4) + (c4 & 1 ? 2 : 0);
+            for (int f = 0; f < 8; ++f) v[26 + f] = my[(18 + f) * THREADS];
+            v[4] = tot[0]; v[6] = tot[1]; v[13] = tot[2]; v[15] = tot[3];           // I D i d
+            v[5] = best[0]; v[7] = best[1]; v[14] = best[2]; v[16] = best[3];       // I1 D1 i1 d1 (CT:210-213)
+            if (depth_out && (slot % N_POS) == CENTER) {                            // depth of alt_info (CT:208)
+                int d = 0;
+                #pragma unroll
+                for (int ch = 0; ch < 18; ++ch)
+                    if (ch != 5 && ch != 7 && ch != 14 && ch != 16) d += v[ch];
+                depth_out[slot / N_POS] = d;
+            }
+            // reference channel := -(sum of the four base counts) in each of the six groups (CT:223-228)
+            #pragma unroll
+            for (int g = 0; g < 6; ++g) {
+                const int gb = g == 0 ? 0 : (g == 1 ? 9 : 18 + (g - 2) * 4);
+                const int sum = v[gb] + v[gb + 1] + v[gb + 2] + v[gb + 3];
+                #pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k == ref) v[gb + k] = -sum;
+            }
+        } else if (active && depth_out && (slot % N_POS) == CENTER) {
+            depth_out[slot / N_POS] = 0;                                            // CT:461: no pileup row
         }
-        if (ch >= 0) cnt[ch] = v;
-        if (lane < 4) {                                 // I1, D1, i1, d1 (CT:210-213)
-            const int ch1 = (lane & 2 ? 14 : 5) + (lane & 1 ? 2 : 0);
-            cnt[ch1] = lane == 0 ? best[0] : lane == 1 ? best[1] : lane == 2 ? best[2] : best[3];
-        }
+        #pragma unroll
+        for (int ch = 0; ch < N_CH; ch += 2)
+            *reinterpret_cast<uint32_t*>(o + ch) = (uint32_t)(uint16_t)v[ch] | ((uint32_t)(uint16_t)v[ch + 1] << 16);
     }
-    __syncwarp();
+    __syncthreads();
 
-    if (is_center && depth_out) {                       // depth of alt_info (CT:167-195, 208)
-        int d = 0;
-        if (lane < 18) {
-            const int ch = lane;
-            const bool counted = ch != 5 && ch != 7 && ch != 14 && ch != 16;
-            d = counted ? cnt[ch] : 0;
-        }
-        d = __reduce_add_sync(0xffffffffu, d);
-        if (lane == 0) depth_out[slot / N_POS] = d;
-    }
-
-    // reference channel := -(sum of the four base counts) in each of the six groups (CT:223-228)
-    #pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-        const int ch = lane + rep * 32;
-        if (ch < N_CH) {
-            int v = cnt[ch];
-            int g = -1;
-            if (ch < 4) g = 0;
-            else if (ch >= 9 && ch < 13) g = 9;
-            else if (ch >= 18) g = 18 + ((ch - 18) & ~3);
-            if (g >= 0 && ch - g == ref) v = -(cnt[g] + cnt[g + 1] + cnt[g + 2] + cnt[g + 3]);
-            out[ch] = (int16_t)v;
-        }
+    // coalesced 16-byte stores of the group's contiguous output block
+    const int64_t out_byte0 = slot0 * N_CH * 2;
+    const int64_t total_bytes = n_slots * N_CH * 2;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(s_out);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(tensor) + out_byte0;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const int64_t remain = total_bytes - out_byte0;
+    const int n_bytes = (int)(remain < OUT_BYTES ? remain : OUT_BYTES);
+    if (vec_ok) {
+        for (int b = tid * 16; b + 16 <= n_bytes; b += THREADS * 16)
+            *reinterpret_cast<uint4*>(dst + b) = *reinterpret_cast<const uint4*>(src + b);
+        const int tail = n_bytes & ~15;
+        if (tid < n_bytes - tail) dst[tail + tid] = src[tail + tid];
+    } else {
+        for (int b = tid * 2; b < n_bytes; b += THREADS * 2)
+            *reinterpret_cast<uint16_t*>(dst + b) = *reinterpret_cast<const uint16_t*>(src + b);
     }
 }
+
+constexpr int SMEM_BYTES = 3 * STAGE_CAP + N_FIELDS * THREADS * 2 + SLOTS * N_CH * 2 + 16;
+
+}  // namespace enc
 
 int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq,
                          const int32_t* pos_off, const uint8_t* ref_code, const int32_t* ind_off,
@@ -189,9 +233,14 @@ int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* 
                          int low_bq_cut, int16_t* tensor, int32_t* depth, cudaStream_t stream) {
     if (n_candidates <= 0) return 0;
     const int64_t n_slots = n_candidates * N_POS;
-    const int64_t grid = (n_slots + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int64_t grid = (n_candidates + enc::GROUP - 1) / enc::GROUP;
     CTO_REQUIRE(grid < (1ll << 31), "encode_pileup: too many candidates in one launch (%lld)", (long long)n_candidates);
-    encode_pileup_kernel<<<(unsigned)grid, WARPS_PER_CTA * 32, 0, stream>>>(
+    static bool attr = false;
+    if (!attr) {
+        CTO_CHECK(cudaFuncSetAttribute(enc::encode_pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, enc::SMEM_BYTES));
+        attr = true;
+    }
+    enc::encode_pileup_kernel<<<(unsigned)grid, enc::THREADS, enc::SMEM_BYTES, stream>>>(
         code, bq, mq, pos_off, ref_code, ind_off, ind_entry, win_pos, n_slots, low_bq_cut, tensor, depth);
     CTO_CHECK(cudaGetLastError());
     count_launch();
