@@ -36,6 +36,9 @@ SIGNATURES = {
     "cto_gemm_nt": (INT, [P, I64, P, P, P, I64, P, I64, I64, INT, INT, INT, INT, P]),
     "cto_posterior_from_probs": (INT, [P, INT, P, P, I64, P, P, P]),
     "cto_launch_count": (I64, []),
+    "cto_debug_set": (None, [INT]),
+    "cto_debug_timing": (None, [P]),
+    "cto_debug_gru_cluster": (None, [INT]),
     "cto_engine_profile": (INT, [P, INT]),
     "cto_engine_profile_kinds": (INT, []),
     "cto_engine_profile_name": (C.c_char_p, [INT]),

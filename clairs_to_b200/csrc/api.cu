@@ -28,6 +28,7 @@ int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* 
 
 }  // namespace cto
 
+namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; extern int g_gru_cluster; extern long long* g_gru_timing; }
 using namespace cto;
 
 struct cto_engine {
@@ -197,6 +198,10 @@ int cto_posterior_from_probs(const double* tables_host, int n_heads, const doubl
 
 int64_t cto_launch_count(void) { return launches(); }
 
+void cto_debug_set(int flags) { cto::g_gemm_debug = flags; }
+void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; cto::g_gru_timing = dev_buf ? dev_buf + 24 : nullptr; }
+void cto_debug_gru_cluster(int c) { if (c == 1 || c == 2 || c == 4) cto::g_gru_cluster = c; }
+
 int cto_engine_set_tensor_cores(cto_engine* h, int enable) {
     CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");
     h->e.use_tc = enable != 0;
@@ -222,7 +227,7 @@ int cto_gemm_nt(const float* a, int64_t lda, const float* w, const float* bias, 
 
 int cto_engine_profile(cto_engine* h, int enable) {
     CTO_REQUIRE(h, "engine_profile: NULL engine");
-    h->e.profile = enable != 0;
+    h->e.profile = enable < 0 ? 0 : enable;
     return 0;
 }
 

@@ -206,7 +206,8 @@ void engine_free(Engine& e) {
 }
 
 const char* prof_kind_name(int kind) {
-    static const char* names[PK_COUNT] = {"aff_forward", "neg_proj1_gemm", "neg_gru1_recurrent", "neg_proj2_gemm",
+    static const char* names[PK_COUNT] = {"aff_forward", "aff_gemm_1x1", "aff_embed_conv", "aff_channel_ln", "aff_dwconv", "aff_attention",
+                                          "aff_heads", "neg_proj1_gemm", "neg_gru1_recurrent", "neg_proj2_gemm",
                                           "neg_gru2_recurrent", "neg_fc1_gemm", "neg_heads"};
     return (kind >= 0 && kind < PK_COUNT) ? names[kind] : "?";
 }
@@ -236,8 +237,15 @@ static int take_event(Engine& e, cudaEvent_t* ev) {
     return 0;
 }
 
+static bool prof_wanted(const Engine& e, int kind) {
+    if (!e.profile) return false;
+    const bool fine = kind >= PK_AFF_GEMM && kind <= PK_AFF_HEADS;
+    return e.profile >= 2 ? kind != PK_AFF : !fine;
+}
+
 int prof_begin(Engine& e, int kind, cudaStream_t s) {
-    if (!e.profile) return 0;
+    e.prof_open = prof_wanted(e, kind);
+    if (!e.prof_open) return 0;
     Engine::ProfRec r{kind, nullptr, nullptr};
     if (take_event(e, &r.start) || take_event(e, &r.stop)) return 1;
     CTO_CHECK(cudaEventRecord(r.start, s));
@@ -246,7 +254,8 @@ int prof_begin(Engine& e, int kind, cudaStream_t s) {
 }
 
 int prof_end(Engine& e, cudaStream_t s) {
-    if (!e.profile) return 0;
+    if (!e.prof_open) return 0;
+    e.prof_open = false;
     CTO_CHECK(cudaEventRecord(e.prof.back().stop, s));
     return 0;
 }
@@ -295,36 +304,70 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
     CTO_REQUIRE(n <= e.max_batch, "aff_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
     const AffModel& m = e.aff;
     const float* cur = x;
-    RUN(prof_begin(e, PK_AFF, s));
+    cudaEvent_t aff_start = nullptr, aff_stop = nullptr;
+    if (e.profile == 1) {                      // AFF as one block (its parts are only timed at level 2)
+        RUN(prof_begin(e, PK_AFF, s));
+        aff_start = e.prof.back().start;
+        aff_stop = e.prof.back().stop;
+        e.prof_open = false;
+    }
     for (int si = 0; si < m.n_stages; ++si) {
         const CvtStage& st = m.st[si];
         const int c = st.c, inner = st.heads * DIM_HEAD;
         const int64_t rows = n * st.wout, rows_kv = n * st.wkv;
         // embed conv (3-tap, stride 2, pad 1) + channel LN  (clairs/model.py:195-196)
+        RUN(prof_begin(e, PK_AFF_EMBED, s));
         RUN(gemm(e, conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows, c,
                            3 * st.cin, ACT_NONE, s));
+        RUN(prof_end(e, s));
+        RUN(prof_begin(e, PK_AFF_LN, s));
         RUN(launch_channel_ln(e.a_t0, st.ln_g, st.ln_b, e.a_xs, rows, c, s));
+        RUN(prof_end(e, s));
         for (int d = 0; d < st.depth; ++d) {
             const CvtLayer& L = st.layers[d];
             // x = Attention(LN(x)) + x   (clairs/model.py:145)
-            RUN(launch_channel_ln(e.a_xs, L.ln1_g, L.ln1_b, e.a_y, rows, c, s));
-            RUN(launch_dwconv3(e.a_y, L.q_dw, e.a_dq, n, st.wout, st.wout, 1, c, s));
-            RUN(launch_dwconv3(e.a_y, L.kv_dw, e.a_dkv, n, st.wout, st.wkv, 2, c, s));
-            RUN(gemm(e, plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c, ACT_NONE, s));
-            RUN(gemm(e, plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv, 2 * inner, c,
+            RUN(prof_begin(e, PK_AFF_LN, s));
+        RUN(launch_channel_ln(e.a_xs, L.ln1_g, L.ln1_b, e.a_y, rows, c, s));
+        RUN(prof_end(e, s));
+            RUN(prof_begin(e, PK_AFF_DWCONV, s));
+        RUN(launch_dwconv3(e.a_y, L.q_dw, e.a_dq, n, st.wout, st.wout, 1, c, s));
+        RUN(prof_end(e, s));
+            RUN(prof_begin(e, PK_AFF_DWCONV, s));
+        RUN(launch_dwconv3(e.a_y, L.kv_dw, e.a_dkv, n, st.wout, st.wkv, 2, c, s));
+        RUN(prof_end(e, s));
+            RUN(prof_begin(e, PK_AFF_GEMM, s));
+        RUN(gemm(e, plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c, ACT_NONE, s));
+        RUN(prof_end(e, s));
+            RUN(prof_begin(e, PK_AFF_GEMM, s));
+        RUN(gemm(e, plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv, 2 * inner, c,
                                ACT_NONE, s));
-            RUN(launch_attention(e.a_q, e.a_kv, e.a_att, n, st.wout, st.wkv, st.heads, s));
-            RUN(gemm(e, plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner, ACT_NONE, s));
+        RUN(prof_end(e, s));
+            RUN(prof_begin(e, PK_AFF_ATTENTION, s));
+        RUN(launch_attention(e.a_q, e.a_kv, e.a_att, n, st.wout, st.wkv, st.heads, s));
+        RUN(prof_end(e, s));
+            RUN(prof_begin(e, PK_AFF_GEMM, s));
+        RUN(gemm(e, plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner, ACT_NONE, s));
+        RUN(prof_end(e, s));
             // x = FF(LN(x)) + x          (clairs/model.py:146)
-            RUN(launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, e.a_y, rows, c, s));
-            RUN(gemm(e, plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
-            RUN(gemm(e, plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c, ACT_NONE, s));
+            RUN(prof_begin(e, PK_AFF_LN, s));
+        RUN(launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, e.a_y, rows, c, s));
+        RUN(prof_end(e, s));
+            RUN(prof_begin(e, PK_AFF_GEMM, s));
+        RUN(gemm(e, plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
+        RUN(prof_end(e, s));
+            RUN(prof_begin(e, PK_AFF_GEMM, s));
+        RUN(gemm(e, plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c, ACT_NONE, s));
+        RUN(prof_end(e, s));
         }
         // the next stage reads a_xs while writing a_t0, so no copy is needed
         cur = e.a_xs;
     }
+    RUN(prof_begin(e, PK_AFF_HEADS, s));
     RUN(run_heads(e, m.head, cur, m.feat, m.n_heads, n, e.f1, e.f2, logits, s));
-    return prof_end(e, s);
+    RUN(prof_end(e, s));
+    if (aff_stop) CTO_CHECK(cudaEventRecord(aff_stop, s));
+    (void)aff_start;
+    return 0;
 }
 
 int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {

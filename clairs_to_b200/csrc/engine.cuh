@@ -74,13 +74,14 @@ struct Engine {
     std::vector<void*> allocs;
     bool use_tc = true;                                        // dense contractions on tcgen05 (TF32) where shapes allow
     // optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
-    bool profile = false;
+    int profile = 0;           // 0 off, 1 = NEG kernel families + AFF as one block, 2 = every AFF kernel family too
     struct ProfRec { int kind; cudaEvent_t start, stop; };
     std::vector<ProfRec> prof;
+    bool prof_open = false;
     std::vector<cudaEvent_t> ev_free;
 };
 
-enum ProfKind { PK_AFF = 0, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
+enum ProfKind { PK_AFF = 0, PK_AFF_GEMM, PK_AFF_EMBED, PK_AFF_LN, PK_AFF_DWCONV, PK_AFF_ATTENTION, PK_AFF_HEADS, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
 const char* prof_kind_name(int kind);
 double prof_kind_flops_per_candidate(const Engine& e, int kind);
 int prof_begin(Engine& e, int kind, cudaStream_t s);

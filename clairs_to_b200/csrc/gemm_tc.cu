@@ -108,12 +108,17 @@ __device__ __forceinline__ float selu(float x) {
     return scale * (x > 0.0f ? x : alpha * expm1f(x));
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_whi,
                    const __grid_constant__ CUtensorMap tma_wlo, const __grid_constant__ CUtensorMap tma_c,
                    const float* __restrict__ bias, const float* residual, int64_t ldr, int64_t m_total, int n_total,
-                   int k_total, int bn, int act) {
+                   int k_total, int bn, int dbg, long long* timing) {
     extern __shared__ uint8_t smem_raw[];
+    const bool tim = (dbg & 16) && blockIdx.x == 0 && timing != nullptr;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    #define TIC long long _t0 = tim ? clock64() : 0
+    #define TOC(i) do { if (tim) { long long _t1 = clock64(); tacc[i] += _t1 - _t0; _t0 = _t1; } } while (0)
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = base + STAGES * STAGE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(staging + 2 * STAGING_BYTES);
@@ -152,14 +157,18 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    TIC;
                     mbar_wait(&empty[s], ph ^ 1);
+                    TOC(0);
                     mbar_expect_tx(&full[s], tx);
                     uint8_t* st = base + s * STAGE_BYTES;
                     tma_load_2d(&tma_a, &full[s], st, kb * BK, m0);
                     tma_load_2d(&tma_whi, &full[s], st + 2 * TILE_BYTES, kb * BK, n0);
                     tma_load_2d(&tma_wlo, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
+                    TOC(1);
                 }
             }
+            if (tim) { timing[0] = tacc[0]; timing[1] = tacc[1]; }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                   // ---- MMA issuer ----
@@ -167,14 +176,18 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             uint32_t it = 0, acc_it = 0;
             for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
                 const uint32_t ab = acc_it & 1, aph = (acc_it >> 1) & 1;
+                TIC;
                 mbar_wait(&acc_empty[ab], aph ^ 1);        // epilogue has drained this accumulator
+                TOC(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + ab * MAX_BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);               // W tiles landed
+                    TOC(1);
                     mbar_wait(&conv[s], ph);               // A split into hi / lo
+                    TOC(2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = smem_u32(base + s * STAGE_BYTES);
                     const uint64_t d_ahi = make_desc_k_sw128(a_addr);
@@ -186,13 +199,17 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         // 8 tf32 = 32 bytes along the swizzle row: +2 in the (>>4) start-address field
                         const uint64_t o = (uint64_t)(k * 2);
                         mma_tf32(acc, d_ahi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
-                        mma_tf32(acc, d_alo + o, d_whi + o, idesc, 1u);
-                        mma_tf32(acc, d_ahi + o, d_wlo + o, idesc, 1u);
+                        if (!(dbg & 8)) {
+                            mma_tf32(acc, d_alo + o, d_whi + o, idesc, 1u);
+                            mma_tf32(acc, d_ahi + o, d_wlo + o, idesc, 1u);
+                        }
                     }
                     tcgen05_commit(&empty[s]);             // stage reusable once these MMAs retire
+                    TOC(3);
                 }
                 tcgen05_commit(&acc_full[ab]);             // accumulator complete
             }
+            if (tim) { for (int i = 0; i < 4; ++i) timing[4 + i] = tacc[i]; }
         }
     } else if (warp < 6) {                                 // ---- converter: warps 2..5 ----
         const int ct = threadIdx.x - 64;                   // 0..127
@@ -201,9 +218,12 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
+                TIC;
                 mbar_wait(&full[s], ph);
+                TOC(0);
                 float4* a_hi = reinterpret_cast<float4*>(base + s * STAGE_BYTES);
                 float4* a_lo = reinterpret_cast<float4*>(base + s * STAGE_BYTES + TILE_BYTES);
+                if (!(dbg & 2))
                 #pragma unroll
                 for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {       // elementwise: the swizzle is irrelevant
                     const int idx = ct + i * 128;
@@ -214,10 +234,13 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     a_hi[idx] = hi;
                     a_lo[idx] = lo;
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> UMMA reads
+                TOC(1);
+                if (!(dbg & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> UMMA reads
+                TOC(2);
                 mbar_arrive(&conv[s]);
             }
         }
+        if (tim && ct == 0) { for (int i = 0; i < 3; ++i) timing[8 + i] = tacc[i]; }
     } else {                                               // ---- epilogue: warps 6..9 ----
         const int quad = warp & 3;                         // TMEM lanes [32*quad, 32*quad+32)
         const int et = threadIdx.x - 192;                  // 0..127
@@ -226,7 +249,9 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
             const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * bn;
             const uint32_t ab = acc_it & 1, aph = (acc_it >> 1) & 1;
+            TIC;
             mbar_wait(&acc_full[ab], aph);
+            TOC(0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = (int64_t)m0 + r_in_tile;
             const bool row_ok = row < m_total;
@@ -242,6 +267,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                TOC(1);
                 if (cb + SLAB >= bn) {                     // accumulator fully read: hand it back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&acc_empty[ab]);
@@ -250,17 +276,20 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 // the TMA store that last read this staging buffer (two slabs ago) must have finished reading it
                 if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+                TOC(2);
                 const float* rrow = (residual && row_ok) ? residual + row * ldr + n0 + cb : nullptr;
                 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float v[4];
-                    #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x = __uint_as_float(r[q * 4 + e]);
-                        if (bias) x += __ldg(bias + n0 + cb + q * 4 + e);
-                        if (act == ACT_GELU) x = gelu_erf(x);
-                        else if (act == ACT_SELU) x = selu(x);
-                        v[e] = x;
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + cb) + q);
+                    float v[4] = {__uint_as_float(r[q * 4]) + bv.x, __uint_as_float(r[q * 4 + 1]) + bv.y,
+                                  __uint_as_float(r[q * 4 + 2]) + bv.z, __uint_as_float(r[q * 4 + 3]) + bv.w};
+                    if (ACT == ACT_GELU) {
+                        #pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = gelu_erf(v[e]);
+                    } else if (ACT == ACT_SELU) {
+                        #pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = selu(v[e]);
                     }
                     if (rrow) {
                         const float4 rv = *reinterpret_cast<const float4*>(rrow + q * 4);
@@ -270,15 +299,19 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     *reinterpret_cast<float4*>(stg + r_in_tile * 128 + ((q ^ (r_in_tile & 7)) << 4)) =
                         make_float4(v[0], v[1], v[2], v[3]);
                 }
+                TOC(3);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                TOC(4);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
+                TOC(5);
+                if (et == 0 && !(dbg & 4)) {
                     tma_store_2d(&tma_c, stg, n0 + cb, m0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
         if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (tim && et == 0) { for (int i = 0; i < 6; ++i) timing[12 + i] = tacc[i]; timing[20] = (long long)num_tiles; timing[21] = num_kb; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -328,6 +361,9 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
 
 }  // namespace tc
 
+long long* g_gemm_timing = nullptr;   // device buffer [32] filled by CTA 0 when (dbg & 16)
+int g_gemm_debug = 0;       // timing experiments only (results are wrong when non-zero); see cto_debug_set
+
 int launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s) {
     if (n <= 0) return 0;
     tc::split_tf32_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w, hi, lo, n);
@@ -364,12 +400,19 @@ int launch_gemm_tc(const float* a, int64_t lda, const float* w_hi, const float* 
         int dev = 0;
         CTO_CHECK(cudaGetDevice(&dev));
         CTO_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel<ACT_SELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     }
     const int64_t tiles = (int64_t)ceil_div(m, tc::BM) * (n / bn);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    tc::gemm_3xtf32_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_whi, map_wlo, map_c, bias, residual, ldr,
-                                                                    m, n, k, bn, act);
+#define CTO_LAUNCH_GEMM(A)                                                                                     \
+    tc::gemm_3xtf32_kernel<A><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_whi, map_wlo, map_c, bias, residual, \
+                                                                       ldr, m, n, k, bn, g_gemm_debug, g_gemm_timing)
+    if (act == ACT_GELU) CTO_LAUNCH_GEMM(ACT_GELU);
+    else if (act == ACT_SELU) CTO_LAUNCH_GEMM(ACT_SELU);
+    else CTO_LAUNCH_GEMM(ACT_NONE);
+#undef CTO_LAUNCH_GEMM
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

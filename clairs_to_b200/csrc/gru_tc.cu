@@ -50,6 +50,24 @@ __device__ __forceinline__ void g_tma_load_2d(const CUtensorMap* map, uint64_t* 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(g_smem_u32(dst)), "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void g_tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(g_smem_u32(dst)), "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void g_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(g_smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t g_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void g_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void g_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(g_smem_u32(bar)) : "memory");
 }
@@ -89,7 +107,7 @@ __device__ __forceinline__ void g_tmem_ld8(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr));
 }
 // gate non-linearities through MUFU.EX2 / MUFU.RCP: absolute error ~1e-7, far inside the 1e-3 contract
-__device__ __forceinline__ float g_sigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float g_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float g_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 constexpr int GM = 64;                       // candidates per CTA (MMA M)
@@ -106,13 +124,18 @@ template <int H>
 struct GruSmem {
     static constexpr int KB = H / GK;        // k-blocks (and also unit blocks)
     static constexpr int H_BYTES = 2 * KB * G_HTILE;
-    static constexpr int TOTAL = H_BYTES + G_STAGES * G_STAGE + 1024 + 256;
+    static constexpr int TOTAL = H_BYTES + G_STAGES * G_STAGE + 1024 + 256 + H * 4;
 };
 
-template <int H>
+template <int H, int C>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__ CUtensorMap tma_wlo,
-              const float* __restrict__ xproj, const float* __restrict__ bhn, float* __restrict__ out, int64_t batch) {
+              const float* __restrict__ xproj, const float* __restrict__ bhn, float* __restrict__ out, int64_t batch,
+              long long* timing) {
+    const bool tim = timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    #define GTIC long long _t0 = tim ? clock64() : 0
+    #define GTOC(i) do { if (tim) { long long _t1 = clock64(); tacc[i] += _t1 - _t0; _t0 = _t1; } } while (0)
     constexpr int KB = H / GK;               // 4 (H=128) or 6 (H=192)
     constexpr int NB = H / GBLK;             // unit blocks, == KB
     constexpr int PAIRS = NB / 2;
@@ -124,16 +147,23 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
     uint8_t* wring = base + 2 * KB * G_HTILE;
     uint64_t* full = reinterpret_cast<uint64_t*>(wring + G_STAGES * G_STAGE);
     uint64_t* empty = full + G_STAGES;
-    uint64_t* acc_full = empty + G_STAGES;
-    uint64_t* h_ready = acc_full + 1;
+    uint64_t* acc_full = empty + G_STAGES;                 // one per unit-block pair
+    uint64_t* h_ready = acc_full + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
+    float* s_bhn = reinterpret_cast<float*>(tmem_slot + 4);      // b_hn of this direction (L1 is ~empty: smem is full)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
+    for (int i = threadIdx.x; i < H; i += G_THREADS) s_bhn[i] = bhn[dir * H + i];
+    // cluster of C CTAs (same direction, different candidates): every W_hh stage is fetched from L2 once per
+    // cluster - each CTA loads 1/C of the rows and multicasts them into all C shared memories
+    const uint32_t crank = C > 1 ? g_cluster_rank() : 0;
+    constexpr uint16_t CMASK = (uint16_t)((1u << C) - 1);
+    constexpr int SLICE_ROWS = GN / C;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G_STAGES; ++s) { g_mbar_init(&full[s], 1); g_mbar_init(&empty[s], 1); }
-        g_mbar_init(acc_full, 1);
+        for (int s = 0; s < G_STAGES; ++s) { g_mbar_init(&full[s], 1); g_mbar_init(&empty[s], C); }
+        for (int p = 0; p < 3; ++p) g_mbar_init(&acc_full[p], 1);
         g_mbar_init(h_ready, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -143,6 +173,7 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (C > 1) g_cluster_sync();                           // every CTA's barriers exist before any remote arrive
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -158,8 +189,14 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
                         g_mbar_expect_tx(&full[s], G_STAGE);
                         uint8_t* st = wring + s * G_STAGE;
                         const int row = dir * 3 * H + blk * GN;
-                        g_tma_load_2d(&tma_whi, &full[s], st, kb * GK, row);
-                        g_tma_load_2d(&tma_wlo, &full[s], st + G_WTILE, kb * GK, row);
+                        if (C == 1) {
+                            g_tma_load_2d(&tma_whi, &full[s], st, kb * GK, row);
+                            g_tma_load_2d(&tma_wlo, &full[s], st + G_WTILE, kb * GK, row);
+                        } else {
+                            const int off = (int)crank * SLICE_ROWS;
+                            g_tma_load_2d_mc(&tma_whi, &full[s], st + off * 128, kb * GK, row + off, CMASK);
+                            g_tma_load_2d_mc(&tma_wlo, &full[s], st + G_WTILE + off * 128, kb * GK, row + off, CMASK);
+                        }
                     }
                 }
             }
@@ -170,7 +207,9 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
             uint32_t it = 0;
             for (int step = 0; step < N_POS; ++step) {
+                GTIC;
                 g_mbar_wait(h_ready, step & 1);            // h_{t-1} (hi/lo) is in smem, accumulators drained
+                GTOC(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int blk = 0; blk < NB; ++blk) {
                     const uint32_t acc = tmem_base + ((uint32_t)((blk & 1) * 16) << 16) + (uint32_t)((blk >> 1) * GN);
@@ -178,6 +217,7 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
                         const int s = it % G_STAGES;
                         const uint32_t ph = (it / G_STAGES) & 1;
                         g_mbar_wait(&full[s], ph);
+                        GTOC(1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t d_hhi = g_desc_k_sw128(g_smem_u32(h_hi + kb * G_HTILE));
                         const uint64_t d_hlo = g_desc_k_sw128(g_smem_u32(h_lo + kb * G_HTILE));
@@ -191,11 +231,14 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
                             g_mma_tf32(acc, d_hlo + o, d_whi + o, idesc, 1u);
                             g_mma_tf32(acc, d_hhi + o, d_wlo + o, idesc, 1u);
                         }
-                        g_commit(&empty[s]);
+                        if (C == 1) g_commit(&empty[s]);
+                        else g_commit_mc(&empty[s], CMASK);     // frees the stage in every CTA of the cluster
+                        GTOC(2);
                     }
+                    if (blk & 1) g_commit(&acc_full[blk >> 1]);  // both unit blocks of this pair are accumulated
                 }
-                g_commit(acc_full);
             }
+            if (tim) { timing[0] = tacc[0]; timing[1] = tacc[1]; timing[2] = tacc[2]; }
         }
     } else {                                               // ---- gate math: warps 2..9 ----
         // two warps per TMEM lane quadrant; thread = (candidate row m, unit block parity `sub`, 16-unit half `part`)
@@ -219,7 +262,7 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         g_mbar_arrive(h_ready);
 
-        const float* bhn_d = bhn + dir * H;
+        const float* bhn_d = s_bhn;
         constexpr int ITERS = PAIRS * 2;                   // 8 units per iteration
         float4 xq[6];                                      // prefetched xproj: r(2) z(2) n(2) float4
         auto prefetch = [&](int step, int i) {
@@ -237,14 +280,33 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
         for (int step = 0; step < N_POS; ++step) {
             const int t = dir ? (N_POS - 1 - step) : step;
             float* op = out + (b * N_POS + t) * (int64_t)(2 * H) + dir * H;
-            g_mbar_wait(acc_full, step & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            #pragma unroll 1
+            // pull the xproj lines of the NEXT step into L2 now (the register prefetch is one iteration deep)
+            if (step + 1 < N_POS) {
+                const int tn = dir ? (N_POS - 2 - step) : step + 1;
+                const float* xn = xproj + (b * N_POS + tn) * (int64_t)(6 * H) + dir * 3 * H + sub * GBLK + part * 16;
+                #pragma unroll
+                for (int p = 0; p < PAIRS; ++p)
+                    #pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + 2 * p * GBLK + g * H));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + 2 * p * GBLK + g * H + 8));
+                    }
+            }
+            // h_t of this thread's units stays in registers until every MMA of the step has read h_{t-1}:
+            // the gate math of unit-block pair p overlaps the MMAs of the pairs behind it
+            float hk[PAIRS * 16];
+            GTIC;
+            #pragma unroll
             for (int i = 0; i < ITERS; ++i) {
                 const int p = i >> 1;
                 const int blk = 2 * p + sub;
                 const int uu = blk * GBLK + part * 16 + (i & 1) * 8;       // first of this iteration's 8 units
                 const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p * GN + part * 16 + (i & 1) * 8);
+                if ((i & 1) == 0) {
+                    g_mbar_wait(&acc_full[p], step & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (i == 0) GTOC(3);
+                }
                 uint32_t ar[8], az[8], an[8];
                 g_tmem_ld8(tcol, ar);
                 g_tmem_ld8(tcol + GBLK, az);
@@ -260,12 +322,11 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
                 for (int q = 0; q < 2; ++q) {
                     const float4 bn = *reinterpret_cast<const float4*>(bhn_d + uu + q * 4);
                     const uint32_t chunk = (uint32_t)(((part * 4 + (i & 1) * 2 + q) ^ (m & 7)) << 4);
-                    float4* p_hi = reinterpret_cast<float4*>(h_hi + blk * G_HTILE + row_off + chunk);
-                    float4* p_lo = reinterpret_cast<float4*>(h_lo + blk * G_HTILE + row_off + chunk);
-                    const float4 ohi = *p_hi, olo = *p_lo;
+                    const float4 ohi = *reinterpret_cast<const float4*>(h_hi + blk * G_HTILE + row_off + chunk);
+                    const float4 olo = *reinterpret_cast<const float4*>(h_lo + blk * G_HTILE + row_off + chunk);
                     const float hp[4] = {ohi.x + olo.x, ohi.y + olo.y, ohi.z + olo.z, ohi.w + olo.w};
                     const float bnv[4] = {bn.x, bn.y, bn.z, bn.w};
-                    float hn[4], hh[4], hl[4];
+                    float hn[4];
                     #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = q * 4 + e;
@@ -273,21 +334,40 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
                         const float z = g_sigmoid(xv[8 + c] + __uint_as_float(az[c]));
                         const float n = g_tanh(xv[16 + c] + r * (__uint_as_float(an[c]) + bnv[e]));
                         hn[e] = (1.0f - z) * n + z * hp[e];
-                        hh[e] = g_round_tf32(hn[e]);
-                        hl[e] = hn[e] - hh[e];
+                        hk[i * 8 + c] = hn[e];
                     }
-                    *p_hi = make_float4(hh[0], hh[1], hh[2], hh[3]);
-                    *p_lo = make_float4(hl[0], hl[1], hl[2], hl[3]);
                     if (b_ok) *reinterpret_cast<float4*>(op + uu + q * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                }
+            }
+            GTOC(4);
+            // the last pair's barrier implies all MMAs of this step retired: h_{t-1} may now be overwritten
+            #pragma unroll
+            for (int i = 0; i < ITERS; ++i) {
+                const int blk = 2 * (i >> 1) + sub;
+                #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const uint32_t chunk = (uint32_t)(((part * 4 + (i & 1) * 2 + q) ^ (m & 7)) << 4);
+                    float hh[4], hl[4];
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float v = hk[i * 8 + q * 4 + e];
+                        hh[e] = g_round_tf32(v);
+                        hl[e] = v - hh[e];
+                    }
+                    *reinterpret_cast<float4*>(h_hi + blk * G_HTILE + row_off + chunk) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                    *reinterpret_cast<float4*>(h_lo + blk * G_HTILE + row_off + chunk) = make_float4(hl[0], hl[1], hl[2], hl[3]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             g_mbar_arrive(h_ready);
+            GTOC(5);
         }
+        if (tim && threadIdx.x == 64) { timing[3] = tacc[3]; timing[4] = tacc[4]; timing[5] = tacc[5]; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (C > 1) g_cluster_sync();                           // nobody exits while peers may still multicast to it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -298,32 +378,58 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
 
 }  // namespace tc
 
+extern int g_gemm_debug;
+long long* g_gru_timing = nullptr;   // device buffer [8] (debug): per-phase cycles of CTA (0,0)
+
+template <int H, int C>
+static int launch_gru_tc_t(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const float* xproj, const float* bhn,
+                           float* out, int64_t batch, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        CTO_CHECK(cudaFuncSetAttribute(tc::gru_tc_kernel<H, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       tc::GruSmem<H>::TOTAL));
+        attr = true;
+    }
+    const int ctas = ceil_div(batch, tc::GM);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((ctas + C - 1) / C * C), 2, 1);
+    cfg.blockDim = dim3(tc::G_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = tc::GruSmem<H>::TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CTO_CHECK(cudaLaunchKernelEx(&cfg, tc::gru_tc_kernel<H, C>, map_hi, map_lo, xproj, bhn, out, batch, g_gru_timing));
+    return 0;
+}
+
+int g_gru_cluster = 2;      // CTAs per cluster sharing one W_hh stream (1, 2 or 4)
+
 // w_hi / w_lo: [2 directions][3H rows regrouped as (unit block, gate, unit)][H] fp32 (TF32 hi / lo)
 int launch_gru_tc(const float* xproj, const float* w_hi, const float* w_lo, const float* bhn, float* out, int64_t batch,
                   int hidden, cudaStream_t s) {
     if (batch <= 0) return 0;
+    CTO_REQUIRE(hidden == 128 || hidden == 192, "gru_tc: hidden size %d not built (128 and 192 are, clairs/model.py:403-404)",
+                hidden);
+    const int c = g_gru_cluster;
     CUtensorMap map_hi, map_lo;
-    if (tc::make_map(&map_hi, w_hi, 6 * hidden, hidden, hidden, tc::GN)) return 1;
-    if (tc::make_map(&map_lo, w_lo, 6 * hidden, hidden, hidden, tc::GN)) return 1;
-    dim3 grid(ceil_div(batch, tc::GM), 2);
-    static bool attr128 = false, attr192 = false;
+    if (tc::make_map(&map_hi, w_hi, 6 * hidden, hidden, hidden, tc::GN / c)) return 1;
+    if (tc::make_map(&map_lo, w_lo, 6 * hidden, hidden, hidden, tc::GN / c)) return 1;
+    int rc;
     if (hidden == 128) {
-        if (!attr128) {
-            CTO_CHECK(cudaFuncSetAttribute(tc::gru_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tc::GruSmem<128>::TOTAL));
-            attr128 = true;
-        }
-        tc::gru_tc_kernel<128><<<grid, tc::G_THREADS, tc::GruSmem<128>::TOTAL, s>>>(map_hi, map_lo, xproj, bhn, out, batch);
-    } else if (hidden == 192) {
-        if (!attr192) {
-            CTO_CHECK(cudaFuncSetAttribute(tc::gru_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tc::GruSmem<192>::TOTAL));
-            attr192 = true;
-        }
-        tc::gru_tc_kernel<192><<<grid, tc::G_THREADS, tc::GruSmem<192>::TOTAL, s>>>(map_hi, map_lo, xproj, bhn, out, batch);
+        rc = c == 4 ? launch_gru_tc_t<128, 4>(map_hi, map_lo, xproj, bhn, out, batch, s)
+           : c == 2 ? launch_gru_tc_t<128, 2>(map_hi, map_lo, xproj, bhn, out, batch, s)
+                    : launch_gru_tc_t<128, 1>(map_hi, map_lo, xproj, bhn, out, batch, s);
     } else {
-        CTO_REQUIRE(false, "gru_tc: hidden size %d not built (128 and 192 are, clairs/model.py:403-404)", hidden);
+        rc = c == 4 ? launch_gru_tc_t<192, 4>(map_hi, map_lo, xproj, bhn, out, batch, s)
+           : c == 2 ? launch_gru_tc_t<192, 2>(map_hi, map_lo, xproj, bhn, out, batch, s)
+                    : launch_gru_tc_t<192, 1>(map_hi, map_lo, xproj, bhn, out, batch, s);
     }
+    if (rc) return rc;
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

@@ -121,6 +121,15 @@ int cto_engine_profile_kinds(void);
 const char* cto_engine_profile_name(int kind);
 int cto_engine_profile_read(cto_engine* e, double* ms, int64_t* launches, double* flops_per_candidate);
 
+/*
+ * Tuning / debugging knobs (not part of the drop-in surface): timing-experiment flags for the GEMM kernel
+ * (results are wrong when non-zero), a device buffer [32 x int64] for its per-phase cycle counters, and the
+ * thread-block-cluster size (1, 2 or 4) that shares one W_hh stream in the tensor-core GRU.
+ */
+void cto_debug_set(int flags);
+void cto_debug_timing(long long* dev_buf);
+void cto_debug_gru_cluster(int ctas_per_cluster);
+
 /* Strand-count recovery of clairs/predict.py:626-642 from the un-rescaled AFF tensor: int32 [n,4] x2. */
 int cto_strand_counts(const int16_t* x_aff_dev, int64_t n, int32_t* fwd_dev, int32_t* rev_dev, void* stream);
 

@@ -263,3 +263,20 @@ def test_full_size_properties(eng4):
     assert np.abs(a['probs'].cpu().numpy() - b['probs'].cpu().numpy()[perm]).max() < 1e-5
     assert np.isfinite(b['probs'].cpu().numpy()).all()
     assert np.allclose(b['probs'].cpu().numpy().sum(-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+def test_gru_cluster_multicast_sizes(golden_dir, cluster):
+    """The tensor-core GRU shares one W_hh stream per thread-block cluster (TMA multicast); every
+    cluster size must give the same logits (and odd CTA counts exercise the padded cluster)."""
+    eng, _, neg_sd = _engine(4, max_batch=512)
+    eng.lib.cto_debug_gru_cluster(cluster)
+    try:
+        rng = np.random.default_rng(cluster)
+        x = torch.from_numpy(rng.integers(-50, 51, size=(200, 33, 34)).astype(np.float32))   # 4 CTAs per direction, last one partial
+        got = eng.forward_neg(x).cpu().numpy()
+        want = nn_oracle.neg_forward(x.numpy(), neg_sd).numpy()
+        assert np.abs(got - want).max() < TOL
+    finally:
+        eng.lib.cto_debug_gru_cluster(2)
+        eng.close()
