@@ -326,15 +326,9 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         for (int d = 0; d < st.depth; ++d) {
             const CvtLayer& L = st.layers[d];
             // x = Attention(LN(x)) + x   (clairs/model.py:145)
-            RUN(prof_begin(e, PK_AFF_LN, s));
-        RUN(launch_channel_ln(e.a_xs, L.ln1_g, L.ln1_b, e.a_y, rows, c, s));
-        RUN(prof_end(e, s));
             RUN(prof_begin(e, PK_AFF_DWCONV, s));
-        RUN(launch_dwconv3(e.a_y, L.q_dw, e.a_dq, n, st.wout, st.wout, 1, c, s));
-        RUN(prof_end(e, s));
-            RUN(prof_begin(e, PK_AFF_DWCONV, s));
-        RUN(launch_dwconv3(e.a_y, L.kv_dw, e.a_dkv, n, st.wout, st.wkv, 2, c, s));
-        RUN(prof_end(e, s));
+            RUN(launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, e.a_dq, e.a_dkv, n, st.wout, st.wkv, c, s));
+            RUN(prof_end(e, s));
             RUN(prof_begin(e, PK_AFF_GEMM, s));
         RUN(gemm(e, plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c, ACT_NONE, s));
         RUN(prof_end(e, s));

@@ -115,7 +115,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                    const float* __restrict__ bias, const float* residual, int64_t ldr, int64_t m_total, int n_total,
                    int k_total, int bn, int dbg, long long* timing) {
     extern __shared__ uint8_t smem_raw[];
-    const bool tim = (dbg & 16) && blockIdx.x == 0 && timing != nullptr;
+    const bool tim = dbg && blockIdx.x == 0 && timing != nullptr;    // per-phase cycle counters (profiles/)
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     #define TIC long long _t0 = tim ? clock64() : 0
     #define TOC(i) do { if (tim) { long long _t1 = clock64(); tacc[i] += _t1 - _t0; _t0 = _t1; } } while (0)
@@ -199,10 +199,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         // 8 tf32 = 32 bytes along the swizzle row: +2 in the (>>4) start-address field
                         const uint64_t o = (uint64_t)(k * 2);
                         mma_tf32(acc, d_ahi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
-                        if (!(dbg & 8)) {
-                            mma_tf32(acc, d_alo + o, d_whi + o, idesc, 1u);
-                            mma_tf32(acc, d_ahi + o, d_wlo + o, idesc, 1u);
-                        }
+                        mma_tf32(acc, d_alo + o, d_whi + o, idesc, 1u);
+                        mma_tf32(acc, d_ahi + o, d_wlo + o, idesc, 1u);
                     }
                     tcgen05_commit(&empty[s]);             // stage reusable once these MMAs retire
                     TOC(3);
@@ -223,7 +221,6 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 TOC(0);
                 float4* a_hi = reinterpret_cast<float4*>(base + s * STAGE_BYTES);
                 float4* a_lo = reinterpret_cast<float4*>(base + s * STAGE_BYTES + TILE_BYTES);
-                if (!(dbg & 2))
                 #pragma unroll
                 for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {       // elementwise: the swizzle is irrelevant
                     const int idx = ct + i * 128;
@@ -235,7 +232,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     a_lo[idx] = lo;
                 }
                 TOC(1);
-                if (!(dbg & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> UMMA reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> UMMA reads
                 TOC(2);
                 mbar_arrive(&conv[s]);
             }
@@ -304,7 +301,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 TOC(4);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 TOC(5);
-                if (et == 0 && !(dbg & 4)) {
+                if (et == 0) {
                     tma_store_2d(&tma_c, stg, n0 + cb, m0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
@@ -362,7 +359,7 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
 }  // namespace tc
 
 long long* g_gemm_timing = nullptr;   // device buffer [32] filled by CTA 0 when (dbg & 16)
-int g_gemm_debug = 0;       // timing experiments only (results are wrong when non-zero); see cto_debug_set
+int g_gemm_debug = 0;       // non-zero: CTA 0 records per-phase cycle counters into g_gemm_timing (cto_debug_set)
 
 int launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s) {
     if (n <= 0) return 0;
@@ -389,12 +386,6 @@ int launch_gemm_tc(const float* a, int64_t lda, const float* w_hi, const float* 
                     (reinterpret_cast<uintptr_t>(w_lo) & 15) == 0,
                 "gemm_tc: unsupported shape/alignment m=%lld n=%d k=%d lda=%lld ldc=%lld", (long long)m, n, k,
                 (long long)lda, (long long)ldc);
-    const int bn = (n % 128 == 0) ? 128 : 64;
-    CUtensorMap map_a, map_whi, map_wlo, map_c;
-    if (tc::make_map(&map_a, a, m, k, lda, tc::BM)) return 1;
-    if (tc::make_map(&map_whi, w_hi, n, k, k, bn)) return 1;
-    if (tc::make_map(&map_wlo, w_lo, n, k, k, bn)) return 1;
-    if (tc::make_map(&map_c, c, m, n, ldc, tc::BM)) return 1;
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
@@ -404,6 +395,13 @@ int launch_gemm_tc(const float* a, int64_t lda, const float* w_hi, const float* 
         CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel<ACT_SELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     }
+    // 128-wide tiles unless that leaves SMs without a tile (long-K, few-row GEMMs such as the NEG fc1)
+    const int bn = (n % 128 == 0 && (int64_t)ceil_div(m, tc::BM) * (n / 128) >= sm_count) ? 128 : 64;
+    CUtensorMap map_a, map_whi, map_wlo, map_c;
+    if (tc::make_map(&map_a, a, m, k, lda, tc::BM)) return 1;
+    if (tc::make_map(&map_whi, w_hi, n, k, k, bn)) return 1;
+    if (tc::make_map(&map_wlo, w_lo, n, k, k, bn)) return 1;
+    if (tc::make_map(&map_c, c, m, n, ldc, tc::BM)) return 1;
     const int64_t tiles = (int64_t)ceil_div(m, tc::BM) * (n / bn);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
 #define CTO_LAUNCH_GEMM(A)                                                                                     \

@@ -292,6 +292,83 @@ int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch,
 }
 
 // ------------------------------------------------------------------------------------------
+// fused PreNorm + both depth-wise convolutions of the attention block (M:57-67, 91-97, 112-113):
+//   y = channel_LN(x);  dq = dw3_stride1(y) * BN-scale;  dkv = dw3_stride2(y) * BN-scale
+// One warp per candidate; the candidate's <= 17 x 128 activations stay in shared memory, so x is read
+// once and y never touches HBM.
+// ------------------------------------------------------------------------------------------
+constexpr int LND_WARPS = 4, LND_MAXW = 17, LND_MAXC = 128;
+
+__global__ void __launch_bounds__(LND_WARPS * 32)
+ln_dwconv_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                 const float* __restrict__ taps_q, const float* __restrict__ taps_kv, float* __restrict__ dq,
+                 float* __restrict__ dkv, int64_t batch, int w, int wkv, int c) {
+    __shared__ float sy[LND_WARPS][LND_MAXW][LND_MAXC];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t cand = (int64_t)blockIdx.x * LND_WARPS + wib;
+    if (cand >= batch) return;
+    const float* xc = x + cand * w * c;
+    for (int r = 0; r < w; ++r) {
+        float v[4], sum = 0.0f;
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = lane + 32 * i;
+            v[i] = ch < c ? xc[r * c + ch] : 0.0f;
+            sum += v[i];
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / (float)c;
+        float sq = 0.0f;
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float d = (lane + 32 * i) < c ? v[i] - mean : 0.0f;
+            sq += d * d;
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float denom = sqrtf(sq / (float)c) + 1e-5f;
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ch = lane + 32 * i;
+            if (ch < c) sy[wib][r][ch] = (v[i] - mean) / denom * g[ch] + b[ch];
+        }
+    }
+    __syncwarp();
+    for (int i = 0; i < 4; ++i) {
+        const int ch = lane + 32 * i;
+        if (ch >= c) break;
+        const float q0 = taps_q[ch], q1 = taps_q[c + ch], q2 = taps_q[2 * c + ch];
+        const float k0 = taps_kv[ch], k1 = taps_kv[c + ch], k2 = taps_kv[2 * c + ch];
+        for (int r = 0; r < w; ++r) {
+            float acc = 0.0f;                                   // same tap order as dwconv3_kernel
+            if (r - 1 >= 0) acc = fmaf(sy[wib][r - 1][ch], q0, acc);
+            acc = fmaf(sy[wib][r][ch], q1, acc);
+            if (r + 1 < w) acc = fmaf(sy[wib][r + 1][ch], q2, acc);
+            dq[(cand * w + r) * c + ch] = acc;
+        }
+        for (int r = 0; r < wkv; ++r) {
+            const int s0 = 2 * r - 1;
+            float acc = 0.0f;
+            if (s0 >= 0) acc = fmaf(sy[wib][s0][ch], k0, acc);
+            acc = fmaf(sy[wib][s0 + 1][ch], k1, acc);
+            if (s0 + 2 < w) acc = fmaf(sy[wib][s0 + 2][ch], k2, acc);
+            dkv[(cand * wkv + r) * c + ch] = acc;
+        }
+    }
+}
+
+int launch_ln_dwconv(const float* x, const float* g, const float* b, const float* taps_q, const float* taps_kv, float* dq,
+                     float* dkv, int64_t batch, int w, int wkv, int c, cudaStream_t s) {
+    if (batch <= 0) return 0;
+    CTO_REQUIRE(w <= LND_MAXW && c <= LND_MAXC, "ln_dwconv: W=%d C=%d exceed %d/%d", w, c, LND_MAXW, LND_MAXC);
+    ln_dwconv_kernel<<<ceil_div(batch, LND_WARPS), LND_WARPS * 32, 0, s>>>(x, g, b, taps_q, taps_kv, dq, dkv, batch, w, wkv, c);
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // attention over <= 17 query and <= 9 key positions, dim_head 64 (M:120-132); one warp per
 // (candidate, head).  The 64^-0.5 scale is folded into the q projection on the host.
 // ------------------------------------------------------------------------------------------

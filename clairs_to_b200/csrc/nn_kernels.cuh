@@ -38,6 +38,8 @@ int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_o
 int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s);
 int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch, int win, int wout, int stride,
                    int c, cudaStream_t s);
+int launch_ln_dwconv(const float* x, const float* g, const float* b, const float* taps_q, const float* taps_kv, float* dq,
+                     float* dkv, int64_t batch, int w, int wkv, int c, cudaStream_t s);
 int launch_attention(const float* q, const float* kv, float* out, int64_t batch, int w, int wkv, int heads,
                      cudaStream_t s);
 int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bhn, float* out, int64_t batch,

@@ -122,9 +122,10 @@ const char* cto_engine_profile_name(int kind);
 int cto_engine_profile_read(cto_engine* e, double* ms, int64_t* launches, double* flops_per_candidate);
 
 /*
- * Tuning / debugging knobs (not part of the drop-in surface): timing-experiment flags for the GEMM kernel
- * (results are wrong when non-zero), a device buffer [32 x int64] for its per-phase cycle counters, and the
- * thread-block-cluster size (1, 2 or 4) that shares one W_hh stream in the tensor-core GRU.
+ * Tuning / profiling knobs (not part of the drop-in surface): cto_debug_set(1) + cto_debug_timing(buf) make
+ * CTA 0 of the GEMM and GRU kernels record per-phase clock64() counters into a device buffer [32 x int64]
+ * (profiles/phase_timing.py prints them); cto_debug_gru_cluster sets the thread-block-cluster size (1, 2 or 4)
+ * that shares one W_hh stream (TMA multicast) in the tensor-core GRU.
  */
 void cto_debug_set(int flags);
 void cto_debug_timing(long long* dev_buf);

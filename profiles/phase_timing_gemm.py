@@ -1,5 +1,5 @@
 import sys, ctypes as C, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from clairs_to_b200 import _lib
 from clairs_to_b200.engine import gemm_nt
 lib = _lib.lib()
@@ -10,7 +10,7 @@ names = ["prod.wait_empty","prod.issue","-","-","mma.wait_acc_empty","mma.wait_f
          "conv.wait_full","conv.math","conv.fence","-","epi.wait_acc_full","epi.tmem_ld","epi.waitgrp+bar","epi.math+sts","epi.fence","epi.bar2"]
 for (m,n,k) in [(161024,64,16),(161024,64,64),(9472*33,1152,256),(9472*5,512,128)]:
     a = torch.randn(m,k,device='cuda'); w = torch.randn(n,k,device='cuda')/k**0.5; b = torch.randn(n,device='cuda')
-    for dbg in (0, 16):
+    for dbg in (0, 1):
         lib.cto_debug_set(dbg)
         for _ in range(3): gemm_nt(a,w,b,None,0,True)
         torch.cuda.synchronize()

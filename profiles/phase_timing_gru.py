@@ -1,5 +1,5 @@
 import sys, ctypes as C, torch, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from clairs_to_b200 import _lib
 from clairs_to_b200.engine import Engine
 from oracle import nn_oracle
