@@ -4,6 +4,8 @@
 #include <string.h>
 #include <algorithm>
 #include <new>
+#include <vector>
+#include <climits>
 
 namespace cto {
 
@@ -279,41 +281,110 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
                        int16_t* tensor_neg_host, void* stream) {
     CTO_REQUIRE(h && aff, "run_sites_host: NULL argument");
     if (n <= 0) return 0;
+    Engine& e = h->e;
     cudaStream_t s = (cudaStream_t)stream;
-    const int nh = h->e.aff.n_heads;
+    const int nh = e.aff.n_heads;
     const int64_t xin = (int64_t)N_POS * N_CH;
-    DevStream da, dn;
-    int16_t *ta = nullptr, *tn = nullptr;
-    int32_t *dpa = nullptr, *dpn = nullptr, *call = nullptr;
+    if (!e.copy_stream) CTO_CHECK(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = e.copy_stream;
+
+    const cto_host_stream* hs[2] = {aff, neg};
+    const int n_streams = neg ? 2 : 1;
+    DevStream d[2];
+    int16_t* tens[2] = {nullptr, nullptr};
+    int32_t* dep[2] = {nullptr, nullptr};
+    int32_t* call = nullptr;
     float *la = nullptr, *ln = nullptr, *probs = nullptr;
     double* post = nullptr;
-    int rc = upload_stream(aff, n, da, s);
-    if (!rc && neg) rc = upload_stream(neg, n, dn, s);
-    auto alloc = [&](void** p, int64_t bytes) { return cudaMallocAsync(p, bytes, s) != cudaSuccess; };
-    if (!rc) {
-        rc |= alloc((void**)&ta, sizeof(int16_t) * n * xin);
-        rc |= alloc((void**)&dpa, sizeof(int32_t) * n);
-        if (neg) {
-            rc |= alloc((void**)&tn, sizeof(int16_t) * n * xin);
-            rc |= alloc((void**)&dpn, sizeof(int32_t) * n);
-        }
-        rc |= alloc((void**)&la, sizeof(float) * n * nh * 2);
-        rc |= alloc((void**)&ln, sizeof(float) * n * nh * 2);
-        rc |= alloc((void**)&probs, sizeof(float) * n * nh * 4);
-        rc |= alloc((void**)&post, sizeof(double) * n * nh);
-        rc |= alloc((void**)&call, sizeof(int32_t) * n);
-        if (rc) set_error("run_sites_host: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    std::vector<cudaEvent_t> events;
+    int rc = 0;
+    auto alloc = [&](void** p, int64_t bytes) {
+        if (cudaMallocAsync(p, bytes > 16 ? bytes : 16, s) != cudaSuccess) rc = 1;
+    };
+    // device arrays: the big per-read arrays are only ALLOCATED here and filled span by span below, so that
+    // the host->device copy of chunk c+1 overlaps the kernels of chunk c; the small per-row arrays go at once
+    for (int k = 0; k < n_streams && !rc; ++k) {
+        const cto_host_stream* x = hs[k];
+        alloc((void**)&d[k].code, x->n_reads);
+        alloc((void**)&d[k].bq, x->n_reads);
+        alloc((void**)&d[k].mq, x->n_reads);
+        alloc((void**)&d[k].ind_entry, sizeof(uint32_t) * x->n_ind);
+        alloc((void**)&d[k].pos_off, sizeof(int32_t) * (x->n_rows + 1));
+        alloc((void**)&d[k].ind_off, sizeof(int32_t) * (x->n_rows + 1));
+        alloc((void**)&d[k].ref_code, x->n_rows);
+        alloc((void**)&d[k].win_pos, sizeof(int32_t) * n * N_POS);
+        alloc((void**)&tens[k], sizeof(int16_t) * n * xin);
+        alloc((void**)&dep[k], sizeof(int32_t) * n);
+        if (rc) break;
+        cudaError_t ce = cudaMemcpyAsync(d[k].pos_off, x->pos_off, sizeof(int32_t) * (x->n_rows + 1), cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].ind_off, x->ind_off, sizeof(int32_t) * (x->n_rows + 1), cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess && x->n_rows) ce = cudaMemcpyAsync(d[k].ref_code, x->ref_code, x->n_rows, cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].win_pos, x->win_pos, sizeof(int32_t) * n * N_POS, cudaMemcpyHostToDevice, s);
+        if (ce != cudaSuccess) rc = 1;
     }
-    if (!rc)
-        rc = launch_encode_pileup(da.code, da.bq, da.mq, da.pos_off, da.ref_code, da.ind_off, da.ind_entry, da.win_pos, n,
-                                  low_bq_cut, ta, dpa, s);
-    if (!rc && neg)
-        rc = launch_encode_pileup(dn.code, dn.bq, dn.mq, dn.pos_off, dn.ref_code, dn.ind_off, dn.ind_entry, dn.win_pos, n,
-                                  low_bq_cut, tn, dpn, s);
-    const bool want_post = h->e.tables && (post_host || call_host);
-    if (!rc)
-        rc = cto_predict(h, ta, dpa, neg ? tn : ta, neg ? dpn : dpa, n, la, ln, probs, want_post ? post : nullptr,
-                         want_post ? call : nullptr, nullptr, nullptr, s);
+    alloc((void**)&la, sizeof(float) * n * nh * 2);
+    alloc((void**)&ln, sizeof(float) * n * nh * 2);
+    alloc((void**)&probs, sizeof(float) * n * nh * 4);
+    alloc((void**)&post, sizeof(double) * n * nh);
+    alloc((void**)&call, sizeof(int32_t) * n);
+    if (rc) set_error("run_sites_host: device allocation / copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const bool want_post = e.tables && (post_host || call_host);
+
+    auto new_event = [&](cudaEvent_t* ev) {
+        if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) { rc = 1; return; }
+        events.push_back(*ev);
+    };
+    if (!rc) {
+        cudaEvent_t ready;
+        new_event(&ready);
+        if (!rc) {
+            cudaEventRecord(ready, s);                       // allocations are usable from the copy stream after this
+            cudaStreamWaitEvent(cs, ready, 0);
+        }
+    }
+    const int64_t step = e.max_batch;
+    for (int64_t c0 = 0; c0 < n && !rc; c0 += step) {
+        const int64_t nc = std::min(step, n - c0);
+        for (int k = 0; k < n_streams; ++k) {
+            const cto_host_stream* x = hs[k];
+            // rows touched by this chunk -> one contiguous span of reads (rows are position sorted)
+            int32_t r0 = INT32_MAX, r1 = -1;
+            const int32_t* wp = x->win_pos + c0 * N_POS;
+            for (int64_t i = 0; i < nc * N_POS; ++i) {
+                const int32_t r = wp[i];
+                if (r < 0) continue;
+                r0 = r < r0 ? r : r0;
+                r1 = r > r1 ? r : r1;
+            }
+            if (r1 < 0) continue;
+            if (r1 >= x->n_rows) { set_error("run_sites_host: win_pos row %d outside the %lld pileup rows", r1, (long long)x->n_rows); rc = 2; break; }
+            const int64_t a = x->pos_off[r0], b2 = x->pos_off[r1 + 1];
+            const int64_t ia = x->ind_off[r0], ib = x->ind_off[r1 + 1];
+            cudaError_t ce = cudaSuccess;
+            if (b2 > a) {
+                ce = cudaMemcpyAsync(d[k].code + a, x->code + a, b2 - a, cudaMemcpyHostToDevice, cs);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].bq + a, x->bq + a, b2 - a, cudaMemcpyHostToDevice, cs);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].mq + a, x->mq + a, b2 - a, cudaMemcpyHostToDevice, cs);
+            }
+            if (ce == cudaSuccess && ib > ia)
+                ce = cudaMemcpyAsync(d[k].ind_entry + ia, x->ind_entry + ia, sizeof(uint32_t) * (ib - ia), cudaMemcpyHostToDevice, cs);
+            if (ce != cudaSuccess) { set_error("run_sites_host: H2D copy failed: %s", cudaGetErrorString(ce)); rc = 1; break; }
+        }
+        if (rc) break;
+        cudaEvent_t copied;
+        new_event(&copied);
+        if (rc) break;
+        cudaEventRecord(copied, cs);
+        cudaStreamWaitEvent(s, copied, 0);
+        for (int k = 0; k < n_streams && !rc; ++k)
+            rc = launch_encode_pileup(d[k].code, d[k].bq, d[k].mq, d[k].pos_off, d[k].ref_code, d[k].ind_off, d[k].ind_entry,
+                                      d[k].win_pos + c0 * N_POS, nc, low_bq_cut, tens[k] + c0 * xin, dep[k] + c0, s);
+        const int kn = neg ? 1 : 0;
+        if (!rc)
+            rc = cto_predict(h, tens[0] + c0 * xin, dep[0] + c0, tens[kn] + c0 * xin, dep[kn] + c0, nc, la + c0 * nh * 2,
+                             ln + c0 * nh * 2, probs + c0 * nh * 4, want_post ? post + c0 * nh : nullptr,
+                             want_post ? call + c0 : nullptr, nullptr, nullptr, s);
+    }
     if (!rc) {
         cudaError_t ce = cudaSuccess;
         if (probs_host) ce = cudaMemcpyAsync(probs_host, probs, sizeof(float) * n * nh * 4, cudaMemcpyDeviceToHost, s);
@@ -322,20 +393,25 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
         if (ce == cudaSuccess && want_post && call_host)
             ce = cudaMemcpyAsync(call_host, call, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && tensor_aff_host)
-            ce = cudaMemcpyAsync(tensor_aff_host, ta, sizeof(int16_t) * n * xin, cudaMemcpyDeviceToHost, s);
+            ce = cudaMemcpyAsync(tensor_aff_host, tens[0], sizeof(int16_t) * n * xin, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && tensor_neg_host)
-            ce = cudaMemcpyAsync(tensor_neg_host, neg ? tn : ta, sizeof(int16_t) * n * xin, cudaMemcpyDeviceToHost, s);
+            ce = cudaMemcpyAsync(tensor_neg_host, tens[neg ? 1 : 0], sizeof(int16_t) * n * xin, cudaMemcpyDeviceToHost, s);
         if (ce != cudaSuccess) {
             set_error("run_sites_host: D2H copy failed: %s", cudaGetErrorString(ce));
             rc = 1;
         }
     }
-    free_stream(da, s);
-    free_stream(dn, s);
-    void* ptrs[] = {ta, tn, dpa, dpn, la, ln, probs, post, call};
+    cudaStreamSynchronize(cs);                                // every span copy has landed (or failed) before frees
+    for (int k = 0; k < 2; ++k) {
+        free_stream(d[k], s);
+        if (tens[k]) cudaFreeAsync(tens[k], s);
+        if (dep[k]) cudaFreeAsync(dep[k], s);
+    }
+    void* ptrs[] = {la, ln, probs, post, call};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, s);
     cudaError_t se = cudaStreamSynchronize(s);
+    for (cudaEvent_t ev : events) cudaEventDestroy(ev);
     if (!rc && se != cudaSuccess) {
         set_error("run_sites_host: %s", cudaGetErrorString(se));
         rc = 1;

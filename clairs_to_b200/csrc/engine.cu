@@ -193,6 +193,8 @@ int engine_alloc(Engine& e, int64_t max_batch) {
 void engine_free(Engine& e) {
     for (void* p : e.allocs) cudaFree(p);
     e.allocs.clear();
+    if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
+    e.copy_stream = nullptr;
     release(e.aff.ws);
     release(e.neg.ws);
     release(e.neg.wih1_pad);

@@ -72,6 +72,7 @@ struct Engine {
     double* tables = nullptr;                                  // likelihood tables, n_heads * 122
     int table_heads = 0;
     std::vector<void*> allocs;
+    cudaStream_t copy_stream = nullptr;                        // H2D spans of cto_run_sites_host overlap the kernels
     bool use_tc = true;                                        // dense contractions on tcgen05 (TF32) where shapes allow
     // optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
     int profile = 0;           // 0 off, 1 = NEG kernel families + AFF as one block, 2 = every AFF kernel family too
