@@ -30,7 +30,7 @@ int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* 
 
 }  // namespace cto
 
-namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; extern int g_gru_cluster; extern long long* g_gru_timing; }
+namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; extern int g_gru_cluster; extern long long* g_gru_timing; extern int g_gru_pair; }
 using namespace cto;
 
 struct cto_engine {
@@ -202,7 +202,10 @@ int64_t cto_launch_count(void) { return launches(); }
 
 void cto_debug_set(int flags) { cto::g_gemm_debug = flags; }
 void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; cto::g_gru_timing = dev_buf ? dev_buf + 24 : nullptr; }
-void cto_debug_gru_cluster(int c) { if (c == 1 || c == 2 || c == 4) cto::g_gru_cluster = c; }
+void cto_debug_gru_cluster(int c) {
+    if (c == 1 || c == 2 || c == 4) { cto::g_gru_cluster = c; cto::g_gru_pair = 0; }
+    if (c == 22) cto::g_gru_pair = 1;                 // CTA-pair kernel (tcgen05 cta_group::2)
+}
 
 int cto_engine_set_tensor_cores(cto_engine* h, int enable) {
     CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");

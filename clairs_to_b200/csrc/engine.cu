@@ -146,6 +146,18 @@ int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
                             blk[((size_t)d * 3 * h + row) * h + k] = wt[((size_t)d * h + k) * 3 * h + col];
                     }
         if (upload(blk.data(), (int64_t)blk.size(), m.whh_blk[l])) return 1;
+        // CTA-pair kernel: inside a block the 16-unit halves come first, so that each CTA of the pair streams the
+        // 48 rows (r,z,n x 16 units) whose accumulator columns land in its half of the TMEM lanes
+        for (int d = 0; d < 2; ++d)
+            for (int b = 0; b < h / 32; ++b)
+                for (int hf = 0; hf < 2; ++hf)
+                    for (int g = 0; g < 3; ++g)
+                        for (int j = 0; j < 16; ++j) {
+                            const int row = b * 96 + hf * 48 + g * 16 + j, col = g * h + b * 32 + hf * 16 + j;
+                            for (int k = 0; k < h; ++k)
+                                blk[((size_t)d * 3 * h + row) * h + k] = wt[((size_t)d * h + k) * 3 * h + col];
+                        }
+        if (upload(blk.data(), (int64_t)blk.size(), m.whh_pair[l])) return 1;
     }
     return 0;
 }
@@ -200,6 +212,8 @@ void engine_free(Engine& e) {
     release(e.neg.wih1_pad);
     release(e.neg.whh_blk[0]);
     release(e.neg.whh_blk[1]);
+    release(e.neg.whh_pair[0]);
+    release(e.neg.whh_pair[1]);
     if (e.tables) cudaFree(e.tables);
     for (auto& r : e.prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
     for (cudaEvent_t ev : e.ev_free) cudaEventDestroy(ev);
@@ -278,6 +292,8 @@ int prof_collect(Engine& e, double* ms, int64_t* count) {
 }
 
 #define RUN(x) do { if (int _rc = (x)) return _rc; } while (0)
+
+int g_gru_pair = 1;        // 1: CTA-pair (cta_group::2) recurrence kernel, 0: single-CTA kernel with cluster multicast
 
 // dense contraction: tcgen05 TF32 when the engine allows it and the shape fits, CUDA-core fp32 otherwise
 static int gemm(const Engine& e, const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr,
@@ -385,7 +401,9 @@ int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         }
         RUN(prof_end(e, s));
         RUN(prof_begin(e, l ? PK_NEG_GRU2 : PK_NEG_GRU1, s));
-        if (e.use_tc && m.whh_blk[l].hi) {
+        if (e.use_tc && g_gru_pair && m.whh_pair[l].hi) {
+            RUN(launch_gru_pair(e.n_xp, m.whh_pair[l].hi, m.whh_pair[l].lo, g.bhn, outs[l], n, h, s));
+        } else if (e.use_tc && m.whh_blk[l].hi) {
             RUN(launch_gru_tc(e.n_xp, m.whh_blk[l].hi, m.whh_blk[l].lo, g.bhn, outs[l], n, h, s));
         } else {
             RUN(launch_gru_recurrent(e.n_xp, g.whh_t, g.bhn, outs[l], n, h, s));

@@ -56,6 +56,7 @@ struct NegModel {
     WeightSet ws;
     WeightSet wih1_pad;        // layer-1 W_ih with K padded 34 -> NEG_IN_LD (zeros), for the tensor-core path
     WeightSet whh_blk[2];      // per layer: W_hh [2 dirs][unit block (32) x gate x unit][H], for gru_tc.cu
+    WeightSet whh_pair[2];     // per layer: W_hh [2 dirs][unit block (32) x half (16) x gate x unit][H], for gru_tc2.cu
 };
 
 struct Engine {

@@ -78,6 +78,20 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp; the surrounding loop stays warp-uniform so that descriptors live in uniform
+// registers (inside an `if (lane == 0)` region ptxas wraps every UTCHMMA / UTMALDG in an ELECT /
+// R2UR.BROADCAST / BRA.U.ANY loop, ~70 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float round_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -149,7 +163,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {                                   // ---- TMA producer ----
+        {                                                  // ---- TMA producer (warp-uniform loop, elected lane issues) ----
             const uint32_t tx = (uint32_t)(BM + 2 * bn) * BK * 4;
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -160,18 +174,21 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     TIC;
                     mbar_wait(&empty[s], ph ^ 1);
                     TOC(0);
-                    mbar_expect_tx(&full[s], tx);
                     uint8_t* st = base + s * STAGE_BYTES;
-                    tma_load_2d(&tma_a, &full[s], st, kb * BK, m0);
-                    tma_load_2d(&tma_whi, &full[s], st + 2 * TILE_BYTES, kb * BK, n0);
-                    tma_load_2d(&tma_wlo, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[s], tx);
+                        tma_load_2d(&tma_a, &full[s], st, kb * BK, m0);
+                        tma_load_2d(&tma_whi, &full[s], st + 2 * TILE_BYTES, kb * BK, n0);
+                        tma_load_2d(&tma_wlo, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
+                    }
+                    __syncwarp();
                     TOC(1);
                 }
             }
-            if (tim) { timing[0] = tacc[0]; timing[1] = tacc[1]; }
+            if (tim && lane == 0) { timing[0] = tacc[0]; timing[1] = tacc[1]; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {                                   // ---- MMA issuer ----
+        {                                                  // ---- MMA issuer (warp-uniform loop, elected lane issues) ----
             const uint32_t idesc = make_idesc_tf32(bn);
             uint32_t it = 0, acc_it = 0;
             for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
@@ -194,20 +211,23 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     const uint64_t d_alo = make_desc_k_sw128(a_addr + TILE_BYTES);
                     const uint64_t d_whi = make_desc_k_sw128(a_addr + 2 * TILE_BYTES);
                     const uint64_t d_wlo = make_desc_k_sw128(a_addr + 3 * TILE_BYTES);
-                    #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        // 8 tf32 = 32 bytes along the swizzle row: +2 in the (>>4) start-address field
-                        const uint64_t o = (uint64_t)(k * 2);
-                        mma_tf32(acc, d_ahi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
-                        mma_tf32(acc, d_alo + o, d_whi + o, idesc, 1u);
-                        mma_tf32(acc, d_ahi + o, d_wlo + o, idesc, 1u);
+                    if (elect_one()) {
+                        #pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            // 8 tf32 = 32 bytes along the swizzle row: +2 in the (>>4) start-address field
+                            const uint64_t o = (uint64_t)(k * 2);
+                            mma_tf32(acc, d_ahi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
+                            mma_tf32(acc, d_alo + o, d_whi + o, idesc, 1u);
+                            mma_tf32(acc, d_ahi + o, d_wlo + o, idesc, 1u);
+                        }
+                        tcgen05_commit(&empty[s]);             // stage reusable once these MMAs retire
+                        if (kb == num_kb - 1) tcgen05_commit(&acc_full[ab]);   // accumulator complete
                     }
-                    tcgen05_commit(&empty[s]);             // stage reusable once these MMAs retire
+                    __syncwarp();
                     TOC(3);
                 }
-                tcgen05_commit(&acc_full[ab]);             // accumulator complete
             }
-            if (tim) { for (int i = 0; i < 4; ++i) timing[4 + i] = tacc[i]; }
+            if (tim && lane == 0) { for (int i = 0; i < 4; ++i) timing[4 + i] = tacc[i]; }
         }
     } else if (warp < 6) {                                 // ---- converter: warps 2..5 ----
         const int ct = threadIdx.x - 64;                   // 0..127
@@ -224,11 +244,14 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 #pragma unroll
                 for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {       // elementwise: the swizzle is irrelevant
                     const int idx = ct + i * 128;
+                    // the tensor core reads an fp32 word as TF32 by dropping the 13 low mantissa bits, so the raw
+                    // tile already is the "hi" operand; only lo = a - trunc(a) (exact in fp32) has to be written
                     const float4 v = a_hi[idx];
-                    float4 hi, lo;
-                    hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
-                    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-                    a_hi[idx] = hi;
+                    float4 lo;
+                    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
                     a_lo[idx] = lo;
                 }
                 TOC(1);

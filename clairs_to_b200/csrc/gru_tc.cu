@@ -17,99 +17,11 @@
 //     quadrant) read the gate pre-activations with tcgen05.ld, add the software-prefetched xproj,
 //     apply the gate math in fp32, write h_t to HBM and the TF32 hi/lo split of h_t back into the
 //     shared-memory tiles for the next step.
-#include "nn_kernels.cuh"
-#include <cuda.h>
+#include "gru_ptx.cuh"
 
 namespace cto {
 
 namespace tc {
-// helpers shared with gemm_tc.cu (same translation-unit-local definitions)
-__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void g_mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void g_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void g_mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(g_smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void g_tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(g_smem_u32(dst)), "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void g_tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(g_smem_u32(dst)), "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void g_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(g_smem_u32(bar)), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t g_cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void g_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void g_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(g_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void g_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ float g_round_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ uint64_t g_desc_k_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__device__ __forceinline__ void g_tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-
-__device__ __forceinline__ void g_tmem_ld8(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-// gate non-linearities through MUFU.EX2 / MUFU.RCP: absolute error ~1e-7, far inside the 1e-3 contract
-__device__ __forceinline__ float g_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float g_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
-
 constexpr int GM = 64;                       // candidates per CTA (MMA M)
 constexpr int GBLK = 32;                     // hidden units per block
 constexpr int GN = 3 * GBLK;                 // 96 gate columns per block (MMA N)
@@ -178,7 +90,7 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {                                   // ---- TMA producer: W_hh blocks, every step ----
+        {                                                  // ---- TMA producer: W_hh blocks, every step (warp-uniform) ----
             uint32_t it = 0;
             for (int step = 0; step < N_POS; ++step) {
                 for (int blk = 0; blk < NB; ++blk) {
@@ -186,9 +98,10 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
                         const int s = it % G_STAGES;
                         const uint32_t ph = (it / G_STAGES) & 1;
                         g_mbar_wait(&empty[s], ph ^ 1);
-                        g_mbar_expect_tx(&full[s], G_STAGE);
                         uint8_t* st = wring + s * G_STAGE;
                         const int row = dir * 3 * H + blk * GN;
+                        if (!g_elect_one()) continue;
+                        g_mbar_expect_tx(&full[s], G_STAGE);
                         if (C == 1) {
                             g_tma_load_2d(&tma_whi, &full[s], st, kb * GK, row);
                             g_tma_load_2d(&tma_wlo, &full[s], st + G_WTILE, kb * GK, row);
@@ -202,7 +115,7 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {                                   // ---- MMA issuer ----
+        {                                                  // ---- MMA issuer: whole warp runs the loop, one elected lane issues ----
             // D=f32, A=B=tf32, K-major, M=64, N=96
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
             uint32_t it = 0;
@@ -224,21 +137,24 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
                         const uint32_t w_addr = g_smem_u32(wring + s * G_STAGE);
                         const uint64_t d_whi = g_desc_k_sw128(w_addr);
                         const uint64_t d_wlo = g_desc_k_sw128(w_addr + G_WTILE);
-                        #pragma unroll
-                        for (int k = 0; k < GK / 8; ++k) {
-                            const uint64_t o = (uint64_t)(k * 2);
-                            g_mma_tf32(acc, d_hhi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
-                            g_mma_tf32(acc, d_hlo + o, d_whi + o, idesc, 1u);
-                            g_mma_tf32(acc, d_hhi + o, d_wlo + o, idesc, 1u);
+                        if (g_elect_one()) {
+                            #pragma unroll
+                            for (int k = 0; k < GK / 8; ++k) {
+                                const uint64_t o = (uint64_t)(k * 2);
+                                g_mma_tf32(acc, d_hhi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
+                                g_mma_tf32(acc, d_hlo + o, d_whi + o, idesc, 1u);
+                                g_mma_tf32(acc, d_hhi + o, d_wlo + o, idesc, 1u);
+                            }
+                            if (C == 1) g_commit(&empty[s]);
+                            else g_commit_mc(&empty[s], CMASK);     // frees the stage in every CTA of the cluster
+                            if ((blk & 1) && kb == KB - 1) g_commit(&acc_full[blk >> 1]);   // the pair is accumulated
                         }
-                        if (C == 1) g_commit(&empty[s]);
-                        else g_commit_mc(&empty[s], CMASK);     // frees the stage in every CTA of the cluster
+                        __syncwarp();
                         GTOC(2);
                     }
-                    if (blk & 1) g_commit(&acc_full[blk >> 1]);  // both unit blocks of this pair are accumulated
                 }
             }
-            if (tim) { timing[0] = tacc[0]; timing[1] = tacc[1]; timing[2] = tacc[2]; }
+            if (tim && lane == 0) { timing[0] = tacc[0]; timing[1] = tacc[1]; timing[2] = tacc[2]; }
         }
     } else {                                               // ---- gate math: warps 2..9 ----
         // two warps per TMEM lane quadrant; thread = (candidate row m, unit block parity `sub`, 16-unit half `part`)
@@ -373,8 +289,6 @@ gru_tc_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
-
-int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 }  // namespace tc
 

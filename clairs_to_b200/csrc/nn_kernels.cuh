@@ -47,6 +47,9 @@ int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bh
 // tensor-core recurrence (gru_tc.cu): w_hi / w_lo = W_hh regrouped per 32-unit block, TF32 hi / lo
 int launch_gru_tc(const float* xproj, const float* w_hi, const float* w_lo, const float* bhn, float* out, int64_t batch,
                   int hidden, cudaStream_t s);
+// CTA-pair recurrence (gru_tc2.cu, tcgen05 cta_group::2): W_hh regrouped per (32-unit block, 16-unit half, gate)
+int launch_gru_pair(const float* xproj, const float* w_hi, const float* w_lo, const float* bhn, float* out, int64_t batch,
+                    int hidden, cudaStream_t s);
 int launch_head_fc3(const float* y, const float* w3, const float* b3, float* logits, int64_t batch, int n_heads,
                     cudaStream_t s);
 int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,

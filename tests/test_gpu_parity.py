@@ -265,7 +265,7 @@ def test_full_size_properties(eng4):
     assert np.allclose(b['probs'].cpu().numpy().sum(-1), 1.0, atol=1e-5)
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("cluster", [1, 2, 4, 22])
 def test_gru_cluster_multicast_sizes(golden_dir, cluster):
     """The tensor-core GRU shares one W_hh stream per thread-block cluster (TMA multicast); every
     cluster size must give the same logits (and odd CTA counts exercise the padded cluster)."""
