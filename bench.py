@@ -193,7 +193,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.check(lib.cto_engine_profile(eng.handle, 1))
+    _lib.check(lib.cto_engine_profile(eng.handle, int(os.environ.get('CTO_PROFILE_LEVEL', '1'))))
     launches0 = lib.cto_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

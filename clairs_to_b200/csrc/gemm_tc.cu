@@ -13,7 +13,7 @@
 //   warps 2-5   converter: A -> A_hi (in place) + A_lo (second buffer), fence to the async proxy
 //   warp 1      MMA issuer (one elected thread): tcgen05.mma.kind::tf32, M=128, N=BN, K=8;
 //               tcgen05.commit releases smem stages and publishes the accumulator
-//   warps 6-9   epilogue: tcgen05.ld (one TMEM lane = one output row), bias / GELU / SELU /
+//   warps 6-13  epilogue (two groups of four warps, alternating 32-column slabs): tcgen05.ld (one TMEM lane = one output row), bias / GELU / SELU /
 //               residual in fp32, swizzled staging in smem, TMA store (full 128-byte lines,
 //               M tail clipped by the tensor map)
 // The accumulator is double buffered in TMEM (2 x 128 columns) so the epilogue of tile i overlaps
@@ -33,7 +33,7 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A | A_lo | W_hi | W_lo
 constexpr int STAGES = 3;
 constexpr int SLAB = 32;                     // epilogue works on 128 x 32 fp32 slabs
 constexpr int STAGING_BYTES = BM * SLAB * 4; // 16 KB, two of them
-constexpr int THREADS = 320;
+constexpr int THREADS = 448;                 // warp 0 TMA, 1 MMA, 2-5 converter, 6-13 two epilogue groups
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGING_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -150,7 +150,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -261,11 +261,14 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             }
         }
         if (tim && ct == 0) { for (int i = 0; i < 3; ++i) timing[8 + i] = tacc[i]; }
-    } else {                                               // ---- epilogue: warps 6..9 ----
+    } else {                                               // ---- epilogue: warps 6..13, two groups of four ----
+        // both groups cover all four TMEM lane quadrants; group g takes the 32-column slabs with index % 2 == g
         const int quad = warp & 3;                         // TMEM lanes [32*quad, 32*quad+32)
-        const int et = threadIdx.x - 192;                  // 0..127
+        const int grp = (warp - 6) >> 2;
+        const int et = (threadIdx.x - 192) & 127;          // 0..127 inside the group
         const int r_in_tile = quad * 32 + lane;
-        uint32_t acc_it = 0, slab_it = 0;
+        uint8_t* stg = staging + grp * STAGING_BYTES;      // one staging buffer per group
+        uint32_t acc_it = 0;
         for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
             const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * bn;
             const uint32_t ab = acc_it & 1, aph = (acc_it >> 1) & 1;
@@ -275,7 +278,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = (int64_t)m0 + r_in_tile;
             const bool row_ok = row < m_total;
-            for (int cb = 0; cb < bn; cb += SLAB, ++slab_it) {
+            for (int cb = grp * SLAB; cb < bn; cb += 2 * SLAB) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ab * MAX_BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
                 asm volatile(
@@ -288,14 +291,13 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 TOC(1);
-                if (cb + SLAB >= bn) {                     // accumulator fully read: hand it back to the MMA warp
+                if (cb + 2 * SLAB >= bn) {                 // this group's last slab of the tile: hand the accumulator back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&acc_empty[ab]);
                 }
-                uint8_t* stg = staging + (slab_it & 1) * STAGING_BYTES;
-                // the TMA store that last read this staging buffer (two slabs ago) must have finished reading it
-                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // the group's previous TMA store must have finished reading the staging buffer
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 TOC(2);
                 const float* rrow = (residual && row_ok) ? residual + row * ldr + n0 + cb : nullptr;
                 #pragma unroll
@@ -322,7 +324,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 TOC(3);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 TOC(4);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 TOC(5);
                 if (et == 0) {
                     tma_store_2d(&tma_c, stg, n0 + cb, m0);
@@ -331,7 +333,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             }
         }
         if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        if (tim && et == 0) { for (int i = 0; i < 6; ++i) timing[12 + i] = tacc[i]; timing[20] = (long long)num_tiles; timing[21] = num_kb; }
+        if (tim && et == 0 && grp == 0) { for (int i = 0; i < 6; ++i) timing[12 + i] = tacc[i]; timing[20] = (long long)num_tiles; timing[21] = num_kb; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
