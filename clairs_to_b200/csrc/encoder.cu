@@ -3,7 +3,7 @@
 // Replaces decode_pileup_bases() + window assembly of the reference
 // (src/create_tensor_pileup_calling.py:146-229, 461, 513-516, 537-543; cited as CT).
 //
-// HBM-bound integer work.  One CTA encodes a group of 8 candidates = 264 (candidate, flank slot)
+// HBM-bound integer work.  One CTA encodes a group of 4 candidates = 132 (candidate, flank slot)
 // pairs, one THREAD per slot:
 //   1. the group's rows cover one contiguous span of the read arrays (rows are position-sorted), so the
 //      three byte streams (code, bq, mq) of the span are fetched with three bulk async copies
@@ -12,7 +12,7 @@
 //      counters kept field-major in shared memory (bank = thread, so no conflicts and no atomics);
 //   3. the rare indel-carrying reads come from a sparse side list and are resolved exactly (per-allele
 //      maximum, CT:184-187, 201-204) with a K^2 scan that has no table-size limit;
-//   4. the 34 int16 of each slot are staged in shared memory and the group's 17.5 KB output block is
+//   4. the 34 int16 of each slot are staged in shared memory and the group's 8.8 KB output block is
 //      written with 16-byte coalesced stores.
 // Groups whose span does not fit the staging buffers (very deep pileups, scattered rows) take the
 // same code path with the pointers left in global memory.
@@ -22,12 +22,12 @@ namespace cto {
 
 namespace enc {
 
-constexpr int GROUP = 8;                          // candidates per CTA
-constexpr int SLOTS = GROUP * N_POS;              // 264
-constexpr int THREADS = 288;                      // 9 warps
-constexpr int STAGE_CAP = 20 * 1024;              // bytes per staged array
+constexpr int GROUP = 4;                          // candidates per CTA (4 CTAs per SM hide the bulk-copy latency)
+constexpr int SLOTS = GROUP * N_POS;              // 132
+constexpr int THREADS = 160;                      // 5 warps
+constexpr int STAGE_CAP = 10 * 1024;              // bytes per staged array
 constexpr int N_FIELDS = 26;                      // 18 set-A + 8 set-B counters
-constexpr int OUT_BYTES = SLOTS * N_CH * 2;       // 17952
+constexpr int OUT_BYTES = SLOTS * N_CH * 2;       // 8976
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

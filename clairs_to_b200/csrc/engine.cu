@@ -318,14 +318,21 @@ static int run_heads(const Engine& e, const HeadW& h, const float* feat, int fea
     return 0;
 }
 
+// one launch timed under a profile kind (no-op unless the engine profiles that kind)
+#define TIMED(kind, call)            \
+    do {                             \
+        RUN(prof_begin(e, kind, s)); \
+        RUN(call);                   \
+        RUN(prof_end(e, s));         \
+    } while (0)
+
 int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {
     CTO_REQUIRE(n <= e.max_batch, "aff_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
     const AffModel& m = e.aff;
     const float* cur = x;
-    cudaEvent_t aff_start = nullptr, aff_stop = nullptr;
+    cudaEvent_t aff_stop = nullptr;
     if (e.profile == 1) {                      // AFF as one block (its parts are only timed at level 2)
         RUN(prof_begin(e, PK_AFF, s));
-        aff_start = e.prof.back().start;
         aff_stop = e.prof.back().stop;
         e.prof_open = false;
     }
@@ -334,51 +341,32 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         const int c = st.c, inner = st.heads * DIM_HEAD;
         const int64_t rows = n * st.wout, rows_kv = n * st.wkv;
         // embed conv (3-tap, stride 2, pad 1) + channel LN  (clairs/model.py:195-196)
-        RUN(prof_begin(e, PK_AFF_EMBED, s));
-        RUN(gemm(e, conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows, c,
-                           3 * st.cin, ACT_NONE, s));
-        RUN(prof_end(e, s));
-        RUN(prof_begin(e, PK_AFF_LN, s));
-        RUN(launch_channel_ln(e.a_t0, st.ln_g, st.ln_b, e.a_xs, rows, c, s));
-        RUN(prof_end(e, s));
+        TIMED(PK_AFF_EMBED, gemm(e, conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows,
+                                 c, 3 * st.cin, ACT_NONE, s));
+        TIMED(PK_AFF_LN, launch_channel_ln(e.a_t0, st.ln_g, st.ln_b, e.a_xs, rows, c, s));
         for (int d = 0; d < st.depth; ++d) {
             const CvtLayer& L = st.layers[d];
-            // x = Attention(LN(x)) + x   (clairs/model.py:145)
-            RUN(prof_begin(e, PK_AFF_DWCONV, s));
-            RUN(launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, e.a_dq, e.a_dkv, n, st.wout, st.wkv, c, s));
-            RUN(prof_end(e, s));
-            RUN(prof_begin(e, PK_AFF_GEMM, s));
-        RUN(gemm(e, plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c, ACT_NONE, s));
-        RUN(prof_end(e, s));
-            RUN(prof_begin(e, PK_AFF_GEMM, s));
-        RUN(gemm(e, plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv, 2 * inner, c,
-                               ACT_NONE, s));
-        RUN(prof_end(e, s));
-            RUN(prof_begin(e, PK_AFF_ATTENTION, s));
-        RUN(launch_attention(e.a_q, e.a_kv, e.a_att, n, st.wout, st.wkv, st.heads, s));
-        RUN(prof_end(e, s));
-            RUN(prof_begin(e, PK_AFF_GEMM, s));
-        RUN(gemm(e, plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner, ACT_NONE, s));
-        RUN(prof_end(e, s));
+            // x = Attention(LN(x)) + x   (clairs/model.py:145); LN and both depth-wise convs are one kernel
+            TIMED(PK_AFF_DWCONV, launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, e.a_dq, e.a_dkv, n, st.wout,
+                                                  st.wkv, c, s));
+            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c,
+                                    ACT_NONE, s));
+            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv,
+                                    2 * inner, c, ACT_NONE, s));
+            TIMED(PK_AFF_ATTENTION, launch_attention(e.a_q, e.a_kv, e.a_att, n, st.wout, st.wkv, st.heads, s));
+            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner,
+                                    ACT_NONE, s));
             // x = FF(LN(x)) + x          (clairs/model.py:146)
-            RUN(prof_begin(e, PK_AFF_LN, s));
-        RUN(launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, e.a_y, rows, c, s));
-        RUN(prof_end(e, s));
-            RUN(prof_begin(e, PK_AFF_GEMM, s));
-        RUN(gemm(e, plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
-        RUN(prof_end(e, s));
-            RUN(prof_begin(e, PK_AFF_GEMM, s));
-        RUN(gemm(e, plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c, ACT_NONE, s));
-        RUN(prof_end(e, s));
+            TIMED(PK_AFF_LN, launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, e.a_y, rows, c, s));
+            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
+            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c,
+                                    ACT_NONE, s));
         }
         // the next stage reads a_xs while writing a_t0, so no copy is needed
         cur = e.a_xs;
     }
-    RUN(prof_begin(e, PK_AFF_HEADS, s));
-    RUN(run_heads(e, m.head, cur, m.feat, m.n_heads, n, e.f1, e.f2, logits, s));
-    RUN(prof_end(e, s));
+    TIMED(PK_AFF_HEADS, run_heads(e, m.head, cur, m.feat, m.n_heads, n, e.f1, e.f2, logits, s));
     if (aff_stop) CTO_CHECK(cudaEventRecord(aff_stop, s));
-    (void)aff_start;
     return 0;
 }
 

@@ -377,9 +377,10 @@ constexpr int ATT_MAXW = 17, ATT_MAXKV = 9, ATT_D = 64, ATT_WARPS = 4;
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, int64_t n_bh, int w,
                  int wkv, int heads) {
-    __shared__ float sq[ATT_WARPS][ATT_MAXW][ATT_D + 1];
-    __shared__ float sk[ATT_WARPS][ATT_MAXKV][ATT_D + 1];
-    __shared__ float sv[ATT_WARPS][ATT_MAXKV][ATT_D + 1];
+    // rows padded to 68 floats: 16-byte aligned for float4 reads, and 8 consecutive rows start 4 banks apart
+    __shared__ __align__(16) float sq[ATT_WARPS][ATT_MAXW][ATT_D + 4];
+    __shared__ __align__(16) float sk[ATT_WARPS][ATT_MAXKV][ATT_D + 4];
+    __shared__ __align__(16) float sv[ATT_WARPS][ATT_MAXKV][ATT_D + 4];
     __shared__ float sp[ATT_WARPS][ATT_MAXW][ATT_MAXKV + 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t bh = (int64_t)blockIdx.x * ATT_WARPS + wib;
@@ -402,9 +403,17 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
     __syncwarp();
     for (int p = lane; p < w * wkv; p += 32) {
         const int i = p / wkv, j = p - i * wkv;
+        const float4* qr = reinterpret_cast<const float4*>(sq[wib][i]);
+        const float4* kr = reinterpret_cast<const float4*>(sk[wib][j]);
         float acc = 0.0f;
-        #pragma unroll 16
-        for (int d = 0; d < ATT_D; ++d) acc = fmaf(sq[wib][i][d], sk[wib][j][d], acc);
+        #pragma unroll
+        for (int d = 0; d < ATT_D / 4; ++d) {              // same summation order as the scalar loop
+            const float4 a = qr[d], b = kr[d];
+            acc = fmaf(a.x, b.x, acc);
+            acc = fmaf(a.y, b.y, acc);
+            acc = fmaf(a.z, b.z, acc);
+            acc = fmaf(a.w, b.w, acc);
+        }
         sp[wib][i][j] = acc;
     }
     __syncwarp();
