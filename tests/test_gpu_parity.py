@@ -280,3 +280,62 @@ def test_gru_cluster_multicast_sizes(golden_dir, cluster):
     finally:
         eng.lib.cto_debug_gru_cluster(2)
         eng.close()
+
+
+def test_run_sites_host_pipelined_chunks_and_sparse_windows():
+    """cto_run_sites_host copies the read arrays span by span while earlier chunks compute: many small
+    chunks (max_batch 64), windows with missing rows (-1) and windows that overlap the previous candidate."""
+    from clairs_to_b200.engine import stream_to_device
+    eng, _, _ = _engine(4, max_batch=64)
+    (aff, _), (neg, _) = synth.synth_pair(300, 17, 'ont', depth_lo=0, depth_hi=90)
+    rng = np.random.default_rng(3)
+    for s in (aff, neg):
+        win = s.win_pos.reshape(-1, N_POS).copy()
+        win[rng.random(win.shape) < 0.05] = -1                    # rows without pileup output (CT:461)
+        win[5] = win[4] + 7                                        # candidate 5 re-uses rows of candidate 4 (overlap)
+        win[5][win[4] < 0] = -1
+        s.win_pos = win.reshape(-1)
+    neg.win_pos = aff.win_pos.copy()
+    dev = eng.run_sites(stream_to_device(aff, eng.device), stream_to_device(neg, eng.device), 30, posterior=False)
+    host = eng.run_sites_host(aff, neg, 30, want_tensors=True)
+    assert np.array_equal(host['tensor_aff'].numpy(), dev['tensor_aff'].cpu().numpy())
+    assert np.array_equal(host['tensor_neg'].numpy(), dev['tensor_neg'].cpu().numpy())
+    assert np.array_equal(host['probs'].numpy(), dev['probs'].cpu().numpy())
+    t = host['tensor_aff'].numpy()
+    assert not t.reshape(-1, N_CH)[aff.win_pos < 0].any()         # absent rows are all-zero rows
+    eng.close()
+
+
+@pytest.mark.parametrize("platform,n_heads,single_stream", [("ont", 6, False), ("ilmn", 4, True), ("hifi", 6, False)])
+def test_baseline_config_shapes_end_to_end(platform, n_heads, single_stream):
+    """BASELINE.json configs 3-5 in miniature: indel (6-head) models, the Illumina single-stream case
+    (NEG symlinked to AFF, run_clairs_to:1248-1252) and HiFi, host arrays in -> posteriors out, against the oracle."""
+    lk = np.concatenate([np.random.default_rng(1).uniform(0.05, 0.95, size=(10 * n_heads, 10)),
+                         np.sort(np.random.default_rng(2).uniform(0.02, 0.98, size=(2 * n_heads, 10)), axis=1)])
+    eng, aff_sd, neg_sd = _engine(n_heads, max_batch=128, likelihood=lk)
+    (aff, _), (neg, _) = synth.synth_pair(200, 41, platform, depth_mean=70, depth_hi=180)
+    out = eng.run_sites_host(aff, None if single_stream else neg, 30, want_tensors=True)
+    ta, tn = out['tensor_aff'].numpy(), out['tensor_neg'].numpy()
+    if single_stream:
+        assert np.array_equal(ta, tn)
+    from clairs_to_b200.engine import stream_to_device
+    da = eng.encode(stream_to_device(aff, eng.device), 30)[1].cpu().numpy()
+    dn = eng.encode(stream_to_device(aff if single_stream else neg, eng.device), 30)[1].cpu().numpy()
+    xa = np.stack([posterior_oracle.rescale_tensor(t, d) for t, d in zip(ta, da)])
+    xn = np.stack([posterior_oracle.rescale_tensor(t, d) for t, d in zip(tn, dn)])
+    pa = nn_oracle.softmax_heads(nn_oracle.aff_forward(xa, aff_sd)).numpy()
+    pn = nn_oracle.softmax_heads(nn_oracle.neg_forward(xn, neg_sd)).numpy()
+    probs = out['probs'].numpy()
+    assert np.abs(probs[:, :n_heads] - pa).max() < TOL and np.abs(probs[:, n_heads:] - pn).max() < TOL
+    mats, ea, en = posterior_oracle.load_likelihood(lk, n_heads)
+    post = out['post'].numpy()
+    agree = 0
+    for k in range(200):
+        p8 = [float("{:0.8f}".format(v)) for v in probs[k, :, 1]]
+        want = posterior_oracle.posterior(p8[:n_heads], p8[n_heads:], mats, ea, en)
+        assert np.array_equal(post[k], want)                       # fp64 combine is bit-exact on identical inputs
+        ref = posterior_oracle.posterior([float("{:0.8f}".format(v)) for v in pa[k, :, 1]],
+                                         [float("{:0.8f}".format(v)) for v in pn[k, :, 1]], mats, ea, en)
+        agree += int(np.abs(ref - want).max() < 5e-3)
+    assert agree >= 198      # end to end vs the oracle: only bin-edge flips (probability within 1e-3 of an edge) may differ
+    eng.close()
