@@ -115,7 +115,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--candidates", type=int, default=100000, help="candidate sites per GPU per step")
-    ap.add_argument("--max-batch", type=int, default=9472, help="engine chunk (candidates per network pass)")
+    ap.add_argument("--max-batch", type=int, default=37888, help="engine chunk (candidates per network pass)")
     ap.add_argument("--cpu-sample", type=int, default=300, help="CPU baseline: candidates per host process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -157,8 +157,8 @@ def main():
     neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 200 + n_heads)
     eng = Engine(aff_sd, neg_sd, max_batch=args.max_batch, device=dev, likelihood=synthetic_likelihood(n_heads))
     lib = eng.lib
-    if os.environ.get("CTO_GRU_CLUSTER"):
-        lib.cto_debug_gru_cluster(int(os.environ["CTO_GRU_CLUSTER"]))
+    if os.environ.get("CTO_GRU_GATE_WARPS"):
+        lib.cto_debug_gru_gate_warps(int(os.environ["CTO_GRU_GATE_WARPS"]))
     if os.environ.get("CTO_DEBUG"):
         lib.cto_debug_set(int(os.environ["CTO_DEBUG"]))
     d_aff, d_neg = stream_to_device(aff, dev), stream_to_device(neg, dev)

@@ -30,7 +30,7 @@ int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* 
 
 }  // namespace cto
 
-namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; extern int g_gru_cluster; extern long long* g_gru_timing; extern int g_gru_pair; }
+namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; extern int g_gru3_gw; }
 using namespace cto;
 
 struct cto_engine {
@@ -201,11 +201,8 @@ int cto_posterior_from_probs(const double* tables_host, int n_heads, const doubl
 int64_t cto_launch_count(void) { return launches(); }
 
 void cto_debug_set(int flags) { cto::g_gemm_debug = flags; }
-void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; cto::g_gru_timing = dev_buf ? dev_buf + 24 : nullptr; }
-void cto_debug_gru_cluster(int c) {
-    if (c == 1 || c == 2 || c == 4) { cto::g_gru_cluster = c; cto::g_gru_pair = 0; }
-    if (c == 22) cto::g_gru_pair = 1;                 // CTA-pair kernel (tcgen05 cta_group::2)
-}
+void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; }
+void cto_debug_gru_gate_warps(int gw) { cto::g_gru3_gw = (gw == 2 || gw == 3 || gw == 4) ? gw : 0; }
 
 int cto_engine_set_tensor_cores(cto_engine* h, int enable) {
     CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");
@@ -217,11 +214,11 @@ int cto_gemm_nt(const float* a, int64_t lda, const float* w, const float* bias, 
                 float* c, int64_t ldc, int64_t m, int n, int k, int act, int use_tensor_cores, void* stream) {
     if (use_tensor_cores) {
         // split the weights on the fly (the engine does this once at load time)
-        float *hi = nullptr, *lo = nullptr;
+        uint16_t *hi = nullptr, *lo = nullptr;
         cudaStream_t s = (cudaStream_t)stream;
-        CTO_CHECK(cudaMallocAsync((void**)&hi, sizeof(float) * (size_t)n * k, s));
-        CTO_CHECK(cudaMallocAsync((void**)&lo, sizeof(float) * (size_t)n * k, s));
-        int rc = launch_split_tf32(w, hi, lo, (int64_t)n * k, s);
+        CTO_CHECK(cudaMallocAsync((void**)&hi, sizeof(uint16_t) * (size_t)n * k, s));
+        CTO_CHECK(cudaMallocAsync((void**)&lo, sizeof(uint16_t) * (size_t)n * k, s));
+        int rc = launch_split_bf16(w, hi, lo, (int64_t)n * k, s);
         if (!rc) rc = launch_gemm_tc(a, lda, hi, lo, bias, residual, ldr, c, ldc, m, n, k, act, s);
         cudaFreeAsync(hi, s);
         cudaFreeAsync(lo, s);

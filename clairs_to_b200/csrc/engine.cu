@@ -12,26 +12,30 @@ struct Walker {
     int64_t off = 0, total;
     const float* take(int64_t n) {
         const float* p = base + off;
-        off += (n + 3) & ~int64_t(3);          // every segment is padded to 4 floats (16 B)
+        off += (n + SEG_ALIGN - 1) & ~int64_t(SEG_ALIGN - 1);   // segments are padded to 8 floats (bf16 copies stay 16-byte aligned)
         return p;
     }
 };
 
-int upload(const float* host, int64_t n, WeightSet& ws) {
+enum SplitKind { SPLIT_NONE = 0, SPLIT_BF16 = 1 };
+
+int upload(const float* host, int64_t n, WeightSet& ws, int split) {
     ws.n = n;
     CTO_CHECK(cudaMalloc(&ws.blob, sizeof(float) * n));
-    CTO_CHECK(cudaMalloc(&ws.hi, sizeof(float) * n));
-    CTO_CHECK(cudaMalloc(&ws.lo, sizeof(float) * n));
     CTO_CHECK(cudaMemcpy(ws.blob, host, sizeof(float) * n, cudaMemcpyHostToDevice));
-    if (int rc = launch_split_tf32(ws.blob, ws.hi, ws.lo, n, nullptr)) return rc;
+    if (split & SPLIT_BF16) {
+        CTO_CHECK(cudaMalloc(&ws.bhi, sizeof(uint16_t) * n));
+        CTO_CHECK(cudaMalloc(&ws.bmid, sizeof(uint16_t) * n));
+        if (int rc = launch_split_bf16(ws.blob, ws.bhi, ws.bmid, n, nullptr)) return rc;
+    }
     CTO_CHECK(cudaDeviceSynchronize());
     return 0;
 }
 
 void release(WeightSet& ws) {
     if (ws.blob) cudaFree(ws.blob);
-    if (ws.hi) cudaFree(ws.hi);
-    if (ws.lo) cudaFree(ws.lo);
+    if (ws.bhi) cudaFree(ws.bhi);
+    if (ws.bmid) cudaFree(ws.bmid);
     ws = WeightSet();
 }
 
@@ -51,7 +55,7 @@ int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
     m.n_stages = cfg[1];
     CTO_REQUIRE(m.n_stages >= 1 && m.n_stages <= 3, "aff cfg: %d stages unsupported", m.n_stages);
     CTO_REQUIRE(m.n_heads == 4 || m.n_heads == 6, "aff cfg: %d heads (expected 4 or 6)", m.n_heads);
-    if (upload(host_blob, n, m.ws)) return 1;
+    if (upload(host_blob, n, m.ws, SPLIT_BF16)) return 1;
     Walker w{m.ws.blob, 0, n};
     int cin = N_CH, win = N_POS;
     for (int s = 0; s < m.n_stages; ++s) {
@@ -108,7 +112,7 @@ int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
     m.n_heads = cfg[0];
     CTO_REQUIRE(m.n_heads == 4 || m.n_heads == 6, "neg cfg: %d heads (expected 4 or 6)", m.n_heads);
     CTO_REQUIRE(cfg[1] == N_CH, "neg cfg: input dim %d != %d", cfg[1], N_CH);
-    if (upload(host_blob, n, m.ws)) return 1;
+    if (upload(host_blob, n, m.ws, SPLIT_BF16)) return 1;
     Walker w{m.ws.blob, 0, n};
     int in_dim = cfg[1];
     for (int l = 0; l < 2; ++l) {
@@ -130,24 +134,16 @@ int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
         const float* src = host_blob + (m.l[0].wih - m.ws.blob);
         for (int r = 0; r < rows; ++r)
             for (int c = 0; c < k; ++c) pad[(size_t)r * NEG_IN_LD + c] = src[(size_t)r * k + c];
-        if (upload(pad.data(), (int64_t)pad.size(), m.wih1_pad)) return 1;
+        if (upload(pad.data(), (int64_t)pad.size(), m.wih1_pad, SPLIT_BF16)) return 1;
     }
-    for (int l = 0; l < 2; ++l) {   // W_hh rows regrouped as (32-unit block, gate, unit) for the tensor-core recurrence
+    for (int l = 0; l < 2; ++l) {
+        // W_hh rows regrouped for the CTA-pair recurrence (gru_tc3.cu): (32-unit block, 16-unit half, gate, unit), so
+        // that each CTA of the pair streams the 48 rows (r,z,n x 16 units) whose accumulator columns land in its
+        // half of the TMEM lanes
         const int h = m.l[l].hidden;
-        if (h % 64 != 0) continue;
+        CTO_REQUIRE(h == 128 || h == 192, "neg cfg: GRU hidden size %d has no tensor-core recurrence kernel (128 / 192 built)", h);
         const float* wt = host_blob + (m.l[l].whh_t - m.ws.blob);      // [2][H (k)][3H (gate*H + unit)]
         std::vector<float> blk((size_t)2 * 3 * h * h);
-        for (int d = 0; d < 2; ++d)
-            for (int b = 0; b < h / 32; ++b)
-                for (int g = 0; g < 3; ++g)
-                    for (int j = 0; j < 32; ++j) {
-                        const int row = b * 96 + g * 32 + j, col = g * h + b * 32 + j;
-                        for (int k = 0; k < h; ++k)
-                            blk[((size_t)d * 3 * h + row) * h + k] = wt[((size_t)d * h + k) * 3 * h + col];
-                    }
-        if (upload(blk.data(), (int64_t)blk.size(), m.whh_blk[l])) return 1;
-        // CTA-pair kernel: inside a block the 16-unit halves come first, so that each CTA of the pair streams the
-        // 48 rows (r,z,n x 16 units) whose accumulator columns land in its half of the TMEM lanes
         for (int d = 0; d < 2; ++d)
             for (int b = 0; b < h / 32; ++b)
                 for (int hf = 0; hf < 2; ++hf)
@@ -157,7 +153,7 @@ int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
                             for (int k = 0; k < h; ++k)
                                 blk[((size_t)d * 3 * h + row) * h + k] = wt[((size_t)d * h + k) * 3 * h + col];
                         }
-        if (upload(blk.data(), (int64_t)blk.size(), m.whh_pair[l])) return 1;
+        if (upload(blk.data(), (int64_t)blk.size(), m.whh_pair[l], SPLIT_BF16)) return 1;
     }
     return 0;
 }
@@ -190,8 +186,21 @@ int engine_alloc(Engine& e, int64_t max_batch) {
     rc |= dev_alloc(e, &e.a_kv, b * a.sz_kv);
     rc |= dev_alloc(e, &e.a_att, b * a.sz_q);
     rc |= dev_alloc(e, &e.a_ff, b * a.sz_ff);
+    e.bp_max = (b + 127) / 128 * 128;
     const int64_t xp = (int64_t)N_POS * 6 * std::max(g.l[0].hidden, g.l[1].hidden);
-    rc |= dev_alloc(e, &e.n_xp, b * xp);
+    rc |= dev_alloc(e, &e.n_xp, e.bp_max * xp);
+    {   // zeroed once: rows of padded candidates are never written, they only have to stay finite
+        const int64_t rows = N_POS * e.bp_max;
+        const int64_t sizes[6] = {rows * NEG_IN_LD, rows * NEG_IN_LD, rows * 2 * g.l[0].hidden, rows * 2 * g.l[0].hidden,
+                                  rows * 2 * g.l[1].hidden, rows * 2 * g.l[1].hidden};
+        uint16_t** ptrs[6] = {&e.nx_hi, &e.nx_mid, &e.o1_hi, &e.o1_mid, &e.o2_hi, &e.o2_mid};
+        for (int i = 0; i < 6 && !rc; ++i) {
+            float* p = nullptr;
+            rc |= dev_alloc(e, &p, (sizes[i] + 1) / 2);
+            if (!rc) CTO_CHECK(cudaMemset(p, 0, sizeof(uint16_t) * sizes[i]));
+            *ptrs[i] = reinterpret_cast<uint16_t*>(p);
+        }
+    }
     rc |= dev_alloc(e, &e.n_o1, b * N_POS * 2 * g.l[0].hidden);
     rc |= dev_alloc(e, &e.n_o2, b * N_POS * 2 * g.l[1].hidden);
     rc |= dev_alloc(e, &e.f1, b * FC_DIM);
@@ -210,8 +219,6 @@ void engine_free(Engine& e) {
     release(e.aff.ws);
     release(e.neg.ws);
     release(e.neg.wih1_pad);
-    release(e.neg.whh_blk[0]);
-    release(e.neg.whh_blk[1]);
     release(e.neg.whh_pair[0]);
     release(e.neg.whh_pair[1]);
     if (e.tables) cudaFree(e.tables);
@@ -293,16 +300,15 @@ int prof_collect(Engine& e, double* ms, int64_t* count) {
 
 #define RUN(x) do { if (int _rc = (x)) return _rc; } while (0)
 
-int g_gru_pair = 1;        // 1: CTA-pair (cta_group::2) recurrence kernel, 0: single-CTA kernel with cluster multicast
-
-// dense contraction: tcgen05 TF32 when the engine allows it and the shape fits, CUDA-core fp32 otherwise
+// dense contraction: tcgen05 bf16x3 when the engine allows it and the shape fits, CUDA-core fp32 otherwise
 static int gemm(const Engine& e, const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr,
                 float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s) {
     if (e.use_tc && !a.conv && gemm_tc_supported(a.ptr, a.lda, w, m, n, k, c, ldc, residual, ldr)) {
         const WeightSet* ws = e.aff.ws.owns(w) ? &e.aff.ws : (e.neg.ws.owns(w) ? &e.neg.ws : nullptr);
         if (ws) {
             const int64_t off = w - ws->blob;
-            return launch_gemm_tc(a.ptr, a.lda, ws->hi + off, ws->lo + off, bias, residual, ldr, c, ldc, m, n, k, act, s);
+            if (off % SEG_ALIGN == 0)
+                return launch_gemm_tc(a.ptr, a.lda, ws->bhi + off, ws->bmid + off, bias, residual, ldr, c, ldc, m, n, k, act, s);
         }
     }
     return launch_gemm_nt(a, w, bias, residual, ldr, c, ldc, m, n, k, act, s);
@@ -370,32 +376,70 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
     return 0;
 }
 
+// Tensor-core NEG path.  Both input projections are computed TRANSPOSED, xproj^T[6H, 33*bp] = W_ih * X^T, so that
+// the recurrence kernel reads them with fully coalesced loads (gru_tc3.cu); every GEMM operand on this path is
+// already split into bf16 hi / mid planes by its producer, so the GEMM kernel runs without its converter warps.
+static int neg_forward_tc(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {
+    const NegModel& m = e.neg;
+    const int64_t bp = (n + 127) / 128 * 128, ldx = (int64_t)N_POS * bp;
+    CTO_REQUIRE(bp <= e.bp_max, "neg_forward: batch %lld > workspace", (long long)n);
+    const int h1 = m.l[0].hidden, h2 = m.l[1].hidden;
+    RUN(prof_begin(e, PK_NEG_PROJ1, s));
+    RUN(launch_split_time_major(x, n, N_POS, NEG_IN_LD, bp, e.nx_hi, e.nx_mid, s));
+    GemmTc g;
+    g.flags = GEMM_A_PRESPLIT | GEMM_BIAS_PER_ROW | GEMM_TILES_N_MAJOR;
+    g.a_hi = m.wih1_pad.bhi; g.a_mid = m.wih1_pad.bmid; g.lda = NEG_IN_LD;
+    g.w_hi = e.nx_hi; g.w_mid = e.nx_mid; g.ldw = NEG_IN_LD;
+    g.bias = m.l[0].bih; g.c = e.n_xp; g.ldc = ldx; g.m = 6 * h1; g.n = (int)ldx; g.k = NEG_IN_LD;
+    RUN(launch_gemm_tc_ex(g, s));
+    RUN(prof_end(e, s));
+    RUN(prof_begin(e, PK_NEG_GRU1, s));
+    RUN(launch_gru3(e.n_xp, ldx, bp, m.whh_pair[0].bhi, m.whh_pair[0].bmid, m.l[0].bhn, e.o1_hi, e.o1_mid, 1, bp, n, h1, s));
+    RUN(prof_end(e, s));
+    RUN(prof_begin(e, PK_NEG_PROJ2, s));
+    const int64_t off2 = m.l[1].wih - m.ws.blob;
+    g.a_hi = m.ws.bhi + off2; g.a_mid = m.ws.bmid + off2; g.lda = 2 * h1;
+    g.w_hi = e.o1_hi; g.w_mid = e.o1_mid; g.ldw = 2 * h1;
+    g.bias = m.l[1].bih; g.m = 6 * h2; g.k = 2 * h1;
+    RUN(launch_gemm_tc_ex(g, s));
+    RUN(prof_end(e, s));
+    RUN(prof_begin(e, PK_NEG_GRU2, s));
+    RUN(launch_gru3(e.n_xp, ldx, bp, m.whh_pair[1].bhi, m.whh_pair[1].bmid, m.l[1].bhn, e.o2_hi, e.o2_mid, N_POS, 1, n, h2, s));
+    RUN(prof_end(e, s));
+    const int feat = N_POS * 2 * h2;
+    const HeadW& hd = m.head;
+    RUN(prof_begin(e, PK_NEG_FC1, s));
+    const int64_t off1 = hd.fc1_w - m.ws.blob;
+    GemmTc f;
+    f.flags = GEMM_A_PRESPLIT;
+    f.a_hi = e.o2_hi; f.a_mid = e.o2_mid; f.lda = feat;
+    f.w_hi = m.ws.bhi + off1; f.w_mid = m.ws.bmid + off1; f.ldw = feat;
+    f.bias = hd.fc1_b; f.c = e.f1n; f.ldc = FC_DIM; f.m = n; f.n = FC_DIM; f.k = feat; f.act = ACT_SELU;
+    RUN(launch_gemm_tc_ex(f, s));
+    RUN(prof_end(e, s));
+    RUN(prof_begin(e, PK_NEG_HEADS, s));
+    RUN(gemm(e, plain_a(e.f1n, FC_DIM), hd.fc2_w, hd.fc2_b, nullptr, 0, e.f2n, (int64_t)m.n_heads * FC_DIM, n,
+                       m.n_heads * FC_DIM, FC_DIM, ACT_SELU, s));
+    RUN(launch_head_fc3(e.f2n, hd.fc3_w, hd.fc3_b, logits, n, m.n_heads, s));
+    return prof_end(e, s);
+}
+
 int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {
     CTO_REQUIRE(n <= e.max_batch, "neg_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
     const NegModel& m = e.neg;
+    if (e.use_tc) return neg_forward_tc(e, x, n, logits, s);
+    // fp32 CUDA-core path (cto_engine_set_tensor_cores(e, 0)): row-major projections + thread-per-unit recurrence
     const float* cur = x;
     float* outs[2] = {e.n_o1, e.n_o2};
     for (int l = 0; l < 2; ++l) {
         const GruLayerW& g = m.l[l];
         const int h = g.hidden;
         RUN(prof_begin(e, l ? PK_NEG_PROJ2 : PK_NEG_PROJ1, s));
-        if (l == 0 && e.use_tc) {
-            // x rows are padded to NEG_IN_LD floats; the zero-padded W_ih copy makes K = NEG_IN_LD exact
-            RUN(launch_gemm_tc(cur, NEG_IN_LD, m.wih1_pad.hi, m.wih1_pad.lo, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS,
-                               6 * h, NEG_IN_LD, ACT_NONE, s));
-        } else {
-            RUN(gemm(e, plain_a(cur, l == 0 ? NEG_IN_LD : g.in_dim), g.wih, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS,
-                     6 * h, g.in_dim, ACT_NONE, s));
-        }
+        RUN(gemm(e, plain_a(cur, l == 0 ? NEG_IN_LD : g.in_dim), g.wih, g.bih, nullptr, 0, e.n_xp, 6 * h, n * N_POS, 6 * h,
+                 g.in_dim, ACT_NONE, s));
         RUN(prof_end(e, s));
         RUN(prof_begin(e, l ? PK_NEG_GRU2 : PK_NEG_GRU1, s));
-        if (e.use_tc && g_gru_pair && m.whh_pair[l].hi) {
-            RUN(launch_gru_pair(e.n_xp, m.whh_pair[l].hi, m.whh_pair[l].lo, g.bhn, outs[l], n, h, s));
-        } else if (e.use_tc && m.whh_blk[l].hi) {
-            RUN(launch_gru_tc(e.n_xp, m.whh_blk[l].hi, m.whh_blk[l].lo, g.bhn, outs[l], n, h, s));
-        } else {
-            RUN(launch_gru_recurrent(e.n_xp, g.whh_t, g.bhn, outs[l], n, h, s));
-        }
+        RUN(launch_gru_recurrent(e.n_xp, g.whh_t, g.bhn, outs[l], n, h, s));
         RUN(prof_end(e, s));
         cur = outs[l];
     }

@@ -26,11 +26,14 @@ struct HeadW {
     const float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
 };
 
-constexpr int NEG_IN_LD = 36;      // NEG input rows are padded 34 -> 36 floats (16-byte row stride for TMA)
+constexpr int NEG_IN_LD = 40;      // NEG input rows are padded 34 -> 40 floats (16-byte row stride for the fp32 x rows
+                                   // AND for the bf16 rows of the K-padded W_ih copy)
+constexpr int SEG_ALIGN = 8;       // every blob segment starts on a multiple of 8 elements (16 bytes as bf16)
 
-// fp32 weights plus their TF32 hi / lo split (same offsets in all three blobs)
+// fp32 weights plus their bf16 hi / mid split (same element offsets in all three arrays) for the bf16x3 tensor-core kernels
 struct WeightSet {
-    float *blob = nullptr, *hi = nullptr, *lo = nullptr;
+    float* blob = nullptr;
+    uint16_t *bhi = nullptr, *bmid = nullptr;
     int64_t n = 0;
     bool owns(const float* w) const { return w >= blob && w < blob + n; }
 };
@@ -55,8 +58,7 @@ struct NegModel {
     HeadW head;
     WeightSet ws;
     WeightSet wih1_pad;        // layer-1 W_ih with K padded 34 -> NEG_IN_LD (zeros), for the tensor-core path
-    WeightSet whh_blk[2];      // per layer: W_hh [2 dirs][unit block (32) x gate x unit][H], for gru_tc.cu
-    WeightSet whh_pair[2];     // per layer: W_hh [2 dirs][unit block (32) x half (16) x gate x unit][H], for gru_tc2.cu
+    WeightSet whh_pair[2];     // per layer: W_hh [2 dirs][unit block (32) x half (16) x gate x unit][H], for gru_tc3.cu
 };
 
 struct Engine {
@@ -68,13 +70,17 @@ struct Engine {
     float *a_t0 = nullptr, *a_xs = nullptr, *a_y = nullptr, *a_dq = nullptr, *a_dkv = nullptr;
     float *a_q = nullptr, *a_kv = nullptr, *a_att = nullptr, *a_ff = nullptr;
     float *n_xp = nullptr, *n_o1 = nullptr, *n_o2 = nullptr;
+    // tensor-core NEG path: bf16 hi / mid planes. x and o1 are time-major [33, bp, .] (operands of the transposed
+    // input projections), o2 is batch-major [n, 33 * 2H] (A operand of the flattening fc1); bp = chunk rounded up to 128
+    uint16_t *nx_hi = nullptr, *nx_mid = nullptr, *o1_hi = nullptr, *o1_mid = nullptr, *o2_hi = nullptr, *o2_mid = nullptr;
+    int64_t bp_max = 0;
     float *f1 = nullptr, *f2 = nullptr;                        // head activations (shared sizes)
     float *f1n = nullptr, *f2n = nullptr;
     double* tables = nullptr;                                  // likelihood tables, n_heads * 122
     int table_heads = 0;
     std::vector<void*> allocs;
     cudaStream_t copy_stream = nullptr;                        // H2D spans of cto_run_sites_host overlap the kernels
-    bool use_tc = true;                                        // dense contractions on tcgen05 (TF32) where shapes allow
+    bool use_tc = true;                                        // dense contractions on tcgen05 (bf16x3) where shapes allow
     // optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
     int profile = 0;           // 0 off, 1 = NEG kernel families + AFF as one block, 2 = every AFF kernel family too
     struct ProfRec { int kind; cudaEvent_t start, stop; };

@@ -1,23 +1,27 @@
-// tcgen05 (5th-gen tensor core) GEMM for sm_100a with fp32-grade accuracy ("3xTF32"):
+// tcgen05 (5th-gen tensor core) GEMM for sm_100a with fp32-grade accuracy ("bf16x3"):
 //
 //     C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual)
 //
-// Plain TF32 (10 mantissa bits per operand) moves the AFF/NEG logits by up to 1e-2, ten times the
-// parity contract, so every operand is split into an exactly representable TF32 "hi" part and a
-// "lo" remainder and three MMAs are accumulated per k-step in fp32 TMEM:  hi*hi + lo*hi + hi*lo.
-// Weights are split once at load time (W_hi, W_lo in HBM); activations are split on the fly.
+// A single reduced-precision pass (TF32 or bf16) moves the AFF/NEG logits by up to 1e-2, ten times the
+// parity contract.  Every fp32 operand is therefore split into two bf16 parts, hi = bf16(x) and
+// mid = bf16(x - hi) (x - hi - mid is below 2^-18 |x|), and three kind::f16 MMAs are accumulated per
+// k-step in fp32 TMEM:  hi*hi + mid*hi + hi*mid  (the dropped mid*mid term is 2^-18 relative too).
+// Compared with the 3xTF32 split this kernel used first, the bf16 MMAs run at twice the tensor rate
+// and the split operands take half the shared memory; measured max |d logit| stays below 1e-4.
+// Weights are split once at load time (W_hi, W_mid as bf16 in HBM); activations on the fly.
 //
 // Persistent, warp-specialised, one CTA per SM:
-//   warp 0      TMA producer: A (128x32 fp32), W_hi, W_lo (BN x 32) boxes -> 3-stage smem ring,
-//               128-byte swizzle as the UMMA descriptors expect
-//   warps 2-5   converter: A -> A_hi (in place) + A_lo (second buffer), fence to the async proxy
-//   warp 1      MMA issuer (one elected thread): tcgen05.mma.kind::tf32, M=128, N=BN, K=8;
+//   warp 0      TMA producer: A as two 128x32 fp32 boxes, W_hi, W_mid (BN x 64 bf16) -> 3-stage smem
+//               ring, 128-byte swizzle as the UMMA descriptors expect
+//   warps 2-5   converter: fp32 A boxes -> bf16 A_hi / A_mid tiles (128 x 64, in place: row r of the two
+//               boxes is exactly the storage of row r of the two tiles), fence to the async proxy
+//   warp 1      MMA issuer (one elected thread): tcgen05.mma.kind::f16 (bf16), M=128, N=BN, K=16;
 //               tcgen05.commit releases smem stages and publishes the accumulator
-//   warps 6-13  epilogue (two groups of four warps, alternating 32-column slabs): tcgen05.ld (one TMEM lane = one output row), bias / GELU / SELU /
-//               residual in fp32, swizzled staging in smem, TMA store (full 128-byte lines,
-//               M tail clipped by the tensor map)
+//   warps 6-13  epilogue (two groups of four warps, alternating 32-column slabs): tcgen05.ld (one TMEM
+//               lane = one output row), bias / GELU / SELU / residual in fp32, swizzled staging in smem,
+//               TMA store (full 128-byte lines, M tail clipped by the tensor map)
 // The accumulator is double buffered in TMEM (2 x 128 columns) so the epilogue of tile i overlaps
-// the main loop of tile i+1.  K and M tails are zero-filled by TMA; N must be a multiple of 64.
+// the main loop of tile i+1.  K and M tails are zero-filled by TMA; N must be a multiple of 64, K of 8.
 #include "nn_kernels.cuh"
 #include <cuda.h>
 
@@ -26,10 +30,11 @@ namespace cto {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                       // fp32 elements = one 128-byte swizzle row
+constexpr int BK = 64;                       // K elements per stage = one 128-byte swizzle row of bf16
 constexpr int MAX_BN = 128;
-constexpr int TILE_BYTES = BM * BK * 4;      // 16 KB (A, A_lo; W tiles use BN*128 bytes of theirs)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A | A_lo | W_hi | W_lo
+constexpr int TILE_BYTES = BM * 128;         // 16 KB: one fp32 A box (128 x 32) on arrival, one bf16 tile (128 x 64) after
+                                             // the conversion; W tiles use BN*128 bytes of theirs
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A box 0 -> A_hi | A box 1 -> A_mid | W_hi | W_mid
 constexpr int STAGES = 3;
 constexpr int SLAB = 32;                     // epilogue works on 128 x 32 fp32 slabs
 constexpr int STAGING_BYTES = BM * SLAB * 4; // 16 KB, two of them
@@ -70,13 +75,26 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// two fp32 -> packed bf16x2 (round to nearest even); `lo` lands in the low half = the lower address
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// x[0..1] -> hi pair, mid pair:  hi = bf16(x), mid = bf16(x - hi)  (x - hi is exact in fp32)
+__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& mid) {
+    hi = pack_bf16x2(x0, x1);
+    const float r0 = x0 - __uint_as_float(hi << 16);
+    const float r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
+    mid = pack_bf16x2(r0, r1);
 }
 // one lane of a converged warp; the surrounding loop stays warp-uniform so that descriptors live in uniform
 // registers (inside an `if (lane == 0)` region ptxas wraps every UTCHMMA / UTMALDG in an ELECT /
@@ -92,11 +110,6 @@ __device__ __forceinline__ bool elect_one() {
         "}" : "+r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ float round_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B: rows of 128 bytes, 8-row groups
 // 1024 bytes apart (SBO), LBO unused (=1), descriptor version 1 (sm_100).
@@ -110,9 +123,9 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=bn
-__device__ __forceinline__ uint32_t make_idesc_tf32(int bn) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -124,16 +137,21 @@ __device__ __forceinline__ float selu(float x) {
 
 template <int ACT>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_whi,
-                   const __grid_constant__ CUtensorMap tma_wlo, const __grid_constant__ CUtensorMap tma_c,
-                   const float* __restrict__ bias, const float* residual, int64_t ldr, int64_t m_total, int n_total,
-                   int k_total, int bn, int dbg, long long* timing) {
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_amid,
+                   const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__ CUtensorMap tma_wmid,
+                   const __grid_constant__ CUtensorMap tma_c, const float* __restrict__ bias, const float* residual,
+                   int64_t ldr, int64_t m_total, int n_total, int k_total, int bn, int flags, int dbg, long long* timing) {
+    const bool presplit = flags & GEMM_A_PRESPLIT;       // A arrives as bf16 hi / mid planes: no converter pass
+    const bool bias_row = flags & GEMM_BIAS_PER_ROW;     // bias indexed by the output row (transposed products)
+    const bool n_major = flags & GEMM_TILES_N_MAJOR;     // consecutive CTAs share the W tile instead of the A tile
     extern __shared__ uint8_t smem_raw[];
     const bool tim = dbg && blockIdx.x == 0 && timing != nullptr;    // per-phase cycle counters (profiles/)
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     #define TIC long long _t0 = tim ? clock64() : 0
     #define TOC(i) do { if (tim) { long long _t1 = clock64(); tacc[i] += _t1 - _t0; _t0 = _t1; } } while (0)
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by POINTER arithmetic on the __shared__ array: rounding through uintptr_t makes the
+    // compiler lose the address space and emit generic LD.E / ST.E for every shared-memory access
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* staging = base + STAGES * STAGE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(staging + 2 * STAGING_BYTES);
     uint64_t* conv = full + STAGES;
@@ -164,10 +182,10 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
     if (warp == 0) {
         {                                                  // ---- TMA producer (warp-uniform loop, elected lane issues) ----
-            const uint32_t tx = (uint32_t)(BM + 2 * bn) * BK * 4;
             uint32_t it = 0;
             for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * bn;
+                const int m0 = (n_major ? (int)(t % m_tiles) : (int)(t / n_tiles)) * BM;
+                const int n0 = (n_major ? (int)(t / m_tiles) : (int)(t % n_tiles)) * bn;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -175,11 +193,15 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     mbar_wait(&empty[s], ph ^ 1);
                     TOC(0);
                     uint8_t* st = base + s * STAGE_BYTES;
+                    // fp32 A: the second 128 x 32 box is skipped when it holds no live column; pre-split A: hi and mid tile
+                    const bool two = presplit || k_total - kb * BK > 32;
                     if (elect_one()) {
-                        mbar_expect_tx(&full[s], tx);
+                        mbar_expect_tx(&full[s], (uint32_t)((two ? 2 : 1) * TILE_BYTES + 2 * bn * 128));
                         tma_load_2d(&tma_a, &full[s], st, kb * BK, m0);
+                        if (presplit) tma_load_2d(&tma_amid, &full[s], st + TILE_BYTES, kb * BK, m0);
+                        else if (two) tma_load_2d(&tma_a, &full[s], st + TILE_BYTES, kb * BK + 32, m0);
                         tma_load_2d(&tma_whi, &full[s], st + 2 * TILE_BYTES, kb * BK, n0);
-                        tma_load_2d(&tma_wlo, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
+                        tma_load_2d(&tma_wmid, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
                     }
                     __syncwarp();
                     TOC(1);
@@ -189,7 +211,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         }
     } else if (warp == 1) {
         {                                                  // ---- MMA issuer (warp-uniform loop, elected lane issues) ----
-            const uint32_t idesc = make_idesc_tf32(bn);
+            const uint32_t idesc = make_idesc_bf16(bn);
             uint32_t it = 0, acc_it = 0;
             for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
                 const uint32_t ab = acc_it & 1, aph = (acc_it >> 1) & 1;
@@ -203,22 +225,24 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);               // W tiles landed
                     TOC(1);
-                    mbar_wait(&conv[s], ph);               // A split into hi / lo
+                    if (!presplit) mbar_wait(&conv[s], ph);  // A split into bf16 hi / mid
                     TOC(2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = smem_u32(base + s * STAGE_BYTES);
                     const uint64_t d_ahi = make_desc_k_sw128(a_addr);
-                    const uint64_t d_alo = make_desc_k_sw128(a_addr + TILE_BYTES);
+                    const uint64_t d_amid = make_desc_k_sw128(a_addr + TILE_BYTES);
                     const uint64_t d_whi = make_desc_k_sw128(a_addr + 2 * TILE_BYTES);
-                    const uint64_t d_wlo = make_desc_k_sw128(a_addr + 3 * TILE_BYTES);
+                    const uint64_t d_wmid = make_desc_k_sw128(a_addr + 3 * TILE_BYTES);
+                    const int ksteps = min(BK / 16, (k_total - kb * BK + 15) >> 4);   // K tail: skip all-zero k-steps
                     if (elect_one()) {
                         #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) {
-                            // 8 tf32 = 32 bytes along the swizzle row: +2 in the (>>4) start-address field
+                        for (int k = 0; k < BK / 16; ++k) {
+                            if (k >= ksteps) break;
+                            // 16 bf16 = 32 bytes along the swizzle row: +2 in the (>>4) start-address field
                             const uint64_t o = (uint64_t)(k * 2);
-                            mma_tf32(acc, d_ahi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
-                            mma_tf32(acc, d_alo + o, d_whi + o, idesc, 1u);
-                            mma_tf32(acc, d_ahi + o, d_wlo + o, idesc, 1u);
+                            mma_bf16(acc, d_ahi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
+                            mma_bf16(acc, d_amid + o, d_whi + o, idesc, 1u);
+                            mma_bf16(acc, d_ahi + o, d_wmid + o, idesc, 1u);
                         }
                         tcgen05_commit(&empty[s]);             // stage reusable once these MMAs retire
                         if (kb == num_kb - 1) tcgen05_commit(&acc_full[ab]);   // accumulator complete
@@ -231,28 +255,51 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         }
     } else if (warp < 6) {                                 // ---- converter: warps 2..5 ----
         const int ct = threadIdx.x - 64;                   // 0..127
+        const int cw = warp - 2;
+        const int c = lane & 7;                            // 16-byte output chunk = 8 consecutive k
         uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int64_t t = blockIdx.x; t < num_tiles && !presplit; t += gridDim.x) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 TIC;
                 mbar_wait(&full[s], ph);
                 TOC(0);
-                float4* a_hi = reinterpret_cast<float4*>(base + s * STAGE_BYTES);
-                float4* a_lo = reinterpret_cast<float4*>(base + s * STAGE_BYTES + TILE_BYTES);
+                uint8_t* st = base + s * STAGE_BYTES;
+                const int nchunks = min(8, ((k_total - kb * BK + 15) >> 4) * 2);   // chunks the MMAs will read
+                // fp32 element (r, k) sits in box k/32 at 16-byte unit ((k%32)/4) ^ (r%8) of row r; bf16 element
+                // (r, k) goes to chunk (k/8) ^ (r%8) of row r.  Eight lanes own one row per pass, so the in-place
+                // rewrite only needs the warp to finish its loads before its stores.
                 #pragma unroll
-                for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {       // elementwise: the swizzle is irrelevant
-                    const int idx = ct + i * 128;
-                    // the tensor core reads an fp32 word as TF32 by dropping the 13 low mantissa bits, so the raw
-                    // tile already is the "hi" operand; only lo = a - trunc(a) (exact in fp32) has to be written
-                    const float4 v = a_hi[idx];
-                    float4 lo;
-                    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    a_lo[idx] = lo;
+                for (int half = 0; half < 2; ++half) {             // 4 rows per lane in flight: loads, then stores
+                    float4 v[4][2];
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = (half * 4 + j) * 16 + cw * 4 + (lane >> 3);
+                        const uint8_t* src = st + (c >> 2) * TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+                        const int u0 = 2 * (c & 3);
+                        v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c < nchunks) {
+                            v[j][0] = *reinterpret_cast<const float4*>(src + ((u0 ^ (r & 7)) << 4));
+                            v[j][1] = *reinterpret_cast<const float4*>(src + (((u0 + 1) ^ (r & 7)) << 4));
+                        }
+                    }
+                    __syncwarp();
+                    if (c < nchunks) {
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int r = (half * 4 + j) * 16 + cw * 4 + (lane >> 3);
+                            uint4 hi, mid;
+                            split2_bf16(v[j][0].x, v[j][0].y, hi.x, mid.x);
+                            split2_bf16(v[j][0].z, v[j][0].w, hi.y, mid.y);
+                            split2_bf16(v[j][1].x, v[j][1].y, hi.z, mid.z);
+                            split2_bf16(v[j][1].z, v[j][1].w, hi.w, mid.w);
+                            const uint32_t dst = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+                            *reinterpret_cast<uint4*>(st + dst) = hi;
+                            *reinterpret_cast<uint4*>(st + TILE_BYTES + dst) = mid;
+                        }
+                    }
+                    __syncwarp();
                 }
                 TOC(1);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> UMMA reads
@@ -270,7 +317,8 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         uint8_t* stg = staging + grp * STAGING_BYTES;      // one staging buffer per group
         uint32_t acc_it = 0;
         for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++acc_it) {
-            const int m0 = (int)(t / n_tiles) * BM, n0 = (int)(t % n_tiles) * bn;
+            const int m0 = (n_major ? (int)(t % m_tiles) : (int)(t / n_tiles)) * BM;
+            const int n0 = (n_major ? (int)(t / m_tiles) : (int)(t % n_tiles)) * bn;
             const uint32_t ab = acc_it & 1, aph = (acc_it >> 1) & 1;
             TIC;
             mbar_wait(&acc_full[ab], aph);
@@ -278,6 +326,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = (int64_t)m0 + r_in_tile;
             const bool row_ok = row < m_total;
+            const float rbias = (bias_row && bias && row_ok) ? __ldg(bias + row) : 0.0f;
             for (int cb = grp * SLAB; cb < bn; cb += 2 * SLAB) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ab * MAX_BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb;
@@ -295,15 +344,14 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&acc_empty[ab]);
                 }
-                // the group's previous TMA store must have finished reading the staging buffer
-                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 TOC(2);
                 const float* rrow = (residual && row_ok) ? residual + row * ldr + n0 + cb : nullptr;
+                float4 o[8];
                 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + cb) + q);
+                    if (bias_row) bv = make_float4(rbias, rbias, rbias, rbias);
+                    else if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + cb) + q);
                     float v[4] = {__uint_as_float(r[q * 4]) + bv.x, __uint_as_float(r[q * 4 + 1]) + bv.y,
                                   __uint_as_float(r[q * 4 + 2]) + bv.z, __uint_as_float(r[q * 4 + 3]) + bv.w};
                     if (ACT == ACT_GELU) {
@@ -317,22 +365,26 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         const float4 rv = *reinterpret_cast<const float4*>(rrow + q * 4);
                         v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
                     }
-                    // 128-byte swizzle: 16-byte chunk q of row r lives at chunk (q ^ (r % 8))
-                    *reinterpret_cast<float4*>(stg + r_in_tile * 128 + ((q ^ (r_in_tile & 7)) << 4)) =
-                        make_float4(v[0], v[1], v[2], v[3]);
+                    o[q] = make_float4(v[0], v[1], v[2], v[3]);
                 }
                 TOC(3);
+                // this warp's previous TMA store must have finished reading its 32-row staging strip
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                #pragma unroll
+                for (int q = 0; q < 8; ++q)   // 128-byte swizzle: 16-byte chunk q of row r lives at chunk (q ^ (r % 8))
+                    *reinterpret_cast<float4*>(stg + r_in_tile * 128 + ((q ^ (r_in_tile & 7)) << 4)) = o[q];
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 TOC(4);
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+                __syncwarp();
                 TOC(5);
-                if (et == 0) {
-                    tma_store_2d(&tma_c, stg, n0 + cb, m0);
+                if (lane == 0) {                               // one 32 x 32 box per warp: no cross-warp barrier in the epilogue
+                    tma_store_2d(&tma_c, stg + quad * (32 * 128), n0 + cb, m0 + quad * 32);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
-        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (tim && et == 0 && grp == 0) { for (int i = 0; i < 6; ++i) timing[12 + i] = tacc[i]; timing[20] = (long long)num_tiles; timing[21] = num_kb; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -343,20 +395,22 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     }
 }
 
-// fp32 -> exactly representable TF32 hi (round to nearest) + TF32 lo remainder
-__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+// fp32 -> bf16 hi + bf16 mid (both round to nearest even)
+__global__ void split_bf16_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ mid, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float v = w[i];
-    const float h = round_tf32(v);
-    hi[i] = h;
-    lo[i] = round_tf32(v - h);
+    uint32_t h, m;
+    split2_bf16(w[i], 0.0f, h, m);
+    hi[i] = (uint16_t)(h & 0xFFFFu);
+    mid[i] = (uint16_t)(m & 0xFFFFu);
 }
 
-int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D tiled tensor map with 128-byte swizzle; the box is (128 bytes of the inner dimension) x box_rows
+static int make_map_any(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* ptr, int64_t rows, int64_t cols,
+                        int64_t ld, int box_rows) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     // resolved through the runtime so that the library has no link-time dependency on libcuda
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -370,9 +424,8 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
         CTO_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
         encode = reinterpret_cast<encode_fn>(fn);
     }
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(map, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
                   (long long)cols, (long long)ld);
@@ -381,64 +434,92 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
     return 0;
 }
 
+int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    return make_map_any(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, rows, cols, ld, box_rows);
+}
+int make_map_bf16(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    return make_map_any(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, rows, cols, ld, box_rows);
+}
+
 }  // namespace tc
 
 long long* g_gemm_timing = nullptr;   // device buffer [32] filled by CTA 0 when (dbg & 16)
 int g_gemm_debug = 0;       // non-zero: CTA 0 records per-phase cycle counters into g_gemm_timing (cto_debug_set)
 
-int launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s) {
+int launch_split_bf16(const float* w, uint16_t* hi, uint16_t* mid, int64_t n, cudaStream_t s) {
     if (n <= 0) return 0;
-    tc::split_tf32_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w, hi, lo, n);
+    tc::split_bf16_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w, hi, mid, n);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;
 }
 
-bool gemm_tc_supported(const float* a, int64_t lda, const float* w, int64_t m, int n, int k, const float* c, int64_t ldc,
+bool gemm_tc_supported(const float* a, int64_t lda, const void* w, int64_t m, int n, int k, const float* c, int64_t ldc,
                        const float* residual, int64_t ldr) {
-    if (m <= 0 || n < 64 || n % 64 != 0 || k < 8) return false;
-    if (lda % 4 != 0 || k % 4 != 0 || ldc % 4 != 0 || (residual && ldr % 4 != 0)) return false;
+    if (m <= 0 || n < 64 || n % 64 != 0 || k < 8 || k % 8 != 0) return false;     // bf16 W rows: 16-byte strides
+    if (lda % 4 != 0 || ldc % 4 != 0 || (residual && ldr % 4 != 0)) return false;
     if (m >= (1ll << 31) - tc::BM) return false;
     const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) |
                            reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(residual);
     return (bits & 15) == 0;
 }
 
-int launch_gemm_tc(const float* a, int64_t lda, const float* w_hi, const float* w_lo, const float* bias,
-                   const float* residual, int64_t ldr, float* c, int64_t ldc, int64_t m, int n, int k, int act,
-                   cudaStream_t s) {
-    CTO_REQUIRE(gemm_tc_supported(a, lda, w_hi, m, n, k, c, ldc, residual, ldr) && w_lo &&
-                    (reinterpret_cast<uintptr_t>(w_lo) & 15) == 0,
-                "gemm_tc: unsupported shape/alignment m=%lld n=%d k=%d lda=%lld ldc=%lld", (long long)m, n, k,
-                (long long)lda, (long long)ldc);
+int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s) {
+    const bool presplit = g.flags & GEMM_A_PRESPLIT;
+    const void* a_any = presplit ? (const void*)g.a_hi : (const void*)g.a;
+    const int64_t a_align = presplit ? 8 : 4;            // elements per 16 bytes
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(a_any) | reinterpret_cast<uintptr_t>(g.a_mid) |
+                           reinterpret_cast<uintptr_t>(g.w_hi) | reinterpret_cast<uintptr_t>(g.w_mid) |
+                           reinterpret_cast<uintptr_t>(g.c) | reinterpret_cast<uintptr_t>(g.residual);
+    CTO_REQUIRE(a_any && g.w_hi && g.w_mid && g.c && (!presplit || g.a_mid) && (bits & 15) == 0 && g.m > 0 &&
+                    g.m < (1ll << 31) - tc::BM && g.n >= 64 && g.n % 64 == 0 && g.k >= 8 && g.k % 8 == 0 &&
+                    g.lda % a_align == 0 && g.ldw % 8 == 0 && g.ldc % 4 == 0 && (!g.residual || g.ldr % 4 == 0),
+                "gemm_tc: unsupported shape/alignment m=%lld n=%d k=%d lda=%lld ldw=%lld ldc=%lld flags=%d", (long long)g.m,
+                g.n, g.k, (long long)g.lda, (long long)g.ldw, (long long)g.ldc, g.flags);
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
         CTO_CHECK(cudaGetDevice(&dev));
         CTO_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_3xtf32_kernel<ACT_SELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<ACT_SELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     }
     // 128-wide tiles unless that leaves SMs without a tile (long-K, few-row GEMMs such as the NEG fc1)
-    const int bn = (n % 128 == 0 && (int64_t)ceil_div(m, tc::BM) * (n / 128) >= sm_count) ? 128 : 64;
-    CUtensorMap map_a, map_whi, map_wlo, map_c;
-    if (tc::make_map(&map_a, a, m, k, lda, tc::BM)) return 1;
-    if (tc::make_map(&map_whi, w_hi, n, k, k, bn)) return 1;
-    if (tc::make_map(&map_wlo, w_lo, n, k, k, bn)) return 1;
-    if (tc::make_map(&map_c, c, m, n, ldc, tc::BM)) return 1;
-    const int64_t tiles = (int64_t)ceil_div(m, tc::BM) * (n / bn);
+    const int bn = (g.n % 128 == 0 && (int64_t)ceil_div(g.m, tc::BM) * (g.n / 128) >= sm_count) ? 128 : 64;
+    CUtensorMap map_a, map_amid, map_whi, map_wmid, map_c;
+    if (presplit) {
+        if (tc::make_map_bf16(&map_a, g.a_hi, g.m, g.k, g.lda, tc::BM)) return 1;
+        if (tc::make_map_bf16(&map_amid, g.a_mid, g.m, g.k, g.lda, tc::BM)) return 1;
+    } else {
+        if (tc::make_map(&map_a, g.a, g.m, g.k, g.lda, tc::BM)) return 1;
+        map_amid = map_a;
+    }
+    if (tc::make_map_bf16(&map_whi, g.w_hi, g.n, g.k, g.ldw, bn)) return 1;
+    if (tc::make_map_bf16(&map_wmid, g.w_mid, g.n, g.k, g.ldw, bn)) return 1;
+    if (tc::make_map(&map_c, g.c, g.m, g.n, g.ldc, 32)) return 1;          // every epilogue warp stores its own 32-row strip
+    const int64_t tiles = (int64_t)ceil_div(g.m, tc::BM) * (g.n / bn);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-#define CTO_LAUNCH_GEMM(A)                                                                                     \
-    tc::gemm_3xtf32_kernel<A><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_whi, map_wlo, map_c, bias, residual, \
-                                                                       ldr, m, n, k, bn, g_gemm_debug, g_gemm_timing)
-    if (act == ACT_GELU) CTO_LAUNCH_GEMM(ACT_GELU);
-    else if (act == ACT_SELU) CTO_LAUNCH_GEMM(ACT_SELU);
+#define CTO_LAUNCH_GEMM(A)                                                                                             \
+    tc::gemm_bf16x3_kernel<A><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_amid, map_whi, map_wmid, map_c, g.bias, \
+                                                                       g.residual, g.ldr, g.m, g.n, g.k, bn, g.flags,   \
+                                                                       g_gemm_debug, g_gemm_timing)
+    if (g.act == ACT_GELU) CTO_LAUNCH_GEMM(ACT_GELU);
+    else if (g.act == ACT_SELU) CTO_LAUNCH_GEMM(ACT_SELU);
     else CTO_LAUNCH_GEMM(ACT_NONE);
 #undef CTO_LAUNCH_GEMM
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;
+}
+
+int launch_gemm_tc(const float* a, int64_t lda, const uint16_t* w_hi, const uint16_t* w_mid, const float* bias,
+                   const float* residual, int64_t ldr, float* c, int64_t ldc, int64_t m, int n, int k, int act,
+                   cudaStream_t s) {
+    GemmTc g;
+    g.a = a; g.lda = lda; g.w_hi = w_hi; g.w_mid = w_mid; g.ldw = k; g.bias = bias; g.residual = residual; g.ldr = ldr;
+    g.c = c; g.ldc = ldc; g.m = m; g.n = n; g.k = k; g.act = act;
+    return launch_gemm_tc_ex(g, s);
 }
 
 }  // namespace cto

@@ -68,6 +68,42 @@ int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_o
     return 0;
 }
 
+// fp32 rows [n, t_len, ld] -> time-major bf16 hi / mid planes [t_len, bp, ld]; one thread per 8-element chunk
+__global__ void split_time_major_kernel(const float* __restrict__ x, int64_t n, int t_len, int ld, int64_t bp,
+                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ mid) {
+    const int chunks = ld / 8;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * t_len * chunks) return;
+    const int c = (int)(i % chunks);
+    const int64_t row = i / chunks;                    // b * t_len + t
+    const int64_t b = row / t_len;
+    const int t = (int)(row - b * t_len);
+    const float4 v0 = *reinterpret_cast<const float4*>(x + row * ld + c * 8);
+    const float4 v1 = *reinterpret_cast<const float4*>(x + row * ld + c * 8 + 4);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t h[4], m[4];
+    #pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(v[2 * e + 1]), "f"(v[2 * e]));
+        const float r0 = v[2 * e] - __uint_as_float(h[e] << 16), r1 = v[2 * e + 1] - __uint_as_float(h[e] & 0xFFFF0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m[e]) : "f"(r1), "f"(r0));
+    }
+    const int64_t o = ((int64_t)t * bp + b) * ld + c * 8;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(mid + o) = make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+int launch_split_time_major(const float* x, int64_t n, int t_len, int ld_in, int64_t bp, uint16_t* hi, uint16_t* mid,
+                            cudaStream_t s) {
+    if (n <= 0) return 0;
+    CTO_REQUIRE(ld_in % 8 == 0 && bp >= n, "split_time_major: ld %d must be a multiple of 8 and bp >= n", ld_in);
+    const int64_t total = n * t_len * (ld_in / 8);
+    split_time_major_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, n, t_len, ld_in, bp, hi, mid);
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 // strand-count recovery (P:626-642): centre row, forward cols 0:4, reverse cols 9:13
 __global__ void strand_counts_kernel(const int16_t* __restrict__ x, int64_t n, int32_t* __restrict__ fwd,
                                      int32_t* __restrict__ rev) {

@@ -23,14 +23,31 @@ static inline AView conv_a(const float* p, int win, int wout, int cin) { return 
 int launch_gemm_nt(const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr,
                    float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s);
 
-// tcgen05 TF32 path (gemm_tc.cu); plain row-major A only
-bool gemm_tc_supported(const float* a, int64_t lda, const float* w, int64_t m, int n, int k, const float* c, int64_t ldc,
+// tcgen05 bf16x3 path (gemm_tc.cu); plain row-major fp32 A only
+bool gemm_tc_supported(const float* a, int64_t lda, const void* w, int64_t m, int n, int k, const float* c, int64_t ldc,
                        const float* residual, int64_t ldr);
-// w_hi / w_lo: the weight matrix split into TF32 hi + lo parts (launch_split_tf32)
-int launch_gemm_tc(const float* a, int64_t lda, const float* w_hi, const float* w_lo, const float* bias,
+// w_hi / w_mid: the weight matrix [n, k] split into bf16 hi + mid parts (launch_split_bf16)
+int launch_gemm_tc(const float* a, int64_t lda, const uint16_t* w_hi, const uint16_t* w_mid, const float* bias,
                    const float* residual, int64_t ldr, float* c, int64_t ldc, int64_t m, int n, int k, int act,
                    cudaStream_t s);
-int launch_split_tf32(const float* w, float* hi, float* lo, int64_t n, cudaStream_t s);
+int launch_split_bf16(const float* w, uint16_t* hi, uint16_t* mid, int64_t n, cudaStream_t s);
+// the general form: A either fp32 (split by the kernel's converter warps) or already split into bf16 hi / mid
+// planes; W always pre-split, row stride ldw
+enum GemmFlags { GEMM_A_PRESPLIT = 1, GEMM_BIAS_PER_ROW = 2, GEMM_TILES_N_MAJOR = 4 };
+struct GemmTc {
+    const float* a = nullptr;                          // fp32 A [m, k], row stride lda        (flags & A_PRESPLIT == 0)
+    const uint16_t *a_hi = nullptr, *a_mid = nullptr;  // bf16 planes of A [m, k], row stride lda (flags & A_PRESPLIT)
+    int64_t lda = 0;
+    const uint16_t *w_hi = nullptr, *w_mid = nullptr;  // bf16 planes of W [n, k], row stride ldw
+    int64_t ldw = 0;
+    const float* bias = nullptr;                       // [n], or [m] with GEMM_BIAS_PER_ROW
+    const float* residual = nullptr;
+    int64_t ldr = 0;
+    float* c = nullptr;
+    int64_t ldc = 0, m = 0;
+    int n = 0, k = 0, act = ACT_NONE, flags = 0;
+};
+int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s);
 
 // ld_out >= 34: row stride of the fp32 output (extra columns are zero-filled)
 int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, int ld_out, cudaStream_t s);
@@ -44,12 +61,13 @@ int launch_attention(const float* q, const float* kv, float* out, int64_t batch,
                      cudaStream_t s);
 int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bhn, float* out, int64_t batch,
                          int hidden, cudaStream_t s);
-// tensor-core recurrence (gru_tc.cu): w_hi / w_lo = W_hh regrouped per 32-unit block, TF32 hi / lo
-int launch_gru_tc(const float* xproj, const float* w_hi, const float* w_lo, const float* bhn, float* out, int64_t batch,
-                  int hidden, cudaStream_t s);
-// CTA-pair recurrence (gru_tc2.cu, tcgen05 cta_group::2): W_hh regrouped per (32-unit block, 16-unit half, gate)
-int launch_gru_pair(const float* xproj, const float* w_hi, const float* w_lo, const float* bhn, float* out, int64_t batch,
-                    int hidden, cudaStream_t s);
+// tensor-core recurrence (gru_tc3.cu): CTA pair (tcgen05 cta_group::2) + bf16x3, reads the TRANSPOSED projection xproj[6H][t * bp + b], writes
+// h_t as bf16 hi / mid planes at row (b * osb + t * ost) of [.., 2H]
+int launch_gru3(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_hi, const uint16_t* w_mid, const float* bhn,
+                uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch, int hidden, cudaStream_t s);
+// fp32 rows [n, t_len, ld_in] -> time-major bf16 hi / mid planes [t_len, bp, ld_in] (rows b >= n are left untouched)
+int launch_split_time_major(const float* x, int64_t n, int t_len, int ld_in, int64_t bp, uint16_t* hi, uint16_t* mid,
+                            cudaStream_t s);
 int launch_head_fc3(const float* y, const float* w3, const float* b3, float* logits, int64_t batch, int n_heads,
                     cudaStream_t s);
 int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,

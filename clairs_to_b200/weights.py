@@ -3,7 +3,8 @@
 The reference stores whole pickled modules, ``{'model_acgt': CvT...}`` / ``{'model_nacgt': BiGRU...}``
 (clairs/predict.py:512-568); hyper-parameters live only in tensor shapes, so everything here is
 derived from the ``state_dict``.  The segment order below is walked identically
-by ``csrc/engine.cu`` (``aff_load`` / ``neg_load``); every segment is padded to 4 floats.
+by ``csrc/engine.cu`` (``aff_load`` / ``neg_load``); every segment is padded to 8 floats
+(so that the engine's bf16 copies of the same segments stay 16-byte aligned for TMA).
 
 Host-side folding (exact up to fp32 rounding of the folded constants):
   * 3x3 kernels act on H=1 maps -> only the middle kernel row is kept (clairs/model.py:195, 93);
@@ -21,6 +22,7 @@ import numpy as np
 DIM_HEAD = 64
 BN_EPS = 1e-5
 N_POS, N_CH = 33, 34
+SEG_ALIGN = 8          # csrc/engine.cuh SEG_ALIGN
 
 
 def _np(t):
@@ -35,7 +37,7 @@ class _Blob:
 
     def add(self, arr):
         a = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
-        pad = (-a.size) % 4
+        pad = (-a.size) % SEG_ALIGN
         if pad:
             a = np.concatenate([a, np.zeros(pad, dtype=np.float32)])
         self.parts.append(a)

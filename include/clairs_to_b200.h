@@ -123,13 +123,13 @@ int cto_engine_profile_read(cto_engine* e, double* ms, int64_t* launches, double
 
 /*
  * Tuning / profiling knobs (not part of the drop-in surface): cto_debug_set(1) + cto_debug_timing(buf) make
- * CTA 0 of the GEMM and GRU kernels record per-phase clock64() counters into a device buffer [32 x int64]
- * (profiles/phase_timing.py prints them); cto_debug_gru_cluster sets the thread-block-cluster size (1, 2 or 4)
- * that shares one W_hh stream (TMA multicast) in the tensor-core GRU.
+ * CTA 0 of the GEMM kernel record per-phase clock64() counters into a device buffer [32 x int64]
+ * (profiles/phase_timing_gemm.py prints them); cto_debug_gru_gate_warps picks the number of gate-math warps per
+ * TMEM lane quadrant in the tensor-core GRU (2, 3 or 4; 0 = the measured best per hidden size).
  */
 void cto_debug_set(int flags);
 void cto_debug_timing(long long* dev_buf);
-void cto_debug_gru_cluster(int ctas_per_cluster);
+void cto_debug_gru_gate_warps(int warps_per_quadrant);
 
 /* Strand-count recovery of clairs/predict.py:626-642 from the un-rescaled AFF tensor: int32 [n,4] x2. */
 int cto_strand_counts(const int16_t* x_aff_dev, int64_t n, int32_t* fwd_dev, int32_t* rev_dev, void* stream);
