@@ -229,7 +229,7 @@ void engine_free(Engine& e) {
 }
 
 const char* prof_kind_name(int kind) {
-    static const char* names[PK_COUNT] = {"aff_forward", "aff_gemm_1x1", "aff_embed_conv", "aff_channel_ln", "aff_dwconv", "aff_attention",
+    static const char* names[PK_COUNT] = {"aff_forward", "aff_stage1_fused", "aff_gemm_1x1", "aff_embed_conv", "aff_channel_ln", "aff_dwconv", "aff_attention",
                                           "aff_heads", "neg_proj1_gemm", "neg_gru1_recurrent", "neg_proj2_gemm",
                                           "neg_gru2_recurrent", "neg_fc1_gemm", "neg_heads"};
     return (kind >= 0 && kind < PK_COUNT) ? names[kind] : "?";
@@ -262,7 +262,7 @@ static int take_event(Engine& e, cudaEvent_t* ev) {
 
 static bool prof_wanted(const Engine& e, int kind) {
     if (!e.profile) return false;
-    const bool fine = kind >= PK_AFF_GEMM && kind <= PK_AFF_HEADS;
+    const bool fine = kind >= PK_AFF_STAGE1 && kind <= PK_AFF_HEADS;
     return e.profile >= 2 ? kind != PK_AFF : !fine;
 }
 
@@ -346,6 +346,11 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         const CvtStage& st = m.st[si];
         const int c = st.c, inner = st.heads * DIM_HEAD;
         const int64_t rows = n * st.wout, rows_kv = n * st.wkv;
+        if (si == 0 && e.use_tc && aff_stage1_fused_supported(st)) {
+            TIMED(PK_AFF_STAGE1, launch_aff_stage1(st, cur, e.a_xs, n, s));
+            cur = e.a_xs;
+            continue;
+        }
         // embed conv (3-tap, stride 2, pad 1) + channel LN  (clairs/model.py:195-196)
         TIMED(PK_AFF_EMBED, gemm(e, conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows,
                                  c, 3 * st.cin, ACT_NONE, s));

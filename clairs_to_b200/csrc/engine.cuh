@@ -89,13 +89,17 @@ struct Engine {
     std::vector<cudaEvent_t> ev_free;
 };
 
-enum ProfKind { PK_AFF = 0, PK_AFF_GEMM, PK_AFF_EMBED, PK_AFF_LN, PK_AFF_DWCONV, PK_AFF_ATTENTION, PK_AFF_HEADS, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
+enum ProfKind { PK_AFF = 0, PK_AFF_STAGE1, PK_AFF_GEMM, PK_AFF_EMBED, PK_AFF_LN, PK_AFF_DWCONV, PK_AFF_ATTENTION, PK_AFF_HEADS, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
 const char* prof_kind_name(int kind);
 double prof_kind_flops_per_candidate(const Engine& e, int kind);
 int prof_begin(Engine& e, int kind, cudaStream_t s);
 int prof_end(Engine& e, cudaStream_t s);
 // synchronises, sums elapsed ms and launch counts per kind, clears the records
 int prof_collect(Engine& e, double* ms, int64_t* count);
+
+// whole first CvT stage in one kernel (aff_stage1.cu) when the stage has the predict.py shape (C=16, 1 head, depth 1)
+bool aff_stage1_fused_supported(const CvtStage& st);
+int launch_aff_stage1(const CvtStage& st, const float* x, float* out, int64_t n, cudaStream_t s);
 
 int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg, int cfg_len);
 int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg, int cfg_len);
