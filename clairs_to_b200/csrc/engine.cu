@@ -63,7 +63,7 @@ int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
         st.c = cfg[2 + 3 * s];
         st.heads = cfg[3 + 3 * s];
         st.depth = cfg[4 + 3 * s];
-        CTO_REQUIRE(st.depth <= MAX_DEPTH && st.c <= 128 && st.c % 4 == 0, "aff cfg: stage %d C=%d depth=%d unsupported",
+        CTO_REQUIRE(st.depth <= MAX_DEPTH && (st.c == 16 || st.c == 32 || st.c == 64 || st.c == 128), "aff cfg: stage %d C=%d depth=%d unsupported (C must be 16, 32, 64 or 128)",
                     s, st.c, st.depth);
         st.cin = cin;
         st.win = win;
@@ -186,6 +186,16 @@ int engine_alloc(Engine& e, int64_t max_batch) {
     rc |= dev_alloc(e, &e.a_kv, b * a.sz_kv);
     rc |= dev_alloc(e, &e.a_att, b * a.sz_q);
     rc |= dev_alloc(e, &e.a_ff, b * a.sz_ff);
+    {
+        const int64_t sizes[5] = {b * a.sz_x, b * a.sz_kvin, b * a.sz_q, b * a.sz_x, b * a.sz_ff};
+        uint16_t** ptrs[5] = {e.p_dq, e.p_dkv, e.p_att, e.p_y, e.p_ff};
+        for (int i = 0; i < 5 && !rc; ++i)
+            for (int h = 0; h < 2 && !rc; ++h) {
+                float* p = nullptr;
+                rc |= dev_alloc(e, &p, (sizes[i] + 1) / 2);
+                ptrs[i][h] = reinterpret_cast<uint16_t*>(p);
+            }
+    }
     e.bp_max = (b + 127) / 128 * 128;
     const int64_t xp = (int64_t)N_POS * 6 * std::max(g.l[0].hidden, g.l[1].hidden);
     rc |= dev_alloc(e, &e.n_xp, e.bp_max * xp);
@@ -355,7 +365,41 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
         TIMED(PK_AFF_EMBED, gemm(e, conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows,
                                  c, 3 * st.cin, ACT_NONE, s));
         TIMED(PK_AFF_LN, launch_channel_ln(e.a_t0, st.ln_g, st.ln_b, e.a_xs, rows, c, s));
-        for (int d = 0; d < st.depth; ++d) {
+        // every GEMM of a stage whose width is a multiple of 64 runs on the tensor cores, so the tensors between the
+        // kernels that only feed a GEMM travel as bf16 hi / mid planes (no converter pass in the GEMM)
+        const bool planes = e.use_tc && c % 64 == 0;
+        for (int d = 0; d < st.depth && planes; ++d) {
+            const CvtLayer& L = st.layers[d];
+            const WeightSet& ws = m.ws;
+            auto pg = [&](uint16_t* const* ap, int k, const float* w, const float* bias, int nn, int64_t mm) {
+                GemmTc g;
+                g.flags = GEMM_A_PRESPLIT;
+                g.a_hi = ap[0]; g.a_mid = ap[1]; g.lda = k;
+                g.w_hi = ws.bhi + (w - ws.blob); g.w_mid = ws.bmid + (w - ws.blob); g.ldw = k;
+                g.bias = bias; g.m = mm; g.n = nn; g.k = k;
+                return g;
+            };
+            TIMED(PK_AFF_DWCONV, launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, nullptr, nullptr, n, st.wout, st.wkv, c,
+                                                  s, e.p_dq[0], e.p_dq[1], e.p_dkv[0], e.p_dkv[1]));
+            GemmTc g = pg(e.p_dq, c, L.q_pw, L.q_bias, inner, rows);
+            g.c = e.a_q; g.ldc = inner;
+            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+            g = pg(e.p_dkv, c, L.kv_pw, L.kv_bias, 2 * inner, rows_kv);
+            g.c = e.a_kv; g.ldc = 2 * inner;
+            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+            TIMED(PK_AFF_ATTENTION, launch_attention(e.a_q, e.a_kv, nullptr, n, st.wout, st.wkv, st.heads, s, e.p_att[0], e.p_att[1]));
+            g = pg(e.p_att, inner, L.out_w, L.out_b, c, rows);
+            g.c = e.a_xs; g.ldc = c; g.residual = e.a_xs; g.ldr = c;
+            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+            TIMED(PK_AFF_LN, launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, nullptr, rows, c, s, e.p_y[0], e.p_y[1]));
+            g = pg(e.p_y, c, L.ff1_w, L.ff1_b, 4 * c, rows);
+            g.flags |= GEMM_OUT_SPLIT; g.c_hi = e.p_ff[0]; g.c_mid = e.p_ff[1]; g.ldc = 4 * c; g.act = ACT_GELU;
+            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+            g = pg(e.p_ff, 4 * c, L.ff2_w, L.ff2_b, c, rows);
+            g.c = e.a_xs; g.ldc = c; g.residual = e.a_xs; g.ldr = c;
+            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+        }
+        for (int d = 0; d < st.depth && !planes; ++d) {
             const CvtLayer& L = st.layers[d];
             // x = Attention(LN(x)) + x   (clairs/model.py:145); LN and both depth-wise convs are one kernel
             TIMED(PK_AFF_DWCONV, launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, e.a_dq, e.a_dkv, n, st.wout,

@@ -69,6 +69,9 @@ struct Engine {
     float *x_aff = nullptr, *x_neg = nullptr;                  // rescaled inputs: AFF [chunk,33,34], NEG [chunk,33,NEG_IN_LD]
     float *a_t0 = nullptr, *a_xs = nullptr, *a_y = nullptr, *a_dq = nullptr, *a_dkv = nullptr;
     float *a_q = nullptr, *a_kv = nullptr, *a_att = nullptr, *a_ff = nullptr;
+    // tensor-core AFF path: bf16 hi / mid planes of every tensor that only feeds a GEMM (index 0 = hi, 1 = mid)
+    uint16_t *p_dq[2] = {nullptr, nullptr}, *p_dkv[2] = {nullptr, nullptr}, *p_att[2] = {nullptr, nullptr},
+             *p_y[2] = {nullptr, nullptr}, *p_ff[2] = {nullptr, nullptr};
     float *n_xp = nullptr, *n_o1 = nullptr, *n_o2 = nullptr;
     // tensor-core NEG path: bf16 hi / mid planes. x and o1 are time-major [33, bp, .] (operands of the transposed
     // input projections), o2 is batch-major [n, 33 * 2H] (A operand of the flattening fc1); bp = chunk rounded up to 128

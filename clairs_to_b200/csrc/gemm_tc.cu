@@ -139,11 +139,13 @@ template <int ACT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_amid,
                    const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__ CUtensorMap tma_wmid,
-                   const __grid_constant__ CUtensorMap tma_c, const float* __restrict__ bias, const float* residual,
+                   const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_cmid,
+                   const float* __restrict__ bias, const float* residual,
                    int64_t ldr, int64_t m_total, int n_total, int k_total, int bn, int flags, int dbg, long long* timing) {
     const bool presplit = flags & GEMM_A_PRESPLIT;       // A arrives as bf16 hi / mid planes: no converter pass
     const bool bias_row = flags & GEMM_BIAS_PER_ROW;     // bias indexed by the output row (transposed products)
     const bool n_major = flags & GEMM_TILES_N_MAJOR;     // consecutive CTAs share the W tile instead of the A tile
+    const bool out_split = flags & GEMM_OUT_SPLIT;       // C leaves as bf16 hi / mid planes (tma_c / tma_cmid)
     extern __shared__ uint8_t smem_raw[];
     const bool tim = dbg && blockIdx.x == 0 && timing != nullptr;    // per-phase cycle counters (profiles/)
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -371,15 +373,31 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 // this warp's previous TMA store must have finished reading its 32-row staging strip
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
-                #pragma unroll
-                for (int q = 0; q < 8; ++q)   // 128-byte swizzle: 16-byte chunk q of row r lives at chunk (q ^ (r % 8))
-                    *reinterpret_cast<float4*>(stg + r_in_tile * 128 + ((q ^ (r_in_tile & 7)) << 4)) = o[q];
+                uint8_t* wstg = stg + quad * (32 * 128);       // this warp's 4 KB strip of the staging buffer
+                if (out_split) {
+                    // two un-swizzled 32 x 32 bf16 boxes (64-byte rows): hi plane, then mid plane
+                    #pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 hi, mid;
+                        split2_bf16(o[2 * q].x, o[2 * q].y, hi.x, mid.x);
+                        split2_bf16(o[2 * q].z, o[2 * q].w, hi.y, mid.y);
+                        split2_bf16(o[2 * q + 1].x, o[2 * q + 1].y, hi.z, mid.z);
+                        split2_bf16(o[2 * q + 1].z, o[2 * q + 1].w, hi.w, mid.w);
+                        *reinterpret_cast<uint4*>(wstg + lane * 64 + q * 16) = hi;
+                        *reinterpret_cast<uint4*>(wstg + 2048 + lane * 64 + q * 16) = mid;
+                    }
+                } else {
+                    #pragma unroll
+                    for (int q = 0; q < 8; ++q)   // 128-byte swizzle: 16-byte chunk q of row r lives at chunk (q ^ (r % 8))
+                        *reinterpret_cast<float4*>(stg + r_in_tile * 128 + ((q ^ (r_in_tile & 7)) << 4)) = o[q];
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 TOC(4);
                 __syncwarp();
                 TOC(5);
                 if (lane == 0) {                               // one 32 x 32 box per warp: no cross-warp barrier in the epilogue
-                    tma_store_2d(&tma_c, stg + quad * (32 * 128), n0 + cb, m0 + quad * 32);
+                    tma_store_2d(&tma_c, wstg, n0 + cb, m0 + quad * 32);
+                    if (out_split) tma_store_2d(&tma_cmid, wstg + 2048, n0 + cb, m0 + quad * 32);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -407,10 +425,10 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, uint16_t* __restr
 
 // 2-D tiled tensor map with 128-byte swizzle; the box is (128 bytes of the inner dimension) x box_rows
 static int make_map_any(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* ptr, int64_t rows, int64_t cols,
-                        int64_t ld, int box_rows) {
+                        int64_t ld, int box_rows, int box_cols = 0, bool swizzle = true) {
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(box_cols ? box_cols : 128 / elem_bytes), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     // resolved through the runtime so that the library has no link-time dependency on libcuda
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -425,7 +443,8 @@ static int make_map_any(CUtensorMap* map, CUtensorMapDataType dtype, int elem_by
         encode = reinterpret_cast<encode_fn>(fn);
     }
     CUresult r = encode(map, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
                   (long long)cols, (long long)ld);
@@ -465,13 +484,16 @@ bool gemm_tc_supported(const float* a, int64_t lda, const void* w, int64_t m, in
 }
 
 int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s) {
-    const bool presplit = g.flags & GEMM_A_PRESPLIT;
+    const bool presplit = g.flags & GEMM_A_PRESPLIT, out_split = g.flags & GEMM_OUT_SPLIT;
+    const void* c_any = out_split ? (const void*)g.c_hi : (const void*)g.c;
     const void* a_any = presplit ? (const void*)g.a_hi : (const void*)g.a;
     const int64_t a_align = presplit ? 8 : 4;            // elements per 16 bytes
     const uintptr_t bits = reinterpret_cast<uintptr_t>(a_any) | reinterpret_cast<uintptr_t>(g.a_mid) |
                            reinterpret_cast<uintptr_t>(g.w_hi) | reinterpret_cast<uintptr_t>(g.w_mid) |
-                           reinterpret_cast<uintptr_t>(g.c) | reinterpret_cast<uintptr_t>(g.residual);
-    CTO_REQUIRE(a_any && g.w_hi && g.w_mid && g.c && (!presplit || g.a_mid) && (bits & 15) == 0 && g.m > 0 &&
+                           reinterpret_cast<uintptr_t>(c_any) | reinterpret_cast<uintptr_t>(g.c_mid) |
+                           reinterpret_cast<uintptr_t>(g.residual);
+    CTO_REQUIRE(a_any && g.w_hi && g.w_mid && c_any && (!presplit || g.a_mid) && (!out_split || (g.c_mid && g.ldc % 8 == 0)) &&
+                    (bits & 15) == 0 && g.m > 0 &&
                     g.m < (1ll << 31) - tc::BM && g.n >= 64 && g.n % 64 == 0 && g.k >= 8 && g.k % 8 == 0 &&
                     g.lda % a_align == 0 && g.ldw % 8 == 0 && g.ldc % 4 == 0 && (!g.residual || g.ldr % 4 == 0),
                 "gemm_tc: unsupported shape/alignment m=%lld n=%d k=%d lda=%lld ldw=%lld ldc=%lld flags=%d", (long long)g.m,
@@ -487,7 +509,7 @@ int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s) {
     }
     // 128-wide tiles unless that leaves SMs without a tile (long-K, few-row GEMMs such as the NEG fc1)
     const int bn = (g.n % 128 == 0 && (int64_t)ceil_div(g.m, tc::BM) * (g.n / 128) >= sm_count) ? 128 : 64;
-    CUtensorMap map_a, map_amid, map_whi, map_wmid, map_c;
+    CUtensorMap map_a, map_amid, map_whi, map_wmid, map_c, map_cmid;
     if (presplit) {
         if (tc::make_map_bf16(&map_a, g.a_hi, g.m, g.k, g.lda, tc::BM)) return 1;
         if (tc::make_map_bf16(&map_amid, g.a_mid, g.m, g.k, g.lda, tc::BM)) return 1;
@@ -497,11 +519,18 @@ int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s) {
     }
     if (tc::make_map_bf16(&map_whi, g.w_hi, g.n, g.k, g.ldw, bn)) return 1;
     if (tc::make_map_bf16(&map_wmid, g.w_mid, g.n, g.k, g.ldw, bn)) return 1;
-    if (tc::make_map(&map_c, g.c, g.m, g.n, g.ldc, 32)) return 1;          // every epilogue warp stores its own 32-row strip
+    // every epilogue warp stores its own 32-row strip: one swizzled 32 x 32 fp32 box, or two plain 32 x 32 bf16 boxes
+    if (out_split) {
+        if (tc::make_map_any(&map_c, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.c_hi, g.m, g.n, g.ldc, 32, 32, false)) return 1;
+        if (tc::make_map_any(&map_cmid, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.c_mid, g.m, g.n, g.ldc, 32, 32, false)) return 1;
+    } else {
+        if (tc::make_map(&map_c, g.c, g.m, g.n, g.ldc, 32)) return 1;
+        map_cmid = map_c;
+    }
     const int64_t tiles = (int64_t)ceil_div(g.m, tc::BM) * (g.n / bn);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
 #define CTO_LAUNCH_GEMM(A)                                                                                             \
-    tc::gemm_bf16x3_kernel<A><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_amid, map_whi, map_wmid, map_c, g.bias, \
+    tc::gemm_bf16x3_kernel<A><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_amid, map_whi, map_wmid, map_c, map_cmid, g.bias, \
                                                                        g.residual, g.ldr, g.m, g.n, g.k, bn, g.flags,   \
                                                                        g_gemm_debug, g_gemm_timing)
     if (g.act == ACT_GELU) CTO_LAUNCH_GEMM(ACT_GELU);

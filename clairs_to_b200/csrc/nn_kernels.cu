@@ -253,44 +253,81 @@ int launch_gemm_nt(const AView& a, const float* w, const float* bias, const floa
 // ------------------------------------------------------------------------------------------
 // channel LayerNorm (M:57-67): population std, eps added to the std; one warp per (b, w) row
 // ------------------------------------------------------------------------------------------
-__global__ void channel_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
-                                  const float* __restrict__ b, float* __restrict__ y, int64_t rows, int c) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const float* xr = x + row * c;
-    float v[4];
-    float sum = 0.0f;
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ch = lane + 32 * i;
-        v[i] = ch < c ? xr[ch] : 0.0f;
-        sum += v[i];
-    }
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / (float)c;
-    float sq = 0.0f;
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ch = lane + 32 * i;
-        const float d = ch < c ? v[i] - mean : 0.0f;
-        sq += d * d;
-    }
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float denom = sqrtf(sq / (float)c) + 1e-5f;
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ch = lane + 32 * i;
-        if (ch < c) y[row * c + ch] = (v[i] - mean) / denom * g[ch] + b[ch];
+// Split-plane outputs: a tensor that is only read as the A operand of a bf16x3 GEMM is written as two bf16
+// planes (hi = bf16(v), mid = bf16(v - hi)) instead of fp32 -- same bytes, and the GEMM needs no converter pass.
+// Lanes hold consecutive elements; even lanes store their value and their neighbour's as one packed word.
+__device__ __forceinline__ void store_split_pair(uint16_t* __restrict__ hi, uint16_t* __restrict__ mid, int64_t idx, float v, int lane) {
+    const float v1 = __shfl_down_sync(0xffffffffu, v, 1);
+    if (!(lane & 1)) {
+        uint32_t h, m;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v));
+        const float r0 = v - __uint_as_float(h << 16), r1 = v1 - __uint_as_float(h & 0xFFFF0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(r1), "f"(r0));
+        *reinterpret_cast<uint32_t*>(hi + idx) = h;
+        *reinterpret_cast<uint32_t*>(mid + idx) = m;
     }
 }
 
-int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s) {
+// Each lane owns four consecutive channels (one float4), C/4 lanes form a row group, 128/C rows per warp; the
+// scalar version of this kernel was instruction-bound (ncu: 85 % issue utilisation at 20 % of the HBM rate).
+template <bool SPLIT, int LPR>                          // LPR = lanes per row = C / 4
+__global__ void channel_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                  const float* __restrict__ b, float* __restrict__ y, uint16_t* __restrict__ y_hi,
+                                  uint16_t* __restrict__ y_mid, int64_t rows) {
+    constexpr int C = 4 * LPR, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+    const int ch = (lane % LPR) * 4;
+    const bool ok = row < rows;
+    const float4 v = ok ? *reinterpret_cast<const float4*>(x + row * C + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float sum = (v.x + v.y) + (v.z + v.w);
+    #pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    float sq = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    #pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float denom = sqrtf(sq / (float)C) + 1e-5f;
+    if (!ok) return;
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g + ch)), bv = __ldg(reinterpret_cast<const float4*>(b + ch));
+    const float o0 = d0 / denom * gv.x + bv.x, o1 = d1 / denom * gv.y + bv.y, o2 = d2 / denom * gv.z + bv.z,
+                o3 = d3 / denom * gv.w + bv.w;
+    if (SPLIT) {
+        uint32_t h0, h1, m0, m1;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(o1), "f"(o0));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(o3), "f"(o2));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m0) : "f"(o1 - __uint_as_float(h0 & 0xFFFF0000u)), "f"(o0 - __uint_as_float(h0 << 16)));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m1) : "f"(o3 - __uint_as_float(h1 & 0xFFFF0000u)), "f"(o2 - __uint_as_float(h1 << 16)));
+        *reinterpret_cast<uint2*>(y_hi + row * C + ch) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(y_mid + row * C + ch) = make_uint2(m0, m1);
+    } else {
+        *reinterpret_cast<float4*>(y + row * C + ch) = make_float4(o0, o1, o2, o3);
+    }
+}
+
+template <bool SPLIT>
+static int launch_channel_ln_t(const float* x, const float* g, const float* b, float* y, uint16_t* y_hi, uint16_t* y_mid,
+                               int64_t rows, int c, cudaStream_t s) {
+    const int rpw = 128 / c;                            // rows per warp
+    const int grid = ceil_div(rows, 8 * rpw);
+    switch (c) {
+        case 16: channel_ln_kernel<SPLIT, 4><<<grid, 256, 0, s>>>(x, g, b, y, y_hi, y_mid, rows); break;
+        case 32: channel_ln_kernel<SPLIT, 8><<<grid, 256, 0, s>>>(x, g, b, y, y_hi, y_mid, rows); break;
+        case 64: channel_ln_kernel<SPLIT, 16><<<grid, 256, 0, s>>>(x, g, b, y, y_hi, y_mid, rows); break;
+        case 128: channel_ln_kernel<SPLIT, 32><<<grid, 256, 0, s>>>(x, g, b, y, y_hi, y_mid, rows); break;
+        default: CTO_REQUIRE(false, "channel_ln: C=%d not built (16, 32, 64, 128 are)", c);
+    }
+    return 0;
+}
+
+int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s,
+                      uint16_t* y_hi, uint16_t* y_mid) {
     if (rows <= 0) return 0;
-    CTO_REQUIRE(c <= 128, "channel_ln: C=%d > 128 unsupported", c);
-    channel_ln_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, g, b, y, rows, c);
+    CTO_REQUIRE(y_hi ? y_mid != nullptr : y != nullptr, "channel_ln: no output buffer");
+    if (int rc = y_hi ? launch_channel_ln_t<true>(x, g, b, nullptr, y_hi, y_mid, rows, c, s)
+                      : launch_channel_ln_t<false>(x, g, b, y, nullptr, nullptr, rows, c, s))
+        return rc;
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;
@@ -335,14 +372,18 @@ int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch,
 // ------------------------------------------------------------------------------------------
 constexpr int LND_WARPS = 4, LND_MAXW = 17, LND_MAXC = 128;
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(LND_WARPS * 32)
 ln_dwconv_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                  const float* __restrict__ taps_q, const float* __restrict__ taps_kv, float* __restrict__ dq,
-                 float* __restrict__ dkv, int64_t batch, int w, int wkv, int c) {
-    __shared__ float sy[LND_WARPS][LND_MAXW][LND_MAXC];
+                 float* __restrict__ dkv, uint16_t* __restrict__ dq_hi, uint16_t* __restrict__ dq_mid,
+                 uint16_t* __restrict__ dkv_hi, uint16_t* __restrict__ dkv_mid, int64_t batch, int w, int wkv, int c) {
+    extern __shared__ float lnd_smem[];                  // [LND_WARPS][w][c]: sized for the actual stage, not the maxima
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t cand = (int64_t)blockIdx.x * LND_WARPS + wib;
     if (cand >= batch) return;
+    float* sy = lnd_smem + wib * w * c;
+    #define SY(r, ch) sy[(r) * c + (ch)]
     const float* xc = x + cand * w * c;
     for (int r = 0; r < w; ++r) {
         float v[4], sum = 0.0f;
@@ -367,7 +408,7 @@ ln_dwconv_kernel(const float* __restrict__ x, const float* __restrict__ g, const
         #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ch = lane + 32 * i;
-            if (ch < c) sy[wib][r][ch] = (v[i] - mean) / denom * g[ch] + b[ch];
+            if (ch < c) SY(r, ch) = (v[i] - mean) / denom * g[ch] + b[ch];
         }
     }
     __syncwarp();
@@ -378,27 +419,37 @@ ln_dwconv_kernel(const float* __restrict__ x, const float* __restrict__ g, const
         const float k0 = taps_kv[ch], k1 = taps_kv[c + ch], k2 = taps_kv[2 * c + ch];
         for (int r = 0; r < w; ++r) {
             float acc = 0.0f;                                   // same tap order as dwconv3_kernel
-            if (r - 1 >= 0) acc = fmaf(sy[wib][r - 1][ch], q0, acc);
-            acc = fmaf(sy[wib][r][ch], q1, acc);
-            if (r + 1 < w) acc = fmaf(sy[wib][r + 1][ch], q2, acc);
-            dq[(cand * w + r) * c + ch] = acc;
+            if (r - 1 >= 0) acc = fmaf(SY(r - 1, ch), q0, acc);
+            acc = fmaf(SY(r, ch), q1, acc);
+            if (r + 1 < w) acc = fmaf(SY(r + 1, ch), q2, acc);
+            if (SPLIT) store_split_pair(dq_hi, dq_mid, (cand * w + r) * c + ch, acc, lane);
+            else dq[(cand * w + r) * c + ch] = acc;
         }
         for (int r = 0; r < wkv; ++r) {
             const int s0 = 2 * r - 1;
             float acc = 0.0f;
-            if (s0 >= 0) acc = fmaf(sy[wib][s0][ch], k0, acc);
-            acc = fmaf(sy[wib][s0 + 1][ch], k1, acc);
-            if (s0 + 2 < w) acc = fmaf(sy[wib][s0 + 2][ch], k2, acc);
-            dkv[(cand * wkv + r) * c + ch] = acc;
+            if (s0 >= 0) acc = fmaf(SY(s0, ch), k0, acc);
+            acc = fmaf(SY(s0 + 1, ch), k1, acc);
+            if (s0 + 2 < w) acc = fmaf(SY(s0 + 2, ch), k2, acc);
+            if (SPLIT) store_split_pair(dkv_hi, dkv_mid, (cand * wkv + r) * c + ch, acc, lane);
+            else dkv[(cand * wkv + r) * c + ch] = acc;
         }
     }
+    #undef SY
 }
 
 int launch_ln_dwconv(const float* x, const float* g, const float* b, const float* taps_q, const float* taps_kv, float* dq,
-                     float* dkv, int64_t batch, int w, int wkv, int c, cudaStream_t s) {
+                     float* dkv, int64_t batch, int w, int wkv, int c, cudaStream_t s, uint16_t* dq_hi, uint16_t* dq_mid,
+                     uint16_t* dkv_hi, uint16_t* dkv_mid) {
     if (batch <= 0) return 0;
     CTO_REQUIRE(w <= LND_MAXW && c <= LND_MAXC, "ln_dwconv: W=%d C=%d exceed %d/%d", w, c, LND_MAXW, LND_MAXC);
-    ln_dwconv_kernel<<<ceil_div(batch, LND_WARPS), LND_WARPS * 32, 0, s>>>(x, g, b, taps_q, taps_kv, dq, dkv, batch, w, wkv, c);
+    if (dq_hi) {
+        CTO_REQUIRE(dq_mid && dkv_hi && dkv_mid && c % 32 == 0, "ln_dwconv: split output needs C %% 32 == 0 (C=%d)", c);
+        ln_dwconv_kernel<true><<<ceil_div(batch, LND_WARPS), LND_WARPS * 32, sizeof(float) * LND_WARPS * w * c, s>>>(x, g, b, taps_q, taps_kv, nullptr, nullptr, dq_hi,
+                                                                                  dq_mid, dkv_hi, dkv_mid, batch, w, wkv, c);
+    } else
+    ln_dwconv_kernel<false><<<ceil_div(batch, LND_WARPS), LND_WARPS * 32, sizeof(float) * LND_WARPS * w * c, s>>>(x, g, b, taps_q, taps_kv, dq, dkv, nullptr, nullptr,
+                                                                               nullptr, nullptr, batch, w, wkv, c);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;
@@ -410,15 +461,21 @@ int launch_ln_dwconv(const float* x, const float* g, const float* b, const float
 // ------------------------------------------------------------------------------------------
 constexpr int ATT_MAXW = 17, ATT_MAXKV = 9, ATT_D = 64, ATT_WARPS = 4;
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, int64_t n_bh, int w,
-                 int wkv, int heads) {
-    // rows padded to 68 floats: 16-byte aligned for float4 reads, and 8 consecutive rows start 4 banks apart
-    __shared__ __align__(16) float sq[ATT_WARPS][ATT_MAXW][ATT_D + 4];
-    __shared__ __align__(16) float sk[ATT_WARPS][ATT_MAXKV][ATT_D + 4];
-    __shared__ __align__(16) float sv[ATT_WARPS][ATT_MAXKV][ATT_D + 4];
-    __shared__ float sp[ATT_WARPS][ATT_MAXW][ATT_MAXKV + 1];
+attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, uint16_t* __restrict__ out_hi,
+                 uint16_t* __restrict__ out_mid, int64_t n_bh, int w, int wkv, int heads) {
+    // rows padded to 68 floats: 16-byte aligned for float4 reads, and 8 consecutive rows start 4 banks apart.
+    // Dynamic shared memory sized for the actual (w, wkv) of the stage: twice the occupancy of arrays sized for 17 / 9.
+    extern __shared__ __align__(16) float att_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int LD = ATT_D + 4;
+    const int per_warp = (w + 2 * wkv) * LD + ((w * (wkv + 1) + 3) & ~3);
+    float* sq = att_smem + wib * per_warp;               // [w][68]
+    float* sk = sq + w * LD;                             // [wkv][68]
+    float* sv = sk + wkv * LD;                           // [wkv][68]
+    float* sp = sv + wkv * LD;                           // [w][wkv + 1]
+    const int ldp = wkv + 1;
     const int64_t bh = (int64_t)blockIdx.x * ATT_WARPS + wib;
     if (bh >= n_bh) return;
     const int64_t b = bh / heads;
@@ -426,21 +483,21 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
     const int inner = heads * ATT_D;
     for (int i = 0; i < w; ++i) {
         const float* src = q + (b * w + i) * inner + h * ATT_D;
-        sq[wib][i][lane] = src[lane];
-        sq[wib][i][lane + 32] = src[lane + 32];
+        sq[i * LD + lane] = src[lane];
+        sq[i * LD + lane + 32] = src[lane + 32];
     }
     for (int j = 0; j < wkv; ++j) {
         const float* src = kv + (b * wkv + j) * (2 * inner) + h * ATT_D;
-        sk[wib][j][lane] = src[lane];
-        sk[wib][j][lane + 32] = src[lane + 32];
-        sv[wib][j][lane] = src[inner + lane];
-        sv[wib][j][lane + 32] = src[inner + lane + 32];
+        sk[j * LD + lane] = src[lane];
+        sk[j * LD + lane + 32] = src[lane + 32];
+        sv[j * LD + lane] = src[inner + lane];
+        sv[j * LD + lane + 32] = src[inner + lane + 32];
     }
     __syncwarp();
     for (int p = lane; p < w * wkv; p += 32) {
         const int i = p / wkv, j = p - i * wkv;
-        const float4* qr = reinterpret_cast<const float4*>(sq[wib][i]);
-        const float4* kr = reinterpret_cast<const float4*>(sk[wib][j]);
+        const float4* qr = reinterpret_cast<const float4*>(sq + i * LD);
+        const float4* kr = reinterpret_cast<const float4*>(sk + j * LD);
         float acc = 0.0f;
         #pragma unroll
         for (int d = 0; d < ATT_D / 4; ++d) {              // same summation order as the scalar loop
@@ -450,41 +507,48 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
             acc = fmaf(a.z, b.z, acc);
             acc = fmaf(a.w, b.w, acc);
         }
-        sp[wib][i][j] = acc;
+        sp[i * ldp + j] = acc;
     }
     __syncwarp();
     if (lane < w) {
         float mx = -FLT_MAX;
-        for (int j = 0; j < wkv; ++j) mx = fmaxf(mx, sp[wib][lane][j]);
+        for (int j = 0; j < wkv; ++j) mx = fmaxf(mx, sp[lane * ldp + j]);
         float sum = 0.0f;
         for (int j = 0; j < wkv; ++j) {
-            const float e = expf(sp[wib][lane][j] - mx);
-            sp[wib][lane][j] = e;
+            const float e = expf(sp[lane * ldp + j] - mx);
+            sp[lane * ldp + j] = e;
             sum += e;
         }
         const float inv = 1.0f / sum;
-        for (int j = 0; j < wkv; ++j) sp[wib][lane][j] *= inv;
+        for (int j = 0; j < wkv; ++j) sp[lane * ldp + j] *= inv;
     }
     __syncwarp();
     for (int i = 0; i < w; ++i) {
         float o0 = 0.0f, o1 = 0.0f;
         for (int j = 0; j < wkv; ++j) {
-            const float pij = sp[wib][i][j];
-            o0 = fmaf(pij, sv[wib][j][lane], o0);
-            o1 = fmaf(pij, sv[wib][j][lane + 32], o1);
+            const float pij = sp[i * ldp + j];
+            o0 = fmaf(pij, sv[j * LD + lane], o0);
+            o1 = fmaf(pij, sv[j * LD + lane + 32], o1);
         }
-        float* dst = out + (b * w + i) * inner + h * ATT_D;
-        dst[lane] = o0;
-        dst[lane + 32] = o1;
+        const int64_t o = (b * w + i) * inner + h * ATT_D;
+        if (SPLIT) {
+            store_split_pair(out_hi, out_mid, o + lane, o0, lane);
+            store_split_pair(out_hi, out_mid, o + lane + 32, o1, lane);
+        } else {
+            out[o + lane] = o0;
+            out[o + lane + 32] = o1;
+        }
     }
 }
 
 int launch_attention(const float* q, const float* kv, float* out, int64_t batch, int w, int wkv, int heads,
-                     cudaStream_t s) {
+                     cudaStream_t s, uint16_t* out_hi, uint16_t* out_mid) {
     const int64_t n_bh = batch * heads;
     if (n_bh <= 0) return 0;
     CTO_REQUIRE(w <= ATT_MAXW && wkv <= ATT_MAXKV, "attention: W=%d Wkv=%d exceed %d/%d", w, wkv, ATT_MAXW, ATT_MAXKV);
-    attention_kernel<<<ceil_div(n_bh, ATT_WARPS), ATT_WARPS * 32, 0, s>>>(q, kv, out, n_bh, w, wkv, heads);
+    const size_t smem = sizeof(float) * ATT_WARPS * ((w + 2 * wkv) * (ATT_D + 4) + ((w * (wkv + 1) + 3) & ~3));
+    if (out_hi) attention_kernel<true><<<ceil_div(n_bh, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(q, kv, nullptr, out_hi, out_mid, n_bh, w, wkv, heads);
+    else attention_kernel<false><<<ceil_div(n_bh, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(q, kv, out, nullptr, nullptr, n_bh, w, wkv, heads);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

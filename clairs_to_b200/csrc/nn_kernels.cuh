@@ -33,7 +33,7 @@ int launch_gemm_tc(const float* a, int64_t lda, const uint16_t* w_hi, const uint
 int launch_split_bf16(const float* w, uint16_t* hi, uint16_t* mid, int64_t n, cudaStream_t s);
 // the general form: A either fp32 (split by the kernel's converter warps) or already split into bf16 hi / mid
 // planes; W always pre-split, row stride ldw
-enum GemmFlags { GEMM_A_PRESPLIT = 1, GEMM_BIAS_PER_ROW = 2, GEMM_TILES_N_MAJOR = 4 };
+enum GemmFlags { GEMM_A_PRESPLIT = 1, GEMM_BIAS_PER_ROW = 2, GEMM_TILES_N_MAJOR = 4, GEMM_OUT_SPLIT = 8 };
 struct GemmTc {
     const float* a = nullptr;                          // fp32 A [m, k], row stride lda        (flags & A_PRESPLIT == 0)
     const uint16_t *a_hi = nullptr, *a_mid = nullptr;  // bf16 planes of A [m, k], row stride lda (flags & A_PRESPLIT)
@@ -43,7 +43,8 @@ struct GemmTc {
     const float* bias = nullptr;                       // [n], or [m] with GEMM_BIAS_PER_ROW
     const float* residual = nullptr;
     int64_t ldr = 0;
-    float* c = nullptr;
+    float* c = nullptr;                                // fp32 C [m, n], row stride ldc          (flags & OUT_SPLIT == 0)
+    uint16_t *c_hi = nullptr, *c_mid = nullptr;        // bf16 planes of C, row stride ldc       (flags & OUT_SPLIT)
     int64_t ldc = 0, m = 0;
     int n = 0, k = 0, act = ACT_NONE, flags = 0;
 };
@@ -52,13 +53,17 @@ int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s);
 // ld_out >= 34: row stride of the fp32 output (extra columns are zero-filled)
 int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, int ld_out, cudaStream_t s);
 int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_out, cudaStream_t s);
-int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s);
+// y_hi / y_mid, dq_hi .., out_hi ..: when given, the result is written as bf16 hi / mid planes (the pre-split A
+// operand of the next GEMM) instead of fp32
+int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s,
+                      uint16_t* y_hi = nullptr, uint16_t* y_mid = nullptr);
 int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch, int win, int wout, int stride,
                    int c, cudaStream_t s);
 int launch_ln_dwconv(const float* x, const float* g, const float* b, const float* taps_q, const float* taps_kv, float* dq,
-                     float* dkv, int64_t batch, int w, int wkv, int c, cudaStream_t s);
+                     float* dkv, int64_t batch, int w, int wkv, int c, cudaStream_t s, uint16_t* dq_hi = nullptr,
+                     uint16_t* dq_mid = nullptr, uint16_t* dkv_hi = nullptr, uint16_t* dkv_mid = nullptr);
 int launch_attention(const float* q, const float* kv, float* out, int64_t batch, int w, int wkv, int heads,
-                     cudaStream_t s);
+                     cudaStream_t s, uint16_t* out_hi = nullptr, uint16_t* out_mid = nullptr);
 int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bhn, float* out, int64_t batch,
                          int hidden, cudaStream_t s);
 // tensor-core recurrence (gru_tc3.cu): CTA pair (tcgen05 cta_group::2) + bf16x3, reads the TRANSPOSED projection xproj[6H][t * bp + b], writes
