@@ -255,18 +255,6 @@ int launch_gemm_nt(const AView& a, const float* w, const float* bias, const floa
 // ------------------------------------------------------------------------------------------
 // Split-plane outputs: a tensor that is only read as the A operand of a bf16x3 GEMM is written as two bf16
 // planes (hi = bf16(v), mid = bf16(v - hi)) instead of fp32 -- same bytes, and the GEMM needs no converter pass.
-// Lanes hold consecutive elements; even lanes store their value and their neighbour's as one packed word.
-__device__ __forceinline__ void store_split_pair(uint16_t* __restrict__ hi, uint16_t* __restrict__ mid, int64_t idx, float v, int lane) {
-    const float v1 = __shfl_down_sync(0xffffffffu, v, 1);
-    if (!(lane & 1)) {
-        uint32_t h, m;
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v));
-        const float r0 = v - __uint_as_float(h << 16), r1 = v1 - __uint_as_float(h & 0xFFFF0000u);
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(r1), "f"(r0));
-        *reinterpret_cast<uint32_t*>(hi + idx) = h;
-        *reinterpret_cast<uint32_t*>(mid + idx) = m;
-    }
-}
 
 // Each lane owns four consecutive channels (one float4), C/4 lanes form a row group, 128/C rows per warp; the
 // scalar version of this kernel was instruction-bound (ncu: 85 % issue utilisation at 20 % of the HBM rate).
@@ -370,86 +358,113 @@ int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch,
 // One warp per candidate; the candidate's <= 17 x 128 activations stay in shared memory, so x is read
 // once and y never touches HBM.
 // ------------------------------------------------------------------------------------------
-constexpr int LND_WARPS = 4, LND_MAXW = 17, LND_MAXC = 128;
+constexpr int LND_WARPS = 4, LND_MAXW = 17;
 
+__device__ __forceinline__ float4 fma4(const float4 a, const float4 b, const float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
 template <bool SPLIT>
+__device__ __forceinline__ void store4(float* __restrict__ o, uint16_t* __restrict__ hi, uint16_t* __restrict__ mid, int64_t idx,
+                                       const float4 v) {
+    if (SPLIT) {
+        uint32_t h0, h1, m0, m1;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v.w), "f"(v.z));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m0) : "f"(v.y - __uint_as_float(h0 & 0xFFFF0000u)), "f"(v.x - __uint_as_float(h0 << 16)));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m1) : "f"(v.w - __uint_as_float(h1 & 0xFFFF0000u)), "f"(v.z - __uint_as_float(h1 << 16)));
+        *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(mid + idx) = make_uint2(m0, m1);
+    } else {
+        *reinterpret_cast<float4*>(o + idx) = v;
+    }
+}
+
+// Each lane owns four consecutive channels; C/4 lanes form a row group and the 32/LPR groups of the warp take
+// alternate rows (the scalar version was instruction-bound).
+template <bool SPLIT, int LPR>
 __global__ void __launch_bounds__(LND_WARPS * 32)
 ln_dwconv_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                  const float* __restrict__ taps_q, const float* __restrict__ taps_kv, float* __restrict__ dq,
                  float* __restrict__ dkv, uint16_t* __restrict__ dq_hi, uint16_t* __restrict__ dq_mid,
-                 uint16_t* __restrict__ dkv_hi, uint16_t* __restrict__ dkv_mid, int64_t batch, int w, int wkv, int c) {
-    extern __shared__ float lnd_smem[];                  // [LND_WARPS][w][c]: sized for the actual stage, not the maxima
+                 uint16_t* __restrict__ dkv_hi, uint16_t* __restrict__ dkv_mid, int64_t batch, int w, int wkv) {
+    constexpr int C = 4 * LPR, RPW = 32 / LPR;
+    extern __shared__ __align__(16) float lnd_smem[];    // [LND_WARPS][w][C]: sized for the actual stage, not the maxima
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t cand = (int64_t)blockIdx.x * LND_WARPS + wib;
     if (cand >= batch) return;
-    float* sy = lnd_smem + wib * w * c;
-    #define SY(r, ch) sy[(r) * c + (ch)]
-    const float* xc = x + cand * w * c;
-    for (int r = 0; r < w; ++r) {
-        float v[4], sum = 0.0f;
+    float* sy = lnd_smem + wib * w * C;
+    const int grp = lane / LPR, ch = (lane % LPR) * 4;
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g + ch)), bv = __ldg(reinterpret_cast<const float4*>(b + ch));
+    for (int r0 = 0; r0 < w; r0 += RPW) {
+        const int r = r0 + grp;
+        const bool ok = r < w;
+        const float4 v = ok ? *reinterpret_cast<const float4*>(x + (cand * w + r) * C + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float sum = (v.x + v.y) + (v.z + v.w);
         #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ch = lane + 32 * i;
-            v[i] = ch < c ? xc[r * c + ch] : 0.0f;
-            sum += v[i];
-        }
+        for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / (float)C;
+        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        float sq = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
         #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum / (float)c;
-        float sq = 0.0f;
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float d = (lane + 32 * i) < c ? v[i] - mean : 0.0f;
-            sq += d * d;
-        }
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const float denom = sqrtf(sq / (float)c) + 1e-5f;
-        #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ch = lane + 32 * i;
-            if (ch < c) SY(r, ch) = (v[i] - mean) / denom * g[ch] + b[ch];
-        }
+        for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float denom = sqrtf(sq / (float)C) + 1e-5f;
+        if (ok)
+            *reinterpret_cast<float4*>(sy + r * C + ch) = make_float4(d0 / denom * gv.x + bv.x, d1 / denom * gv.y + bv.y,
+                                                                      d2 / denom * gv.z + bv.z, d3 / denom * gv.w + bv.w);
     }
     __syncwarp();
-    for (int i = 0; i < 4; ++i) {
-        const int ch = lane + 32 * i;
-        if (ch >= c) break;
-        const float q0 = taps_q[ch], q1 = taps_q[c + ch], q2 = taps_q[2 * c + ch];
-        const float k0 = taps_kv[ch], k1 = taps_kv[c + ch], k2 = taps_kv[2 * c + ch];
-        for (int r = 0; r < w; ++r) {
-            float acc = 0.0f;                                   // same tap order as dwconv3_kernel
-            if (r - 1 >= 0) acc = fmaf(SY(r - 1, ch), q0, acc);
-            acc = fmaf(SY(r, ch), q1, acc);
-            if (r + 1 < w) acc = fmaf(SY(r + 1, ch), q2, acc);
-            if (SPLIT) store_split_pair(dq_hi, dq_mid, (cand * w + r) * c + ch, acc, lane);
-            else dq[(cand * w + r) * c + ch] = acc;
-        }
-        for (int r = 0; r < wkv; ++r) {
-            const int s0 = 2 * r - 1;
-            float acc = 0.0f;
-            if (s0 >= 0) acc = fmaf(SY(s0, ch), k0, acc);
-            acc = fmaf(SY(s0 + 1, ch), k1, acc);
-            if (s0 + 2 < w) acc = fmaf(SY(s0 + 2, ch), k2, acc);
-            if (SPLIT) store_split_pair(dkv_hi, dkv_mid, (cand * wkv + r) * c + ch, acc, lane);
-            else dkv[(cand * wkv + r) * c + ch] = acc;
-        }
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(taps_q + ch)), q1 = __ldg(reinterpret_cast<const float4*>(taps_q + C + ch)),
+                 q2 = __ldg(reinterpret_cast<const float4*>(taps_q + 2 * C + ch));
+    const float4 k0 = __ldg(reinterpret_cast<const float4*>(taps_kv + ch)), k1 = __ldg(reinterpret_cast<const float4*>(taps_kv + C + ch)),
+                 k2 = __ldg(reinterpret_cast<const float4*>(taps_kv + 2 * C + ch));
+    #define SY4(r) (*reinterpret_cast<const float4*>(sy + (r) * C + ch))
+    for (int r = grp; r < w; r += RPW) {                    // stride 1, pad 1; same tap order as dwconv3_kernel
+        float4 acc = zero;
+        if (r - 1 >= 0) acc = fma4(SY4(r - 1), q0, acc);
+        acc = fma4(SY4(r), q1, acc);
+        if (r + 1 < w) acc = fma4(SY4(r + 1), q2, acc);
+        store4<SPLIT>(dq, dq_hi, dq_mid, (cand * w + r) * C + ch, acc);
     }
-    #undef SY
+    for (int r = grp; r < wkv; r += RPW) {                  // stride 2, pad 1
+        const int s0 = 2 * r - 1;
+        float4 acc = zero;
+        if (s0 >= 0) acc = fma4(SY4(s0), k0, acc);
+        acc = fma4(SY4(s0 + 1), k1, acc);
+        if (s0 + 2 < w) acc = fma4(SY4(s0 + 2), k2, acc);
+        store4<SPLIT>(dkv, dkv_hi, dkv_mid, (cand * wkv + r) * C + ch, acc);
+    }
+    #undef SY4
+}
+
+template <bool SPLIT>
+static int launch_ln_dwconv_t(const float* x, const float* g, const float* b, const float* taps_q, const float* taps_kv, float* dq,
+                              float* dkv, uint16_t* dq_hi, uint16_t* dq_mid, uint16_t* dkv_hi, uint16_t* dkv_mid, int64_t batch,
+                              int w, int wkv, int c, cudaStream_t s) {
+    const int grid = ceil_div(batch, LND_WARPS);
+    const size_t smem = sizeof(float) * LND_WARPS * w * c;
+#define CTO_LND(LPR) ln_dwconv_kernel<SPLIT, LPR><<<grid, LND_WARPS * 32, smem, s>>>(x, g, b, taps_q, taps_kv, dq, dkv, dq_hi, dq_mid, \
+                                                                                  dkv_hi, dkv_mid, batch, w, wkv)
+    switch (c) {
+        case 16: CTO_LND(4); break;
+        case 32: CTO_LND(8); break;
+        case 64: CTO_LND(16); break;
+        case 128: CTO_LND(32); break;
+        default: CTO_REQUIRE(false, "ln_dwconv: C=%d not built (16, 32, 64, 128 are)", c);
+    }
+#undef CTO_LND
+    return 0;
 }
 
 int launch_ln_dwconv(const float* x, const float* g, const float* b, const float* taps_q, const float* taps_kv, float* dq,
                      float* dkv, int64_t batch, int w, int wkv, int c, cudaStream_t s, uint16_t* dq_hi, uint16_t* dq_mid,
                      uint16_t* dkv_hi, uint16_t* dkv_mid) {
     if (batch <= 0) return 0;
-    CTO_REQUIRE(w <= LND_MAXW && c <= LND_MAXC, "ln_dwconv: W=%d C=%d exceed %d/%d", w, c, LND_MAXW, LND_MAXC);
-    if (dq_hi) {
-        CTO_REQUIRE(dq_mid && dkv_hi && dkv_mid && c % 32 == 0, "ln_dwconv: split output needs C %% 32 == 0 (C=%d)", c);
-        ln_dwconv_kernel<true><<<ceil_div(batch, LND_WARPS), LND_WARPS * 32, sizeof(float) * LND_WARPS * w * c, s>>>(x, g, b, taps_q, taps_kv, nullptr, nullptr, dq_hi,
-                                                                                  dq_mid, dkv_hi, dkv_mid, batch, w, wkv, c);
-    } else
-    ln_dwconv_kernel<false><<<ceil_div(batch, LND_WARPS), LND_WARPS * 32, sizeof(float) * LND_WARPS * w * c, s>>>(x, g, b, taps_q, taps_kv, dq, dkv, nullptr, nullptr,
-                                                                               nullptr, nullptr, batch, w, wkv, c);
+    CTO_REQUIRE(w <= LND_MAXW, "ln_dwconv: W=%d exceeds %d", w, LND_MAXW);
+    CTO_REQUIRE(dq_hi ? (dq_mid && dkv_hi && dkv_mid) : (dq && dkv), "ln_dwconv: no output buffer");
+    if (int rc = dq_hi ? launch_ln_dwconv_t<true>(x, g, b, taps_q, taps_kv, nullptr, nullptr, dq_hi, dq_mid, dkv_hi, dkv_mid, batch, w, wkv, c, s)
+                       : launch_ln_dwconv_t<false>(x, g, b, taps_q, taps_kv, dq, dkv, nullptr, nullptr, nullptr, nullptr, batch, w, wkv, c, s))
+        return rc;
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;
@@ -470,28 +485,28 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
     extern __shared__ __align__(16) float att_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr int LD = ATT_D + 4;
-    const int per_warp = (w + 2 * wkv) * LD + ((w * (wkv + 1) + 3) & ~3);
+    const int per_warp = (w + wkv) * LD + ((w * (wkv + 1) + 3) & ~3);
     float* sq = att_smem + wib * per_warp;               // [w][68]
     float* sk = sq + w * LD;                             // [wkv][68]
-    float* sv = sk + wkv * LD;                           // [wkv][68]
-    float* sp = sv + wkv * LD;                           // [w][wkv + 1]
+    float* sp = sk + wkv * LD;                           // [w][wkv + 1]
     const int ldp = wkv + 1;
     const int64_t bh = (int64_t)blockIdx.x * ATT_WARPS + wib;
     if (bh >= n_bh) return;
     const int64_t b = bh / heads;
     const int h = (int)(bh - b * heads);
     const int inner = heads * ATT_D;
-    for (int i = 0; i < w; ++i) {
-        const float* src = q + (b * w + i) * inner + h * ATT_D;
-        sq[i * LD + lane] = src[lane];
-        sq[i * LD + lane + 32] = src[lane + 32];
-    }
-    for (int j = 0; j < wkv; ++j) {
-        const float* src = kv + (b * wkv + j) * (2 * inner) + h * ATT_D;
-        sk[j * LD + lane] = src[lane];
-        sk[j * LD + lane + 32] = src[lane + 32];
-        sv[j * LD + lane] = src[inner + lane];
-        sv[j * LD + lane + 32] = src[inner + lane + 32];
+    // each lane owns head dimensions 2*lane, 2*lane+1: 8-byte global accesses, v stays in registers
+    float2 vreg[ATT_MAXKV];
+    for (int i = 0; i < w; ++i)
+        *reinterpret_cast<float2*>(sq + i * LD + 2 * lane) = *reinterpret_cast<const float2*>(q + (b * w + i) * inner + h * ATT_D + 2 * lane);
+    #pragma unroll
+    for (int j = 0; j < ATT_MAXKV; ++j) {
+        vreg[j] = make_float2(0.f, 0.f);
+        if (j < wkv) {
+            const float* src = kv + (b * wkv + j) * (2 * inner) + h * ATT_D + 2 * lane;
+            *reinterpret_cast<float2*>(sk + j * LD + 2 * lane) = *reinterpret_cast<const float2*>(src);
+            vreg[j] = *reinterpret_cast<const float2*>(src + inner);
+        }
     }
     __syncwarp();
     for (int p = lane; p < w * wkv; p += 32) {
@@ -525,18 +540,23 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
     __syncwarp();
     for (int i = 0; i < w; ++i) {
         float o0 = 0.0f, o1 = 0.0f;
-        for (int j = 0; j < wkv; ++j) {
-            const float pij = sp[i * ldp + j];
-            o0 = fmaf(pij, sv[j * LD + lane], o0);
-            o1 = fmaf(pij, sv[j * LD + lane + 32], o1);
+        #pragma unroll
+        for (int j = 0; j < ATT_MAXKV; ++j) {
+            if (j < wkv) {
+                const float pij = sp[i * ldp + j];
+                o0 = fmaf(pij, vreg[j].x, o0);
+                o1 = fmaf(pij, vreg[j].y, o1);
+            }
         }
-        const int64_t o = (b * w + i) * inner + h * ATT_D;
+        const int64_t o = (b * w + i) * inner + h * ATT_D + 2 * lane;
         if (SPLIT) {
-            store_split_pair(out_hi, out_mid, o + lane, o0, lane);
-            store_split_pair(out_hi, out_mid, o + lane + 32, o1, lane);
+            uint32_t hh, mm;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hh) : "f"(o1), "f"(o0));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mm) : "f"(o1 - __uint_as_float(hh & 0xFFFF0000u)), "f"(o0 - __uint_as_float(hh << 16)));
+            *reinterpret_cast<uint32_t*>(out_hi + o) = hh;
+            *reinterpret_cast<uint32_t*>(out_mid + o) = mm;
         } else {
-            out[o + lane] = o0;
-            out[o + lane + 32] = o1;
+            *reinterpret_cast<float2*>(out + o) = make_float2(o0, o1);
         }
     }
 }
@@ -546,7 +566,7 @@ int launch_attention(const float* q, const float* kv, float* out, int64_t batch,
     const int64_t n_bh = batch * heads;
     if (n_bh <= 0) return 0;
     CTO_REQUIRE(w <= ATT_MAXW && wkv <= ATT_MAXKV, "attention: W=%d Wkv=%d exceed %d/%d", w, wkv, ATT_MAXW, ATT_MAXKV);
-    const size_t smem = sizeof(float) * ATT_WARPS * ((w + 2 * wkv) * (ATT_D + 4) + ((w * (wkv + 1) + 3) & ~3));
+    const size_t smem = sizeof(float) * ATT_WARPS * ((w + wkv) * (ATT_D + 4) + ((w * (wkv + 1) + 3) & ~3));
     if (out_hi) attention_kernel<true><<<ceil_div(n_bh, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(q, kv, nullptr, out_hi, out_mid, n_bh, w, wkv, heads);
     else attention_kernel<false><<<ceil_div(n_bh, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(q, kv, out, nullptr, nullptr, n_bh, w, wkv, heads);
     CTO_CHECK(cudaGetLastError());
