@@ -76,6 +76,26 @@ class ClockSampler:
                     power_w_max=max(float(r[3]) for r in rows))
 
 
+TRAFFIC_KERNEL = {"neg_gru2_recurrent": "gru3_kernel<192", "neg_gru1_recurrent": "gru3_kernel<128",
+                  "encoder": "encode_pileup_kernel", "aff_stage1_fused": "aff_stage1_kernel"}
+
+
+def ncu_traffic(family, candidates_per_launch):
+    """DRAM bytes per launch of the kernel behind a profile family, from the committed ncu capture
+    (profiles/r1_traffic.json, written by profiles/summarize.py traffic), scaled linearly from the capture's
+    launch size to this run's mean launch size (every byte these kernels move is per candidate); None when the
+    capture does not hold that kernel."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    key = TRAFFIC_KERNEL.get(family)
+    if not key or not os.path.exists(path):
+        return None
+    t = json.load(open(path))
+    for name, k in t["kernels"].items():
+        if key in name:
+            return k["dram_bytes"] * float(candidates_per_launch) / float(t["candidates_per_launch"])
+    return None
+
+
 def synthetic_likelihood(n_heads, seed=1):
     import numpy as np
     rng = np.random.default_rng(seed)
@@ -227,17 +247,24 @@ def main():
     enc_bytes = aff.algorithmic_bytes() + neg.algorithmic_bytes()
     enc = dict(bound="hbm", achieved=enc_bytes / ((enc_aff_ms + enc_neg_ms) * 1e-3) / 1e9, peak=peaks["hbm"],
                unit="GB/s", traffic=None, kernel="encode_pileup_kernel", ms_per_step=enc_aff_ms + enc_neg_ms,
+               launches_per_step=2,
                algorithmic_bytes_per_step=enc_bytes, peak_source=peaks["source"])
     enc["frac"] = enc["achieved"] / enc["peak"]
+    enc_tr = ncu_traffic("encoder", n)
+    if enc_tr is not None:                              # the capture holds one launch per stream; report their mean
+        enc["traffic"] = enc_tr
+        enc["algorithmic_bytes_per_launch"] = enc_bytes / 2
     tensor_fams = [f for f in fam if f["flop_per_candidate"] > 0]
     top = max(tensor_fams, key=lambda f: f["ms_per_step"])
     per_launch_ms = top["ms_per_step"] / top["launches_per_step"]
     cand_per_launch = n / top["launches_per_step"]
     achieved = top["flop_per_candidate"] * cand_per_launch / (per_launch_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["tensor_sustained"], unit="TFLOP/s",
-                    frac=achieved / peaks["tensor_sustained"], traffic=None, kernel=top["name"],
-                    ms_per_launch=per_launch_ms, launches_per_step=top["launches_per_step"],
-                    peak_source=peaks["source"] + ", bf16 sustained; kernel computes in fp32/tf32",
+                    frac=achieved / peaks["tensor_sustained"], traffic=ncu_traffic(top["name"], cand_per_launch),
+                    kernel=top["name"], ms_per_launch=per_launch_ms, launches_per_step=top["launches_per_step"],
+                    algorithmic_flop_per_launch=top["flop_per_candidate"] * cand_per_launch,
+                    peak_source=peaks["source"] + ", dense bf16 sustained; the kernel issues 3 bf16 MMAs per algorithmic "
+                                                  "multiply-add (bf16x3 split for fp32-grade accuracy), so 1/3 is its ceiling",
                     families=fam, encoder=enc)
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
@@ -283,7 +310,7 @@ def main():
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32", data="synthetic",
+                    dtype="f32 (tensor-core contractions as bf16x3 split products, f32 accumulate)", data="synthetic",
                     config=dict(workload="BASELINE configs[1]: synthetic 100k ONT-shape candidate sites, pileup SNV "
                                          "model, AFF+NEG (+posterior)", candidates_per_gpu=n, platform=literal,
                                 heads=n_heads, engine_chunk=args.max_batch, weights="seeded random init",

@@ -212,19 +212,39 @@ int cto_engine_set_tensor_cores(cto_engine* h, int enable) {
 
 int cto_gemm_nt(const float* a, int64_t lda, const float* w, const float* bias, const float* residual, int64_t ldr,
                 float* c, int64_t ldc, int64_t m, int n, int k, int act, int use_tensor_cores, void* stream) {
-    if (use_tensor_cores) {
-        // split the weights on the fly (the engine does this once at load time)
-        uint16_t *hi = nullptr, *lo = nullptr;
-        cudaStream_t s = (cudaStream_t)stream;
-        CTO_CHECK(cudaMallocAsync((void**)&hi, sizeof(uint16_t) * (size_t)n * k, s));
-        CTO_CHECK(cudaMallocAsync((void**)&lo, sizeof(uint16_t) * (size_t)n * k, s));
-        int rc = launch_split_bf16(w, hi, lo, (int64_t)n * k, s);
-        if (!rc) rc = launch_gemm_tc(a, lda, hi, lo, bias, residual, ldr, c, ldc, m, n, k, act, s);
-        cudaFreeAsync(hi, s);
-        cudaFreeAsync(lo, s);
-        return rc;
+    if (!use_tensor_cores) return launch_gemm_nt(plain_a(a, lda), w, bias, residual, ldr, c, ldc, m, n, k, act, (cudaStream_t)stream);
+    // tensor-core modes (bit 0 set): the operands are split here on the fly; the engine does it once at load time
+    // (weights) or in the producing kernel (activations).  bit 1: A pre-split into bf16 planes, bit 2: C written as
+    // bf16 planes and recombined, bit 3: bias indexed by the output row + n-major tile order.
+    const bool presplit = use_tensor_cores & 2, out_split = use_tensor_cores & 4, by_row = use_tensor_cores & 8;
+    CTO_REQUIRE(!presplit || lda == k, "gemm_nt: pre-split A needs a dense A (lda == k)");
+    CTO_REQUIRE(!out_split || (ldc == n && !residual), "gemm_nt: split C needs a dense C (ldc == n) and no residual");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint16_t *whi = nullptr, *wmid = nullptr, *ahi = nullptr, *amid = nullptr, *chi = nullptr, *cmid = nullptr;
+    auto alloc = [&](uint16_t** p, size_t n_elem) { return cudaMallocAsync((void**)p, sizeof(uint16_t) * n_elem, s); };
+    CTO_CHECK(alloc(&whi, (size_t)n * k));
+    CTO_CHECK(alloc(&wmid, (size_t)n * k));
+    int rc = launch_split_bf16(w, whi, wmid, (int64_t)n * k, s);
+    GemmTc g;
+    g.a = a; g.lda = lda; g.w_hi = whi; g.w_mid = wmid; g.ldw = k; g.bias = bias; g.residual = residual; g.ldr = ldr;
+    g.c = c; g.ldc = ldc; g.m = m; g.n = n; g.k = k; g.act = act;
+    if (presplit && !rc) {
+        CTO_CHECK(alloc(&ahi, (size_t)m * k));
+        CTO_CHECK(alloc(&amid, (size_t)m * k));
+        rc = launch_split_bf16(a, ahi, amid, m * k, s);
+        g.flags |= GEMM_A_PRESPLIT; g.a_hi = ahi; g.a_mid = amid;
     }
-    return launch_gemm_nt(plain_a(a, lda), w, bias, residual, ldr, c, ldc, m, n, k, act, (cudaStream_t)stream);
+    if (out_split && !rc) {
+        CTO_CHECK(alloc(&chi, (size_t)m * n));
+        CTO_CHECK(alloc(&cmid, (size_t)m * n));
+        g.flags |= GEMM_OUT_SPLIT; g.c_hi = chi; g.c_mid = cmid;
+    }
+    if (by_row) g.flags |= GEMM_BIAS_PER_ROW | GEMM_TILES_N_MAJOR;
+    if (!rc) rc = launch_gemm_tc_ex(g, s);
+    if (out_split && !rc) rc = launch_join_bf16(chi, cmid, c, m * n, s);
+    for (uint16_t* p : {whi, wmid, ahi, amid, chi, cmid})
+        if (p) cudaFreeAsync(p, s);
+    return rc;
 }
 
 int cto_engine_profile(cto_engine* h, int enable) {
@@ -261,8 +281,7 @@ int cto_predict(cto_engine* h, const int16_t* x_aff, const int32_t* depth_aff, c
     for (int64_t o = 0; o < n; o += e.max_batch) {
         const int64_t nb = std::min(e.max_batch, n - o);
         // both networks saturate the GPU on their own, so they run back to back on the caller's stream
-        if (int rc = launch_rescale(x_neg + o * xin, depth_neg + o, nb, e.x_neg, NEG_IN_LD, s)) return rc;
-        if (int rc = neg_forward(e, e.x_neg, nb, logits_neg + o * nh * 2, s)) return rc;
+        if (int rc = neg_forward_from_counts(e, x_neg + o * xin, depth_neg + o, nb, logits_neg + o * nh * 2, s)) return rc;
         if (int rc = launch_rescale(x_aff + o * xin, depth_aff + o, nb, e.x_aff, N_CH, s)) return rc;
         if (int rc = aff_forward(e, e.x_aff, nb, logits_aff + o * nh * 2, s)) return rc;
     }

@@ -428,13 +428,15 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
 // Tensor-core NEG path.  Both input projections are computed TRANSPOSED, xproj^T[6H, 33*bp] = W_ih * X^T, so that
 // the recurrence kernel reads them with fully coalesced loads (gru_tc3.cu); every GEMM operand on this path is
 // already split into bf16 hi / mid planes by its producer, so the GEMM kernel runs without its converter warps.
+// x: fp32 [n, 33, NEG_IN_LD], or nullptr when the caller has already filled the input planes e.nx_hi / e.nx_mid
+// (neg_forward_from_counts: rescale and split in one kernel)
 static int neg_forward_tc(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {
     const NegModel& m = e.neg;
     const int64_t bp = (n + 127) / 128 * 128, ldx = (int64_t)N_POS * bp;
     CTO_REQUIRE(bp <= e.bp_max, "neg_forward: batch %lld > workspace", (long long)n);
     const int h1 = m.l[0].hidden, h2 = m.l[1].hidden;
     RUN(prof_begin(e, PK_NEG_PROJ1, s));
-    RUN(launch_split_time_major(x, n, N_POS, NEG_IN_LD, bp, e.nx_hi, e.nx_mid, s));
+    if (x) RUN(launch_split_time_major(x, n, N_POS, NEG_IN_LD, bp, e.nx_hi, e.nx_mid, s));
     GemmTc g;
     g.flags = GEMM_A_PRESPLIT | GEMM_BIAS_PER_ROW | GEMM_TILES_N_MAJOR;
     g.a_hi = m.wih1_pad.bhi; g.a_mid = m.wih1_pad.bmid; g.lda = NEG_IN_LD;
@@ -471,6 +473,17 @@ static int neg_forward_tc(Engine& e, const float* x, int64_t n, float* logits, c
                        m.n_heads * FC_DIM, FC_DIM, ACT_SELU, s));
     RUN(launch_head_fc3(e.f2n, hd.fc3_w, hd.fc3_b, logits, n, m.n_heads, s));
     return prof_end(e, s);
+}
+
+int neg_forward_from_counts(Engine& e, const int16_t* x, const int32_t* depth, int64_t n, float* logits, cudaStream_t s) {
+    CTO_REQUIRE(n <= e.max_batch, "neg_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
+    static_assert(NEG_IN_LD == NEG_PLANE_LD, "plane row stride");
+    if (e.use_tc) {
+        RUN(launch_rescale_split_time_major(x, depth, n, (n + 127) / 128 * 128, e.nx_hi, e.nx_mid, s));
+        return neg_forward_tc(e, nullptr, n, logits, s);
+    }
+    RUN(launch_rescale(x, depth, n, e.x_neg, NEG_IN_LD, s));
+    return neg_forward(e, e.x_neg, n, logits, s);
 }
 
 int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {

@@ -113,5 +113,7 @@ void engine_free(Engine& e);
 // logits: device fp32 [n, n_heads, 2]; n <= max_batch
 int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
 int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
+// the same from the encoder's int16 tensor [n, 33, 34] + per-candidate depth (depth rescale of clairs/predict.py:179-197 fused in)
+int neg_forward_from_counts(Engine& e, const int16_t* x, const int32_t* depth, int64_t n, float* logits, cudaStream_t s);
 
 }  // namespace cto

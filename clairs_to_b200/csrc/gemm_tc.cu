@@ -423,6 +423,13 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, uint16_t* __restr
     mid[i] = (uint16_t)(m & 0xFFFFu);
 }
 
+// bf16 hi + mid planes -> fp32 (the inverse of the split up to 2^-17 relative; used by tests and debugging)
+__global__ void join_bf16_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ mid, float* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = __uint_as_float((uint32_t)hi[i] << 16) + __uint_as_float((uint32_t)mid[i] << 16);
+}
+
 // 2-D tiled tensor map with 128-byte swizzle; the box is (128 bytes of the inner dimension) x box_rows
 static int make_map_any(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* ptr, int64_t rows, int64_t cols,
                         int64_t ld, int box_rows, int box_cols = 0, bool swizzle = true) {
@@ -468,6 +475,14 @@ int g_gemm_debug = 0;       // non-zero: CTA 0 records per-phase cycle counters 
 int launch_split_bf16(const float* w, uint16_t* hi, uint16_t* mid, int64_t n, cudaStream_t s) {
     if (n <= 0) return 0;
     tc::split_bf16_kernel<<<ceil_div(n, 256), 256, 0, s>>>(w, hi, mid, n);
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int launch_join_bf16(const uint16_t* hi, const uint16_t* mid, float* out, int64_t n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    tc::join_bf16_kernel<<<ceil_div(n, 256), 256, 0, s>>>(hi, mid, out, n);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

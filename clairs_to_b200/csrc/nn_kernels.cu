@@ -42,11 +42,73 @@ __global__ void rescale_kernel(const int16_t* __restrict__ x, const int32_t* __r
     out[i] = d > MIN_RESCALE_COV ? __double2float_rn(__dmul_rn(v, __ddiv_rn(50.0, (double)d))) : (float)v;
 }
 
+// One thread per (candidate, position) row of 34 counts: the scale factor is computed once per row and the
+// row is read as 17 aligned 32-bit words.  SPLIT = false: fp32 rows [n, 33, 34] (AFF input).  SPLIT = true: the
+// NEG input as time-major bf16 hi / mid planes [33, bp, 40] (operand of the transposed input projection); threads
+// are ordered position-major there so that a warp writes 32 consecutive output rows.
+template <bool SPLIT>
+__global__ void rescale_rows_kernel(const int16_t* __restrict__ x, const int32_t* __restrict__ depth, int64_t n, int64_t bp,
+                                    float* __restrict__ out, uint16_t* __restrict__ hi, uint16_t* __restrict__ mid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * N_POS) return;
+    const int64_t b = SPLIT ? i % n : i / N_POS;
+    const int t = (int)(SPLIT ? i / n : i - b * N_POS);
+    const int d = depth[b];
+    const bool scale = d > MIN_RESCALE_COV;
+    const double f = __ddiv_rn(50.0, (double)(scale ? d : 50));
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + (b * N_POS + t) * N_CH);      // 68-byte rows: 4-byte aligned
+    float v[40];
+    #pragma unroll
+    for (int k = 0; k < N_CH / 2; ++k) {
+        const uint32_t wd = __ldg(src + k);
+        const int lo = (int)(int16_t)(wd & 0xFFFFu), hi16 = (int)(int16_t)(wd >> 16);
+        // python: float(item) * (50.0 / depth) in double, then numpy float32 cast (P:179-197)
+        v[2 * k] = scale ? __double2float_rn(__dmul_rn((double)lo, f)) : (float)lo;
+        v[2 * k + 1] = scale ? __double2float_rn(__dmul_rn((double)hi16, f)) : (float)hi16;
+    }
+    if (SPLIT) {
+        #pragma unroll
+        for (int k = N_CH; k < 40; ++k) v[k] = 0.0f;
+        const int64_t o = ((int64_t)t * bp + b) * 40;
+        #pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            uint32_t h[4], m[4];
+            #pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a0 = v[8 * q + 2 * e], a1 = v[8 * q + 2 * e + 1];
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[e]) : "f"(a1), "f"(a0));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m[e]) : "f"(a1 - __uint_as_float(h[e] & 0xFFFF0000u)), "f"(a0 - __uint_as_float(h[e] << 16)));
+            }
+            *reinterpret_cast<uint4*>(hi + o + 8 * q) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(mid + o + 8 * q) = make_uint4(m[0], m[1], m[2], m[3]);
+        }
+    } else {
+        float2* dst = reinterpret_cast<float2*>(out + i * N_CH);                               // 136-byte rows: 8-byte aligned
+        #pragma unroll
+        for (int k = 0; k < N_CH / 2; ++k) dst[k] = make_float2(v[2 * k], v[2 * k + 1]);
+    }
+}
+
 int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, int ld_out, cudaStream_t s) {
     if (n <= 0) return 0;
     CTO_REQUIRE(ld_out >= N_CH, "rescale: ld_out %d < %d", ld_out, N_CH);
-    const int64_t total = n * N_POS * ld_out;
-    rescale_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, depth, n * N_POS, ld_out, out);
+    if (ld_out == N_CH && (reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+        rescale_rows_kernel<false><<<ceil_div(n * N_POS, 128), 128, 0, s>>>(x, depth, n, 0, out, nullptr, nullptr);
+    } else {
+        const int64_t total = n * N_POS * ld_out;
+        rescale_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, depth, n * N_POS, ld_out, out);
+    }
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int launch_rescale_split_time_major(const int16_t* x, const int32_t* depth, int64_t n, int64_t bp, uint16_t* hi, uint16_t* mid,
+                                    cudaStream_t s) {
+    if (n <= 0) return 0;
+    CTO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0 && bp >= n, "rescale_split: unaligned input or bp < n");
+    static_assert(NEG_PLANE_LD == 40, "rescale_rows_kernel writes 40-element plane rows");
+    rescale_rows_kernel<true><<<ceil_div(n * N_POS, 128), 128, 0, s>>>(x, depth, n, bp, nullptr, hi, mid);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

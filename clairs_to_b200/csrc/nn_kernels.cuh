@@ -31,6 +31,7 @@ int launch_gemm_tc(const float* a, int64_t lda, const uint16_t* w_hi, const uint
                    const float* residual, int64_t ldr, float* c, int64_t ldc, int64_t m, int n, int k, int act,
                    cudaStream_t s);
 int launch_split_bf16(const float* w, uint16_t* hi, uint16_t* mid, int64_t n, cudaStream_t s);
+int launch_join_bf16(const uint16_t* hi, const uint16_t* mid, float* out, int64_t n, cudaStream_t s);
 // the general form: A either fp32 (split by the kernel's converter warps) or already split into bf16 hi / mid
 // planes; W always pre-split, row stride ldw
 enum GemmFlags { GEMM_A_PRESPLIT = 1, GEMM_BIAS_PER_ROW = 2, GEMM_TILES_N_MAJOR = 4, GEMM_OUT_SPLIT = 8 };
@@ -52,6 +53,10 @@ int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s);
 
 // ld_out >= 34: row stride of the fp32 output (extra columns are zero-filled)
 int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, int ld_out, cudaStream_t s);
+constexpr int NEG_PLANE_LD = 40;   // row stride of the NEG input planes (34 channels + zeros; = engine.cuh NEG_IN_LD)
+// int16 tensor -> rescaled NEG input written directly as time-major bf16 hi / mid planes [33, bp, 40]
+int launch_rescale_split_time_major(const int16_t* x, const int32_t* depth, int64_t n, int64_t bp, uint16_t* hi, uint16_t* mid,
+                                    cudaStream_t s);
 int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_out, cudaStream_t s);
 // y_hi / y_mid, dq_hi .., out_hi ..: when given, the result is written as bf16 hi / mid planes (the pre-split A
 // operand of the next GEMM) instead of fp32

@@ -222,7 +222,8 @@ class Engine:
 
 def gemm_nt(a, w, bias=None, residual=None, act=0, tensor_cores=True):
     """C = act(A @ W^T + bias) (+ residual) through ``cto_gemm_nt``: the dense-contraction building
-    block of both networks, on tcgen05 (TF32) or on the fp32 CUDA-core kernel."""
+    block of both networks, on tcgen05 (bf16x3) or on the fp32 CUDA-core kernel.  ``tensor_cores`` may
+    also be the integer mode mask of ``cto_gemm_nt`` (1 | 2 pre-split A | 4 split C | 8 bias per row)."""
     lib = _lib.lib()
     assert a.is_cuda and a.dtype == torch.float32 and w.dtype == torch.float32
     m, k = a.shape
@@ -231,5 +232,5 @@ def gemm_nt(a, w, bias=None, residual=None, act=0, tensor_cores=True):
     assert a.stride(1) == 1 and w.is_contiguous()
     _lib.check(lib.cto_gemm_nt(C.c_void_p(a.data_ptr()), a.stride(0), _ptr(w), _ptr(bias), _ptr(residual),
                                residual.stride(0) if residual is not None else 0, _ptr(c), n, m, n, k, int(act),
-                               1 if tensor_cores else 0, _stream_ptr()), "cto_gemm_nt")
+                               int(tensor_cores), _stream_ptr()), "cto_gemm_nt")
     return c

@@ -98,11 +98,14 @@ int cto_posterior_from_probs(const double* tables_host, int n_heads, const doubl
                              int64_t n, double* post_dev, int32_t* call_dev, void* stream);
 
 /*
- * Dense contractions and the GRU recurrence run on tcgen05 tensor cores by default, as 3xTF32
- * (operands split into TF32 hi + lo, three MMAs per k-step, fp32 accumulate in TMEM) because
- * single-pass TF32 breaks the 1e-3 logit contract; enable = 0 forces the fp32 CUDA-core kernels
- * everywhere (the parity tests run both).  cto_gemm_nt exposes the building block itself:
- * C[m,n] = act(A[m,k] * W[n,k]^T + bias) (+ residual), act 0 none / 1 GELU(erf) / 2 SELU.
+ * Dense contractions and the GRU recurrence run on tcgen05 tensor cores by default, as "bf16x3"
+ * (every fp32 operand split into bf16 hi + mid, three kind::f16 MMAs per k-step, fp32 accumulate in
+ * TMEM) because a single reduced-precision pass breaks the 1e-3 logit contract; enable = 0 forces the
+ * fp32 CUDA-core kernels everywhere (the parity tests run both).  cto_gemm_nt exposes the building
+ * block itself: C[m,n] = act(A[m,k] * W[n,k]^T + bias) (+ residual), act 0 none / 1 GELU(erf) / 2 SELU.
+ * use_tensor_cores: 0 = fp32 CUDA cores; bit 0 = tensor cores, plus (the modes the engine uses between its
+ * own kernels) bit 1 = A handed over as pre-split bf16 planes, bit 2 = C produced as bf16 planes, bit 3 =
+ * bias indexed by the output row and n-major tile order (the transposed input projections of the GRU).
  */
 int cto_engine_set_tensor_cores(cto_engine* e, int enable);
 int cto_gemm_nt(const float* a_dev, int64_t lda, const float* w_dev, const float* bias_dev, const float* residual_dev,

@@ -1,6 +1,6 @@
-"""GPU: the tcgen05 3xTF32 GEMM (csrc/gemm_tc.cu) against an fp64 torch reference and against the
+"""GPU: the tcgen05 bf16x3 GEMM (csrc/gemm_tc.cu) against an fp64 torch reference and against the
 fp32 CUDA-core GEMM it replaces.  Floating point: both paths are held to fp32-rounding level,
-2e-5 relative to sum |a||w| (a single-pass TF32 product would be ~1e-3: the hi/lo split matters)."""
+2e-5 relative to sum |a||w| (a single bf16 pass would be ~4e-3: the hi/mid split matters)."""
 
 import numpy as np
 import pytest
@@ -58,3 +58,28 @@ def test_gemm_tf32_strided_a_and_inplace_residual():
     want = a.double() @ w.double().t() + res.double()
     got = gemm_nt(a, w, None, res, 0, tensor_cores=True)
     assert (got.double() - want).abs().max().item() < 1e-4
+
+
+MODES = [3, 5, 7, 9, 11]     # cto_gemm_nt mode masks: 1 | 2 pre-split A | 4 split C | 8 bias per row + n-major tiles
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 128, 64), (1000, 1152, 256), (515, 128, 12672), (768, 33 * 128, 40), (45, 512, 128),
+                                   (1152, 640, 256), (130, 64, 16)])
+@pytest.mark.parametrize("mode", MODES)
+def test_gemm_engine_modes(m, n, k, mode):
+    """The operand / result layouts the engine uses between its own kernels: A handed over as bf16 hi/mid planes
+    (no converter pass), C emitted as planes, bias per output row (transposed GRU input projections)."""
+    from clairs_to_b200.engine import gemm_nt
+    g = torch.Generator(device="cpu").manual_seed(m + 3 * n + 7 * k + mode)
+    a = torch.randn(m, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) / np.sqrt(k)).cuda()
+    by_row = bool(mode & 8)
+    bias = torch.randn(m if by_row else n, generator=g).cuda()
+    act = 1 if mode & 4 else 0
+    want = a.double() @ w.double().t() + (bias.double()[:, None] if by_row else bias.double())
+    want = _act(want, act)
+    scale = (a.double().abs() @ w.double().abs().t()).max().item()
+    got = gemm_nt(a, w, bias, None, act, tensor_cores=mode)
+    err = (got.double() - want).abs().max().item()
+    assert err < 2e-5 * max(scale, 1.0), (err, scale)
+    assert torch.isfinite(got).all()
