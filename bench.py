@@ -23,6 +23,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "candidate sites/sec (pileup+AFF+NEG)"
+WORKLOAD = "BASELINE configs[1]: synthetic 100k ONT-shape candidate sites, pileup SNV model, AFF+NEG (+posterior)"
 UNIT = "candidate sites/s"
 
 
@@ -120,9 +121,11 @@ def run_reference(args, rank, world):
     value = sum(vals) / len(vals)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * sum(times) / len(times), higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="synthetic ONT-shape candidate sites, SNV AFF+NEG (BASELINE configs[1]), "
-                                     "bounded CPU sample per step", candidates_per_step=per_proc * cores),
+                dtype="f32 (torch CPU)", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, platform="ont_r10_dorado_sup_5khz", heads=4, weights="seeded random init",
+                            candidates_per_step=per_proc * cores,
+                            sample="each step is a bounded sample of the workload: %d candidates per host process x %d "
+                                   "single-thread processes (the reference's own process model)" % (per_proc, cores)),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=last["sample"]),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -311,8 +314,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32 (tensor-core contractions as bf16x3 split products, f32 accumulate)", data="synthetic",
-                    config=dict(workload="BASELINE configs[1]: synthetic 100k ONT-shape candidate sites, pileup SNV "
-                                         "model, AFF+NEG (+posterior)", candidates_per_gpu=n, platform=literal,
+                    config=dict(workload=WORKLOAD, candidates_per_gpu=n, platform=literal,
                                 heads=n_heads, engine_chunk=args.max_batch, weights="seeded random init",
                                 l2_policy="inputs (%.0f MB per step) larger than the 126 MB L2" % ((aff.nbytes() + neg.nbytes()) / 1e6),
                                 parallelism="candidates sharded x%d, one gather of probabilities" % world,

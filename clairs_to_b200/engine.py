@@ -112,7 +112,7 @@ class Engine:
             pass
 
     def set_tensor_cores(self, enable: bool):
-        """TF32 tcgen05 contractions (default) or the exact fp32 CUDA-core kernels everywhere."""
+        """bf16x3 tcgen05 contractions (default) or the fp32 CUDA-core kernels everywhere."""
         _lib.check(self.lib.cto_engine_set_tensor_cores(self.handle, 1 if enable else 0), "set_tensor_cores")
 
     def set_likelihood(self, path_or_array):

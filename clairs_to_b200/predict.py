@@ -108,7 +108,7 @@ def predict(args):
     start = time()
     if args.is_from_tables:
         return                                                   # clairs/predict.py:575: nothing to do
-    engine = Engine.from_checkpoints(args.chkpnt_fn_acgt, args.chkpnt_fn_nacgt, max_batch=9472)
+    engine = Engine.from_checkpoints(args.chkpnt_fn_acgt, args.chkpnt_fn_nacgt, max_batch=10240)     # one reference chunk file (<= 10 000 candidates, shared/param.py:21) per network pass
     expect_heads = 4 if args.disable_indel_calling else 6
     if engine.n_heads != expect_heads:
         sys.exit("[ERROR] checkpoints carry %d heads but --disable_indel_calling %s expects %d"

@@ -133,7 +133,7 @@ def test_encoder_edge_cases(eng4):
 @pytest.mark.parametrize("tensor_cores,tol", [(True, TOL), (False, 5e-5)])
 @pytest.mark.parametrize("n_heads", [4, 6])
 def test_forward_matches_reference_golden(golden_dir, n_heads, tensor_cores, tol):
-    """Reference logits (golden) vs the engine: TF32 tensor-core path within the 1e-3 contract,
+    """Reference logits (golden) vs the engine: bf16x3 tensor-core path within the 1e-3 contract,
     fp32 CUDA-core path at fp32 rounding level."""
     eng, _, _ = _engine(n_heads, max_batch=16, tensor_cores=tensor_cores)   # 24 candidates -> two internal chunks
     g = np.load(os.path.join(golden_dir, "nn_golden.npz"))
