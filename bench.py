@@ -180,8 +180,6 @@ def main():
     neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 200 + n_heads)
     eng = Engine(aff_sd, neg_sd, max_batch=args.max_batch, device=dev, likelihood=synthetic_likelihood(n_heads))
     lib = eng.lib
-    if os.environ.get("CTO_GRU_GATE_WARPS"):
-        lib.cto_debug_gru_gate_warps(int(os.environ["CTO_GRU_GATE_WARPS"]))
     if os.environ.get("CTO_DEBUG"):
         lib.cto_debug_set(int(os.environ["CTO_DEBUG"]))
     d_aff, d_neg = stream_to_device(aff, dev), stream_to_device(neg, dev)

@@ -30,7 +30,7 @@ int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* 
 
 }  // namespace cto
 
-namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; extern int g_gru3_gw; }
+namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; }
 using namespace cto;
 
 struct cto_engine {
@@ -202,8 +202,6 @@ int64_t cto_launch_count(void) { return launches(); }
 
 void cto_debug_set(int flags) { cto::g_gemm_debug = flags; }
 void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; }
-void cto_debug_gru_gate_warps(int gw) { cto::g_gru3_gw = (gw == 2 || gw == 3 || gw == 4) ? gw : 0; }
-
 int cto_engine_set_tensor_cores(cto_engine* h, int enable) {
     CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");
     h->e.use_tc = enable != 0;

@@ -1,4 +1,4 @@
-// GRU recurrence, third generation: CTA pair (tcgen05 cta_group::2) + bf16x3 operands + 16 gate-math warps.
+// GRU recurrence, third generation: CTA pair (tcgen05 cta_group::2) + bf16x3 operands, register-resident state.
 //
 // Arithmetic: torch.nn.GRU semantics (clairs/model.py:412-417), gate order r|z|n,
 //     n = tanh(W_in x + b_in + r * (W_hn h + b_hn)),   h' = (1 - z) * n + z * h,
@@ -8,12 +8,14 @@
 //
 // What the ncu capture of the previous kernel (gru_tc2.cu, profiles/r1_ncu_gru_pair_stalls.txt) showed and what
 // changed here:
-//   * the eight gate-math warps were latency-bound (17 % issue utilisation, two warps per scheduler)
-//       -> sixteen gate-math warps, each thread owns 8 units of (ITERS) half-blocks for ONE candidate row;
+//   * the gate-math warps were latency-bound (17 % issue utilisation): every LDG.128 of the row-major input projection
+//     touched 32 lines -> transposed projection, one line per load
+//     (more gate-math warps were measured too: 12 / 16 warps are slower than 8);
 //   * every gate thread re-read its old h from shared memory and kept the new h in registers until all MMAs of
 //     the step had retired -> h tiles are double buffered (bf16 halves the tile size), h_t is written at once,
 //     h_{t-1} comes from registers;
-//   * 512 cluster-scope release arrives per step (MEMBAR + ERRBAR each) -> one arrive per warp;
+//   * 512 cluster-scope release arrives per step (MEMBAR + ERRBAR each) -> one arrive per warp (a CTA-local barrier
+//     relayed to the leader by an idle warp was measured too: no gain);
 //   * W_hh as TF32 hi/lo streamed 885 KB per step and pair from L2 -> bf16 hi/mid halves that and the
 //     shared-memory operand traffic of the MMAs (the M=64-per-CTA MMA is smem-bandwidth bound).
 //
@@ -36,6 +38,10 @@ constexpr int Q_WTILE = Q_HALF * 128;        // 6 KB
 constexpr int Q_STAGE = 2 * Q_WTILE;         // hi | mid
 constexpr int Q_STAGES = 8;
 // GW = gate-math warps per TMEM lane quadrant; the block is warp 0 TMA, warp 1 MMA, 4*GW gate-math warps
+}  // namespace tc
+extern long long* g_gemm_timing;      // cto_debug_timing(): device buffer [32]
+extern int g_gemm_debug;
+namespace tc {
 constexpr uint32_t Q_PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 template <int H>
@@ -89,11 +95,17 @@ __device__ __forceinline__ void q_split2(float x0, float x1, uint32_t& hi, uint3
     mid = q_pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xFFFF0000u));
 }
 
-template <int H, int GW>
+template <int H, int GW, int VAR>
 __global__ void __launch_bounds__(64 + 128 * GW, 1)
 gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__ CUtensorMap tma_wmid,
             const float* __restrict__ xproj, int64_t ldx, int64_t bp, const float* __restrict__ bhn,
-            uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_mid, int64_t osb, int64_t ost, int64_t batch) {
+            uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_mid, int64_t osb, int64_t ost, int64_t batch,
+            long long* timing) {
+    // per-phase clock64() counters of cluster 0, direction 0 (profiles/phase_timing_gru.py); timing == nullptr in production
+    const bool tim = timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    long long tacc[6] = {0, 0, 0, 0, 0, 0};
+    #define GTIC long long _t0 = tim ? clock64() : 0
+    #define GTOC(i) do { if (tim) { long long _t1 = clock64(); tacc[i] += _t1 - _t0; _t0 = _t1; } } while (0)
     constexpr int KB = H / Q_K;
     constexpr int NB = H / Q_BLK;
     constexpr int PAIRS = NB / 2;
@@ -111,9 +123,9 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     uint64_t* full = reinterpret_cast<uint64_t*>(wring + Q_STAGES * Q_STAGE);
     uint64_t* empty = full + Q_STAGES;
     uint64_t* acc_full = empty + Q_STAGES;
-    uint64_t* h_ready = acc_full + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
-    float* s_bhn = reinterpret_cast<float*>(tmem_slot + 4);
+    uint64_t* h_ready = acc_full + 3;                     // leader only: h_t complete in both CTAs, accumulators drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 2);
+    float* s_bhn = reinterpret_cast<float*>(tmem_slot + 6);   // barriers take 168 bytes: keep the float4 reads of s_bhn 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -162,7 +174,9 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Q_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             uint32_t it = 0;
             for (int step = 0; step < N_POS; ++step) {
+                GTIC;
                 q_wait_cluster(h_ready, step & 1);         // h_{t-1} is in BOTH shared memories, accumulators drained
+                GTOC(0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint8_t* hb = hbuf + (step & 1) * HBUF;
                 for (int blk = 0; blk < NB; ++blk) {
@@ -171,6 +185,7 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                         const int s = it % Q_STAGES;
                         const uint32_t ph = (it / Q_STAGES) & 1;
                         g_mbar_wait(&full[s], ph);
+                        GTOC(1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t d_hhi = g_desc_k_sw128(g_smem_u32(hb + kb * Q_HTILE));
                         const uint64_t d_hmid = g_desc_k_sw128(g_smem_u32(hb + (KB + kb) * Q_HTILE));
@@ -189,9 +204,11 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                             if ((blk & 1) && kb == KB - 1) q_commit_2sm(&acc_full[blk >> 1]);
                         }
                         __syncwarp();
+                        GTOC(2);
                     }
                 }
             }
+            if (tim && lane == 0) { timing[0] = tacc[0]; timing[1] = tacc[1]; timing[2] = tacc[2]; }
         }
     } else {                                               // ---- gate math: warps 2..17 in both CTAs ----
         const int quad = warp & 3;                         // TMEM lanes [32*quad, +32)
@@ -225,16 +242,18 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
         // the input projection is stored TRANSPOSED, xproj[gate unit][t * bp + b]: the 32 lanes of a warp are 32
         // consecutive candidates, so each scalar load below is one fully used 128-byte line (the row-major layout
         // cost 32 lines per load instruction and made the L1 tag stage the bottleneck of the whole kernel)
-        float xq[24];
-        auto prefetch = [&](int step, int j) {
+        // One half-block of register look-ahead.  Two (a double-buffered xq) were measured: the 48 extra registers spill
+        // at the 168-register limit of a ten-warp CTA and the kernel gets 7 % slower.
+        float xq[1][24];
+        auto prefetch = [&](int buf, int step, int j) {
             const int t = dir ? (N_POS - 1 - step) : step;
             const float* xp = xbase + unit0(j) * ldx + t * bp;
             #pragma unroll
             for (int g = 0; g < 3; ++g)
                 #pragma unroll
-                for (int c = 0; c < 8; ++c) xq[g * 8 + c] = __ldg(xp + (int64_t)(g * H + c) * ldx);
+                for (int c = 0; c < 8; ++c) xq[buf][g * 8 + c] = (VAR & 2) ? 0.25f : __ldg(xp + (int64_t)(g * H + c) * ldx);
         };
-        prefetch(0, 0);
+        prefetch(0, 0, 0);
         for (int step = 0; step < N_POS; ++step) {
             const int t = dir ? (N_POS - 1 - step) : step;
             const int64_t orow = (b * osb + t * ost) * (int64_t)(2 * H) + dir * H;
@@ -252,7 +271,9 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                 const int uu = unit0(j);
                 // block blk: accumulator columns [48*blk, +48) = r(16) z(16) n(16) of this lane's 16 units
                 const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(blk * Q_HALF + (hb & 1) * 8);
+                GTIC;
                 g_mbar_wait(&acc_full[blk >> 1], step & 1);
+                GTOC(j < 2 ? 0 : (j < ITERS - 2 ? 1 : 2));     // wait for the first / middle / last accumulators of the step
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t ar[8], az[8], an[8];
                 g_tmem_ld8(tcol, ar);
@@ -260,18 +281,26 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                 g_tmem_ld8(tcol + 32, an);
                 float xv[24];
                 #pragma unroll
-                for (int q = 0; q < 24; ++q) xv[q] = xq[q];
-                if (j + 1 < ITERS) prefetch(step, j + 1);
-                else if (step + 1 < N_POS) prefetch(step + 1, 0);
+                for (int q = 0; q < 24; ++q) xv[q] = xq[0][q];
+                if (j + 1 < ITERS) prefetch(0, step, j + 1);
+                else if (step + 1 < N_POS) prefetch(0, step + 1, 0);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                GTOC(3);
                 const float4 bn0 = *reinterpret_cast<const float4*>(s_bhn + uu);
                 const float4 bn1 = *reinterpret_cast<const float4*>(s_bhn + uu + 4);
                 const float bnv[8] = {bn0.x, bn0.y, bn0.z, bn0.w, bn1.x, bn1.y, bn1.z, bn1.w};
                 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const float r = g_sigmoid(xv[c] + __uint_as_float(ar[c]));
-                    const float z = g_sigmoid(xv[8 + c] + __uint_as_float(az[c]));
-                    const float n = g_tanh(xv[16 + c] + r * (__uint_as_float(an[c]) + bnv[c]));
+                    float r, z, n;
+                    if (VAR & 8) {                             // timing experiment only: no MUFU
+                        r = 0.5f + 0.25f * (xv[c] + __uint_as_float(ar[c]));
+                        z = 0.5f + 0.25f * (xv[8 + c] + __uint_as_float(az[c]));
+                        n = 0.5f * (xv[16 + c] + r * (__uint_as_float(an[c]) + bnv[c]));
+                    } else {
+                        r = g_sigmoid(xv[c] + __uint_as_float(ar[c]));
+                        z = g_sigmoid(xv[8 + c] + __uint_as_float(az[c]));
+                        n = g_tanh(xv[16 + c] + r * (__uint_as_float(an[c]) + bnv[c]));
+                    }
                     hk[j * 8 + c] = (1.0f - z) * n + z * hk[j * 8 + c];
                 }
                 const float* hv = hk + j * 8;
@@ -283,10 +312,11 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                 const uint32_t to = tile_off(j);
                 *reinterpret_cast<uint4*>(hnext + to) = hi;
                 *reinterpret_cast<uint4*>(hnext + KB * Q_HTILE + to) = mid;
-                if (b_ok) {                                    // pre-split output: an operand of the next GEMM
+                if (b_ok && !(VAR & 4)) {                      // pre-split output: an operand of the next GEMM
                     *reinterpret_cast<uint4*>(out_hi + orow + uu) = hi;
                     *reinterpret_cast<uint4*>(out_mid + orow + uu) = mid;
                 }
+                GTOC(4);
             }
             // every tcgen05.ld of the step has completed (wait::ld above) and h_t is in this CTA's shared memory
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -294,7 +324,10 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
             __syncwarp();
             if (lane == 0) q_arrive_leader(h_ready);
         }
+        if (tim && warp == 2 && lane == 0) { for (int i = 0; i < 5; ++i) timing[8 + i] = tacc[i]; timing[15] = clock64(); }
     }
+    #undef GTIC
+    #undef GTOC
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     g_cluster_sync();
@@ -304,13 +337,13 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     }
 }
 
-template <int H, int GW>
+template <int H, int GW, int VAR>
 static int launch_gru3_t(const CUtensorMap& map_hi, const CUtensorMap& map_mid, const float* xproj, int64_t ldx, int64_t bp,
                          const float* bhn, uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch,
                          cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        CTO_CHECK(cudaFuncSetAttribute(gru3_kernel<H, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gru3Smem<H>::TOTAL));
+        CTO_CHECK(cudaFuncSetAttribute(gru3_kernel<H, GW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gru3Smem<H>::TOTAL));
         attr = true;
     }
     const int ctas = ceil_div(batch, Q_M);
@@ -326,14 +359,15 @@ static int launch_gru3_t(const CUtensorMap& map_hi, const CUtensorMap& map_mid, 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CTO_CHECK(cudaLaunchKernelEx(&cfg, gru3_kernel<H, GW>, map_hi, map_mid, xproj, ldx, bp, bhn, out_hi, out_mid, osb, ost, batch));
+    CTO_CHECK(cudaLaunchKernelEx(&cfg, gru3_kernel<H, GW, VAR>, map_hi, map_mid, xproj, ldx, bp, bhn, out_hi, out_mid, osb, ost, batch,
+                                 (g_gemm_debug && g_gemm_timing) ? g_gemm_timing + 32 : nullptr));   // GEMM kernels own [0, 32)
     return 0;
 }
 
 }  // namespace tc
 
-// gate-math warps per TMEM lane quadrant: 0 = measured best (2: eight gate-math warps, no register spills), 3 (H=192 only), 4
-int g_gru3_gw = 0;
+// Eight gate-math warps (GW = 2 per TMEM lane quadrant).  12 and 16 warps were built and measured in round 1: slower
+// (register spills at <= 112 registers per thread, and the gate phase is not short of warps but of load latency).
 
 // w_hi / w_mid: [2 directions][3H rows regrouped as (32-unit block, 16-unit half, gate, unit)][H] as bf16 hi / mid.
 // xproj: TRANSPOSED input projection, fp32 [6H (dir, gate, unit)][ldx], column t * bp + b; bp >= batch rounded up to 128.
@@ -347,11 +381,18 @@ int launch_gru3(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_h
     CUtensorMap map_hi, map_mid;
     if (tc::make_map_bf16(&map_hi, w_hi, 6 * hidden, hidden, hidden, tc::Q_HALF)) return 1;
     if (tc::make_map_bf16(&map_mid, w_mid, 6 * hidden, hidden, hidden, tc::Q_HALF)) return 1;
-#define CTO_GRU3(HH, GG) tc::launch_gru3_t<HH, GG>(map_hi, map_mid, xproj, ldx, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
+#define CTO_GRU3(HH, GG) tc::launch_gru3_t<HH, GG, 0>(map_hi, map_mid, xproj, ldx, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
+#define CTO_GRU3V(VV) tc::launch_gru3_t<192, 2, VV>(map_hi, map_mid, xproj, ldx, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
     int rc;
-    if (hidden == 128) rc = g_gru3_gw == 4 ? CTO_GRU3(128, 4) : CTO_GRU3(128, 2);
-    else rc = g_gru3_gw == 4 ? CTO_GRU3(192, 4) : (g_gru3_gw == 3 ? CTO_GRU3(192, 3) : CTO_GRU3(192, 2));
+    const int var = g_gemm_debug & 14;                       // timing experiments (wrong results): profiles/phase_timing_gru.py
+    if (hidden == 128) rc = CTO_GRU3(128, 2);
+    else if (var == 2) rc = CTO_GRU3V(2);
+    else if (var == 4) rc = CTO_GRU3V(4);
+    else if (var == 8) rc = CTO_GRU3V(8);
+    else if (var == 14) rc = CTO_GRU3V(14);
+    else rc = CTO_GRU3(192, 2);
 #undef CTO_GRU3
+#undef CTO_GRU3V
     if (rc) return rc;
     CTO_CHECK(cudaGetLastError());
     count_launch();

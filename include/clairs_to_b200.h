@@ -126,13 +126,11 @@ int cto_engine_profile_read(cto_engine* e, double* ms, int64_t* launches, double
 
 /*
  * Tuning / profiling knobs (not part of the drop-in surface): cto_debug_set(1) + cto_debug_timing(buf) make
- * CTA 0 of the GEMM kernel record per-phase clock64() counters into a device buffer [32 x int64]
- * (profiles/phase_timing_gemm.py prints them); cto_debug_gru_gate_warps picks the number of gate-math warps per
- * TMEM lane quadrant in the tensor-core GRU (2, 3 or 4; 0 = the measured best per hidden size).
+ * CTA 0 of the GEMM kernel (slots [0,32)) and cluster 0 of the GRU kernel (slots [32,64)) record per-phase
+ * clock64() counters into a device buffer [64 x int64] (profiles/phase_timing_*.py print them).
  */
 void cto_debug_set(int flags);
 void cto_debug_timing(long long* dev_buf);
-void cto_debug_gru_gate_warps(int warps_per_quadrant);
 
 /* Strand-count recovery of clairs/predict.py:626-642 from the un-rescaled AFF tensor: int32 [n,4] x2. */
 int cto_strand_counts(const int16_t* x_aff_dev, int64_t n, int32_t* fwd_dev, int32_t* rev_dev, void* stream);
