@@ -463,6 +463,10 @@ static int make_map_any(CUtensorMap* map, CUtensorMapDataType dtype, int elem_by
 int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     return make_map_any(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, rows, cols, ld, box_rows);
 }
+// un-swizzled fp32 box (box_cols x box_rows) for staging that is read by ordinary LDS
+int make_map_plain(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols) {
+    return make_map_any(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, rows, cols, ld, box_rows, box_cols, false);
+}
 int make_map_bf16(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
     return make_map_any(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, rows, cols, ld, box_rows);
 }

@@ -110,6 +110,7 @@ __device__ __forceinline__ float g_tanh(float x) { return 1.0f - __fdividef(2.0f
 
 int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 int make_map_bf16(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+int make_map_plain(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 
 }  // namespace tc
 }  // namespace cto

@@ -9,7 +9,7 @@
 // What the ncu capture of the previous kernel (gru_tc2.cu, profiles/r1_ncu_gru_pair_stalls.txt) showed and what
 // changed here:
 //   * the gate-math warps were latency-bound (17 % issue utilisation): every LDG.128 of the row-major input projection
-//     touched 32 lines -> transposed projection, one line per load
+//     touched 32 lines -> transposed projection, staged through shared memory by a TMA producer warp (conflict-free LDS)
 //     (more gate-math warps were measured too: 12 / 16 warps are slower than 8);
 //   * every gate thread re-read its old h from shared memory and kept the new h in registers until all MMAs of
 //     the step had retired -> h tiles are double buffered (bf16 halves the tile size), h_t is written at once,
@@ -36,7 +36,9 @@ constexpr int Q_K = 64;                      // bf16 elements per 128-byte swizz
 constexpr int Q_HTILE = Q_M * 128;           // 8 KB: 64 rows x 64 k (bf16)
 constexpr int Q_WTILE = Q_HALF * 128;        // 6 KB
 constexpr int Q_STAGE = 2 * Q_WTILE;         // hi | mid
-constexpr int Q_STAGES = 8;
+constexpr int Q_STAGES = 6;
+constexpr int Q_XSTAGES = 2;                 // input-projection ring: one stage = 3 gates x 32 units x 64 candidates fp32
+constexpr int Q_XSTAGE = 3 * Q_BLK * Q_M * 4; // 24 KB
 // GW = gate-math warps per TMEM lane quadrant; the block is warp 0 TMA, warp 1 MMA, 4*GW gate-math warps
 }  // namespace tc
 extern long long* g_gemm_timing;      // cto_debug_timing(): device buffer [32]
@@ -48,7 +50,7 @@ template <int H>
 struct Gru3Smem {
     static constexpr int KB = H / Q_K;
     static constexpr int HBUF = 2 * KB * Q_HTILE;             // hi | mid tiles of one h_t
-    static constexpr int TOTAL = 2 * HBUF + Q_STAGES * Q_STAGE + 1024 + 256 + H * 4;
+    static constexpr int TOTAL = 2 * HBUF + Q_STAGES * Q_STAGE + Q_XSTAGES * Q_XSTAGE + 1024 + 256 + H * 4;
 };
 
 __device__ __forceinline__ void q_tma_load_2sm(const CUtensorMap* map, uint64_t* leader_bar, void* dst, int c0, int c1) {
@@ -96,9 +98,9 @@ __device__ __forceinline__ void q_split2(float x0, float x1, uint32_t& hi, uint3
 }
 
 template <int H, int GW, int VAR>
-__global__ void __launch_bounds__(64 + 128 * GW, 1)
+__global__ void __launch_bounds__(96 + 128 * GW, 1)
 gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__ CUtensorMap tma_wmid,
-            const float* __restrict__ xproj, int64_t ldx, int64_t bp, const float* __restrict__ bhn,
+            const __grid_constant__ CUtensorMap tma_x, int64_t bp, const float* __restrict__ bhn,
             uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_mid, int64_t osb, int64_t ost, int64_t batch,
             long long* timing) {
     // per-phase clock64() counters of cluster 0, direction 0 (profiles/phase_timing_gru.py); timing == nullptr in production
@@ -110,7 +112,7 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     constexpr int NB = H / Q_BLK;
     constexpr int PAIRS = NB / 2;
     constexpr int Q_GW = GW;
-    constexpr int Q_THREADS = 64 + 128 * GW;
+    constexpr int Q_THREADS = 96 + 128 * GW;              // warp 0 W producer, warp 1 MMA, 4*GW gate warps, last warp x producer
     constexpr int ITERS = 2 * NB / Q_GW;                      // 8-unit half-blocks per gate thread
     constexpr int HBUF = Gru3Smem<H>::HBUF;
     constexpr uint32_t TMEM_COLS = NB * Q_HALF <= 256 ? 256 : 512;
@@ -120,9 +122,12 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     uint8_t* base = smem_raw + ((1024u - (g_smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* hbuf = base;                                     // [2 buffers][hi | mid][KB][64 x 128 B]
     uint8_t* wring = base + 2 * HBUF;
-    uint64_t* full = reinterpret_cast<uint64_t*>(wring + Q_STAGES * Q_STAGE);
+    float* xring = reinterpret_cast<float*>(wring + Q_STAGES * Q_STAGE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(wring + Q_STAGES * Q_STAGE + Q_XSTAGES * Q_XSTAGE);
     uint64_t* empty = full + Q_STAGES;
-    uint64_t* acc_full = empty + Q_STAGES;
+    uint64_t* xfull = empty + Q_STAGES;
+    uint64_t* xempty = xfull + Q_XSTAGES;
+    uint64_t* acc_full = xempty + Q_XSTAGES;
     uint64_t* h_ready = acc_full + 3;                     // leader only: h_t complete in both CTAs, accumulators drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 2);
     float* s_bhn = reinterpret_cast<float*>(tmem_slot + 6);   // barriers take 168 bytes: keep the float4 reads of s_bhn 16-byte aligned
@@ -136,6 +141,7 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < Q_STAGES; ++s) { g_mbar_init(&full[s], 1); g_mbar_init(&empty[s], 1); }
         for (int p = 0; p < 3; ++p) g_mbar_init(&acc_full[p], 1);
+        for (int s = 0; s < Q_XSTAGES; ++s) { g_mbar_init(&xfull[s], 1); g_mbar_init(&xempty[s], 4 * Q_GW); }
         g_mbar_init(h_ready, 2 * 4 * Q_GW);                  // one arrive per gate-math warp of BOTH CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -210,7 +216,31 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
             }
             if (tim && lane == 0) { timing[0] = tacc[0]; timing[1] = tacc[1]; timing[2] = tacc[2]; }
         }
-    } else {                                               // ---- gate math: warps 2..17 in both CTAs ----
+    } else if (warp == 2 + 4 * Q_GW) {
+        // ---- x producer: the input projection xproj^T[(dir, gate, unit)][t * bp + b] of this CTA's 64 candidates, one
+        // 32-unit block (= one half-block per gate warp) per stage, by TMA, up to two half-blocks ahead of the gate math
+        // and across step boundaries.  (Per-thread global loads with one half-block of register look-ahead cost a
+        // third of the kernel in long-scoreboard stalls; deeper register look-ahead spilled.  An extra L2 tensor
+        // prefetch one step ahead was measured too: no gain, the gate warps wait < 4 % of a step for this ring.)
+        static_assert(Q_GW == 2, "one x stage = block j: the half-block order of two gate warps per quadrant");
+        const int b0 = (int)blockIdx.x * Q_M;
+        uint32_t q = 0;
+        for (int step = 0; step < N_POS; ++step) {
+            const int t = dir ? (N_POS - 1 - step) : step;
+            for (int j = 0; j < NB; ++j, ++q) {
+                const int s = q % Q_XSTAGES;
+                g_mbar_wait(&xempty[s], ((q / Q_XSTAGES) & 1) ^ 1);
+                if (g_elect_one()) {
+                    g_mbar_expect_tx(&xfull[s], Q_XSTAGE);
+                    #pragma unroll
+                    for (int g = 0; g < 3; ++g)
+                        g_tma_load_2d(&tma_x, &xfull[s], xring + (s * 3 + g) * (Q_BLK * Q_M), (int)(t * bp) + b0,
+                                      dir * 3 * H + g * H + j * Q_BLK);
+                }
+                __syncwarp();
+            }
+        }
+    } else {                                               // ---- gate math: warps 2..9 in both CTAs ----
         const int quad = warp & 3;                         // TMEM lanes [32*quad, +32)
         const int wsel = (warp - 2) >> 2;                  // 0..GW-1: half-blocks wsel, wsel+GW, wsel+2*GW, ...
         const int tl = quad * 32 + lane;                   // TMEM lane
@@ -218,7 +248,6 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
         const int uhalf = tl >> 6;                         // units [16*uhalf, +16) of each block
         const int64_t b = ((int64_t)blockIdx.x) * Q_M + m;   // < bp: the transposed projection has columns for padded rows
         const bool b_ok = b < batch;
-        const float* xbase = xproj + (int64_t)dir * 3 * H * ldx + b;
         const uint32_t row_off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
         // half-block j of this thread: block blk_j, 8 units starting at uu_j; its bf16 values are 16-byte chunk
         // ((uu % 64) / 8) of row m in k-block uu / 64
@@ -239,31 +268,14 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
         __syncwarp();
         if (lane == 0) q_arrive_leader(h_ready);
 
-        // the input projection is stored TRANSPOSED, xproj[gate unit][t * bp + b]: the 32 lanes of a warp are 32
-        // consecutive candidates, so each scalar load below is one fully used 128-byte line (the row-major layout
-        // cost 32 lines per load instruction and made the L1 tag stage the bottleneck of the whole kernel)
-        // One half-block of register look-ahead.  Two (a double-buffered xq) were measured: the 48 extra registers spill
-        // at the 168-register limit of a ten-warp CTA and the kernel gets 7 % slower.
-        float xq[1][24];
-        auto prefetch = [&](int buf, int step, int j) {
-            const int t = dir ? (N_POS - 1 - step) : step;
-            const float* xp = xbase + unit0(j) * ldx + t * bp;
-            #pragma unroll
-            for (int g = 0; g < 3; ++g)
-                #pragma unroll
-                for (int c = 0; c < 8; ++c) xq[buf][g * 8 + c] = (VAR & 2) ? 0.25f : __ldg(xp + (int64_t)(g * H + c) * ldx);
-        };
-        prefetch(0, 0, 0);
+        // The input projection is stored TRANSPOSED, xproj[gate unit][t * bp + b], and staged by the x producer as
+        // [gate][unit of the block][candidate]: lanes are consecutive candidates, so the 24 reads below are conflict-free
+        // LDS (the row-major layout of round 1 cost 32 L1 lines per load instruction).
+        uint32_t xq_it = 0;
         for (int step = 0; step < N_POS; ++step) {
             const int t = dir ? (N_POS - 1 - step) : step;
             const int64_t orow = (b * osb + t * ost) * (int64_t)(2 * H) + dir * H;
             uint8_t* hnext = hbuf + ((step + 1) & 1) * HBUF;   // read by the MMAs of step + 1; those of step - 1 have retired
-            if (step + 1 < N_POS && lane < 24) {           // next step's xproj lines -> L2, one line per lane
-                const int tn = dir ? (N_POS - 2 - step) : step + 1;
-                const float* xn = xbase + tn * bp + (int64_t)((lane >> 3) * H + (lane & 7)) * ldx;
-                #pragma unroll
-                for (int j = 0; j < ITERS; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + unit0(j) * ldx));
-            }
             #pragma unroll
             for (int j = 0; j < ITERS; ++j) {
                 const int hb = wsel + Q_GW * j;
@@ -271,7 +283,21 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                 const int uu = unit0(j);
                 // block blk: accumulator columns [48*blk, +48) = r(16) z(16) n(16) of this lane's 16 units
                 const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(blk * Q_HALF + (hb & 1) * 8);
+                float xv[24];
                 GTIC;
+                {
+                    const int xs = xq_it % Q_XSTAGES;
+                    g_mbar_wait(&xfull[xs], (xq_it / Q_XSTAGES) & 1);
+                    GTOC(5);
+                    const float* xp = xring + xs * (3 * Q_BLK * Q_M) + (uhalf * 16 + (hb & 1) * 8) * Q_M + m;
+                    #pragma unroll
+                    for (int g = 0; g < 3; ++g)
+                        #pragma unroll
+                        for (int c = 0; c < 8; ++c) xv[g * 8 + c] = (VAR & 2) ? 0.25f : xp[(g * Q_BLK + c) * Q_M];
+                    __syncwarp();
+                    if (lane == 0) g_mbar_arrive(&xempty[xs]);
+                    ++xq_it;
+                }
                 g_mbar_wait(&acc_full[blk >> 1], step & 1);
                 GTOC(j < 2 ? 0 : (j < ITERS - 2 ? 1 : 2));     // wait for the first / middle / last accumulators of the step
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -279,11 +305,6 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                 g_tmem_ld8(tcol, ar);
                 g_tmem_ld8(tcol + 16, az);
                 g_tmem_ld8(tcol + 32, an);
-                float xv[24];
-                #pragma unroll
-                for (int q = 0; q < 24; ++q) xv[q] = xq[0][q];
-                if (j + 1 < ITERS) prefetch(0, step, j + 1);
-                else if (step + 1 < N_POS) prefetch(0, step + 1, 0);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 GTOC(3);
                 const float4 bn0 = *reinterpret_cast<const float4*>(s_bhn + uu);
@@ -324,7 +345,7 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
             __syncwarp();
             if (lane == 0) q_arrive_leader(h_ready);
         }
-        if (tim && warp == 2 && lane == 0) { for (int i = 0; i < 5; ++i) timing[8 + i] = tacc[i]; timing[15] = clock64(); }
+        if (tim && warp == 2 && lane == 0) { for (int i = 0; i < 6; ++i) timing[8 + i] = tacc[i]; timing[15] = clock64(); }
     }
     #undef GTIC
     #undef GTOC
@@ -338,7 +359,7 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
 }
 
 template <int H, int GW, int VAR>
-static int launch_gru3_t(const CUtensorMap& map_hi, const CUtensorMap& map_mid, const float* xproj, int64_t ldx, int64_t bp,
+static int launch_gru3_t(const CUtensorMap& map_hi, const CUtensorMap& map_mid, const CUtensorMap& map_x, int64_t bp,
                          const float* bhn, uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch,
                          cudaStream_t s) {
     static bool attr = false;
@@ -349,7 +370,7 @@ static int launch_gru3_t(const CUtensorMap& map_hi, const CUtensorMap& map_mid, 
     const int ctas = ceil_div(batch, Q_M);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((ctas + 1) / 2 * 2), 2, 1);
-    cfg.blockDim = dim3(64 + 128 * GW, 1, 1);
+    cfg.blockDim = dim3(96 + 128 * GW, 1, 1);
     cfg.dynamicSmemBytes = Gru3Smem<H>::TOTAL;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -359,7 +380,7 @@ static int launch_gru3_t(const CUtensorMap& map_hi, const CUtensorMap& map_mid, 
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CTO_CHECK(cudaLaunchKernelEx(&cfg, gru3_kernel<H, GW, VAR>, map_hi, map_mid, xproj, ldx, bp, bhn, out_hi, out_mid, osb, ost, batch,
+    CTO_CHECK(cudaLaunchKernelEx(&cfg, gru3_kernel<H, GW, VAR>, map_hi, map_mid, map_x, bp, bhn, out_hi, out_mid, osb, ost, batch,
                                  (g_gemm_debug && g_gemm_timing) ? g_gemm_timing + 32 : nullptr));   // GEMM kernels own [0, 32)
     return 0;
 }
@@ -378,11 +399,13 @@ int launch_gru3(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_h
     if (batch <= 0) return 0;
     CTO_REQUIRE(hidden == 128 || hidden == 192, "gru3: hidden size %d not built", hidden);
     CTO_REQUIRE(xproj && out_hi && out_mid && bp % 128 == 0 && bp >= batch && ldx >= N_POS * bp, "gru3: bad buffers / padding");
-    CUtensorMap map_hi, map_mid;
+    CTO_REQUIRE(ldx % 4 == 0 && ldx < (1ll << 31), "gru3: projection row stride %lld", (long long)ldx);
+    CUtensorMap map_hi, map_mid, map_x;
     if (tc::make_map_bf16(&map_hi, w_hi, 6 * hidden, hidden, hidden, tc::Q_HALF)) return 1;
     if (tc::make_map_bf16(&map_mid, w_mid, 6 * hidden, hidden, hidden, tc::Q_HALF)) return 1;
-#define CTO_GRU3(HH, GG) tc::launch_gru3_t<HH, GG, 0>(map_hi, map_mid, xproj, ldx, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
-#define CTO_GRU3V(VV) tc::launch_gru3_t<192, 2, VV>(map_hi, map_mid, xproj, ldx, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
+    if (tc::make_map_plain(&map_x, xproj, 6 * hidden, ldx, ldx, tc::Q_BLK, tc::Q_M)) return 1;   // box: 32 units x 64 candidates
+#define CTO_GRU3(HH, GG) tc::launch_gru3_t<HH, GG, 0>(map_hi, map_mid, map_x, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
+#define CTO_GRU3V(VV) tc::launch_gru3_t<192, 2, VV>(map_hi, map_mid, map_x, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
     int rc;
     const int var = g_gemm_debug & 14;                       // timing experiments (wrong results): profiles/phase_timing_gru.py
     if (hidden == 128) rc = CTO_GRU3(128, 2);

@@ -22,6 +22,6 @@ for dbg in (0, 2, 4, 8, 14, 1):      # 2: no xproj loads, 4: no output stores, 8
     print("dbg", dbg, "neg forward %.3f ms for %d candidates" % (e0.elapsed_time(e1), n))
 t = buf.cpu().tolist()[32:]
 names = {0: "mma.wait_h_ready", 1: "mma.wait_w_full", 2: "mma.issue+commit", 8: "gate.wait_acc(first pair)", 9: "gate.wait_acc(middle)",
-         10: "gate.wait_acc(last pair)", 11: "gate.tmem_ld+xproj regs", 12: "gate.math+stores"}
+         10: "gate.wait_acc(last pair)", 11: "gate.tmem_ld", 12: "gate.math+stores", 13: "gate.wait_x_stage"}
 print("cycles per step (33 steps), H=192:")
 for i, nm in names.items(): print("    %-28s %9.0f" % (nm, t[i] / 33.0))
