@@ -8,8 +8,10 @@
 //   1. the group's rows cover one contiguous span of the read arrays (rows are position-sorted), so the
 //      three byte streams (code, bq, mq) of the span are fetched with three bulk async copies
 //      (cp.async.bulk, completion on an mbarrier) into shared memory - full-line HBM reads, no LSU work;
-//   2. every thread walks the reads of its own row in shared memory and bumps private 16-bit
-//      counters kept field-major in shared memory (bank = thread, so no conflicts and no atomics);
+//   2. every thread walks the reads of its own row in shared memory and counts in REGISTERS: the three
+//      groups of eight base fields (MQ >= 20, MQ < 20, low BQ) are three 64-bit registers of 8-bit lanes,
+//      one shifted increment per read, flushed into 32-bit totals every 255 reads (round 1 kept 16-bit
+//      counters in shared memory: a load-add-store chain per read, 45 % issue utilisation);
 //   3. the rare indel-carrying reads come from a sparse side list and are resolved exactly (per-allele
 //      maximum, CT:184-187, 201-204) with a K^2 scan that has no table-size limit;
 //   4. the 34 int16 of each slot are staged in shared memory and the group's 8.8 KB output block is
@@ -26,7 +28,7 @@ constexpr int GROUP = 4;                          // candidates per CTA (4 CTAs 
 constexpr int SLOTS = GROUP * N_POS;              // 132
 constexpr int THREADS = 160;                      // 5 warps
 constexpr int STAGE_CAP = 10 * 1024;              // bytes per staged array
-constexpr int N_FIELDS = 26;                      // 18 set-A + 8 set-B counters
+constexpr int FLUSH = 255;                        // reads per pass of the 8-bit lane counters
 constexpr int OUT_BYTES = SLOTS * N_CH * 2;       // 8976
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -40,6 +42,41 @@ __device__ __forceinline__ int channel_of_a(int f) {
     return f + 8;                       // LMQ      -> 18..25
 }
 
+// Reads [lo, hi) of one row -> the 26 counters (CT:146-149, 160-221).  The same code for the staged (shared
+// memory) and the unstaged (global) arrays; the pointer type keeps the address space, so the staged instance
+// compiles to LDS.  One read = one shifted 64-bit increment `1 << 8*b8` added to up to two of the three lane
+// registers under a predicate; indel-carrying reads (bit 4 of the code) count nowhere here (CT:160-204).
+template <typename P>
+__device__ __forceinline__ void count_reads(P p_code, P p_bq, P p_mq, int lo, int hi, int low_bq_cut, int (&cnt)[26]) {
+    for (int base = lo; base < hi; base += FLUSH) {
+        const int end = min(hi, base + FLUSH);
+        unsigned long long a = 0, l = 0, b = 0;           // 8 x 8-bit lanes each: MQ >= 20 | MQ < 20 | low BQ
+        unsigned int sh = 0;                              // '*' in bits 0-15, '#' in bits 16-31
+        for (int i = base; i < end; ++i) {
+            const unsigned int c = p_code[i], m = p_mq[i], q = p_bq[i];
+            const unsigned int sym = c & 0xF;
+            const bool plain = !(c & 0x10);
+            const bool base8 = plain && (sym < 4 || (sym - 5u) < 4u);                  // A C G T a c g t
+            const unsigned int b8 = sym - (sym > 4 ? 1u : 0u);
+            const bool mq_hi = m >= (unsigned)MIN_MQ && m != (unsigned)QUAL_ABSENT;
+            const unsigned long long inc = base8 ? (1ull << (8 * b8)) : 0ull;
+            a += mq_hi ? inc : 0ull;
+            l += m < (unsigned)MIN_MQ ? inc : 0ull;                                    // CT:215-217
+            b += (q != (unsigned)QUAL_ABSENT && (int)q < low_bq_cut) ? inc : 0ull;     // CT:149, 219-221
+            sh += (plain && mq_hi && sym == 10) ? 1u : 0u;
+            sh += (plain && mq_hi && sym == 11) ? 0x10000u : 0u;
+        }
+        #pragma unroll
+        for (int f = 0; f < 8; ++f) {
+            cnt[f] += (int)((a >> (8 * f)) & 0xFF);
+            cnt[10 + f] += (int)((l >> (8 * f)) & 0xFF);
+            cnt[18 + f] += (int)((b >> (8 * f)) & 0xFF);
+        }
+        cnt[8] += (int)(sh & 0xFFFF);
+        cnt[9] += (int)(sh >> 16);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS)
 encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ bq,
                      const uint8_t* __restrict__ mq, const int32_t* __restrict__ pos_off,
@@ -51,8 +88,7 @@ encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict
     uint8_t* s_code = smem;
     uint8_t* s_bq = smem + STAGE_CAP;
     uint8_t* s_mq = smem + 2 * STAGE_CAP;
-    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem + 3 * STAGE_CAP);                 // [N_FIELDS][THREADS]
-    int16_t* s_out = reinterpret_cast<int16_t*>(smem + 3 * STAGE_CAP + N_FIELDS * THREADS * 2);   // [SLOTS][34]
+    int16_t* s_out = reinterpret_cast<int16_t*>(smem + 3 * STAGE_CAP);   // [SLOTS][34]
     __shared__ uint64_t s_bar;
     __shared__ int s_min_row, s_max_row;
 
@@ -68,8 +104,6 @@ encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    #pragma unroll
-    for (int f = 0; f < N_FIELDS; ++f) s_hist[f * THREADS + tid] = 0;
     __syncthreads();
     if (row >= 0) {
         // warp-aggregated min / max of the rows this group touches
@@ -142,30 +176,13 @@ encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict
             "ENC_DONE:\n\t"
             "}" ::"r"(smem_u32(&s_bar)) : "memory");
     }
-    const uint8_t* p_code = staged ? s_code : code;                  // generic pointers: smem or global
-    const uint8_t* p_bq = staged ? s_bq : bq;
-    const uint8_t* p_mq = staged ? s_mq : mq;
-    const int shift = staged ? (int)a_lo : 0;
-    lo -= shift;
-    hi -= shift;
-
-    uint16_t* my = s_hist + tid;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t c = p_code[i];
-        if (c & 0x10) continue;                                       // indel-carrying read (CT:160-204)
-        const uint32_t sym = c & 0xF;
-        const uint32_t m = p_mq[i], q = p_bq[i];
-        int b8 = -1;
-        if (sym < 4) b8 = sym;
-        else if (sym >= 5 && sym <= 8) b8 = sym - 1;
-        int fa = -1;
-        if (m != QUAL_ABSENT) {
-            if (m >= MIN_MQ) fa = b8 >= 0 ? b8 : (sym == 10 ? 8 : (sym == 11 ? 9 : -1));
-            else if (b8 >= 0) fa = 10 + b8;                           // CT:215-217
-        }
-        if (fa >= 0) my[fa * THREADS] += 1;
-        if (b8 >= 0 && q != QUAL_ABSENT && (int)q < low_bq_cut) my[(18 + b8) * THREADS] += 1;   // CT:149, 219-221
-    }
+    // counts of this slot: cnt[0..7] = A C G T a c g t with MQ >= 20, cnt[8] = '*', cnt[9] = '#',
+    // cnt[10..17] = the eight bases with MQ < 20, cnt[18..25] = the eight bases with BQ < low_bq_cut
+    int cnt[26];
+    #pragma unroll
+    for (int f = 0; f < 26; ++f) cnt[f] = 0;
+    if (staged) count_reads(s_code, s_bq, s_mq, lo - (int)a_lo, hi - (int)a_lo, low_bq_cut, cnt);
+    else count_reads(code, bq, mq, lo, hi, low_bq_cut, cnt);
 
     if (tid < SLOTS) {
         int16_t* o = s_out + tid * N_CH;
@@ -174,9 +191,9 @@ encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict
         for (int ch = 0; ch < N_CH; ++ch) v[ch] = 0;
         if (row >= 0) {
             #pragma unroll
-            for (int f = 0; f < 18; ++f) v[channel_of_a(f)] = my[f * THREADS];
+            for (int f = 0; f < 18; ++f) v[channel_of_a(f)] = cnt[f];
             #pragma unroll
-            for (int f = 0; f < 8; ++f) v[26 + f] = my[(18 + f) * THREADS];
+            for (int f = 0; f < 8; ++f) v[26 + f] = cnt[18 + f];
             v[4] = tot[0]; v[6] = tot[1]; v[13] = tot[2]; v[15] = tot[3];           // I D i d
             v[5] = best[0]; v[7] = best[1]; v[14] = best[2]; v[16] = best[3];       // I1 D1 i1 d1 (CT:210-213)
             if (depth_out && (slot % N_POS) == CENTER) {                            // depth of alt_info (CT:208)
@@ -223,7 +240,7 @@ encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict
     }
 }
 
-constexpr int SMEM_BYTES = 3 * STAGE_CAP + N_FIELDS * THREADS * 2 + SLOTS * N_CH * 2 + 16;
+constexpr int SMEM_BYTES = 3 * STAGE_CAP + SLOTS * N_CH * 2 + 16;
 
 }  // namespace enc
 
