@@ -98,6 +98,7 @@ int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
         m.sz_q = std::max<int64_t>(m.sz_q, (int64_t)st.wout * inner);
         m.sz_kv = std::max<int64_t>(m.sz_kv, (int64_t)st.wkv * 2 * inner);
         m.sz_ff = std::max<int64_t>(m.sz_ff, (int64_t)st.wout * 4 * c);
+        m.sz_col = std::max<int64_t>(m.sz_col, (int64_t)st.wout * 3 * cin);
         cin = c;
         win = st.wout;
     }
@@ -187,9 +188,9 @@ int engine_alloc(Engine& e, int64_t max_batch) {
     rc |= dev_alloc(e, &e.a_att, b * a.sz_q);
     rc |= dev_alloc(e, &e.a_ff, b * a.sz_ff);
     {
-        const int64_t sizes[5] = {b * a.sz_x, b * a.sz_kvin, b * a.sz_q, b * a.sz_x, b * a.sz_ff};
-        uint16_t** ptrs[5] = {e.p_dq, e.p_dkv, e.p_att, e.p_y, e.p_ff};
-        for (int i = 0; i < 5 && !rc; ++i)
+        const int64_t sizes[6] = {b * a.sz_x, b * a.sz_kvin, b * a.sz_q, b * a.sz_x, b * a.sz_ff, b * a.sz_col};
+        uint16_t** ptrs[6] = {e.p_dq, e.p_dkv, e.p_att, e.p_y, e.p_ff, e.p_col};
+        for (int i = 0; i < 6 && !rc; ++i)
             for (int h = 0; h < 2 && !rc; ++h) {
                 float* p = nullptr;
                 rc |= dev_alloc(e, &p, (sizes[i] + 1) / 2);
@@ -362,6 +363,18 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
             continue;
         }
         // embed conv (3-tap, stride 2, pad 1) + channel LN  (clairs/model.py:195-196)
+        if (e.use_tc && c % 64 == 0 && (3 * st.cin) % 8 == 0) {
+            // tensor-core stages: explicit conv rows as split planes (one small kernel), then a pre-split GEMM
+            RUN(prof_begin(e, PK_AFF_EMBED, s));
+            RUN(launch_im2col3_split(cur, n, st.win, st.wout, st.cin, e.p_col[0], e.p_col[1], s));
+            GemmTc g;
+            g.flags = GEMM_A_PRESPLIT;
+            g.a_hi = e.p_col[0]; g.a_mid = e.p_col[1]; g.lda = 3 * st.cin;
+            g.w_hi = m.ws.bhi + (st.embed_w - m.ws.blob); g.w_mid = m.ws.bmid + (st.embed_w - m.ws.blob); g.ldw = 3 * st.cin;
+            g.bias = st.embed_b; g.c = e.a_t0; g.ldc = c; g.m = rows; g.n = c; g.k = 3 * st.cin;
+            RUN(launch_gemm_tc_ex(g, s));
+            RUN(prof_end(e, s));
+        } else
         TIMED(PK_AFF_EMBED, gemm(e, conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows,
                                  c, 3 * st.cin, ACT_NONE, s));
         TIMED(PK_AFF_LN, launch_channel_ln(e.a_t0, st.ln_g, st.ln_b, e.a_xs, rows, c, s));

@@ -44,7 +44,7 @@ struct AffModel {
     HeadW head;
     WeightSet ws;
     // per-candidate workspace sizes (floats)
-    int64_t sz_x = 0, sz_kvin = 0, sz_q = 0, sz_kv = 0, sz_ff = 0;
+    int64_t sz_x = 0, sz_kvin = 0, sz_q = 0, sz_kv = 0, sz_ff = 0, sz_col = 0;
 };
 
 struct GruLayerW {
@@ -71,7 +71,7 @@ struct Engine {
     float *a_q = nullptr, *a_kv = nullptr, *a_att = nullptr, *a_ff = nullptr;
     // tensor-core AFF path: bf16 hi / mid planes of every tensor that only feeds a GEMM (index 0 = hi, 1 = mid)
     uint16_t *p_dq[2] = {nullptr, nullptr}, *p_dkv[2] = {nullptr, nullptr}, *p_att[2] = {nullptr, nullptr},
-             *p_y[2] = {nullptr, nullptr}, *p_ff[2] = {nullptr, nullptr};
+             *p_y[2] = {nullptr, nullptr}, *p_ff[2] = {nullptr, nullptr}, *p_col[2] = {nullptr, nullptr};
     float *n_xp = nullptr, *n_o1 = nullptr, *n_o2 = nullptr;
     // tensor-core NEG path: bf16 hi / mid planes. x and o1 are time-major [33, bp, .] (operands of the transposed
     // input projections), o2 is batch-major [n, 33 * 2H] (A operand of the flattening fc1); bp = chunk rounded up to 128

@@ -166,6 +166,43 @@ int launch_split_time_major(const float* x, int64_t n, int t_len, int ld_in, int
     return 0;
 }
 
+// Rows of the 3-tap / stride-2 / pad-1 embed convolution (M:195 on H=1 maps) as an explicit matrix, written as bf16
+// hi / mid planes [n * wout, 3 * cin] so that the convolution runs as a pre-split tensor-core GEMM.  One thread per
+// four channels of one tap.
+__global__ void im2col3_split_kernel(const float* __restrict__ x, int64_t n, int win, int wout, int cin,
+                                     uint16_t* __restrict__ hi, uint16_t* __restrict__ mid) {
+    const int q4 = cin / 4;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * wout * 3 * q4) return;
+    const int c4 = (int)(i % q4);
+    const int64_t r3 = i / q4;                          // (b * wout + w) * 3 + tap
+    const int tap = (int)(r3 % 3);
+    const int64_t row = r3 / 3;
+    const int w = (int)(row % wout);
+    const int64_t b = row / wout;
+    const int pos = 2 * w - 1 + tap;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos >= 0 && pos < win) v = *reinterpret_cast<const float4*>(x + (b * win + pos) * cin + 4 * c4);
+    uint32_t h0, h1, m0, m1;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v.w), "f"(v.z));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m0) : "f"(v.y - __uint_as_float(h0 & 0xFFFF0000u)), "f"(v.x - __uint_as_float(h0 << 16)));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m1) : "f"(v.w - __uint_as_float(h1 & 0xFFFF0000u)), "f"(v.z - __uint_as_float(h1 << 16)));
+    const int64_t o = r3 * cin + 4 * c4;                // = row * 3 * cin + tap * cin + 4 * c4
+    *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(mid + o) = make_uint2(m0, m1);
+}
+
+int launch_im2col3_split(const float* x, int64_t n, int win, int wout, int cin, uint16_t* hi, uint16_t* mid, cudaStream_t s) {
+    if (n <= 0) return 0;
+    CTO_REQUIRE(cin % 4 == 0 && wout == (win + 1) / 2, "im2col3: cin %d / win %d / wout %d", cin, win, wout);
+    const int64_t total = n * wout * 3 * (cin / 4);
+    im2col3_split_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, n, win, wout, cin, hi, mid);
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 // strand-count recovery (P:626-642): centre row, forward cols 0:4, reverse cols 9:13
 __global__ void strand_counts_kernel(const int16_t* __restrict__ x, int64_t n, int32_t* __restrict__ fwd,
                                      int32_t* __restrict__ rev) {

@@ -53,6 +53,8 @@ int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s);
 
 // ld_out >= 34: row stride of the fp32 output (extra columns are zero-filled)
 int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, int ld_out, cudaStream_t s);
+// fp32 [n, win, cin] -> rows of the 3-tap / stride-2 / pad-1 convolution as bf16 hi / mid planes [n * wout, 3 * cin]
+int launch_im2col3_split(const float* x, int64_t n, int win, int wout, int cin, uint16_t* hi, uint16_t* mid, cudaStream_t s);
 constexpr int NEG_PLANE_LD = 40;   // row stride of the NEG input planes (34 channels + zeros; = engine.cuh NEG_IN_LD)
 // int16 tensor -> rescaled NEG input written directly as time-major bf16 hi / mid planes [33, bp, 40]
 int launch_rescale_split_time_major(const int16_t* x, const int32_t* depth, int64_t n, int64_t bp, uint16_t* hi, uint16_t* mid,
