@@ -156,6 +156,24 @@ int neg_load(NegModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
                         }
         if (upload(blk.data(), (int64_t)blk.size(), m.whh_pair[l], SPLIT_BF16)) return 1;
     }
+    m.fuse_l1 = m.l[0].hidden == 128 && m.l[0].in_dim < NEG_IN_LD;
+    if (m.fuse_l1) {   // W_ih of layer 1 in the row order of whh_pair, K = 64, the (folded) input bias in column in_dim
+        const int h = m.l[0].hidden, k = m.l[0].in_dim;
+        const float* wih = host_blob + (m.l[0].wih - m.ws.blob);       // [2 * 3H (dir, gate, unit)][in_dim]
+        const float* bih = host_blob + (m.l[0].bih - m.ws.blob);
+        std::vector<float> win((size_t)2 * 3 * h * 64, 0.0f);
+        for (int d = 0; d < 2; ++d)
+            for (int b = 0; b < h / 32; ++b)
+                for (int hf = 0; hf < 2; ++hf)
+                    for (int g = 0; g < 3; ++g)
+                        for (int j = 0; j < 16; ++j) {
+                            const size_t row = (size_t)d * 3 * h + b * 96 + hf * 48 + g * 16 + j;
+                            const size_t src = (size_t)d * 3 * h + g * h + b * 32 + hf * 16 + j;
+                            for (int c = 0; c < k; ++c) win[row * 64 + c] = wih[src * k + c];
+                            win[row * 64 + k] = bih[src];
+                        }
+        if (upload(win.data(), (int64_t)win.size(), m.win_pair, SPLIT_BF16)) return 1;
+    }
     return 0;
 }
 
@@ -230,6 +248,7 @@ void engine_free(Engine& e) {
     release(e.aff.ws);
     release(e.neg.ws);
     release(e.neg.wih1_pad);
+    release(e.neg.win_pair);
     release(e.neg.whh_pair[0]);
     release(e.neg.whh_pair[1]);
     if (e.tables) cudaFree(e.tables);
@@ -252,7 +271,7 @@ double prof_kind_flops_per_candidate(const Engine& e, int kind) {
     const double t = N_POS;
     switch (kind) {
         case PK_NEG_PROJ1: return 2.0 * t * l[0].in_dim * 6 * l[0].hidden;
-        case PK_NEG_GRU1: return 2.0 * t * l[0].hidden * 6 * l[0].hidden;
+        case PK_NEG_GRU1: return 2.0 * t * l[0].hidden * 6 * l[0].hidden + (e.neg.fuse_l1 && e.use_tc ? 2.0 * t * l[0].in_dim * 6 * l[0].hidden : 0.0);
         case PK_NEG_PROJ2: return 2.0 * t * l[1].in_dim * 6 * l[1].hidden;
         case PK_NEG_GRU2: return 2.0 * t * l[1].hidden * 6 * l[1].hidden;
         case PK_NEG_FC1: return 2.0 * t * 2 * l[1].hidden * FC_DIM;
@@ -448,18 +467,27 @@ static int neg_forward_tc(Engine& e, const float* x, int64_t n, float* logits, c
     const int64_t bp = (n + 127) / 128 * 128, ldx = (int64_t)N_POS * bp;
     CTO_REQUIRE(bp <= e.bp_max, "neg_forward: batch %lld > workspace", (long long)n);
     const int h1 = m.l[0].hidden, h2 = m.l[1].hidden;
-    RUN(prof_begin(e, PK_NEG_PROJ1, s));
-    if (x) RUN(launch_split_time_major(x, n, N_POS, NEG_IN_LD, bp, e.nx_hi, e.nx_mid, s));
+    // the input planes carry a constant 1.0 in column in_dim when layer 1 runs fused (its bias rides in W_ih)
+    if (x) RUN(launch_split_time_major(x, n, N_POS, NEG_IN_LD, bp, e.nx_hi, e.nx_mid, s, m.fuse_l1 ? m.l[0].in_dim : -1));
     GemmTc g;
     g.flags = GEMM_A_PRESPLIT | GEMM_BIAS_PER_ROW | GEMM_TILES_N_MAJOR;
-    g.a_hi = m.wih1_pad.bhi; g.a_mid = m.wih1_pad.bmid; g.lda = NEG_IN_LD;
-    g.w_hi = e.nx_hi; g.w_mid = e.nx_mid; g.ldw = NEG_IN_LD;
-    g.bias = m.l[0].bih; g.c = e.n_xp; g.ldc = ldx; g.m = 6 * h1; g.n = (int)ldx; g.k = NEG_IN_LD;
-    RUN(launch_gemm_tc_ex(g, s));
-    RUN(prof_end(e, s));
-    RUN(prof_begin(e, PK_NEG_GRU1, s));
-    RUN(launch_gru3(e.n_xp, ldx, bp, m.whh_pair[0].bhi, m.whh_pair[0].bmid, m.l[0].bhn, e.o1_hi, e.o1_mid, 1, bp, n, h1, s));
-    RUN(prof_end(e, s));
+    g.c = e.n_xp; g.ldc = ldx; g.n = (int)ldx;
+    if (m.fuse_l1) {
+        RUN(prof_begin(e, PK_NEG_GRU1, s));
+        RUN(launch_gru1_fused(e.nx_hi, e.nx_mid, NEG_IN_LD, bp, m.win_pair.bhi, m.win_pair.bmid, m.whh_pair[0].bhi,
+                              m.whh_pair[0].bmid, m.l[0].bhn, e.o1_hi, e.o1_mid, 1, bp, n, h1, s));
+        RUN(prof_end(e, s));
+    } else {
+        RUN(prof_begin(e, PK_NEG_PROJ1, s));
+        g.a_hi = m.wih1_pad.bhi; g.a_mid = m.wih1_pad.bmid; g.lda = NEG_IN_LD;
+        g.w_hi = e.nx_hi; g.w_mid = e.nx_mid; g.ldw = NEG_IN_LD;
+        g.bias = m.l[0].bih; g.m = 6 * h1; g.k = NEG_IN_LD;
+        RUN(launch_gemm_tc_ex(g, s));
+        RUN(prof_end(e, s));
+        RUN(prof_begin(e, PK_NEG_GRU1, s));
+        RUN(launch_gru3(e.n_xp, ldx, bp, m.whh_pair[0].bhi, m.whh_pair[0].bmid, m.l[0].bhn, e.o1_hi, e.o1_mid, 1, bp, n, h1, s));
+        RUN(prof_end(e, s));
+    }
     RUN(prof_begin(e, PK_NEG_PROJ2, s));
     const int64_t off2 = m.l[1].wih - m.ws.blob;
     g.a_hi = m.ws.bhi + off2; g.a_mid = m.ws.bmid + off2; g.lda = 2 * h1;
@@ -492,7 +520,10 @@ int neg_forward_from_counts(Engine& e, const int16_t* x, const int32_t* depth, i
     CTO_REQUIRE(n <= e.max_batch, "neg_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
     static_assert(NEG_IN_LD == NEG_PLANE_LD, "plane row stride");
     if (e.use_tc) {
-        RUN(launch_rescale_split_time_major(x, depth, n, (n + 127) / 128 * 128, e.nx_hi, e.nx_mid, s));
+        RUN(prof_begin(e, PK_NEG_PROJ1, s));               // "proj1" family = producing the layer-1 input planes
+        RUN(launch_rescale_split_time_major(x, depth, n, (n + 127) / 128 * 128, e.nx_hi, e.nx_mid, s,
+                                            e.neg.fuse_l1 ? e.neg.l[0].in_dim : -1));
+        RUN(prof_end(e, s));
         return neg_forward_tc(e, nullptr, n, logits, s);
     }
     RUN(launch_rescale(x, depth, n, e.x_neg, NEG_IN_LD, s));

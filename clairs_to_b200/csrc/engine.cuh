@@ -59,6 +59,8 @@ struct NegModel {
     WeightSet ws;
     WeightSet wih1_pad;        // layer-1 W_ih with K padded 34 -> NEG_IN_LD (zeros), for the tensor-core path
     WeightSet whh_pair[2];     // per layer: W_hh [2 dirs][unit block (32) x half (16) x gate x unit][H], for gru_tc3.cu
+    WeightSet win_pair;        // layer 1: W_ih in the same row order, K padded to 64, bias in column in_dim (gru_in_tc.cu)
+    bool fuse_l1 = false;      // layer 1 runs with its input projection fused into the recurrence kernel
 };
 
 struct Engine {

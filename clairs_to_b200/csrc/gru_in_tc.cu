@@ -1,0 +1,345 @@
+// First GRU layer with its input projection fused in (H = 128, input width <= 39 + bias column).
+//
+// gru_tc3.cu reads the input projection W_ih x_t + b from HBM: for layer 1 that tensor is 10 GB per 100 000
+// candidates, written by a GEMM whose K is only 34 and read back once.  Here the projection is part of the
+// recurrence step: the step's MMAs are   acc[r|z|n_h] = h_{t-1} W_hh^T   (K = 128)   followed by
+// acc[r|z] += x_t W_i{r,z}^T   and   acc[n_x] = x_t W_in^T   (K = 48: 34 channels, a constant-one column that
+// carries the biases, zero padding), all as bf16x3 split products on a CTA pair (tcgen05 cta_group::2).
+// With H = 128 every weight of one direction fits in shared memory (W_hh half 96 KB + W_ih half 48 KB per CTA), so
+// nothing is streamed but the 16 KB x_t tile per step: no W ring, no projection ring.
+//
+// Arithmetic, thread mapping of the gate math, TMEM lane layout, the h tiles and the output planes are those of
+// gru_tc3.cu (torch.nn.GRU semantics, clairs/model.py:412-417); see there.
+#include "gru_ptx.cuh"
+
+namespace cto {
+
+namespace tc {
+
+constexpr int F_H = 128;
+constexpr int F_M = 64;                      // candidates per CTA
+constexpr int F_NB = F_H / 32;               // 4 blocks of 32 hidden units
+constexpr int F_KB = F_H / 64;               // 2 k-blocks of the recurrent product
+constexpr int F_HALF = 48;                   // B rows / accumulator columns per CTA and block: r16 z16 n16
+constexpr int F_HTILE = F_M * 128;           // 8 KB: 64 rows x 64 k (bf16)
+constexpr int F_WTILE = F_HALF * 128;        // 6 KB
+constexpr int F_HBUF = 2 * F_KB * F_HTILE;   // hi | mid tiles of one h_t: 32 KB
+constexpr int F_WHH = F_NB * F_KB * 2 * F_WTILE;   // 96 KB: [blk][kb][hi | mid]
+constexpr int F_WIN = F_NB * 2 * F_WTILE;          // 48 KB: [blk][hi | mid], K padded to 64
+constexpr int F_XS = 2 * F_HTILE;                  // 16 KB: x_t hi | mid
+constexpr int F_KIN_STEPS = 3;               // K = 48 covers the 34 channels and the bias column
+constexpr int F_XN_COL = F_NB * F_HALF;      // TMEM column of the n_x accumulators (16 per block)
+constexpr int F_THREADS = 320;               // warp 0 loader, warp 1 MMA, 8 gate-math warps
+constexpr int F_SMEM = 2 * F_HBUF + F_WHH + F_WIN + F_XS + 1024 + 128 + F_H * 4;
+constexpr uint32_t F_PEER_MASK = 0xFEFFFFFFu;
+
+__device__ __forceinline__ void f_tma_load_2sm(const CUtensorMap* map, uint64_t* leader_bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(g_smem_u32(dst)), "l"(map), "r"(g_smem_u32(leader_bar) & F_PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void f_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void f_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(g_smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void f_arrive_leader(uint64_t* bar) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(g_smem_u32(bar)));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void f_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "FW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FW_DONE;\n\t"
+        "bra FW_LOOP;\n\t"
+        "FW_DONE:\n\t"
+        "}" ::"r"(g_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t f_pack(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void f_split2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
+    hi = f_pack(x0, x1);
+    mid = f_pack(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xFFFF0000u));
+}
+// D=f32, A=B=bf16, K-major, M=128 (64 rows per CTA), N=n
+__device__ __forceinline__ uint32_t f_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+gru1_fused_kernel(const __grid_constant__ CUtensorMap tma_whh_hi, const __grid_constant__ CUtensorMap tma_whh_mid,
+                  const __grid_constant__ CUtensorMap tma_win_hi, const __grid_constant__ CUtensorMap tma_win_mid,
+                  const __grid_constant__ CUtensorMap tma_x_hi, const __grid_constant__ CUtensorMap tma_x_mid, int64_t bp,
+                  const float* __restrict__ bhn, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_mid, int64_t osb,
+                  int64_t ost, int64_t batch) {
+    constexpr int ITERS = 4;                               // 8-unit half-blocks per gate thread (two gate warps per quadrant)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (g_smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* hbuf = base;                                  // [2 buffers][hi | mid][KB][64 x 128 B]
+    uint8_t* whh = base + 2 * F_HBUF;                      // [blk][kb][hi | mid][48 x 128 B]   resident
+    uint8_t* win = whh + F_WHH;                            // [blk][hi | mid][48 x 128 B]       resident
+    uint8_t* xs = win + F_WIN;                             // [hi | mid][64 x 128 B]            x_t of this CTA's candidates
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(xs + F_XS);
+    uint64_t* xfull = wfull + 1;                           // leader: both CTAs' x_t tiles have landed
+    uint64_t* xempty = xfull + 1;                          // the step's input MMAs have retired (multicast commit)
+    uint64_t* acc_full = xempty + 1;                       // [2]: block pairs
+    uint64_t* h_ready = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
+    float* s_bhn = reinterpret_cast<float*>(wfull + 8);    // 64 bytes after the barriers: 16-byte aligned
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y;
+    const uint32_t crank = g_cluster_rank();
+    const bool leader = crank == 0;
+    for (int i = threadIdx.x; i < F_H; i += F_THREADS) s_bhn[i] = bhn[dir * F_H + i];
+
+    if (threadIdx.x == 0) {
+        g_mbar_init(wfull, 1);
+        g_mbar_init(xfull, 1);
+        g_mbar_init(xempty, 1);
+        g_mbar_init(&acc_full[0], 1);
+        g_mbar_init(&acc_full[1], 1);
+        g_mbar_init(h_ready, 2 * 8);                       // one arrive per gate-math warp of BOTH CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    // resident weights: this CTA's half (48 rows) of every W_hh / W_ih block, once
+    if (warp == 0) {
+        if (g_elect_one()) {
+            g_mbar_expect_tx(wfull, F_WHH + F_WIN);
+            const int row0 = dir * 3 * F_H + (int)crank * F_HALF;
+            for (int blk = 0; blk < F_NB; ++blk) {
+                for (int kb = 0; kb < F_KB; ++kb) {
+                    g_tma_load_2d(&tma_whh_hi, wfull, whh + ((blk * F_KB + kb) * 2) * F_WTILE, kb * 64, row0 + blk * 96);
+                    g_tma_load_2d(&tma_whh_mid, wfull, whh + ((blk * F_KB + kb) * 2 + 1) * F_WTILE, kb * 64, row0 + blk * 96);
+                }
+                g_tma_load_2d(&tma_win_hi, wfull, win + (blk * 2) * F_WTILE, 0, row0 + blk * 96);
+                g_tma_load_2d(&tma_win_mid, wfull, win + (blk * 2 + 1) * F_WTILE, 0, row0 + blk * 96);
+            }
+        }
+        __syncwarp();
+        g_mbar_wait(wfull, 0);
+    }
+    __syncthreads();
+    g_cluster_sync();                                      // both CTAs hold their weights; barriers and TMEM are set up
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- x_t loader: one 64-candidate x 64-column bf16 tile (hi, mid) per step; both CTAs signal the leader ----
+        const int b0 = (int)blockIdx.x * F_M;
+        for (int step = 0; step < N_POS; ++step) {
+            const int t = dir ? (N_POS - 1 - step) : step;
+            g_mbar_wait(xempty, (step & 1) ^ 1);
+            if (g_elect_one()) {
+                if (leader) g_mbar_expect_tx(xfull, 2 * F_XS);
+                f_tma_load_2sm(&tma_x_hi, xfull, xs, 0, (int)(t * bp) + b0);
+                f_tma_load_2sm(&tma_x_mid, xfull, xs + F_HTILE, 0, (int)(t * bp) + b0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        if (leader) {                                      // ---- MMA issuer (leader CTA only; warp-uniform loop) ----
+            const uint32_t id96 = f_idesc(96), id64 = f_idesc(64), id32 = f_idesc(32);
+            for (int step = 0; step < N_POS; ++step) {
+                f_wait_cluster(h_ready, step & 1);         // h_{t-1} in BOTH shared memories, accumulators drained
+                g_mbar_wait(xfull, step & 1);              // x_t in BOTH shared memories
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint8_t* hb = hbuf + (step & 1) * F_HBUF;
+                const uint64_t d_xhi = g_desc_k_sw128(g_smem_u32(xs)), d_xmid = g_desc_k_sw128(g_smem_u32(xs + F_HTILE));
+                for (int blk = 0; blk < F_NB; ++blk) {
+                    const uint32_t acc = tmem_base + (uint32_t)(blk * F_HALF);
+                    const uint32_t accx = tmem_base + (uint32_t)(F_XN_COL + blk * 16);
+                    const uint64_t d_ihi = g_desc_k_sw128(g_smem_u32(win + (blk * 2) * F_WTILE));
+                    const uint64_t d_imid = g_desc_k_sw128(g_smem_u32(win + (blk * 2 + 1) * F_WTILE));
+                    constexpr uint64_t NROW = (32 * 128) >> 4;      // the n rows follow the 32 r,z rows of a 48-row tile
+                    if (g_elect_one()) {
+                        #pragma unroll
+                        for (int kb = 0; kb < F_KB; ++kb) {         // recurrent part, K = 128, all three gates (N = 96)
+                            const uint64_t d_hhi = g_desc_k_sw128(g_smem_u32(hb + kb * F_HTILE));
+                            const uint64_t d_hmid = g_desc_k_sw128(g_smem_u32(hb + (F_KB + kb) * F_HTILE));
+                            const uint64_t d_whi = g_desc_k_sw128(g_smem_u32(whh + ((blk * F_KB + kb) * 2) * F_WTILE));
+                            const uint64_t d_wmid = g_desc_k_sw128(g_smem_u32(whh + ((blk * F_KB + kb) * 2 + 1) * F_WTILE));
+                            #pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t o = (uint64_t)(k * 2);
+                                f_mma(acc, d_hhi + o, d_whi + o, id96, (kb | k) ? 1u : 0u);
+                                f_mma(acc, d_hmid + o, d_whi + o, id96, 1u);
+                                f_mma(acc, d_hhi + o, d_wmid + o, id96, 1u);
+                            }
+                        }
+                        #pragma unroll
+                        for (int k = 0; k < F_KIN_STEPS; ++k) {     // input part, K = 48: r,z on top (N = 64), n_x apart (N = 32)
+                            const uint64_t o = (uint64_t)(k * 2);
+                            f_mma(acc, d_xhi + o, d_ihi + o, id64, 1u);
+                            f_mma(acc, d_xmid + o, d_ihi + o, id64, 1u);
+                            f_mma(acc, d_xhi + o, d_imid + o, id64, 1u);
+                            f_mma(accx, d_xhi + o, d_ihi + NROW + o, id32, k ? 1u : 0u);
+                            f_mma(accx, d_xmid + o, d_ihi + NROW + o, id32, 1u);
+                            f_mma(accx, d_xhi + o, d_imid + NROW + o, id32, 1u);
+                        }
+                        if (blk & 1) f_commit_2sm(&acc_full[blk >> 1]);
+                        if (blk == F_NB - 1) f_commit_2sm(xempty);   // x_t consumed in both CTAs
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {                                               // ---- gate math: warps 2..9 in both CTAs ----
+        const int quad = warp & 3;                         // TMEM lanes [32*quad, +32)
+        const int wsel = (warp - 2) >> 2;                  // 0..1: half-blocks wsel, wsel+2, wsel+4, wsel+6
+        const int tl = quad * 32 + lane;
+        const int m = tl & 63;                             // candidate row inside the CTA
+        const int uhalf = tl >> 6;                         // units [16*uhalf, +16) of each block
+        const int64_t b = ((int64_t)blockIdx.x) * F_M + m;
+        const bool b_ok = b < batch;
+        const uint32_t row_off = (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+        auto unit0 = [&](int j) { const int hb = wsel + 2 * j; return (hb >> 1) * 32 + uhalf * 16 + (hb & 1) * 8; };
+        auto tile_off = [&](int j) {
+            const int uu = unit0(j);
+            return (uint32_t)((uu / 64) * F_HTILE) + row_off + (uint32_t)(((((uu % 64) >> 3)) ^ (m & 7)) << 4);
+        };
+        float hk[ITERS * 8];                               // fp32 state of this thread's units
+        #pragma unroll
+        for (int j = 0; j < ITERS; ++j) {                  // h_0 = 0
+            #pragma unroll
+            for (int c = 0; c < 8; ++c) hk[j * 8 + c] = 0.0f;
+            *reinterpret_cast<uint4*>(hbuf + tile_off(j)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(hbuf + F_KB * F_HTILE + tile_off(j)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) f_arrive_leader(h_ready);
+
+        for (int step = 0; step < N_POS; ++step) {
+            const int t = dir ? (N_POS - 1 - step) : step;
+            const int64_t orow = (b * osb + t * ost) * (int64_t)(2 * F_H) + dir * F_H;
+            uint8_t* hnext = hbuf + ((step + 1) & 1) * F_HBUF;
+            #pragma unroll
+            for (int j = 0; j < ITERS; ++j) {
+                const int hb = wsel + 2 * j;
+                const int blk = hb >> 1;
+                const int uu = unit0(j);
+                const uint32_t lanes = (uint32_t)(quad * 32) << 16;
+                const uint32_t tcol = tmem_base + lanes + (uint32_t)(blk * F_HALF + (hb & 1) * 8);
+                const uint32_t xcol = tmem_base + lanes + (uint32_t)(F_XN_COL + blk * 16 + (hb & 1) * 8);
+                g_mbar_wait(&acc_full[blk >> 1], step & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t ar[8], az[8], an[8], ax[8];
+                g_tmem_ld8(tcol, ar);                      // W_hr h + W_ir x + b_r
+                g_tmem_ld8(tcol + 16, az);                 // W_hz h + W_iz x + b_z
+                g_tmem_ld8(tcol + 32, an);                 // W_hn h
+                g_tmem_ld8(xcol, ax);                      // W_in x + b_in
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const float4 bn0 = *reinterpret_cast<const float4*>(s_bhn + uu);
+                const float4 bn1 = *reinterpret_cast<const float4*>(s_bhn + uu + 4);
+                const float bnv[8] = {bn0.x, bn0.y, bn0.z, bn0.w, bn1.x, bn1.y, bn1.z, bn1.w};
+                #pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    // five MUFU ops per element: z = 1 / (1 + ez) and n = 1 - 2 / (en + 1) share one reciprocal (gru_tc3.cu)
+                    const float r = g_sigmoid(__uint_as_float(ar[c]));
+                    const float xz = fminf(fmaxf(__uint_as_float(az[c]), -30.0f), 30.0f);
+                    const float y = fminf(fmaxf(__uint_as_float(ax[c]) + r * (__uint_as_float(an[c]) + bnv[c]), -15.0f), 15.0f);
+                    const float dz = 1.0f + __expf(-xz), dn = __expf(2.0f * y) + 1.0f;
+                    const float inv = __fdividef(1.0f, dz * dn);
+                    const float z = dn * inv;
+                    const float n = 1.0f - 2.0f * dz * inv;
+                    hk[j * 8 + c] = (1.0f - z) * n + z * hk[j * 8 + c];
+                }
+                const float* hv = hk + j * 8;
+                uint4 hi, mid;
+                f_split2(hv[0], hv[1], hi.x, mid.x);
+                f_split2(hv[2], hv[3], hi.y, mid.y);
+                f_split2(hv[4], hv[5], hi.z, mid.z);
+                f_split2(hv[6], hv[7], hi.w, mid.w);
+                const uint32_t to = tile_off(j);
+                *reinterpret_cast<uint4*>(hnext + to) = hi;
+                *reinterpret_cast<uint4*>(hnext + F_KB * F_HTILE + to) = mid;
+                if (b_ok) {                                // pre-split output: an operand of the next projection GEMM
+                    *reinterpret_cast<uint4*>(out_hi + orow + uu) = hi;
+                    *reinterpret_cast<uint4*>(out_mid + orow + uu) = mid;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) f_arrive_leader(h_ready);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    g_cluster_sync();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
+}  // namespace tc
+
+// x_hi / x_mid:   bf16 planes of the layer input, time-major [33, bp, ldx] with a constant 1.0 in column `in_dim`
+// win_hi / _mid:  [2 directions][(32-unit block, 16-unit half, gate, unit) rows][64] bf16: W_ih, the bias in column
+//                 `in_dim`, zeros beyond;   whh_hi / _mid: as for launch_gru3
+// out_hi / _mid:  bf16 split of h_t, row (b * osb + t * ost) of [.., 256]
+int launch_gru1_fused(const uint16_t* x_hi, const uint16_t* x_mid, int ldx, int64_t bp, const uint16_t* win_hi,
+                      const uint16_t* win_mid, const uint16_t* whh_hi, const uint16_t* whh_mid, const float* bhn,
+                      uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch, int hidden,
+                      cudaStream_t s) {
+    if (batch <= 0) return 0;
+    CTO_REQUIRE(hidden == tc::F_H, "gru1_fused: hidden size %d (only %d is built)", hidden, tc::F_H);
+    CTO_REQUIRE(x_hi && x_mid && out_hi && out_mid && bp % 128 == 0 && bp >= batch && ldx % 8 == 0 && ldx <= 64 &&
+                    (int64_t)N_POS * bp < (1ll << 31),
+                "gru1_fused: bad buffers / padding");
+    CUtensorMap m_whh_hi, m_whh_mid, m_win_hi, m_win_mid, m_x_hi, m_x_mid;
+    if (tc::make_map_bf16(&m_whh_hi, whh_hi, 6 * hidden, hidden, hidden, tc::F_HALF)) return 1;
+    if (tc::make_map_bf16(&m_whh_mid, whh_mid, 6 * hidden, hidden, hidden, tc::F_HALF)) return 1;
+    if (tc::make_map_bf16(&m_win_hi, win_hi, 6 * hidden, 64, 64, tc::F_HALF)) return 1;
+    if (tc::make_map_bf16(&m_win_mid, win_mid, 6 * hidden, 64, 64, tc::F_HALF)) return 1;
+    // columns beyond ldx are out of bounds of the map: the 64-wide box is zero-filled there
+    if (tc::make_map_bf16(&m_x_hi, x_hi, (int64_t)N_POS * bp, ldx, ldx, tc::F_M)) return 1;
+    if (tc::make_map_bf16(&m_x_mid, x_mid, (int64_t)N_POS * bp, ldx, ldx, tc::F_M)) return 1;
+    static bool attr = false;
+    if (!attr) {
+        CTO_CHECK(cudaFuncSetAttribute(tc::gru1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F_SMEM));
+        attr = true;
+    }
+    const int ctas = ceil_div(batch, tc::F_M);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((ctas + 1) / 2 * 2), 2, 1);
+    cfg.blockDim = dim3(tc::F_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = tc::F_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CTO_CHECK(cudaLaunchKernelEx(&cfg, tc::gru1_fused_kernel, m_whh_hi, m_whh_mid, m_win_hi, m_win_mid, m_x_hi, m_x_mid, bp, bhn,
+                                 out_hi, out_mid, osb, ost, batch));
+    CTO_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace cto

@@ -48,7 +48,7 @@ __global__ void rescale_kernel(const int16_t* __restrict__ x, const int32_t* __r
 // are ordered position-major there so that a warp writes 32 consecutive output rows.
 template <bool SPLIT>
 __global__ void rescale_rows_kernel(const int16_t* __restrict__ x, const int32_t* __restrict__ depth, int64_t n, int64_t bp,
-                                    float* __restrict__ out, uint16_t* __restrict__ hi, uint16_t* __restrict__ mid) {
+                                    float* __restrict__ out, uint16_t* __restrict__ hi, uint16_t* __restrict__ mid, int one_col) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * N_POS) return;
     const int64_t b = SPLIT ? i % n : i / N_POS;
@@ -68,7 +68,7 @@ __global__ void rescale_rows_kernel(const int16_t* __restrict__ x, const int32_t
     }
     if (SPLIT) {
         #pragma unroll
-        for (int k = N_CH; k < 40; ++k) v[k] = 0.0f;
+        for (int k = N_CH; k < 40; ++k) v[k] = k == one_col ? 1.0f : 0.0f;   // optional constant-one column (bias rides in W_ih)
         const int64_t o = ((int64_t)t * bp + b) * 40;
         #pragma unroll
         for (int q = 0; q < 5; ++q) {
@@ -93,7 +93,7 @@ int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out
     if (n <= 0) return 0;
     CTO_REQUIRE(ld_out >= N_CH, "rescale: ld_out %d < %d", ld_out, N_CH);
     if (ld_out == N_CH && (reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
-        rescale_rows_kernel<false><<<ceil_div(n * N_POS, 128), 128, 0, s>>>(x, depth, n, 0, out, nullptr, nullptr);
+        rescale_rows_kernel<false><<<ceil_div(n * N_POS, 128), 128, 0, s>>>(x, depth, n, 0, out, nullptr, nullptr, -1);
     } else {
         const int64_t total = n * N_POS * ld_out;
         rescale_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, depth, n * N_POS, ld_out, out);
@@ -104,11 +104,12 @@ int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out
 }
 
 int launch_rescale_split_time_major(const int16_t* x, const int32_t* depth, int64_t n, int64_t bp, uint16_t* hi, uint16_t* mid,
-                                    cudaStream_t s) {
+                                    cudaStream_t s, int one_col) {
     if (n <= 0) return 0;
     CTO_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0 && bp >= n, "rescale_split: unaligned input or bp < n");
     static_assert(NEG_PLANE_LD == 40, "rescale_rows_kernel writes 40-element plane rows");
-    rescale_rows_kernel<true><<<ceil_div(n * N_POS, 128), 128, 0, s>>>(x, depth, n, bp, nullptr, hi, mid);
+    CTO_REQUIRE(one_col < 0 || (one_col >= N_CH && one_col < NEG_PLANE_LD), "rescale_split: constant column %d", one_col);
+    rescale_rows_kernel<true><<<ceil_div(n * N_POS, 128), 128, 0, s>>>(x, depth, n, bp, nullptr, hi, mid, one_col);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;
@@ -132,7 +133,7 @@ int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_o
 
 // fp32 rows [n, t_len, ld] -> time-major bf16 hi / mid planes [t_len, bp, ld]; one thread per 8-element chunk
 __global__ void split_time_major_kernel(const float* __restrict__ x, int64_t n, int t_len, int ld, int64_t bp,
-                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ mid) {
+                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ mid, int one_col) {
     const int chunks = ld / 8;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * t_len * chunks) return;
@@ -142,7 +143,8 @@ __global__ void split_time_major_kernel(const float* __restrict__ x, int64_t n, 
     const int t = (int)(row - b * t_len);
     const float4 v0 = *reinterpret_cast<const float4*>(x + row * ld + c * 8);
     const float4 v1 = *reinterpret_cast<const float4*>(x + row * ld + c * 8 + 4);
-    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    if (one_col >= c * 8 && one_col < c * 8 + 8) v[one_col - c * 8] = 1.0f;      // optional constant-one column
     uint32_t h[4], m[4];
     #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -156,11 +158,11 @@ __global__ void split_time_major_kernel(const float* __restrict__ x, int64_t n, 
 }
 
 int launch_split_time_major(const float* x, int64_t n, int t_len, int ld_in, int64_t bp, uint16_t* hi, uint16_t* mid,
-                            cudaStream_t s) {
+                            cudaStream_t s, int one_col) {
     if (n <= 0) return 0;
     CTO_REQUIRE(ld_in % 8 == 0 && bp >= n, "split_time_major: ld %d must be a multiple of 8 and bp >= n", ld_in);
     const int64_t total = n * t_len * (ld_in / 8);
-    split_time_major_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, n, t_len, ld_in, bp, hi, mid);
+    split_time_major_kernel<<<ceil_div(total, 256), 256, 0, s>>>(x, n, t_len, ld_in, bp, hi, mid, one_col);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

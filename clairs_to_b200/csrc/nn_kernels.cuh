@@ -58,7 +58,7 @@ int launch_im2col3_split(const float* x, int64_t n, int win, int wout, int cin, 
 constexpr int NEG_PLANE_LD = 40;   // row stride of the NEG input planes (34 channels + zeros; = engine.cuh NEG_IN_LD)
 // int16 tensor -> rescaled NEG input written directly as time-major bf16 hi / mid planes [33, bp, 40]
 int launch_rescale_split_time_major(const int16_t* x, const int32_t* depth, int64_t n, int64_t bp, uint16_t* hi, uint16_t* mid,
-                                    cudaStream_t s);
+                                    cudaStream_t s, int one_col = -1);
 int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_out, cudaStream_t s);
 // y_hi / y_mid, dq_hi .., out_hi ..: when given, the result is written as bf16 hi / mid planes (the pre-split A
 // operand of the next GEMM) instead of fp32
@@ -78,8 +78,14 @@ int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bh
 int launch_gru3(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_hi, const uint16_t* w_mid, const float* bhn,
                 uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch, int hidden, cudaStream_t s);
 // fp32 rows [n, t_len, ld_in] -> time-major bf16 hi / mid planes [t_len, bp, ld_in] (rows b >= n are left untouched)
+// one_col >= 0: that (padding) column is set to 1.0 -- the bias column of the fused first GRU layer
 int launch_split_time_major(const float* x, int64_t n, int t_len, int ld_in, int64_t bp, uint16_t* hi, uint16_t* mid,
-                            cudaStream_t s);
+                            cudaStream_t s, int one_col = -1);
+// first GRU layer with the input projection fused in (gru_in_tc.cu)
+int launch_gru1_fused(const uint16_t* x_hi, const uint16_t* x_mid, int ldx, int64_t bp, const uint16_t* win_hi,
+                      const uint16_t* win_mid, const uint16_t* whh_hi, const uint16_t* whh_mid, const float* bhn,
+                      uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch, int hidden,
+                      cudaStream_t s);
 int launch_head_fc3(const float* y, const float* w3, const float* b3, float* logits, int64_t batch, int n_heads,
                     cudaStream_t s);
 int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,
