@@ -359,9 +359,12 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
             cudaStreamWaitEvent(cs, ready, 0);
         }
     }
+    // The copy of chunk c+1 overlaps the kernels of chunk c, so only the FIRST chunk's copy is exposed: it is a
+    // quarter-size chunk (a multiple of 128 candidates), the others are full engine chunks.
     const int64_t step = e.max_batch;
-    for (int64_t c0 = 0; c0 < n && !rc; c0 += step) {
-        const int64_t nc = std::min(step, n - c0);
+    const int64_t first = n > step ? std::max<int64_t>(128, (step / 4) / 128 * 128) : step;
+    for (int64_t c0 = 0, nc = 0; c0 < n && !rc; c0 += nc) {
+        nc = std::min(c0 == 0 ? first : step, n - c0);
         for (int k = 0; k < n_streams; ++k) {
             const cto_host_stream* x = hs[k];
             // rows touched by this chunk -> one contiguous span of reads (rows are position sorted)
