@@ -359,12 +359,15 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
             cudaStreamWaitEvent(cs, ready, 0);
         }
     }
-    // The copy of chunk c+1 overlaps the kernels of chunk c, so only the FIRST chunk's copy is exposed: it is a
-    // quarter-size chunk (a multiple of 128 candidates), the others are full engine chunks.
+    // The copy of chunk c+1 overlaps the kernels of chunk c, so only the FIRST chunk's copy is exposed: the chunk
+    // sizes ramp up (1/16, 1/4 of an engine chunk, then full chunks; multiples of 128 candidates).
     const int64_t step = e.max_batch;
-    const int64_t first = n > step ? std::max<int64_t>(128, (step / 4) / 128 * 128) : step;
-    for (int64_t c0 = 0, nc = 0; c0 < n && !rc; c0 += nc) {
-        nc = std::min(c0 == 0 ? first : step, n - c0);
+    const bool ramp = n > step;
+    int chunk_idx = 0;
+    for (int64_t c0 = 0, nc = 0; c0 < n && !rc; c0 += nc, ++chunk_idx) {
+        int64_t want = step;
+        if (ramp && chunk_idx < 2) want = std::max<int64_t>(128, (step / (chunk_idx == 0 ? 16 : 4)) / 128 * 128);
+        nc = std::min(want, n - c0);
         for (int k = 0; k < n_streams; ++k) {
             const cto_host_stream* x = hs[k];
             // rows touched by this chunk -> one contiguous span of reads (rows are position sorted)

@@ -423,38 +423,8 @@ int launch_channel_ln(const float* x, const float* g, const float* b, float* y, 
 }
 
 // ------------------------------------------------------------------------------------------
-// depth-wise 3-tap conv along positions, pad 1 (M:93-97).  The eval-mode BatchNorm scale is
-// folded into the taps on the host; its shift is folded into the following 1x1 conv's bias.
-// ------------------------------------------------------------------------------------------
-__global__ void dwconv3_kernel(const float* __restrict__ y, const float* __restrict__ taps, float* __restrict__ out,
-                               int64_t total, int win, int wout, int stride, int c) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int ch = (int)(i % c);
-    const int64_t bw = i / c;
-    const int w = (int)(bw % wout);
-    const int64_t b = bw / wout;
-    float acc = 0.0f;
-    #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        const int src = w * stride - 1 + t;
-        if (src >= 0 && src < win) acc = fmaf(y[(b * win + src) * c + ch], taps[t * c + ch], acc);
-    }
-    out[i] = acc;
-}
-
-int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch, int win, int wout, int stride, int c,
-                   cudaStream_t s) {
-    const int64_t total = batch * wout * c;
-    if (total <= 0) return 0;
-    dwconv3_kernel<<<ceil_div(total, 256), 256, 0, s>>>(y, taps, out, total, win, wout, stride, c);
-    CTO_CHECK(cudaGetLastError());
-    count_launch();
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------
-// fused PreNorm + both depth-wise convolutions of the attention block (M:57-67, 91-97, 112-113):
+// fused PreNorm + both depth-wise 3-tap convolutions (pad 1) of the attention block (M:57-67, 91-97, 112-113); the
+// eval-mode BatchNorm scale is folded into the taps on the host, its shift into the following 1x1 conv's bias:
 //   y = channel_LN(x);  dq = dw3_stride1(y) * BN-scale;  dkv = dw3_stride2(y) * BN-scale
 // One warp per candidate; the candidate's <= 17 x 128 activations stay in shared memory, so x is read
 // once and y never touches HBM.
@@ -520,7 +490,7 @@ ln_dwconv_kernel(const float* __restrict__ x, const float* __restrict__ g, const
     const float4 k0 = __ldg(reinterpret_cast<const float4*>(taps_kv + ch)), k1 = __ldg(reinterpret_cast<const float4*>(taps_kv + C + ch)),
                  k2 = __ldg(reinterpret_cast<const float4*>(taps_kv + 2 * C + ch));
     #define SY4(r) (*reinterpret_cast<const float4*>(sy + (r) * C + ch))
-    for (int r = grp; r < w; r += RPW) {                    // stride 1, pad 1; same tap order as dwconv3_kernel
+    for (int r = grp; r < w; r += RPW) {                    // stride 1, pad 1; taps in position order, BN scale folded on the host
         float4 acc = zero;
         if (r - 1 >= 0) acc = fma4(SY4(r - 1), q0, acc);
         acc = fma4(SY4(r), q1, acc);

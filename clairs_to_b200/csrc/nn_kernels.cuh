@@ -64,8 +64,6 @@ int launch_pad_rows(const float* x, int64_t rows, int cols, float* out, int ld_o
 // operand of the next GEMM) instead of fp32
 int launch_channel_ln(const float* x, const float* g, const float* b, float* y, int64_t rows, int c, cudaStream_t s,
                       uint16_t* y_hi = nullptr, uint16_t* y_mid = nullptr);
-int launch_dwconv3(const float* y, const float* taps, float* out, int64_t batch, int win, int wout, int stride,
-                   int c, cudaStream_t s);
 int launch_ln_dwconv(const float* x, const float* g, const float* b, const float* taps_q, const float* taps_kv, float* dq,
                      float* dkv, int64_t batch, int w, int wkv, int c, cudaStream_t s, uint16_t* dq_hi = nullptr,
                      uint16_t* dq_mid = nullptr, uint16_t* dkv_hi = nullptr, uint16_t* dkv_mid = nullptr);
