@@ -57,14 +57,21 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples that arrived inside [t0, t1] (the timed region); the sampler is started before the warm-up because
+        nvidia-smi needs a few hundred ms to deliver its first line, so if the region was shorter than one sampling
+        period the samples taken under the warm-up load are used instead (and `window` says so)."""
         if self.proc is None:
             return None
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for r in self.rows if len(r) >= 9]
+        every = [(t, r) for t, r in self.rows if len(r) >= 9]
+        rows = [r for t, r in every if t0 is None or (t0 <= t <= t1 + 0.1)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for _, r in every], "warm-up + timed region"
         if not rows:
             return None
         sm = sorted(float(r[1]) for r in rows)
@@ -74,7 +81,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(rows[0][2]), reasons=sorted(reasons), samples=len(rows),
-                    power_w_max=max(float(r[3]) for r in rows))
+                    power_w_max=max(float(r[3]) for r in rows), window=window)
 
 
 TRAFFIC_KERNEL = {"neg_gru2_recurrent": "gru3_kernel<192", "neg_gru1_recurrent": "gru3_kernel<128",
@@ -208,24 +215,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(False)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
     _lib.check(lib.cto_engine_profile(eng.handle, int(os.environ.get('CTO_PROFILE_LEVEL', '1'))))
     launches0 = lib.cto_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         out = step(True)
     ev1.record()
     barrier()
+    wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = lib.cto_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     kinds = lib.cto_engine_profile_kinds()
     import ctypes as C
     pms = (C.c_double * kinds)(); pcnt = (C.c_int64 * kinds)(); pfl = (C.c_double * kinds)()
