@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -339,6 +340,134 @@ int cto_parse_tensor_row(const char* text, int64_t len, int16_t* row) {
         row[i] = (int16_t)(negv ? -v : v);
     }
     return 0;
+}
+
+// ---- whole chunk files at once ------------------------------------------
+// After the GPU offload the per-row Python work of the predict sub-command (split, parse, format) is what a chunk
+// costs; these two calls take a whole decompressed tensor_can file and produce a whole predict file body.
+
+static inline const char* find_char(const char* p, const char* end, char c) {
+    const void* q = memchr(p, c, (size_t)(end - p));
+    return q ? (const char*)q : end;
+}
+
+int cto_parse_tensor_file(const char* text, int64_t len, int64_t max_rows, int16_t* tensor, int32_t* depth, int64_t* fields,
+                          int64_t* n_rows) {
+    if (!text || !tensor || !depth || !fields || !n_rows) { cto::set_error("parse_tensor_file: NULL argument"); return 2; }
+    const int n_val = CTO_N_POS * CTO_N_CH;
+    const char* p = text;
+    const char* const end = text + len;
+    int64_t kept = 0, line_no = 0;
+    // pass 1 (serial, memchr-bound): split rows and fields, apply the two row filters, parse the depth
+    while (p < end) {
+        const char* eol = find_char(p, end, '\n');
+        ++line_no;
+        // the first seven tab-separated fields (clairs/predict.py:172-175); shorter rows are skipped
+        const char* f0[7];
+        const char* f1[7];
+        const char* q = p;
+        int nf = 0;
+        while (nf < 7 && q <= eol) {
+            const char* t = find_char(q, eol, '\t');
+            f0[nf] = q;
+            f1[nf] = t;
+            ++nf;
+            if (t >= eol) break;
+            q = t + 1;
+        }
+        const char* next = eol < end ? eol + 1 : end;
+        if (nf < 7) { p = next; continue; }
+        // rows whose centre reference base is not ACGT are dropped (clairs/predict.py:219-220)
+        if (f1[2] - f0[2] <= 16) { cto::set_error("parse_tensor_file: line %lld: reference context shorter than 17 bases", (long long)line_no); return 2; }
+        const char cb = f0[2][16];
+        if (cb != 'A' && cb != 'C' && cb != 'G' && cb != 'T') { p = next; continue; }
+        if (kept >= max_rows) { cto::set_error("parse_tensor_file: more than %lld rows", (long long)max_rows); return 2; }
+        // depth = float(alt_info.split('-')[0]) (clairs/predict.py:179); written by "%d" in the encoder
+        {
+            const char* a = f0[4];
+            const char* dash = find_char(a, f1[4], '-');
+            char tmp[32];
+            const size_t dl = (size_t)(dash - a) < sizeof(tmp) - 1 ? (size_t)(dash - a) : sizeof(tmp) - 1;
+            memcpy(tmp, a, dl);
+            tmp[dl] = 0;
+            char* stop = nullptr;
+            const double dv = strtod(tmp, &stop);
+            if (stop == tmp) { cto::set_error("parse_tensor_file: line %lld: alt_info does not start with a depth", (long long)line_no); return 2; }
+            depth[kept] = (int32_t)dv;
+        }
+        // the last kept field loses a trailing CR like str.strip() would (ref_center is stripped in predict.py)
+        const char* e6 = f1[6];
+        while (e6 > f0[6] && (e6[-1] == '\r' || e6[-1] == ' ')) --e6;
+        f1[6] = e6;
+        for (int k = 0; k < 7; ++k) {
+            fields[(kept * 7 + k) * 2] = (int64_t)(f0[k] - text);
+            fields[(kept * 7 + k) * 2 + 1] = (int64_t)(f1[k] - f0[k]);
+        }
+        ++kept;
+        p = next;
+    }
+    // pass 2 (parallel over rows): the 1122 integers of every kept row
+    // up to 8 host threads (CTO_HOST_THREADS overrides; the reference predict pins itself to one, clairs/predict.py:475)
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_thr = (int)(hw ? (hw < 8 ? hw : 8) : 1);
+    if (const char* ev = getenv("CTO_HOST_THREADS")) n_thr = atoi(ev) > 0 ? atoi(ev) : 1;
+    if (n_thr > 64) n_thr = 64;
+    if (kept < 256) n_thr = 1;
+    std::vector<int> bad(n_thr, 0);
+    auto work = [&](int tid) {
+        const int64_t r0 = kept * tid / n_thr, r1 = kept * (tid + 1) / n_thr;
+        for (int64_t r = r0; r < r1; ++r) {
+            const int64_t* f = fields + (r * 7 + 3) * 2;
+            if (cto_parse_tensor_row(text + f[0], f[1], tensor + r * n_val)) { bad[tid] = 1; return; }
+        }
+    };
+    if (n_thr == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_thr; ++t) pool.emplace_back(work, t);
+        for (auto& th : pool) th.join();
+    }
+    for (int t = 0; t < n_thr; ++t)
+        if (bad[t]) { cto::set_error("parse_tensor_file: a tensor field does not hold %d integers", n_val); return 2; }
+    *n_rows = kept;
+    return 0;
+}
+
+static inline char* put_count_list(char* o, const int32_t* v) {           // str([float(a), ...]) of integer-valued floats
+    *o++ = '[';
+    for (int k = 0; k < 4; ++k) {
+        if (k) { *o++ = ','; *o++ = ' '; }
+        o = put_int(o, v[k]);
+        *o++ = '.';
+        *o++ = '0';
+    }
+    *o++ = ']';
+    return o;
+}
+
+int64_t cto_format_predict_rows(const char* text, const int64_t* fields, int64_t n, const int32_t* fwd, const int32_t* rev,
+                                const float* probs, int n_heads, char* out, int64_t cap) {
+    if (!text || !fields || !fwd || !rev || !probs || !out || (n_heads != 4 && n_heads != 6)) return -2;
+    char* o = out;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t* f = fields + r * 14;
+        const int64_t need = f[1] + f[3] + f[9] + 2 * 64 + (int64_t)n_heads * 2 * 32 + 64;
+        if (cap - (o - out) < need) return -1;
+        memcpy(o, text + f[0], (size_t)f[1]); o += f[1]; *o++ = '\t';               // contig
+        memcpy(o, text + f[2], (size_t)f[3]); o += f[3]; *o++ = '\t';               // position
+        const char c = text[f[4] + 16];                                            // seq[16].upper()
+        *o++ = (char)((c >= 'a' && c <= 'z') ? c - 32 : c); *o++ = '\t';
+        memcpy(o, text + f[8], (size_t)f[9]); o += f[9]; *o++ = '\t';               // alt_info
+        o = put_count_list(o, fwd + r * 4); *o++ = '\t';
+        o = put_count_list(o, rev + r * 4); *o++ = '\t';
+        const int64_t w = cto_format_prob_fields(probs + r * n_heads * 4, 2 * n_heads, o, cap - (o - out));
+        if (w < 0) return -1;
+        o += w;
+        if (n_heads == 4) *o++ = '\t';                                             // the SNV row ends with an empty field
+        *o++ = '\n';
+    }
+    return (int64_t)(o - out);
 }
 
 }  // extern "C"

@@ -96,3 +96,42 @@ def format_prob_fields(probs) -> str:
     if n < 0:
         raise _lib.CtoError("cto_format_prob_fields: buffer too small")
     return buf.raw[:n].decode()
+
+
+class TensorFile:
+    """A whole tensor_can chunk file parsed by one native call (``cto_parse_tensor_file``): ``tensor`` int16
+    [n,33,34], ``depth`` int32 [n], and the text fields of row r as slices of ``text`` via ``field(r, k)``
+    (k: 0 contig, 1 position, 2 ref33, 4 alt_info, 5 variant_type, 6 ref_centre).  Rows whose centre reference
+    base is not ACGT are already dropped (clairs/predict.py:219-220)."""
+
+    def __init__(self, text: bytes):
+        lib = _lib.lib()
+        self.text = text
+        max_rows = text.count(b"\n") + 1
+        self.tensor = np.empty((max_rows, N_POS, N_CH), np.int16)
+        self.depth = np.empty(max_rows, np.int32)
+        self.fields = np.empty((max_rows, 7, 2), np.int64)
+        n = C.c_int64(0)
+        _lib.check(lib.cto_parse_tensor_file(text, len(text), max_rows, _p(self.tensor), _p(self.depth), _p(self.fields),
+                                             C.byref(n)), "cto_parse_tensor_file")
+        self.n = int(n.value)
+        self.tensor, self.depth, self.fields = self.tensor[:self.n], self.depth[:self.n], self.fields[:self.n]
+
+    def field(self, r, k) -> str:
+        o, ln = self.fields[r, k]
+        return self.text[o:o + ln].decode()
+
+
+def format_predict_rows(tf: TensorFile, start, n, fwd, rev, probs, n_heads) -> bytes:
+    """The predict-file rows (clairs/predict.py:114-152) of rows [start, start+n) of a parsed tensor file."""
+    lib = _lib.lib()
+    fwd = np.ascontiguousarray(fwd, dtype=np.int32).reshape(n, 4)
+    rev = np.ascontiguousarray(rev, dtype=np.int32).reshape(n, 4)
+    probs = np.ascontiguousarray(probs, dtype=np.float32).reshape(n, 2 * n_heads, 2)
+    fields = np.ascontiguousarray(tf.fields[start:start + n])
+    cap = int(fields[:, (0, 1, 4), 1].sum()) + n * (2 * 64 + n_heads * 64 + 64) + 64
+    buf = C.create_string_buffer(cap)
+    w = lib.cto_format_predict_rows(tf.text, _p(fields), n, _p(fwd), _p(rev), _p(probs), n_heads, buf, cap)
+    if w < 0:
+        raise _lib.CtoError("cto_format_predict_rows failed (%d)" % w)
+    return buf.raw[:w]

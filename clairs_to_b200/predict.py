@@ -51,6 +51,20 @@ def _open_reader(path):
     return proc, proc.stdout
 
 
+def read_tensor_file(path) -> "host.TensorFile":
+    """A whole tensor_can chunk file (<= 10 000 candidates, shared/param.py:21) decompressed by the same ``gzip -fdc``
+    as the reference (clairs/predict.py:159) and parsed by ONE native call instead of a Python loop over rows."""
+    if path == "PIPE":
+        text = sys.stdin.buffer.read()
+    else:
+        proc = Popen(shlex.split("%s -fdc %s" % (ZSTD, path)), stdout=PIPE, bufsize=8388608)
+        text = proc.stdout.read()
+        proc.stdout.close()
+        if proc.wait() != 0:
+            sys.exit("[ERROR] %s -fdc %s failed" % (ZSTD, path))
+    return host.TensorFile(text)
+
+
 def read_tensor_rows(path):
     """Yield (contig, pos, ref33, int16[33,34], alt_info, variant_type, ref_centre) for rows that
     survive the centre-base filter (clairs/predict.py:172-175, 219-220)."""
@@ -120,25 +134,28 @@ def predict(args):
         if predict_dir and not os.path.exists(predict_dir):
             os.makedirs(predict_dir, exist_ok=True)
         fpo = open(predict_fn, "wb")
-        zproc = Popen(shlex.split("%s -c" % ZSTD), stdin=PIPE, stdout=fpo, bufsize=8388608, universal_newlines=True)
+        zproc = Popen(shlex.split("%s -c" % ZSTD), stdin=PIPE, stdout=fpo, bufsize=8388608)
         out_file = zproc.stdin
     else:
-        fpo, zproc, out_file = None, None, sys.stdout
+        fpo, zproc, out_file = None, None, sys.stdout.buffer
 
-    total = 0
-    aff_rows = read_tensor_rows(args.tensor_fn_acgt)
-    neg_rows = read_tensor_rows(args.tensor_fn_nacgt)
+    # whole chunk files: one native parse per file, one GPU call and one native format per PREDICT_BATCH rows.
+    # The two files are consumed in lock-step by row index, so min(rows) rows are predicted.
+    aff_tf = read_tensor_file(args.tensor_fn_acgt)
+    neg_tf = read_tensor_file(args.tensor_fn_nacgt)
+    n_rows = min(aff_tf.n, neg_tf.n)
     dev = engine.device
-    for aff_batch, neg_batch in zip(_batches(aff_rows, PREDICT_BATCH), _batches(neg_rows, PREDICT_BATCH)):
-        n = min(len(aff_batch), len(neg_batch))                   # lock-step consumption, SURVEY.md 9.11
-        xa = torch.from_numpy(np.stack([r[3] for r in aff_batch[:n]])).to(dev)
-        xn = torch.from_numpy(np.stack([r[3] for r in neg_batch[:n]])).to(dev)
-        da = torch.tensor([int(float(r[4].split('-')[0])) for r in aff_batch[:n]], dtype=torch.int32, device=dev)
-        dn = torch.tensor([int(float(r[4].split('-')[0])) for r in neg_batch[:n]], dtype=torch.int32, device=dev)
+    total = 0
+    for r0 in range(0, n_rows, PREDICT_BATCH):
+        n = min(PREDICT_BATCH, n_rows - r0)
+        xa = torch.from_numpy(aff_tf.tensor[r0:r0 + n]).to(dev)
+        xn = torch.from_numpy(neg_tf.tensor[r0:r0 + n]).to(dev)
+        da = torch.from_numpy(aff_tf.depth[r0:r0 + n]).to(dev)
+        dn = torch.from_numpy(neg_tf.depth[r0:r0 + n]).to(dev)
         res = engine.predict(xa, da, xn, dn, posterior=False)
         probs = res['probs'].cpu().numpy()
         fwd, rev = res['fwd'].cpu().numpy(), res['rev'].cpu().numpy()
-        out_file.writelines(format_rows(aff_batch[:n], fwd, rev, probs, engine.n_heads))
+        out_file.write(host.format_predict_rows(aff_tf, r0, n, fwd, rev, probs, engine.n_heads))
         if total // 20000 != (total + n) // 20000:
             print("Processed %d tensors" % ((total + n) // 20000 * 20000), file=sys.stderr)
         total += n

@@ -195,6 +195,22 @@ int64_t cto_format_tensor_row(const int16_t* tensor_row, char* out, int64_t cap)
 int64_t cto_format_prob_fields(const float* probs, int n_pairs, char* out, int64_t cap);
 int cto_parse_tensor_row(const char* text, int64_t len, int16_t* tensor_row);
 
+/*
+ * Whole chunk files at once.
+ * cto_parse_tensor_file: `text` = a decompressed tensor_can file (rows of src/create_tensor_pileup_calling.py:561-568).
+ * Replaces the row loop of tensor_generator_from (clairs/predict.py:172-175, 179, 219-220): rows with fewer than 7
+ * tab-separated fields are skipped, rows whose centre reference base is not ACGT are dropped.  For each kept row r:
+ * tensor[r] = the 1122 ints, depth[r] = the leading number of alt_info, fields[r][k] = (byte offset, length) in `text`
+ * of field k (contig, position, ref33, tensor, alt_info, variant_type, ref_centre; int64 [rows][7][2]).
+ * cto_format_predict_rows: the predict-file rows of clairs/predict.py:114-152 for n kept rows (strand counts
+ * int32 [n,4] x2 as recovered by cto_strand_counts, probabilities float32 [n, 2*n_heads, 2]); returns the bytes
+ * written, -1 if `cap` is too small, -2 on a bad argument.
+ */
+int cto_parse_tensor_file(const char* text, int64_t len, int64_t max_rows, int16_t* tensor, int32_t* depth, int64_t* fields,
+                          int64_t* n_rows);
+int64_t cto_format_predict_rows(const char* text, const int64_t* fields, int64_t n, const int32_t* fwd, const int32_t* rev,
+                                const float* probs, int n_heads, char* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

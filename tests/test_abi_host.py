@@ -96,3 +96,68 @@ def test_prob_field_format_matches_python():
         fields = format_prob_fields(p[k]).split("\t")
         expect = posterior_oracle.format_predict_row("c", 1, "A", "x", [0.0], [0.0], list(p[k])).split("\t")[6:14]
         assert fields == expect
+
+
+def _python_rows(text):
+    """the row-wise Python path the whole-file codec replaces (clairs_to_b200/predict.py:read_tensor_rows)"""
+    from clairs_to_b200 import host
+    rows = []
+    for row in text.decode().splitlines(True):
+        cols = row.split("\t")[:7]
+        if len(cols) < 7 or cols[2][16] not in "ACGT":
+            continue
+        rows.append((cols[0], cols[1], cols[2], host.parse_tensor_row(cols[3]), cols[4], cols[5], cols[6].strip()))
+    return rows
+
+
+def _golden_tensor_texts():
+    import glob
+    import gzip
+    here = os.path.dirname(os.path.abspath(__file__))
+    for path in sorted(glob.glob(os.path.join(here, "golden", "pipeline", "tensor_can_*")) +
+                       glob.glob(os.path.join(here, "golden", "create_tensor", "tensor_can_*"))):
+        raw = open(path, "rb").read()
+        yield path, (gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw)
+
+
+def test_parse_tensor_file_matches_rowwise_parser_on_golden_files():
+    from clairs_to_b200 import host
+    seen = 0
+    for path, text in _golden_tensor_texts():
+        # add the cases the reference reader filters: a short row, a row with a non-ACGT centre base, CRLF
+        lines = text.split(b"\n")
+        extra = b"chrX\t5\tshort row\n"
+        first = lines[0].split(b"\t")
+        bad = b"\t".join([first[0], first[1], first[2][:16] + b"N" + first[2][17:]] + first[3:]) + b"\n"
+        text2 = extra + bad + text.replace(b"\n", b"\r\n", 1)
+        want = _python_rows(text2)
+        tf = host.TensorFile(text2)
+        assert tf.n == len(want) == len(_python_rows(text)), path
+        for r, w in enumerate(want):
+            assert (tf.field(r, 0), tf.field(r, 1), tf.field(r, 2), tf.field(r, 4), tf.field(r, 5), tf.field(r, 6)) == \
+                   (w[0], w[1], w[2], w[4], w[5], w[6])
+            assert np.array_equal(tf.tensor[r], w[3])
+            assert tf.depth[r] == int(float(w[4].split('-')[0]))
+        seen += tf.n
+    assert seen > 0
+
+
+@pytest.mark.parametrize("n_heads", [4, 6])
+def test_format_predict_rows_matches_python_formatter(n_heads):
+    from clairs_to_b200 import host
+    from clairs_to_b200.predict import format_rows
+    path, text = next(_golden_tensor_texts())
+    tf = host.TensorFile(text)
+    n = tf.n
+    rng = np.random.default_rng(n_heads)
+    fwd = rng.integers(0, 200, size=(n, 4)).astype(np.int32)
+    rev = rng.integers(0, 200, size=(n, 4)).astype(np.int32)
+    probs = rng.random(size=(n, 2 * n_heads, 2)).astype(np.float32)
+    probs[0, 0] = (1.0, 0.0)
+    probs[0, 1] = (0.999999996, 4e-9)                      # rounds to 1.00000000 / 0.00000000 at 8 decimals
+    meta = [tuple(tf.field(r, k) if k != 3 else None for k in range(7)) for r in range(n)]
+    want = "".join(format_rows(meta, fwd, rev, probs, n_heads)).encode()
+    assert host.format_predict_rows(tf, 0, n, fwd, rev, probs, n_heads) == want
+    half = n // 2
+    assert host.format_predict_rows(tf, half, n - half, fwd[half:], rev[half:], probs[half:], n_heads) == \
+        "".join(format_rows(meta[half:], fwd[half:], rev[half:], probs[half:], n_heads)).encode()
