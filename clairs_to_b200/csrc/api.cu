@@ -302,7 +302,18 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
     cudaStream_t s = (cudaStream_t)stream;
     const int nh = e.aff.n_heads;
     const int64_t xin = (int64_t)N_POS * N_CH;
-    if (!e.copy_stream) CTO_CHECK(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
+    if (!e.copy_stream) {
+        CTO_CHECK(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
+        // this call allocates ~14 KB per candidate from the stream-ordered pool and frees it at the end; with the default
+        // release threshold (0) the pool hands everything back to the driver at the final synchronise, and every call
+        // pays the allocation again (milliseconds).  Keep the memory cached in the device's default pool instead.
+        int dev = 0;
+        cudaMemPool_t pool = nullptr;
+        CTO_CHECK(cudaGetDevice(&dev));
+        CTO_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;
+        CTO_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     cudaStream_t cs = e.copy_stream;
 
     const cto_host_stream* hs[2] = {aff, neg};
@@ -318,8 +329,8 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
     auto alloc = [&](void** p, int64_t bytes) {
         if (cudaMallocAsync(p, bytes > 16 ? bytes : 16, s) != cudaSuccess) rc = 1;
     };
-    // device arrays: the big per-read arrays are only ALLOCATED here and filled span by span below, so that
-    // the host->device copy of chunk c+1 overlaps the kernels of chunk c; the small per-row arrays go at once
+    // device arrays are only ALLOCATED here and filled span by span below (per-read arrays, per-row arrays and the
+    // window table alike), so that the host->device copy of chunk c+1 overlaps the kernels of chunk c
     for (int k = 0; k < n_streams && !rc; ++k) {
         const cto_host_stream* x = hs[k];
         alloc((void**)&d[k].code, x->n_reads);
@@ -333,11 +344,6 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
         alloc((void**)&tens[k], sizeof(int16_t) * n * xin);
         alloc((void**)&dep[k], sizeof(int32_t) * n);
         if (rc) break;
-        cudaError_t ce = cudaMemcpyAsync(d[k].pos_off, x->pos_off, sizeof(int32_t) * (x->n_rows + 1), cudaMemcpyHostToDevice, s);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].ind_off, x->ind_off, sizeof(int32_t) * (x->n_rows + 1), cudaMemcpyHostToDevice, s);
-        if (ce == cudaSuccess && x->n_rows) ce = cudaMemcpyAsync(d[k].ref_code, x->ref_code, x->n_rows, cudaMemcpyHostToDevice, s);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].win_pos, x->win_pos, sizeof(int32_t) * n * N_POS, cudaMemcpyHostToDevice, s);
-        if (ce != cudaSuccess) rc = 1;
     }
     alloc((void**)&la, sizeof(float) * n * nh * 2);
     alloc((void**)&ln, sizeof(float) * n * nh * 2);
@@ -379,12 +385,19 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
                 r0 = r < r0 ? r : r0;
                 r1 = r > r1 ? r : r1;
             }
+            {   // the window table of the chunk goes even when every slot is an absent row
+                const cudaError_t we = cudaMemcpyAsync(d[k].win_pos + c0 * N_POS, wp, sizeof(int32_t) * nc * N_POS, cudaMemcpyHostToDevice, cs);
+                if (we != cudaSuccess) { set_error("run_sites_host: H2D copy failed: %s", cudaGetErrorString(we)); rc = 1; break; }
+            }
             if (r1 < 0) continue;
             if (r1 >= x->n_rows) { set_error("run_sites_host: win_pos row %d outside the %lld pileup rows", r1, (long long)x->n_rows); rc = 2; break; }
             const int64_t a = x->pos_off[r0], b2 = x->pos_off[r1 + 1];
             const int64_t ia = x->ind_off[r0], ib = x->ind_off[r1 + 1];
-            cudaError_t ce = cudaSuccess;
-            if (b2 > a) {
+            // per-row arrays of the rows this chunk touches (offsets are absolute, so slices are enough) + its windows
+            cudaError_t ce = cudaMemcpyAsync(d[k].pos_off + r0, x->pos_off + r0, sizeof(int32_t) * (r1 - r0 + 2), cudaMemcpyHostToDevice, cs);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].ind_off + r0, x->ind_off + r0, sizeof(int32_t) * (r1 - r0 + 2), cudaMemcpyHostToDevice, cs);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].ref_code + r0, x->ref_code + r0, r1 - r0 + 1, cudaMemcpyHostToDevice, cs);
+            if (ce == cudaSuccess && b2 > a) {
                 ce = cudaMemcpyAsync(d[k].code + a, x->code + a, b2 - a, cudaMemcpyHostToDevice, cs);
                 if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].bq + a, x->bq + a, b2 - a, cudaMemcpyHostToDevice, cs);
                 if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].mq + a, x->mq + a, b2 - a, cudaMemcpyHostToDevice, cs);
