@@ -114,37 +114,42 @@ def create_tensor(args):
     text, _ = mp.communicate()
 
     tok = host.tokenize_mpileup(text, reference, reference_start, sorted(cand), max_indel_length)
-    row_of = {int(p): i for i, p in enumerate(tok.row_pos)}
+    # window assembly (ibid. 513-516, 537-553), vectorised: rows are position sorted, so the row of a position is a
+    # binary search; -1 = no pileup row (an all-zero row, ibid. 461)
     table_len = extend_end - extend_start
-    keep, windows = [], []
-    for pos in sorted(cand):
-        start = pos - FLANK - extend_start
-        if start < 0 or start + N_POS >= table_len:                      # ibid. 542-543
-            continue
-        if pos not in row_of:                                            # no alt_info for it, ibid. 552-553
-            continue
-        keep.append(pos)
-        windows.append([row_of.get(pos - FLANK + j, -1) for j in range(N_POS)])
+    row_pos = np.asarray(tok.row_pos, dtype=np.int64)
+    cpos = np.asarray(sorted(cand), dtype=np.int64)
+    start = cpos - FLANK - extend_start
+    ok = (start >= 0) & (start + N_POS < table_len)                      # ibid. 542-543
+    if row_pos.size:
+        ci = np.searchsorted(row_pos, cpos)
+        ok &= (ci < row_pos.size) & (row_pos[np.minimum(ci, row_pos.size - 1)] == cpos)   # no alt_info for it, ibid. 552-553
+    else:
+        ok &= False
+    keep = cpos[ok]
+    if keep.size:
+        want = keep[:, None] - FLANK + np.arange(N_POS, dtype=np.int64)[None, :]
+        wi = np.searchsorted(row_pos, want)
+        hit = (wi < row_pos.size) & (row_pos[np.minimum(wi, row_pos.size - 1)] == want)
+        windows = np.where(hit, wi, -1).astype(np.int32)
+        centre_rows = windows[:, FLANK]
 
     if tensor_out := (args.tensor_can_fn != "PIPE"):
         fpo = open(args.tensor_can_fn, "wb")
-        zp = _popen("{} -c".format(args.zstd), stdin=PIPE, stdout=fpo)
+        zp = Popen(shlex.split("{} -c".format(args.zstd)), stdin=PIPE, stdout=fpo, bufsize=8388608)
         out = zp.stdin
     else:
-        out = sys.stdout
+        out = sys.stdout.buffer
 
     count = 0
-    if keep:
+    if keep.size:
         dev = torch.device('cuda', torch.cuda.current_device())
-        tok.stream.win_pos = np.asarray(windows, dtype=np.int32).reshape(-1)
+        tok.stream.win_pos = windows.reshape(-1)
         tensor, _ = encode_pileup(stream_to_device(tok.stream, dev), PIPELINE_LOW_BQ_CUT, dev)
-        rows_text = host.format_tensor_rows(tensor.cpu().numpy())
-        for pos, flat in zip(keep, rows_text):
-            off = pos - reference_start
-            ref_seq = reference[off - FLANK: off + FLANK + 1].upper()
-            out.write("%s\t%d\t%s\t%s\t%s\t%s\t%s\n" % (ctg_name, pos, ref_seq, flat, tok.alt_info[row_of[pos]],
-                                                       cand[pos], ref_seq[FLANK]))
-            count += 1
+        ref33 = [reference[int(p) - reference_start - FLANK: int(p) - reference_start + FLANK + 1].upper() for p in keep]
+        out.write(host.format_tensor_can_rows(ctg_name, keep, ref33, tensor.cpu().numpy(),
+                                              [tok.alt_info[int(r)] for r in centre_rows], [cand[int(p)] for p in keep]))
+        count = int(keep.size)
     if tensor_out:
         zp.stdin.close()
         zp.wait()

@@ -434,6 +434,35 @@ int cto_parse_tensor_file(const char* text, int64_t len, int64_t max_rows, int16
     return 0;
 }
 
+int64_t cto_format_tensor_can_rows(const char* ctg, int64_t ctg_len, int64_t n, const int64_t* pos, const char* ref33,
+                                   const int16_t* tensor, const char* blob, const int64_t* alt_off, const int64_t* type_off,
+                                   char* out, int64_t cap) {
+    if (!ctg || !pos || !ref33 || !tensor || !blob || !alt_off || !type_off || !out) return -2;
+    const int n_val = CTO_N_POS * CTO_N_CH;
+    char* o = out;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t al = alt_off[2 * r + 1], tl = type_off[2 * r + 1];
+        if (cap - (o - out) < ctg_len + 24 + CTO_N_POS + (int64_t)n_val * 7 + al + tl + 16) return -1;
+        memcpy(o, ctg, (size_t)ctg_len); o += ctg_len; *o++ = '\t';
+        {   // "%d" of the (positive) genomic position
+            char tmp[24];
+            int k = 0;
+            long long v = (long long)pos[r];
+            if (v < 0) { *o++ = '-'; v = -v; }
+            do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+            while (k) *o++ = tmp[--k];
+        }
+        *o++ = '\t';
+        memcpy(o, ref33 + r * CTO_N_POS, CTO_N_POS); o += CTO_N_POS; *o++ = '\t';
+        o += cto_format_tensor_row(tensor + r * n_val, o, cap - (o - out)); *o++ = '\t';
+        memcpy(o, blob + alt_off[2 * r], (size_t)al); o += al; *o++ = '\t';
+        memcpy(o, blob + type_off[2 * r], (size_t)tl); o += tl; *o++ = '\t';
+        *o++ = ref33[r * CTO_N_POS + CTO_N_POS / 2];
+        *o++ = '\n';
+    }
+    return (int64_t)(o - out);
+}
+
 static inline char* put_count_list(char* o, const int32_t* v) {           // str([float(a), ...]) of integer-valued floats
     *o++ = '[';
     for (int k = 0; k < 4; ++k) {

@@ -135,3 +135,30 @@ def format_predict_rows(tf: TensorFile, start, n, fwd, rev, probs, n_heads) -> b
     if w < 0:
         raise _lib.CtoError("cto_format_predict_rows failed (%d)" % w)
     return buf.raw[:w]
+
+
+def format_tensor_can_rows(ctg, pos, ref33, tensors, alt_infos, types) -> bytes:
+    """All rows of a tensor_can chunk file (src/create_tensor_pileup_calling.py:561-568) with one native call.
+    pos: n genomic positions; ref33: n strings of 33 reference bases; tensors int16 [n,33,34]; alt_infos / types: n strings."""
+    lib = _lib.lib()
+    n = len(pos)
+    if n == 0:
+        return b""
+    pos = np.ascontiguousarray(pos, dtype=np.int64)
+    t = np.ascontiguousarray(tensors, dtype=np.int16).reshape(n, N_POS * N_CH)
+    ref = "".join(ref33).encode()
+    assert len(ref) == n * N_POS, "every reference context must be %d bases" % N_POS
+    parts, alt_off, type_off, o = [], np.empty((n, 2), np.int64), np.empty((n, 2), np.int64), 0
+    for k in range(n):
+        a, ty = alt_infos[k].encode(), types[k].encode()
+        alt_off[k] = (o, len(a)); o += len(a)
+        type_off[k] = (o, len(ty)); o += len(ty)
+        parts.append(a); parts.append(ty)
+    blob = b"".join(parts)
+    ctg_b = ctg.encode()
+    cap = n * (len(ctg_b) + 24 + N_POS + N_POS * N_CH * 7 + 16) + len(blob) + 64
+    buf = C.create_string_buffer(cap)
+    w = lib.cto_format_tensor_can_rows(ctg_b, len(ctg_b), n, _p(pos), ref, _p(t), blob, _p(alt_off), _p(type_off), buf, cap)
+    if w < 0:
+        raise _lib.CtoError("cto_format_tensor_can_rows failed (%d)" % w)
+    return buf.raw[:w]

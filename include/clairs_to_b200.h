@@ -206,6 +206,15 @@ int cto_parse_tensor_row(const char* text, int64_t len, int16_t* tensor_row);
  * int32 [n,4] x2 as recovered by cto_strand_counts, probabilities float32 [n, 2*n_heads, 2]); returns the bytes
  * written, -1 if `cap` is too small, -2 on a bad argument.
  */
+/*
+ * The rows of a tensor_can chunk file (src/create_tensor_pileup_calling.py:561-568) for n candidates of one contig:
+ * "ctg \t pos \t ref33 \t 1122 ints \t alt_info \t variant_type \t ref33[16] \n".  ref33: n x 33 characters;
+ * alt_off / type_off: int64 [n][2] = (byte offset, length) of the row's alt_info / variant type inside `blob`.
+ * Returns the bytes written, -1 if `cap` is too small, -2 on a NULL argument.
+ */
+int64_t cto_format_tensor_can_rows(const char* ctg, int64_t ctg_len, int64_t n, const int64_t* pos, const char* ref33,
+                                   const int16_t* tensor, const char* blob, const int64_t* alt_off, const int64_t* type_off,
+                                   char* out, int64_t cap);
 int cto_parse_tensor_file(const char* text, int64_t len, int64_t max_rows, int16_t* tensor, int32_t* depth, int64_t* fields,
                           int64_t* n_rows);
 int64_t cto_format_predict_rows(const char* text, const int64_t* fields, int64_t n, const int32_t* fwd, const int32_t* rev,

@@ -161,3 +161,21 @@ def test_format_predict_rows_matches_python_formatter(n_heads):
     half = n // 2
     assert host.format_predict_rows(tf, half, n - half, fwd[half:], rev[half:], probs[half:], n_heads) == \
         "".join(format_rows(meta[half:], fwd[half:], rev[half:], probs[half:], n_heads)).encode()
+
+
+def test_format_tensor_can_rows_matches_python_formatting():
+    from clairs_to_b200 import host
+    rng = np.random.default_rng(3)
+    n = 57
+    tensors = rng.integers(-300, 300, size=(n, 33, 34)).astype(np.int16)
+    tensors[0, 0, 0], tensors[0, 0, 1] = -32768, 32767
+    pos = np.sort(rng.integers(1, 2_000_000_000, size=n))
+    ref33 = ["".join(rng.choice(list("ACGTN"), size=33)) for _ in range(n)]
+    alts = ["%d-X%s %d R%s %d-" % (rng.integers(1, 99), "ACGT"[k % 4], k, "ACGT"[(k + 1) % 4], 2 * k) for k in range(n)]
+    alts[3] = ""
+    types = [("snv", "indel", "unknown")[k % 3] for k in range(n)]
+    flat = format_tensor_rows(tensors)
+    want = "".join("%s\t%d\t%s\t%s\t%s\t%s\t%s\n" % ("chr20", pos[k], ref33[k], flat[k], alts[k], types[k], ref33[k][16])
+                   for k in range(n)).encode()
+    assert host.format_tensor_can_rows("chr20", pos, ref33, tensors, alts, types) == want
+    assert host.format_tensor_can_rows("chr20", pos[:0], [], tensors[:0], [], []) == b""
