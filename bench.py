@@ -168,7 +168,7 @@ def main():
     from clairs_to_b200 import _lib, dist as cdist, synth
     from clairs_to_b200.engine import PIPELINE_LOW_BQ_CUT, Engine, stream_to_device
     from clairs_to_b200.pileup_format import PileupStream
-    from oracle import nn_oracle      # only for the seeded random-init weight generator shared with the tests
+    from clairs_to_b200 import synth_weights
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -183,8 +183,8 @@ def main():
     t_gen = time.time()
     aff, neg = synth.synth_pair_large(n, 20241 + rank, 'ont')
     t_gen = time.time() - t_gen
-    aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads), 100 + n_heads)
-    neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 200 + n_heads)
+    aff_sd = synth_weights.synth_state_dict(synth_weights.aff_state_dict_shapes(n_heads), 100 + n_heads)
+    neg_sd = synth_weights.synth_state_dict(synth_weights.neg_state_dict_shapes(n_heads), 200 + n_heads)
     eng = Engine(aff_sd, neg_sd, max_batch=args.max_batch, device=dev, likelihood=synthetic_likelihood(n_heads))
     lib = eng.lib
     if os.environ.get("CTO_DEBUG"):
