@@ -179,3 +179,20 @@ def test_format_tensor_can_rows_matches_python_formatting():
                    for k in range(n)).encode()
     assert host.format_tensor_can_rows("chr20", pos, ref33, tensors, alts, types) == want
     assert host.format_tensor_can_rows("chr20", pos[:0], [], tensors[:0], [], []) == b""
+
+
+def test_parse_tensor_file_edge_cases():
+    from clairs_to_b200 import host
+    assert host.TensorFile(b"").n == 0
+    assert host.TensorFile(b"\n\n").n == 0
+    ints = " ".join(str(v) for v in range(-561, 561))
+    row = "chr1\t77\t%s\t%s\t12-XA 2-\tsnv\tA" % ("ACGT" * 8 + "A", ints)
+    # no trailing newline, extra columns after the seventh, a lower-case centre base (dropped: not in "ACGT")
+    lower = row.replace("ACGT" * 8 + "A", "ACGT" * 4 + "a" + "CGT" + "ACGT" * 3 + "A")
+    tf = host.TensorFile((row + "\textra\tcols\n" + lower + "\n" + row).encode())
+    assert tf.n == 2
+    assert tf.field(0, 6) == "A" and tf.field(1, 6) == "A" and tf.field(0, 1) == "77"
+    assert tf.tensor[1].reshape(-1).tolist() == list(range(-561, 561))
+    assert tf.depth.tolist() == [12, 12]
+    with pytest.raises(_lib.CtoError):                       # a tensor field that is too short
+        host.TensorFile(("chr1\t77\t%s\t1 2 3\t12-\tsnv\tA\n" % ("ACGT" * 8 + "A")).encode())
