@@ -84,7 +84,7 @@ class ClockSampler:
                     power_w_max=max(float(r[3]) for r in rows), window=window)
 
 
-TRAFFIC_KERNEL = {"neg_gru2_recurrent": "gru3_kernel<192", "neg_gru1_recurrent": "gru3_kernel<128",
+TRAFFIC_KERNEL = {"neg_gru2_recurrent": "gru3_kernel<192", "neg_gru1_recurrent": "gru1_fused_kernel",
                   "encoder": "encode_pileup_kernel", "aff_stage1_fused": "aff_stage1_kernel"}
 
 
