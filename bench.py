@@ -119,12 +119,17 @@ def run_reference(args, rank, world):
     cores = len(os.sched_getaffinity(0))
     per_proc = args.cpu_sample
     times, vals, last = [], [], None
-    for step in range(args.warmup + args.steps):
-        r = cpu_baseline.run(per_proc=per_proc, procs=cores, seed=9000 + 17 * step)
-        if step >= args.warmup:
-            times.append(r["seconds"])
-            vals.append(r["value"])
-        last = r
+    pool, cores = cpu_baseline.make_pool(cores)          # workers import torch once, not once per step
+    try:
+        for step in range(args.warmup + args.steps):
+            r = cpu_baseline.run(per_proc=per_proc, procs=cores, seed=9000 + 17 * step, pool=pool)
+            if step >= args.warmup:
+                times.append(r["seconds"])
+                vals.append(r["value"])
+            last = r
+    finally:
+        pool.close()
+        pool.join()
     value = sum(vals) / len(vals)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * sum(times) / len(times), higher_is_better=True, scaling="weak", vs_baseline=None,

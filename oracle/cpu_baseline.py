@@ -65,13 +65,27 @@ def _worker(args):
     return total, t_enc, len(posts)
 
 
-def run(per_proc=300, procs=None, n_heads=4, seed=9000):
-    """Returns dict(value=candidates/s over all processes, cores, sample, seconds, encoder_share)."""
+def make_pool(procs=None):
+    """A pool of single-thread worker processes (spawned once: every worker imports torch, which costs seconds)."""
     import multiprocessing as mp
     procs = procs or len(os.sched_getaffinity(0))
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
+    return mp.get_context("spawn").Pool(procs), procs
+
+
+def run(per_proc=300, procs=None, n_heads=4, seed=9000, pool=None):
+    """Returns dict(value=candidates/s over all processes, cores, sample, seconds, encoder_share).  `pool` (from
+    make_pool) is reused when given, so that a multi-step run pays the process start-up once."""
+    own = pool is None
+    if own:
+        pool, procs = make_pool(procs)
+    else:
+        procs = procs or len(os.sched_getaffinity(0))
+    try:
         res = pool.map(_worker, [(seed + i, per_proc, n_heads) for i in range(procs)])
+    finally:
+        if own:
+            pool.close()
+            pool.join()
     slowest = max(r[0] for r in res)
     done = sum(r[2] for r in res)
     return dict(value=done / slowest, unit="candidate sites/s", cores=procs, kind="port",
