@@ -23,6 +23,18 @@ static int64_t g_launches = 0;
 void count_launch(int n) { __atomic_add_fetch(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
 int64_t launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
+int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    int v = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
+    if (!v) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        __atomic_store_n(&cached[dev], v, __ATOMIC_RELAXED);
+    }
+    return v;
+}
+
 int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off,
                          const uint8_t* ref_code, const int32_t* ind_off, const uint32_t* ind_entry,
                          const int32_t* win_pos, int64_t n_candidates, int low_bq_cut, int16_t* tensor,
@@ -202,9 +214,23 @@ int64_t cto_launch_count(void) { return launches(); }
 
 void cto_debug_set(int flags) { cto::g_gemm_debug = flags; }
 void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; }
-int cto_engine_set_tensor_cores(cto_engine* h, int enable) {
+int cto_engine_set_tensor_cores(cto_engine* h, int mode) {
     CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");
-    h->e.use_tc = enable != 0;
+    CTO_REQUIRE(mode >= 0 && mode <= 2, "engine_set_tensor_cores: mode %d (0 exact fp32, 1 tensor cores, 2 tensor cores without the fused AFF layers)", mode);
+    h->e.use_tc = mode != 0;
+    h->e.use_fused = mode == 1;
+    return 0;
+}
+
+int cto_aff_stage_layers(cto_engine* h, int stage, float* x_dev, int64_t n, void* stream) {
+    CTO_REQUIRE(h && x_dev, "aff_stage_layers: NULL argument");
+    return aff_stage_layers_on(h->e, stage, x_dev, n, (cudaStream_t)stream);
+}
+
+int cto_engine_fused_status(cto_engine* h, int32_t* out8) {
+    CTO_REQUIRE(h && out8, "engine_fused_status: NULL argument");
+    CTO_CHECK(cudaDeviceSynchronize());
+    CTO_CHECK(cudaMemcpy(out8, h->e.fused_dbg, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -38,6 +38,15 @@ const char* get_error();
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// SM count of the CURRENT device (cached per device; several engines on several GPUs may live in one process)
+int device_sm_count();
+// opt-in dynamic shared memory above 48 KB.  The attribute belongs to the (function, device) pair, so it is set on
+// every call instead of behind a process-wide flag (a second engine on another GPU failed to launch)
+template <typename F>
+static inline cudaError_t set_max_dynamic_smem(F* kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 // number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
 int64_t launches();

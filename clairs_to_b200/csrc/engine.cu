@@ -105,6 +105,9 @@ int aff_load(AffModel& m, const float* host_blob, int64_t n, const int32_t* cfg,
     m.feat = cin * win;
     walk_head(w, m.head, m.feat, m.n_heads);
     CTO_REQUIRE(w.off == n, "aff blob: %lld floats given, layout needs %lld", (long long)n, (long long)w.off);
+    for (int s = 0; s < m.n_stages; ++s)
+        if (aff_layers_fused_supported(m.st[s]) && !(s == 0 && aff_stage1_fused_supported(m.st[s])))
+            if (int rc = aff_fused_prepare(m.st[s], host_blob, m.ws.blob)) return rc;
     return 0;
 }
 
@@ -236,6 +239,12 @@ int engine_alloc(Engine& e, int64_t max_batch) {
     rc |= dev_alloc(e, &e.f2, b * 6 * FC_DIM);
     rc |= dev_alloc(e, &e.f1n, b * FC_DIM);
     rc |= dev_alloc(e, &e.f2n, b * 6 * FC_DIM);
+    {
+        float* d = nullptr;
+        rc |= dev_alloc(e, &d, 8);
+        e.fused_dbg = reinterpret_cast<int*>(d);
+        if (!rc) CTO_CHECK(cudaMemset(e.fused_dbg, 0, sizeof(int) * 8));
+    }
     if (rc) return 1;
     return 0;
 }
@@ -245,6 +254,7 @@ void engine_free(Engine& e) {
     e.allocs.clear();
     if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
     e.copy_stream = nullptr;
+    for (int s = 0; s < 3; ++s) aff_fused_release(e.aff.st[s]);
     release(e.aff.ws);
     release(e.neg.ws);
     release(e.neg.wih1_pad);
@@ -259,10 +269,30 @@ void engine_free(Engine& e) {
 }
 
 const char* prof_kind_name(int kind) {
-    static const char* names[PK_COUNT] = {"aff_forward", "aff_stage1_fused", "aff_gemm_1x1", "aff_embed_conv", "aff_channel_ln", "aff_dwconv", "aff_attention",
+    static const char* names[PK_COUNT] = {"aff_forward", "aff_stage1_fused", "aff_gemm_1x1", "aff_embed_conv", "aff_channel_ln", "aff_dwconv", "aff_attention", "aff_layers_fused",
                                           "aff_heads", "neg_proj1_gemm", "neg_gru1_recurrent", "neg_proj2_gemm",
                                           "neg_gru2_recurrent", "neg_fc1_gemm", "neg_heads"};
     return (kind >= 0 && kind < PK_COUNT) ? names[kind] : "?";
+}
+
+// AFF FLOP per candidate (multiply-add = 2 FLOP, 3-tap convolutions, attention products included):
+// part 0 = everything, 1 = the transformer layers of the stages that run in the fused kernel, 2 = first stage when it
+// runs in the CUDA-core fused kernel, 3 = heads
+static double aff_flops(const Engine& e, int part) {
+    const AffModel& m = e.aff;
+    double total = 0.0, layers_fused = 0.0, stage1 = 0.0;
+    for (int s = 0; s < m.n_stages; ++s) {
+        const CvtStage& st = m.st[s];
+        const double c = st.c, inner = st.heads * DIM_HEAD, w = st.wout, wkv = st.wkv;
+        const double embed = 2.0 * w * 3 * st.cin * c;
+        const double layer = 2.0 * (w * c * inner + wkv * c * 2 * inner + 2.0 * st.heads * w * wkv * DIM_HEAD + w * inner * c + 2.0 * w * c * 4 * c);
+        total += embed + st.depth * layer;
+        if (st.fused_stream) layers_fused += st.depth * layer;
+        if (s == 0 && aff_stage1_fused_supported(st)) stage1 = embed + st.depth * layer;
+    }
+    const double heads = 2.0 * (m.feat * FC_DIM + m.n_heads * (FC_DIM * FC_DIM + 2 * FC_DIM));
+    total += heads;
+    return part == 0 ? total : (part == 1 ? layers_fused : (part == 2 ? stage1 : heads));
 }
 
 // multiply-add = 2 FLOP; matches SURVEY.md section 8(d) accounting
@@ -270,6 +300,10 @@ double prof_kind_flops_per_candidate(const Engine& e, int kind) {
     const GruLayerW* l = e.neg.l;
     const double t = N_POS;
     switch (kind) {
+        case PK_AFF: return aff_flops(e, 0);
+        case PK_AFF_LAYERS: return e.use_tc && e.use_fused ? aff_flops(e, 1) : 0.0;
+        case PK_AFF_STAGE1: return aff_flops(e, 2);
+        case PK_AFF_HEADS: return aff_flops(e, 3);
         case PK_NEG_PROJ1: return 2.0 * t * l[0].in_dim * 6 * l[0].hidden;
         case PK_NEG_GRU1: return 2.0 * t * l[0].hidden * 6 * l[0].hidden + (e.neg.fuse_l1 && e.use_tc ? 2.0 * t * l[0].in_dim * 6 * l[0].hidden : 0.0);
         case PK_NEG_PROJ2: return 2.0 * t * l[1].in_dim * 6 * l[1].hidden;
@@ -330,18 +364,20 @@ int prof_collect(Engine& e, double* ms, int64_t* count) {
 
 #define RUN(x) do { if (int _rc = (x)) return _rc; } while (0)
 
-// dense contraction: tcgen05 bf16x3 when the engine allows it and the shape fits, CUDA-core fp32 otherwise
+// dense contraction: tcgen05 bf16x3 on the tensor-core engine, fp32 CUDA cores on the exact engine
+// (cto_engine_set_tensor_cores(e, 0)).  There is NO shape-driven fallback between the two: on the tensor-core engine a
+// shape the tcgen05 kernel cannot take is an error, except for the one product that is CUDA-core BY DESIGN
+// (`cuda_core_by_design`: the first stage's embed convolution, K = 3 * 34 = 102 is not a multiple of 8 and N <= 32).
 static int gemm(const Engine& e, const AView& a, const float* w, const float* bias, const float* residual, int64_t ldr,
-                float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s) {
-    if (e.use_tc && !a.conv && gemm_tc_supported(a.ptr, a.lda, w, m, n, k, c, ldc, residual, ldr)) {
-        const WeightSet* ws = e.aff.ws.owns(w) ? &e.aff.ws : (e.neg.ws.owns(w) ? &e.neg.ws : nullptr);
-        if (ws) {
-            const int64_t off = w - ws->blob;
-            if (off % SEG_ALIGN == 0)
-                return launch_gemm_tc(a.ptr, a.lda, ws->bhi + off, ws->bmid + off, bias, residual, ldr, c, ldc, m, n, k, act, s);
-        }
-    }
-    return launch_gemm_nt(a, w, bias, residual, ldr, c, ldc, m, n, k, act, s);
+                float* c, int64_t ldc, int64_t m, int n, int k, int act, cudaStream_t s, bool cuda_core_by_design = false) {
+    if (!e.use_tc || cuda_core_by_design) return launch_gemm_nt(a, w, bias, residual, ldr, c, ldc, m, n, k, act, s);
+    const WeightSet* ws = e.aff.ws.owns(w) ? &e.aff.ws : (e.neg.ws.owns(w) ? &e.neg.ws : nullptr);
+    CTO_REQUIRE(!a.conv && ws && (w - ws->blob) % SEG_ALIGN == 0 && gemm_tc_supported(a.ptr, a.lda, w, m, n, k, c, ldc, residual, ldr),
+                "tensor-core engine: no tcgen05 kernel for the product m=%lld n=%d k=%d (conv rows: %d); this network "
+                "configuration is not supported (use cto_engine_set_tensor_cores(e, 0) for the exact fp32 engine)",
+                (long long)m, n, k, a.conv);
+    const int64_t off = w - ws->blob;
+    return launch_gemm_tc(a.ptr, a.lda, ws->bhi + off, ws->bmid + off, bias, residual, ldr, c, ldc, m, n, k, act, s);
 }
 
 static int run_heads(const Engine& e, const HeadW& h, const float* feat, int feat_dim, int n_heads, int64_t n, float* f1, float* f2,
@@ -362,6 +398,82 @@ static int run_heads(const Engine& e, const HeadW& h, const float* feat, int fea
         RUN(prof_end(e, s));         \
     } while (0)
 
+// All transformer layers of one stage on the residual stream e.a_xs [n, wout, C], in place (clairs/model.py:143-147).
+static int aff_stage_layers(Engine& e, const CvtStage& st, int64_t n, cudaStream_t s) {
+    const AffModel& m = e.aff;
+    const int c = st.c, inner = st.heads * DIM_HEAD;
+    const int64_t rows = n * st.wout, rows_kv = n * st.wkv;
+    // every GEMM of a stage whose width is a multiple of 64 runs on the tensor cores, so the tensors between the
+    // kernels that only feed a GEMM travel as bf16 hi / mid planes (no converter pass in the GEMM)
+    if (e.use_tc && e.use_fused && st.fused_stream) {
+        // every transformer layer of the stage in one tcgen05 kernel, x stays in tensor memory (aff_fused.cu)
+        TIMED(PK_AFF_LAYERS, launch_aff_layers(st, e.a_xs, n, e.fused_dbg, s));
+        return 0;
+    }
+    const bool planes = e.use_tc && c % 64 == 0;
+    for (int d = 0; d < st.depth && planes; ++d) {
+        const CvtLayer& L = st.layers[d];
+        const WeightSet& ws = m.ws;
+        auto pg = [&](uint16_t* const* ap, int k, const float* w, const float* bias, int nn, int64_t mm) {
+            GemmTc g;
+            g.flags = GEMM_A_PRESPLIT;
+            g.a_hi = ap[0]; g.a_mid = ap[1]; g.lda = k;
+            g.w_hi = ws.bhi + (w - ws.blob); g.w_mid = ws.bmid + (w - ws.blob); g.ldw = k;
+            g.bias = bias; g.m = mm; g.n = nn; g.k = k;
+            return g;
+        };
+        TIMED(PK_AFF_DWCONV, launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, nullptr, nullptr, n, st.wout, st.wkv, c,
+                                              s, e.p_dq[0], e.p_dq[1], e.p_dkv[0], e.p_dkv[1]));
+        GemmTc g = pg(e.p_dq, c, L.q_pw, L.q_bias, inner, rows);
+        g.c = e.a_q; g.ldc = inner;
+        TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+        g = pg(e.p_dkv, c, L.kv_pw, L.kv_bias, 2 * inner, rows_kv);
+        g.c = e.a_kv; g.ldc = 2 * inner;
+        TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+        TIMED(PK_AFF_ATTENTION, launch_attention(e.a_q, e.a_kv, nullptr, n, st.wout, st.wkv, st.heads, s, e.p_att[0], e.p_att[1]));
+        g = pg(e.p_att, inner, L.out_w, L.out_b, c, rows);
+        g.c = e.a_xs; g.ldc = c; g.residual = e.a_xs; g.ldr = c;
+        TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+        TIMED(PK_AFF_LN, launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, nullptr, rows, c, s, e.p_y[0], e.p_y[1]));
+        g = pg(e.p_y, c, L.ff1_w, L.ff1_b, 4 * c, rows);
+        g.flags |= GEMM_OUT_SPLIT; g.c_hi = e.p_ff[0]; g.c_mid = e.p_ff[1]; g.ldc = 4 * c; g.act = ACT_GELU;
+        TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+        g = pg(e.p_ff, 4 * c, L.ff2_w, L.ff2_b, c, rows);
+        g.c = e.a_xs; g.ldc = c; g.residual = e.a_xs; g.ldr = c;
+        TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
+    }
+    for (int d = 0; d < st.depth && !planes; ++d) {
+        const CvtLayer& L = st.layers[d];
+        // x = Attention(LN(x)) + x   (clairs/model.py:145); LN and both depth-wise convs are one kernel
+        TIMED(PK_AFF_DWCONV, launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, e.a_dq, e.a_dkv, n, st.wout,
+                                              st.wkv, c, s));
+        TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c,
+                                ACT_NONE, s));
+        TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv,
+                                2 * inner, c, ACT_NONE, s));
+        TIMED(PK_AFF_ATTENTION, launch_attention(e.a_q, e.a_kv, e.a_att, n, st.wout, st.wkv, st.heads, s));
+        TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner,
+                                ACT_NONE, s));
+        // x = FF(LN(x)) + x          (clairs/model.py:146)
+        TIMED(PK_AFF_LN, launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, e.a_y, rows, c, s));
+        TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
+        TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c,
+                                ACT_NONE, s));
+    }
+    return 0;
+}
+
+// Kernel-level parity hook (cto_aff_stage_layers): the layers of stage `si` on a caller-provided residual stream.
+int aff_stage_layers_on(Engine& e, int si, float* x, int64_t n, cudaStream_t s) {
+    CTO_REQUIRE(si >= 0 && si < e.aff.n_stages && n <= e.max_batch, "aff_stage_layers: stage %d / batch %lld out of range", si, (long long)n);
+    const CvtStage& st = e.aff.st[si];
+    const size_t bytes = sizeof(float) * (size_t)n * st.wout * st.c;
+    CTO_CHECK(cudaMemcpyAsync(e.a_xs, x, bytes, cudaMemcpyDeviceToDevice, s));
+    RUN(aff_stage_layers(e, st, n, s));
+    CTO_CHECK(cudaMemcpyAsync(x, e.a_xs, bytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
 int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s) {
     CTO_REQUIRE(n <= e.max_batch, "aff_forward: batch %lld > engine max_batch %lld", (long long)n, (long long)e.max_batch);
     const AffModel& m = e.aff;
@@ -374,8 +486,8 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
     }
     for (int si = 0; si < m.n_stages; ++si) {
         const CvtStage& st = m.st[si];
-        const int c = st.c, inner = st.heads * DIM_HEAD;
-        const int64_t rows = n * st.wout, rows_kv = n * st.wkv;
+        const int c = st.c;
+        const int64_t rows = n * st.wout;
         if (si == 0 && e.use_tc && aff_stage1_fused_supported(st)) {
             TIMED(PK_AFF_STAGE1, launch_aff_stage1(st, cur, e.a_xs, n, s));
             cur = e.a_xs;
@@ -395,60 +507,9 @@ int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_
             RUN(prof_end(e, s));
         } else
         TIMED(PK_AFF_EMBED, gemm(e, conv_a(cur, st.win, st.wout, st.cin), st.embed_w, st.embed_b, nullptr, 0, e.a_t0, c, rows,
-                                 c, 3 * st.cin, ACT_NONE, s));
+                                 c, 3 * st.cin, ACT_NONE, s, /*cuda_core_by_design=*/si == 0));
         TIMED(PK_AFF_LN, launch_channel_ln(e.a_t0, st.ln_g, st.ln_b, e.a_xs, rows, c, s));
-        // every GEMM of a stage whose width is a multiple of 64 runs on the tensor cores, so the tensors between the
-        // kernels that only feed a GEMM travel as bf16 hi / mid planes (no converter pass in the GEMM)
-        const bool planes = e.use_tc && c % 64 == 0;
-        for (int d = 0; d < st.depth && planes; ++d) {
-            const CvtLayer& L = st.layers[d];
-            const WeightSet& ws = m.ws;
-            auto pg = [&](uint16_t* const* ap, int k, const float* w, const float* bias, int nn, int64_t mm) {
-                GemmTc g;
-                g.flags = GEMM_A_PRESPLIT;
-                g.a_hi = ap[0]; g.a_mid = ap[1]; g.lda = k;
-                g.w_hi = ws.bhi + (w - ws.blob); g.w_mid = ws.bmid + (w - ws.blob); g.ldw = k;
-                g.bias = bias; g.m = mm; g.n = nn; g.k = k;
-                return g;
-            };
-            TIMED(PK_AFF_DWCONV, launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, nullptr, nullptr, n, st.wout, st.wkv, c,
-                                                  s, e.p_dq[0], e.p_dq[1], e.p_dkv[0], e.p_dkv[1]));
-            GemmTc g = pg(e.p_dq, c, L.q_pw, L.q_bias, inner, rows);
-            g.c = e.a_q; g.ldc = inner;
-            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
-            g = pg(e.p_dkv, c, L.kv_pw, L.kv_bias, 2 * inner, rows_kv);
-            g.c = e.a_kv; g.ldc = 2 * inner;
-            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
-            TIMED(PK_AFF_ATTENTION, launch_attention(e.a_q, e.a_kv, nullptr, n, st.wout, st.wkv, st.heads, s, e.p_att[0], e.p_att[1]));
-            g = pg(e.p_att, inner, L.out_w, L.out_b, c, rows);
-            g.c = e.a_xs; g.ldc = c; g.residual = e.a_xs; g.ldr = c;
-            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
-            TIMED(PK_AFF_LN, launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, nullptr, rows, c, s, e.p_y[0], e.p_y[1]));
-            g = pg(e.p_y, c, L.ff1_w, L.ff1_b, 4 * c, rows);
-            g.flags |= GEMM_OUT_SPLIT; g.c_hi = e.p_ff[0]; g.c_mid = e.p_ff[1]; g.ldc = 4 * c; g.act = ACT_GELU;
-            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
-            g = pg(e.p_ff, 4 * c, L.ff2_w, L.ff2_b, c, rows);
-            g.c = e.a_xs; g.ldc = c; g.residual = e.a_xs; g.ldr = c;
-            TIMED(PK_AFF_GEMM, launch_gemm_tc_ex(g, s));
-        }
-        for (int d = 0; d < st.depth && !planes; ++d) {
-            const CvtLayer& L = st.layers[d];
-            // x = Attention(LN(x)) + x   (clairs/model.py:145); LN and both depth-wise convs are one kernel
-            TIMED(PK_AFF_DWCONV, launch_ln_dwconv(e.a_xs, L.ln1_g, L.ln1_b, L.q_dw, L.kv_dw, e.a_dq, e.a_dkv, n, st.wout,
-                                                  st.wkv, c, s));
-            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_dq, c), L.q_pw, L.q_bias, nullptr, 0, e.a_q, inner, rows, inner, c,
-                                    ACT_NONE, s));
-            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_dkv, c), L.kv_pw, L.kv_bias, nullptr, 0, e.a_kv, 2 * inner, rows_kv,
-                                    2 * inner, c, ACT_NONE, s));
-            TIMED(PK_AFF_ATTENTION, launch_attention(e.a_q, e.a_kv, e.a_att, n, st.wout, st.wkv, st.heads, s));
-            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_att, inner), L.out_w, L.out_b, e.a_xs, c, e.a_xs, c, rows, c, inner,
-                                    ACT_NONE, s));
-            // x = FF(LN(x)) + x          (clairs/model.py:146)
-            TIMED(PK_AFF_LN, launch_channel_ln(e.a_xs, L.ln2_g, L.ln2_b, e.a_y, rows, c, s));
-            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_y, c), L.ff1_w, L.ff1_b, nullptr, 0, e.a_ff, 4 * c, rows, 4 * c, c, ACT_GELU, s));
-            TIMED(PK_AFF_GEMM, gemm(e, plain_a(e.a_ff, 4 * c), L.ff2_w, L.ff2_b, e.a_xs, c, e.a_xs, c, rows, c, 4 * c,
-                                    ACT_NONE, s));
-        }
+        RUN(aff_stage_layers(e, st, n, s));
         // the next stage reads a_xs while writing a_t0, so no copy is needed
         cur = e.a_xs;
     }

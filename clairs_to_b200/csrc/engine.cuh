@@ -16,10 +16,21 @@ struct CvtLayer {
     const float *ln2_g, *ln2_b, *ff1_w, *ff1_b, *ff2_w, *ff2_b;
 };
 
+// per-layer small vectors of the fused transformer kernel (aff_fused.cu): device pointers into the weight blob, plus the
+// cumulative out-projection / FF2 biases (x lives in tensor memory WITHOUT them: x_true = x_tmem + cb)
+struct FusedLayerVecs {
+    const float *ln1_g, *ln1_b, *tq, *tk, *bq, *bkv, *ln2_g, *ln2_b, *b1, *cb1, *cb2;
+};
+
 struct CvtStage {
     int c, cin, heads, depth, win, wout, wkv;
     const float *embed_w, *embed_b, *ln_g, *ln_b;
     CvtLayer layers[MAX_DEPTH];
+    // fused transformer layers (aff_fused.cu): prepacked weight tile stream, vector table, cumulative biases
+    uint8_t* fused_stream = nullptr;
+    FusedLayerVecs* fused_vecs = nullptr;
+    float* fused_cb = nullptr;
+    long long fused_layer_bytes = 0;
 };
 
 struct HeadW {
@@ -85,7 +96,9 @@ struct Engine {
     int table_heads = 0;
     std::vector<void*> allocs;
     cudaStream_t copy_stream = nullptr;                        // H2D spans of cto_run_sites_host overlap the kernels
-    bool use_tc = true;                                        // dense contractions on tcgen05 (bf16x3) where shapes allow
+    bool use_tc = true;                                        // dense contractions on tcgen05 (bf16x3)
+    bool use_fused = true;                                     // AFF transformer layers in the fused kernel (aff_fused.cu)
+    int* fused_dbg = nullptr;                                  // device int[8]: barrier-timeout report of the fused kernel
     // optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
     int profile = 0;           // 0 off, 1 = NEG kernel families + AFF as one block, 2 = every AFF kernel family too
     struct ProfRec { int kind; cudaEvent_t start, stop; };
@@ -94,7 +107,7 @@ struct Engine {
     std::vector<cudaEvent_t> ev_free;
 };
 
-enum ProfKind { PK_AFF = 0, PK_AFF_STAGE1, PK_AFF_GEMM, PK_AFF_EMBED, PK_AFF_LN, PK_AFF_DWCONV, PK_AFF_ATTENTION, PK_AFF_HEADS, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
+enum ProfKind { PK_AFF = 0, PK_AFF_STAGE1, PK_AFF_GEMM, PK_AFF_EMBED, PK_AFF_LN, PK_AFF_DWCONV, PK_AFF_ATTENTION, PK_AFF_LAYERS, PK_AFF_HEADS, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
 const char* prof_kind_name(int kind);
 double prof_kind_flops_per_candidate(const Engine& e, int kind);
 int prof_begin(Engine& e, int kind, cudaStream_t s);
@@ -103,6 +116,11 @@ int prof_end(Engine& e, cudaStream_t s);
 int prof_collect(Engine& e, double* ms, int64_t* count);
 
 // whole first CvT stage in one kernel (aff_stage1.cu) when the stage has the predict.py shape (C=16, 1 head, depth 1)
+// all transformer layers of one stage in one tcgen05 kernel (aff_fused.cu); C = 32 / 64 / 128
+bool aff_layers_fused_supported(const CvtStage& st);
+int aff_fused_prepare(CvtStage& st, const float* host_blob, const float* dev_blob);
+void aff_fused_release(CvtStage& st);
+int launch_aff_layers(const CvtStage& st, float* x, int64_t n, int* dbg, cudaStream_t s);
 bool aff_stage1_fused_supported(const CvtStage& st);
 int launch_aff_stage1(const CvtStage& st, const float* x, float* out, int64_t n, cudaStream_t s);
 
@@ -114,6 +132,7 @@ void engine_free(Engine& e);
 // aff: x device fp32 [n, 33, 34]; neg: x device fp32 [n, 33, NEG_IN_LD] (zero padded);
 // logits: device fp32 [n, n_heads, 2]; n <= max_batch
 int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
+int aff_stage_layers_on(Engine& e, int si, float* x, int64_t n, cudaStream_t s);
 int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
 // the same from the encoder's int16 tensor [n, 33, 34] + per-candidate depth (depth rescale of clairs/predict.py:179-197 fused in)
 int neg_forward_from_counts(Engine& e, const int16_t* x, const int32_t* depth, int64_t n, float* logits, cudaStream_t s);

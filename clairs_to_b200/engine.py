@@ -111,9 +111,16 @@ class Engine:
         except Exception:
             pass
 
-    def set_tensor_cores(self, enable: bool):
-        """bf16x3 tcgen05 contractions (default) or the fp32 CUDA-core kernels everywhere."""
-        _lib.check(self.lib.cto_engine_set_tensor_cores(self.handle, 1 if enable else 0), "set_tensor_cores")
+    def set_tensor_cores(self, mode):
+        """0 / False: the exact fp32 CUDA-core engine; 1 / True (default): bf16x3 tcgen05 contractions with the fused
+        AFF transformer kernel; 2: tcgen05 contractions with one kernel per op (round-1 layers, kept for A/B tests)."""
+        _lib.check(self.lib.cto_engine_set_tensor_cores(self.handle, int(mode)), "set_tensor_cores")
+
+    def fused_status(self):
+        """Watchdog record of the fused AFF kernel (synchronises): all zeros unless an in-kernel barrier wait timed out."""
+        out = np.zeros(8, np.int32)
+        _lib.check(self.lib.cto_engine_fused_status(self.handle, _ptr(out)), "fused_status")
+        return out
 
     def set_likelihood(self, path_or_array):
         tables = np.ascontiguousarray(likelihood_tables(path_or_array, self.n_heads))

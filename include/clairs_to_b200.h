@@ -107,7 +107,22 @@ int cto_posterior_from_probs(const double* tables_host, int n_heads, const doubl
  * own kernels) bit 1 = A handed over as pre-split bf16 planes, bit 2 = C produced as bf16 planes, bit 3 =
  * bias indexed by the output row and n-major tile order (the transposed input projections of the GRU).
  */
-int cto_engine_set_tensor_cores(cto_engine* e, int enable);
+int cto_engine_set_tensor_cores(cto_engine* e, int mode);
+/*
+ * mode 1 (default) additionally runs all transformer layers of a CvT stage (clairs/model.py:134-147) in ONE tcgen05
+ * kernel that keeps the stage's residual stream in tensor memory (csrc/aff_fused.cu); mode 2 = tensor cores with the
+ * round-1 kernel-per-op layers (kept for A/B parity tests).  There is no shape-driven fallback from the tensor-core
+ * engine to the CUDA-core kernels: an unsupported network configuration is an error.
+ * cto_engine_fused_status: synchronises and copies the fused kernel's watchdog record (int32[8]; [0] != 0 means an
+ * in-kernel barrier wait timed out: [0] barrier code, [1] CTA, [2] thread, [3] parity).
+ */
+int cto_engine_fused_status(cto_engine* e, int32_t* out8);
+/*
+ * Kernel-level building block, like cto_gemm_nt: all transformer layers (x += Attention(LN(x)); x += FF(LN(x)),
+ * clairs/model.py:143-147) of CvT stage `stage` (0-based) on a residual stream x fp32 [n, W_stage, C_stage]
+ * (channels-last, device memory, in place), on whichever engine mode is selected.  n <= max_batch.
+ */
+int cto_aff_stage_layers(cto_engine* e, int stage, float* x_dev, int64_t n, void* stream);
 int cto_gemm_nt(const float* a_dev, int64_t lda, const float* w_dev, const float* bias_dev, const float* residual_dev,
                 int64_t ldr, float* c_dev, int64_t ldc, int64_t m, int n, int k, int act, int use_tensor_cores,
                 void* stream);
