@@ -40,6 +40,7 @@ SIGNATURES = {
     "cto_launch_count": (I64, []),
     "cto_debug_set": (None, [INT]),
     "cto_debug_timing": (None, [P]),
+    "cto_debug_timing_fused": (None, [P]),
     "cto_engine_profile": (INT, [P, INT]),
     "cto_engine_profile_kinds": (INT, []),
     "cto_engine_profile_name": (C.c_char_p, [INT]),

@@ -27,7 +27,7 @@
 //   * per head: q | k | v accumulators (192 TMEM columns, double buffered), attention output -> A planes of the
 //     out-projection; feed-forward hidden units in chunks of 64 (six 64-column accumulators), GELU -> A planes of FF2.
 //
-// Warp roles: 0 weight producer, 1 MMA issuer (+ TMEM allocation), 4-7 compute group A (everything), 8-11 group B
+// Warp roles: 0 weight producer, 1 MMA issuer (+ TMEM allocation), 2-5 compute group A (everything), 6-9 group B
 // (odd feed-forward chunks).  Every mbarrier wait is bounded: on a timeout the kernel records which barrier stalled
 // in p.dbg and unwinds instead of hanging the GPU.
 #include "engine.cuh"
@@ -44,7 +44,7 @@ constexpr int ROWS = 128;
 constexpr int TILE_A = ROWS * 128;            // 16 KB: one [128 rows x 64 k] bf16 plane k-block
 constexpr int WTILE = 64 * 128;               // 8 KB:  one [64 n x 64 k] bf16 weight plane tile
 constexpr int WSTAGE = 2 * WTILE;             // hi | mid
-constexpr int THREADS = 384;                  // 12 warps
+constexpr int THREADS = 320;                  // 10 warps: 204 registers per thread
 constexpr int NB = 6;                         // feed-forward hidden accumulators (64 TMEM columns each)
 constexpr int LAG = 2;                        // FF1 MMAs run this many chunks ahead of FF2
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
@@ -74,6 +74,7 @@ struct Params {
     int W, WKV, heads, depth;
     int tiles, cpw;               // tiles of 4 * cpw candidates; cpw = candidates per warp = 32 / W
     int* dbg;                     // [8] abort flag + diagnostics
+    long long* timing;            // optional [32] per-phase clock64() sums of CTA 0 (profiles/phase_timing_aff.py); nullptr in production
 };
 
 // ---- PTX helpers not in gru_ptx.cuh ------------------------------------------------------------------------
@@ -201,30 +202,56 @@ __device__ __forceinline__ uint32_t f_idesc64() {
 // barrier codes reported in dbg[0] on a timeout
 enum { B_WFULL = 1, B_WEMPTY, B_AB, B_QKVFULL, B_QKVFREE, B_PCREADY, B_PCFREE, B_XREADY, B_Y2, B_HIDFULL, B_HIDFREE, B_LAYER };
 
-// channel LayerNorm of one row held in registers (clairs/model.py:57-67): population std, eps added to the std
+// channel LayerNorm (clairs/model.py:57-67): population std over the C channels of a row, eps added to the std.
+// The row lives in tensor memory (x_true = x_tmem + cb); statistics with the shifted-data formulas (shift = first channel).
 template <int C>
-__device__ __forceinline__ void f_layernorm(float* v, const float* __restrict__ g, const float* __restrict__ b) {
-    float sum = 0.0f;
+__device__ __forceinline__ void f_row_stats(uint32_t trow, const float* __restrict__ cb, float& mean, float& inv) {
+    float s1 = 0.0f, s2 = 0.0f, shift = 0.0f;
     #pragma unroll
-    for (int c = 0; c < C; ++c) sum += v[c];
-    const float mean = sum * (1.0f / (float)C);
-    float sq = 0.0f;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        float v[32];
+        f_tmem_ld32(trow + (uint32_t)c0, v);
+        f_wait_ld();
+        #pragma unroll
+        for (int c4 = 0; c4 < 32; c4 += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(cb + c0 + c4));
+            v[c4] += t.x; v[c4 + 1] += t.y; v[c4 + 2] += t.z; v[c4 + 3] += t.w;
+        }
+        if (c0 == 0) shift = v[0];
+        float a1 = 0.0f, a2 = 0.0f, b1 = 0.0f, b2 = 0.0f;
+        #pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+            const float d0 = v[c] - shift, d1 = v[c + 1] - shift;
+            a1 += d0; a2 = fmaf(d0, d0, a2);
+            b1 += d1; b2 = fmaf(d1, d1, b2);
+        }
+        s1 += a1 + b1;
+        s2 += a2 + b2;
+    }
+    const float m = s1 * (1.0f / (float)C);
+    mean = shift + m;
+    const float var = fmaxf(s2 * (1.0f / (float)C) - m * m, 0.0f);
+    inv = 1.0f / (sqrtf(var) + 1e-5f);
+}
+// 32 channels of the row: (x_tmem + cb - mean) * inv * g + b
+__device__ __forceinline__ void f_normalise32(float* v, const float* __restrict__ cb, const float* __restrict__ g,
+                                              const float* __restrict__ b, float mean, float inv) {
     #pragma unroll
-    for (int c = 0; c < C; ++c) { v[c] -= mean; sq = fmaf(v[c], v[c], sq); }
-    const float inv = 1.0f / (sqrtf(sq * (1.0f / (float)C)) + 1e-5f);
-    #pragma unroll
-    for (int c4 = 0; c4 < C; c4 += 4) {
+    for (int c4 = 0; c4 < 32; c4 += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(cb + c4));
         const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c4)), bv = __ldg(reinterpret_cast<const float4*>(b + c4));
-        v[c4] = fmaf(v[c4] * inv, gv.x, bv.x);
-        v[c4 + 1] = fmaf(v[c4 + 1] * inv, gv.y, bv.y);
-        v[c4 + 2] = fmaf(v[c4 + 2] * inv, gv.z, bv.z);
-        v[c4 + 3] = fmaf(v[c4 + 3] * inv, gv.w, bv.w);
+        v[c4] = fmaf((v[c4] + t.x - mean) * inv, gv.x, bv.x);
+        v[c4 + 1] = fmaf((v[c4 + 1] + t.y - mean) * inv, gv.y, bv.y);
+        v[c4 + 2] = fmaf((v[c4 + 2] + t.z - mean) * inv, gv.z, bv.z);
+        v[c4 + 3] = fmaf((v[c4 + 3] + t.w - mean) * inv, gv.w, bv.w);
     }
 }
 
-template <int C>
+template <int C, int W>
 __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) {
     using K = Cfg<C>;
+    constexpr int WKV = (W + 1) / 2;                  // keys per candidate (stride-2 projection)
+    constexpr int CPW = 32 / W;                       // candidates per warp
     constexpr int CP = K::CP, KB = K::KB, NT = K::NT, NH = K::NH, NPC = K::NPC, WST = K::WST;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (g_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -249,6 +276,10 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* dbg = p.dbg;
+    const bool tim = p.timing != nullptr && blockIdx.x == 0;
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = tim ? clock64() : 0;
+    #define FTOC(i) do { if (tim) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } } while (0)
     const int heads = p.heads, depth = p.depth;
     const int tiles_per_layer = heads * (3 * KB + NT) + NH * (KB + NT);
 
@@ -302,7 +333,9 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
         auto product = [&](uint32_t d_col, const uint8_t* a_hi, const uint8_t* a_mid, int nkb, bool acc_first) -> bool {
             for (int kb = 0; kb < nkb; ++kb, ++wit) {
                 const int s = wit % WST;
+                FTOC(0);
                 if (!f_wait(&w_full[s], (wit / WST) & 1, B_WFULL, dbg)) return false;
+                FTOC(1);
                 f_fence_after();
                 const uint64_t d_ahi = g_desc_k_sw128(g_smem_u32(a_hi + kb * TILE_A));
                 const uint64_t d_amid = g_desc_k_sw128(g_smem_u32(a_mid + kb * TILE_A));
@@ -325,7 +358,9 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
         // x[:, nt*64 .. +64) += PC[p] * W_tile(nt)^T  for the plane buffer of use `pit`
         auto onto_x = [&](uint32_t pit) -> bool {
             const int pbuf = pit % NPC;
+            FTOC(0);
             if (!f_wait(&pc_ready[pbuf], (pit / NPC) & 1, B_PCREADY, dbg)) return false;
+            FTOC(2);
             f_fence_after();
             const uint8_t* a = pc + pbuf * K::PCBUF;
             for (int nt = 0; nt < NT; ++nt)
@@ -342,11 +377,15 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
         for (int tile = blockIdx.x; tile < p.tiles && alive; tile += gridDim.x) {
             for (int l = 0; l < depth && alive; ++l, ++lit) {
                 const uint32_t pit0 = lit * (uint32_t)(heads + NH);
+                FTOC(0);
                 if (!f_wait(ab_ready, lit & 1, B_AB, dbg)) { alive = false; break; }
+                FTOC(3);
                 f_fence_after();
                 for (int h = 0; h < heads && alive; ++h) {
                     const uint32_t hit = lit * (uint32_t)heads + h, b = hit & 1;
+                    FTOC(0);
                     if (!f_wait(&qkv_free[b], ((hit >> 1) & 1) ^ 1, B_QKVFREE, dbg)) { alive = false; break; }
+                    FTOC(4);
                     f_fence_after();
                     const uint32_t acc = tmem_base + (uint32_t)(CP + b * 192);
                     alive = product(acc, pa, pa + KB * TILE_A, KB, false) &&
@@ -361,11 +400,15 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                 if (!onto_x(pit0 + heads - 1)) { alive = false; break; }
                 if (g_elect_one()) g_commit(x_ready);
                 __syncwarp();
+                FTOC(0);
                 if (!f_wait(y2_ready, lit & 1, B_Y2, dbg)) { alive = false; break; }
+                FTOC(5);
                 f_fence_after();
                 for (int j = 0; j < NH && alive; ++j) {
                     const uint32_t cit = lit * (uint32_t)NH + j, hb = cit % NB;
+                    FTOC(0);
                     if (!f_wait(&hid_free[hb], ((cit / NB) & 1) ^ 1, B_HIDFREE, dbg)) { alive = false; break; }
+                    FTOC(6);
                     f_fence_after();
                     if (!product(tmem_base + (uint32_t)(CP + hb * 64), pa, pa + KB * TILE_A, KB, false)) { alive = false; break; }
                     if (g_elect_one()) g_commit(&hid_full[hb]);
@@ -378,11 +421,13 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                 __syncwarp();
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+        FTOC(0);
+        if (tim && lane == 0) { for (int i = 0; i < 7; ++i) p.timing[i] = tacc[i]; p.timing[7] = (long long)lit; }
+    } else if (warp < 6) {
         // ---- compute group A: one thread per row (TMEM lane = row) ----
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int W = p.W, WKV = p.WKV, cpw = p.cpw;
+        constexpr int cpw = CPW;
         const int cl = lane / W, w = lane - cl * W;                    // candidate inside the warp, position
         const bool lane_ok = lane < cpw * W;
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -409,70 +454,77 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                 f_tmem_st32(trow + (uint32_t)c0, v);
             }
             f_wait_st();
+            FTOC(0);
             for (int l = 0; l < depth && alive; ++l, ++lit) {
                 const FusedLayerVecs lv = p.vecs[l];
                 const uint32_t pit0 = lit * (uint32_t)(heads + NH);
                 // ---------- LN1 + depth-wise convolutions -> dq (PA), dkv (PB) ----------
+                // The row is read from tensor memory twice, 32 columns at a time: statistics, then normalise + convolve +
+                // store (the whole 128-channel row in registers left no room for batched shuffles).
                 {
-                    float v[C];
+                    float mean, inv;
+                    f_row_stats<C>(trow, lv.cb1, mean, inv);
                     #pragma unroll
-                    for (int c0 = 0; c0 < C; c0 += 32) f_tmem_ld32(trow + (uint32_t)c0, v + c0);
-                    f_wait_ld();
-                    #pragma unroll
-                    for (int c4 = 0; c4 < C; c4 += 4) {                // x_true = x_tmem + biases accumulated so far
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(lv.cb1 + c4));
-                        v[c4] += t.x; v[c4 + 1] += t.y; v[c4 + 2] += t.z; v[c4 + 3] += t.w;
-                    }
-                    f_layernorm<C>(v, lv.ln1_g, lv.ln1_b);
-                    #pragma unroll
-                    for (int c8 = 0; c8 < CP; c8 += 8) {
-                        float dq[8], dk[8];
-                        if (c8 < C) {
-                            float t0[8], t1[8], t2[8], k0[8], k1[8], k2[8];
-                            #pragma unroll
-                            for (int h4 = 0; h4 < 8; h4 += 4) {
-                                const float4 a0 = __ldg(reinterpret_cast<const float4*>(lv.tq + c8 + h4));
-                                const float4 a1 = __ldg(reinterpret_cast<const float4*>(lv.tq + C + c8 + h4));
-                                const float4 a2 = __ldg(reinterpret_cast<const float4*>(lv.tq + 2 * C + c8 + h4));
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(lv.tk + c8 + h4));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(lv.tk + C + c8 + h4));
-                                const float4 b2 = __ldg(reinterpret_cast<const float4*>(lv.tk + 2 * C + c8 + h4));
-                                t0[h4] = a0.x; t0[h4 + 1] = a0.y; t0[h4 + 2] = a0.z; t0[h4 + 3] = a0.w;
-                                t1[h4] = a1.x; t1[h4 + 1] = a1.y; t1[h4 + 2] = a1.z; t1[h4 + 3] = a1.w;
-                                t2[h4] = a2.x; t2[h4 + 1] = a2.y; t2[h4 + 2] = a2.z; t2[h4 + 3] = a2.w;
-                                k0[h4] = b0.x; k0[h4 + 1] = b0.y; k0[h4 + 2] = b0.z; k0[h4 + 3] = b0.w;
-                                k1[h4] = b1.x; k1[h4 + 1] = b1.y; k1[h4 + 2] = b1.z; k1[h4 + 3] = b1.w;
-                                k2[h4] = b2.x; k2[h4 + 1] = b2.y; k2[h4 + 2] = b2.z; k2[h4 + 3] = b2.w;
-                            }
-                            #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float y = v[c8 + e];
-                                float up = __shfl_up_sync(0xffffffffu, y, 1), dn = __shfl_down_sync(0xffffffffu, y, 1);
-                                up = has_up ? up : 0.0f;
-                                dn = has_dn ? dn : 0.0f;
-                                // taps in position order, pad 1 (zero rows outside the candidate); BN scale folded on the host
-                                dq[e] = fmaf(dn, t2[e], fmaf(y, t1[e], up * t0[e]));
-                                const float kvv = fmaf(dn, k2[e], fmaf(y, k1[e], up * k0[e]));
-                                dk[e] = kv_row ? kvv : 0.0f;          // stride-2 conv = stride-1 conv at even positions
-                                if (!lane_ok) dq[e] = 0.0f;
-                            }
-                        } else {
-                            #pragma unroll
-                            for (int e = 0; e < 8; ++e) { dq[e] = 0.0f; dk[e] = 0.0f; }
+                    for (int c0 = 0; c0 < CP; c0 += 32) {
+                        float v[32];
+                        if (c0 < C) {
+                            f_tmem_ld32(trow + (uint32_t)c0, v);
+                            f_wait_ld();
+                            f_normalise32(v, lv.cb1 + c0, lv.ln1_g + c0, lv.ln1_b + c0, mean, inv);
                         }
-                        const int kb = c8 >> 6, ch = (c8 & 63) >> 3;
-                        f_store8(pa + kb * TILE_A, pa_mid + kb * TILE_A, row, ch, dq);
-                        f_store8(pb + kb * TILE_A, pb_mid + kb * TILE_A, row, ch, dk);
+                        #pragma unroll
+                        for (int c8 = 0; c8 < 32; c8 += 8) {
+                            float dq[8], dk[8];
+                            if (c0 < C) {
+                                // neighbour rows by warp shuffles, issued as a batch (a shuffle feeding its own FMA serialises
+                                // on the shuffle latency: measured 10 cycles per instruction)
+                                float up[8], dn[8];
+                                #pragma unroll
+                                for (int e = 0; e < 8; ++e) up[e] = __shfl_up_sync(0xffffffffu, v[c8 + e], 1);
+                                #pragma unroll
+                                for (int e = 0; e < 8; ++e) dn[e] = __shfl_down_sync(0xffffffffu, v[c8 + e], 1);
+                                #pragma unroll
+                                for (int h4 = 0; h4 < 8; h4 += 4) {
+                                    const int c = c0 + c8 + h4;
+                                    const float4 a0 = __ldg(reinterpret_cast<const float4*>(lv.tq + c));
+                                    const float4 a1 = __ldg(reinterpret_cast<const float4*>(lv.tq + C + c));
+                                    const float4 a2 = __ldg(reinterpret_cast<const float4*>(lv.tq + 2 * C + c));
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(lv.tk + c));
+                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(lv.tk + C + c));
+                                    const float4 b2 = __ldg(reinterpret_cast<const float4*>(lv.tk + 2 * C + c));
+                                    const float t0[4] = {a0.x, a0.y, a0.z, a0.w}, t1[4] = {a1.x, a1.y, a1.z, a1.w}, t2[4] = {a2.x, a2.y, a2.z, a2.w};
+                                    const float k0[4] = {b0.x, b0.y, b0.z, b0.w}, k1[4] = {b1.x, b1.y, b1.z, b1.w}, k2[4] = {b2.x, b2.y, b2.z, b2.w};
+                                    #pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float y = v[c8 + h4 + e];
+                                        const float u = has_up ? up[h4 + e] : 0.0f, dd = has_dn ? dn[h4 + e] : 0.0f;
+                                        // taps in position order, pad 1 (zero rows outside the candidate); BN scale folded on the host
+                                        const float qv = fmaf(dd, t2[e], fmaf(y, t1[e], u * t0[e]));
+                                        const float kvv = fmaf(dd, k2[e], fmaf(y, k1[e], u * k0[e]));
+                                        dq[h4 + e] = lane_ok ? qv : 0.0f;
+                                        dk[h4 + e] = kv_row ? kvv : 0.0f;   // stride-2 conv = stride-1 conv at even positions
+                                    }
+                                }
+                            } else {
+                                #pragma unroll
+                                for (int e = 0; e < 8; ++e) { dq[e] = 0.0f; dk[e] = 0.0f; }
+                            }
+                            const int cc = c0 + c8, kb = cc >> 6, ch = (cc & 63) >> 3;
+                            f_store8(pa + kb * TILE_A, pa_mid + kb * TILE_A, row, ch, dq);
+                            f_store8(pb + kb * TILE_A, pb_mid + kb * TILE_A, row, ch, dk);
+                        }
                     }
                 }
                 f_fence_async();
                 f_fence_before();
                 __syncwarp();
                 if (lane == 0) g_mbar_arrive(ab_ready);
+                FTOC(1);
                 // ---------- attention, head by head ----------
                 for (int h = 0; h < heads && alive; ++h) {
                     const uint32_t hit = lit * (uint32_t)heads + h, b = hit & 1;
                     if (!f_wait(&qkv_full[b], (hit >> 1) & 1, B_QKVFULL, dbg)) { alive = false; break; }
+                    FTOC(2);
                     f_fence_after();
                     const uint32_t acc = trow + (uint32_t)(CP + b * 192);
                     float q[64], kv[64];
@@ -494,12 +546,19 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                     float s[9];
                     const int src0 = cl * W;
                     #pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        s[j] = 0.0f;
-                        if (j < WKV) {
-                            const int src = src0 + 2 * j;
-                            #pragma unroll
-                            for (int d = 0; d < 64; ++d) s[j] = fmaf(q[d], __shfl_sync(0xffffffffu, kv[d], src), s[j]);
+                    for (int j = 0; j < 9; ++j) s[j] = 0.0f;
+                    #pragma unroll
+                    for (int d0 = 0; d0 < 64; d0 += 8) {
+                        #pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            if (j < WKV) {
+                                const int src = src0 + 2 * j;
+                                float t[8];
+                                #pragma unroll
+                                for (int e = 0; e < 8; ++e) t[e] = __shfl_sync(0xffffffffu, kv[d0 + e], src);   // batch of shuffles first
+                                #pragma unroll
+                                for (int e = 0; e < 8; ++e) s[j] = fmaf(q[d0 + e], t[e], s[j]);
+                            }
                         }
                     }
                     float mx = s[0];
@@ -523,24 +582,36 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                         kv[d4] += c.x; kv[d4 + 1] += c.y; kv[d4 + 2] += c.z; kv[d4 + 3] += c.w;
                     }
                     #pragma unroll
-                    for (int d = 0; d < 64; ++d) q[d] = 0.0f;
+                    for (int j = 0; j < 9; ++j) s[j] *= inv;
                     #pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        if (j < WKV) {
-                            const int src = src0 + 2 * j;
-                            const float pj = s[j] * inv;
-                            #pragma unroll
-                            for (int d = 0; d < 64; ++d) q[d] = fmaf(pj, __shfl_sync(0xffffffffu, kv[d], src), q[d]);
+                    for (int d0 = 0; d0 < 64; d0 += 8) {
+                        float o[8];
+                        #pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+                        #pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            if (j < WKV) {
+                                const int src = src0 + 2 * j;
+                                float t[8];
+                                #pragma unroll
+                                for (int e = 0; e < 8; ++e) t[e] = __shfl_sync(0xffffffffu, kv[d0 + e], src);
+                                #pragma unroll
+                                for (int e = 0; e < 8; ++e) o[e] = fmaf(s[j], t[e], o[e]);
+                            }
                         }
+                        #pragma unroll
+                        for (int e = 0; e < 8; ++e) q[d0 + e] = o[e];
                     }
                     __syncwarp();
                     if (lane == 0) g_mbar_arrive(&qkv_free[b]);                // every TMEM read of this buffer has completed
                     const uint32_t pit = pit0 + h;
                     const int pbuf = pit % NPC;
+                    FTOC(3);
                     if (pit >= (uint32_t)NPC) {                                // the MMAs that read the buffer's previous use have retired
                         if (!f_wait(&pc_free[pbuf], fcnt[pbuf] & 1, B_PCFREE, dbg)) { alive = false; break; }
                         ++fcnt[pbuf];
                     }
+                    FTOC(4);
                     uint8_t* pch = pc + pbuf * K::PCBUF;
                     #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) f_store8(pch, pch + TILE_A, row, ch, q + 8 * ch);
@@ -550,36 +621,41 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                 }
                 if (!alive) break;
                 // ---------- LN2 -> PA ----------
+                FTOC(3);
                 if (!f_wait(x_ready, lit & 1, B_XREADY, dbg)) { alive = false; break; }
+                FTOC(5);
                 f_fence_after();
                 {
-                    float v[C];
+                    float mean, inv;
+                    f_row_stats<C>(trow, lv.cb2, mean, inv);
                     #pragma unroll
-                    for (int c0 = 0; c0 < C; c0 += 32) f_tmem_ld32(trow + (uint32_t)c0, v + c0);
-                    f_wait_ld();
-                    #pragma unroll
-                    for (int c4 = 0; c4 < C; c4 += 4) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(lv.cb2 + c4));
-                        v[c4] += t.x; v[c4 + 1] += t.y; v[c4 + 2] += t.z; v[c4 + 3] += t.w;
-                    }
-                    f_layernorm<C>(v, lv.ln2_g, lv.ln2_b);
-                    #pragma unroll
-                    for (int c8 = 0; c8 < CP; c8 += 8) {
-                        float z[8];
+                    for (int c0 = 0; c0 < CP; c0 += 32) {
+                        float v[32];
+                        if (c0 < C) {
+                            f_tmem_ld32(trow + (uint32_t)c0, v);
+                            f_wait_ld();
+                            f_normalise32(v, lv.cb2 + c0, lv.ln2_g + c0, lv.ln2_b + c0, mean, inv);
+                        }
                         #pragma unroll
-                        for (int e = 0; e < 8; ++e) z[e] = (c8 < C && lane_ok) ? v[(c8 < C ? c8 : 0) + e] : 0.0f;
-                        const int kb = c8 >> 6, ch = (c8 & 63) >> 3;
-                        f_store8(pa + kb * TILE_A, pa_mid + kb * TILE_A, row, ch, z);
+                        for (int c8 = 0; c8 < 32; c8 += 8) {
+                            float z[8];
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) z[e] = (c0 < C && lane_ok) ? v[c8 + e] : 0.0f;
+                            const int cc = c0 + c8, kb = cc >> 6, ch = (cc & 63) >> 3;
+                            f_store8(pa + kb * TILE_A, pa_mid + kb * TILE_A, row, ch, z);
+                        }
                     }
                 }
                 f_fence_async();
                 f_fence_before();
                 __syncwarp();
                 if (lane == 0) g_mbar_arrive(y2_ready);
+                FTOC(6);
                 // ---------- feed-forward hidden chunks (even ones; group B takes the odd ones) ----------
                 for (int j = 0; j < NH && alive; j += 2) {
                     const uint32_t cit = lit * (uint32_t)NH + j, hb = cit % NB;
                     if (!f_wait(&hid_full[hb], (cit / NB) & 1, B_HIDFULL, dbg)) { alive = false; break; }
+                    FTOC(7);
                     f_fence_after();
                     float hdn[64];
                     f_tmem_ld32(trow + (uint32_t)(CP + hb * 64), hdn);
@@ -597,19 +673,23 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                     }
                     const uint32_t pit = pit0 + heads + j;
                     const int pbuf = pit % NPC;
+                    FTOC(8);
                     if (pit >= (uint32_t)NPC) {
                         if (!f_wait(&pc_free[pbuf], fcnt[pbuf] & 1, B_PCFREE, dbg)) { alive = false; break; }
                         ++fcnt[pbuf];
                     }
+                    FTOC(4);
                     uint8_t* pch = pc + pbuf * K::PCBUF;
                     #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) f_store8(pch, pch + TILE_A, row, ch, hdn + 8 * ch);
                     f_fence_async();
                     __syncwarp();
                     if (lane == 0) g_mbar_arrive(&pc_ready[pbuf]);
+                    FTOC(8);
                 }
                 if (!alive) break;
                 if (!f_wait(layer_done, lit & 1, B_LAYER, dbg)) { alive = false; break; }
+                FTOC(9);
                 f_fence_after();
             }
             if (!alive) break;
@@ -629,8 +709,10 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                 }
             }
             f_fence_before();
+            FTOC(10);
         }
-    } else if (warp >= 8) {
+        if (tim && warp == 4 && lane == 0) { for (int i = 0; i < 11; ++i) p.timing[8 + i] = tacc[i]; }
+    } else {
         // ---- compute group B: the odd feed-forward chunks ----
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
@@ -676,6 +758,7 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
             }
         }
     }
+    #undef FTOC
     f_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -720,9 +803,11 @@ static void emit_tile(std::vector<uint8_t>& out, const float* w, int n_total, in
 
 }  // namespace fz
 
+long long* g_fused_timing = nullptr;     // cto_debug_timing_fused(): device buffer [32], debug only
+
 bool aff_layers_fused_supported(const CvtStage& st) {
     if (!(st.c == 32 || st.c == 64 || st.c == 128)) return false;
-    if (st.depth < 1 || st.heads < 1 || st.wout > 32 || st.wkv > 9 || st.wkv != (st.wout + 1) / 2) return false;
+    if (st.depth < 1 || st.heads < 1 || !(st.wout == 17 || st.wout == 9 || st.wout == 5) || st.wkv != (st.wout + 1) / 2) return false;
     return true;
 }
 
@@ -791,11 +876,18 @@ void aff_fused_release(CvtStage& st) {
     st.fused_cb = nullptr;
 }
 
-template <int C>
+template <int C, int W>
 static int launch_layers_t(const fz::Params& p, int grid, cudaStream_t s) {
-    CTO_CHECK(set_max_dynamic_smem(fz::aff_layers_kernel<C>, fz::Cfg<C>::SMEM));
-    fz::aff_layers_kernel<C><<<grid, fz::THREADS, fz::Cfg<C>::SMEM, s>>>(p);
+    CTO_CHECK(set_max_dynamic_smem(fz::aff_layers_kernel<C, W>, fz::Cfg<C>::SMEM));
+    fz::aff_layers_kernel<C, W><<<grid, fz::THREADS, fz::Cfg<C>::SMEM, s>>>(p);
     return 0;
+}
+template <int C>
+static int launch_layers_w(const fz::Params& p, int grid, cudaStream_t s) {
+    // the stage widths of a 33-position input: 17 -> 9 -> 5 (3-tap, stride 2, pad 1)
+    if (p.W == 17) return launch_layers_t<C, 17>(p, grid, s);
+    if (p.W == 9) return launch_layers_t<C, 9>(p, grid, s);
+    return launch_layers_t<C, 5>(p, grid, s);
 }
 
 // x: fp32 [n, W, C], the stage's residual stream after the embed convolution + LN; all `depth` layers in place.
@@ -822,13 +914,14 @@ int launch_aff_layers(const CvtStage& st, float* x, int64_t n, int* dbg, cudaStr
     CTO_REQUIRE(tiles < (1ll << 31), "aff_layers: too many tiles");
     p.tiles = (int)tiles;
     p.dbg = dbg;
+    p.timing = g_fused_timing;
     const int sms = device_sm_count();
     CTO_REQUIRE(sms > 0, "aff_layers: no device");
     const int grid = (int)(tiles < sms ? tiles : sms);
     int rc;
-    if (st.c == 32) rc = launch_layers_t<32>(p, grid, s);
-    else if (st.c == 64) rc = launch_layers_t<64>(p, grid, s);
-    else rc = launch_layers_t<128>(p, grid, s);
+    if (st.c == 32) rc = launch_layers_w<32>(p, grid, s);
+    else if (st.c == 64) rc = launch_layers_w<64>(p, grid, s);
+    else rc = launch_layers_w<128>(p, grid, s);
     if (rc) return rc;
     CTO_CHECK(cudaGetLastError());
     count_launch();

@@ -42,7 +42,7 @@ int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* 
 
 }  // namespace cto
 
-namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; }
+namespace cto { extern int g_gemm_debug; extern long long* g_gemm_timing; extern long long* g_fused_timing; }
 using namespace cto;
 
 struct cto_engine {
@@ -214,6 +214,7 @@ int64_t cto_launch_count(void) { return launches(); }
 
 void cto_debug_set(int flags) { cto::g_gemm_debug = flags; }
 void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; }
+void cto_debug_timing_fused(long long* dev_buf) { cto::g_fused_timing = dev_buf; }
 int cto_engine_set_tensor_cores(cto_engine* h, int mode) {
     CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");
     CTO_REQUIRE(mode >= 0 && mode <= 2, "engine_set_tensor_cores: mode %d (0 exact fp32, 1 tensor cores, 2 tensor cores without the fused AFF layers)", mode);

@@ -146,6 +146,7 @@ int cto_engine_profile_read(cto_engine* e, double* ms, int64_t* launches, double
  */
 void cto_debug_set(int flags);
 void cto_debug_timing(long long* dev_buf);
+void cto_debug_timing_fused(long long* dev_buf);   /* [32] phase counters of CTA 0 of the fused AFF layer kernel */
 
 /* Strand-count recovery of clairs/predict.py:626-642 from the un-rescaled AFF tensor: int32 [n,4] x2. */
 int cto_strand_counts(const int16_t* x_aff_dev, int64_t n, int32_t* fwd_dev, int32_t* rev_dev, void* stream);
