@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- candidate sites/sec through the per-candidate hot path (pileup encoder + AFF + NEG
-+ posterior) on N B200s, next to the CPU port of the reference timed on the same box.
+"""bench.py -- candidate sites/sec through the per-candidate hot path (pileup encoder + AFF + NEG + posterior
+[+ QUAL/FILTER]) on N B200s, next to the CPU port of the reference timed on the same box.
 
-    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
-    python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --gpus N --steps K --warmup W [--config C]        (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W [--config C]
 
-Workload (BASELINE.json configs[1]): 100 000 synthetic ONT-shape candidate sites per GPU, SNV
-AFF+NEG models with seeded random weights, synthetic likelihood tables.  One step = one pass of
-the whole hot path over the batch.  Prints ONE JSON line (rank 0).
+--config selects the BASELINE.json workload (index into its `configs` list; default 1, the configuration the metric
+is quoted on):
+    1  100 000 ONT-shape candidate sites PER GPU, SNV AFF+NEG models                       (weak scaling)
+    2  ONT 50x COLO829-shape: 2 000 000 SNV + 200 000 indel candidates in total, sharded    (strong scaling)
+    3  Illumina ilmn_ssrs: 1 000 000 candidates, ONE pileup stream feeds both networks      (strong scaling)
+    4  PacBio Revio hifi_revio: 1 000 000 SNV + 100 000 indel candidates, posterior + QUAL -> FILTER on device (strong)
+Synthetic sites (clairs_to_b200/synth.py), seeded random weights, synthetic likelihood tables.  One step = one pass
+of the whole hot path over the batch.  Prints ONE JSON line (rank 0).
 """
 
 import argparse
@@ -23,8 +28,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "candidate sites/sec (pileup+AFF+NEG)"
-WORKLOAD = "BASELINE configs[1]: synthetic 100k ONT-shape candidate sites, pileup SNV model, AFF+NEG (+posterior)"
 UNIT = "candidate sites/s"
+
+# parts: (n_heads, candidates); "total" = sharded over the ranks (strong scaling), otherwise per GPU (weak scaling)
+CONFIGS = {
+    1: dict(workload="BASELINE configs[1]: synthetic 100k ONT-shape candidate sites, pileup SNV model, AFF+NEG (+posterior)",
+            platform="ont", literal="ont_r10_dorado_sup_5khz", parts=[(4, 100000)], total=False, single_stream=False, qual=None),
+    2: dict(workload="BASELINE configs[2]: ONT 50x COLO829-shape synthetic, 2M SNV + 200k indel candidates, SNV then indel model pair",
+            platform="ont", literal="ont_r10_dorado_sup_5khz", parts=[(4, 2000000), (6, 200000)], total=True, single_stream=False, qual=None),
+    3: dict(workload="BASELINE configs[3]: Illumina ilmn_ssrs, short-read pileup shape, 1M candidates, one stream feeds both networks",
+            platform="ilmn", literal="ilmn_ssrs", parts=[(4, 1000000)], total=True, single_stream=True, qual=None),
+    4: dict(workload="BASELINE configs[4]: PacBio Revio hifi_revio 50x synthetic, 1M SNV + 100k indel candidates, "
+                     "AFF+NEG+posterior+QUAL->FILTER (shared/param.py:35-40 thresholds) on device",
+            platform="hifi", literal="hifi_revio", parts=[(4, 1000000), (6, 100000)], total=True, single_stream=False,
+            qual=(8.0, 8.0, 12.0)),
+}
 
 
 def load_peaks():
@@ -85,22 +103,27 @@ class ClockSampler:
 
 
 TRAFFIC_KERNEL = {"neg_gru2_recurrent": "gru3_kernel<192", "neg_gru1_recurrent": "gru1_fused_kernel",
-                  "encoder": "encode_pileup_kernel", "aff_stage1_fused": "aff_stage1_kernel"}
+                  "encoder": "encode_pileup_kernel", "aff_stage1_fused": "aff_stage1_kernel", "aff_layers_fused": "aff_layers_kernel",
+                  "neg_proj2_gemm": "gemm_bf16x3_kernel<0>"}
 
 
 def ncu_traffic(family, candidates_per_launch):
-    """DRAM bytes per launch of the kernel behind a profile family, from the committed ncu capture
-    (profiles/r1_traffic.json, written by profiles/summarize.py traffic), scaled linearly from the capture's
-    launch size to this run's mean launch size (every byte these kernels move is per candidate); None when the
-    capture does not hold that kernel."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """DRAM bytes per launch of the kernel behind a profile family, from the committed ncu capture (profiles/
+    r2_traffic.json, falling back to r1_traffic.json; written by profiles/summarize.py traffic), scaled linearly from
+    the capture's launch size to this run's mean launch size (every byte these kernels move is per candidate); None
+    when no capture holds that kernel."""
     key = TRAFFIC_KERNEL.get(family)
-    if not key or not os.path.exists(path):
+    if not key:
         return None
-    t = json.load(open(path))
-    for name, k in t["kernels"].items():
-        if key in name:
-            return k["dram_bytes"] * float(candidates_per_launch) / float(t["candidates_per_launch"])
+    for fn in ("r2_traffic.json", "r1_traffic.json"):
+        path = os.path.join(ROOT, "profiles", fn)
+        if not os.path.exists(path):
+            continue
+        t = json.load(open(path))
+        for name, k in t["kernels"].items():
+            if key in name:
+                per = k.get("candidates_per_launch", t.get("candidates_per_launch"))
+                return k["dram_bytes"] * float(candidates_per_launch) / float(per)
     return None
 
 
@@ -111,7 +134,12 @@ def synthetic_likelihood(n_heads, seed=1):
                            np.sort(rng.uniform(0.02, 0.98, size=(2 * n_heads, 10)), axis=1)])
 
 
-def run_reference(args, rank, world):
+def cpu_mix(cfg):
+    total = float(sum(n for _, n in cfg["parts"]))
+    return [(h, n / total) for h, n in cfg["parts"]]
+
+
+def run_reference(args, cfg, rank, world):
     """--impl reference: the CPU port of the reference's path on all host cores (oracle/cpu_baseline.py)."""
     if rank != 0:
         return
@@ -122,7 +150,8 @@ def run_reference(args, rank, world):
     pool, cores = cpu_baseline.make_pool(cores)          # workers import torch once, not once per step
     try:
         for step in range(args.warmup + args.steps):
-            r = cpu_baseline.run(per_proc=per_proc, procs=cores, seed=9000 + 17 * step, pool=pool)
+            r = cpu_baseline.run(per_proc=per_proc, procs=cores, seed=9000 + 17 * step, pool=pool, platform=cfg["platform"],
+                                 mix=cpu_mix(cfg), single_stream=cfg["single_stream"])
             if step >= args.warmup:
                 times.append(r["seconds"])
                 vals.append(r["value"])
@@ -132,13 +161,14 @@ def run_reference(args, rank, world):
         pool.join()
     value = sum(vals) / len(vals)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * sum(times) / len(times), higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32 (torch CPU)", data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, platform="ont_r10_dorado_sup_5khz", heads=4, weights="seeded random init",
-                            candidates_per_step=per_proc * cores,
+                ms_per_step=1e3 * sum(times) / len(times), higher_is_better=True, scaling="strong" if cfg["total"] else "weak",
+                vs_baseline=None, dtype="f32 (torch CPU)", data="synthetic", impl="reference",
+                config=dict(workload=cfg["workload"], platform=cfg["literal"], heads=[h for h, _ in cfg["parts"]],
+                            weights="seeded random init", candidates_per_step=last["candidates"],
                             sample="each step is a bounded sample of the workload: %d candidates per host process x %d "
-                                   "single-thread processes (the reference's own process model)" % (per_proc, cores)),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=last["sample"]),
+                                   "single-thread processes (the reference's own process model), from mpileup text" % (per_proc, cores)),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=last["sample"],
+                                  encoder_share=last["encoder_share"]),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
@@ -146,73 +176,103 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--candidates", type=int, default=100000, help="candidate sites per GPU per step")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="index into BASELINE.json configs")
+    ap.add_argument("--candidates", type=int, default=None, help="override: candidate sites of the first part (per GPU for "
+                                                                  "config 1, in total otherwise); other parts scale along")
     ap.add_argument("--max-batch", type=int, default=37888, help="engine chunk (candidates per network pass)")
     ap.add_argument("--cpu-sample", type=int, default=300, help="CPU baseline: candidates per host process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-text", action="store_true", help="skip the mpileup-text end-to-end leg (config 1)")
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: allow fewer warm-up steps "
                                                        "(numbers printed in this mode are NOT bench values)")
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.candidates:
+        scale = args.candidates / float(cfg["parts"][0][1])
+        cfg["parts"] = [(h, max(1, int(round(n * scale)))) for h, n in cfg["parts"]]
+    if args.steps is None:
+        args.steps = 20 if args.config == 1 else 5
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank, world)
         return
     if args.warmup < 3 and not args.ncu:
         args.warmup = 3
 
+    import ctypes as C
     import numpy as np
     import torch
     import torch.distributed as dist
-    from clairs_to_b200 import _lib, dist as cdist, synth
-    from clairs_to_b200.engine import PIPELINE_LOW_BQ_CUT, Engine, stream_to_device
-    from clairs_to_b200.pileup_format import PileupStream
-    from clairs_to_b200 import synth_weights
+    from clairs_to_b200 import _lib, dist as cdist, synth, synth_weights
+    from clairs_to_b200.engine import PIPELINE_LOW_BQ_CUT, Engine, packed_to_device
+    from clairs_to_b200.host import tokenize_mpileup
+    from clairs_to_b200.pileup_format import N_POS, PackedStream, pack_stream
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    n = args.candidates
-    n_heads = 4
-    literal = "ont_r10_dorado_sup_5khz"
     cut = PIPELINE_LOW_BQ_CUT
+    host_threads = max(1, len(os.sched_getaffinity(0)) // world)
 
+    def pin(a):
+        a = np.ascontiguousarray(a)
+        return torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).pin_memory()
+
+    # ---- workload: per part an engine + this rank's shard of packed streams (device-resident and pinned host copies) ----
     t_gen = time.time()
-    aff, neg = synth.synth_pair_large(n, 20241 + rank, 'ont')
+    parts = []
+    for pi, (n_heads, n_part) in enumerate(cfg["parts"]):
+        n_loc = (cdist.shard_bounds(n_part, world, rank)[1] - cdist.shard_bounds(n_part, world, rank)[0]) if cfg["total"] else n_part
+        # config 1 generates every site (as in round 1; also gives the text leg its indel sequences), the large
+        # configs generate 50 000 distinct sites and tile them
+        (aff, aff_aux), (neg, neg_aux) = synth.synth_pair_tiled(n_loc, 20241 + 7 * pi + rank, cfg["platform"],
+                                                                base=200000 if args.config == 1 else 50000)
+        if cfg["single_stream"]:
+            aff, aff_aux = neg, neg_aux                 # NEG is a symlink of AFF when both use --min-BQ 0 (run_clairs_to:1248-1252)
+        streams = [aff] if cfg["single_stream"] else [aff, neg]
+        host = [pack_stream(s, cut, n_threads=host_threads) for s in streams]
+        pinned = [PackedStream(*[pin(a) for a in h.arrays()], h.n_groups, h.low_bq_cut, h.n_reads) for h in host]
+        device = [packed_to_device(h, dev) for h in host]
+        aff_sd = synth_weights.synth_state_dict(synth_weights.aff_state_dict_shapes(n_heads), 100 + n_heads)
+        neg_sd = synth_weights.synth_state_dict(synth_weights.neg_state_dict_shapes(n_heads), 200 + n_heads)
+        eng = Engine(aff_sd, neg_sd, max_batch=args.max_batch, device=dev, likelihood=synthetic_likelihood(n_heads))
+        if cfg["qual"]:
+            eng.set_qual_thresholds(*cfg["qual"])
+        parts.append(dict(n=n_loc, n_total=n_part * (1 if cfg["total"] else world), heads=n_heads, eng=eng, dev=device, pinned=pinned,
+                          raw=(aff, aff_aux, neg, neg_aux), alg_bytes=sum(h.algorithmic_bytes() for h in host),
+                          h2d=sum(h.nbytes() for h in host), reads=sum(h.n_reads for h in host)))
     t_gen = time.time() - t_gen
-    aff_sd = synth_weights.synth_state_dict(synth_weights.aff_state_dict_shapes(n_heads), 100 + n_heads)
-    neg_sd = synth_weights.synth_state_dict(synth_weights.neg_state_dict_shapes(n_heads), 200 + n_heads)
-    eng = Engine(aff_sd, neg_sd, max_batch=args.max_batch, device=dev, likelihood=synthetic_likelihood(n_heads))
-    lib = eng.lib
-    if os.environ.get("CTO_DEBUG"):
-        lib.cto_debug_set(int(os.environ["CTO_DEBUG"]))
-    d_aff, d_neg = stream_to_device(aff, dev), stream_to_device(neg, dev)
+    lib = parts[0]["eng"].lib
     torch.cuda.synchronize()
+    n_local = sum(p["n"] for p in parts)
+    n_global = sum(p["n_total"] for p in parts)
 
     enc_ev = []
 
     def step(timed):
-        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
-        s2 = torch.cuda.Event(enable_timing=True)
-        s0.record()
-        xa, da = eng.encode(d_aff, cut)
-        s1.record()
-        xn, dn = eng.encode(d_neg, cut)
-        s2.record()
-        if timed:
-            enc_ev.append((s0, s1, s2))
-        out = eng.predict(xa, da, xn, dn)
-        if world > 1:
-            # the path's single exchange: per-candidate results to rank 0
-            cdist.gather_rows(out['probs'].reshape(n, -1), n * world)
+        out = None
+        for p in parts:
+            eng = p["eng"]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            enc = [eng.encode(d) for d in p["dev"]]
+            ev[1].record()
+            if timed:
+                enc_ev.append(ev)
+            (xa, da), (xn, dn) = enc[0], enc[-1]
+            out = eng.predict(xa, da, xn, dn)
+            if world > 1:
+                # the path's single exchange: per-candidate results to rank 0
+                cdist.gather_rows(out['probs'].reshape(p["n"], -1), p["n_total"] if cfg["total"] else p["n"] * world)
         return out
 
     def barrier():
@@ -226,14 +286,15 @@ def main():
     for _ in range(args.warmup):
         step(False)
     barrier()
-    _lib.check(lib.cto_engine_profile(eng.handle, int(os.environ.get('CTO_PROFILE_LEVEL', '1'))))
+    for p in parts:
+        _lib.check(lib.cto_engine_profile(p["eng"].handle, int(os.environ.get('CTO_PROFILE_LEVEL', '2'))))
     launches0 = lib.cto_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
-        out = step(True)
+        step(True)
     ev1.record()
     barrier()
     wall1 = time.time()
@@ -241,99 +302,149 @@ def main():
     launches = lib.cto_launch_count() - launches0
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     kinds = lib.cto_engine_profile_kinds()
-    import ctypes as C
-    pms = (C.c_double * kinds)(); pcnt = (C.c_int64 * kinds)(); pfl = (C.c_double * kinds)()
-    _lib.check(lib.cto_engine_profile_read(eng.handle, pms, pcnt, pfl))
-    _lib.check(lib.cto_engine_profile(eng.handle, 0))
+    fam = {}
+    for p in parts:
+        pms = (C.c_double * kinds)(); pcnt = (C.c_int64 * kinds)(); pfl = (C.c_double * kinds)()
+        _lib.check(lib.cto_engine_profile_read(p["eng"].handle, pms, pcnt, pfl))
+        _lib.check(lib.cto_engine_profile(p["eng"].handle, 0))
+        for k in range(kinds):
+            if pcnt[k]:
+                name = lib.cto_engine_profile_name(k).decode() + ("" if len(parts) == 1 else "[%d heads]" % p["heads"])
+                fam[name] = dict(name=name, ms_per_step=pms[k] / args.steps, launches_per_step=pcnt[k] / args.steps,
+                                 flop_per_candidate=pfl[k], candidates_per_step=p["n"])
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
-    value = n * world * args.steps / (ms_max / 1e3)
+    value = n_global * args.steps / (ms_max / 1e3)
 
-    # ---- roofline of the dominant kernel family + the encoder -----------------------------------
-    fam = []
-    for k in range(kinds):
-        if pcnt[k]:
-            fam.append(dict(name=lib.cto_engine_profile_name(k).decode(), ms_per_step=pms[k] / args.steps,
-                            launches_per_step=pcnt[k] / args.steps, flop_per_candidate=pfl[k]))
-    enc_aff_ms = sum(a.elapsed_time(b) for a, b, _ in enc_ev) / len(enc_ev)
-    enc_neg_ms = sum(b.elapsed_time(c) for _, b, c in enc_ev) / len(enc_ev)
-    enc_bytes = aff.algorithmic_bytes() + neg.algorithmic_bytes()
-    enc = dict(bound="hbm", achieved=enc_bytes / ((enc_aff_ms + enc_neg_ms) * 1e-3) / 1e9, peak=peaks["hbm"],
-               unit="GB/s", traffic=None, kernel="encode_pileup_kernel", ms_per_step=enc_aff_ms + enc_neg_ms,
-               launches_per_step=2,
-               algorithmic_bytes_per_step=enc_bytes, peak_source=peaks["source"])
+    # ---- roofline: the dominant tensor-core kernel family, and the encoder against the HBM peak -----------------
+    fam = list(fam.values())
+    enc_ms = sum(a.elapsed_time(b) for a, b in enc_ev) / args.steps
+    enc_bytes = sum(p["alg_bytes"] for p in parts)
+    enc_real = sum(p["h2d"] + 2 * N_POS * 34 * p["n"] * len(p["dev"]) for p in parts)
+    n_enc_launches = sum(len(p["dev"]) for p in parts)
+    enc = dict(bound="hbm", achieved=enc_bytes / (enc_ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s", traffic=None,
+               kernel="encode_pileup_kernel", ms_per_step=enc_ms, launches_per_step=n_enc_launches,
+               algorithmic_bytes_per_step=enc_bytes, bytes_moved_per_step=enc_real,
+               moved_gbs=enc_real / (enc_ms * 1e-3) / 1e9, peak_source=peaks["source"],
+               note="algorithmic bytes = SURVEY.md 8(d): 3 B per read + 5 B per window slot + 2244 B out per candidate-stream; the "
+                    "bit-plane packed input moves 1 B per read, so bytes_moved < algorithmic bytes")
     enc["frac"] = enc["achieved"] / enc["peak"]
-    enc_tr = ncu_traffic("encoder", n)
+    enc_tr = ncu_traffic("encoder", n_local)
     if enc_tr is not None:                              # the capture holds one launch per stream; report their mean
         enc["traffic"] = enc_tr
-        enc["algorithmic_bytes_per_launch"] = enc_bytes / 2
+        enc["algorithmic_bytes_per_launch"] = enc_bytes / n_enc_launches
     tensor_fams = [f for f in fam if f["flop_per_candidate"] > 0]
     top = max(tensor_fams, key=lambda f: f["ms_per_step"])
     per_launch_ms = top["ms_per_step"] / top["launches_per_step"]
-    cand_per_launch = n / top["launches_per_step"]
-    achieved = top["flop_per_candidate"] * cand_per_launch / (per_launch_ms * 1e-3) / 1e12
+    cand_per_launch = top["candidates_per_step"] / top["launches_per_step"]
+    flop_launch = top["flop_per_candidate"] * top["candidates_per_step"] / top["launches_per_step"]
+    achieved = flop_launch / (per_launch_ms * 1e-3) / 1e12
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["tensor_sustained"], unit="TFLOP/s",
-                    frac=achieved / peaks["tensor_sustained"], traffic=ncu_traffic(top["name"], cand_per_launch),
+                    frac=achieved / peaks["tensor_sustained"], traffic=ncu_traffic(top["name"].split("[")[0], cand_per_launch),
                     kernel=top["name"], ms_per_launch=per_launch_ms, launches_per_step=top["launches_per_step"],
-                    algorithmic_flop_per_launch=top["flop_per_candidate"] * cand_per_launch,
+                    algorithmic_flop_per_launch=flop_launch,
                     peak_source=peaks["source"] + ", dense bf16 sustained; the kernel issues 3 bf16 MMAs per algorithmic "
                                                   "multiply-add (bf16x3 split for fp32-grade accuracy), so 1/3 is its ceiling",
                     families=fam, encoder=enc)
+    whole = sum(f["flop_per_candidate"] * f["candidates_per_step"] for f in fam if not f["name"].startswith("aff_forward"))
+    roofline["whole_pass"] = dict(tflops_per_gpu=whole / (ms_max / args.steps * 1e-3) / 1e12,
+                                  note="algorithmic FLOP of every timed kernel family of one rank / step time")
 
-    # ---- end to end through the host-buffer C-ABI call ------------------------------------------
+    # ---- end to end through the host-buffer C-ABI call (packed pinned host buffers -> pinned host results) -------
     e2e = None
     if not args.no_e2e:
-        def pin(s):
-            arrs = []
-            for a in s.arrays():
-                a = np.ascontiguousarray(a)
-                t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).pin_memory()
-                arrs.append(t)
-            return PileupStream(*arrs)
-        p_aff, p_neg = pin(aff), pin(neg)
-        h = eng.n_heads
-        outb = dict(probs=torch.empty((n, 2 * h, 2), dtype=torch.float32).pin_memory(),
-                    post=torch.empty((n, h), dtype=torch.float64).pin_memory(),
-                    call=torch.empty((n,), dtype=torch.int32).pin_memory())
+        outs = []
+        for p in parts:
+            h = p["heads"]
+            outs.append(dict(probs=torch.empty((p["n"], 2 * h, 2), dtype=torch.float32).pin_memory(),
+                             post=torch.empty((p["n"], h), dtype=torch.float64).pin_memory(),
+                             call=torch.empty((p["n"],), dtype=torch.int32).pin_memory(),
+                             qual=torch.empty((p["n"],), dtype=torch.float64).pin_memory(),
+                             filter=torch.empty((p["n"],), dtype=torch.int32).pin_memory()))
+
+        def e2e_step():
+            for p, o in zip(parts, outs):
+                p["eng"].run_sites_host(p["pinned"][0], None if cfg["single_stream"] else p["pinned"][1], out=o)
+
         for _ in range(2):
-            eng.run_sites_host(p_aff, p_neg, cut, out=outb)
+            e2e_step()
         barrier()
-        t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         k_e2e = max(2, min(args.steps, 5))
+        e0.record()
         for _ in range(k_e2e):
-            eng.run_sites_host(p_aff, p_neg, cut, out=outb)
+            e2e_step()
         e1.record()
         barrier()
         e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-        h2d = aff.nbytes() + neg.nbytes()
-        d2h = sum(t.numel() * t.element_size() for t in outb.values())
-        e2e = dict(value=n * world * k_e2e / (float(e_ms.item()) / 1e3), unit=UNIT, h2d_bytes_per_step=h2d,
-                   d2h_bytes_per_step=d2h, steps=k_e2e, api="cto_run_sites_host (pinned host buffers)")
+        d2h = sum(sum(t.numel() * t.element_size() for t in o.values()) for o in outs)
+        e2e = dict(value=n_global * k_e2e / (float(e_ms.item()) / 1e3), unit=UNIT, h2d_bytes_per_step=sum(p["h2d"] for p in parts),
+                   d2h_bytes_per_step=d2h, steps=k_e2e,
+                   api="cto_run_sites_host (pinned host buffers in the packed 1-byte-per-read layout the tokenizer emits)")
+
+        # ---- the same from mpileup TEXT: tokenizer (multi-threaded host C++) + packer + the call above --------------
+        p0 = parts[0]
+        if args.config == 1 and not args.no_text and p0["raw"][1] is not None:
+            aff, aff_aux, neg, neg_aux = p0["raw"]
+            texts = [synth.render_mpileup_text(s, a) for s, a in ((aff, aff_aux), (neg, neg_aux))]
+            ref = ''.join("ACGT"[c] for c in neg.ref_code)
+            cands = np.arange(1001 + 16, 1001 + neg.n_rows, N_POS, dtype=np.int64)
+            win = np.arange(neg.n_rows, dtype=np.int32)
+
+            def text_step(timing=None):
+                t0 = time.perf_counter()
+                packed = []
+                for txt in texts:
+                    tok = tokenize_mpileup(txt, ref, 1001, cands, 60, n_threads=host_threads)
+                    tok.stream.win_pos = win
+                    packed.append(pack_stream(tok.stream, cut, n_threads=host_threads))
+                t1 = time.perf_counter()
+                p0["eng"].run_sites_host(packed[0], packed[1], out=outs[0])
+                if timing is not None:
+                    timing.append((t1 - t0, time.perf_counter() - t1))
+
+            text_step()
+            barrier()
+            tt = []
+            w0 = time.perf_counter()
+            k_txt = 2
+            for _ in range(k_txt):
+                text_step(tt)
+            torch.cuda.synchronize()
+            w = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(w, op=dist.ReduceOp.MAX)
+            text_bytes = sum(len(t) for t in texts)
+            e2e["text"] = dict(value=p0["n"] * world * k_txt / float(w.item()), unit=UNIT, steps=k_txt,
+                               text_bytes_per_step=text_bytes, host_threads=host_threads,
+                               tokenize_pack_s=sum(a for a, _ in tt) / k_txt, gpu_call_s=sum(b for _, b in tt) / k_txt,
+                               tokenizer_gb_per_s=text_bytes / 1e9 / (sum(a for a, _ in tt) / k_txt),
+                               api="mpileup text (host memory) -> cto_tokenize_mpileup + cto_pack_reads -> cto_run_sites_host; "
+                                   "tokenisation is not yet overlapped with the GPU call")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline
-        r = cpu_baseline.run(per_proc=args.cpu_sample)
-        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
+        r = cpu_baseline.run(per_proc=args.cpu_sample, platform=cfg["platform"], mix=cpu_mix(cfg), single_stream=cfg["single_stream"])
+        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"], encoder_share=r["encoder_share"])
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32 (tensor-core contractions as bf16x3 split products, f32 accumulate)", data="synthetic",
-                    config=dict(workload=WORKLOAD, candidates_per_gpu=n, platform=literal,
-                                heads=n_heads, engine_chunk=args.max_batch, weights="seeded random init",
-                                l2_policy="inputs (%.0f MB per step) larger than the 126 MB L2" % ((aff.nbytes() + neg.nbytes()) / 1e6),
+                    ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="strong" if cfg["total"] else "weak",
+                    vs_baseline=None, dtype="f32 (tensor-core contractions as bf16x3 split products, f32 accumulate)", data="synthetic",
+                    config=dict(workload=cfg["workload"], candidates_per_gpu=n_local, candidates_total=n_global, platform=cfg["literal"],
+                                heads=[h for h, _ in cfg["parts"]], engine_chunk=args.max_batch, weights="seeded random init",
+                                l2_policy="inputs (%.0f MB per step and GPU) larger than the 126 MB L2" % (sum(p["h2d"] for p in parts) / 1e6),
                                 parallelism="candidates sharded x%d, one gather of probabilities" % world,
                                 datagen_s=round(t_gen, 1)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
-    eng.close()
+    for p in parts:
+        p["eng"].close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,9 +12,9 @@ _lib = None
 
 
 class HostStream(C.Structure):
-    _fields_ = [("code", C.c_void_p), ("bq", C.c_void_p), ("mq", C.c_void_p), ("pos_off", C.c_void_p),
-                ("ref_code", C.c_void_p), ("ind_off", C.c_void_p), ("ind_entry", C.c_void_p),
-                ("win_pos", C.c_void_p), ("n_reads", C.c_int64), ("n_rows", C.c_int64), ("n_ind", C.c_int64)]
+    _fields_ = [("planes", C.c_void_p), ("grp_off", C.c_void_p), ("ref_code", C.c_void_p), ("ind_off", C.c_void_p),
+                ("ind_entry", C.c_void_p), ("win_pos", C.c_void_p), ("n_groups", C.c_int64), ("n_rows", C.c_int64),
+                ("n_ind", C.c_int64)]
 
 
 P, I32, I64, INT = C.c_void_p, C.c_int32, C.c_int64, C.c_int
@@ -23,7 +23,8 @@ SIGNATURES = {
     "cto_abi_version": (INT, []),
     "cto_last_error": (C.c_char_p, []),
     "cto_device_check": (INT, [P]),
-    "cto_encode_pileup": (INT, [P, P, P, P, P, P, P, P, I64, INT, P, P, P]),
+    "cto_encode_pileup": (INT, [P, P, P, P, P, P, I64, I64, P, P, P]),
+    "cto_pack_reads": (INT, [P, P, P, P, I64, INT, P, P, INT]),
     "cto_engine_create": (INT, [P, I64, P, INT, P, I64, P, INT, I64, P]),
     "cto_engine_destroy": (None, [P]),
     "cto_engine_heads": (INT, [P]),
@@ -31,7 +32,8 @@ SIGNATURES = {
     "cto_rescale": (INT, [P, P, I64, P, P]),
     "cto_forward_aff": (INT, [P, P, I64, P, P]),
     "cto_forward_neg": (INT, [P, P, I64, P, P]),
-    "cto_softmax_posterior": (INT, [P, P, P, I64, P, P, P, P]),
+    "cto_softmax_posterior": (INT, [P, P, P, I64, P, P, P, P, P, P]),
+    "cto_engine_set_qual_thresholds": (INT, [P, C.c_double, C.c_double, C.c_double]),
     "cto_engine_set_tensor_cores": (INT, [P, INT]),
     "cto_engine_fused_status": (INT, [P, P]),
     "cto_aff_stage_layers": (INT, [P, INT, P, I64, P]),
@@ -46,12 +48,13 @@ SIGNATURES = {
     "cto_engine_profile_name": (C.c_char_p, [INT]),
     "cto_engine_profile_read": (INT, [P, P, P, P]),
     "cto_strand_counts": (INT, [P, I64, P, P, P]),
-    "cto_predict": (INT, [P, P, P, P, P, I64, P, P, P, P, P, P, P, P]),
-    "cto_run_sites_host": (INT, [P, P, P, I64, INT, P, P, P, P, P, P]),
-    "cto_tokenize_mpileup": (INT, [C.c_char_p, I64, C.c_char_p, I64, I64, P, I64, INT, P]),
+    "cto_predict": (INT, [P, P, P, P, P, I64, P, P, P, P, P, P, P, P, P, P]),
+    "cto_run_sites_host": (INT, [P, P, P, I64, P, P, P, P, P, P, P, P]),
+    "cto_tokenize_mpileup": (INT, [C.c_char_p, I64, C.c_char_p, I64, I64, P, I64, INT, INT, P]),
     "cto_tokens_sizes": (INT, [P, P, P, P, P]),
     "cto_tokens_export": (INT, [P, P, P, P, P, P, P, P, P, P, P]),
     "cto_tokens_destroy": (None, [P]),
+    "cto_render_mpileup": (I64, [P, P, P, P, I64, P, P, P, C.c_char_p, I64, P, I64]),
     "cto_format_tensor_row": (I64, [P, P, I64]),
     "cto_format_prob_fields": (I64, [P, INT, P, I64]),
     "cto_parse_tensor_row": (INT, [C.c_char_p, I64, P]),

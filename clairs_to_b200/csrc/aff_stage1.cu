@@ -289,13 +289,9 @@ int launch_aff_stage1(const CvtStage& st, const float* x, float* out, int64_t n,
     if (n <= 0) return 0;
     CTO_REQUIRE(aff_stage1_fused_supported(st), "aff_stage1: stage shape C=%d Cin=%d W=%d heads=%d depth=%d is not the fused one",
                 st.c, st.cin, st.win, st.heads, st.depth);
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        CTO_CHECK(cudaGetDevice(&dev));
-        CTO_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CTO_CHECK(cudaFuncSetAttribute(s1::aff_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s1::SMEM_BYTES));
-    }
+    const int sm_count = device_sm_count();
+    CTO_REQUIRE(sm_count > 0, "aff_stage1: no CUDA device");
+    CTO_CHECK(set_max_dynamic_smem(s1::aff_stage1_kernel, s1::SMEM_BYTES));
     const CvtLayer& L = st.layers[0];
     s1::Weights w{st.embed_w, st.embed_b, st.ln_g, st.ln_b, L.ln1_g, L.ln1_b, L.q_dw, L.q_pw, L.q_bias, L.kv_dw, L.kv_pw,
                   L.kv_bias, L.out_w, L.out_b, L.ln2_g, L.ln2_b, L.ff1_w, L.ff1_b, L.ff2_w, L.ff2_b};

@@ -35,10 +35,9 @@ int device_sm_count() {
     return v;
 }
 
-int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off,
-                         const uint8_t* ref_code, const int32_t* ind_off, const uint32_t* ind_entry,
-                         const int32_t* win_pos, int64_t n_candidates, int low_bq_cut, int16_t* tensor,
-                         int32_t* depth, cudaStream_t stream);
+int launch_encode_pileup(const uint8_t* planes, const int32_t* grp_off, const uint8_t* ref_code, const int32_t* ind_off,
+                         const uint32_t* ind_entry, const int32_t* win_pos, int64_t n_candidates, int64_t n_groups,
+                         int16_t* tensor, int32_t* depth, cudaStream_t stream);
 
 }  // namespace cto
 
@@ -51,36 +50,36 @@ struct cto_engine {
 
 namespace {
 struct DevStream {
-    uint8_t *code = nullptr, *bq = nullptr, *mq = nullptr, *ref_code = nullptr;
-    int32_t *pos_off = nullptr, *ind_off = nullptr, *win_pos = nullptr;
+    uint8_t *planes = nullptr, *ref_code = nullptr;
+    int32_t *grp_off = nullptr, *ind_off = nullptr, *win_pos = nullptr;
     uint32_t* ind_entry = nullptr;
 };
 
-template <typename T>
-int h2d(T** dst, const T* src, int64_t n, cudaStream_t s) {
-    CTO_CHECK(cudaMallocAsync((void**)dst, std::max<int64_t>(sizeof(T) * n, 16), s));
-    if (n > 0) CTO_CHECK(cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, s));
-    return 0;
-}
-
-int upload_stream(const cto_host_stream* hs, int64_t n_cand, DevStream& d, cudaStream_t s) {
-    int rc = 0;
-    rc |= h2d(&d.code, hs->code, hs->n_reads, s);
-    rc |= h2d(&d.bq, hs->bq, hs->n_reads, s);
-    rc |= h2d(&d.mq, hs->mq, hs->n_reads, s);
-    rc |= h2d(&d.pos_off, hs->pos_off, hs->n_rows + 1, s);
-    rc |= h2d(&d.ref_code, hs->ref_code, hs->n_rows, s);
-    rc |= h2d(&d.ind_off, hs->ind_off, hs->n_rows + 1, s);
-    rc |= h2d(&d.ind_entry, hs->ind_entry, hs->n_ind, s);
-    rc |= h2d(&d.win_pos, hs->win_pos, n_cand * N_POS, s);
-    return rc;
-}
-
 void free_stream(DevStream& d, cudaStream_t s) {
-    void* ptrs[] = {d.code, d.bq, d.mq, d.ref_code, d.pos_off, d.ind_off, d.win_pos, d.ind_entry};
+    void* ptrs[] = {d.planes, d.ref_code, d.grp_off, d.ind_off, d.win_pos, d.ind_entry};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, s);
 }
+
+// Span bookkeeping of the pipelined host call: [lo, hi) of an array that is already on its way to the device.  A new span
+// that starts inside it only copies the part beyond `hi` (windows of consecutive chunks overlap; re-copying bytes that
+// the previous chunk's kernels are still reading was an unordered write/read pair).
+struct Copied {
+    int64_t lo = 0, hi = 0;
+    // returns the sub-range of [a, b) that still has to be copied and records it
+    void claim(int64_t a, int64_t b, int64_t& ca, int64_t& cb) {
+        if (hi > lo && a >= lo && a <= hi) {
+            ca = hi < b ? hi : b;
+            cb = b;
+            if (b > hi) hi = b;
+        } else {
+            ca = a;
+            cb = b;
+            lo = a;
+            hi = b;
+        }
+    }
+};
 }  // namespace
 
 
@@ -100,15 +99,13 @@ int cto_device_check(int* sm_count) {
     return 0;
 }
 
-int cto_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off,
-                      const uint8_t* ref_code, const int32_t* ind_off, const uint32_t* ind_entry,
-                      const int32_t* win_pos, int64_t n_candidates, int low_bq_cut, int16_t* tensor, int32_t* depth,
-                      void* stream) {
+int cto_encode_pileup(const uint8_t* planes, const int32_t* grp_off, const uint8_t* ref_code, const int32_t* ind_off,
+                      const uint32_t* ind_entry, const int32_t* win_pos, int64_t n_candidates, int64_t n_groups,
+                      int16_t* tensor, int32_t* depth, void* stream) {
     CTO_REQUIRE(n_candidates >= 0, "encode_pileup: negative candidate count");
-    CTO_REQUIRE(n_candidates == 0 || (pos_off && ref_code && ind_off && win_pos && tensor),
-                "encode_pileup: NULL array");
-    return launch_encode_pileup(code, bq, mq, pos_off, ref_code, ind_off, ind_entry, win_pos, n_candidates, low_bq_cut,
-                                tensor, depth, (cudaStream_t)stream);
+    CTO_REQUIRE(n_candidates == 0 || (grp_off && ref_code && ind_off && win_pos && tensor), "encode_pileup: NULL array");
+    return launch_encode_pileup(planes, grp_off, ref_code, ind_off, ind_entry, win_pos, n_candidates, n_groups, tensor, depth,
+                                (cudaStream_t)stream);
 }
 
 int cto_engine_create(const float* aff_blob, int64_t aff_len, const int32_t* aff_cfg, int aff_cfg_len,
@@ -127,12 +124,21 @@ int cto_engine_create(const float* aff_blob, int64_t aff_len, const int32_t* aff
     }
     if (!rc) rc = engine_alloc(h->e, max_batch);
     if (!rc) {
-        // keep stream-ordered allocations of cto_run_sites_host cached between calls
+        // private stream-ordered pool for the end-to-end host call: keeps its memory between calls
         int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        if (cudaGetDevice(&dev) != cudaSuccess) rc = 1;
+        props.location.id = dev;
+        if (!rc && cudaMemPoolCreate(&h->e.pool, &props) != cudaSuccess) {
+            set_error("engine_create: cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = 1;
+        }
+        if (!rc) {
             uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaMemPoolSetAttribute(h->e.pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
     if (rc) {
@@ -157,9 +163,19 @@ int cto_engine_set_likelihood(cto_engine* h, const double* tables, int n_heads) 
     CTO_REQUIRE(h && tables, "set_likelihood: NULL argument");
     CTO_REQUIRE(n_heads == h->e.aff.n_heads, "set_likelihood: tables for %d heads, engine has %d", n_heads,
                 h->e.aff.n_heads);
-    if (!h->e.tables) CTO_CHECK(cudaMalloc(&h->e.tables, sizeof(double) * 122 * 6));
+    if (!h->e.tables) {
+        CTO_CHECK(cudaMalloc(&h->e.tables, sizeof(double) * (122 * 6 + 3)));
+        CTO_CHECK(cudaMemset(h->e.tables, 0, sizeof(double) * (122 * 6 + 3)));      // thresholds default to 0: every QUAL passes
+    }
     CTO_CHECK(cudaMemcpy(h->e.tables, tables, sizeof(double) * 122 * n_heads, cudaMemcpyHostToDevice));
     h->e.table_heads = n_heads;
+    return 0;
+}
+
+int cto_engine_set_qual_thresholds(cto_engine* h, double qual_pass, double qual_phaseable, double qual_unphaseable) {
+    CTO_REQUIRE(h && h->e.tables, "set_qual_thresholds: set the likelihood tables first");
+    const double thr[3] = {qual_pass, qual_phaseable, qual_unphaseable};
+    CTO_CHECK(cudaMemcpy(h->e.tables + 122 * 6, thr, sizeof(thr), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -190,11 +206,12 @@ int cto_forward_neg(cto_engine* h, const float* x, int64_t n, float* logits, voi
 }
 
 int cto_softmax_posterior(cto_engine* h, const float* la, const float* ln, int64_t n, float* probs, double* post,
-                          int32_t* call, void* stream) {
+                          int32_t* call, double* qual, int32_t* filter, void* stream) {
     CTO_REQUIRE(h && (n == 0 || (la && ln)), "softmax_posterior: NULL argument");
-    const double* tables = (post || call) ? h->e.tables : nullptr;
-    CTO_REQUIRE(!(post || call) || tables, "softmax_posterior: posterior requested but no likelihood tables set");
-    return launch_softmax_posterior(la, ln, n, h->e.aff.n_heads, tables, probs, post, call, (cudaStream_t)stream);
+    const bool want = post || call || qual || filter;
+    const double* tables = want ? h->e.tables : nullptr;
+    CTO_REQUIRE(!want || tables, "softmax_posterior: posterior requested but no likelihood tables set");
+    return launch_softmax_posterior(la, ln, n, h->e.aff.n_heads, tables, probs, post, call, (cudaStream_t)stream, qual, filter);
 }
 
 int cto_posterior_from_probs(const double* tables_host, int n_heads, const double* p_aff_dev, const double* p_neg_dev,
@@ -212,7 +229,13 @@ int cto_posterior_from_probs(const double* tables_host, int n_heads, const doubl
 
 int64_t cto_launch_count(void) { return launches(); }
 
-void cto_debug_set(int flags) { cto::g_gemm_debug = flags; }
+void cto_debug_set(int flags) {
+#ifdef CTO_DEBUG_KNOBS
+    cto::g_gemm_debug = flags;
+#else
+    cto::g_gemm_debug = flags & 1;      // release library: phase counters only; the wrong-result timing variants are not compiled in
+#endif
+}
 void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; }
 void cto_debug_timing_fused(long long* dev_buf) { cto::g_fused_timing = dev_buf; }
 int cto_engine_set_tensor_cores(cto_engine* h, int mode) {
@@ -296,7 +319,7 @@ int cto_strand_counts(const int16_t* x, int64_t n, int32_t* fwd, int32_t* rev, v
 
 int cto_predict(cto_engine* h, const int16_t* x_aff, const int32_t* depth_aff, const int16_t* x_neg,
                 const int32_t* depth_neg, int64_t n, float* logits_aff, float* logits_neg, float* probs, double* post,
-                int32_t* call, int32_t* fwd, int32_t* rev, void* stream) {
+                int32_t* call, int32_t* fwd, int32_t* rev, double* qual, int32_t* filter, void* stream) {
     CTO_REQUIRE(h && (n == 0 || (x_aff && x_neg && depth_aff && depth_neg && logits_aff && logits_neg)),
                 "predict: NULL argument");
     Engine& e = h->e;
@@ -312,35 +335,25 @@ int cto_predict(cto_engine* h, const int16_t* x_aff, const int32_t* depth_aff, c
     }
     if (fwd && rev)
         if (int rc = launch_strand_counts(x_aff, n, fwd, rev, s)) return rc;
-    if (probs || post || call) {
-        const double* tables = (post || call) ? e.tables : nullptr;
-        CTO_REQUIRE(!(post || call) || tables, "predict: posterior requested but no likelihood tables set");
-        if (int rc = launch_softmax_posterior(logits_aff, logits_neg, n, nh, tables, probs, post, call, s)) return rc;
+    if (probs || post || call || qual || filter) {
+        const bool want = post || call || qual || filter;
+        const double* tables = want ? e.tables : nullptr;
+        CTO_REQUIRE(!want || tables, "predict: posterior requested but no likelihood tables set");
+        if (int rc = launch_softmax_posterior(logits_aff, logits_neg, n, nh, tables, probs, post, call, s, qual, filter)) return rc;
     }
     return 0;
 }
 
-int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host_stream* neg, int64_t n, int low_bq_cut,
-                       float* probs_host, double* post_host, int32_t* call_host, int16_t* tensor_aff_host,
-                       int16_t* tensor_neg_host, void* stream) {
+int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host_stream* neg, int64_t n,
+                       float* probs_host, double* post_host, int32_t* call_host, double* qual_host, int32_t* filter_host,
+                       int16_t* tensor_aff_host, int16_t* tensor_neg_host, void* stream) {
     CTO_REQUIRE(h && aff, "run_sites_host: NULL argument");
     if (n <= 0) return 0;
     Engine& e = h->e;
     cudaStream_t s = (cudaStream_t)stream;
     const int nh = e.aff.n_heads;
     const int64_t xin = (int64_t)N_POS * N_CH;
-    if (!e.copy_stream) {
-        CTO_CHECK(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
-        // this call allocates ~14 KB per candidate from the stream-ordered pool and frees it at the end; with the default
-        // release threshold (0) the pool hands everything back to the driver at the final synchronise, and every call
-        // pays the allocation again (milliseconds).  Keep the memory cached in the device's default pool instead.
-        int dev = 0;
-        cudaMemPool_t pool = nullptr;
-        CTO_CHECK(cudaGetDevice(&dev));
-        CTO_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
-        unsigned long long keep = ~0ull;
-        CTO_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
+    if (!e.copy_stream) CTO_CHECK(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
     cudaStream_t cs = e.copy_stream;
 
     const cto_host_stream* hs[2] = {aff, neg};
@@ -350,21 +363,22 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
     int32_t* dep[2] = {nullptr, nullptr};
     int32_t* call = nullptr;
     float *la = nullptr, *ln = nullptr, *probs = nullptr;
-    double* post = nullptr;
+    double *post = nullptr, *qual = nullptr;
+    int32_t* flt = nullptr;
     std::vector<cudaEvent_t> events;
     int rc = 0;
+    // this call allocates ~8 KB per candidate and frees it at the end: a PRIVATE stream-ordered pool that keeps its
+    // memory between calls (the default pool of the host application is left alone)
     auto alloc = [&](void** p, int64_t bytes) {
-        if (cudaMallocAsync(p, bytes > 16 ? bytes : 16, s) != cudaSuccess) rc = 1;
+        if (cudaMallocFromPoolAsync(p, bytes > 16 ? bytes : 16, e.pool, s) != cudaSuccess) rc = 1;
     };
-    // device arrays are only ALLOCATED here and filled span by span below (per-read arrays, per-row arrays and the
-    // window table alike), so that the host->device copy of chunk c+1 overlaps the kernels of chunk c
+    // device arrays are only ALLOCATED here and filled span by span below (plane bytes, per-row arrays and the window
+    // table alike), so that the host->device copy of chunk c+1 overlaps the kernels of chunk c
     for (int k = 0; k < n_streams && !rc; ++k) {
         const cto_host_stream* x = hs[k];
-        alloc((void**)&d[k].code, x->n_reads);
-        alloc((void**)&d[k].bq, x->n_reads);
-        alloc((void**)&d[k].mq, x->n_reads);
+        alloc((void**)&d[k].planes, ((x->n_groups * 8 + 15) & ~int64_t(15)) + 16);
         alloc((void**)&d[k].ind_entry, sizeof(uint32_t) * x->n_ind);
-        alloc((void**)&d[k].pos_off, sizeof(int32_t) * (x->n_rows + 1));
+        alloc((void**)&d[k].grp_off, sizeof(int32_t) * (x->n_rows + 1));
         alloc((void**)&d[k].ind_off, sizeof(int32_t) * (x->n_rows + 1));
         alloc((void**)&d[k].ref_code, x->n_rows);
         alloc((void**)&d[k].win_pos, sizeof(int32_t) * n * N_POS);
@@ -377,8 +391,11 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
     alloc((void**)&probs, sizeof(float) * n * nh * 4);
     alloc((void**)&post, sizeof(double) * n * nh);
     alloc((void**)&call, sizeof(int32_t) * n);
-    if (rc) set_error("run_sites_host: device allocation / copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-    const bool want_post = e.tables && (post_host || call_host);
+    alloc((void**)&qual, sizeof(double) * n);
+    alloc((void**)&flt, sizeof(int32_t) * n);
+    if (rc) set_error("run_sites_host: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const bool want_post = e.tables && (post_host || call_host || qual_host || filter_host);
+    const bool want_qual = e.tables && (qual_host || filter_host);
 
     auto new_event = [&](cudaEvent_t* ev) {
         if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) { rc = 1; return; }
@@ -397,13 +414,14 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
     const int64_t step = e.max_batch;
     const bool ramp = n > step;
     int chunk_idx = 0;
+    Copied done_rows[2], done_bytes[2], done_ind[2];
     for (int64_t c0 = 0, nc = 0; c0 < n && !rc; c0 += nc, ++chunk_idx) {
         int64_t want = step;
         if (ramp && chunk_idx < 2) want = std::max<int64_t>(128, (step / (chunk_idx == 0 ? 16 : 4)) / 128 * 128);
         nc = std::min(want, n - c0);
         for (int k = 0; k < n_streams; ++k) {
             const cto_host_stream* x = hs[k];
-            // rows touched by this chunk -> one contiguous span of reads (rows are position sorted)
+            // rows touched by this chunk -> one contiguous span of plane bytes (rows are position sorted)
             int32_t r0 = INT32_MAX, r1 = -1;
             const int32_t* wp = x->win_pos + c0 * N_POS;
             for (int64_t i = 0; i < nc * N_POS; ++i) {
@@ -418,19 +436,21 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
             }
             if (r1 < 0) continue;
             if (r1 >= x->n_rows) { set_error("run_sites_host: win_pos row %d outside the %lld pileup rows", r1, (long long)x->n_rows); rc = 2; break; }
-            const int64_t a = x->pos_off[r0], b2 = x->pos_off[r1 + 1];
-            const int64_t ia = x->ind_off[r0], ib = x->ind_off[r1 + 1];
-            // per-row arrays of the rows this chunk touches (offsets are absolute, so slices are enough) + its windows
-            cudaError_t ce = cudaMemcpyAsync(d[k].pos_off + r0, x->pos_off + r0, sizeof(int32_t) * (r1 - r0 + 2), cudaMemcpyHostToDevice, cs);
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].ind_off + r0, x->ind_off + r0, sizeof(int32_t) * (r1 - r0 + 2), cudaMemcpyHostToDevice, cs);
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].ref_code + r0, x->ref_code + r0, r1 - r0 + 1, cudaMemcpyHostToDevice, cs);
-            if (ce == cudaSuccess && b2 > a) {
-                ce = cudaMemcpyAsync(d[k].code + a, x->code + a, b2 - a, cudaMemcpyHostToDevice, cs);
-                if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].bq + a, x->bq + a, b2 - a, cudaMemcpyHostToDevice, cs);
-                if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].mq + a, x->mq + a, b2 - a, cudaMemcpyHostToDevice, cs);
+            cudaError_t ce = cudaSuccess;
+            int64_t ca, cb;
+            // per-row arrays of the rows this chunk touches (offsets are absolute, so slices are enough); element r1 + 1 of
+            // the offset arrays is re-sent with the next span (same value)
+            done_rows[k].claim(r0, (int64_t)r1 + 1, ca, cb);
+            if (cb > ca) {
+                ce = cudaMemcpyAsync(d[k].grp_off + ca, x->grp_off + ca, sizeof(int32_t) * (cb - ca + 1), cudaMemcpyHostToDevice, cs);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].ind_off + ca, x->ind_off + ca, sizeof(int32_t) * (cb - ca + 1), cudaMemcpyHostToDevice, cs);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(d[k].ref_code + ca, x->ref_code + ca, cb - ca, cudaMemcpyHostToDevice, cs);
             }
-            if (ce == cudaSuccess && ib > ia)
-                ce = cudaMemcpyAsync(d[k].ind_entry + ia, x->ind_entry + ia, sizeof(uint32_t) * (ib - ia), cudaMemcpyHostToDevice, cs);
+            done_bytes[k].claim((int64_t)x->grp_off[r0] * 8, (int64_t)x->grp_off[r1 + 1] * 8, ca, cb);
+            if (ce == cudaSuccess && cb > ca) ce = cudaMemcpyAsync(d[k].planes + ca, x->planes + ca, cb - ca, cudaMemcpyHostToDevice, cs);
+            done_ind[k].claim(x->ind_off[r0], x->ind_off[r1 + 1], ca, cb);
+            if (ce == cudaSuccess && cb > ca)
+                ce = cudaMemcpyAsync(d[k].ind_entry + ca, x->ind_entry + ca, sizeof(uint32_t) * (cb - ca), cudaMemcpyHostToDevice, cs);
             if (ce != cudaSuccess) { set_error("run_sites_host: H2D copy failed: %s", cudaGetErrorString(ce)); rc = 1; break; }
         }
         if (rc) break;
@@ -440,13 +460,14 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
         cudaEventRecord(copied, cs);
         cudaStreamWaitEvent(s, copied, 0);
         for (int k = 0; k < n_streams && !rc; ++k)
-            rc = launch_encode_pileup(d[k].code, d[k].bq, d[k].mq, d[k].pos_off, d[k].ref_code, d[k].ind_off, d[k].ind_entry,
-                                      d[k].win_pos + c0 * N_POS, nc, low_bq_cut, tens[k] + c0 * xin, dep[k] + c0, s);
+            rc = launch_encode_pileup(d[k].planes, d[k].grp_off, d[k].ref_code, d[k].ind_off, d[k].ind_entry, d[k].win_pos + c0 * N_POS,
+                                      nc, hs[k]->n_groups, tens[k] + c0 * xin, dep[k] + c0, s);
         const int kn = neg ? 1 : 0;
         if (!rc)
             rc = cto_predict(h, tens[0] + c0 * xin, dep[0] + c0, tens[kn] + c0 * xin, dep[kn] + c0, nc, la + c0 * nh * 2,
                              ln + c0 * nh * 2, probs + c0 * nh * 4, want_post ? post + c0 * nh : nullptr,
-                             want_post ? call + c0 : nullptr, nullptr, nullptr, s);
+                             want_post ? call + c0 : nullptr, nullptr, nullptr, want_qual ? qual + c0 : nullptr,
+                             want_qual ? flt + c0 : nullptr, s);
     }
     if (!rc) {
         cudaError_t ce = cudaSuccess;
@@ -455,6 +476,10 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
             ce = cudaMemcpyAsync(post_host, post, sizeof(double) * n * nh, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && want_post && call_host)
             ce = cudaMemcpyAsync(call_host, call, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess && want_qual && qual_host)
+            ce = cudaMemcpyAsync(qual_host, qual, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess && want_qual && filter_host)
+            ce = cudaMemcpyAsync(filter_host, flt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && tensor_aff_host)
             ce = cudaMemcpyAsync(tensor_aff_host, tens[0], sizeof(int16_t) * n * xin, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && tensor_neg_host)
@@ -470,7 +495,7 @@ int cto_run_sites_host(cto_engine* h, const cto_host_stream* aff, const cto_host
         if (tens[k]) cudaFreeAsync(tens[k], s);
         if (dep[k]) cudaFreeAsync(dep[k], s);
     }
-    void* ptrs[] = {la, ln, probs, post, call};
+    void* ptrs[] = {la, ln, probs, post, call, qual, flt};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, s);
     cudaError_t se = cudaStreamSynchronize(s);

@@ -1,37 +1,83 @@
-// Pileup tensor encoder: per-site read arrays -> int16 [N, 33, 34].
+// Pileup tensor encoder: packed per-site read planes -> int16 [N, 33, 34].
 //
 // Replaces decode_pileup_bases() + window assembly of the reference
 // (src/create_tensor_pileup_calling.py:146-229, 461, 513-516, 537-543; cited as CT).
 //
-// HBM-bound integer work.  One CTA encodes a group of 4 candidates = 132 (candidate, flank slot)
-// pairs, one THREAD per slot:
-//   1. the group's rows cover one contiguous span of the read arrays (rows are position-sorted), so the
-//      three byte streams (code, bq, mq) of the span are fetched with three bulk async copies
-//      (cp.async.bulk, completion on an mbarrier) into shared memory - full-line HBM reads, no LSU work;
-//   2. every thread walks the reads of its own row in shared memory and counts in REGISTERS: the three
-//      groups of eight base fields (MQ >= 20, MQ < 20, low BQ) are three 64-bit registers of 8-bit lanes,
-//      one shifted increment per read, flushed into 32-bit totals every 255 reads (round 1 kept 16-bit
-//      counters in shared memory: a load-add-store chain per read, 45 % issue utilisation);
-//   3. the rare indel-carrying reads come from a sparse side list and are resolved exactly (per-allele
-//      maximum, CT:184-187, 201-204) with a K^2 scan that has no table-size limit;
-//   4. the 34 int16 of each slot are staged in shared memory and the group's 8.8 KB output block is
-//      written with 16-byte coalesced stores.
-// Groups whose span does not fit the staging buffers (very deep pileups, scattered rows) take the
-// same code path with the pointers left in global memory.
+// HBM-bound integer work.  Round 1 walked the reads of a row one byte at a time (three byte arrays: symbol, base
+// quality, mapping quality) and was instruction-bound at 19 % of the HBM rate (~30 instructions per read).  Round 2
+// counts BIT-SLICED: the host packs every read into ONE byte (clairs_to_b200/pileup_format.py: symbol nibble, "plain"
+// flag, MQ >= 20 flag, MQ < 20 flag, low-BQ flag -- everything decode_pileup_bases() looks at) and stores each group of
+// eight reads as eight bit-plane bytes.  A thread that owns a pileup row loads four groups (32 reads) with four 8-byte
+// loads, regroups them into eight 32-bit plane words with byte permutes, forms the 26 class masks (8 bases x {MQ >= 20,
+// MQ < 20, low BQ} + '*' + '#') with one LOP3 each and adds their population counts: ~4 instructions per read
+// instead of ~30, and 1 byte per read over PCIe / HBM instead of 3.
+//
+// One CTA encodes 4 candidates = 132 (candidate, flank slot) pairs, one THREAD per slot:
+//   1. the group's rows cover one contiguous span of the plane array (rows are position-sorted): one bulk async copy
+//      (cp.async.bulk, completion on an mbarrier) stages it in shared memory -- full-line HBM reads, no LSU work;
+//   2. every thread counts its own row from shared memory as above;
+//   3. the rare indel-carrying reads come from a sparse side list and are resolved exactly (per-allele maximum,
+//      CT:184-187, 201-204) with a K^2 scan that has no table-size limit;
+//   4. the 34 int16 of each slot are staged in shared memory and the group's 8.8 KB output block is written with
+//      16-byte coalesced stores.
+// Groups whose span does not fit the staging buffer (very deep pileups, scattered rows), or whose plane array is not
+// 16-byte aligned, take the same code path with the pointer left in global memory.
 #include "common.cuh"
 
 namespace cto {
 
 namespace enc {
 
-constexpr int GROUP = 4;                          // candidates per CTA (4 CTAs per SM hide the bulk-copy latency)
+constexpr int GROUP = 4;                          // candidates per CTA
 constexpr int SLOTS = GROUP * N_POS;              // 132
 constexpr int THREADS = 160;                      // 5 warps
-constexpr int STAGE_CAP = 10 * 1024;              // bytes per staged array
-constexpr int FLUSH = 255;                        // reads per pass of the 8-bit lane counters
+constexpr int STAGE_CAP = 16 * 1024;              // bytes of staged planes
 constexpr int OUT_BYTES = SLOTS * N_CH * 2;       // 8976
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// the 24 base counters + '*' + '#' of reads [8 * g_lo, 8 * g_hi) of one row.  planes: 8 bytes per group of eight reads,
+// byte j = bit j of the eight packed read bytes (pileup_format.py):  bits 0-3 symbol (0-3 ACGT, 4-7 acgt, 8 '*', 9 '#',
+// 10 N, 11 n), bit 4 plain (a real read without an indel suffix; CT:160-204 counts indel reads only toward I/D),
+// bit 5 MQ >= 20 (CT:147), bit 6 MQ < 20 (CT:148), bit 7 BQ < low-BQ cut (CT:149).  A zero byte is a null read.
+template <typename P>
+__device__ __forceinline__ void count_planes(P planes, int64_t byte_bias, int64_t g_lo, int64_t g_hi, int (&cnt)[26]) {
+    for (int64_t g = g_lo; g < g_hi; g += 4) {
+        uint2 grp[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            grp[k] = make_uint2(0u, 0u);
+            if (g + k < g_hi) grp[k] = *reinterpret_cast<const uint2*>(planes + ((g + k) * 8 - byte_bias));
+        }
+        // plane word j = byte j of the four groups: 32 reads per word
+        uint32_t pl[8];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t sel = (uint32_t)j | ((uint32_t)(4 + j) << 4);
+            pl[j] = __byte_perm(__byte_perm(grp[0].x, grp[1].x, sel), __byte_perm(grp[2].x, grp[3].x, sel), 0x5410);
+            pl[4 + j] = __byte_perm(__byte_perm(grp[0].y, grp[1].y, sel), __byte_perm(grp[2].y, grp[3].y, sel), 0x5410);
+        }
+        const uint32_t f_hi = pl[4] & pl[5];                  // plain, MQ >= 20   -> A C G T a c g t * #
+        const uint32_t f_lo = pl[4] & pl[6];                  // plain, MQ < 20    -> LMQ channels (CT:215-217)
+        const uint32_t f_bq = pl[4] & pl[7];                  // plain, low BQ     -> LBQ channels (CT:219-221)
+        const uint32_t base = ~pl[3];                         // symbols 0..7
+        const uint32_t e0 = base & ~pl[1] & ~pl[0], e1 = base & ~pl[1] & pl[0], e2 = base & pl[1] & ~pl[0], e3 = base & pl[1] & pl[0];
+        const uint32_t fw = ~pl[2], rv = pl[2];
+        const uint32_t eb[4] = {e0, e1, e2, e3};
+        #pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            cnt[b] += __popc(f_hi & fw & eb[b]);
+            cnt[4 + b] += __popc(f_hi & rv & eb[b]);
+            cnt[10 + b] += __popc(f_lo & fw & eb[b]);
+            cnt[14 + b] += __popc(f_lo & rv & eb[b]);
+            cnt[18 + b] += __popc(f_bq & fw & eb[b]);
+            cnt[22 + b] += __popc(f_bq & rv & eb[b]);
+        }
+        const uint32_t star_hash = f_hi & pl[3] & ~pl[2] & ~pl[1];
+        cnt[8] += __popc(star_hash & ~pl[0]);
+        cnt[9] += __popc(star_hash & pl[0]);
+    }
+}
 
 // set-A field -> channel (CT:55-58)
 __device__ __forceinline__ int channel_of_a(int f) {
@@ -42,53 +88,15 @@ __device__ __forceinline__ int channel_of_a(int f) {
     return f + 8;                       // LMQ      -> 18..25
 }
 
-// Reads [lo, hi) of one row -> the 26 counters (CT:146-149, 160-221).  The same code for the staged (shared
-// memory) and the unstaged (global) arrays; the pointer type keeps the address space, so the staged instance
-// compiles to LDS.  One read = one shifted 64-bit increment `1 << 8*b8` added to up to two of the three lane
-// registers under a predicate; indel-carrying reads (bit 4 of the code) count nowhere here (CT:160-204).
-template <typename P>
-__device__ __forceinline__ void count_reads(P p_code, P p_bq, P p_mq, int lo, int hi, int low_bq_cut, int (&cnt)[26]) {
-    for (int base = lo; base < hi; base += FLUSH) {
-        const int end = min(hi, base + FLUSH);
-        unsigned long long a = 0, l = 0, b = 0;           // 8 x 8-bit lanes each: MQ >= 20 | MQ < 20 | low BQ
-        unsigned int sh = 0;                              // '*' in bits 0-15, '#' in bits 16-31
-        for (int i = base; i < end; ++i) {
-            const unsigned int c = p_code[i], m = p_mq[i], q = p_bq[i];
-            const unsigned int sym = c & 0xF;
-            const bool plain = !(c & 0x10);
-            const bool base8 = plain && (sym < 4 || (sym - 5u) < 4u);                  // A C G T a c g t
-            const unsigned int b8 = sym - (sym > 4 ? 1u : 0u);
-            const bool mq_hi = m >= (unsigned)MIN_MQ && m != (unsigned)QUAL_ABSENT;
-            const unsigned long long inc = base8 ? (1ull << (8 * b8)) : 0ull;
-            a += mq_hi ? inc : 0ull;
-            l += m < (unsigned)MIN_MQ ? inc : 0ull;                                    // CT:215-217
-            b += (q != (unsigned)QUAL_ABSENT && (int)q < low_bq_cut) ? inc : 0ull;     // CT:149, 219-221
-            sh += (plain && mq_hi && sym == 10) ? 1u : 0u;
-            sh += (plain && mq_hi && sym == 11) ? 0x10000u : 0u;
-        }
-        #pragma unroll
-        for (int f = 0; f < 8; ++f) {
-            cnt[f] += (int)((a >> (8 * f)) & 0xFF);
-            cnt[10 + f] += (int)((l >> (8 * f)) & 0xFF);
-            cnt[18 + f] += (int)((b >> (8 * f)) & 0xFF);
-        }
-        cnt[8] += (int)(sh & 0xFFFF);
-        cnt[9] += (int)(sh >> 16);
-    }
-}
-
 __global__ void __launch_bounds__(THREADS)
-encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict__ bq,
-                     const uint8_t* __restrict__ mq, const int32_t* __restrict__ pos_off,
+encode_pileup_kernel(const uint8_t* __restrict__ planes, const int32_t* __restrict__ grp_off,
                      const uint8_t* __restrict__ ref_code, const int32_t* __restrict__ ind_off,
                      const uint32_t* __restrict__ ind_entry, const int32_t* __restrict__ win_pos,
-                     int64_t n_slots, int low_bq_cut, int16_t* __restrict__ tensor,
+                     int64_t n_slots, int64_t plane_bytes, int stage_ok, int16_t* __restrict__ tensor,
                      int32_t* __restrict__ depth_out) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* s_code = smem;
-    uint8_t* s_bq = smem + STAGE_CAP;
-    uint8_t* s_mq = smem + 2 * STAGE_CAP;
-    int16_t* s_out = reinterpret_cast<int16_t*>(smem + 3 * STAGE_CAP);   // [SLOTS][34]
+    uint8_t* s_planes = smem;
+    int16_t* s_out = reinterpret_cast<int16_t*>(smem + STAGE_CAP);   // [SLOTS][34]
     __shared__ uint64_t s_bar;
     __shared__ int s_min_row, s_max_row;
 
@@ -118,29 +126,27 @@ encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict
     const int min_row = s_min_row, max_row = s_max_row;
     int64_t span_lo = 0, span_hi = 0;
     if (max_row >= 0) {
-        span_lo = pos_off[min_row];
-        span_hi = pos_off[max_row + 1];
+        span_lo = (int64_t)grp_off[min_row] * 8;
+        span_hi = (int64_t)grp_off[max_row + 1] * 8;
     }
-    const int64_t a_lo = span_lo & ~int64_t(15);                      // 16-byte aligned superset of the span
-    const int64_t a_hi = (span_hi + 15) & ~int64_t(15);
-    const bool staged = (a_hi - a_lo) <= STAGE_CAP && a_hi > a_lo;
+    const int64_t a_lo = span_lo & ~int64_t(15);                      // 16-byte aligned superset of the span,
+    int64_t a_hi = (span_hi + 15) & ~int64_t(15);                     // clamped to the (16-byte padded) array
+    if (a_hi > plane_bytes) a_hi = plane_bytes;
+    const bool staged = stage_ok && (a_hi - a_lo) <= STAGE_CAP && a_hi > a_lo && span_hi <= a_hi;
     if (staged && tid == 0) {
         const uint32_t bytes = (uint32_t)(a_hi - a_lo);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(3 * bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(s_code)), "l"(code + a_lo), "r"(bytes), "r"(smem_u32(&s_bar)) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(s_bq)), "l"(bq + a_lo), "r"(bytes), "r"(smem_u32(&s_bar)) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(s_mq)), "l"(mq + a_lo), "r"(bytes), "r"(smem_u32(&s_bar)) : "memory");
+                     ::"r"(smem_u32(s_planes)), "l"(planes + a_lo), "r"(bytes), "r"(smem_u32(&s_bar)) : "memory");
     }
 
-    // per-slot metadata and the sparse indel list are read while the bulk copies are in flight
-    int lo = 0, hi = 0, ref = 0;
+    // per-slot metadata and the sparse indel list are read while the bulk copy is in flight
+    int64_t g_lo = 0, g_hi = 0;
+    int ref = 0;
     int tot[4] = {0, 0, 0, 0}, best[4] = {0, 0, 0, 0};
     if (row >= 0) {
-        lo = pos_off[row];
-        hi = pos_off[row + 1];
+        g_lo = grp_off[row];
+        g_hi = grp_off[row + 1];
         ref = ref_code[row];
         const int ilo = ind_off[row], ihi = ind_off[row + 1];
         for (int i = ilo; i < ihi; ++i) {
@@ -181,8 +187,8 @@ encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict
     int cnt[26];
     #pragma unroll
     for (int f = 0; f < 26; ++f) cnt[f] = 0;
-    if (staged) count_reads(s_code, s_bq, s_mq, lo - (int)a_lo, hi - (int)a_lo, low_bq_cut, cnt);
-    else count_reads(code, bq, mq, lo, hi, low_bq_cut, cnt);
+    if (staged) count_planes(s_planes, a_lo, g_lo, g_hi, cnt);        // the pointer type keeps the address space: LDS
+    else count_planes(planes, (int64_t)0, g_lo, g_hi, cnt);
 
     if (tid < SLOTS) {
         int16_t* o = s_out + tid * N_CH;
@@ -240,25 +246,27 @@ encode_pileup_kernel(const uint8_t* __restrict__ code, const uint8_t* __restrict
     }
 }
 
-constexpr int SMEM_BYTES = 3 * STAGE_CAP + SLOTS * N_CH * 2 + 16;
+constexpr int SMEM_BYTES = STAGE_CAP + SLOTS * N_CH * 2 + 16;
 
 }  // namespace enc
 
-int launch_encode_pileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq,
-                         const int32_t* pos_off, const uint8_t* ref_code, const int32_t* ind_off,
-                         const uint32_t* ind_entry, const int32_t* win_pos, int64_t n_candidates,
-                         int low_bq_cut, int16_t* tensor, int32_t* depth, cudaStream_t stream) {
+// planes: 8 * n_groups bytes of bit planes; the ALLOCATION must extend to the next multiple of 16 bytes (the staged path
+// copies 16-byte aligned supersets of a span) -- clairs_to_b200.pileup_format.pack_stream and the host call guarantee it.
+// A plane array that is not 16-byte aligned (an offset view) is read with ordinary loads instead of bulk copies.
+int launch_encode_pileup(const uint8_t* planes, const int32_t* grp_off, const uint8_t* ref_code, const int32_t* ind_off,
+                         const uint32_t* ind_entry, const int32_t* win_pos, int64_t n_candidates, int64_t n_groups,
+                         int16_t* tensor, int32_t* depth, cudaStream_t stream) {
     if (n_candidates <= 0) return 0;
     const int64_t n_slots = n_candidates * N_POS;
     const int64_t grid = (n_candidates + enc::GROUP - 1) / enc::GROUP;
     CTO_REQUIRE(grid < (1ll << 31), "encode_pileup: too many candidates in one launch (%lld)", (long long)n_candidates);
-    static bool attr = false;
-    if (!attr) {
-        CTO_CHECK(cudaFuncSetAttribute(enc::encode_pileup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, enc::SMEM_BYTES));
-        attr = true;
-    }
+    CTO_REQUIRE(n_groups >= 0 && n_groups < (1ll << 31), "encode_pileup: group count %lld out of range", (long long)n_groups);
+    CTO_REQUIRE((reinterpret_cast<uintptr_t>(planes) & 7) == 0, "encode_pileup: the plane array must be 8-byte aligned");
+    const int stage_ok = (reinterpret_cast<uintptr_t>(planes) & 15) == 0 ? 1 : 0;
+    const int64_t plane_bytes = (n_groups * 8 + 15) & ~int64_t(15);
+    CTO_CHECK(set_max_dynamic_smem(enc::encode_pileup_kernel, enc::SMEM_BYTES));
     enc::encode_pileup_kernel<<<(unsigned)grid, enc::THREADS, enc::SMEM_BYTES, stream>>>(
-        code, bq, mq, pos_off, ref_code, ind_off, ind_entry, win_pos, n_slots, low_bq_cut, tensor, depth);
+        planes, grp_off, ref_code, ind_off, ind_entry, win_pos, n_slots, plane_bytes, stage_ok, tensor, depth);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

@@ -254,6 +254,8 @@ void engine_free(Engine& e) {
     e.allocs.clear();
     if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
     e.copy_stream = nullptr;
+    if (e.pool) cudaMemPoolDestroy(e.pool);
+    e.pool = nullptr;
     for (int s = 0; s < 3; ++s) aff_fused_release(e.aff.st[s]);
     release(e.aff.ws);
     release(e.neg.ws);

@@ -96,6 +96,7 @@ struct Engine {
     int table_heads = 0;
     std::vector<void*> allocs;
     cudaStream_t copy_stream = nullptr;                        // H2D spans of cto_run_sites_host overlap the kernels
+    cudaMemPool_t pool = nullptr;                              // private stream-ordered pool of cto_run_sites_host
     bool use_tc = true;                                        // dense contractions on tcgen05 (bf16x3)
     bool use_fused = true;                                     // AFF transformer layers in the fused kernel (aff_fused.cu)
     int* fused_dbg = nullptr;                                  // device int[8]: barrier-timeout report of the fused kernel

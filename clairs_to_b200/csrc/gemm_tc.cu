@@ -517,15 +517,11 @@ int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s) {
                     g.lda % a_align == 0 && g.ldw % 8 == 0 && g.ldc % 4 == 0 && (!g.residual || g.ldr % 4 == 0),
                 "gemm_tc: unsupported shape/alignment m=%lld n=%d k=%d lda=%lld ldw=%lld ldc=%lld flags=%d", (long long)g.m,
                 g.n, g.k, (long long)g.lda, (long long)g.ldw, (long long)g.ldc, g.flags);
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        CTO_CHECK(cudaGetDevice(&dev));
-        CTO_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        CTO_CHECK(cudaFuncSetAttribute(tc::gemm_bf16x3_kernel<ACT_SELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    }
+    const int sm_count = device_sm_count();
+    CTO_REQUIRE(sm_count > 0, "gemm_tc: no CUDA device");
+    if (g.act == ACT_GELU) CTO_CHECK(set_max_dynamic_smem(tc::gemm_bf16x3_kernel<ACT_GELU>, tc::SMEM_BYTES));
+    else if (g.act == ACT_SELU) CTO_CHECK(set_max_dynamic_smem(tc::gemm_bf16x3_kernel<ACT_SELU>, tc::SMEM_BYTES));
+    else CTO_CHECK(set_max_dynamic_smem(tc::gemm_bf16x3_kernel<ACT_NONE>, tc::SMEM_BYTES));
     // 128-wide tiles unless that leaves SMs without a tile (long-K, few-row GEMMs such as the NEG fc1)
     const int bn = (g.n % 128 == 0 && (int64_t)ceil_div(g.m, tc::BM) * (g.n / 128) >= sm_count) ? 128 : 64;
     CUtensorMap map_a, map_amid, map_whi, map_wmid, map_c, map_cmid;

@@ -317,11 +317,7 @@ int launch_gru1_fused(const uint16_t* x_hi, const uint16_t* x_mid, int ldx, int6
     // columns beyond ldx are out of bounds of the map: the 64-wide box is zero-filled there
     if (tc::make_map_bf16(&m_x_hi, x_hi, (int64_t)N_POS * bp, ldx, ldx, tc::F_M)) return 1;
     if (tc::make_map_bf16(&m_x_mid, x_mid, (int64_t)N_POS * bp, ldx, ldx, tc::F_M)) return 1;
-    static bool attr = false;
-    if (!attr) {
-        CTO_CHECK(cudaFuncSetAttribute(tc::gru1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::F_SMEM));
-        attr = true;
-    }
+    CTO_CHECK(set_max_dynamic_smem(tc::gru1_fused_kernel, tc::F_SMEM));
     const int ctas = ceil_div(batch, tc::F_M);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((ctas + 1) / 2 * 2), 2, 1);

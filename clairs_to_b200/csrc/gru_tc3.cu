@@ -369,11 +369,7 @@ template <int H, int GW, int VAR>
 static int launch_gru3_t(const CUtensorMap& map_hi, const CUtensorMap& map_mid, const CUtensorMap& map_x, int64_t bp,
                          const float* bhn, uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch,
                          cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        CTO_CHECK(cudaFuncSetAttribute(gru3_kernel<H, GW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gru3Smem<H>::TOTAL));
-        attr = true;
-    }
+    CTO_CHECK(set_max_dynamic_smem(gru3_kernel<H, GW, VAR>, Gru3Smem<H>::TOTAL));
     const int ctas = ceil_div(batch, Q_M);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((ctas + 1) / 2 * 2), 2, 1);
@@ -412,17 +408,20 @@ int launch_gru3(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_h
     if (tc::make_map_bf16(&map_mid, w_mid, 6 * hidden, hidden, hidden, tc::Q_HALF)) return 1;
     if (tc::make_map_plain(&map_x, xproj, 6 * hidden, ldx, ldx, tc::Q_BLK, tc::Q_M)) return 1;   // box: 32 units x 64 candidates
 #define CTO_GRU3(HH, GG) tc::launch_gru3_t<HH, GG, 0>(map_hi, map_mid, map_x, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
-#define CTO_GRU3V(VV) tc::launch_gru3_t<192, 2, VV>(map_hi, map_mid, map_x, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
     int rc;
-    const int var = g_gemm_debug & 14;                       // timing experiments (wrong results): profiles/phase_timing_gru.py
     if (hidden == 128) rc = CTO_GRU3(128, 2);
-    else if (var == 2) rc = CTO_GRU3V(2);
-    else if (var == 4) rc = CTO_GRU3V(4);
-    else if (var == 8) rc = CTO_GRU3V(8);
-    else if (var == 14) rc = CTO_GRU3V(14);
+#ifdef CTO_DEBUG_KNOBS
+    // timing-attribution builds (WRONG results: no projection loads / no output stores / no MUFU); only compiled into the
+    // debug library (python -m clairs_to_b200.build --debug), never into the release libcto_b200.so
+#define CTO_GRU3V(VV) tc::launch_gru3_t<192, 2, VV>(map_hi, map_mid, map_x, bp, bhn, out_hi, out_mid, osb, ost, batch, s)
+    else if ((g_gemm_debug & 14) == 2) rc = CTO_GRU3V(2);
+    else if ((g_gemm_debug & 14) == 4) rc = CTO_GRU3V(4);
+    else if ((g_gemm_debug & 14) == 8) rc = CTO_GRU3V(8);
+    else if ((g_gemm_debug & 14) == 14) rc = CTO_GRU3V(14);
+#undef CTO_GRU3V
+#endif
     else rc = CTO_GRU3(192, 2);
 #undef CTO_GRU3
-#undef CTO_GRU3V
     if (rc) return rc;
     CTO_CHECK(cudaGetLastError());
     count_launch();

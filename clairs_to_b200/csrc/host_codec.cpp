@@ -6,8 +6,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <limits.h>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -57,20 +59,19 @@ struct cto_tokens {
     std::vector<int64_t> alt_off;
 };
 
-extern "C" {
+namespace {
 
-int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq, int64_t ref_len, int64_t ref_start,
-                         const int64_t* candidate_pos, int64_t n_candidates, int max_indel_length, cto_tokens** out) {
-    if (!text || !ref_seq || !out) {
-        cto::set_error("tokenize_mpileup: NULL argument");
-        return 2;
-    }
-    std::unordered_set<int64_t> cand;
-    for (int64_t i = 0; i < n_candidates; ++i) cand.insert(candidate_pos[i]);
-    cto_tokens* t = new cto_tokens();
+// one contiguous range of whole rows -> its own token block (rows are independent)
+int tokenize_range(const char* text, int64_t text_len, const char* ref_seq, int64_t ref_len, int64_t ref_start,
+                   const std::unordered_set<int64_t>& cand, int max_indel_length, cto_tokens* t, std::string& err) {
     t->pos_off.push_back(0);
     t->ind_off.push_back(0);
     t->alt_off.push_back(0);
+    {   // a row of depth d takes about 3 d + 30 characters: reserve once instead of growing by doubling
+        const size_t reads = (size_t)text_len / 3 + 64, rows = (size_t)text_len / 64 + 64;
+        t->code.reserve(reads); t->bq.reserve(reads); t->mq.reserve(reads);
+        t->ref_code.reserve(rows); t->row_pos.reserve(rows); t->pos_off.reserve(rows); t->ind_off.reserve(rows); t->alt_off.reserve(rows);
+    }
     std::vector<Entry> entries;
     std::unordered_map<std::string, uint32_t> allele_ids;
     std::vector<std::pair<std::string, int>> main_counts;          // first-occurrence ordered Counter
@@ -98,16 +99,14 @@ int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq
         const char* next = eol + 1;
         if (ncol == 0 || (ncol == 1 && col_len[0] == 0)) { p = next; continue; }
         if (ncol < 7) {
-            cto::set_error("tokenize_mpileup: row with %d columns (need 7: chr pos ref depth bases BQ MQ)", ncol);
-            delete t;
+            err = "tokenize_mpileup: row with " + std::to_string(ncol) + " columns (need 7: chr pos ref depth bases BQ MQ)";
             return 2;
         }
         while (col_len[6] > 0 && (col[6][col_len[6] - 1] == '\r' || col[6][col_len[6] - 1] == ' ')) --col_len[6];   // row.strip()
         const int64_t pos = strtoll(col[1], nullptr, 10);
         const int64_t roff = pos - ref_start;
         if (roff < 0 || roff >= ref_len) {
-            cto::set_error("tokenize_mpileup: position %lld outside the reference window", (long long)pos);
-            delete t;
+            err = "tokenize_mpileup: position " + std::to_string((long long)pos) + " outside the reference window";
             return 2;
         }
         const int ref = coerce_ref(ref_seq[roff]);
@@ -144,7 +143,8 @@ int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq
             const uint8_t mqv = (int)k < n_mq ? (uint8_t)(col[6][k] - 33) : QUAL_ABSENT;
             const uint8_t bqv = (int)k < n_bq ? (uint8_t)(col[5][k] - 33) : QUAL_ABSENT;
             uint8_t c = (uint8_t)symbol_index(e.sym);
-            std::string key(1, e.sym);
+            std::string key;
+            if (e.sign || is_cand) key.assign(1, e.sym);
             if (e.sign) {
                 const bool is_del = e.sign == '-';
                 const int seq_len = e.seq_len;
@@ -249,7 +249,209 @@ int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq
         t->alt_off.push_back((int64_t)t->alt_info.size());
         p = next;
     }
+    return 0;
+}
+
+// 8 packed read bytes (read i in byte i) -> 8 bit-plane bytes (plane j in byte j; bit i of plane j = bit j of read i)
+inline uint64_t transpose8x8(uint64_t x) {
+    uint64_t t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAULL;  x = x ^ t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCULL; x = x ^ t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ULL; x = x ^ t ^ (t << 28);
+    return x;
+}
+
+int resolve_threads(int n_threads, int64_t work_items, int64_t min_items_per_thread) {
+    int n = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    const int64_t cap = work_items / (min_items_per_thread > 0 ? min_items_per_thread : 1);
+    if (cap < n) n = cap < 1 ? 1 : (int)cap;
+    return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq, int64_t ref_len, int64_t ref_start,
+                         const int64_t* candidate_pos, int64_t n_candidates, int max_indel_length, int n_threads,
+                         cto_tokens** out) {
+    if (!text || !ref_seq || !out) {
+        cto::set_error("tokenize_mpileup: NULL argument");
+        return 2;
+    }
+    std::unordered_set<int64_t> cand;
+    for (int64_t i = 0; i < n_candidates; ++i) cand.insert(candidate_pos[i]);
+    const int nt = resolve_threads(n_threads, text_len, 1 << 20);
+    // split at row boundaries
+    std::vector<int64_t> cut(nt + 1, 0);
+    cut[nt] = text_len;
+    for (int k = 1; k < nt; ++k) {
+        int64_t c = text_len * k / nt;
+        if (c < cut[k - 1]) c = cut[k - 1];
+        const char* nl = (const char*)memchr(text + c, '\n', (size_t)(text_len - c));
+        cut[k] = nl ? (int64_t)(nl - text) + 1 : text_len;
+    }
+    const bool timing = getenv("CTO_TOKENIZE_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    std::vector<cto_tokens> parts(nt);
+    std::vector<std::string> errs(nt);
+    std::vector<int> rcs(nt, 0);
+    auto work = [&](int k) {
+        const auto w0 = std::chrono::steady_clock::now();
+        rcs[k] = tokenize_range(text + cut[k], cut[k + 1] - cut[k], ref_seq, ref_len, ref_start, cand, max_indel_length, &parts[k], errs[k]);
+        if (timing) fprintf(stderr, "[tokenize]   part %d: %lld bytes in %.3f s\n", k, (long long)(cut[k + 1] - cut[k]),
+                            std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count());
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back(work, k);
+        for (auto& x : th) x.join();
+    }
+    for (int k = 0; k < nt; ++k)
+        if (rcs[k]) {
+            cto::set_error("%s", errs[k].c_str());
+            return rcs[k];
+        }
+    const auto t_tok = std::chrono::steady_clock::now();
+    cto_tokens* t = new cto_tokens();
+    if (nt == 1) {
+        *t = std::move(parts[0]);
+    } else {
+        size_t n_reads = 0, n_rows = 0, n_ind = 0, n_alt = 0;
+        for (auto& p : parts) { n_reads += p.code.size(); n_rows += p.ref_code.size(); n_ind += p.ind_entry.size(); n_alt += p.alt_info.size(); }
+        if (n_reads >= (size_t)INT32_MAX) {
+            cto::set_error("tokenize_mpileup: %zu reads in one call (limit 2^31)", n_reads);
+            delete t;
+            return 2;
+        }
+        t->code.reserve(n_reads); t->bq.reserve(n_reads); t->mq.reserve(n_reads);
+        t->ref_code.reserve(n_rows); t->row_pos.reserve(n_rows); t->ind_entry.reserve(n_ind);
+        t->pos_off.reserve(n_rows + 1); t->ind_off.reserve(n_rows + 1); t->alt_off.reserve(n_rows + 1);
+        t->alt_info.reserve(n_alt);
+        t->pos_off.push_back(0); t->ind_off.push_back(0); t->alt_off.push_back(0);
+        for (auto& p : parts) {
+            const int32_t r0 = (int32_t)t->code.size(), i0 = (int32_t)t->ind_entry.size();
+            const int64_t a0 = (int64_t)t->alt_info.size();
+            t->code.insert(t->code.end(), p.code.begin(), p.code.end());
+            t->bq.insert(t->bq.end(), p.bq.begin(), p.bq.end());
+            t->mq.insert(t->mq.end(), p.mq.begin(), p.mq.end());
+            t->ref_code.insert(t->ref_code.end(), p.ref_code.begin(), p.ref_code.end());
+            t->row_pos.insert(t->row_pos.end(), p.row_pos.begin(), p.row_pos.end());
+            t->ind_entry.insert(t->ind_entry.end(), p.ind_entry.begin(), p.ind_entry.end());
+            t->alt_info += p.alt_info;
+            for (size_t r = 1; r < p.pos_off.size(); ++r) {
+                t->pos_off.push_back(p.pos_off[r] + r0);
+                t->ind_off.push_back(p.ind_off[r] + i0);
+                t->alt_off.push_back(p.alt_off[r] + a0);
+            }
+        }
+    }
+    if (timing)
+        fprintf(stderr, "[tokenize] %d threads: tokenize %.3f s, merge %.3f s\n", nt,
+                std::chrono::duration<double>(t_tok - t_start).count(),
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_tok).count());
     *out = t;
+    return 0;
+}
+
+// Synthetic `samtools mpileup` text for a read-array stream (the inverse of the tokenizer; bench.py's text-in leg and the
+// tests render the same sites as text): rows "ctg \t pos \t N \t depth \t bases \t BQ \t MQ \n", position = first_pos + row.
+// ind_len / ind_seq: per indel-carrying read (in read order) the indel length and, for insertions, the inserted bases
+// packed two bits each (deletions print N / n like samtools without -f).  Returns bytes written, -1 if cap is too small.
+int64_t cto_render_mpileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off, int64_t n_rows,
+                           const uint32_t* ind_entry, const int64_t* ind_len, const int64_t* ind_seq, const char* ctg,
+                           int64_t first_pos, char* out, int64_t cap) {
+    static const char SYM[] = "ACGTNacgtn*#";
+    int64_t w = 0, k = 0;
+    const size_t ctg_len = strlen(ctg);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int32_t lo = pos_off[r], hi = pos_off[r + 1];
+        // worst case per read: symbol + sign + 3 digits + 60 bases, + 2 quality characters
+        if (w + (int64_t)ctg_len + 64 + (int64_t)(hi - lo) * 70 > cap) return -1;
+        memcpy(out + w, ctg, ctg_len); w += ctg_len;
+        w += snprintf(out + w, 48, "\t%lld\tN\t%d\t", (long long)(first_pos + r), hi - lo);
+        if (hi == lo) {
+            memcpy(out + w, "*\t*\t*\n", 6); w += 6;
+            continue;
+        }
+        for (int32_t i = lo; i < hi; ++i) {
+            const uint8_t c = code[i];
+            out[w++] = SYM[c & 0xF];
+            if (c & HAS_INDEL) {
+                const uint32_t e = ind_entry[k];
+                const bool is_del = e & IND_DEL, rev = e & IND_REV;
+                const int64_t len = ind_len[k];
+                int64_t seq = ind_seq[k];
+                ++k;
+                w += snprintf(out + w, 16, "%c%lld", is_del ? '-' : '+', (long long)len);
+                for (int64_t z = 0; z < len; ++z) {
+                    char b = is_del ? 'N' : "ACGT"[seq & 3];
+                    seq >>= 2;
+                    out[w++] = rev ? (char)(b + 32) : b;
+                }
+            }
+        }
+        out[w++] = '\t';
+        for (int32_t i = lo; i < hi; ++i) out[w++] = (char)(33 + bq[i]);
+        out[w++] = '\t';
+        for (int32_t i = lo; i < hi; ++i) out[w++] = (char)(33 + mq[i]);
+        out[w++] = '\n';
+    }
+    return w;
+}
+
+int cto_pack_reads(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off, int64_t n_rows,
+                   int low_bq_cut, const int32_t* grp_off, uint8_t* planes_out, int n_threads) {
+    if (n_rows < 0 || !pos_off || !grp_off || (n_rows > 0 && grp_off[n_rows] > 0 && (!code || !bq || !mq || !planes_out))) {
+        cto::set_error("pack_reads: NULL / negative argument");
+        return 2;
+    }
+    // old symbol order "ACGTNacgtn*#" -> packed order ACGT acgt * # N n
+    static const uint8_t RECODE[16] = {0, 1, 2, 3, 10, 4, 5, 6, 7, 11, 8, 9, 15, 15, 15, 15};
+    const int64_t total = (int64_t)grp_off[n_rows] * 8;
+    const int64_t padded = (total + 15) & ~int64_t(15);
+    for (int64_t i = total; i < padded; ++i) planes_out[i] = 0;
+    const int nt = resolve_threads(n_threads, n_rows, 4096);
+    int bad = 0;
+    auto work = [&](int k) {
+        const int64_t r_lo = n_rows * k / nt, r_hi = n_rows * (k + 1) / nt;
+        for (int64_t r = r_lo; r < r_hi; ++r) {
+            const int32_t lo = pos_off[r], hi = pos_off[r + 1];
+            const int64_t g0 = grp_off[r], g1 = grp_off[r + 1];
+            if (hi < lo || (int64_t)(hi - lo + 7) / 8 != g1 - g0) { __atomic_store_n(&bad, 1, __ATOMIC_RELAXED); return; }
+            for (int64_t g = g0; g < g1; ++g) {
+                uint64_t x = 0;
+                const int32_t base = lo + (int32_t)(g - g0) * 8;
+                for (int i = 0; i < 8; ++i) {
+                    const int32_t idx = base + i;
+                    if (idx >= hi) break;
+                    const uint8_t c = code[idx], m = mq[idx], q = bq[idx];
+                    uint8_t b = RECODE[c & 0xF];
+                    if (!(c & HAS_INDEL)) b |= 0x10;                                   // plain read
+                    if (m != QUAL_ABSENT) b |= (m >= 20) ? 0x20 : 0x40;                // CT:147-148
+                    if (q != QUAL_ABSENT && (int)q < low_bq_cut) b |= 0x80;            // CT:149
+                    x |= (uint64_t)b << (8 * i);
+                }
+                x = transpose8x8(x);
+                memcpy(planes_out + g * 8, &x, 8);
+            }
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back(work, k);
+        for (auto& x : th) x.join();
+    }
+    if (bad) {
+        cto::set_error("pack_reads: grp_off is not the prefix sum of ceil(row depth / 8)");
+        return 2;
+    }
     return 0;
 }
 

@@ -790,9 +790,25 @@ __device__ __forceinline__ int digitize11(double x, const double* edges) {   // 
     return c - 1;
 }
 
+// QUAL of clairs/call_variants.py:81-88 from the winning posterior, and the QUAL -> FILTER thresholds
+// (call_variants.py:67-76 `--qual`, src/postprocess_vcf.py:61-82 phaseable / unphaseable cuts; shared/param.py:35-40):
+// flt bit 0 = QUAL >= thr[0] (PASS of call_variants), bit 1 = QUAL >= thr[1] (phaseable), bit 2 = QUAL >= thr[2]
+// (unphaseable).  The RefCall decision needs the alt_info strings and stays on the host.
+__device__ __forceinline__ void qual_filter(double p, const double* thr, double* qual, int32_t* flt, int64_t i) {
+    // Phred_Trans * log(((1 - p) + 1e-10) / (p + 1e-10)) + 2, floored at 0, rounded to 4 decimals
+    const double phred_trans = -4.3429448190325175;                     // -10 * log(e, 10)
+    const double ratio = __ddiv_rn(__dadd_rn(__dsub_rn(1.0, p), 1e-10), __dadd_rn(p, 1e-10));
+    double t = __dadd_rn(__dmul_rn(phred_trans, log(ratio)), 2.0);
+    t = t > 0.0 ? t : 0.0;
+    const double q = __ddiv_rn(rint(__dmul_rn(t, 1e4)), 1e4);
+    if (qual) qual[i] = q;
+    if (flt) flt[i] = (q >= thr[0] ? 1 : 0) | (q >= thr[1] ? 2 : 0) | (q >= thr[2] ? 4 : 0);
+}
+
 __global__ void softmax_posterior_kernel(const float* __restrict__ la, const float* __restrict__ ln, int64_t n,
                                          int n_heads, const double* __restrict__ tables, float* __restrict__ probs,
-                                         double* __restrict__ post, int32_t* __restrict__ call) {
+                                         double* __restrict__ post, int32_t* __restrict__ call, double* __restrict__ qual,
+                                         int32_t* __restrict__ flt) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double best = -1.0;
@@ -836,6 +852,7 @@ __global__ void softmax_posterior_kernel(const float* __restrict__ la, const flo
         if (ps > best) { best = ps; best_h = h; }          // first maximum wins like np.argmax
     }
     if (call && tables) call[i] = best_h | (clamped << 8);
+    if (tables && (qual || flt)) qual_filter(best, tables + 6 * 122, qual, flt, i);   // thresholds follow the tables
 }
 
 // Bayes combine on probabilities that were already parsed from a predict file (clairs/call_variants.py:798-829):
@@ -876,10 +893,11 @@ int launch_posterior_from_probs(const double* pa, const double* pn, int64_t n, i
 }
 
 int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,
-                             const double* tables, float* probs, double* post, int32_t* call, cudaStream_t s) {
+                             const double* tables, float* probs, double* post, int32_t* call, cudaStream_t s, double* qual,
+                             int32_t* flt) {
     if (n <= 0) return 0;
     softmax_posterior_kernel<<<ceil_div(n, 128), 128, 0, s>>>(logits_aff, logits_neg, n, n_heads, tables, probs, post,
-                                                              call);
+                                                              call, qual, flt);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;

@@ -86,8 +86,10 @@ int launch_gru1_fused(const uint16_t* x_hi, const uint16_t* x_mid, int ldx, int6
                       cudaStream_t s);
 int launch_head_fc3(const float* y, const float* w3, const float* b3, float* logits, int64_t batch, int n_heads,
                     cudaStream_t s);
+// tables: n_heads x 122 likelihood doubles at [0, 6 * 122), then the three QUAL thresholds at [6 * 122, 6 * 122 + 3)
 int launch_softmax_posterior(const float* logits_aff, const float* logits_neg, int64_t n, int n_heads,
-                             const double* tables, float* probs, double* post, int32_t* call, cudaStream_t s);
+                             const double* tables, float* probs, double* post, int32_t* call, cudaStream_t s,
+                             double* qual = nullptr, int32_t* flt = nullptr);
 int launch_posterior_from_probs(const double* pa, const double* pn, int64_t n, int n_heads, const double* tables,
                                 double* post, int32_t* call, cudaStream_t s);
 int launch_strand_counts(const int16_t* x_aff, int64_t n, int32_t* fwd, int32_t* rev, cudaStream_t s);

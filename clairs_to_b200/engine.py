@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .pileup_format import N_CH, N_POS, PileupStream
+from .pileup_format import N_CH, N_POS, PackedStream, PileupStream, pack_stream
 from .weights import export_aff, export_neg, likelihood_tables, state_dict_from_checkpoint
 
 
@@ -50,28 +50,59 @@ def _stream_ptr():
 _TORCH_VIEW = {np.dtype(np.uint32): np.int32}
 
 
-def stream_to_device(stream: PileupStream, device) -> PileupStream:
-    """numpy PileupStream -> the same arrays in HBM (uint32 carried as int32 bits)."""
+def packed_to_device(ps: PackedStream, device) -> PackedStream:
+    """Host PackedStream -> the same arrays in HBM (uint32 carried as int32 bits)."""
     out = []
-    for a in stream.arrays():
+    for a in ps.arrays():
+        if isinstance(a, torch.Tensor):
+            out.append(a.to(device, non_blocking=True))
+            continue
         a = np.ascontiguousarray(a)
         if a.dtype in _TORCH_VIEW:
             a = a.view(_TORCH_VIEW[a.dtype])
         out.append(torch.from_numpy(a).to(device, non_blocking=True))
-    return PileupStream(*out)
+    return PackedStream(*out, ps.n_groups, ps.low_bq_cut, ps.n_reads)
 
 
-def encode_pileup(s: PileupStream, low_bq_cut: int, device=None):
-    """Device PileupStream -> (int16 [N,33,34], int32 centre depth [N]) through ``cto_encode_pileup``.
+class DeviceStream:
+    """A PileupStream on its way to the GPU.  The low-BQ literal of decode_pileup_bases
+    (src/create_tensor_pileup_calling.py:149) is applied when the reads are packed to one byte, so the packed device
+    copy is made (and cached) per cut on first use."""
+
+    def __init__(self, stream: PileupStream, device):
+        self.host, self.device, self._packed = stream, device, {}
+
+    def packed(self, low_bq_cut: int) -> PackedStream:
+        cut = int(low_bq_cut)
+        if cut not in self._packed:
+            self._packed[cut] = packed_to_device(pack_stream(self.host, cut), self.device)
+        return self._packed[cut]
+
+    @property
+    def win_pos(self):
+        return self.host.win_pos
+
+
+def stream_to_device(stream: PileupStream, device) -> DeviceStream:
+    """numpy PileupStream -> handle whose packed device copy is built at the first encode."""
+    return DeviceStream(stream, device)
+
+
+def encode_pileup(s, low_bq_cut: int = None, device=None):
+    """DeviceStream / device PackedStream -> (int16 [N,33,34], int32 centre depth [N]) through ``cto_encode_pileup``.
     Needs no weights, so the create_tensor sub-command uses it without building an Engine."""
     lib = _lib.lib()
+    if isinstance(s, DeviceStream):
+        s = s.packed(low_bq_cut)
+    elif low_bq_cut is not None and int(low_bq_cut) != s.low_bq_cut:
+        raise ValueError("stream was packed with low_bq_cut=%d, encode asked for %d" % (s.low_bq_cut, low_bq_cut))
     device = s.win_pos.device if device is None else device
     n = s.win_pos.numel() // N_POS
     tensor = torch.empty((n, N_POS, N_CH), dtype=torch.int16, device=device)
     depth = torch.empty((n,), dtype=torch.int32, device=device)
-    _lib.check(lib.cto_encode_pileup(_ptr(s.code), _ptr(s.bq), _ptr(s.mq), _ptr(s.pos_off), _ptr(s.ref_code),
-                                     _ptr(s.ind_off), _ptr(s.ind_entry), _ptr(s.win_pos), n, int(low_bq_cut),
-                                     _ptr(tensor), _ptr(depth), _stream_ptr()), "cto_encode_pileup")
+    _lib.check(lib.cto_encode_pileup(_ptr(s.planes), _ptr(s.grp_off), _ptr(s.ref_code), _ptr(s.ind_off), _ptr(s.ind_entry),
+                                     _ptr(s.win_pos), n, s.n_groups, _ptr(tensor), _ptr(depth), _stream_ptr()),
+               "cto_encode_pileup")
     return tensor, depth
 
 
@@ -122,14 +153,21 @@ class Engine:
         _lib.check(self.lib.cto_engine_fused_status(self.handle, _ptr(out)), "fused_status")
         return out
 
+    def set_qual_thresholds(self, qual_pass, qual_phaseable=None, qual_unphaseable=None):
+        """QUAL -> FILTER thresholds evaluated on the device (clairs/call_variants.py:67-76 ``--qual``;
+        src/postprocess_vcf.py:61-82; platform defaults in shared/param.py:35-40)."""
+        qp = qual_pass if qual_phaseable is None else qual_phaseable
+        qu = qual_pass if qual_unphaseable is None else qual_unphaseable
+        _lib.check(self.lib.cto_engine_set_qual_thresholds(self.handle, float(qual_pass), float(qp), float(qu)), "set_qual_thresholds")
+
     def set_likelihood(self, path_or_array):
         tables = np.ascontiguousarray(likelihood_tables(path_or_array, self.n_heads))
         _lib.check(self.lib.cto_engine_set_likelihood(self.handle, _ptr(tables), self.n_heads), "set_likelihood")
         self.has_likelihood = True
 
     # ---- encoder ----------------------------------------------------------------------------
-    def encode(self, s: PileupStream, low_bq_cut: int):
-        """Device PileupStream -> (int16 [N,33,34], int32 depth [N])."""
+    def encode(self, s, low_bq_cut: int = None):
+        """DeviceStream / device PackedStream -> (int16 [N,33,34], int32 depth [N])."""
         return encode_pileup(s, low_bq_cut, self.device)
 
     # ---- networks ---------------------------------------------------------------------------
@@ -166,14 +204,16 @@ class Engine:
             rev=torch.empty((n, 4), dtype=torch.int32, device=dev),
             post=torch.empty((n, h), dtype=torch.float64, device=dev) if posterior else None,
             call=torch.empty((n,), dtype=torch.int32, device=dev) if posterior else None,
+            qual=torch.empty((n,), dtype=torch.float64, device=dev) if posterior else None,
+            filter=torch.empty((n,), dtype=torch.int32, device=dev) if posterior else None,
         )
         _lib.check(self.lib.cto_predict(self.handle, _ptr(x_aff), _ptr(depth_aff), _ptr(x_neg), _ptr(depth_neg), n,
                                         _ptr(out['logits_aff']), _ptr(out['logits_neg']), _ptr(out['probs']),
                                         _ptr(out['post']), _ptr(out['call']), _ptr(out['fwd']), _ptr(out['rev']),
-                                        _stream_ptr()), "cto_predict")
+                                        _ptr(out['qual']), _ptr(out['filter']), _stream_ptr()), "cto_predict")
         return out
 
-    def run_sites(self, aff: PileupStream, neg: PileupStream | None, low_bq_cut: int, posterior=None):
+    def run_sites(self, aff, neg, low_bq_cut: int = None, posterior=None):
         """Device-resident hot path: encode both streams, then predict."""
         xa, da = self.encode(aff, low_bq_cut)
         if neg is None:
@@ -186,10 +226,10 @@ class Engine:
 
     # ---- end to end from host memory ----------------------------------------------------------
     @staticmethod
-    def _host_struct(s: PileupStream):
+    def _host_struct(s: PackedStream):
         hs = _lib.HostStream()
         keep = []
-        for name in PileupStream.__slots__:
+        for name in PackedStream.ARRAYS:
             a = getattr(s, name)
             if isinstance(a, torch.Tensor):
                 ptr = a.data_ptr()
@@ -198,15 +238,19 @@ class Engine:
                 ptr = a.ctypes.data
             keep.append(a)
             setattr(hs, name, ptr)
-        hs.n_reads = len(s.code)
+        hs.n_groups = s.n_groups
         hs.n_rows = len(s.ref_code)
         hs.n_ind = len(s.ind_entry)
         return hs, keep
 
-    def run_sites_host(self, aff: PileupStream, neg: PileupStream | None, low_bq_cut: int, out=None,
-                       want_tensors=False):
-        """Host arrays in -> host results out through ``cto_run_sites_host`` (H2D + D2H inside).
+    def run_sites_host(self, aff, neg, low_bq_cut: int = None, out=None, want_tensors=False):
+        """Host arrays in -> host results out through ``cto_run_sites_host`` (H2D + D2H inside).  ``aff`` / ``neg``:
+        PackedStream (host, ideally pinned), or PileupStream, which is packed here first (``low_bq_cut`` required).
         ``out`` may carry preallocated (pinned) host tensors 'probs', 'post', 'call'."""
+        if isinstance(aff, PileupStream):
+            aff = pack_stream(aff, low_bq_cut)
+        if isinstance(neg, PileupStream):
+            neg = pack_stream(neg, low_bq_cut)
         n = len(aff.win_pos) // N_POS
         h = self.n_heads
         out = dict(out or {})
@@ -215,14 +259,17 @@ class Engine:
         if self.has_likelihood:
             out.setdefault('post', torch.empty((n, h), dtype=torch.float64))
             out.setdefault('call', torch.empty((n,), dtype=torch.int32))
+            out.setdefault('qual', torch.empty((n,), dtype=torch.float64))
+            out.setdefault('filter', torch.empty((n,), dtype=torch.int32))
         if want_tensors:
             out['tensor_aff'] = torch.empty((n, N_POS, N_CH), dtype=torch.int16)
             out['tensor_neg'] = torch.empty((n, N_POS, N_CH), dtype=torch.int16)
         ha, keep_a = self._host_struct(aff)
         hn, keep_n = (None, None) if neg is None else self._host_struct(neg)
         _lib.check(self.lib.cto_run_sites_host(self.handle, C.byref(ha), C.byref(hn) if hn is not None else None, n,
-                                               int(low_bq_cut), _ptr(out['probs']), _ptr(out.get('post')),
-                                               _ptr(out.get('call')), _ptr(out.get('tensor_aff')),
+                                               _ptr(out['probs']), _ptr(out.get('post')),
+                                               _ptr(out.get('call')), _ptr(out.get('qual')), _ptr(out.get('filter')),
+                                               _ptr(out.get('tensor_aff')),
                                                _ptr(out.get('tensor_neg')), _stream_ptr()), "cto_run_sites_host")
         return out
 

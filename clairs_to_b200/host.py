@@ -9,7 +9,6 @@ predict chunk files byte-compatibly (ibid. 551; clairs/predict.py:121-132).
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
 
 import numpy as np
 
@@ -17,27 +16,38 @@ from . import _lib
 from .pileup_format import N_CH, N_POS, PileupStream
 
 
-@dataclass
 class Tokens:
-    stream: PileupStream          # win_pos is empty: the caller maps candidates to rows
-    row_pos: np.ndarray           # genomic position of every pileup row
-    alt_info: list                # per row: alt_info string for candidate rows, '' otherwise
+    """stream: PileupStream (win_pos empty: the caller maps candidates to rows); row_pos: genomic position of every
+    pileup row; alt_info: per row the alt_info string for candidate rows, '' otherwise (sliced lazily from one blob)."""
+
+    def __init__(self, stream, row_pos, alt_blob, alt_off):
+        self.stream, self.row_pos, self._blob, self._off, self._list = stream, row_pos, alt_blob, alt_off, None
+
+    @property
+    def alt_info(self):
+        if self._list is None:
+            blob, off = self._blob.decode(), self._off
+            self._list = [blob[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+        return self._list
+
+    def alt_info_of(self, row):
+        return self._blob[self._off[row]:self._off[row + 1]].decode()
 
 
 def _p(a):
     return C.c_void_p(a.ctypes.data)
 
 
-def tokenize_mpileup(text, ref_seq, ref_start, candidate_pos, max_indel_length=60) -> Tokens:
+def tokenize_mpileup(text, ref_seq, ref_start, candidate_pos, max_indel_length=60, n_threads=0) -> Tokens:
     lib = _lib.lib()
     if isinstance(text, str):
         text = text.encode()
     if isinstance(ref_seq, str):
         ref_seq = ref_seq.encode()
-    cand = np.ascontiguousarray(np.asarray(list(candidate_pos), dtype=np.int64))
+    cand = np.ascontiguousarray(np.asarray(candidate_pos if isinstance(candidate_pos, np.ndarray) else list(candidate_pos), dtype=np.int64))
     handle = C.c_void_p()
     _lib.check(lib.cto_tokenize_mpileup(text, len(text), ref_seq, len(ref_seq), int(ref_start), _p(cand), cand.size,
-                                        int(max_indel_length), C.byref(handle)), "cto_tokenize_mpileup")
+                                        int(max_indel_length), int(n_threads), C.byref(handle)), "cto_tokenize_mpileup")
     try:
         sizes = [C.c_int64() for _ in range(4)]
         _lib.check(lib.cto_tokens_sizes(handle, *[C.byref(s) for s in sizes]), "cto_tokens_sizes")
@@ -56,10 +66,8 @@ def tokenize_mpileup(text, ref_seq, ref_start, candidate_pos, max_indel_length=6
                                          _p(ind_entry), _p(row_pos), _p(alt), _p(alt_off)), "cto_tokens_export")
     finally:
         lib.cto_tokens_destroy(handle)
-    blob = alt.tobytes()[:n_alt].decode()
-    infos = [blob[alt_off[i]:alt_off[i + 1]] for i in range(n_rows)]
     stream = PileupStream(code, bq, mq, pos_off, ref_code, ind_off, ind_entry, np.empty(0, np.int32))
-    return Tokens(stream, row_pos, infos)
+    return Tokens(stream, row_pos, alt.tobytes()[:n_alt], alt_off)
 
 
 def format_tensor_rows(tensors) -> list:

@@ -224,3 +224,53 @@ def render_mpileup(stream: PileupStream, aux, ctg='chr1', first_pos=1001, decora
             bases = bqs = mqs = '*'
         rows.append("%s\t%d\tN\t%d\t%s\t%s\t%s\n" % (ctg, first_pos + r, hi - lo, bases, bqs, mqs))
     return rows
+
+
+def render_mpileup_text(stream: PileupStream, aux, ctg='chr1', first_pos=1001) -> bytes:
+    """The rows of ``render_mpileup`` (without decorations) as one bytes object, by the native renderer
+    (``cto_render_mpileup``): bench-scale streams cannot go through a Python loop per read."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.lib()
+    n_ind = len(stream.ind_entry)
+    ind_len = np.ascontiguousarray(aux['ind_len'], dtype=np.int64) if n_ind else np.zeros(1, np.int64)
+    ind_seq = np.ascontiguousarray(aux['ind_seq'], dtype=np.int64) if n_ind else np.zeros(1, np.int64)
+    cap = int(stream.n_reads) * 3 + int(ind_len.sum()) + 8 * n_ind + stream.n_rows * (len(ctg) + 48) + 1024
+    buf = np.empty(cap, dtype=np.uint8)
+    arrs = [np.ascontiguousarray(a) for a in (stream.code, stream.bq, stream.mq, stream.pos_off, stream.ind_entry)]
+    if arrs[4].size == 0:
+        arrs[4] = np.zeros(1, np.uint32)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    w = lib.cto_render_mpileup(p(arrs[0]), p(arrs[1]), p(arrs[2]), p(arrs[3]), stream.n_rows, p(arrs[4]), p(ind_len), p(ind_seq),
+                               ctg.encode(), int(first_pos), p(buf), cap)
+    if w < 0:
+        raise RuntimeError("cto_render_mpileup: buffer too small")
+    return buf[:w].tobytes()
+
+
+def take_candidates(stream: PileupStream, n: int) -> PileupStream:
+    """The first ``n`` candidates of a stream whose windows are disjoint and in row order (what synth_stream makes)."""
+    rows = n * N_POS
+    reads, inds = int(stream.pos_off[rows]), int(stream.ind_off[rows])
+    return PileupStream(stream.code[:reads], stream.bq[:reads], stream.mq[:reads], stream.pos_off[:rows + 1],
+                        stream.ref_code[:rows], stream.ind_off[:rows + 1], stream.ind_entry[:inds], stream.win_pos[:rows])
+
+
+def synth_pair_tiled(n_candidates, seed, platform='ont', base=50000, **kw):
+    """Bench-scale batches: ``base`` distinct candidates generated once and tiled to ``n_candidates`` (separate copies in
+    memory, so the bytes moved are real).  Returns ((aff, aff_aux), (neg, neg_aux)) like synth_pair when
+    n_candidates <= base, else ((aff, None), (neg, None))."""
+    if n_candidates <= base:
+        if n_candidates <= 20000:
+            return synth_pair(n_candidates, seed, platform, **kw)
+        affs, negs, a_aux, n_aux = [], [], [], []                      # bounded-memory pieces, aux arrays concatenated
+        for k, lo in enumerate(range(0, n_candidates, 20000)):
+            (a, aa), (g, ga) = synth_pair(min(20000, n_candidates - lo), seed * 1000 + k, platform, **kw)
+            affs.append(a); negs.append(g); a_aux.append(aa); n_aux.append(ga)
+        cat = lambda auxs: dict(ind_len=np.concatenate([x['ind_len'] for x in auxs]), ind_seq=np.concatenate([x['ind_seq'] for x in auxs]))
+        return (concat_streams(affs), cat(a_aux)), (concat_streams(negs), cat(n_aux))
+    (a, _), (g, _) = synth_pair(base, seed, platform, **kw)
+    reps = -(-n_candidates // base)
+    aff = take_candidates(concat_streams([a] * reps), n_candidates)
+    neg = take_candidates(concat_streams([g] * reps), n_candidates)
+    return (aff, None), (neg, None)

@@ -28,7 +28,7 @@ extern "C" {
 
 #define CTO_N_POS 33       /* shared/param.py:60 */
 #define CTO_N_CH 34        /* shared/param.py:56 */
-#define CTO_ABI_VERSION 1
+#define CTO_ABI_VERSION 2
 
 typedef struct cto_engine cto_engine;
 
@@ -40,16 +40,30 @@ int cto_device_check(int* sm_count);
 
 /*
  * Pileup tensor encoder.  Replaces decode_pileup_bases() + the window assembly of create_tensor()
- * (src/create_tensor_pileup_calling.py:146-229, 461, 513-516, 537-543).  Input layout: see
- * clairs_to_b200/pileup_format.py.  Output tensor int16 [n_candidates, 33, 34]; depth_dev
- * (nullable) receives the centre-row depth that leads the reference's alt_info string (ibid. 208).
- * low_bq_cut is the literal of ibid. 149: 30 if platform == 'ont' else 10.
+ * (src/create_tensor_pileup_calling.py:146-229, 461, 513-516, 537-543).  Input = one packed stream (see
+ * clairs_to_b200/pileup_format.py and cto_pack_reads below): `planes` holds 8 bit-plane bytes per group of eight
+ * reads, grp_off[row] .. grp_off[row + 1] are the groups of a pileup row; ref_code / ind_off / ind_entry / win_pos as
+ * documented there.  The low-BQ literal of ibid. 149 (30 if platform == 'ont' else 10) is applied when the reads are
+ * packed.  Output tensor int16 [n_candidates, 33, 34]; depth_dev (nullable) receives the centre-row depth that leads
+ * the reference's alt_info string (ibid. 208).
+ * Contract: planes_dev 8-byte aligned (16-byte aligned arrays take the faster bulk-copy path) and ALLOCATED up to the
+ * next multiple of 16 bytes beyond 8 * n_groups.
  */
-int cto_encode_pileup(const uint8_t* code_dev, const uint8_t* bq_dev, const uint8_t* mq_dev,
-                      const int32_t* pos_off_dev, const uint8_t* ref_code_dev,
-                      const int32_t* ind_off_dev, const uint32_t* ind_entry_dev,
-                      const int32_t* win_pos_dev, int64_t n_candidates, int low_bq_cut,
-                      int16_t* tensor_dev, int32_t* depth_dev, void* stream);
+int cto_encode_pileup(const uint8_t* planes_dev, const int32_t* grp_off_dev, const uint8_t* ref_code_dev,
+                      const int32_t* ind_off_dev, const uint32_t* ind_entry_dev, const int32_t* win_pos_dev,
+                      int64_t n_candidates, int64_t n_groups, int16_t* tensor_dev, int32_t* depth_dev, void* stream);
+
+/*
+ * Host packer: per-read byte arrays (code / bq / mq as produced by cto_tokenize_mpileup; pos_off = CSR offsets of the
+ * rows) -> the encoder's bit-plane layout.  One packed byte per read: bits 0-3 symbol (0-3 ACGT, 4-7 acgt, 8 '*',
+ * 9 '#', 10 N, 11 n), bit 4 "plain" (no indel suffix: src/create_tensor_pileup_calling.py:160-204 counts indel reads
+ * only toward I/D), bit 5 MQ >= 20 (ibid. 147), bit 6 MQ < 20 (148), bit 7 BQ < low_bq_cut (149); rows are padded to
+ * whole groups of eight reads with null bytes, and each group is stored bit-sliced (byte j = bit j of its eight reads).
+ * grp_off: int32 [n_rows + 1], the prefix sum of ceil(row depth / 8) (computed by the caller); planes_out: 8 *
+ * grp_off[n_rows] bytes (+ padding to a multiple of 16, which is zero-filled).  n_threads <= 0: all host cores.
+ */
+int cto_pack_reads(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off, int64_t n_rows,
+                   int low_bq_cut, const int32_t* grp_off, uint8_t* planes_out, int n_threads);
 
 /*
  * Engine = AFF + NEG weights (flat fp32 blobs in HOST memory, produced by
@@ -87,7 +101,17 @@ int cto_forward_neg(cto_engine* e, const float* x_dev, int64_t n, float* logits_
  * post_dev double [n, n_heads]; call_dev int32 [n]: bits 0-7 argmax, bit 8 = bin index clamped.
  */
 int cto_softmax_posterior(cto_engine* e, const float* logits_aff_dev, const float* logits_neg_dev, int64_t n,
-                          float* probs_dev, double* post_dev, int32_t* call_dev, void* stream);
+                          float* probs_dev, double* post_dev, int32_t* call_dev, double* qual_dev, int32_t* filter_dev,
+                          void* stream);
+/*
+ * QUAL and the QUAL -> FILTER thresholds on the device (same kernel): qual_dev double [n] = quality_score_from of the
+ * winning posterior (clairs/call_variants.py:81-88: Phred_Trans * log(((1-p)+1e-10)/(p+1e-10)) + 2, floored at 0,
+ * 4 decimals); filter_dev int32 [n]: bit 0 QUAL >= qual_pass (`--qual`, call_variants.py:67-76), bit 1 QUAL >=
+ * qual_phaseable, bit 2 QUAL >= qual_unphaseable (src/postprocess_vcf.py:61-82; defaults shared/param.py:35-40).
+ * The RefCall / variant decision needs the alt_info strings (call_variants.py:306-358) and stays on the host.
+ * Thresholds default to 0 (every QUAL passes).
+ */
+int cto_engine_set_qual_thresholds(cto_engine* e, double qual_pass, double qual_phaseable, double qual_unphaseable);
 
 /*
  * The Bayes combine alone, for the call_variants sub-command whose input is a predict FILE
@@ -142,7 +166,9 @@ int cto_engine_profile_read(cto_engine* e, double* ms, int64_t* launches, double
 /*
  * Tuning / profiling knobs (not part of the drop-in surface): cto_debug_set(1) + cto_debug_timing(buf) make
  * CTA 0 of the GEMM kernel (slots [0,32)) and cluster 0 of the GRU kernel (slots [32,64)) record per-phase
- * clock64() counters into a device buffer [64 x int64] (profiles/phase_timing_*.py print them).
+ * clock64() counters into a device buffer [64 x int64] (profiles/phase_timing_*.py print them).  Results stay correct.
+ * Flag bits other than bit 0 select timing-attribution kernel variants that compute WRONG results; they exist only in
+ * a debug library built with CTO_DEBUG_KNOBS=1 and are ignored by the release libcto_b200.so.
  */
 void cto_debug_set(int flags);
 void cto_debug_timing(long long* dev_buf);
@@ -153,54 +179,62 @@ int cto_strand_counts(const int16_t* x_aff_dev, int64_t n, int32_t* fwd_dev, int
 
 /*
  * The per-mini-batch body of predict() (clairs/predict.py:610-699) for n candidates at once:
- * rescale both tensors, NEG and AFF forward, softmax, strand counts, posterior.
+ * rescale both tensors, NEG and AFF forward, softmax, strand counts, posterior, QUAL / FILTER bits.
  * Nullable outputs are skipped.  x_neg_dev == x_aff_dev is allowed (Illumina symlink case,
  * run_clairs_to:1248-1252).
  */
 int cto_predict(cto_engine* e, const int16_t* x_aff_dev, const int32_t* depth_aff_dev, const int16_t* x_neg_dev,
                 const int32_t* depth_neg_dev, int64_t n, float* logits_aff_dev, float* logits_neg_dev,
                 float* probs_dev, double* post_dev, int32_t* call_dev, int32_t* fwd_dev, int32_t* rev_dev,
-                void* stream);
+                double* qual_dev, int32_t* filter_dev, void* stream);
 
 /*
- * One stream of per-site read arrays in HOST memory (see clairs_to_b200/pileup_format.py).
+ * One packed stream in HOST memory (see clairs_to_b200/pileup_format.py, cto_pack_reads).
  */
 typedef struct cto_host_stream {
-    const uint8_t* code;
-    const uint8_t* bq;
-    const uint8_t* mq;
-    const int32_t* pos_off;
+    const uint8_t* planes;
+    const int32_t* grp_off;
     const uint8_t* ref_code;
     const int32_t* ind_off;
     const uint32_t* ind_entry;
     const int32_t* win_pos;
-    int64_t n_reads, n_rows, n_ind;
+    int64_t n_groups, n_rows, n_ind;
 } cto_host_stream;
 
 /*
- * End-to-end host call: host read arrays in -> host probabilities / posteriors out.  Copies both
- * streams to the device, encodes, predicts and copies results back; synchronises before returning.
- * neg == NULL reuses the AFF stream.  Outputs (host, nullable): probs fp32 [n, 2H, 2],
- * post double [n, H], call int32 [n], tensor_aff / tensor_neg int16 [n, 33, 34].
+ * End-to-end host call: packed host streams in -> host probabilities / posteriors out.  Copies both streams to the
+ * device span by span (overlapped with the kernels of the previous chunk), encodes, predicts and copies results back;
+ * synchronises before returning.  neg == NULL reuses the AFF stream (Illumina symlink case, run_clairs_to:1248-1252).
+ * Outputs (host, nullable): probs fp32 [n, 2H, 2], post double [n, H], call int32 [n], qual double [n], filter int32 [n]
+ * (cto_engine_set_qual_thresholds), tensor_aff / tensor_neg int16 [n, 33, 34].
  */
 int cto_run_sites_host(cto_engine* e, const cto_host_stream* aff, const cto_host_stream* neg, int64_t n_candidates,
-                       int low_bq_cut, float* probs_host, double* post_host, int32_t* call_host,
+                       float* probs_host, double* post_host, int32_t* call_host, double* qual_host, int32_t* filter_host,
                        int16_t* tensor_aff_host, int16_t* tensor_neg_host, void* stream);
 
 /*
  * Host tokenizer for `samtools mpileup` text (src/create_tensor_pileup_calling.py:120-144, 472-497):
  * parses rows "chr pos ref depth bases BQ MQ" into the read arrays above, and builds the alt_info
  * strings (ibid. 158-209) of candidate rows.  Two-phase: create -> query sizes -> export -> destroy.
+ * The text is split at row boundaries over n_threads host threads (<= 0: all cores); rows are independent.
  */
 typedef struct cto_tokens cto_tokens;
 int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq, int64_t ref_len,
                          int64_t ref_start, const int64_t* candidate_pos, int64_t n_candidates,
-                         int max_indel_length, cto_tokens** out);
+                         int max_indel_length, int n_threads, cto_tokens** out);
 int cto_tokens_sizes(const cto_tokens* t, int64_t* n_reads, int64_t* n_rows, int64_t* n_ind, int64_t* alt_info_bytes);
 int cto_tokens_export(const cto_tokens* t, uint8_t* code, uint8_t* bq, uint8_t* mq, int32_t* pos_off,
                       uint8_t* ref_code, int32_t* ind_off, uint32_t* ind_entry, int64_t* row_pos,
                       char* alt_info, int64_t* alt_info_off);
 void cto_tokens_destroy(cto_tokens* t);
+/*
+ * The inverse of the tokenizer, for synthetic workloads (bench.py's text-in leg, tests): read arrays -> mpileup text rows
+ * "ctg pos N depth bases BQ MQ" (position = first_pos + row).  ind_len / ind_seq: per indel-carrying read, in read
+ * order, the indel length and the inserted bases packed two bits each.  Returns bytes written, -1 if cap is too small.
+ */
+int64_t cto_render_mpileup(const uint8_t* code, const uint8_t* bq, const uint8_t* mq, const int32_t* pos_off, int64_t n_rows,
+                           const uint32_t* ind_entry, const int64_t* ind_len, const int64_t* ind_seq, const char* ctg,
+                           int64_t first_pos, char* out, int64_t cap);
 
 /*
  * Text codec for the chunk files: the 1122-int tensor field of a tensor_can row

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _worker(args):
-    seed, n, n_heads = args
+    seed, n, n_heads, platform, single_stream = args
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import numpy as np
@@ -29,8 +29,9 @@ def _worker(args):
     from oracle import nn_oracle, pileup_oracle, posterior_oracle
     torch.set_num_threads(1)
     literal = "ont"          # create_tensor() always decodes with the callee default (CT:499-511)
-    (aff, aff_aux), (neg, neg_aux) = synth.synth_pair(n, seed, 'ont')
-    texts = [synth.render_mpileup(s, a) for s, a in ((aff, aff_aux), (neg, neg_aux))]
+    (aff, aff_aux), (neg, neg_aux) = synth.synth_pair(n, seed, platform)
+    pairs = ((neg, neg_aux),) if single_stream else ((aff, aff_aux), (neg, neg_aux))   # Illumina: one tensor feeds both nets
+    texts = [synth.render_mpileup(s, a) for s, a in pairs]
     refs = ["ACGT"[int(c)] for c in neg.ref_code]
     aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads), 100 + n_heads)
     neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 200 + n_heads)
@@ -56,7 +57,7 @@ def _worker(args):
     posts = []
     for lo in range(0, n, 250):
         pa = nn_oracle.softmax_heads(nn_oracle.aff_forward(xs[0][lo:lo + 250], aff_sd)).numpy()
-        pn = nn_oracle.softmax_heads(nn_oracle.neg_forward(xs[1][lo:lo + 250], neg_sd)).numpy()
+        pn = nn_oracle.softmax_heads(nn_oracle.neg_forward(xs[-1][lo:lo + 250], neg_sd)).numpy()
         for k in range(pa.shape[0]):
             p8 = [float("{:0.8f}".format(min(v, 0.99999999))) for v in pa[k, :, 1]]
             q8 = [float("{:0.8f}".format(min(v, 0.99999999))) for v in pn[k, :, 1]]
@@ -72,27 +73,36 @@ def make_pool(procs=None):
     return mp.get_context("spawn").Pool(procs), procs
 
 
-def run(per_proc=300, procs=None, n_heads=4, seed=9000, pool=None):
-    """Returns dict(value=candidates/s over all processes, cores, sample, seconds, encoder_share).  `pool` (from
-    make_pool) is reused when given, so that a multi-step run pays the process start-up once."""
+def run(per_proc=300, procs=None, n_heads=4, seed=9000, pool=None, platform='ont', mix=None, single_stream=False):
+    """Returns dict(value=candidates/s over all processes, cores, sample, seconds, encoder_share, candidates).  `pool`
+    (from make_pool) is reused when given, so that a multi-step run pays the process start-up once.  `mix`: list of
+    (n_heads, fraction) -- the model pairs of the workload (SNV 4 heads, indel 6 heads) and their share of candidates;
+    every process runs each pair on its share, one after the other."""
     own = pool is None
     if own:
         pool, procs = make_pool(procs)
     else:
         procs = procs or len(os.sched_getaffinity(0))
+    mix = mix or [(n_heads, 1.0)]
+    slowest, done, enc, tot = 0.0, 0, 0.0, 0.0
     try:
-        res = pool.map(_worker, [(seed + i, per_proc, n_heads) for i in range(procs)])
+        for heads, frac in mix:
+            n = max(1, int(round(per_proc * frac)))
+            res = pool.map(_worker, [(seed + i, n, heads, platform, single_stream) for i in range(procs)])
+            slowest += max(r[0] for r in res)
+            done += sum(r[2] for r in res)
+            enc += sum(r[1] for r in res)
+            tot += sum(r[0] for r in res)
     finally:
         if own:
             pool.close()
             pool.join()
-    slowest = max(r[0] for r in res)
-    done = sum(r[2] for r in res)
-    return dict(value=done / slowest, unit="candidate sites/s", cores=procs, kind="port",
-                sample="%d candidates (%d per process x %d single-thread processes), ONT-shape synthetic, "
-                       "encoder(2 streams, CPython)+rescale+AFF+NEG(torch CPU fp32)+posterior; no text I/O"
-                       % (done, per_proc, procs),
-                seconds=slowest, encoder_share=sum(r[1] for r in res) / sum(r[0] for r in res))
+    return dict(value=done / slowest, unit="candidate sites/s", cores=procs, kind="port", candidates=done,
+                sample="%d candidates (%d per process x %d single-thread processes; model pairs %s), %s-shape synthetic, "
+                       "mpileup text parse + encoder(%d stream%s, CPython)+rescale+AFF+NEG(torch CPU fp32)+posterior; no gzip I/O"
+                       % (done, per_proc, procs, "+".join("%d-head" % h for h, _ in mix), platform, 1 if single_stream else 2,
+                          "" if single_stream else "s"),
+                seconds=slowest, encoder_share=enc / tot)
 
 
 if __name__ == "__main__":

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(handle, name), "missing export " + name
     assert set(_lib.SIGNATURES) == declared
-    assert _lib.lib().cto_abi_version() == 1
+    assert _lib.lib().cto_abi_version() == 2
 
 
 def test_tokenizer_matches_oracle_on_golden_rows(golden_dir):
@@ -196,3 +196,39 @@ def test_parse_tensor_file_edge_cases():
     assert tf.depth.tolist() == [12, 12]
     with pytest.raises(_lib.CtoError):                       # a tensor field that is too short
         host.TensorFile(("chr1\t77\t%s\t1 2 3\t12-\tsnv\tA\n" % ("ACGT" * 8 + "A")).encode())
+
+
+def test_bit_plane_packer_matches_numpy_statement():
+    """cto_pack_reads (native, multi-threaded) == the numpy statement of the packed layout, for both low-BQ literals."""
+    from clairs_to_b200 import synth
+    from clairs_to_b200.pileup_format import pack_stream, pack_stream_numpy
+    (aff, _), (neg, _) = synth.synth_pair(700, 3, 'ont', depth_lo=0, depth_hi=150)
+    for s in (aff, neg):
+        for cut in (10, 30):
+            for threads in (1, 3):
+                a, b = pack_stream(s, cut, n_threads=threads), pack_stream_numpy(s, cut)
+                assert a.n_groups == b.n_groups and np.array_equal(a.grp_off, b.grp_off)
+                assert np.array_equal(a.planes[:8 * a.n_groups], b.planes[:8 * b.n_groups])
+                assert not a.planes[8 * a.n_groups:].any()            # the 16-byte padding is zero-filled
+    # rows are padded to whole groups with NULL reads: one byte per read + at most 7 per row
+    assert 8 * a.n_groups <= neg.n_reads + 7 * neg.n_rows
+
+
+def test_native_renderer_and_threaded_tokenizer_round_trip():
+    """cto_render_mpileup == the python renderer; the tokenizer gives the same arrays with 1 or 4 threads and
+    reproduces the generated read arrays."""
+    from clairs_to_b200 import synth
+    from clairs_to_b200.host import tokenize_mpileup
+    (aff, aa), (neg, na) = synth.synth_pair(400, 11, 'ont', depth_lo=0, depth_hi=120)
+    for s, a in ((aff, aa), (neg, na)):
+        text = synth.render_mpileup_text(s, a)
+        assert text == ''.join(synth.render_mpileup(s, a)).encode()
+        ref = ''.join("ACGT"[c] for c in s.ref_code)
+        cands = list(range(1001 + 16, 1001 + s.n_rows, 33))
+        t1 = tokenize_mpileup(text, ref, 1001, cands, 60, n_threads=1)
+        t4 = tokenize_mpileup(text * 1, ref, 1001, cands, 60, n_threads=4)
+        for name in ("code", "bq", "mq", "pos_off", "ref_code", "ind_off", "ind_entry"):
+            assert np.array_equal(getattr(t1.stream, name), getattr(t4.stream, name)), name
+        assert t1.alt_info == t4.alt_info and np.array_equal(t1.row_pos, t4.row_pos)
+        assert np.array_equal(t1.stream.code, s.code) and np.array_equal(t1.stream.bq, s.bq) and np.array_equal(t1.stream.mq, s.mq)
+        assert np.array_equal(t1.stream.pos_off, s.pos_off) and np.array_equal(t1.stream.ind_off, s.ind_off)
