@@ -230,31 +230,39 @@ def main():
     # ---- workload: per part an engine + this rank's shard of packed streams (device-resident and pinned host copies) ----
     t_gen = time.time()
     parts = []
+    PIECE = 1000000                       # candidates per batch: one batch holds at most 2^31 reads (int32 CSR offsets)
     for pi, (n_heads, n_part) in enumerate(cfg["parts"]):
         n_loc = (cdist.shard_bounds(n_part, world, rank)[1] - cdist.shard_bounds(n_part, world, rank)[0]) if cfg["total"] else n_part
-        # config 1 generates every site (as in round 1; also gives the text leg its indel sequences), the large
-        # configs generate 50 000 distinct sites and tile them
-        (aff, aff_aux), (neg, neg_aux) = synth.synth_pair_tiled(n_loc, 20241 + 7 * pi + rank, cfg["platform"],
-                                                                base=200000 if args.config == 1 else 50000)
-        if cfg["single_stream"]:
-            aff, aff_aux = neg, neg_aux                 # NEG is a symlink of AFF when both use --min-BQ 0 (run_clairs_to:1248-1252)
-        streams = [aff] if cfg["single_stream"] else [aff, neg]
-        host = [pack_stream(s, cut, n_threads=host_threads) for s in streams]
-        pinned = [PackedStream(*[pin(a) for a in h.arrays()], h.n_groups, h.low_bq_cut, h.n_reads) for h in host]
-        device = [packed_to_device(h, dev) for h in host]
         aff_sd = synth_weights.synth_state_dict(synth_weights.aff_state_dict_shapes(n_heads), 100 + n_heads)
         neg_sd = synth_weights.synth_state_dict(synth_weights.neg_state_dict_shapes(n_heads), 200 + n_heads)
         eng = Engine(aff_sd, neg_sd, max_batch=args.max_batch, device=dev, likelihood=synthetic_likelihood(n_heads))
         if cfg["qual"]:
             eng.set_qual_thresholds(*cfg["qual"])
-        parts.append(dict(n=n_loc, n_total=n_part * (1 if cfg["total"] else world), heads=n_heads, eng=eng, dev=device, pinned=pinned,
-                          raw=(aff, aff_aux, neg, neg_aux), alg_bytes=sum(h.algorithmic_bytes() for h in host),
-                          h2d=sum(h.nbytes() for h in host), reads=sum(h.n_reads for h in host)))
+        for lo in range(0, n_loc, PIECE):
+            n_piece = min(PIECE, n_loc - lo)
+            # config 1 generates every site (as in round 1; also gives the text leg its indel sequences), the large
+            # configs generate 50 000 distinct sites and tile them
+            (aff, aff_aux), (neg, neg_aux) = synth.synth_pair_tiled(n_piece, 20241 + 7 * pi + rank + 101 * (lo // PIECE), cfg["platform"],
+                                                                    base=200000 if args.config == 1 else 50000)
+            if cfg["single_stream"]:
+                aff, aff_aux = neg, neg_aux             # NEG is a symlink of AFF when both use --min-BQ 0 (run_clairs_to:1248-1252)
+            streams = [aff] if cfg["single_stream"] else [aff, neg]
+            host = [pack_stream(s, cut, n_threads=host_threads) for s in streams]
+            pinned = [PackedStream(*[pin(a) for a in h.arrays()], h.n_groups, h.low_bq_cut, h.n_reads) for h in host]
+            device = [packed_to_device(h, dev) for h in host]
+            parts.append(dict(n=n_piece, n_total=(n_part if cfg["total"] else n_part * world) * n_piece // max(n_loc, 1), heads=n_heads, eng=eng,
+                              dev=device, pinned=pinned, raw=(aff, aff_aux, neg, neg_aux) if args.config == 1 else None,
+                              alg_bytes=sum(h.algorithmic_bytes() for h in host), h2d=sum(h.nbytes() for h in host),
+                              reads=sum(h.n_reads for h in host)))
+            del aff, neg, host
     t_gen = time.time() - t_gen
+    if world > 1:
+        for p in parts:
+            p["sizes"] = cdist.exchange_sizes(p["n"], dev)        # shard lengths per batch, exchanged once
     lib = parts[0]["eng"].lib
     torch.cuda.synchronize()
     n_local = sum(p["n"] for p in parts)
-    n_global = sum(p["n_total"] for p in parts)
+    n_global = sum(n for _, n in cfg["parts"]) * (1 if cfg["total"] else world)
 
     enc_ev = []
 
@@ -272,7 +280,7 @@ def main():
             out = eng.predict(xa, da, xn, dn)
             if world > 1:
                 # the path's single exchange: per-candidate results to rank 0
-                cdist.gather_rows(out['probs'].reshape(p["n"], -1), p["n_total"] if cfg["total"] else p["n"] * world)
+                cdist.gather_rows_padded(out['probs'].reshape(p["n"], -1), p["sizes"])
         return out
 
     def barrier():
@@ -287,7 +295,7 @@ def main():
         step(False)
     barrier()
     for p in parts:
-        _lib.check(lib.cto_engine_profile(p["eng"].handle, int(os.environ.get('CTO_PROFILE_LEVEL', '2'))))
+        _lib.check(lib.cto_engine_profile(p["eng"].handle, int(os.environ.get('CTO_PROFILE_LEVEL', '2'))))   # idempotent per engine
     launches0 = lib.cto_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -303,13 +311,18 @@ def main():
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     kinds = lib.cto_engine_profile_kinds()
     fam = {}
+    engines = []
     for p in parts:
+        if not any(p["eng"] is e for e, _ in engines):
+            engines.append((p["eng"], sum(q["n"] for q in parts if q["eng"] is p["eng"])))
+    for eng_k, n_k in engines:
+        p = dict(eng=eng_k, n=n_k, heads=eng_k.n_heads)
         pms = (C.c_double * kinds)(); pcnt = (C.c_int64 * kinds)(); pfl = (C.c_double * kinds)()
         _lib.check(lib.cto_engine_profile_read(p["eng"].handle, pms, pcnt, pfl))
         _lib.check(lib.cto_engine_profile(p["eng"].handle, 0))
         for k in range(kinds):
             if pcnt[k]:
-                name = lib.cto_engine_profile_name(k).decode() + ("" if len(parts) == 1 else "[%d heads]" % p["heads"])
+                name = lib.cto_engine_profile_name(k).decode() + ("" if len(engines) == 1 else "[%d heads]" % p["heads"])
                 fam[name] = dict(name=name, ms_per_step=pms[k] / args.steps, launches_per_step=pcnt[k] / args.steps,
                                  flop_per_candidate=pfl[k], candidates_per_step=p["n"])
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -388,7 +401,7 @@ def main():
 
         # ---- the same from mpileup TEXT: tokenizer (multi-threaded host C++) + packer + the call above --------------
         p0 = parts[0]
-        if args.config == 1 and not args.no_text and p0["raw"][1] is not None:
+        if args.config == 1 and not args.no_text and p0["raw"] is not None and p0["raw"][1] is not None:
             aff, aff_aux, neg, neg_aux = p0["raw"]
             texts = [synth.render_mpileup_text(s, a) for s, a in ((aff, aff_aux), (neg, neg_aux))]
             ref = ''.join("ACGT"[c] for c in neg.ref_code)
@@ -443,8 +456,8 @@ def main():
                                 datagen_s=round(t_gen, 1)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
-    for p in parts:
-        p["eng"].close()
+    for eng_k, _ in engines:
+        eng_k.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -41,3 +41,30 @@ def gather_rows(local: torch.Tensor, n_total: int, dst: int = 0, group=None):
         return None
     out = out.reshape((world, width) + tuple(local.shape[1:]))
     return torch.cat([out[r, :sizes[r]] for r in range(world)], dim=0)
+
+
+def exchange_sizes(n_local: int, device, group=None):
+    """Shard lengths of every rank (one tiny all_gather + a host read: do it once per batch, outside any hot loop)."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([n_local], dtype=torch.int64, device=device)
+    sizes = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    return [int(v) for v in sizes.tolist()]
+
+
+def gather_rows_padded(local: torch.Tensor, sizes=None, dst: int = 0, group=None):
+    """The same single collective for shards of arbitrary lengths ``sizes`` (from ``exchange_sizes``; exchanged here when
+    omitted): rows are padded to the longest shard.  Returns the concatenated rows on ``dst``, None elsewhere."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if sizes is None:
+        sizes = exchange_sizes(local.shape[0], local.device, group)
+    width = max(sizes)
+    padded = local.new_zeros((width,) + tuple(local.shape[1:]))
+    padded[:local.shape[0]] = local
+    out = local.new_empty((world * width,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    if rank != dst:
+        return None
+    out = out.reshape((world, width) + tuple(local.shape[1:]))
+    return torch.cat([out[r, :sizes[r]] for r in range(world)], dim=0)

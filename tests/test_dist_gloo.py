@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from clairs_to_b200.dist import gather_rows, shard_bounds, shard_sizes
+from clairs_to_b200.dist import exchange_sizes, gather_rows, gather_rows_padded, shard_bounds, shard_sizes
 
 
 def test_shard_bounds_cover_and_balance():
@@ -29,10 +29,16 @@ def _worker(rank, world, port, n_total, q):
     full = torch.arange(n_total * 16, dtype=torch.float32).reshape(n_total, 8, 2)
     lo, hi = shard_bounds(n_total, world, rank)
     got = gather_rows(full[lo:hi].clone(), n_total)
+    # uneven shards whose lengths the ranks only know locally (bench.py configs 2-4: batches of a strong-scaled shard)
+    cut = n_total // 3 if rank == 0 else None
+    lo2, hi2 = (0, n_total // 3) if rank == 0 else (n_total // 3, n_total)
+    sizes = exchange_sizes(hi2 - lo2, torch.device("cpu"))
+    got2 = gather_rows_padded(full[lo2:hi2].clone(), sizes)
+    got3 = gather_rows_padded(full[lo2:hi2].clone())
     if rank == 0:
-        q.put(bool(torch.equal(got, full)))
+        q.put(bool(torch.equal(got, full)) and bool(torch.equal(got2, full)) and bool(torch.equal(got3, full)) and sizes == [n_total // 3, n_total - n_total // 3])
     else:
-        assert got is None
+        assert got is None and got2 is None and got3 is None
     dist.barrier()
     dist.destroy_process_group()
 
