@@ -147,11 +147,51 @@ def export_neg(sd):
     return blob.finish(), np.asarray(cfg, dtype=np.int32)
 
 
-def state_dict_from_checkpoint(path, key):
-    """Load a reference checkpoint (``torch.load(..., weights_only=False)[key]``,
-    clairs/predict.py:513-517).  Unpickling needs an importable ``clairs.model`` (App. B)."""
+class _ModuleShell:
+    """Stand-in for a reference class (``clairs.model.CvT`` ...) when the reference package is not importable: pickle
+    only restores attributes (``__init__`` is never called), and all that is needed from the restored object graph are
+    the ``_parameters`` / ``_buffers`` / ``_modules`` dictionaries torch.nn.Module keeps."""
+
+
+def _shell_class(module, name):
     import torch
-    obj = torch.load(path, map_location='cpu', weights_only=False)
+    return type(name, (torch.nn.Module,), {"__module__": module, "__doc__": _ModuleShell.__doc__})
+
+
+def _tolerant_pickle_module():
+    """A ``pickle_module`` for torch.load whose Unpickler resolves classes of missing ``clairs.*`` / ``shared.*``
+    modules to empty torch.nn.Module subclasses."""
+    import pickle
+    import types
+
+    class Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                if module.split('.')[0] in ('clairs', 'shared', 'src'):
+                    return _shell_class(module, name)
+                raise
+
+    shim = types.ModuleType("cto_tolerant_pickle")
+    shim.Unpickler = Unpickler
+    shim.load = lambda f, **kw: Unpickler(f, **kw).load()
+    for k in ("__name__", "dumps", "dump", "loads", "PickleError", "UnpicklingError", "PicklingError", "HIGHEST_PROTOCOL", "DEFAULT_PROTOCOL"):
+        if hasattr(pickle, k) and k != "__name__":
+            setattr(shim, k, getattr(pickle, k))
+    return shim
+
+
+def state_dict_from_checkpoint(path, key):
+    """Load a reference checkpoint: ``torch.load(..., weights_only=False)[key]`` is a whole pickled ``clairs.model``
+    module (clairs/predict.py:513-517); a bare ``state_dict`` under the key is accepted too.  Inside a ClairS-TO checkout
+    ``clairs.model`` is importable and the pickle loads as it does there; elsewhere the classes are resolved to empty
+    torch.nn.Module shells, which is enough to read the parameters (hyper-parameters are derived from tensor shapes)."""
+    import torch
+    try:
+        obj = torch.load(path, map_location='cpu', weights_only=False)
+    except (ImportError, AttributeError, ModuleNotFoundError):
+        obj = torch.load(path, map_location='cpu', weights_only=False, pickle_module=_tolerant_pickle_module())
     model = obj[key] if isinstance(obj, dict) and key in obj else obj
     return model.state_dict() if hasattr(model, 'state_dict') else model
 

@@ -120,6 +120,33 @@ def nn_golden():
     print("nn_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
+CLASS_DEFAULT_CVT = dict(s1=(32, 1, 1), s2=(64, 3, 2), s3=(128, 6, 10))     # clairs/model.py:153-176 (CvT() defaults)
+
+
+def nn_golden_default():
+    """The CvT CLASS-DEFAULT hyper-parameters (stage-1 width 32, stage 3 with 6 heads and depth 10): SNV checkpoints are
+    pickled modules whose dimensions live in the pickle (clairs/predict.py:513-517), so the default-constructed class is
+    a shape the drop-in has to take.  Reference: ``CvT()`` / ``CvT_Indel()`` with no arguments."""
+    from clairs.model import CvT, CvT_Indel
+    torch.set_num_threads(4)
+    out = {}
+    rng = np.random.default_rng(6)
+    for n_heads in (4, 6):
+        aff = (CvT if n_heads == 4 else CvT_Indel)().eval()
+        sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads, CLASS_DEFAULT_CVT), 300 + n_heads, 0.7)
+        missing = aff.load_state_dict(sd, strict=False)
+        assert not missing.unexpected_keys and all(k.endswith("num_batches_tracked") for k in missing.missing_keys), missing
+        x = rng.integers(-60, 61, size=(24, 33, 34)).astype(np.float32)
+        x[rng.random(x.shape) < 0.5] = 0.0
+        x[12:] *= np.float32(0.41)
+        with torch.no_grad():
+            la = torch.stack(aff(torch.from_numpy(x)), 1).numpy()
+        out["x_%d" % n_heads] = x
+        out["aff_logits_%d" % n_heads] = la
+    np.savez_compressed(os.path.join(HERE, "nn_golden_default.npz"), **out)
+    print("nn_golden_default.npz:", {k: v.shape for k, v in out.items()}, {k: float(np.abs(v).max()) for k, v in out.items()})
+
+
 def likelihood_file(path, n_heads, seed):
     rng = np.random.default_rng(seed)
     rows = [rng.uniform(0.05, 0.95, size=(10, 10)) for _ in range(n_heads)]
@@ -255,6 +282,7 @@ if __name__ == "__main__":
         encoder_golden()
     if a.only in (None, "nn"):
         nn_golden()
+        nn_golden_default()
     if a.only in (None, "pipeline"):
         pipeline_golden()
     if a.only in (None, "create_tensor"):

@@ -71,12 +71,66 @@ def _save_checkpoints(tmp_path, n_heads):
     return a, n
 
 
+def _module_tree(sd, class_names):
+    """A torch.nn.Module object graph with the attribute layout of a reference module (parameters / buffers under the
+    dotted names of ``sd``), whose classes are called ``clairs.model.<name>``: what ``torch.save({'model_acgt': model})``
+    pickles in the reference (clairs/predict.py:513-517).  The classes are bare shells registered under a temporary
+    ``clairs.model`` module, so the file refers to ``clairs.model.CvT`` etc. exactly like a real checkpoint."""
+    import types
+    mod = types.ModuleType("clairs.model")
+    pkg = types.ModuleType("clairs")
+    pkg.model = mod
+    classes = {}
+    for name in class_names:
+        classes[name] = type(name, (torch.nn.Module,), {"__module__": "clairs.model"})
+        setattr(mod, name, classes[name])
+    root = classes[class_names[0]]()
+    inner = classes[class_names[1]]
+    for key, value in sd.items():
+        node = root
+        parts = key.split(".")
+        for part in parts[:-1]:
+            if part not in node._modules:
+                node.add_module(part, inner())
+            node = node._modules[part]
+        if parts[-1].startswith("running_") or parts[-1] == "num_batches_tracked":
+            node.register_buffer(parts[-1], value.clone())
+        else:
+            node.register_parameter(parts[-1], torch.nn.Parameter(value.clone(), requires_grad=False))
+    return root, {"clairs": pkg, "clairs.model": mod}
+
+
+def _save_pickled_module_checkpoints(tmp_path, n_heads):
+    aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads), 100 + n_heads)
+    neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 200 + n_heads)
+    a, n = str(tmp_path / "pileup_affirmative.pkl"), str(tmp_path / "pileup_negational.pkl")
+    saved = {k: sys.modules.get(k) for k in ("clairs", "clairs.model")}
+    try:
+        for path, key, sd, names in ((a, 'model_acgt', aff_sd, ["CvT" if n_heads == 4 else "CvT_Indel", "Transformer"]),
+                                     (n, 'model_nacgt', neg_sd, ["BiGRU_NACGT" if n_heads == 4 else "BiGRU_NACGT_Indel", "Transformer"])):
+            model, mods = _module_tree(sd, names)
+            sys.modules.update(mods)
+            torch.save({key: model}, path)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return a, n
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag,n_heads", [("snv", 4), ("indel", 6)])
-def test_predict_cli_against_reference_predict_file(golden_dir, tmp_path, tag, n_heads):
+@pytest.mark.parametrize("tag,n_heads,pickled_modules", [("snv", 4, False), ("indel", 6, False), ("snv", 4, True), ("indel", 6, True)])
+def test_predict_cli_against_reference_predict_file(golden_dir, tmp_path, tag, n_heads, pickled_modules):
+    """pickled_modules: the checkpoints are whole pickled ``clairs.model`` modules (the reference's real format) and
+    ``clairs.model`` is NOT importable when the sub-command loads them (tests/test_oracle_vs_reference.py checks the same
+    loader on checkpoints written by the reference itself)."""
     from clairs_to_b200 import predict as pr
     pdir = os.path.join(golden_dir, "pipeline")
-    ck_a, ck_n = _save_checkpoints(tmp_path, n_heads)
+    ck_a, ck_n = (_save_pickled_module_checkpoints if pickled_modules else _save_checkpoints)(tmp_path, n_heads)
+    if pickled_modules:
+        assert "clairs.model" not in sys.modules
     out = str(tmp_path / ("predict_" + tag))
     pr.main(["--tensor_fn_acgt", os.path.join(pdir, "tensor_can_aff_" + tag),
              "--tensor_fn_nacgt", os.path.join(pdir, "tensor_can_neg_" + tag), "--predict_fn", out,

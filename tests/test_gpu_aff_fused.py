@@ -69,3 +69,41 @@ def test_fused_layers_class_default_cvt(n_heads):
         assert np.abs(exact - want).max() < 5e-5
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("n_heads", [4, 6])
+def test_class_default_cvt_against_reference_golden(golden_dir, n_heads):
+    """The engine on the CvT class-default shape vs logits of the unmodified reference ``CvT()`` / ``CvT_Indel()``
+    (tests/golden/nn_golden_default.npz): tensor-core engine within 1e-3, exact fp32 engine within 5e-5."""
+    import os
+    g = np.load(os.path.join(golden_dir, "nn_golden_default.npz"))
+    aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads, CLASS_DEFAULT_CVT), 300 + n_heads, 0.7)
+    eng = _engine(aff_sd, n_heads, 16)                      # 24 candidates -> two internal chunks
+    try:
+        x = torch.from_numpy(g["x_%d" % n_heads])
+        want = g["aff_logits_%d" % n_heads]
+        got = eng.forward_aff(x).cpu().numpy()
+        assert eng.fused_status()[0] == 0
+        assert np.abs(got - want).max() < TOL
+        eng.set_tensor_cores(0)
+        assert np.abs(eng.forward_aff(x).cpu().numpy() - want).max() < 5e-5
+    finally:
+        eng.close()
+
+
+def test_unsupported_shape_fails_loudly_on_the_tensor_core_engine():
+    """No silent CUDA-core fallback: a CvT whose stage-2 width is 16 has no tcgen05 kernel and must raise on the
+    tensor-core engine (and run on the exact fp32 engine)."""
+    from clairs_to_b200 import _lib
+    cfg = dict(s1=(16, 1, 1), s2=(16, 1, 1), s3=(128, 4, 1))
+    aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(4, cfg), 11)
+    eng = _engine(aff_sd, 4, 64)
+    try:
+        x = torch.from_numpy(_count_like(8, 1))
+        with pytest.raises(_lib.CtoError):
+            eng.forward_aff(x)
+        eng.set_tensor_cores(0)
+        want = nn_oracle.aff_forward(x.numpy(), aff_sd).numpy()
+        assert np.abs(eng.forward_aff(x).cpu().numpy() - want).max() < 5e-5
+    finally:
+        eng.close()

@@ -130,6 +130,30 @@ def test_encoder_edge_cases(eng4):
     assert tok.alt_info[0] == alt
 
 
+def test_encoder_unaligned_plane_array_takes_the_unstaged_path(eng4):
+    """an offset view of the read array (not 16-byte aligned) must not fault or read out of bounds: the launch
+    detects it and reads with ordinary loads instead of 16-byte bulk copies.  Same tensor either way."""
+    import ctypes as C
+    from clairs_to_b200 import _lib
+    from clairs_to_b200.engine import packed_to_device
+    from clairs_to_b200.pileup_format import pack_stream
+    eng = eng4[0]
+    (aff, _), (neg, _) = synth.synth_pair(37, 19, 'ont', depth_lo=0, depth_hi=90)
+    ps = packed_to_device(pack_stream(neg, 30), eng.device)
+    want, want_d = eng.encode(ps)
+    shifted = torch.zeros(ps.planes.numel() + 8, dtype=torch.uint8, device=eng.device)
+    shifted[8:] = ps.planes                                       # 8-byte aligned, not 16
+    view = shifted[8:]
+    assert view.data_ptr() % 16 == 8
+    t = torch.empty_like(want)
+    d = torch.empty_like(want_d)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    _lib.check(eng.lib.cto_encode_pileup(p(view), p(ps.grp_off), p(ps.ref_code), p(ps.ind_off), p(ps.ind_entry), p(ps.win_pos),
+                                         want.shape[0], ps.n_groups, p(t), p(d), None), "encode")
+    torch.cuda.synchronize()
+    assert torch.equal(t, want) and torch.equal(d, want_d)
+
+
 @pytest.mark.parametrize("tensor_cores,tol", [(True, TOL), (False, 5e-5)])
 @pytest.mark.parametrize("n_heads", [4, 6])
 def test_forward_matches_reference_golden(golden_dir, n_heads, tensor_cores, tol):
@@ -150,9 +174,12 @@ def test_forward_matches_reference_golden(golden_dir, n_heads, tensor_cores, tol
 @pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("gain", [0.5, 1.0, 1.5])
 def test_forward_vs_oracle_weight_scales(gain, tensor_cores):
-    """Trained weights are unavailable offline: hold the tolerance across weight scales.  The 1e-3
-    absolute contract is stated for logits of O(1..10); beyond that (gain 1.5 drives |logit| past 30)
-    the bound is the same 1e-3 relative to max |logit| / 10."""
+    """Trained weights are unavailable offline: hold the contract across weight scales.
+    * logits: 1e-3 ABSOLUTE for gain <= 1 (|logit| up to ~7, the regime the contract is stated for);
+    * class probabilities (what predict writes and the posterior consumes): 1e-3 absolute at EVERY gain;
+    * gain 1.5 drives |logit| past 30 (post-SELU, far outside any trained model), where fp32 itself is no longer good to
+      1e-3: the fp32 torch oracle differs from its own fp64 evaluation by > 1e-4 there (asserted below, so this branch
+      cannot silently widen), and the logit bar becomes 1e-3 per 10 units of |logit| (a 1e-4 relative bar)."""
     eng, aff_sd, neg_sd = _engine(4, max_batch=128, gain=gain, tensor_cores=tensor_cores)
     (aff, _), (neg, _) = synth.synth_pair(300, 77, 'ont', depth_mean=70, depth_hi=200)
     from clairs_to_b200.engine import stream_to_device
@@ -170,7 +197,15 @@ def test_forward_vs_oracle_weight_scales(gain, tensor_cores):
     err_a, err_n = np.abs(la - oa).max(), np.abs(ln - on).max()
     print("gain %.1f tc=%s: max |logit err| AFF %.3g (max|logit| %.2f) NEG %.3g (max|logit| %.2f)"
           % (gain, tensor_cores, err_a, np.abs(oa).max(), err_n, np.abs(on).max()))
-    assert err_a < TOL * max(1.0, np.abs(oa).max() / 10) and err_n < TOL * max(1.0, np.abs(on).max() / 10)
+    sm = lambda z: nn_oracle.softmax_heads(z).numpy()
+    assert np.abs(sm(la) - sm(oa)).max() < TOL and np.abs(sm(ln) - sm(on)).max() < TOL
+    assert err_n < TOL
+    if gain <= 1.0:
+        assert err_a < TOL
+    else:
+        o64 = nn_oracle.aff_forward(fa.cpu().numpy(), aff_sd, dtype=torch.float64).numpy()
+        assert np.abs(oa).max() > 20 and np.abs(oa - o64).max() > 1e-4      # fp32 itself is off by > 1e-4 in this regime
+        assert err_a < TOL * np.abs(oa).max() / 10
     eng.close()
 
 
@@ -311,6 +346,7 @@ def test_baseline_config_shapes_end_to_end(platform, n_heads, single_stream):
     lk = np.concatenate([np.random.default_rng(1).uniform(0.05, 0.95, size=(10 * n_heads, 10)),
                          np.sort(np.random.default_rng(2).uniform(0.02, 0.98, size=(2 * n_heads, 10)), axis=1)])
     eng, aff_sd, neg_sd = _engine(n_heads, max_batch=128, likelihood=lk)
+    eng.set_qual_thresholds(8.0, 8.0, 12.0)                        # shared/param.py:35-40 (ont / hifi)
     (aff, _), (neg, _) = synth.synth_pair(200, 41, platform, depth_mean=70, depth_hi=180)
     out = eng.run_sites_host(aff, None if single_stream else neg, 30, want_tensors=True)
     ta, tn = out['tensor_aff'].numpy(), out['tensor_neg'].numpy()
@@ -327,13 +363,32 @@ def test_baseline_config_shapes_end_to_end(platform, n_heads, single_stream):
     assert np.abs(probs[:, :n_heads] - pa).max() < TOL and np.abs(probs[:, n_heads:] - pn).max() < TOL
     mats, ea, en = posterior_oracle.load_likelihood(lk, n_heads)
     post = out['post'].numpy()
-    agree = 0
+    qual, flt = out['qual'].numpy(), out['filter'].numpy()
+    far = 0
     for k in range(200):
         p8 = [float("{:0.8f}".format(v)) for v in probs[k, :, 1]]
         want = posterior_oracle.posterior(p8[:n_heads], p8[n_heads:], mats, ea, en)
         assert np.array_equal(post[k], want)                       # fp64 combine is bit-exact on identical inputs
-        ref = posterior_oracle.posterior([float("{:0.8f}".format(v)) for v in pa[k, :, 1]],
-                                         [float("{:0.8f}".format(v)) for v in pn[k, :, 1]], mats, ea, en)
-        agree += int(np.abs(ref - want).max() < 5e-3)
-    assert agree >= 198      # end to end vs the oracle: only bin-edge flips (probability within 1e-3 of an edge) may differ
+        # QUAL of the winning posterior (call_variants.py:81-88) and the three threshold bits, evaluated on the device
+        q = posterior_oracle.quality_score(want.max())
+        assert abs(qual[k] - q) <= 1.0001e-4
+        assert flt[k] == (1 if qual[k] >= 8.0 else 0) | (2 if qual[k] >= 8.0 else 0) | (4 if qual[k] >= 12.0 else 0)
+        r8 = [float("{:0.8f}".format(v)) for v in np.concatenate([pa[k, :, 1], pn[k, :, 1]])]
+        ref = posterior_oracle.posterior(r8[:n_heads], r8[n_heads:], mats, ea, en)
+        # End to end against the oracle's own probabilities: the posterior is within 1e-3 absolute UNLESS the difference
+        # is explained by (a) a probability within 1e-3 of a likelihood bin edge (the two sides may fall into different
+        # bins: the reference's formula is discontinuous there), or (b) an ill-conditioned head: both class probabilities
+        # so small that num + alt < 0.02, where 1e-3 on a probability moves the ratio by more than 1e-3.
+        for h in range(n_heads):
+            if abs(ref[h] - want[h]) <= TOL:
+                continue
+            p, q1 = r8[h], 1.0 - r8[n_heads + h]
+            near_edge = np.abs(ea[h] - p).min() <= TOL or np.abs(en[h] - q1).min() <= TOL
+            i = min(max(int(np.digitize(p, ea[h])) - 1, 0), 9)
+            j = min(max(int(np.digitize(q1, en[h])) - 1, 0), 9)
+            w = mats[h][i][j]
+            ill = p * q1 * w + (1 - p) * (1 - q1) * (1 - w) < 0.02
+            assert near_edge or ill, (k, h, ref[h], want[h], p, q1)
+            far += 1
+    assert far <= 8                                                 # and such heads are rare (<= 1 % of 200 x H)
     eng.close()

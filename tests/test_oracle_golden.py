@@ -36,6 +36,18 @@ def test_nn_oracle_matches_reference_forward(golden_dir, n_heads):
     assert np.abs(g["aff_logits_%d" % n_heads]).max() > 0.1      # the comparison is not vacuous
 
 
+@pytest.mark.parametrize("n_heads", [4, 6])
+def test_nn_oracle_matches_reference_class_default_cvt(golden_dir, n_heads):
+    """CvT() / CvT_Indel() with the CLASS-DEFAULT hyper-parameters (clairs/model.py:153-176: stage-1 width 32, stage 3 with
+    6 heads and depth 10), golden logits from the unmodified reference (make_golden.nn_golden_default)."""
+    g = np.load(os.path.join(golden_dir, "nn_golden_default.npz"))
+    cfg = dict(s1=(32, 1, 1), s2=(64, 3, 2), s3=(128, 6, 10))
+    sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads, cfg), 300 + n_heads, 0.7)
+    la = nn_oracle.aff_forward(g["x_%d" % n_heads], sd).numpy()
+    assert np.abs(la - g["aff_logits_%d" % n_heads]).max() < 2e-5
+    assert np.abs(g["aff_logits_%d" % n_heads]).max() > 0.1
+
+
 def _read_rows(path):
     with gzip.open(path, "rt") as f:
         return [r.rstrip("\n").split("\t") for r in f]

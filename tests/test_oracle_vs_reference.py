@@ -1,0 +1,137 @@
+"""CPU, build container only: the oracle against the LIVE reference (imported read-only from /root/reference), beyond
+the committed golden vectors -- randomised fuzz of the three pieces the oracle restates, and the reference's own
+checkpoint format (whole pickled modules, clairs/predict.py:513-517) through clairs_to_b200.weights.
+
+Skipped wherever /root/reference does not exist (the GPU box); the golden-vector tests cover that case."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from clairs_to_b200 import synth
+from oracle import nn_oracle, pileup_oracle, posterior_oracle
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "clairs")), reason="reference checkout not present")
+
+CLASS_DEFAULT_CVT = dict(s1=(32, 1, 1), s2=(64, 3, 2), s3=(128, 6, 10))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, REF)
+    try:
+        import clairs.model as model
+        import clairs.call_variants as cv
+        import src.create_tensor_pileup_calling as ct
+        yield dict(model=model, cv=cv, ct=ct)
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k.split('.')[0] in ("clairs", "shared", "src")]:
+            del sys.modules[k]
+
+
+def test_encoder_oracle_fuzz(ref):
+    """decode_pileup_bases (src/create_tensor_pileup_calling.py:95-233) on 600 random synthetic rows, all platforms."""
+    ct = ref["ct"]
+    n = 0
+    for seed, platform, literal in ((1, 'ont', 'ont'), (2, 'ont', 'ont_r10_dorado_sup_5khz'), (3, 'ilmn', 'ilmn_ssrs'), (4, 'hifi', 'hifi_revio')):
+        stream, aux = synth.synth_stream(5, 400 + seed, platform, depth_lo=0, depth_hi=120)
+        for i, text in enumerate(synth.render_mpileup(stream, aux, decorate_seed=seed)):
+            cols = text.rstrip("\n").split("\t")
+            r = "ACGT"[int(stream.ref_code[i])]
+            mq = [ord(c) - 33 for c in cols[6]]
+            bq = [ord(c) - 33 for c in cols[5]]
+            want_vec, want_alt = _decode(ct, cols[4], r, mq, bq, literal)
+            vec, alt = pileup_oracle.position_vector(cols[4], mq, bq, r, is_candidate=True, chunk_ref_seq=(r + "ACGTTGCA" * 8)[:60],
+                                                     platform=literal)
+            assert vec == [int(v) for v in want_vec] and alt == want_alt
+            n += 1
+    assert n >= 600
+
+
+def _decode(ct, bases, ref_base, mq, bq, platform):
+    from argparse import Namespace
+    vec, _, _, _, _, alt = ct.decode_pileup_bases(
+        args=Namespace(max_indel_length=60), pos=100, pileup_bases=bases, reference_base=ref_base,
+        minimum_snp_af_for_candidate=0.05, minimum_indel_af_for_candidate=0.05, has_pileup_candidates=True,
+        candidates_type_dict={100: 'snv'}, is_tumor=True, mapping_quality=mq, base_quality=bq, phasing_info=None,
+        chunk_ref_seq=(ref_base + "ACGTTGCA" * 8)[:60], platform=platform)
+    return vec, alt
+
+
+@pytest.mark.parametrize("n_heads,cfg", [(4, None), (6, None), (4, CLASS_DEFAULT_CVT), (6, CLASS_DEFAULT_CVT)])
+def test_nn_oracle_vs_reference_modules(ref, n_heads, cfg):
+    """CvT / CvT_Indel with the predict.py hyper-parameters and with the class defaults, BiGRU_NACGT / _Indel: the
+    reference modules on random count-like input vs the oracle on the same state_dict."""
+    m = ref["model"]
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    kw = {} if cfg else make_golden.CVT_KW
+    aff = (m.CvT if n_heads == 4 else m.CvT_Indel)(**kw).eval()
+    neg = (m.BiGRU_NACGT if n_heads == 4 else m.BiGRU_NACGT_Indel)(apply_softmax=False, num_classes=2, channel_size=34, model_type="nacgt").eval()
+    aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(n_heads, cfg), 500 + n_heads, 0.8)
+    neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(n_heads), 600 + n_heads, 0.8)
+    aff.load_state_dict(aff_sd, strict=False)
+    neg.load_state_dict(neg_sd, strict=False)
+    rng = np.random.default_rng(n_heads)
+    x = rng.integers(-50, 51, size=(16, 33, 34)).astype(np.float32)
+    x[rng.random(x.shape) < 0.5] = 0
+    with torch.no_grad():
+        la = torch.stack(aff(torch.from_numpy(x)), 1).numpy()
+        ln = torch.stack(neg(torch.from_numpy(x)), 1).numpy()
+    assert np.abs(nn_oracle.aff_forward(x, aff_sd).numpy() - la).max() < 3e-5
+    assert np.abs(nn_oracle.neg_forward(x, neg_sd).numpy() - ln).max() < 3e-5
+
+
+def test_quality_score_matches_reference(ref):
+    cv = ref["cv"]
+    rng = np.random.default_rng(0)
+    for p in list(rng.random(2000)) + [0.0, 1.0, 0.5, 1e-12, 1 - 1e-12]:
+        assert posterior_oracle.quality_score(p) == cv.quality_score_from(p)
+
+
+def test_reference_pickled_checkpoints_load_without_the_reference_package(ref, tmp_path):
+    """The reference checkpoint format: ``torch.save({'model_acgt': <CvT module>})`` (clairs/predict.py:513-517).  Loaded
+    in a fresh interpreter WITHOUT /root/reference on sys.path, so the tolerant unpickler branch of
+    clairs_to_b200.weights.state_dict_from_checkpoint is the one that runs; the result must equal module.state_dict()
+    bit for bit and export to an engine blob."""
+    m = ref["model"]
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    aff = m.CvT(**make_golden.CVT_KW).eval()
+    neg = m.BiGRU_NACGT(apply_softmax=False, num_classes=2, channel_size=34, model_type="nacgt").eval()
+    aff.load_state_dict(nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(4), 104), strict=False)
+    neg.load_state_dict(nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(4), 204), strict=False)
+    pa, pn = str(tmp_path / "pileup_affirmative.pkl"), str(tmp_path / "pileup_negational.pkl")
+    torch.save({'model_acgt': aff}, pa)
+    torch.save({'model_nacgt': neg}, pn)
+    torch.save({k: v for k, v in aff.state_dict().items()}, str(tmp_path / "aff_sd.pt"))
+    torch.save({k: v for k, v in neg.state_dict().items()}, str(tmp_path / "neg_sd.pt"))
+    code = """
+import sys, torch
+assert not any('reference' in p for p in sys.path), sys.path
+from clairs_to_b200.weights import state_dict_from_checkpoint, export_aff, export_neg
+try:
+    import clairs.model
+    raise SystemExit('clairs.model must not be importable in this process')
+except ImportError:
+    pass
+for path, key, sd_path, export in ((%r, 'model_acgt', %r, export_aff), (%r, 'model_nacgt', %r, export_neg)):
+    sd = state_dict_from_checkpoint(path, key)
+    want = torch.load(sd_path)
+    assert set(sd) == set(want), (set(sd) ^ set(want))
+    assert all(torch.equal(sd[k], want[k]) for k in want)
+    blob, cfg = export(sd)
+    print(key, len(blob), cfg.tolist())
+""" % (pa, str(tmp_path / "aff_sd.pt"), pn, str(tmp_path / "neg_sd.pt"))
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=str(tmp_path), capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "model_acgt" in out.stdout and "[4, 3, 16, 1, 1, 64, 3, 2, 128, 4, 3]" in out.stdout
+    assert "model_nacgt" in out.stdout and "[4, 34, 128, 192]" in out.stdout
