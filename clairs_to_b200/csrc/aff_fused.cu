@@ -46,7 +46,7 @@ constexpr int WTILE = 64 * 128;               // 8 KB:  one [64 n x 64 k] bf16 w
 constexpr int WSTAGE = 2 * WTILE;             // hi | mid
 constexpr int THREADS = 320;                  // 10 warps: 204 registers per thread
 constexpr int NB = 6;                         // feed-forward hidden accumulators (64 TMEM columns each)
-constexpr int LAG = 2;                        // FF1 MMAs run this many chunks ahead of FF2
+constexpr int LAG = 2;                        // FF1 MMAs run one pair of hidden chunks ahead of FF2
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 template <int C>
@@ -56,10 +56,15 @@ struct Cfg {
     static constexpr int NT = CP / 64;                        // 64-column output tiles of a C-wide product
     static constexpr int NH = (4 * C) / 64;                   // feed-forward hidden chunks
     static constexpr int NPC = C >= 128 ? 1 : 2;              // attention-output / hidden plane buffers
-    static constexpr int WST = C >= 128 ? 4 : 6;              // weight ring stages
+    static constexpr int WST = C >= 128 ? 3 : 5;              // weight ring stages
+    static constexpr int VEC = 16 * 1024;                     // the layer's small vectors (LN, taps, biases) in shared memory
     static constexpr int PLANE = 2 * KB * TILE_A;             // hi k-blocks | mid k-blocks
     static constexpr int PCBUF = 2 * TILE_A;                  // hi | mid, one k-block
-    static constexpr int SMEM = 2 * PLANE + NPC * PCBUF + WST * WSTAGE + 1024 /*align*/ + 1024 /*barriers*/;
+    static constexpr int NFF = NPC + PLANE / PCBUF;           // plane buffers of the feed-forward phase: pc[] + the (dead) dkv planes
+    static constexpr int SMEM = 2 * PLANE + NPC * PCBUF + WST * WSTAGE + VEC + 1024 /*align*/ + 1024 /*barriers*/;
+    // float offsets inside the layer's vector block (host prepack and kernel agree); + 16 C: bq [inner], bkv [2 inner]
+    static constexpr int O_LN1G = 0, O_LN1B = C, O_TQ = 2 * C, O_TK = 5 * C, O_LN2G = 8 * C, O_LN2B = 9 * C, O_CB1 = 10 * C,
+                         O_CB2 = 11 * C, O_B1 = 12 * C, O_BQ = 16 * C;
     static_assert(C == 32 || C == 64 || C == 128, "stage width");
     static_assert((4 * C) % 64 == 0 && NH >= LAG, "hidden chunking");
 };
@@ -67,7 +72,8 @@ struct Cfg {
 struct Params {
     float* x;                     // [n * W, C] fp32, in place
     const uint8_t* wstream;       // prepacked weight tiles, layer l at l * layer_bytes
-    const FusedLayerVecs* vecs;   // device array [depth]
+    const float* vblocks;         // per layer one block of Cfg::VEC bytes: the layer's small vectors (Cfg::O_*)
+    int vec_bytes;                // live bytes of a block (multiple of 16)
     const float* cb_final;        // [C] sum of every out-projection / FF2 bias of the stage (added when x leaves TMEM)
     long long layer_bytes;
     long long n;
@@ -144,6 +150,17 @@ __device__ __forceinline__ void f_tmem_st32(uint32_t taddr, const float* v) {
           "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
         : "memory");
 }
+__device__ __forceinline__ void f_tmem_ld8f(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    g_tmem_ld8(taddr, r);
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// eight consecutive floats of a (shared-memory) vector: every lane reads the same address, a broadcast
+__device__ __forceinline__ void f_lds8(const float* src, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
 __device__ __forceinline__ void f_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void f_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void f_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -194,27 +211,50 @@ __device__ __forceinline__ float f_gelu(float x) {
     const float erf = copysignf(erf_abs, x);
     return 0.5f * x * (1.0f + erf);
 }
-// D=f32, A=B=bf16, both K-major, M=128, N=64
-__device__ __forceinline__ uint32_t f_idesc64() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// eight elements at once, stage by stage, so that the eight MUFU / FMA chains interleave
+__device__ __forceinline__ void f_gelu8(float* v, const float* bias) {
+    float x[8], ax[8], t[8], pl[8], e[8];
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = v[i] + bias[i]; ax[i] = fabsf(x[i]) * 0.70710678118654752440f; }
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = f_rcp(fmaf(0.3275911f, ax[i], 1.0f));
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = f_ex2(-ax[i] * ax[i] * 1.4426950408889634f);
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float q = fmaf(t[i], 1.061405429f, -1.453152027f);
+        q = fmaf(t[i], q, 1.421413741f);
+        q = fmaf(t[i], q, -0.284496736f);
+        q = fmaf(t[i], q, 0.254829592f);
+        pl[i] = q * t[i];
+    }
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float erf = copysignf(fmaf(-pl[i], e[i], 1.0f), x[i]);
+        v[i] = 0.5f * x[i] * (1.0f + erf);
+    }
+}
+// D=f32, A=B=bf16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t f_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // barrier codes reported in dbg[0] on a timeout
-enum { B_WFULL = 1, B_WEMPTY, B_AB, B_QKVFULL, B_QKVFREE, B_PCREADY, B_PCFREE, B_XREADY, B_Y2, B_HIDFULL, B_HIDFREE, B_LAYER };
+enum { B_WFULL = 1, B_WEMPTY, B_AB, B_QKVFULL, B_QKVFREE, B_PCREADY, B_PCFREE, B_XREADY, B_Y2, B_HIDFULL, B_HIDFREE, B_LAYER, B_XLOADED, B_VEC };
 
 // channel LayerNorm (clairs/model.py:57-67): population std over the C channels of a row, eps added to the std.
 // The row lives in tensor memory (x_true = x_tmem + cb); statistics with the shifted-data formulas (shift = first channel).
 template <int C>
 __device__ __forceinline__ void f_row_stats(uint32_t trow, const float* __restrict__ cb, float& mean, float& inv) {
     float s1 = 0.0f, s2 = 0.0f, shift = 0.0f;
-    #pragma unroll
+    #pragma unroll 1
     for (int c0 = 0; c0 < C; c0 += 32) {
         float v[32];
         f_tmem_ld32(trow + (uint32_t)c0, v);
         f_wait_ld();
         #pragma unroll
         for (int c4 = 0; c4 < 32; c4 += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(cb + c0 + c4));
+            const float4 t = *reinterpret_cast<const float4*>(cb + c0 + c4);
             v[c4] += t.x; v[c4 + 1] += t.y; v[c4 + 2] += t.z; v[c4 + 3] += t.w;
         }
         if (c0 == 0) shift = v[0];
@@ -233,13 +273,21 @@ __device__ __forceinline__ void f_row_stats(uint32_t trow, const float* __restri
     const float var = fmaxf(s2 * (1.0f / (float)C) - m * m, 0.0f);
     inv = 1.0f / (sqrtf(var) + 1e-5f);
 }
+// 8 channels of the row: (x_tmem + cb - mean) * inv * g + b
+__device__ __forceinline__ void f_normalise8(float* v, const float* __restrict__ cb, const float* __restrict__ g,
+                                             const float* __restrict__ b, float mean, float inv) {
+    float t[8], gv[8], bv[8];
+    f_lds8(cb, t); f_lds8(g, gv); f_lds8(b, bv);
+    #pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf((v[e] + t[e] - mean) * inv, gv[e], bv[e]);
+}
 // 32 channels of the row: (x_tmem + cb - mean) * inv * g + b
 __device__ __forceinline__ void f_normalise32(float* v, const float* __restrict__ cb, const float* __restrict__ g,
                                               const float* __restrict__ b, float mean, float inv) {
     #pragma unroll
     for (int c4 = 0; c4 < 32; c4 += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(cb + c4));
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + c4)), bv = __ldg(reinterpret_cast<const float4*>(b + c4));
+        const float4 t = *reinterpret_cast<const float4*>(cb + c4);
+        const float4 gv = *reinterpret_cast<const float4*>(g + c4), bv = *reinterpret_cast<const float4*>(b + c4);
         v[c4] = fmaf((v[c4] + t.x - mean) * inv, gv.x, bv.x);
         v[c4 + 1] = fmaf((v[c4 + 1] + t.y - mean) * inv, gv.y, bv.y);
         v[c4 + 2] = fmaf((v[c4 + 2] + t.z - mean) * inv, gv.z, bv.z);
@@ -258,8 +306,10 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
     uint8_t* pa = base;                               // dq planes, later the LN2 output planes
     uint8_t* pb = pa + K::PLANE;                      // dkv planes
     uint8_t* pc = pb + K::PLANE;                      // attention output / hidden chunk planes [NPC]
-    uint8_t* wring = pc + NPC * K::PCBUF;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wring + WST * WSTAGE);
+    uint8_t* wring_hi = pc + NPC * K::PCBUF;          // [WST] hi tiles; consecutive stages are contiguous: two of them
+    uint8_t* wring_mid = wring_hi + WST * WTILE;      // [WST] mid tiles   form the B operand of one N = 128 MMA
+    float* sv = reinterpret_cast<float*>(wring_mid + WST * WTILE);    // the current layer's vector block
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wring_mid + WST * WTILE + K::VEC);
     uint64_t* w_full = bars;                          // [WST]
     uint64_t* w_empty = w_full + WST;                 // [WST]
     uint64_t* ab_ready = w_empty + WST;
@@ -272,7 +322,11 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
     uint64_t* hid_full = y2_ready + 1;                // [NB]
     uint64_t* hid_free = hid_full + NB;               // [NB]
     uint64_t* layer_done = hid_free + NB;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(layer_done + 1);
+    uint64_t* x_loaded = layer_done + 1;
+    uint64_t* vec_full = x_loaded + 1;
+    uint64_t* ff_ready = vec_full + 1;                // [3]
+    uint64_t* ff_free = ff_ready + 3;                 // [2 writer groups][3 buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ff_free + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* dbg = p.dbg;
@@ -282,19 +336,22 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
     #define FTOC(i) do { if (tim) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } } while (0)
     const int heads = p.heads, depth = p.depth;
     const int tiles_per_layer = heads * (3 * KB + NT) + NH * (KB + NT);
-
     if (threadIdx.x == 0) {
         for (int s = 0; s < WST; ++s) { g_mbar_init(&w_full[s], 1); g_mbar_init(&w_empty[s], 1); }
-        g_mbar_init(ab_ready, 4);
+        g_mbar_init(ab_ready, 8);
         for (int b = 0; b < 2; ++b) {
             g_mbar_init(&qkv_full[b], 1); g_mbar_init(&qkv_free[b], 4);
             g_mbar_init(&pc_ready[b], 4);
         }
         for (int b = 0; b < 4; ++b) g_mbar_init(&pc_free[b], 1);
         g_mbar_init(x_ready, 1);
-        g_mbar_init(y2_ready, 4);
+        g_mbar_init(y2_ready, 8);
         for (int b = 0; b < NB; ++b) { g_mbar_init(&hid_full[b], 1); g_mbar_init(&hid_free[b], 4); }
         g_mbar_init(layer_done, 1);
+        g_mbar_init(x_loaded, 4);
+        g_mbar_init(vec_full, 1);
+        for (int b = 0; b < 3; ++b) g_mbar_init(&ff_ready[b], 4);
+        for (int b = 0; b < 6; ++b) g_mbar_init(&ff_free[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -308,17 +365,28 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
 
     if (warp == 0) {
         // ---- weight producer: the layer's tiles in consumption order through the ring ----
-        uint32_t wit = 0;
+        uint32_t wit = 0, lit = 0;
         bool alive = true;
         for (int tile = blockIdx.x; tile < p.tiles && alive; tile += gridDim.x) {
-            for (int l = 0; l < depth && alive; ++l) {
+            for (int l = 0; l < depth && alive; ++l, ++lit) {
                 const uint8_t* src = p.wstream + (long long)l * p.layer_bytes;
                 for (int i = 0; i < tiles_per_layer; ++i, ++wit) {
+                    if (i == (tiles_per_layer < WST ? tiles_per_layer - 1 : WST - 1)) {
+                        // The layer's vector block, after the first ring-full of weight tiles (those only wait for slots the
+                        // previous layer frees): the previous layer's vectors are dead once its last MMA has retired.
+                        if (lit >= 1 && !f_wait(layer_done, (lit - 1) & 1, B_LAYER, dbg)) { alive = false; break; }
+                        if (g_elect_one()) {
+                            g_mbar_expect_tx(vec_full, (uint32_t)p.vec_bytes);
+                            f_bulk_load(sv, reinterpret_cast<const uint8_t*>(p.vblocks) + (long long)l * K::VEC, (uint32_t)p.vec_bytes, vec_full);
+                        }
+                        __syncwarp();
+                    }
                     const int s = wit % WST;
                     if (!f_wait(&w_empty[s], ((wit / WST) & 1) ^ 1, B_WEMPTY, dbg)) { alive = false; break; }
                     if (g_elect_one()) {
                         g_mbar_expect_tx(&w_full[s], WSTAGE);
-                        f_bulk_load(wring + s * WSTAGE, src + (long long)i * WSTAGE, WSTAGE, &w_full[s]);
+                        f_bulk_load(wring_hi + s * WTILE, src + (long long)i * WSTAGE, WTILE, &w_full[s]);
+                        f_bulk_load(wring_mid + s * WTILE, src + (long long)i * WSTAGE + WTILE, WTILE, &w_full[s]);
                     }
                     __syncwarp();
                 }
@@ -326,61 +394,85 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
         }
     } else if (warp == 1) {
         // ---- MMA issuer (warp-uniform control flow, one elected lane issues) ----
-        const uint32_t idesc = f_idesc64();
+        const uint32_t idesc64 = f_idesc(64), idesc128 = f_idesc(128);
         uint32_t wit = 0, lit = 0;
         bool alive = true;
-        // one [128 x 64*nkb] x [64 x 64*nkb]^T product: nkb weight tiles from the ring, A k-blocks at a_hi / a_mid
-        auto product = [&](uint32_t d_col, const uint8_t* a_hi, const uint8_t* a_mid, int nkb, bool acc_first) -> bool {
-            for (int kb = 0; kb < nkb; ++kb, ++wit) {
-                const int s = wit % WST;
+        // D[128 x 64 (x 2)] (+)= A[128 x 64 nkb] * W^T with nkb (x 2) weight tiles from the ring.  pair: two consecutive
+        // tiles (output columns d_col .. +64 and +64 .. +128) feed ONE N = 128 MMA per k-step when their ring stages are
+        // adjacent (the M = 128, N = 64 MMA re-reads the 4 KB A operand for 2 KB of B: shared-memory-bandwidth bound at
+        // 48 cycles; N = 128 moves 8 KB per 64 cycles), two N = 64 MMAs when the pair wraps around the ring.
+        auto product = [&](uint32_t d_col, const uint8_t* a_hi, const uint8_t* a_mid, int nkb, bool acc_first, bool pair) -> bool {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s0 = wit % WST, s1 = (wit + 1) % WST;
                 FTOC(0);
-                if (!f_wait(&w_full[s], (wit / WST) & 1, B_WFULL, dbg)) return false;
+                if (!f_wait(&w_full[s0], (wit / WST) & 1, B_WFULL, dbg)) return false;
+                if (pair && !f_wait(&w_full[s1], ((wit + 1) / WST) & 1, B_WFULL, dbg)) return false;
                 FTOC(1);
                 f_fence_after();
                 const uint64_t d_ahi = g_desc_k_sw128(g_smem_u32(a_hi + kb * TILE_A));
                 const uint64_t d_amid = g_desc_k_sw128(g_smem_u32(a_mid + kb * TILE_A));
-                const uint32_t w_addr = g_smem_u32(wring + s * WSTAGE);
-                const uint64_t d_whi = g_desc_k_sw128(w_addr), d_wmid = g_desc_k_sw128(w_addr + WTILE);
+                const uint64_t d_whi = g_desc_k_sw128(g_smem_u32(wring_hi + s0 * WTILE));
+                const uint64_t d_wmid = g_desc_k_sw128(g_smem_u32(wring_mid + s0 * WTILE));
+                const bool fused = pair && s1 == s0 + 1;
+                const uint32_t idesc = fused ? idesc128 : idesc64;
+                const uint32_t first = (acc_first || kb) ? 1u : 0u;
                 if (g_elect_one()) {
                     #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t o = (uint64_t)(k * 2);          // 16 bf16 = 32 bytes along the swizzle row
-                        f_mma(d_col, d_ahi + o, d_whi + o, idesc, (acc_first || kb || k) ? 1u : 0u);
+                        f_mma(d_col, d_ahi + o, d_whi + o, idesc, (first || k) ? 1u : 0u);
                         f_mma(d_col, d_amid + o, d_whi + o, idesc, 1u);
                         f_mma(d_col, d_ahi + o, d_wmid + o, idesc, 1u);
                     }
-                    g_commit(&w_empty[s]);
+                    if (pair && !fused) {                              // the pair wraps: second tile from stage 0
+                        const uint64_t e_whi = g_desc_k_sw128(g_smem_u32(wring_hi + s1 * WTILE));
+                        const uint64_t e_wmid = g_desc_k_sw128(g_smem_u32(wring_mid + s1 * WTILE));
+                        #pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t o = (uint64_t)(k * 2);
+                            f_mma(d_col + 64, d_ahi + o, e_whi + o, idesc64, (first || k) ? 1u : 0u);
+                            f_mma(d_col + 64, d_amid + o, e_whi + o, idesc64, 1u);
+                            f_mma(d_col + 64, d_ahi + o, e_wmid + o, idesc64, 1u);
+                        }
+                    }
+                    g_commit(&w_empty[s0]);
+                    if (pair) g_commit(&w_empty[s1]);
                 }
                 __syncwarp();
+                wit += pair ? 2 : 1;
             }
             return true;
         };
-        // x[:, nt*64 .. +64) += PC[p] * W_tile(nt)^T  for the plane buffer of use `pit`
-        auto onto_x = [&](uint32_t pit) -> bool {
-            const int pbuf = pit % NPC;
+        // x[:, 0 .. C) += planes * W^T (out-projection of a head / FF2 of a hidden chunk).  Plane buffers are handed over
+        // with one "ready" barrier per buffer (writer group -> this warp) and one "free" barrier per (writer group,
+        // buffer) (this warp -> the group that writes the buffer next: a barrier that two groups wait on in turns would
+        // let the group that skipped a phase alias an old parity).  All buffers are free at the start of every layer.
+        uint32_t pc_uses[2] = {0, 0}, ff_uses[3] = {0, 0, 0};
+        auto onto_x = [&](const uint8_t* a, uint64_t* ready, uint32_t& uses, uint64_t* free_next) -> bool {
             FTOC(0);
-            if (!f_wait(&pc_ready[pbuf], (pit / NPC) & 1, B_PCREADY, dbg)) return false;
+            if (!f_wait(ready, uses & 1, B_PCREADY, dbg)) return false;
+            ++uses;
             FTOC(2);
             f_fence_after();
-            const uint8_t* a = pc + pbuf * K::PCBUF;
-            for (int nt = 0; nt < NT; ++nt)
-                if (!product(tmem_base + (uint32_t)(nt * 64), a, a + TILE_A, 1, true)) return false;
-            // the buffer goes back to the group that writes use pit + NPC: group A (0) for attention heads and even
-            // hidden chunks, group B (1) for odd hidden chunks.  One barrier per (writer group, buffer): a barrier that
-            // two groups wait on in turns would let the group that skipped a phase alias an old parity
-            const uint32_t r = (pit + NPC) % (uint32_t)(heads + NH);
-            const int next_grp = (r >= (uint32_t)heads && ((r - heads) & 1u)) ? 1 : 0;
-            if (g_elect_one()) g_commit(&pc_free[next_grp * 2 + pbuf]);
+            if (!product(tmem_base, a, a + TILE_A, 1, true, NT == 2)) return false;
+            if (free_next != nullptr && g_elect_one()) g_commit(free_next);
             __syncwarp();
             return true;
         };
+        auto ff_buf = [&](int fb) -> const uint8_t* { return fb < NPC ? pc + fb * K::PCBUF : pb + (fb - NPC) * K::PCBUF; };
         for (int tile = blockIdx.x; tile < p.tiles && alive; tile += gridDim.x) {
             for (int l = 0; l < depth && alive; ++l, ++lit) {
-                const uint32_t pit0 = lit * (uint32_t)(heads + NH);
                 FTOC(0);
                 if (!f_wait(ab_ready, lit & 1, B_AB, dbg)) { alive = false; break; }
                 FTOC(3);
                 f_fence_after();
+                // out-projection of head h: buffer h % NPC, next written by head h + NPC (group = its accumulator buffer)
+                auto out_proj = [&](int h) -> bool {
+                    const int pbuf = h % NPC;
+                    const bool more = h + NPC < heads;
+                    const int next_grp = (int)((lit * (uint32_t)heads + h + NPC) & 1u);
+                    return onto_x(pc + pbuf * K::PCBUF, &pc_ready[pbuf], pc_uses[pbuf], more ? &pc_free[next_grp * 2 + pbuf] : nullptr);
+                };
                 for (int h = 0; h < heads && alive; ++h) {
                     const uint32_t hit = lit * (uint32_t)heads + h, b = hit & 1;
                     FTOC(0);
@@ -388,34 +480,41 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
                     FTOC(4);
                     f_fence_after();
                     const uint32_t acc = tmem_base + (uint32_t)(CP + b * 192);
-                    alive = product(acc, pa, pa + KB * TILE_A, KB, false) &&
-                            product(acc + 64, pb, pb + KB * TILE_A, KB, false) &&
-                            product(acc + 128, pb, pb + KB * TILE_A, KB, false);
+                    alive = product(acc, pa, pa + KB * TILE_A, KB, false, false) &&          // q_h
+                            product(acc + 64, pb, pb + KB * TILE_A, KB, false, true);         // k_h | v_h
                     if (!alive) break;
                     if (g_elect_one()) g_commit(&qkv_full[b]);
                     __syncwarp();
-                    if (h >= 1) alive = onto_x(pit0 + h - 1);
+                    if (h >= 1) alive = out_proj(h - 1);
                 }
                 if (!alive) break;
-                if (!onto_x(pit0 + heads - 1)) { alive = false; break; }
+                if (!out_proj(heads - 1)) { alive = false; break; }
                 if (g_elect_one()) g_commit(x_ready);
                 __syncwarp();
                 FTOC(0);
                 if (!f_wait(y2_ready, lit & 1, B_Y2, dbg)) { alive = false; break; }
                 FTOC(5);
                 f_fence_after();
-                for (int j = 0; j < NH && alive; ++j) {
+                // FF2 of hidden chunk j: buffer j % NFF, next written by chunk j + NFF (group = chunk parity)
+                auto ff2 = [&](int j) -> bool {
+                    const int fb = j % K::NFF;
+                    const bool more = j + K::NFF < NH;
+                    return onto_x(ff_buf(fb), &ff_ready[fb], ff_uses[fb], more ? &ff_free[((j + K::NFF) & 1) * 3 + fb] : nullptr);
+                };
+                for (int j = 0; j < NH && alive; j += 2) {                 // hidden chunks in pairs: one N = 128 product
                     const uint32_t cit = lit * (uint32_t)NH + j, hb = cit % NB;
                     FTOC(0);
-                    if (!f_wait(&hid_free[hb], ((cit / NB) & 1) ^ 1, B_HIDFREE, dbg)) { alive = false; break; }
+                    if (!f_wait(&hid_free[hb], ((cit / NB) & 1) ^ 1, B_HIDFREE, dbg) ||
+                        !f_wait(&hid_free[hb + 1], (((cit + 1) / NB) & 1) ^ 1, B_HIDFREE, dbg)) { alive = false; break; }
                     FTOC(6);
                     f_fence_after();
-                    if (!product(tmem_base + (uint32_t)(CP + hb * 64), pa, pa + KB * TILE_A, KB, false)) { alive = false; break; }
-                    if (g_elect_one()) g_commit(&hid_full[hb]);
+                    if (!product(tmem_base + (uint32_t)(CP + hb * 64), pa, pa + KB * TILE_A, KB, false, true)) { alive = false; break; }
+                    if (g_elect_one()) { g_commit(&hid_full[hb]); g_commit(&hid_full[hb + 1]); }
                     __syncwarp();
-                    if (j >= LAG) alive = onto_x(pit0 + heads + j - LAG);
+                    if (j >= 2) alive = ff2(j - 2) && ff2(j - 1);
                 }
-                for (int j = NH - LAG; j < NH && alive; ++j) alive = onto_x(pit0 + heads + j);
+                if (!alive) break;
+                alive = ff2(NH - 2) && ff2(NH - 1);
                 if (!alive) break;
                 if (g_elect_one()) g_commit(layer_done);
                 __syncwarp();
@@ -423,340 +522,265 @@ __global__ void __launch_bounds__(THREADS, 1) aff_layers_kernel(const Params p) 
         }
         FTOC(0);
         if (tim && lane == 0) { for (int i = 0; i < 7; ++i) p.timing[i] = tacc[i]; p.timing[7] = (long long)lit; }
-    } else if (warp < 6) {
-        // ---- compute group A: one thread per row (TMEM lane = row) ----
+    } else {
+        // ---- compute groups 0 (warps 2-5) and 1 (warps 6-9): one thread per row in each (TMEM lane = row).  The two
+        // groups split every phase: LayerNorm / convolution channel chunks, attention heads, hidden chunks.
+        // Every loop over columns is ROLLED and works on 8 columns read from tensor memory per iteration: the first,
+        // fully unrolled version of this code was 360 KB of SASS and spent a third of its issue slots waiting for
+        // instruction fetch (ncu: stall_no_inst 33 %).
+        const int grp = (warp - 2) >> 2;
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        constexpr int cpw = CPW;
         const int cl = lane / W, w = lane - cl * W;                    // candidate inside the warp, position
-        const bool lane_ok = lane < cpw * W;
+        const bool lane_ok = lane < CPW * W;
         const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
         const bool has_up = lane_ok && w > 0, has_dn = lane_ok && w < W - 1, kv_row = lane_ok && !(w & 1);
+        const int src0 = cl * W;                                       // lane of the candidate's first row: key j lives in lane src0 + 2j
         uint8_t* pa_mid = pa + KB * TILE_A;
         uint8_t* pb_mid = pb + KB * TILE_A;
-        uint32_t lit = 0;
-        uint32_t fcnt[2] = {0, 0};                                     // signalled waits so far on pc_free[group A][buffer]
+        const bool tg = tim && grp == 0;                               // group 0 reports its phase times
+        #define GTOC(i) do { if (tg) { const long long _t = clock64(); tacc[i] += _t - tprev; tprev = _t; } } while (0)
+        uint32_t lit = 0, tit = 0;
+        uint32_t pcf_cnt[2] = {0, 0}, fff_cnt[3] = {0, 0, 0};          // signalled waits so far on pc_free / ff_free [grp][buffer]
         bool alive = true;
-        for (int tile = blockIdx.x; tile < p.tiles && alive; tile += gridDim.x) {
-            const long long cand = ((long long)tile * 4 + quad) * cpw + cl;
+        for (int tile = blockIdx.x; tile < p.tiles && alive; tile += gridDim.x, ++tit) {
+            const long long cand = ((long long)tile * 4 + quad) * CPW + cl;
             const bool ok = lane_ok && cand < p.n;
-            float* xg = p.x + (((long long)tile * 4 + quad) * cpw * W + lane) * (long long)C;
-            // x tile: global -> registers -> TMEM columns [0, CP)
-            #pragma unroll
-            for (int c0 = 0; c0 < CP; c0 += 32) {
-                float v[32];
-                #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok && c0 < C) t = *reinterpret_cast<const float4*>(xg + c0 + 4 * q);
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            float* xg = p.x + (((long long)tile * 4 + quad) * CPW * W + lane) * (long long)C;
+            if (grp == 0) {
+                // x tile: global -> registers -> TMEM columns [0, CP)
+                #pragma unroll 1
+                for (int c0 = 0; c0 < CP; c0 += 32) {
+                    float v[32];
+                    #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok && c0 < C) t = *reinterpret_cast<const float4*>(xg + c0 + 4 * q);
+                        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                    }
+                    f_tmem_st32(trow + (uint32_t)c0, v);
                 }
-                f_tmem_st32(trow + (uint32_t)c0, v);
+                f_wait_st();
+                f_fence_before();
+                __syncwarp();
+                if (lane == 0) g_mbar_arrive(x_loaded);
+                GTOC(0);
+            } else {
+                if (!f_wait(x_loaded, tit & 1, B_XLOADED, dbg)) { alive = false; break; }
+                f_fence_after();
             }
-            f_wait_st();
-            FTOC(0);
             for (int l = 0; l < depth && alive; ++l, ++lit) {
-                const FusedLayerVecs lv = p.vecs[l];
-                const uint32_t pit0 = lit * (uint32_t)(heads + NH);
+                if (!f_wait(vec_full, lit & 1, B_VEC, dbg)) { alive = false; break; }
                 // ---------- LN1 + depth-wise convolutions -> dq (PA), dkv (PB) ----------
-                // The row is read from tensor memory twice, 32 columns at a time: statistics, then normalise + convolve +
-                // store (the whole 128-channel row in registers left no room for batched shuffles).
+                // The row is read from tensor memory twice: statistics (both groups, whole row), then normalise + convolve
+                // + store, 8 channels per iteration, the 8-channel chunks alternating between the groups.
                 {
                     float mean, inv;
-                    f_row_stats<C>(trow, lv.cb1, mean, inv);
-                    #pragma unroll
-                    for (int c0 = 0; c0 < CP; c0 += 32) {
-                        float v[32];
-                        if (c0 < C) {
-                            f_tmem_ld32(trow + (uint32_t)c0, v);
+                    f_row_stats<C>(trow, sv + K::O_CB1, mean, inv);
+                    #pragma unroll 1
+                    for (int c8 = grp * 8; c8 < CP; c8 += 16) {
+                        float dq[8], dk[8];
+                        if (c8 < C) {
+                            float v[8];
+                            f_tmem_ld8f(trow + (uint32_t)c8, v);
                             f_wait_ld();
-                            f_normalise32(v, lv.cb1 + c0, lv.ln1_g + c0, lv.ln1_b + c0, mean, inv);
-                        }
-                        #pragma unroll
-                        for (int c8 = 0; c8 < 32; c8 += 8) {
-                            float dq[8], dk[8];
-                            if (c0 < C) {
-                                // neighbour rows by warp shuffles, issued as a batch (a shuffle feeding its own FMA serialises
-                                // on the shuffle latency: measured 10 cycles per instruction)
-                                float up[8], dn[8];
-                                #pragma unroll
-                                for (int e = 0; e < 8; ++e) up[e] = __shfl_up_sync(0xffffffffu, v[c8 + e], 1);
-                                #pragma unroll
-                                for (int e = 0; e < 8; ++e) dn[e] = __shfl_down_sync(0xffffffffu, v[c8 + e], 1);
-                                #pragma unroll
-                                for (int h4 = 0; h4 < 8; h4 += 4) {
-                                    const int c = c0 + c8 + h4;
-                                    const float4 a0 = __ldg(reinterpret_cast<const float4*>(lv.tq + c));
-                                    const float4 a1 = __ldg(reinterpret_cast<const float4*>(lv.tq + C + c));
-                                    const float4 a2 = __ldg(reinterpret_cast<const float4*>(lv.tq + 2 * C + c));
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(lv.tk + c));
-                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(lv.tk + C + c));
-                                    const float4 b2 = __ldg(reinterpret_cast<const float4*>(lv.tk + 2 * C + c));
-                                    const float t0[4] = {a0.x, a0.y, a0.z, a0.w}, t1[4] = {a1.x, a1.y, a1.z, a1.w}, t2[4] = {a2.x, a2.y, a2.z, a2.w};
-                                    const float k0[4] = {b0.x, b0.y, b0.z, b0.w}, k1[4] = {b1.x, b1.y, b1.z, b1.w}, k2[4] = {b2.x, b2.y, b2.z, b2.w};
-                                    #pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const float y = v[c8 + h4 + e];
-                                        const float u = has_up ? up[h4 + e] : 0.0f, dd = has_dn ? dn[h4 + e] : 0.0f;
-                                        // taps in position order, pad 1 (zero rows outside the candidate); BN scale folded on the host
-                                        const float qv = fmaf(dd, t2[e], fmaf(y, t1[e], u * t0[e]));
-                                        const float kvv = fmaf(dd, k2[e], fmaf(y, k1[e], u * k0[e]));
-                                        dq[h4 + e] = lane_ok ? qv : 0.0f;
-                                        dk[h4 + e] = kv_row ? kvv : 0.0f;   // stride-2 conv = stride-1 conv at even positions
-                                    }
-                                }
-                            } else {
-                                #pragma unroll
-                                for (int e = 0; e < 8; ++e) { dq[e] = 0.0f; dk[e] = 0.0f; }
+                            f_normalise8(v, sv + K::O_CB1 + c8, sv + K::O_LN1G + c8, sv + K::O_LN1B + c8, mean, inv);
+                            // neighbour rows by warp shuffles, issued as a batch (a shuffle feeding its own FMA serialises
+                            // on the shuffle latency: measured 10 cycles per instruction)
+                            float up[8], dn[8];
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) up[e] = __shfl_up_sync(0xffffffffu, v[e], 1);
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) dn[e] = __shfl_down_sync(0xffffffffu, v[e], 1);
+                            float t0[8], t1[8], t2[8], k0[8], k1[8], k2[8];
+                            f_lds8(sv + K::O_TQ + c8, t0); f_lds8(sv + K::O_TQ + C + c8, t1); f_lds8(sv + K::O_TQ + 2 * C + c8, t2);
+                            f_lds8(sv + K::O_TK + c8, k0); f_lds8(sv + K::O_TK + C + c8, k1); f_lds8(sv + K::O_TK + 2 * C + c8, k2);
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float u = has_up ? up[e] : 0.0f, dd = has_dn ? dn[e] : 0.0f;
+                                // taps in position order, pad 1 (zero rows outside the candidate); BN scale folded on the host
+                                const float qv = fmaf(dd, t2[e], fmaf(v[e], t1[e], u * t0[e]));
+                                const float kvv = fmaf(dd, k2[e], fmaf(v[e], k1[e], u * k0[e]));
+                                dq[e] = lane_ok ? qv : 0.0f;
+                                dk[e] = kv_row ? kvv : 0.0f;           // stride-2 conv = stride-1 conv at even positions
                             }
-                            const int cc = c0 + c8, kb = cc >> 6, ch = (cc & 63) >> 3;
-                            f_store8(pa + kb * TILE_A, pa_mid + kb * TILE_A, row, ch, dq);
-                            f_store8(pb + kb * TILE_A, pb_mid + kb * TILE_A, row, ch, dk);
+                        } else {
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) { dq[e] = 0.0f; dk[e] = 0.0f; }
                         }
+                        const int kb = c8 >> 6, ch = (c8 & 63) >> 3;
+                        f_store8(pa + kb * TILE_A, pa_mid + kb * TILE_A, row, ch, dq);
+                        f_store8(pb + kb * TILE_A, pb_mid + kb * TILE_A, row, ch, dk);
                     }
                 }
                 f_fence_async();
                 f_fence_before();
                 __syncwarp();
                 if (lane == 0) g_mbar_arrive(ab_ready);
-                FTOC(1);
-                // ---------- attention, head by head ----------
+                GTOC(1);
+                // ---------- attention: the heads whose accumulator buffer belongs to this group ----------
                 for (int h = 0; h < heads && alive; ++h) {
                     const uint32_t hit = lit * (uint32_t)heads + h, b = hit & 1;
+                    if ((int)b != grp) continue;
                     if (!f_wait(&qkv_full[b], (hit >> 1) & 1, B_QKVFULL, dbg)) { alive = false; break; }
-                    FTOC(2);
+                    GTOC(2);
                     f_fence_after();
                     const uint32_t acc = trow + (uint32_t)(CP + b * 192);
-                    float q[64], kv[64];
-                    f_tmem_ld32(acc, q);
-                    f_tmem_ld32(acc + 32, q + 32);
-                    f_tmem_ld32(acc + 64, kv);
-                    f_tmem_ld32(acc + 96, kv + 32);
-                    f_wait_ld();
-                    const float* bq = lv.bq + h * 64;
-                    const float* bk = lv.bkv + h * 64;
-                    const float* bv = lv.bkv + heads * 64 + h * 64;
+                    const float* bq = sv + K::O_BQ + h * 64;
+                    const float* bk = sv + K::O_BQ + heads * 64 + h * 64;
+                    const float* bv = sv + K::O_BQ + 2 * heads * 64 + h * 64;
+                    // scores against the keys of the own candidate (the 64^-0.5 scale is folded into q on the host)
+                    float s[WKV];
                     #pragma unroll
-                    for (int d4 = 0; d4 < 64; d4 += 4) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(bq + d4)), c = __ldg(reinterpret_cast<const float4*>(bk + d4));
-                        q[d4] += a.x; q[d4 + 1] += a.y; q[d4 + 2] += a.z; q[d4 + 3] += a.w;
-                        kv[d4] += c.x; kv[d4 + 1] += c.y; kv[d4 + 2] += c.z; kv[d4 + 3] += c.w;
-                    }
-                    // scores against the keys of the own candidate: key j lives in the lane of row (cl, 2j)
-                    float s[9];
-                    const int src0 = cl * W;
-                    #pragma unroll
-                    for (int j = 0; j < 9; ++j) s[j] = 0.0f;
-                    #pragma unroll
+                    for (int j = 0; j < WKV; ++j) s[j] = 0.0f;
+                    #pragma unroll 1
                     for (int d0 = 0; d0 < 64; d0 += 8) {
+                        float q[8], k[8], b0[8], b1[8];
+                        f_tmem_ld8f(acc + (uint32_t)d0, q);
+                        f_tmem_ld8f(acc + (uint32_t)(64 + d0), k);
+                        f_lds8(bq + d0, b0);
+                        f_lds8(bk + d0, b1);
+                        f_wait_ld();
                         #pragma unroll
-                        for (int j = 0; j < 9; ++j) {
-                            if (j < WKV) {
-                                const int src = src0 + 2 * j;
-                                float t[8];
-                                #pragma unroll
-                                for (int e = 0; e < 8; ++e) t[e] = __shfl_sync(0xffffffffu, kv[d0 + e], src);   // batch of shuffles first
-                                #pragma unroll
-                                for (int e = 0; e < 8; ++e) s[j] = fmaf(q[d0 + e], t[e], s[j]);
-                            }
+                        for (int e = 0; e < 8; ++e) { q[e] += b0[e]; k[e] += b1[e]; }
+                        #pragma unroll
+                        for (int j = 0; j < WKV; ++j) {
+                            float t[8];
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) t[e] = __shfl_sync(0xffffffffu, k[e], src0 + 2 * j);   // batch of shuffles first
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) s[j] = fmaf(q[e], t[e], s[j]);
                         }
                     }
                     float mx = s[0];
                     #pragma unroll
-                    for (int j = 1; j < 9; ++j) if (j < WKV) mx = fmaxf(mx, s[j]);
+                    for (int j = 1; j < WKV; ++j) mx = fmaxf(mx, s[j]);
                     float sum = 0.0f;
                     #pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        s[j] = j < WKV ? expf(s[j] - mx) : 0.0f;
+                    for (int j = 0; j < WKV; ++j) {
+                        s[j] = expf(s[j] - mx);
                         sum += s[j];
                     }
                     const float inv = 1.0f / sum;
-                    // values: reuse the key registers
-                    f_tmem_ld32(acc + 128, kv);
-                    f_tmem_ld32(acc + 160, kv + 32);
-                    f_wait_ld();
-                    f_fence_before();
                     #pragma unroll
-                    for (int d4 = 0; d4 < 64; d4 += 4) {
-                        const float4 c = __ldg(reinterpret_cast<const float4*>(bv + d4));
-                        kv[d4] += c.x; kv[d4 + 1] += c.y; kv[d4 + 2] += c.z; kv[d4 + 3] += c.w;
+                    for (int j = 0; j < WKV; ++j) s[j] *= inv;
+                    GTOC(3);
+                    // the plane buffer of this head: free once the out-projection of head h - NPC has retired
+                    const int pbuf = h % NPC;
+                    if (h >= NPC) {
+                        if (!f_wait(&pc_free[grp * 2 + pbuf], pcf_cnt[pbuf] & 1, B_PCFREE, dbg)) { alive = false; break; }
+                        ++pcf_cnt[pbuf];
                     }
-                    #pragma unroll
-                    for (int j = 0; j < 9; ++j) s[j] *= inv;
-                    #pragma unroll
-                    for (int d0 = 0; d0 < 64; d0 += 8) {
-                        float o[8];
-                        #pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = 0.0f;
-                        #pragma unroll
-                        for (int j = 0; j < 9; ++j) {
-                            if (j < WKV) {
-                                const int src = src0 + 2 * j;
-                                float t[8];
-                                #pragma unroll
-                                for (int e = 0; e < 8; ++e) t[e] = __shfl_sync(0xffffffffu, kv[d0 + e], src);
-                                #pragma unroll
-                                for (int e = 0; e < 8; ++e) o[e] = fmaf(s[j], t[e], o[e]);
-                            }
-                        }
-                        #pragma unroll
-                        for (int e = 0; e < 8; ++e) q[d0 + e] = o[e];
-                    }
-                    __syncwarp();
-                    if (lane == 0) g_mbar_arrive(&qkv_free[b]);                // every TMEM read of this buffer has completed
-                    const uint32_t pit = pit0 + h;
-                    const int pbuf = pit % NPC;
-                    FTOC(3);
-                    if (pit >= (uint32_t)NPC) {                                // the MMAs that read the buffer's previous use have retired
-                        if (!f_wait(&pc_free[pbuf], fcnt[pbuf] & 1, B_PCFREE, dbg)) { alive = false; break; }
-                        ++fcnt[pbuf];
-                    }
-                    FTOC(4);
+                    GTOC(4);
                     uint8_t* pch = pc + pbuf * K::PCBUF;
-                    #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) f_store8(pch, pch + TILE_A, row, ch, q + 8 * ch);
+                    #pragma unroll 1
+                    for (int d0 = 0; d0 < 64; d0 += 8) {
+                        float v[8], b2[8], o[8];
+                        f_tmem_ld8f(acc + (uint32_t)(128 + d0), v);
+                        f_lds8(bv + d0, b2);
+                        f_wait_ld();
+                        #pragma unroll
+                        for (int e = 0; e < 8; ++e) { v[e] += b2[e]; o[e] = 0.0f; }
+                        #pragma unroll
+                        for (int j = 0; j < WKV; ++j) {
+                            float t[8];
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) t[e] = __shfl_sync(0xffffffffu, v[e], src0 + 2 * j);
+                            #pragma unroll
+                            for (int e = 0; e < 8; ++e) o[e] = fmaf(s[j], t[e], o[e]);
+                        }
+                        f_store8(pch, pch + TILE_A, row, d0 >> 3, o);
+                    }
                     f_fence_async();
+                    f_fence_before();
                     __syncwarp();
-                    if (lane == 0) g_mbar_arrive(&pc_ready[pbuf]);
+                    if (lane == 0) { g_mbar_arrive(&qkv_free[b]); g_mbar_arrive(&pc_ready[pbuf]); }   // TMEM reads done, planes written
+                    GTOC(3);
                 }
                 if (!alive) break;
                 // ---------- LN2 -> PA ----------
-                FTOC(3);
                 if (!f_wait(x_ready, lit & 1, B_XREADY, dbg)) { alive = false; break; }
-                FTOC(5);
+                GTOC(5);
                 f_fence_after();
                 {
                     float mean, inv;
-                    f_row_stats<C>(trow, lv.cb2, mean, inv);
-                    #pragma unroll
-                    for (int c0 = 0; c0 < CP; c0 += 32) {
-                        float v[32];
-                        if (c0 < C) {
-                            f_tmem_ld32(trow + (uint32_t)c0, v);
+                    f_row_stats<C>(trow, sv + K::O_CB2, mean, inv);
+                    #pragma unroll 1
+                    for (int c8 = grp * 8; c8 < CP; c8 += 16) {
+                        float v[8];
+                        if (c8 < C) {
+                            f_tmem_ld8f(trow + (uint32_t)c8, v);
                             f_wait_ld();
-                            f_normalise32(v, lv.cb2 + c0, lv.ln2_g + c0, lv.ln2_b + c0, mean, inv);
+                            f_normalise8(v, sv + K::O_CB2 + c8, sv + K::O_LN2G + c8, sv + K::O_LN2B + c8, mean, inv);
                         }
                         #pragma unroll
-                        for (int c8 = 0; c8 < 32; c8 += 8) {
-                            float z[8];
-                            #pragma unroll
-                            for (int e = 0; e < 8; ++e) z[e] = (c0 < C && lane_ok) ? v[c8 + e] : 0.0f;
-                            const int cc = c0 + c8, kb = cc >> 6, ch = (cc & 63) >> 3;
-                            f_store8(pa + kb * TILE_A, pa_mid + kb * TILE_A, row, ch, z);
-                        }
+                        for (int e = 0; e < 8; ++e) v[e] = (c8 < C && lane_ok) ? v[e] : 0.0f;
+                        const int kb = c8 >> 6, ch = (c8 & 63) >> 3;
+                        f_store8(pa + kb * TILE_A, pa_mid + kb * TILE_A, row, ch, v);
                     }
                 }
                 f_fence_async();
                 f_fence_before();
                 __syncwarp();
                 if (lane == 0) g_mbar_arrive(y2_ready);
-                FTOC(6);
-                // ---------- feed-forward hidden chunks (even ones; group B takes the odd ones) ----------
-                for (int j = 0; j < NH && alive; j += 2) {
+                GTOC(6);
+                // ---------- feed-forward hidden chunks: even ones in group 0, odd ones in group 1 ----------
+                for (int j = grp; j < NH && alive; j += 2) {
                     const uint32_t cit = lit * (uint32_t)NH + j, hb = cit % NB;
+                    const int fb = j % K::NFF;
+                    if (j >= K::NFF) {                                  // FF2 of chunk j - NFF has retired
+                        if (!f_wait(&ff_free[grp * 3 + fb], fff_cnt[fb] & 1, B_PCFREE, dbg)) { alive = false; break; }
+                        ++fff_cnt[fb];
+                    }
+                    GTOC(4);
                     if (!f_wait(&hid_full[hb], (cit / NB) & 1, B_HIDFULL, dbg)) { alive = false; break; }
-                    FTOC(7);
+                    GTOC(7);
                     f_fence_after();
-                    float hdn[64];
-                    f_tmem_ld32(trow + (uint32_t)(CP + hb * 64), hdn);
-                    f_tmem_ld32(trow + (uint32_t)(CP + hb * 64 + 32), hdn + 32);
-                    f_wait_ld();
+                    uint8_t* fbuf = fb < NPC ? pc + fb * K::PCBUF : pb + (fb - NPC) * K::PCBUF;
+                    const float* b1 = sv + K::O_B1 + j * 64;
+                    #pragma unroll 1
+                    for (int d8 = 0; d8 < 64; d8 += 8) {
+                        float hdn[8], bb[8];
+                        f_tmem_ld8f(trow + (uint32_t)(CP + hb * 64 + d8), hdn);
+                        f_lds8(b1 + d8, bb);
+                        f_wait_ld();
+                        f_gelu8(hdn, bb);
+                        f_store8(fbuf, fbuf + TILE_A, row, d8 >> 3, hdn);
+                    }
+                    f_fence_async();
                     f_fence_before();
                     __syncwarp();
-                    if (lane == 0) g_mbar_arrive(&hid_free[hb]);
-                    const float* b1 = lv.b1 + j * 64;
-                    #pragma unroll
-                    for (int d4 = 0; d4 < 64; d4 += 4) {
-                        const float4 c = __ldg(reinterpret_cast<const float4*>(b1 + d4));
-                        hdn[d4] = f_gelu(hdn[d4] + c.x); hdn[d4 + 1] = f_gelu(hdn[d4 + 1] + c.y);
-                        hdn[d4 + 2] = f_gelu(hdn[d4 + 2] + c.z); hdn[d4 + 3] = f_gelu(hdn[d4 + 3] + c.w);
-                    }
-                    const uint32_t pit = pit0 + heads + j;
-                    const int pbuf = pit % NPC;
-                    FTOC(8);
-                    if (pit >= (uint32_t)NPC) {
-                        if (!f_wait(&pc_free[pbuf], fcnt[pbuf] & 1, B_PCFREE, dbg)) { alive = false; break; }
-                        ++fcnt[pbuf];
-                    }
-                    FTOC(4);
-                    uint8_t* pch = pc + pbuf * K::PCBUF;
-                    #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) f_store8(pch, pch + TILE_A, row, ch, hdn + 8 * ch);
-                    f_fence_async();
-                    __syncwarp();
-                    if (lane == 0) g_mbar_arrive(&pc_ready[pbuf]);
-                    FTOC(8);
+                    if (lane == 0) { g_mbar_arrive(&hid_free[hb]); g_mbar_arrive(&ff_ready[fb]); }
+                    GTOC(8);
                 }
                 if (!alive) break;
                 if (!f_wait(layer_done, lit & 1, B_LAYER, dbg)) { alive = false; break; }
-                FTOC(9);
+                GTOC(9);
                 f_fence_after();
             }
             if (!alive) break;
-            // x tile: TMEM + cumulative bias -> global
-            #pragma unroll
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                float v[32];
-                f_tmem_ld32(trow + (uint32_t)c0, v);
-                f_wait_ld();
-                if (ok) {
-                    #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.cb_final + c0 + 4 * q));
-                        *reinterpret_cast<float4*>(xg + c0 + 4 * q) =
-                            make_float4(v[4 * q] + t.x, v[4 * q + 1] + t.y, v[4 * q + 2] + t.z, v[4 * q + 3] + t.w);
-                    }
-                }
-            }
-            f_fence_before();
-            FTOC(10);
-        }
-        if (tim && warp == 4 && lane == 0) { for (int i = 0; i < 11; ++i) p.timing[8 + i] = tacc[i]; }
-    } else {
-        // ---- compute group B: the odd feed-forward chunks ----
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;
-        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-        uint32_t lit = 0;
-        uint32_t fcnt[2] = {0, 0};                                     // signalled waits so far on pc_free[group B][buffer]
-        bool alive = true;
-        for (int tile = blockIdx.x; tile < p.tiles && alive; tile += gridDim.x) {
-            for (int l = 0; l < depth && alive; ++l, ++lit) {
-                const float* b1l = p.vecs[l].b1;
-                const uint32_t pit0 = lit * (uint32_t)(heads + NH);
-                for (int j = 1; j < NH && alive; j += 2) {
-                    const uint32_t cit = lit * (uint32_t)NH + j, hb = cit % NB;
-                    if (!f_wait(&hid_full[hb], (cit / NB) & 1, B_HIDFULL, dbg)) { alive = false; break; }
-                    f_fence_after();
-                    float hdn[64];
-                    f_tmem_ld32(trow + (uint32_t)(CP + hb * 64), hdn);
-                    f_tmem_ld32(trow + (uint32_t)(CP + hb * 64 + 32), hdn + 32);
+            if (grp == 0) {
+                // x tile: TMEM + cumulative bias -> global
+                #pragma unroll 1
+                for (int c0 = 0; c0 < C; c0 += 32) {
+                    float v[32];
+                    f_tmem_ld32(trow + (uint32_t)c0, v);
                     f_wait_ld();
-                    f_fence_before();
-                    __syncwarp();
-                    if (lane == 0) g_mbar_arrive(&hid_free[hb]);
-                    const float* b1 = b1l + j * 64;
-                    #pragma unroll
-                    for (int d4 = 0; d4 < 64; d4 += 4) {
-                        const float4 c = __ldg(reinterpret_cast<const float4*>(b1 + d4));
-                        hdn[d4] = f_gelu(hdn[d4] + c.x); hdn[d4 + 1] = f_gelu(hdn[d4 + 1] + c.y);
-                        hdn[d4 + 2] = f_gelu(hdn[d4 + 2] + c.z); hdn[d4 + 3] = f_gelu(hdn[d4 + 3] + c.w);
+                    if (ok) {
+                        #pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.cb_final + c0 + 4 * q));
+                            *reinterpret_cast<float4*>(xg + c0 + 4 * q) =
+                                make_float4(v[4 * q] + t.x, v[4 * q + 1] + t.y, v[4 * q + 2] + t.z, v[4 * q + 3] + t.w);
+                        }
                     }
-                    const uint32_t pit = pit0 + heads + j;
-                    const int pbuf = pit % NPC;
-                    if (pit >= (uint32_t)NPC) {
-                        if (!f_wait(&pc_free[2 + pbuf], fcnt[pbuf] & 1, B_PCFREE, dbg)) { alive = false; break; }
-                        ++fcnt[pbuf];
-                    }
-                    uint8_t* pch = pc + pbuf * K::PCBUF;
-                    #pragma unroll
-                    for (int ch = 0; ch < 8; ++ch) f_store8(pch, pch + TILE_A, row, ch, hdn + 8 * ch);
-                    f_fence_async();
-                    __syncwarp();
-                    if (lane == 0) g_mbar_arrive(&pc_ready[pbuf]);
                 }
+                f_fence_before();
+                GTOC(10);
             }
         }
+        if (tg && warp == 2 && lane == 0) { for (int i = 0; i < 11; ++i) p.timing[8 + i] = tacc[i]; }
+        #undef GTOC
     }
     #undef FTOC
     f_fence_before();
@@ -817,10 +841,9 @@ int aff_fused_prepare(CvtStage& st, const float* host_blob, const float* dev_blo
     using namespace fz;
     const int c = st.c, cp = c < 64 ? 64 : c, kb = cp / 64, nt = cp / 64, nh = 4 * c / 64, inner = st.heads * DIM_HEAD;
     std::vector<uint8_t> stream;
-    std::vector<FusedLayerVecs> vecs(st.depth);
-    // cumulative biases: cb1[l] = every out-projection / FF2 bias of the layers before l, cb2[l] = cb1[l] + b_out[l]
-    std::vector<float> cbs((size_t)(2 * st.depth + 1) * c, 0.0f), run(c, 0.0f);
-    CTO_CHECK(cudaMalloc(&st.fused_cb, sizeof(float) * cbs.size()));
+    const int vfloats = 16 * c + 3 * inner;
+    CTO_REQUIRE(vfloats * 4 <= 16 * 1024, "aff_fused: %d heads at width %d do not fit the vector block", st.heads, c);
+    std::vector<float> vblocks((size_t)st.depth * 4096, 0.0f), run(c, 0.0f);
     auto host = [&](const float* dev_ptr) { return host_blob + (dev_ptr - dev_blob); };
     for (int d = 0; d < st.depth; ++d) {
         const CvtLayer& L = st.layers[d];
@@ -828,42 +851,52 @@ int aff_fused_prepare(CvtStage& st, const float* host_blob, const float* dev_blo
         const float *wq = host(L.q_pw), *wkv = host(L.kv_pw), *wo = host(L.out_w), *w1 = host(L.ff1_w), *w2 = host(L.ff2_w);
         auto out_tiles = [&](int h) { for (int t = 0; t < nt; ++t) emit_tile(stream, wo, c, inner, t * 64, h * 64); };
         auto ff2_tiles = [&](int j) { for (int t = 0; t < nt; ++t) emit_tile(stream, w2, c, 4 * c, t * 64, j * 64); };
+        // consumption order of the MMA warp; tiles that feed one N = 128 MMA (k_h | v_h, the two halves of a 128-wide
+        // output, hidden chunks j | j + 1) are adjacent
         for (int h = 0; h < st.heads; ++h) {
             for (int k = 0; k < kb; ++k) emit_tile(stream, wq, inner, c, h * 64, k * 64);
-            for (int k = 0; k < kb; ++k) emit_tile(stream, wkv, 2 * inner, c, h * 64, k * 64);
-            for (int k = 0; k < kb; ++k) emit_tile(stream, wkv, 2 * inner, c, inner + h * 64, k * 64);
+            for (int k = 0; k < kb; ++k) {
+                emit_tile(stream, wkv, 2 * inner, c, h * 64, k * 64);
+                emit_tile(stream, wkv, 2 * inner, c, inner + h * 64, k * 64);
+            }
             if (h >= 1) out_tiles(h - 1);
         }
         out_tiles(st.heads - 1);
-        for (int j = 0; j < nh; ++j) {
-            for (int k = 0; k < kb; ++k) emit_tile(stream, w1, 4 * c, c, j * 64, k * 64);
-            if (j >= LAG) ff2_tiles(j - LAG);
+        for (int j = 0; j < nh; j += 2) {
+            for (int k = 0; k < kb; ++k) {
+                emit_tile(stream, w1, 4 * c, c, j * 64, k * 64);
+                emit_tile(stream, w1, 4 * c, c, (j + 1) * 64, k * 64);
+            }
+            if (j >= 2) { ff2_tiles(j - 2); ff2_tiles(j - 1); }
         }
-        for (int j = nh - LAG; j < nh; ++j) ff2_tiles(j);
+        ff2_tiles(nh - 2);
+        ff2_tiles(nh - 1);
         const size_t bytes = stream.size() - before;
         if (d == 0) st.fused_layer_bytes = (long long)bytes;
         CTO_REQUIRE((long long)bytes == st.fused_layer_bytes &&
                         bytes == (size_t)(st.heads * (3 * kb + nt) + nh * (kb + nt)) * WSTAGE,
                     "aff_fused: weight stream of layer %d has %zu bytes", d, bytes);
-        FusedLayerVecs& v = vecs[d];
-        v.ln1_g = L.ln1_g; v.ln1_b = L.ln1_b; v.tq = L.q_dw; v.tk = L.kv_dw; v.bq = L.q_bias; v.bkv = L.kv_bias;
-        v.ln2_g = L.ln2_g; v.ln2_b = L.ln2_b; v.b1 = L.ff1_b;
-        v.cb1 = st.fused_cb + (size_t)(2 * d) * c;
-        v.cb2 = st.fused_cb + (size_t)(2 * d + 1) * c;
+        // the layer's vector block (fz::Cfg<C>::O_*); cb1 / cb2 = the out-projection and FF2 biases accumulated so far
+        float* vb = vblocks.data() + (size_t)d * 4096;
+        auto put = [&](int off, const float* dev_ptr, int n) { std::memcpy(vb + off, host(dev_ptr), sizeof(float) * n); };
+        put(0, L.ln1_g, c); put(c, L.ln1_b, c); put(2 * c, L.q_dw, 3 * c); put(5 * c, L.kv_dw, 3 * c);
+        put(8 * c, L.ln2_g, c); put(9 * c, L.ln2_b, c); put(12 * c, L.ff1_b, 4 * c);
+        put(16 * c, L.q_bias, inner); put(16 * c + inner, L.kv_bias, 2 * inner);
         const float *bo = host(L.out_b), *b2 = host(L.ff2_b);
         for (int i = 0; i < c; ++i) {
-            cbs[(size_t)(2 * d) * c + i] = run[i];
+            vb[10 * c + i] = run[i];
             run[i] += bo[i];
-            cbs[(size_t)(2 * d + 1) * c + i] = run[i];
+            vb[11 * c + i] = run[i];
             run[i] += b2[i];
         }
     }
-    for (int i = 0; i < c; ++i) cbs[(size_t)(2 * st.depth) * c + i] = run[i];
-    CTO_CHECK(cudaMemcpy(st.fused_cb, cbs.data(), sizeof(float) * cbs.size(), cudaMemcpyHostToDevice));
+    st.fused_vec_bytes = (vfloats * 4 + 15) / 16 * 16;
+    CTO_CHECK(cudaMalloc(&st.fused_vecs, sizeof(float) * vblocks.size()));
+    CTO_CHECK(cudaMemcpy(st.fused_vecs, vblocks.data(), sizeof(float) * vblocks.size(), cudaMemcpyHostToDevice));
+    CTO_CHECK(cudaMalloc(&st.fused_cb, sizeof(float) * c));
+    CTO_CHECK(cudaMemcpy(st.fused_cb, run.data(), sizeof(float) * c, cudaMemcpyHostToDevice));
     CTO_CHECK(cudaMalloc(&st.fused_stream, stream.size()));
     CTO_CHECK(cudaMemcpy(st.fused_stream, stream.data(), stream.size(), cudaMemcpyHostToDevice));
-    CTO_CHECK(cudaMalloc(&st.fused_vecs, sizeof(FusedLayerVecs) * st.depth));
-    CTO_CHECK(cudaMemcpy(st.fused_vecs, vecs.data(), sizeof(FusedLayerVecs) * st.depth, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -900,8 +933,9 @@ int launch_aff_layers(const CvtStage& st, float* x, int64_t n, int* dbg, cudaStr
     fz::Params p;
     p.x = x;
     p.wstream = st.fused_stream;
-    p.vecs = st.fused_vecs;
-    p.cb_final = st.fused_cb + (size_t)(2 * st.depth) * st.c;
+    p.vblocks = st.fused_vecs;
+    p.vec_bytes = st.fused_vec_bytes;
+    p.cb_final = st.fused_cb;
     p.layer_bytes = st.fused_layer_bytes;
     p.n = n;
     p.W = st.wout;

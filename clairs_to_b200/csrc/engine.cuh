@@ -16,21 +16,16 @@ struct CvtLayer {
     const float *ln2_g, *ln2_b, *ff1_w, *ff1_b, *ff2_w, *ff2_b;
 };
 
-// per-layer small vectors of the fused transformer kernel (aff_fused.cu): device pointers into the weight blob, plus the
-// cumulative out-projection / FF2 biases (x lives in tensor memory WITHOUT them: x_true = x_tmem + cb)
-struct FusedLayerVecs {
-    const float *ln1_g, *ln1_b, *tq, *tk, *bq, *bkv, *ln2_g, *ln2_b, *b1, *cb1, *cb2;
-};
-
 struct CvtStage {
     int c, cin, heads, depth, win, wout, wkv;
     const float *embed_w, *embed_b, *ln_g, *ln_b;
     CvtLayer layers[MAX_DEPTH];
     // fused transformer layers (aff_fused.cu): prepacked weight tile stream, vector table, cumulative biases
     uint8_t* fused_stream = nullptr;
-    FusedLayerVecs* fused_vecs = nullptr;
-    float* fused_cb = nullptr;
+    float* fused_vecs = nullptr;              // per layer a 16 KB block of small vectors (LN, taps, biases, cumulative biases)
+    float* fused_cb = nullptr;                // [C] sum of every out-projection / FF2 bias of the stage
     long long fused_layer_bytes = 0;
+    int fused_vec_bytes = 0;
 };
 
 struct HeadW {
