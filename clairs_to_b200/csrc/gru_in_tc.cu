@@ -96,10 +96,10 @@ gru1_fused_kernel(const __grid_constant__ CUtensorMap tma_whh_hi, const __grid_c
     uint64_t* wfull = reinterpret_cast<uint64_t*>(xs + F_XS);
     uint64_t* xfull = wfull + 1;                           // leader: both CTAs' x_t tiles have landed
     uint64_t* xempty = xfull + 1;                          // the step's input MMAs have retired (multicast commit)
-    uint64_t* acc_full = xempty + 1;                       // [2]: block pairs
-    uint64_t* h_ready = acc_full + 2;
+    uint64_t* acc_full = xempty + 1;                       // [4]: one per 32-unit block
+    uint64_t* h_ready = acc_full + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
-    float* s_bhn = reinterpret_cast<float*>(wfull + 8);    // 64 bytes after the barriers: 16-byte aligned
+    float* s_bhn = reinterpret_cast<float*>(wfull + 10);   // 80 bytes after the barriers: 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -111,8 +111,7 @@ gru1_fused_kernel(const __grid_constant__ CUtensorMap tma_whh_hi, const __grid_c
         g_mbar_init(wfull, 1);
         g_mbar_init(xfull, 1);
         g_mbar_init(xempty, 1);
-        g_mbar_init(&acc_full[0], 1);
-        g_mbar_init(&acc_full[1], 1);
+        for (int b = 0; b < F_NB; ++b) g_mbar_init(&acc_full[b], 1);
         g_mbar_init(h_ready, 2 * 8);                       // one arrive per gate-math warp of BOTH CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -197,7 +196,7 @@ gru1_fused_kernel(const __grid_constant__ CUtensorMap tma_whh_hi, const __grid_c
                             f_mma(accx, d_xmid + o, d_ihi + NROW + o, id32, 1u);
                             f_mma(accx, d_xhi + o, d_imid + NROW + o, id32, 1u);
                         }
-                        if (blk & 1) f_commit_2sm(&acc_full[blk >> 1]);
+                        f_commit_2sm(&acc_full[blk]);
                         if (blk == F_NB - 1) f_commit_2sm(xempty);   // x_t consumed in both CTAs
                     }
                     __syncwarp();
@@ -242,7 +241,7 @@ gru1_fused_kernel(const __grid_constant__ CUtensorMap tma_whh_hi, const __grid_c
                 const uint32_t lanes = (uint32_t)(quad * 32) << 16;
                 const uint32_t tcol = tmem_base + lanes + (uint32_t)(blk * F_HALF + (hb & 1) * 8);
                 const uint32_t xcol = tmem_base + lanes + (uint32_t)(F_XN_COL + blk * 16 + (hb & 1) * 8);
-                g_mbar_wait(&acc_full[blk >> 1], step & 1);
+                g_mbar_wait(&acc_full[blk], step & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t ar[8], az[8], an[8], ax[8];
                 g_tmem_ld8(tcol, ar);                      // W_hr h + W_ir x + b_r
@@ -255,15 +254,8 @@ gru1_fused_kernel(const __grid_constant__ CUtensorMap tma_whh_hi, const __grid_c
                 const float bnv[8] = {bn0.x, bn0.y, bn0.z, bn0.w, bn1.x, bn1.y, bn1.z, bn1.w};
                 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    // five MUFU ops per element: z = 1 / (1 + ez) and n = 1 - 2 / (en + 1) share one reciprocal (gru_tc3.cu)
-                    const float r = g_sigmoid(__uint_as_float(ar[c]));
-                    const float xz = fminf(fmaxf(__uint_as_float(az[c]), -30.0f), 30.0f);
-                    const float y = fminf(fmaxf(__uint_as_float(ax[c]) + r * (__uint_as_float(an[c]) + bnv[c]), -15.0f), 15.0f);
-                    const float dz = 1.0f + __expf(-xz), dn = __expf(2.0f * y) + 1.0f;
-                    const float inv = __fdividef(1.0f, dz * dn);
-                    const float z = dn * inv;
-                    const float n = 1.0f - 2.0f * dz * inv;
-                    hk[j * 8 + c] = (1.0f - z) * n + z * hk[j * 8 + c];
+                    hk[j * 8 + c] = g_gru_cell(__uint_as_float(ar[c]), __uint_as_float(az[c]), __uint_as_float(an[c]) + bnv[c],
+                                               __uint_as_float(ax[c]), hk[j * 8 + c]);
                 }
                 const float* hv = hk + j * 8;
                 uint4 hi, mid;

@@ -105,6 +105,33 @@ __device__ __forceinline__ void g_tmem_ld8(uint32_t taddr, uint32_t* r) {
 }
 // gate non-linearities through MUFU.EX2 / MUFU.RCP: absolute error ~1e-7, far inside the 1e-3 contract
 __device__ __forceinline__ float g_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// raw MUFU ops: __fdividef wraps its reciprocal in range checks (FSETP + predicated scaling, ~5 instructions per call);
+// the gate math keeps every operand of the reciprocal inside [1, 2^87], so the bare instruction is exact enough
+__device__ __forceinline__ float g_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float g_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// GRU cell update for one element (torch.nn.GRU, gate order r|z|n): pre-activations ar = W_hr h (+ W_ir x + b_r), az likewise,
+// an_h = W_hn h + b_hn, an_x = W_in x + b_in.  Five MUFU ops: z = 1 / (1 + ez) and n = 1 - 2 / (en + 1) share one
+// reciprocal; the clamps keep the product of the two denominators far from fp32 overflow and change sigmoid / tanh by
+// less than 1 ulp.  r needs no clamp: ex2 -> inf gives rcp -> 0, the correct limit.
+__device__ __forceinline__ float g_gru_cell(float ar, float az, float an_h, float an_x, float h) {
+    constexpr float L2E = 1.4426950408889634f;
+    const float r = g_rcp(1.0f + g_ex2(-L2E * ar));
+    const float xz = fminf(fmaxf(az, -30.0f), 30.0f);
+    const float y = fminf(fmaxf(fmaf(r, an_h, an_x), -15.0f), 15.0f);
+    const float dz = 1.0f + g_ex2(-L2E * xz), dn = 1.0f + g_ex2(2.0f * L2E * y);
+    const float inv = g_rcp(dz * dn);
+    const float z = dn * inv;
+    const float n = fmaf(-2.0f * dz, inv, 1.0f);
+    return fmaf(z, h - n, n);                       // (1 - z) * n + z * h
+}
 __device__ __forceinline__ float g_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 

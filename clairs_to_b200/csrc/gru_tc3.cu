@@ -128,9 +128,9 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     uint64_t* xfull = empty + Q_STAGES;
     uint64_t* xempty = xfull + Q_XSTAGES;
     uint64_t* acc_full = xempty + Q_XSTAGES;
-    uint64_t* h_ready = acc_full + 3;                     // leader only: h_t complete in both CTAs, accumulators drained
+    uint64_t* h_ready = acc_full + 6;                     // leader only: h_t complete in both CTAs, accumulators drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 2);
-    float* s_bhn = reinterpret_cast<float*>(tmem_slot + 6);   // barriers take 168 bytes: keep the float4 reads of s_bhn 16-byte aligned
+    float* s_bhn = reinterpret_cast<float*>(tmem_slot + 4);   // barriers take 192 + 16 bytes: keep the float4 reads of s_bhn 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -140,7 +140,7 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Q_STAGES; ++s) { g_mbar_init(&full[s], 1); g_mbar_init(&empty[s], 1); }
-        for (int p = 0; p < 3; ++p) g_mbar_init(&acc_full[p], 1);
+        for (int p = 0; p < 6; ++p) g_mbar_init(&acc_full[p], 1);     // one per 32-unit block (round 1: one per block pair)
         for (int s = 0; s < Q_XSTAGES; ++s) { g_mbar_init(&xfull[s], 1); g_mbar_init(&xempty[s], 4 * Q_GW); }
         g_mbar_init(h_ready, 2 * 4 * Q_GW);                  // one arrive per gate-math warp of BOTH CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -207,7 +207,7 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                                 q_mma_bf16_2sm(acc, d_hhi + o, d_wmid + o, idesc, 1u);
                             }
                             q_commit_2sm(&empty[s]);                   // stage free in both CTAs
-                            if ((blk & 1) && kb == KB - 1) q_commit_2sm(&acc_full[blk >> 1]);
+                            if (kb == KB - 1) q_commit_2sm(&acc_full[blk]);   // the gate math of this block can start
                         }
                         __syncwarp();
                         GTOC(2);
@@ -298,7 +298,7 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                     if (lane == 0) g_mbar_arrive(&xempty[xs]);
                     ++xq_it;
                 }
-                g_mbar_wait(&acc_full[blk >> 1], step & 1);
+                g_mbar_wait(&acc_full[blk], step & 1);
                 GTOC(j < 2 ? 0 : (j < ITERS - 2 ? 1 : 2));     // wait for the first / middle / last accumulators of the step
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t ar[8], az[8], an[8];
@@ -318,16 +318,9 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                         z = 0.5f + 0.25f * (xv[8 + c] + __uint_as_float(az[c]));
                         n = 0.5f * (xv[16 + c] + r * (__uint_as_float(an[c]) + bnv[c]));
                     } else {
-                        // five MUFU ops per element instead of six (the gate phase is bound by the 16/clk/SM MUFU pipe):
-                        // z = 1 / (1 + ez) and n = 1 - 2 / (en + 1) share one reciprocal.  The clamps keep the product of
-                        // the two denominators far from fp32 overflow and do not change sigmoid / tanh beyond 1 ulp.
-                        r = g_sigmoid(xv[c] + __uint_as_float(ar[c]));
-                        const float xz = fminf(fmaxf(xv[8 + c] + __uint_as_float(az[c]), -30.0f), 30.0f);
-                        const float y = fminf(fmaxf(xv[16 + c] + r * (__uint_as_float(an[c]) + bnv[c]), -15.0f), 15.0f);
-                        const float dz = 1.0f + __expf(-xz), dn = __expf(2.0f * y) + 1.0f;
-                        const float inv = __fdividef(1.0f, dz * dn);
-                        z = dn * inv;
-                        n = 1.0f - 2.0f * dz * inv;
+                        hk[j * 8 + c] = g_gru_cell(xv[c] + __uint_as_float(ar[c]), xv[8 + c] + __uint_as_float(az[c]),
+                                                   __uint_as_float(an[c]) + bnv[c], xv[16 + c], hk[j * 8 + c]);
+                        continue;
                     }
                     hk[j * 8 + c] = (1.0f - z) * n + z * hk[j * 8 + c];
                 }
