@@ -134,6 +134,90 @@ def synthetic_likelihood(n_heads, seed=1):
                            np.sort(rng.uniform(0.02, 0.98, size=(2 * n_heads, 10)), axis=1)])
 
 
+def cli_leg(n_chunk, n_heads, likelihood, host_threads):
+    """Chunk-file level: one synthetic chunk of `n_chunk` ONT-shape candidates as
+    the files run_clairs_to hands to the hot path (BAM stand-in = mpileup text behind the tests' samtools shim, reference
+    FASTA, candidate regions, checkpoints, likelihood matrix) -> per-chunk VCF, through (a) the three drop-in sub-commands
+    exchanging gzip files like the reference does, (b) clairs_to_b200.hot_path: the same in one process and in memory with
+    a persistent engine.  Returns candidates/s of one process for both, after checking that the two VCFs are identical."""
+    import shutil
+    import tempfile
+    import numpy as np
+    import torch
+    from clairs_to_b200 import call_variants as cv, create_tensor_pileup_calling as ct, hot_path, predict as pr, synth, synth_weights
+    from clairs_to_b200.engine import Engine
+    work = tempfile.mkdtemp(prefix="cto_cli_")
+    try:
+        (aff, aa), (neg, na) = synth.synth_pair_tiled(n_chunk, 77, 'ont', base=200000)
+        ctg, first = "chr20", 1001
+        for s_, a_, k in ((aff, aa, 20), (neg, na, 0)):
+            open(os.path.join(work, "tumor.bam.minbq%d.mpileup" % k), "wb").write(synth.render_mpileup_text(s_, a_, ctg, first))
+        open(os.path.join(work, "tumor.bam"), "w").close()
+        seq = "N" * (first - 1) + "".join("ACGT"[c] for c in neg.ref_code) + "N" * 64
+        with open(os.path.join(work, "ref.fa"), "w") as f:
+            f.write(">%s\n" % ctg)
+            for i in range(0, len(seq), 60):
+                f.write(seq[i:i + 60] + "\n")
+        open(os.path.join(work, "ref.fa.fai"), "w").write("%s\t%d\t%d\t60\t61\n" % (ctg, len(seq), len(ctg) + 2))
+        with open(os.path.join(work, "%s.0_0_1_snv" % ctg), "w") as f:
+            for i in range(n_chunk):
+                x = first + 33 * i + 16
+                f.write("%s\t%d\t%d\n" % (ctg, max(x - 17, 1), x + 17))
+        np.savetxt(os.path.join(work, "likelihood.txt"), likelihood)
+        aff_sd = synth_weights.synth_state_dict(synth_weights.aff_state_dict_shapes(n_heads), 100 + n_heads)
+        neg_sd = synth_weights.synth_state_dict(synth_weights.neg_state_dict_shapes(n_heads), 200 + n_heads)
+        ck_a, ck_n = os.path.join(work, "aff.pkl"), os.path.join(work, "neg.pkl")
+        torch.save({'model_acgt': aff_sd}, ck_a)
+        torch.save({'model_nacgt': neg_sd}, ck_n)
+        shim = os.path.join(ROOT, "tests", "fake_samtools.py")
+        common = ["--tumor_bam_fn", os.path.join(work, "tumor.bam"), "--ref_fn", os.path.join(work, "ref.fa"), "--ctg_name", ctg,
+                  "--samtools", shim, "--candidates_bed_regions", os.path.join(work, "%s.0_0_1_snv" % ctg),
+                  "--platform", "ont_r10_dorado_sup_5khz"]
+        f = {k: os.path.join(work, k) for k in ("aff", "neg", "predict", "files.vcf", "mem.vcf")}
+        quiet = open(os.devnull, "w")
+        stdout = sys.stdout
+
+        def files_path():
+            for name, k in (("aff", 20), ("neg", 0)):
+                ct.main(common + ["--min_bq", str(k), "--tensor_can_fn", f[name]])
+            pr.main(["--tensor_fn_acgt", f["aff"], "--tensor_fn_nacgt", f["neg"], "--predict_fn", f["predict"], "--chkpnt_fn_acgt", ck_a,
+                     "--chkpnt_fn_nacgt", ck_n, "--use_gpu", "True", "--platform", "ont_r10_dorado_sup_5khz", "--ctg_name", ctg,
+                     "--pileup", "--disable_indel_calling", "True"])
+            cv.main(["--predict_fn", f["predict"], "--call_fn", f["files.vcf"], "--ref_fn", os.path.join(work, "ref.fa"), "--platform",
+                     "ont_r10_dorado_sup_5khz", "--likelihood_matrix_data", os.path.join(work, "likelihood.txt"),
+                     "--disable_indel_calling", "True"])
+
+        hp_args = hot_path.build_parser().parse_args(common + ["--min_bq", "20", "--chkpnt_fn_acgt", ck_a, "--chkpnt_fn_nacgt", ck_n,
+                                                              "--likelihood_matrix_data", os.path.join(work, "likelihood.txt"),
+                                                              "--disable_indel_calling", "True", "--call_fn", f["mem.vcf"]])
+        eng = Engine.from_checkpoints(ck_a, ck_n, max_batch=10240)
+        eng.set_likelihood(os.path.join(work, "likelihood.txt"))
+        sys.stdout = quiet
+        try:
+            files_path()                                    # warm-up (lazy CUDA module load)
+            hot_path.run_chunk(hp_args, engine=eng, host_threads=host_threads)
+            t0 = time.perf_counter()
+            files_path()
+            t1 = time.perf_counter()
+            hot_path.run_chunk(hp_args, engine=eng, host_threads=host_threads)
+            t2 = time.perf_counter()
+        finally:
+            sys.stdout = stdout
+            eng.close()
+        same = open(f["files.vcf"]).read() == open(f["mem.vcf"]).read() if os.path.exists(f["files.vcf"]) else not os.path.exists(f["mem.vcf"])
+        rows = sum(1 for l in open(f["mem.vcf"]) if not l.startswith("#")) if os.path.exists(f["mem.vcf"]) else 0
+        return dict(candidates=n_chunk, vcf_rows=rows, identical_vcf=bool(same),
+                    sub_commands=dict(value=n_chunk / (t1 - t0), unit=UNIT, seconds=t1 - t0,
+                                      what="create_tensor x2 -> predict -> call_variants through gzip chunk files, one process, "
+                                           "engine loaded per predict call like the reference"),
+                    in_memory=dict(value=n_chunk / (t2 - t1), unit=UNIT, seconds=t2 - t1,
+                                   what="clairs_to_b200.hot_path.run_chunk: same inputs, same VCF, no intermediate files, persistent engine"),
+                    note="both include the python samtools shim filtering %d MB of mpileup text (twice) and the host tokenizer"
+                         % (sum(os.path.getsize(os.path.join(work, "tumor.bam.minbq%d.mpileup" % k)) for k in (0, 20)) // 1000000))
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def cpu_mix(cfg):
     total = float(sum(n for _, n in cfg["parts"]))
     return [(h, n / total) for h, n in cfg["parts"]]
@@ -187,6 +271,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-text", action="store_true", help="skip the mpileup-text end-to-end leg (config 1)")
+    ap.add_argument("--no-cli", action="store_true", help="skip the chunk-file level leg (config 1, one GPU)")
+    ap.add_argument("--cli-candidates", type=int, default=2000, help="candidates of the synthetic chunk of the chunk-file leg")
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: allow fewer warm-up steps "
                                                        "(numbers printed in this mode are NOT bench values)")
     args = ap.parse_args()
@@ -445,6 +531,10 @@ def main():
         r = cpu_baseline.run(per_proc=args.cpu_sample, platform=cfg["platform"], mix=cpu_mix(cfg), single_stream=cfg["single_stream"])
         cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"], encoder_share=r["encoder_share"])
 
+    cli = None
+    if rank == 0 and world == 1 and args.config == 1 and not args.no_cli:
+        cli = cli_leg(args.cli_candidates, 4, synthetic_likelihood(4), host_threads)
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="strong" if cfg["total"] else "weak",
@@ -454,7 +544,7 @@ def main():
                                 l2_policy="inputs (%.0f MB per step and GPU) larger than the 126 MB L2" % (sum(p["h2d"] for p in parts) / 1e6),
                                 parallelism="candidates sharded x%d, one gather of probabilities" % world,
                                 datagen_s=round(t_gen, 1)),
-                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clocks)
+                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, cli=cli, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
     for eng_k, _ in engines:
         eng_k.close()

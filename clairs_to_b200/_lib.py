@@ -61,6 +61,7 @@ SIGNATURES = {
     "cto_parse_tensor_file": (INT, [C.c_char_p, I64, I64, P, P, P, P]),
     "cto_format_tensor_can_rows": (I64, [C.c_char_p, I64, I64, P, C.c_char_p, P, C.c_char_p, P, P, P, I64]),
     "cto_format_predict_rows": (I64, [C.c_char_p, P, I64, P, P, P, INT, P, I64]),
+    "cto_parse_predict_file": (INT, [C.c_char_p, I64, INT, I64, P, P, P, P]),
 }
 
 

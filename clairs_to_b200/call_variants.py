@@ -23,6 +23,8 @@ from time import time
 
 import numpy as np
 
+from . import host
+
 logging.basicConfig(format='%(message)s', level=logging.INFO)
 
 ZSTD = 'gzip'                      # shared/param.py:7
@@ -200,6 +202,30 @@ def call_row(chrom, pos, ref, alt_info, fwd_text, rev_text, post, head, snv_mode
                      AF=af, AD=ad, AU=tot[0], CU=tot[1], GU=tot[2], TU=tot[3])
 
 
+def emit_calls(rows, post, call, snv_mode, show_ref, qual, writer):
+    """rows.field(k, 0..5) = chrom, pos, ref, alt_info, forward / reverse strand list-reprs of candidate k."""
+    for k in range(len(post)):
+        chrom, pos = rows.field(k, 0), rows.field(k, 1)
+        if call[k] >> 8:
+            # the reference indexes a 10x10 matrix with bin 10 here and dies with IndexError (SURVEY.md 9.12)
+            sys.exit("[ERROR] probability of exactly 1.0 at %s:%s falls outside the likelihood bins" % (chrom, pos))
+        call_row(chrom, pos, rows.field(k, 2), rows.field(k, 3), rows.field(k, 4), rows.field(k, 5), post[k],
+                 int(call[k] & 0xFF), snv_mode, show_ref, qual, writer)
+
+
+def finish_vcf(call_fn):
+    """clairs/call_variants.py:858-867: a VCF without records is removed."""
+    if os.path.exists(call_fn):
+        content = open(call_fn).readlines()
+        if not len(content):
+            os.remove(call_fn)
+        for row in content:
+            if row[0] != '#':
+                return
+        logging.info("[INFO] No vcf output in file {}, remove.".format(call_fn))
+        os.remove(call_fn)
+
+
 def call_variants_from_probability(args):
     import ctypes as C
     import torch
@@ -222,55 +248,33 @@ def call_variants_from_probability(args):
         if not os.path.exists(path):
             print("[ERROR] Prediction path not found!")
             return
-        proc = Popen(shlex.split("%s -fdc %s" % (ZSTD, path)), stdout=PIPE, bufsize=8388608, universal_newlines=True)
-        fo = proc.stdout
-    else:
-        proc, fo = None, sys.stdin
-    tables = np.ascontiguousarray(likelihood_tables(args.likelihood_matrix_data, n_heads))
-
-    rows, pa, pn = [], [], []
-    for line in fo:
-        cols = line.rstrip().split('\t')
-        rows.append(cols[:6])
-        probs = [[float(v) for v in f.split()] for f in cols[6:6 + 2 * n_heads]]
-        pa.append([p[1] for p in probs[:n_heads]])
-        pn.append([p[1] for p in probs[n_heads:]])
-    if proc is not None:
-        fo.close()
+        proc = Popen(shlex.split("%s -fdc %s" % (ZSTD, path)), stdout=PIPE, bufsize=8388608)
+        text = proc.stdout.read()
+        proc.stdout.close()
         proc.wait()
+    else:
+        text = sys.stdin.buffer.read()
+    tables = np.ascontiguousarray(likelihood_tables(args.likelihood_matrix_data, n_heads))
+    # the whole file by one native parse (clairs/call_variants.py:798-829 loops over rows and float()s every field)
+    pf = host.PredictFile(text, n_heads)
 
-    if rows:
+    if pf.n:
         lib = _lib.lib()
         dev = torch.device('cuda', torch.cuda.current_device())
-        d_pa = torch.tensor(pa, dtype=torch.float64, device=dev)
-        d_pn = torch.tensor(pn, dtype=torch.float64, device=dev)
-        d_post = torch.empty((len(rows), n_heads), dtype=torch.float64, device=dev)
-        d_call = torch.empty((len(rows),), dtype=torch.int32, device=dev)
+        d_pa = torch.from_numpy(pf.p_aff).to(dev)
+        d_pn = torch.from_numpy(pf.p_neg).to(dev)
+        d_post = torch.empty((pf.n, n_heads), dtype=torch.float64, device=dev)
+        d_call = torch.empty((pf.n,), dtype=torch.int32, device=dev)
         _lib.check(lib.cto_posterior_from_probs(C.c_void_p(tables.ctypes.data), n_heads, C.c_void_p(d_pa.data_ptr()),
-                                                C.c_void_p(d_pn.data_ptr()), len(rows), C.c_void_p(d_post.data_ptr()),
+                                                C.c_void_p(d_pn.data_ptr()), pf.n, C.c_void_p(d_post.data_ptr()),
                                                 C.c_void_p(d_call.data_ptr()),
                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                    "cto_posterior_from_probs")
-        post = d_post.cpu().numpy()
-        call = d_call.cpu().numpy()
-        for k, (chrom, pos, ref, alt_info, fwd_text, rev_text) in enumerate(rows):
-            if call[k] >> 8:
-                # the reference indexes a 10x10 matrix with bin 10 here and dies with IndexError
-                sys.exit("[ERROR] probability of exactly 1.0 at %s:%s falls outside the likelihood bins" % (chrom, pos))
-            call_row(chrom, pos, ref, alt_info, fwd_text, rev_text, post[k], int(call[k] & 0xFF), snv_mode,
-                     args.show_ref, args.qual, writer)
+        emit_calls(pf, d_post.cpu().numpy(), d_call.cpu().numpy(), snv_mode, args.show_ref, args.qual, writer)
 
     logging.info("[INFO] Total time elapsed: %.2f s" % (time() - start))
     writer.close()
-    if os.path.exists(args.call_fn):                                   # ibid. 858-867
-        content = open(args.call_fn).readlines()
-        if not len(content):
-            os.remove(args.call_fn)
-        for row in content:
-            if row[0] != '#':
-                return
-        logging.info("[INFO] No vcf output in file {}, remove.".format(args.call_fn))
-        os.remove(args.call_fn)
+    finish_vcf(args.call_fn)
 
 
 def build_parser():

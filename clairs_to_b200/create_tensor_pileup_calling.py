@@ -73,21 +73,37 @@ def reference_sequence_from(samtools, fasta, region):
     return "".join(lines[1:]).upper()
 
 
-def create_tensor(args):
+class EncodedChunk:
+    """The candidates of one chunk after the encoder, still in memory: ``pos`` int64 [n], ``ref33`` list of 33-mers,
+    ``tensor`` int16 [n,33,34] and ``depth`` int32 [n] on the device, ``alt_info`` / ``variant_type`` lists."""
+
+    def __init__(self, ctg, pos, ref33, tensor, depth, alt_info, variant_type):
+        self.ctg, self.pos, self.ref33, self.tensor, self.depth = ctg, pos, ref33, tensor, depth
+        self.alt_info, self.variant_type = alt_info, variant_type
+
+    def __len__(self):
+        return len(self.pos)
+
+
+def encode_chunk(args, min_bq=None, host_threads=0):
+    """samtools mpileup -> native tokenizer -> window table -> CUDA encoder for the candidates of one chunk
+    (src/create_tensor_pileup_calling.py:306-570 up to the row text).  Returns an EncodedChunk (possibly empty)."""
     import torch
     from .engine import PIPELINE_LOW_BQ_CUT, encode_pileup, stream_to_device
 
     if not args.candidates_bed_regions:
         sys.exit("[ERROR] the B200 create_tensor_pileup_calling needs --candidates_bed_regions "
                  "(the only mode run_clairs_to uses)")
-    if args.vcf_fn or args.truth_vcf_fn or args.phase_tumor or args.extend_bed or args.bed_fn:
+    if getattr(args, 'vcf_fn', None) or getattr(args, 'truth_vcf_fn', None) or getattr(args, 'phase_tumor', None) or \
+            getattr(args, 'extend_bed', None) or getattr(args, 'bed_fn', None):
         sys.exit("[ERROR] --vcf_fn/--truth_vcf_fn/--phase_tumor/--extend_bed/--bed_fn are not on the B200 path")
-    if args.flanking is not None and args.flanking != FLANK:
+    if getattr(args, 'flanking', None) is not None and args.flanking != FLANK:
         sys.exit("[ERROR] --flanking %d: the pileup models are built for 16 flanking bases" % args.flanking)
     if not torch.cuda.is_available():
         sys.exit("[ERROR] no CUDA device: the B200 encoder has no CPU fallback")
     ctg_name = args.ctg_name
-    max_indel_length = MAX_INDEL_LENGTH if args.max_indel_length is None else args.max_indel_length
+    max_indel_length = MAX_INDEL_LENGTH if getattr(args, 'max_indel_length', None) is None else args.max_indel_length
+    min_bq = args.min_bq if min_bq is None else min_bq
     fai = args.ref_fn + ".fai"
     if not os.path.exists(fai):
         sys.exit("[ERROR] file %s not found" % fai)
@@ -107,13 +123,13 @@ def create_tensor(args):
     # the exact command of ibid. 426-446 (no -f: bases are literal letters)
     cmd = "{} mpileup --reverse-del".format(args.samtools) + ' --output-MQ ' + \
           ' -r {}:{}-{}'.format(ctg_name, extend_start, extend_end) + ' --min-MQ 0' + \
-          ' --min-BQ {}'.format(args.min_bq) + ' -l {}'.format(args.candidates_bed_regions) + \
+          ' --min-BQ {}'.format(min_bq) + ' -l {}'.format(args.candidates_bed_regions) + \
           ' --excl-flags {}'.format(SAMTOOLS_FILTER_FLAG) + \
-          (' --max-depth {}'.format(args.max_depth) if args.max_depth is not None else "")
-    mp = _popen(cmd + '  ' + args.tumor_bam_fn, stdout=PIPE, stderr=PIPE)
+          (' --max-depth {}'.format(args.max_depth) if getattr(args, 'max_depth', None) is not None else "")
+    mp = Popen(shlex.split(cmd + '  ' + args.tumor_bam_fn), stdout=PIPE, stderr=PIPE, bufsize=8388608)
     text, _ = mp.communicate()
 
-    tok = host.tokenize_mpileup(text, reference, reference_start, sorted(cand), max_indel_length)
+    tok = host.tokenize_mpileup(text, reference, reference_start, sorted(cand), max_indel_length, n_threads=host_threads)
     # window assembly (ibid. 513-516, 537-553), vectorised: rows are position sorted, so the row of a position is a
     # binary search; -1 = no pileup row (an all-zero row, ibid. 461)
     table_len = extend_end - extend_start
@@ -127,34 +143,44 @@ def create_tensor(args):
     else:
         ok &= False
     keep = cpos[ok]
-    if keep.size:
-        want = keep[:, None] - FLANK + np.arange(N_POS, dtype=np.int64)[None, :]
-        wi = np.searchsorted(row_pos, want)
-        hit = (wi < row_pos.size) & (row_pos[np.minimum(wi, row_pos.size - 1)] == want)
-        windows = np.where(hit, wi, -1).astype(np.int32)
-        centre_rows = windows[:, FLANK]
+    # a candidate within 16 bp of a contig end has a reference context shorter than 33 bases; the reference still writes
+    # such a row (ibid. 561) and its predict drops it for the centre-base test (clairs/predict.py:219-220) -- or crashes on
+    # the index.  It cannot become a call either way, so it is dropped here (used to abort the whole chunk).
+    ref33 = [reference[int(p) - reference_start - FLANK: int(p) - reference_start + FLANK + 1].upper() for p in keep]
+    full = np.array([len(r) == N_POS for r in ref33], dtype=bool)
+    if not full.all():
+        keep = keep[full]
+        ref33 = [r for r in ref33 if len(r) == N_POS]
+    if not keep.size:
+        return EncodedChunk(ctg_name, keep, [], None, None, [], [])
+    want = keep[:, None] - FLANK + np.arange(N_POS, dtype=np.int64)[None, :]
+    wi = np.searchsorted(row_pos, want)
+    hit = (wi < row_pos.size) & (row_pos[np.minimum(wi, row_pos.size - 1)] == want)
+    windows = np.where(hit, wi, -1).astype(np.int32)
+    centre_rows = windows[:, FLANK]
+    dev = torch.device('cuda', torch.cuda.current_device())
+    tok.stream.win_pos = windows.reshape(-1)
+    tensor, depth = encode_pileup(stream_to_device(tok.stream, dev), PIPELINE_LOW_BQ_CUT, dev)
+    return EncodedChunk(ctg_name, keep, ref33, tensor, depth, [tok.alt_info_of(int(r)) for r in centre_rows],
+                        [cand[int(p)] for p in keep])
 
+
+def create_tensor(args):
+    chunk = encode_chunk(args)
     if tensor_out := (args.tensor_can_fn != "PIPE"):
         fpo = open(args.tensor_can_fn, "wb")
         zp = Popen(shlex.split("{} -c".format(args.zstd)), stdin=PIPE, stdout=fpo, bufsize=8388608)
         out = zp.stdin
     else:
         out = sys.stdout.buffer
-
-    count = 0
-    if keep.size:
-        dev = torch.device('cuda', torch.cuda.current_device())
-        tok.stream.win_pos = windows.reshape(-1)
-        tensor, _ = encode_pileup(stream_to_device(tok.stream, dev), PIPELINE_LOW_BQ_CUT, dev)
-        ref33 = [reference[int(p) - reference_start - FLANK: int(p) - reference_start + FLANK + 1].upper() for p in keep]
-        out.write(host.format_tensor_can_rows(ctg_name, keep, ref33, tensor.cpu().numpy(),
-                                              [tok.alt_info[int(r)] for r in centre_rows], [cand[int(p)] for p in keep]))
-        count = int(keep.size)
+    if len(chunk):
+        out.write(host.format_tensor_can_rows(chunk.ctg, chunk.pos, chunk.ref33, chunk.tensor.cpu().numpy(), chunk.alt_info,
+                                              chunk.variant_type))
     if tensor_out:
         zp.stdin.close()
         zp.wait()
         fpo.close()
-    print("[INFO] {} {} Tensors generated: {}".format(ctg_name, get_chunk_id(args.candidates_bed_regions), count))
+    print("[INFO] {} {} Tensors generated: {}".format(args.ctg_name, get_chunk_id(args.candidates_bed_regions), len(chunk)))
 
 
 def build_parser():

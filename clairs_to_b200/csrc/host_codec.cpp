@@ -358,6 +358,64 @@ int cto_tokenize_mpileup(const char* text, int64_t text_len, const char* ref_seq
     return 0;
 }
 
+// A decompressed predict chunk file (rows of clairs/predict.py:114-152) in one pass: replaces the row loop of
+// clairs/call_variants.py:798-829.  Per row: fields[r][k] = (offset, length) of chrom, pos, ref, alt_info and the two strand
+// list-reprs; p_aff / p_neg [r][h] = the SECOND number of each "p0 p1" probability field parsed with strtod (correctly
+// rounded, i.e. the same double python's float() gives the reference).  Rows with fewer than 6 + 2 * n_heads fields are
+// an error (the reference would raise on them too).
+int cto_parse_predict_file(const char* text, int64_t len, int n_heads, int64_t max_rows, double* p_aff, double* p_neg,
+                           int64_t* fields, int64_t* n_rows) {
+    if (!text || !p_aff || !p_neg || !fields || !n_rows || (n_heads != 4 && n_heads != 6)) {
+        cto::set_error("parse_predict_file: bad argument");
+        return 2;
+    }
+    int64_t r = 0;
+    const char* p = text;
+    const char* end = text + len;
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        if (eol > p) {
+            if (r >= max_rows) {
+                cto::set_error("parse_predict_file: more than %lld rows", (long long)max_rows);
+                return 2;
+            }
+            const char* q = p;
+            const char* stop = eol;
+            while (stop > q && (stop[-1] == '\r' || stop[-1] == ' ' || stop[-1] == '\t')) --stop;   // line.rstrip()
+            for (int k = 0; k < 6 + 2 * n_heads; ++k) {
+                if (q > stop) {
+                    cto::set_error("parse_predict_file: row %lld has %d fields, expected %d", (long long)r, k, 6 + 2 * n_heads);
+                    return 2;
+                }
+                const char* tab = (const char*)memchr(q, '\t', (size_t)(stop - q));
+                if (!tab) tab = stop;
+                if (k < 6) {
+                    fields[(r * 6 + k) * 2] = (int64_t)(q - text);
+                    fields[(r * 6 + k) * 2 + 1] = (int64_t)(tab - q);
+                } else {
+                    char* e1 = nullptr;
+                    strtod(q, &e1);                                   // p0
+                    char* e2 = nullptr;
+                    const double p1 = strtod(e1, &e2);
+                    if (e1 == q || e2 == e1 || e2 > tab) {
+                        cto::set_error("parse_predict_file: row %lld field %d is not 'p0 p1'", (long long)r, k);
+                        return 2;
+                    }
+                    const int h = k - 6;
+                    if (h < n_heads) p_aff[r * n_heads + h] = p1;
+                    else p_neg[r * n_heads + (h - n_heads)] = p1;
+                }
+                q = tab + 1;
+            }
+            ++r;
+        }
+        p = eol + 1;
+    }
+    *n_rows = r;
+    return 0;
+}
+
 // Synthetic `samtools mpileup` text for a read-array stream (the inverse of the tokenizer; bench.py's text-in leg and the
 // tests render the same sites as text): rows "ctg \t pos \t N \t depth \t bases \t BQ \t MQ \n", position = first_pos + row.
 // ind_len / ind_seq: per indel-carrying read (in read order) the indel length and, for insertions, the inserted bases

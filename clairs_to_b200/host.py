@@ -170,3 +170,26 @@ def format_tensor_can_rows(ctg, pos, ref33, tensors, alt_infos, types) -> bytes:
     if w < 0:
         raise _lib.CtoError("cto_format_tensor_can_rows failed (%d)" % w)
     return buf.raw[:w]
+
+
+class PredictFile:
+    """A whole predict chunk file parsed by one native call (``cto_parse_predict_file``): ``p_aff`` / ``p_neg`` double
+    [n, H] (P(positive class) per head, the doubles the reference gets from float()), and the text fields of row r as
+    slices of ``text`` via ``field(r, k)`` (k: 0 chrom, 1 pos, 2 ref, 3 alt_info, 4 forward counts, 5 reverse counts)."""
+
+    def __init__(self, text: bytes, n_heads: int):
+        lib = _lib.lib()
+        self.text = text
+        max_rows = text.count(b"\n") + 1
+        self.p_aff = np.empty((max_rows, n_heads), np.float64)
+        self.p_neg = np.empty((max_rows, n_heads), np.float64)
+        self.fields = np.empty((max_rows, 6, 2), np.int64)
+        n = C.c_int64(0)
+        _lib.check(lib.cto_parse_predict_file(text, len(text), int(n_heads), max_rows, _p(self.p_aff), _p(self.p_neg), _p(self.fields),
+                                              C.byref(n)), "cto_parse_predict_file")
+        self.n = int(n.value)
+        self.p_aff, self.p_neg, self.fields = self.p_aff[:self.n], self.p_neg[:self.n], self.fields[:self.n]
+
+    def field(self, r, k) -> str:
+        o, ln = self.fields[r, k]
+        return self.text[o:o + ln].decode()

@@ -269,6 +269,14 @@ int cto_parse_tensor_file(const char* text, int64_t len, int64_t max_rows, int16
                           int64_t* n_rows);
 int64_t cto_format_predict_rows(const char* text, const int64_t* fields, int64_t n, const int32_t* fwd, const int32_t* rev,
                                 const float* probs, int n_heads, char* out, int64_t cap);
+/*
+ * cto_parse_predict_file: `text` = a decompressed predict file (rows of clairs/predict.py:114-152).  Replaces the row loop
+ * of clairs/call_variants.py:798-829: fields[r][k] = (byte offset, length) of chrom, pos, ref, alt_info, forward and
+ * reverse strand list-reprs (int64 [rows][6][2]); p_aff / p_neg double [rows][n_heads] = P(positive class) of every head,
+ * parsed with strtod (the doubles python's float() gives the reference).
+ */
+int cto_parse_predict_file(const char* text, int64_t len, int n_heads, int64_t max_rows, double* p_aff, double* p_neg,
+                           int64_t* fields, int64_t* n_rows);
 
 #ifdef __cplusplus
 }

@@ -232,3 +232,22 @@ def test_native_renderer_and_threaded_tokenizer_round_trip():
         assert t1.alt_info == t4.alt_info and np.array_equal(t1.row_pos, t4.row_pos)
         assert np.array_equal(t1.stream.code, s.code) and np.array_equal(t1.stream.bq, s.bq) and np.array_equal(t1.stream.mq, s.mq)
         assert np.array_equal(t1.stream.pos_off, s.pos_off) and np.array_equal(t1.stream.ind_off, s.ind_off)
+
+
+def test_predict_file_parser_matches_python_row_parse(golden_dir):
+    """cto_parse_predict_file == the reference's row loop (clairs/call_variants.py:798-829: split on tabs, float() every
+    probability) on the predict files the unmodified reference wrote."""
+    import gzip
+    from clairs_to_b200.host import PredictFile
+    for tag, n_heads in (("snv", 4), ("indel", 6)):
+        text = gzip.open(os.path.join(golden_dir, "pipeline", "predict_" + tag), "rb").read()
+        pf = PredictFile(text, n_heads)
+        rows = [r.rstrip().split("\t") for r in text.decode().splitlines() if r.strip()]
+        assert pf.n == len(rows) == 39
+        for k, cols in enumerate(rows):
+            assert [pf.field(k, f) for f in range(6)] == cols[:6]
+            probs = [[float(v) for v in f.split()] for f in cols[6:6 + 2 * n_heads]]
+            assert pf.p_aff[k].tolist() == [p[1] for p in probs[:n_heads]]
+            assert pf.p_neg[k].tolist() == [p[1] for p in probs[n_heads:]]
+    with pytest.raises(Exception):
+        PredictFile(b"chr1\t5\tA\t3-XT 1-\t[0.0]\t[0.0]\t0.5 0.5\n", 4)          # too few fields

@@ -175,3 +175,32 @@ def test_vcf_header_matches_reference_fixture(golden_dir):
     want = [l for l in open(os.path.join(golden_dir, "pipeline", "call_snv_showref.vcf")) if l.startswith("##")
             and not l.startswith("##contig")]
     assert vcf_header_text() == "".join(want)
+
+
+@pytest.mark.gpu
+def test_hot_path_in_memory_equals_the_three_sub_commands(golden_dir, tmp_path):
+    """clairs_to_b200.hot_path (encoder -> networks -> posterior -> VCF in one process, tensors never leave the GPU) against
+    the three drop-in sub-commands run one after the other through their gzip chunk files (each of which is pinned to the
+    reference above): identical VCF, and identical intermediate files when asked to write them."""
+    from clairs_to_b200 import call_variants as cv, create_tensor_pileup_calling as ct, hot_path, predict as pr
+    work = os.path.join(golden_dir, "create_tensor")
+    lk = os.path.join(golden_dir, "pipeline", "likelihood_snv.txt")
+    ck_a, ck_n = _save_checkpoints(tmp_path, 4)
+    common = ["--tumor_bam_fn", os.path.join(work, "tumor.bam"), "--ref_fn", os.path.join(work, "ref.fa"), "--ctg_name", "chr20",
+              "--samtools", SHIM, "--candidates_bed_regions", os.path.join(work, "chr20.0_0_9_snv"),
+              "--platform", "ont_r10_dorado_sup_5khz"]
+    files = {k: str(tmp_path / k) for k in ("aff", "neg", "predict", "vcf_files", "aff2", "neg2", "predict2", "vcf_mem")}
+    for name, min_bq in (("aff", 20), ("neg", 0)):
+        ct.main(common + ["--min_bq", str(min_bq), "--tensor_can_fn", files[name]])
+    pr.main(["--tensor_fn_acgt", files["aff"], "--tensor_fn_nacgt", files["neg"], "--predict_fn", files["predict"],
+             "--chkpnt_fn_acgt", ck_a, "--chkpnt_fn_nacgt", ck_n, "--use_gpu", "True", "--platform", "ont_r10_dorado_sup_5khz",
+             "--ctg_name", "chr20", "--pileup", "--disable_indel_calling", "True"])
+    cv.main(["--predict_fn", files["predict"], "--call_fn", files["vcf_files"], "--ref_fn", os.path.join(work, "ref.fa"),
+             "--platform", "ont_r10_dorado_sup_5khz", "--likelihood_matrix_data", lk, "--disable_indel_calling", "True", "--show_ref"])
+    hot_path.main(common + ["--min_bq", "20", "--chkpnt_fn_acgt", ck_a, "--chkpnt_fn_nacgt", ck_n, "--likelihood_matrix_data", lk,
+                            "--disable_indel_calling", "True", "--show_ref", "--call_fn", files["vcf_mem"],
+                            "--tensor_can_fn_acgt", files["aff2"], "--tensor_can_fn_nacgt", files["neg2"], "--predict_fn", files["predict2"]])
+    assert os.path.exists(files["vcf_files"]) and open(files["vcf_mem"]).read() == open(files["vcf_files"]).read()
+    assert sum(1 for l in open(files["vcf_mem"]) if not l.startswith("#")) >= 3
+    for a, b in (("aff", "aff2"), ("neg", "neg2"), ("predict", "predict2")):
+        assert gzip.open(files[a], "rb").read() == gzip.open(files[b], "rb").read(), a
