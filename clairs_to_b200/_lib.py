@@ -37,6 +37,8 @@ SIGNATURES = {
     "cto_engine_set_tensor_cores": (INT, [P, INT]),
     "cto_engine_fused_status": (INT, [P, P]),
     "cto_aff_stage_layers": (INT, [P, INT, P, I64, P]),
+    "cto_neg_recurrence": (INT, [P, P, I64, P, P, INT, P]),
+    "cto_engine_workspace": (INT, [P, INT, P, P]),
     "cto_gemm_nt": (INT, [P, I64, P, P, P, I64, P, I64, I64, INT, INT, INT, INT, P]),
     "cto_posterior_from_probs": (INT, [P, INT, P, P, I64, P, P, P]),
     "cto_launch_count": (I64, []),

@@ -240,15 +240,44 @@ void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; }
 void cto_debug_timing_fused(long long* dev_buf) { cto::g_fused_timing = dev_buf; }
 int cto_engine_set_tensor_cores(cto_engine* h, int mode) {
     CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");
-    CTO_REQUIRE(mode >= 0 && mode <= 2, "engine_set_tensor_cores: mode %d (0 exact fp32, 1 tensor cores, 2 tensor cores without the fused AFF layers)", mode);
+    CTO_REQUIRE(mode >= 0 && mode <= 2, "engine_set_tensor_cores: mode %d (0 exact fp32, 1 tensor cores, 2 tensor cores with the round-1 per-op kernels: no fused AFF layers, one-chain GRU)", mode);
     h->e.use_tc = mode != 0;
     h->e.use_fused = mode == 1;
+    h->e.use_two_chains = mode == 1;
     return 0;
 }
 
 int cto_aff_stage_layers(cto_engine* h, int stage, float* x_dev, int64_t n, void* stream) {
     CTO_REQUIRE(h && x_dev, "aff_stage_layers: NULL argument");
     return aff_stage_layers_on(h->e, stage, x_dev, n, (cudaStream_t)stream);
+}
+
+int cto_neg_recurrence(cto_engine* h, const float* xproj_dev, int64_t n, uint16_t* out_hi_dev, uint16_t* out_mid_dev, int two_chains,
+                       void* stream) {
+    CTO_REQUIRE(h && xproj_dev && out_hi_dev && out_mid_dev, "neg_recurrence: NULL argument");
+    return neg_recurrence_on(h->e, xproj_dev, n, out_hi_dev, out_mid_dev, two_chains, (cudaStream_t)stream);
+}
+
+int cto_engine_workspace(cto_engine* h, int which, void* dst_dev, int64_t* bytes) {
+    const void* src = nullptr;
+    const void** dev_ptr = &src;
+    CTO_REQUIRE(h && bytes, "engine_workspace: NULL argument");
+    Engine& e = h->e;
+    CTO_REQUIRE(e.neg.n_heads > 0 && e.n_xp, "engine_workspace: no NEG workspace");
+    const int64_t rows = (int64_t)N_POS * e.bp_max, h1 = e.neg.l[0].hidden, h2 = e.neg.l[1].hidden;
+    switch (which) {
+        case 0: *dev_ptr = e.n_xp; *bytes = 4 * rows * 6 * std::max(h1, h2); break;
+        case 1: *dev_ptr = e.o1_hi; *bytes = 2 * rows * 2 * h1; break;
+        case 2: *dev_ptr = e.o1_mid; *bytes = 2 * rows * 2 * h1; break;
+        case 3: *dev_ptr = e.o2_hi; *bytes = 2 * rows * 2 * h2; break;
+        case 4: *dev_ptr = e.o2_mid; *bytes = 2 * rows * 2 * h2; break;
+        default: CTO_REQUIRE(false, "engine_workspace: unknown tensor %d", which);
+    }
+    if (dst_dev) {
+        CTO_CHECK(cudaDeviceSynchronize());
+        CTO_CHECK(cudaMemcpy(dst_dev, src, (size_t)*bytes, cudaMemcpyDeviceToDevice));
+    }
+    return 0;
 }
 
 int cto_engine_fused_status(cto_engine* h, int32_t* out8) {

@@ -466,6 +466,20 @@ static int aff_stage_layers(Engine& e, const CvtStage& st, int64_t n, cudaStream
 }
 
 // Kernel-level parity hook (cto_aff_stage_layers): the layers of stage `si` on a caller-provided residual stream.
+// Kernel-level hook (cto_neg_recurrence): the layer-2 recurrence alone, on a caller-supplied transposed input projection.
+int neg_recurrence_on(Engine& e, const float* xproj, int64_t n, uint16_t* out_hi, uint16_t* out_mid, int two_chains, cudaStream_t s) {
+    NegModel& m = e.neg;
+    CTO_REQUIRE(m.n_heads > 0 && m.whh_pair[1].bhi && e.use_tc, "neg_recurrence: needs a loaded NEG network on the tensor-core engine");
+    CTO_REQUIRE(n > 0 && n <= e.max_batch, "neg_recurrence: n %lld outside (0, max_batch]", (long long)n);
+    const int h2 = m.l[1].hidden;
+    const int64_t bp = (n + 127) / 128 * 128, ldx = (int64_t)N_POS * bp;
+    if (two_chains) {
+        CTO_REQUIRE(h2 == 192, "neg_recurrence: the two-chain kernel is built for hidden size 192, not %d", h2);
+        return launch_gru4(xproj, ldx, bp, m.whh_pair[1].bhi, m.whh_pair[1].bmid, m.l[1].bhn, out_hi, out_mid, N_POS, 1, n, h2, e.fused_dbg, s);
+    }
+    return launch_gru3(xproj, ldx, bp, m.whh_pair[1].bhi, m.whh_pair[1].bmid, m.l[1].bhn, out_hi, out_mid, N_POS, 1, n, h2, s);
+}
+
 int aff_stage_layers_on(Engine& e, int si, float* x, int64_t n, cudaStream_t s) {
     CTO_REQUIRE(si >= 0 && si < e.aff.n_stages && n <= e.max_batch, "aff_stage_layers: stage %d / batch %lld out of range", si, (long long)n);
     const CvtStage& st = e.aff.st[si];
@@ -559,7 +573,10 @@ static int neg_forward_tc(Engine& e, const float* x, int64_t n, float* logits, c
     RUN(launch_gemm_tc_ex(g, s));
     RUN(prof_end(e, s));
     RUN(prof_begin(e, PK_NEG_GRU2, s));
-    RUN(launch_gru3(e.n_xp, ldx, bp, m.whh_pair[1].bhi, m.whh_pair[1].bmid, m.l[1].bhn, e.o2_hi, e.o2_mid, N_POS, 1, n, h2, s));
+    if (e.use_two_chains && h2 == 192)
+        RUN(launch_gru4(e.n_xp, ldx, bp, m.whh_pair[1].bhi, m.whh_pair[1].bmid, m.l[1].bhn, e.o2_hi, e.o2_mid, N_POS, 1, n, h2, e.fused_dbg, s));
+    else
+        RUN(launch_gru3(e.n_xp, ldx, bp, m.whh_pair[1].bhi, m.whh_pair[1].bmid, m.l[1].bhn, e.o2_hi, e.o2_mid, N_POS, 1, n, h2, s));
     RUN(prof_end(e, s));
     const int feat = N_POS * 2 * h2;
     const HeadW& hd = m.head;

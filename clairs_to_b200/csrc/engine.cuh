@@ -94,6 +94,7 @@ struct Engine {
     cudaMemPool_t pool = nullptr;                              // private stream-ordered pool of cto_run_sites_host
     bool use_tc = true;                                        // dense contractions on tcgen05 (bf16x3)
     bool use_fused = true;                                     // AFF transformer layers in the fused kernel (aff_fused.cu)
+    bool use_two_chains = true;                                // GRU layer 2 with two chains per CTA pair (gru_tc4.cu)
     int* fused_dbg = nullptr;                                  // device int[8]: barrier-timeout report of the fused kernel
     // optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
     int profile = 0;           // 0 off, 1 = NEG kernel families + AFF as one block, 2 = every AFF kernel family too
@@ -129,6 +130,7 @@ void engine_free(Engine& e);
 // logits: device fp32 [n, n_heads, 2]; n <= max_batch
 int aff_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
 int aff_stage_layers_on(Engine& e, int si, float* x, int64_t n, cudaStream_t s);
+int neg_recurrence_on(Engine& e, const float* xproj, int64_t n, uint16_t* out_hi, uint16_t* out_mid, int two_chains, cudaStream_t s);
 int neg_forward(Engine& e, const float* x, int64_t n, float* logits, cudaStream_t s);
 // the same from the encoder's int16 tensor [n, 33, 34] + per-candidate depth (depth rescale of clairs/predict.py:179-197 fused in)
 int neg_forward_from_counts(Engine& e, const int16_t* x, const int32_t* depth, int64_t n, float* logits, cudaStream_t s);

@@ -53,7 +53,9 @@ __device__ __forceinline__ void f_commit_2sm(uint64_t* bar) {
 __device__ __forceinline__ void f_arrive_leader(uint64_t* bar) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(g_smem_u32(bar)));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    // default semantics (.release.cta), as CUTLASS signals a peer CTA: the .release.cluster form compiles to MEMBAR.ALL.GPU,
+    // which stalls the warp until every output store it has in flight is acknowledged by L2
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void f_wait_cluster(uint64_t* bar, uint32_t parity) {
     asm volatile(

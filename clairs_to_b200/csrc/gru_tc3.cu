@@ -73,7 +73,9 @@ __device__ __forceinline__ void q_commit_2sm(uint64_t* bar) {       // arrives o
 __device__ __forceinline__ void q_arrive_leader(uint64_t* bar) {   // DSMEM arrive on the leader CTA's barrier
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(g_smem_u32(bar)));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    // default semantics (.release.cta), as CUTLASS signals a peer CTA: the .release.cluster form compiles to MEMBAR.ALL.GPU,
+    // which stalls the warp until every output store it has in flight is acknowledged by L2
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void q_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
     asm volatile(
@@ -294,8 +296,6 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                     for (int g = 0; g < 3; ++g)
                         #pragma unroll
                         for (int c = 0; c < 8; ++c) xv[g * 8 + c] = (VAR & 2) ? 0.25f : xp[(g * Q_BLK + c) * Q_M];
-                    __syncwarp();
-                    if (lane == 0) g_mbar_arrive(&xempty[xs]);
                     ++xq_it;
                 }
                 g_mbar_wait(&acc_full[blk], step & 1);
@@ -333,6 +333,11 @@ gru3_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                 const uint32_t to = tile_off(j);
                 *reinterpret_cast<uint4*>(hnext + to) = hi;
                 *reinterpret_cast<uint4*>(hnext + KB * Q_HTILE + to) = mid;
+                // The projection stage goes back to the producer only HERE, behind stores of values computed from all 24 loads:
+                // an arrive issued right behind the loads does not wait for their data, and a refill that hits in L2 can
+                // overwrite the stage under them (profiles/r2_gru4_race.txt).
+                __syncwarp();
+                if (lane == 0) g_mbar_arrive(&xempty[(xq_it - 1) % Q_XSTAGES]);
                 if (b_ok && !(VAR & 4)) {                      // pre-split output: an operand of the next GEMM
                     *reinterpret_cast<uint4*>(out_hi + orow + uu) = hi;
                     *reinterpret_cast<uint4*>(out_mid + orow + uu) = mid;

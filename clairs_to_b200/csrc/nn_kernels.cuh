@@ -75,6 +75,10 @@ int launch_gru_recurrent(const float* xproj, const float* whh_t, const float* bh
 // h_t as bf16 hi / mid planes at row (b * osb + t * ost) of [.., 2H]
 int launch_gru3(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_hi, const uint16_t* w_mid, const float* bhn,
                 uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch, int hidden, cudaStream_t s);
+// the same recurrence with TWO chains per CTA pair (gru_tc4.cu, H = 192): the gate math of one chain overlaps the MMAs of the
+// other; dbg = device int[8] watchdog record
+int launch_gru4(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_hi, const uint16_t* w_mid, const float* bhn,
+                uint16_t* out_hi, uint16_t* out_mid, int64_t osb, int64_t ost, int64_t batch, int hidden, int* dbg, cudaStream_t s);
 // fp32 rows [n, t_len, ld_in] -> time-major bf16 hi / mid planes [t_len, bp, ld_in] (rows b >= n are left untouched)
 // one_col >= 0: that (padding) column is set to 1.0 -- the bias column of the fused first GRU layer
 int launch_split_time_major(const float* x, int64_t n, int t_len, int ld_in, int64_t bp, uint16_t* hi, uint16_t* mid,

@@ -147,6 +147,27 @@ class Engine:
         AFF transformer kernel; 2: tcgen05 contractions with one kernel per op (round-1 layers, kept for A/B tests)."""
         _lib.check(self.lib.cto_engine_set_tensor_cores(self.handle, int(mode)), "set_tensor_cores")
 
+    def neg_recurrence(self, xproj, n, two_chains=True):
+        """Layer-2 GRU recurrence alone (kernel-level hook, cto_neg_recurrence): xproj fp32 [6H, 33 * bp] on the device ->
+        (out_hi, out_mid) int16 views of the bf16 planes [n, 33, 2H]."""
+        bp = (n + 127) // 128 * 128
+        assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.shape[1] == N_POS * bp, xproj.shape
+        h2 = xproj.shape[0] // 6
+        hi = torch.zeros((n, N_POS, 2 * h2), dtype=torch.int16, device=self.device)
+        mid = torch.zeros_like(hi)
+        _lib.check(self.lib.cto_neg_recurrence(self.handle, _ptr(xproj), n, _ptr(hi), _ptr(mid), int(bool(two_chains)), _stream_ptr()),
+                   "neg_recurrence")
+        return hi, mid
+
+    def workspace(self, which):
+        """Test hook (cto_engine_workspace): a COPY of one NEG workspace tensor as raw bytes (uint8 device tensor)."""
+        import ctypes as C
+        nbytes = C.c_int64()
+        _lib.check(self.lib.cto_engine_workspace(self.handle, int(which), None, C.byref(nbytes)), "workspace")
+        out = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.cto_engine_workspace(self.handle, int(which), _ptr(out), C.byref(nbytes)), "workspace")
+        return out
+
     def fused_status(self):
         """Watchdog record of the fused AFF kernel (synchronises): all zeros unless an in-kernel barrier wait timed out."""
         out = np.zeros(8, np.int32)

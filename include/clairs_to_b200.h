@@ -142,11 +142,28 @@ int cto_engine_set_tensor_cores(cto_engine* e, int mode);
  */
 int cto_engine_fused_status(cto_engine* e, int32_t* out8);
 /*
+ * Test hook: size of one NEG workspace tensor and, when dst_dev is not NULL, a device-to-device copy of it as the last
+ * forward left it (synchronises).  which: 0 = the transposed
+ * input projection of the last GRU layer run (fp32 [6H][33 * bp_max]), 1 / 2 = hi / mid bf16 planes of the layer-1 output
+ * (time-major [33][bp][2 H1]), 3 / 4 = hi / mid planes of the layer-2 output (batch-major [n][33][2 H2]).
+ */
+int cto_engine_workspace(cto_engine* e, int which, void* dst_dev, int64_t* bytes);
+/*
  * Kernel-level building block, like cto_gemm_nt: all transformer layers (x += Attention(LN(x)); x += FF(LN(x)),
  * clairs/model.py:143-147) of CvT stage `stage` (0-based) on a residual stream x fp32 [n, W_stage, C_stage]
  * (channels-last, device memory, in place), on whichever engine mode is selected.  n <= max_batch.
  */
 int cto_aff_stage_layers(cto_engine* e, int stage, float* x_dev, int64_t n, void* stream);
+/*
+ * Kernel-level building block: the second GRU layer's recurrence alone (h_t = GRU(x_t, h_{t-1}) in both directions,
+ * torch.nn.GRU as used by clairs/model.py:440-470), with the loaded NEG network's recurrent weights.
+ * xproj_dev: the layer's input projection W_ih x_t + b_ih (+ b_hr, b_hz), TRANSPOSED: fp32 [6H rows (direction, gate r|z|n,
+ * unit)][33 * bp columns (t * bp + candidate)], bp = n rounded up to 128.  out_hi / out_mid: the bf16 split of
+ * h_t, [n][33][2H] (forward | backward).  two_chains: 0 = one recurrence chain per CTA pair (csrc/gru_tc3.cu),
+ * 1 = two chains per CTA pair (csrc/gru_tc4.cu, H = 192 only; what the engine runs in mode 1).  Tensor-core engine only.
+ */
+int cto_neg_recurrence(cto_engine* e, const float* xproj_dev, int64_t n, uint16_t* out_hi_dev, uint16_t* out_mid_dev,
+                       int two_chains, void* stream);
 int cto_gemm_nt(const float* a_dev, int64_t lda, const float* w_dev, const float* bias_dev, const float* residual_dev,
                 int64_t ldr, float* c_dev, int64_t ldc, int64_t m, int n, int k, int act, int use_tensor_cores,
                 void* stream);
