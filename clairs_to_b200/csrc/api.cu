@@ -292,7 +292,9 @@ int cto_gemm_nt(const float* a, int64_t lda, const float* w, const float* bias, 
     if (!use_tensor_cores) return launch_gemm_nt(plain_a(a, lda), w, bias, residual, ldr, c, ldc, m, n, k, act, (cudaStream_t)stream);
     // tensor-core modes (bit 0 set): the operands are split here on the fly; the engine does it once at load time
     // (weights) or in the producing kernel (activations).  bit 1: A pre-split into bf16 planes, bit 2: C written as
-    // bf16 planes and recombined, bit 3: bias indexed by the output row + n-major tile order.
+    // bf16 planes and recombined, bit 3: bias indexed by the output row + n-major tile order, bit 4 (with bit 1): 128 x 256 tiles
+    // when the problem has enough column tiles (the transposed GRU input projections), bit 5 (with bits 1 and 3, K <= 256): the
+    // CTA-pair kernel with A resident in shared memory (gemm_pair.cu) when the shape fits.
     const bool presplit = use_tensor_cores & 2, out_split = use_tensor_cores & 4, by_row = use_tensor_cores & 8;
     CTO_REQUIRE(!presplit || lda == k, "gemm_nt: pre-split A needs a dense A (lda == k)");
     CTO_REQUIRE(!out_split || (ldc == n && !residual), "gemm_nt: split C needs a dense C (ldc == n) and no residual");
@@ -317,7 +319,8 @@ int cto_gemm_nt(const float* a, int64_t lda, const float* w, const float* bias, 
         g.flags |= GEMM_OUT_SPLIT; g.c_hi = chi; g.c_mid = cmid;
     }
     if (by_row) g.flags |= GEMM_BIAS_PER_ROW | GEMM_TILES_N_MAJOR;
-    if (!rc) rc = launch_gemm_tc_ex(g, s);
+    if (use_tensor_cores & 16) g.flags |= GEMM_WIDE_N;
+    if (!rc) rc = ((use_tensor_cores & 32) && gemm_pair_supported(g)) ? launch_gemm_pair(g, s) : launch_gemm_tc_ex(g, s);
     if (out_split && !rc) rc = launch_join_bf16(chi, cmid, c, m * n, s);
     for (uint16_t* p : {whi, wmid, ahi, amid, chi, cmid})
         if (p) cudaFreeAsync(p, s);

@@ -547,7 +547,7 @@ static int neg_forward_tc(Engine& e, const float* x, int64_t n, float* logits, c
     // the input planes carry a constant 1.0 in column in_dim when layer 1 runs fused (its bias rides in W_ih)
     if (x) RUN(launch_split_time_major(x, n, N_POS, NEG_IN_LD, bp, e.nx_hi, e.nx_mid, s, m.fuse_l1 ? m.l[0].in_dim : -1));
     GemmTc g;
-    g.flags = GEMM_A_PRESPLIT | GEMM_BIAS_PER_ROW | GEMM_TILES_N_MAJOR;
+    g.flags = GEMM_A_PRESPLIT | GEMM_BIAS_PER_ROW | GEMM_TILES_N_MAJOR | (e.use_two_chains ? GEMM_WIDE_N : 0);
     g.c = e.n_xp; g.ldc = ldx; g.n = (int)ldx;
     if (m.fuse_l1) {
         RUN(prof_begin(e, PK_NEG_GRU1, s));
@@ -570,7 +570,8 @@ static int neg_forward_tc(Engine& e, const float* x, int64_t n, float* logits, c
     g.a_hi = m.ws.bhi + off2; g.a_mid = m.ws.bmid + off2; g.lda = 2 * h1;
     g.w_hi = e.o1_hi; g.w_mid = e.o1_mid; g.ldw = 2 * h1;
     g.bias = m.l[1].bih; g.m = 6 * h2; g.k = 2 * h1;
-    RUN(launch_gemm_tc_ex(g, s));
+    if (e.use_two_chains && gemm_pair_supported(g)) RUN(launch_gemm_pair(g, s));
+    else RUN(launch_gemm_tc_ex(g, s));
     RUN(prof_end(e, s));
     RUN(prof_begin(e, PK_NEG_GRU2, s));
     if (e.use_two_chains && h2 == 192)

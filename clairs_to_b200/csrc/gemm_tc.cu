@@ -31,11 +31,16 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                       // K elements per stage = one 128-byte swizzle row of bf16
-constexpr int MAX_BN = 128;
+constexpr int MAX_BN = 256;                  // TMEM columns of one accumulator buffer (two buffers = all 512 columns)
 constexpr int TILE_BYTES = BM * 128;         // 16 KB: one fp32 A box (128 x 32) on arrival, one bf16 tile (128 x 64) after
                                              // the conversion; W tiles use BN*128 bytes of theirs
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A box 0 -> A_hi | A box 1 -> A_mid | W_hi | W_mid
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;  // A box 0 -> A_hi | A box 1 -> A_mid | W_hi | W_mid          (BN <= 128)
 constexpr int STAGES = 3;
+// BN = 256 ("wide" tiles of the transposed GRU projections): a stage is A_hi | A_mid | W_hi (32 KB) | W_mid (32 KB) = 96 KB and
+// there are two of them in the same 192 KB.  One MMA then reads 4 KB of A + 8 KB of W per 128 clk = 96 B/clk of shared
+// memory instead of 8 KB per 64 clk = the full 128 B/clk, and a tile needs 25 % fewer L2 bytes per output element.
+constexpr int WIDE_STAGE_BYTES = 2 * TILE_BYTES + 2 * 256 * 128;
+constexpr int WIDE_STAGES = 2;
 constexpr int SLAB = 32;                     // epilogue works on 128 x 32 fp32 slabs
 constexpr int STAGING_BYTES = BM * SLAB * 4; // 16 KB, two of them
 constexpr int THREADS = 448;                 // warp 0 TMA, 1 MMA, 2-5 converter, 6-13 two epilogue groups
@@ -164,9 +169,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (k_total + BK - 1) / BK;
-    const int n_tiles = n_total / bn;
+    const int n_tiles = (n_total + bn - 1) / bn;     // a ragged last column tile is zero-filled / clipped by TMA
     const int64_t m_tiles = (m_total + BM - 1) / BM;
     const int64_t num_tiles = m_tiles * n_tiles;
+    const int nstages = bn > 128 ? WIDE_STAGES : STAGES;
+    const int stage_bytes = bn > 128 ? WIDE_STAGE_BYTES : STAGE_BYTES;
+    const int wmid_off = 2 * TILE_BYTES + (bn > 128 ? bn * 128 : TILE_BYTES);      // W_mid behind W_hi
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
@@ -174,7 +182,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -189,12 +197,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 const int m0 = (n_major ? (int)(t % m_tiles) : (int)(t / n_tiles)) * BM;
                 const int n0 = (n_major ? (int)(t / m_tiles) : (int)(t % n_tiles)) * bn;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % nstages;
+                    const uint32_t ph = (it / nstages) & 1;
                     TIC;
                     mbar_wait(&empty[s], ph ^ 1);
                     TOC(0);
-                    uint8_t* st = base + s * STAGE_BYTES;
+                    uint8_t* st = base + s * stage_bytes;
                     // fp32 A: the second 128 x 32 box is skipped when it holds no live column; pre-split A: hi and mid tile
                     const bool two = presplit || k_total - kb * BK > 32;
                     if (elect_one()) {
@@ -203,7 +211,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                         if (presplit) tma_load_2d(&tma_amid, &full[s], st + TILE_BYTES, kb * BK, m0);
                         else if (two) tma_load_2d(&tma_a, &full[s], st + TILE_BYTES, kb * BK + 32, m0);
                         tma_load_2d(&tma_whi, &full[s], st + 2 * TILE_BYTES, kb * BK, n0);
-                        tma_load_2d(&tma_wmid, &full[s], st + 3 * TILE_BYTES, kb * BK, n0);
+                        tma_load_2d(&tma_wmid, &full[s], st + wmid_off, kb * BK, n0);
                     }
                     __syncwarp();
                     TOC(1);
@@ -223,18 +231,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + ab * MAX_BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % nstages;
+                    const uint32_t ph = (it / nstages) & 1;
                     mbar_wait(&full[s], ph);               // W tiles landed
                     TOC(1);
                     if (!presplit) mbar_wait(&conv[s], ph);  // A split into bf16 hi / mid
                     TOC(2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(base + s * STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(base + s * stage_bytes);
                     const uint64_t d_ahi = make_desc_k_sw128(a_addr);
                     const uint64_t d_amid = make_desc_k_sw128(a_addr + TILE_BYTES);
                     const uint64_t d_whi = make_desc_k_sw128(a_addr + 2 * TILE_BYTES);
-                    const uint64_t d_wmid = make_desc_k_sw128(a_addr + 3 * TILE_BYTES);
+                    const uint64_t d_wmid = make_desc_k_sw128(a_addr + wmid_off);
                     const int ksteps = min(BK / 16, (k_total - kb * BK + 15) >> 4);   // K tail: skip all-zero k-steps
                     if (elect_one()) {
                         #pragma unroll
@@ -262,12 +270,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < num_tiles && !presplit; t += gridDim.x) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+                const int s = it % nstages;
+                const uint32_t ph = (it / nstages) & 1;
                 TIC;
                 mbar_wait(&full[s], ph);
                 TOC(0);
-                uint8_t* st = base + s * STAGE_BYTES;
+                uint8_t* st = base + s * stage_bytes;
                 const int nchunks = min(8, ((k_total - kb * BK + 15) >> 4) * 2);   // chunks the MMAs will read
                 // fp32 element (r, k) sits in box k/32 at 16-byte unit ((k%32)/4) ^ (r%8) of row r; bf16 element
                 // (r, k) goes to chunk (k/8) ^ (r%8) of row r.  Eight lanes own one row per pass, so the in-place
@@ -409,7 +417,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -523,7 +531,11 @@ int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s) {
     else if (g.act == ACT_SELU) CTO_CHECK(set_max_dynamic_smem(tc::gemm_bf16x3_kernel<ACT_SELU>, tc::SMEM_BYTES));
     else CTO_CHECK(set_max_dynamic_smem(tc::gemm_bf16x3_kernel<ACT_NONE>, tc::SMEM_BYTES));
     // 128-wide tiles unless that leaves SMs without a tile (long-K, few-row GEMMs such as the NEG fc1)
-    const int bn = (g.n % 128 == 0 && (int64_t)ceil_div(g.m, tc::BM) * (g.n / 128) >= sm_count) ? 128 : 64;
+    int bn = (g.n % 128 == 0 && (int64_t)ceil_div(g.m, tc::BM) * (g.n / 128) >= sm_count) ? 128 : 64;
+    // wide tiles for the transposed GRU projections (few rows = the layer's 6H gate units, very many columns)
+    if ((g.flags & GEMM_WIDE_N) && presplit && bn == 128 && g.n >= 256 * 8 &&
+        (int64_t)ceil_div(g.m, tc::BM) * ceil_div(g.n, 256) >= 2 * sm_count)
+        bn = 256;
     CUtensorMap map_a, map_amid, map_whi, map_wmid, map_c, map_cmid;
     if (presplit) {
         if (tc::make_map_bf16(&map_a, g.a_hi, g.m, g.k, g.lda, tc::BM)) return 1;
@@ -542,7 +554,7 @@ int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s) {
         if (tc::make_map(&map_c, g.c, g.m, g.n, g.ldc, 32)) return 1;
         map_cmid = map_c;
     }
-    const int64_t tiles = (int64_t)ceil_div(g.m, tc::BM) * (g.n / bn);
+    const int64_t tiles = (int64_t)ceil_div(g.m, tc::BM) * ceil_div(g.n, bn);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
 #define CTO_LAUNCH_GEMM(A)                                                                                             \
     tc::gemm_bf16x3_kernel<A><<<grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_amid, map_whi, map_wmid, map_c, map_cmid, g.bias, \

@@ -34,7 +34,8 @@ int launch_split_bf16(const float* w, uint16_t* hi, uint16_t* mid, int64_t n, cu
 int launch_join_bf16(const uint16_t* hi, const uint16_t* mid, float* out, int64_t n, cudaStream_t s);
 // the general form: A either fp32 (split by the kernel's converter warps) or already split into bf16 hi / mid
 // planes; W always pre-split, row stride ldw
-enum GemmFlags { GEMM_A_PRESPLIT = 1, GEMM_BIAS_PER_ROW = 2, GEMM_TILES_N_MAJOR = 4, GEMM_OUT_SPLIT = 8 };
+// GEMM_WIDE_N (with GEMM_A_PRESPLIT, many column tiles): 128 x 256 tiles in two 96 KB stages instead of 128 x 128 in three 64 KB
+enum GemmFlags { GEMM_A_PRESPLIT = 1, GEMM_BIAS_PER_ROW = 2, GEMM_TILES_N_MAJOR = 4, GEMM_OUT_SPLIT = 8, GEMM_WIDE_N = 16 };
 struct GemmTc {
     const float* a = nullptr;                          // fp32 A [m, k], row stride lda        (flags & A_PRESPLIT == 0)
     const uint16_t *a_hi = nullptr, *a_mid = nullptr;  // bf16 planes of A [m, k], row stride lda (flags & A_PRESPLIT)
@@ -50,6 +51,9 @@ struct GemmTc {
     int n = 0, k = 0, act = ACT_NONE, flags = 0;
 };
 int launch_gemm_tc_ex(const GemmTc& g, cudaStream_t s);
+// the transposed GRU input projection on CTA pairs with A resident in shared memory (gemm_pair.cu)
+bool gemm_pair_supported(const GemmTc& g);
+int launch_gemm_pair(const GemmTc& g, cudaStream_t s);
 
 // ld_out >= 34: row stride of the fp32 output (extra columns are zero-filled)
 int launch_rescale(const int16_t* x, const int32_t* depth, int64_t n, float* out, int ld_out, cudaStream_t s);

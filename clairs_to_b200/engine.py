@@ -298,7 +298,7 @@ class Engine:
 def gemm_nt(a, w, bias=None, residual=None, act=0, tensor_cores=True):
     """C = act(A @ W^T + bias) (+ residual) through ``cto_gemm_nt``: the dense-contraction building
     block of both networks, on tcgen05 (bf16x3) or on the fp32 CUDA-core kernel.  ``tensor_cores`` may
-    also be the integer mode mask of ``cto_gemm_nt`` (1 | 2 pre-split A | 4 split C | 8 bias per row)."""
+    also be the integer mode mask of ``cto_gemm_nt`` (1 | 2 pre-split A | 4 split C | 8 bias per row | 16 wide tiles)."""
     lib = _lib.lib()
     assert a.is_cuda and a.dtype == torch.float32 and w.dtype == torch.float32
     m, k = a.shape

@@ -129,7 +129,9 @@ int cto_posterior_from_probs(const double* tables_host, int n_heads, const doubl
  * block itself: C[m,n] = act(A[m,k] * W[n,k]^T + bias) (+ residual), act 0 none / 1 GELU(erf) / 2 SELU.
  * use_tensor_cores: 0 = fp32 CUDA cores; bit 0 = tensor cores, plus (the modes the engine uses between its
  * own kernels) bit 1 = A handed over as pre-split bf16 planes, bit 2 = C produced as bf16 planes, bit 3 =
- * bias indexed by the output row and n-major tile order (the transposed input projections of the GRU).
+ * bias indexed by the output row and n-major tile order (the transposed input projections of the GRU), bit 4 (with
+ * bit 1) = 128 x 256 output tiles when the problem has enough of them (ignored otherwise), bit 5 (with bits 1 and 3,
+ * k <= 256) = CTA pairs with A resident in shared memory (csrc/gemm_pair.cu; ignored when the shape does not fit).
  */
 int cto_engine_set_tensor_cores(cto_engine* e, int mode);
 /*

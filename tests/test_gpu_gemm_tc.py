@@ -83,3 +83,43 @@ def test_gemm_engine_modes(m, n, k, mode):
     err = (got.double() - want).abs().max().item()
     assert err < 2e-5 * max(scale, 1.0), (err, scale)
     assert torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("m,n,k", [(1152, 33 * 1024, 256), (1152, 33 * 1152, 256), (768, 33 * 1024 + 128, 64), (300, 256 * 400, 192)])
+def test_gemm_wide_tiles_are_bit_identical(m, n, k):
+    """GEMM_WIDE_N (128 x 256 tiles, two 96 KB stages: the transposed GRU input projections) accumulates every output
+    element over the same k-steps in the same order as the 128 x 128 walk: bit-identical, incl. a ragged last column tile
+    (n = 128 mod 256) and ragged row blocks."""
+    from clairs_to_b200.engine import gemm_nt
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) / np.sqrt(k)).cuda()
+    bias = torch.randn(m, generator=g).cuda()
+    plain = gemm_nt(a, w, bias, None, 0, tensor_cores=11)
+    for _ in range(2):
+        wide = gemm_nt(a, w, bias, None, 0, tensor_cores=27)
+        assert torch.equal(plain, wide)
+    want = a.double() @ w.double().t() + bias.double()[:, None]
+    scale = (a.double().abs() @ w.double().abs().t()).max().item()
+    assert (wide.double() - want).abs().max().item() < 2e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("m,n,k", [(1152, 33 * 1024, 256), (1152, 33 * 1152, 256), (768, 33 * 1024 + 128, 64), (300, 128 * 400, 192),
+                                   (1152, 33 * 1024 + 64, 256), (100, 128 * 600, 256)])
+def test_gemm_pair_is_bit_identical(m, n, k):
+    """csrc/gemm_pair.cu (CTA pairs, cta_group::2 M = 256, A resident, half a column tile per CTA): the transposed GRU
+    input projection.  Every output element is accumulated over the same k-steps in the same order as in gemm_tc.cu, so
+    the result is bit-identical -- incl. an odd number of row blocks (the last pair's second CTA lies beyond M), ragged
+    row blocks and a ragged last column tile."""
+    from clairs_to_b200.engine import gemm_nt
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) / np.sqrt(k)).cuda()
+    bias = torch.randn(m, generator=g).cuda()
+    plain = gemm_nt(a, w, bias, None, 0, tensor_cores=11)
+    for _ in range(3):
+        pair = gemm_nt(a, w, bias, None, 0, tensor_cores=11 | 32)
+        assert torch.equal(plain, pair)
+    want = a.double() @ w.double().t() + bias.double()[:, None]
+    scale = (a.double().abs() @ w.double().abs().t()).max().item()
+    assert (pair.double() - want).abs().max().item() < 2e-5 * max(scale, 1.0)
