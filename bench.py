@@ -102,9 +102,9 @@ class ClockSampler:
                     power_w_max=max(float(r[3]) for r in rows), window=window)
 
 
-TRAFFIC_KERNEL = {"neg_gru2_recurrent": "gru3_kernel<192", "neg_gru1_recurrent": "gru1_fused_kernel",
-                  "encoder": "encode_pileup_kernel", "aff_stage1_fused": "aff_stage1_kernel", "aff_layers_fused": "aff_layers_kernel",
-                  "neg_proj2_gemm": "gemm_bf16x3_kernel<0>"}
+TRAFFIC_KERNEL = {"neg_gru2_recurrent": "gru4_kernel<192", "neg_gru1_recurrent": "gru1_fused_kernel",
+                  "encoder": "encode_pileup_kernel", "aff_stage1_fused": "aff_stage1_kernel", "aff_layers_fused": "aff_layers_kernel<128",
+                  "neg_proj2_gemm": "gemm_pair_kernel"}
 
 
 def ncu_traffic(family, candidates_per_launch):

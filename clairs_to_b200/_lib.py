@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcto_b200.so")
 
 _lib = None
+ABI_VERSION = 2       # include/clairs_to_b200.h CTO_ABI_VERSION
 
 
 class HostStream(C.Structure):
@@ -83,6 +84,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.cto_abi_version() != ABI_VERSION:
+            raise CtoError("%s has ABI version %d, this package binds version %d: rebuild with "
+                           "`python -m clairs_to_b200.build --force`" % (LIB_PATH, handle.cto_abi_version(), ABI_VERSION))
         _lib = handle
     return _lib
 
