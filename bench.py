@@ -127,6 +127,20 @@ def ncu_traffic(family, candidates_per_launch):
     return None
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run on the host cores next to that GPU (NVML's ideal CPU affinity), so that the pinned
+    staging buffers are first-touched on the GPU's NUMA node and its H2D copies do not cross sockets.  Returns the number
+    of cores bound to, or None when NVML is not available (then the OS placement stands)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def synthetic_likelihood(n_heads, seed=1):
     import numpy as np
     rng = np.random.default_rng(seed)
@@ -303,6 +317,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
@@ -543,7 +558,7 @@ def main():
                                 heads=[h for h, _ in cfg["parts"]], engine_chunk=args.max_batch, weights="seeded random init",
                                 l2_policy="inputs (%.0f MB per step and GPU) larger than the 126 MB L2" % (sum(p["h2d"] for p in parts) / 1e6),
                                 parallelism="candidates sharded x%d, one gather of probabilities" % world,
-                                datagen_s=round(t_gen, 1)),
+                                host_cores_bound_to_gpu_numa_node=numa, datagen_s=round(t_gen, 1)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, cli=cli, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
     for eng_k, _ in engines:

@@ -439,16 +439,11 @@ __global__ void join_bf16_kernel(const uint16_t* __restrict__ hi, const uint16_t
 }
 
 // 2-D tiled tensor map with 128-byte swizzle; the box is (128 bytes of the inner dimension) x box_rows
-static int make_map_any(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* ptr, int64_t rows, int64_t cols,
-                        int64_t ld, int box_rows, int box_cols = 0, bool swizzle = true) {
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)(box_cols ? box_cols : 128 / elem_bytes), (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    // resolved through the runtime so that the library has no link-time dependency on libcuda
-    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled, resolved through the runtime so that the library has no link-time dependency on libcuda
+typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int get_encode(encode_fn* out) {
     static encode_fn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -457,12 +452,50 @@ static int make_map_any(CUtensorMap* map, CUtensorMapDataType dtype, int elem_by
         CTO_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
         encode = reinterpret_cast<encode_fn>(fn);
     }
+    *out = encode;
+    return 0;
+}
+
+// 2-D tiled tensor map with 128-byte swizzle; the box is (128 bytes of the inner dimension) x box_rows
+static int make_map_any(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* ptr, int64_t rows, int64_t cols,
+                        int64_t ld, int box_rows, int box_cols = 0, bool swizzle = true) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(box_cols ? box_cols : 128 / elem_bytes), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    encode_fn encode;
+    if (get_encode(&encode)) return 1;
     CUresult r = encode(map, dtype, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
                   (long long)cols, (long long)ld);
+        return 1;
+    }
+    return 0;
+}
+
+// un-swizzled fp32 map of rank 2..5 over a row-major [rows][ld] array: dimension 0 = columns, dimension i >= 1 walks rows with
+// a stride of row_stride[i - 1] rows (the views may overlap).  One TMA instruction then gathers a box of several row groups.
+int make_map_rows_nd(CUtensorMap* map, const float* ptr, int rank, int64_t cols, int64_t ld, const int64_t* dim_size,
+                     const int64_t* row_stride, const int* box) {
+    CTO_REQUIRE(rank >= 2 && rank <= 5, "make_map_rows_nd: rank %d", rank);
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t bx[5], estr[5] = {1, 1, 1, 1, 1};
+    dims[0] = (cuuint64_t)cols; bx[0] = (cuuint32_t)box[0];
+    for (int i = 1; i < rank; ++i) {
+        dims[i] = (cuuint64_t)dim_size[i - 1];
+        strides[i - 1] = (cuuint64_t)row_stride[i - 1] * (cuuint64_t)ld * 4;
+        bx[i] = (cuuint32_t)box[i];
+    }
+    encode_fn encode;
+    if (get_encode(&encode)) return 1;
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(ptr), dims, strides, bx, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (rank %d) failed (CUresult %d) cols=%lld ld=%lld", rank, (int)r, (long long)cols, (long long)ld);
         return 1;
     }
     return 0;

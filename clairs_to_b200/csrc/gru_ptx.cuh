@@ -47,6 +47,14 @@ __device__ __forceinline__ void g_tma_load_2d(const CUtensorMap* map, uint64_t* 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(g_smem_u32(dst)), "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void g_tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(g_smem_u32(dst)), "l"(map), "r"(g_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void g_prefetch_map(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void g_tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
@@ -138,6 +146,8 @@ __device__ __forceinline__ float g_tanh(float x) { return 1.0f - __fdividef(2.0f
 int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 int make_map_bf16(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 int make_map_plain(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
+int make_map_rows_nd(CUtensorMap* map, const float* ptr, int rank, int64_t cols, int64_t ld, const int64_t* dim_size,
+                     const int64_t* row_stride, const int* box);
 
 }  // namespace tc
 }  // namespace cto

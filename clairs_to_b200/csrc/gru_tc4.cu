@@ -150,10 +150,10 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     #define RTOC(i) do { if (tim) { long long _t1 = clock64(); tacc[i] += _t1 - _t0; _t0 = _t1; } } while (0)
     constexpr int KB = H / R_K;
     constexpr int NB = H / R_BLK;                              // 6 blocks of 32 units
-    constexpr int NSLOT = NB / 2;                              // 3 accumulator slots = block pairs
+    constexpr int NREG = 3;                                    // accumulator regions (one 32-unit block each) per chain
     constexpr int NHB = 2 * NB;                                // 12 half-blocks (8 units per thread each)
     constexpr int HBUF = Gru4Smem<H, XST, WST>::HBUF;
-    constexpr uint32_t STATE_COL = NSLOT * 2 * R_HALF;         // 288: fp32 state, 96 columns per chain
+    constexpr uint32_t STATE_COL = 2 * NREG * R_HALF;          // 288: fp32 state, 96 columns per chain
     static_assert(H == 192, "the slot / state layout below is written for H = 192 (288 + 2 * 96 <= 512 TMEM columns)");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (g_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -165,9 +165,9 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     uint64_t* empty = full + WST;                        // [6]
     uint64_t* xfull = empty + WST;                       // [chain][2]
     uint64_t* xempty = xfull + 2 * XST;                 // [chain][2]
-    uint64_t* slot_full = xempty + 2 * XST;             // [chain][3]  accumulators of a block pair complete (both CTAs)
-    uint64_t* slot_free = slot_full + 2 * NSLOT;              // [chain][3]  leader: loaded by the gate warps of BOTH CTAs
-    uint64_t* h_ready = slot_free + 2 * NSLOT;                // [chain]     leader: h_t tiles written in BOTH CTAs
+    uint64_t* acc_full = xempty + 2 * XST;              // [chain][3]  accumulators of a block complete (both CTAs)
+    uint64_t* acc_free = acc_full + 2 * NREG;                 // [chain][3]  leader: loaded by the gate warps of BOTH CTAs
+    uint64_t* h_ready = acc_free + 2 * NREG;                  // [chain]     leader: h_t tiles written in BOTH CTAs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 2);
     float* s_bhn = reinterpret_cast<float*>(bars + 48);       // 384 bytes of barriers
 
@@ -181,9 +181,10 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < WST; ++s) { g_mbar_init(&full[s], 1); g_mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2 * XST; ++s) { g_mbar_init(&xfull[s], 1); g_mbar_init(&xempty[s], 4); }
-        for (int s = 0; s < 2 * NSLOT; ++s) { g_mbar_init(&slot_full[s], 1); g_mbar_init(&slot_free[s], 8); }
+        for (int s = 0; s < 2 * NREG; ++s) { g_mbar_init(&acc_full[s], 1); g_mbar_init(&acc_free[s], 8); }
         for (int c = 0; c < 2; ++c) g_mbar_init(&h_ready[c], 8);           // one arrive per gate warp of the chain in BOTH CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        g_prefetch_map(&tma_whi); g_prefetch_map(&tma_wmid); g_prefetch_map(&tma_x);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(512));
@@ -196,10 +197,10 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ---- W producer: this CTA's half of every W block, once per chain-step, in the MMA order ----
+        // ---- W producer: this CTA's half of every W block, ONCE PER STEP: both chains use the stage ----
         uint32_t it = 0;
         bool alive = true;
-        for (int cs = 0; cs < 2 * N_POS && alive; ++cs) {
+        for (int cs = 0; cs < N_POS && alive; ++cs) {
             for (int blk = 0; blk < NB && alive; ++blk) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % WST;
@@ -217,53 +218,55 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
         }
     } else if (warp == 1) {
         if (leader) {
-            // ---- MMA issuer (leader CTA only): chain-steps alternate between the two chains ----
+            // ---- MMA issuer (leader CTA only).  Per step and 32-unit block: chain 0's products, then chain 1's, on the SAME
+            // W stages (the weights are those of the step, not of the chain): W goes through L2 once per step instead of
+            // once per chain-step, and the chains stay one block apart, so each one's gate math runs under the other's MMAs.
             // D=f32, A=B=bf16, K-major, M=128 (64 rows per CTA), N=96
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(R_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             uint32_t it = 0;
             bool alive = true;
             RTIC;
             for (int step = 0; step < N_POS && alive; ++step) {
-                for (int c = 0; c < 2 && alive; ++c) {
-                    if (!r_wait(&h_ready[c], step & 1, true, RB_HREADY, dbg)) { alive = false; break; }   // h_{t-1} of chain c in BOTH CTAs
-                    RTOC(0);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint8_t* hb = hbuf + c * HBUF;
-                    const int n_use = step * 2 + c;                        // chain-step index: slot s was last used by chain-step n_use - 1
-                    for (int s = 0; s < NSLOT && alive; ++s) {
-                        if (n_use >= 1) {
-                            const int k = c == 0 ? step - 1 : step;         // that chain's step
-                            if (!r_wait(&slot_free[(c ^ 1) * NSLOT + s], k & 1, true, RB_SLOTFREE, dbg)) { alive = false; break; }
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int blk = 0; blk < NB && alive; ++blk, it += KB) {
+                    const int r = blk % NREG, u = step * 2 + blk / NREG;       // accumulator region of the chain, and its use count
+                    for (int c = 0; c < 2 && alive; ++c) {
+                        if (blk == 0) {                                        // h_{t-1} of chain c in BOTH CTAs
+                            if (!r_wait(&h_ready[c], step & 1, true, RB_HREADY, dbg)) { alive = false; break; }
+                            RTOC(0);
+                        }
+                        if (u >= 1) {                                          // the chain's gate warps have loaded the region's previous block
+                            if (!r_wait(&acc_free[c * NREG + r], (u - 1) & 1, true, RB_SLOTFREE, dbg)) { alive = false; break; }
                             RTOC(1);
                         }
-                        for (int b2 = 0; b2 < 2 && alive; ++b2) {
-                            const int blk = 2 * s + b2;
-                            const uint32_t acc = tmem_base + (uint32_t)(blk * R_HALF);
-                            for (int kb = 0; kb < KB; ++kb, ++it) {
-                                const int ws = it % WST;
-                                if (!r_wait(&full[ws], (it / WST) & 1, false, RB_WFULL, dbg)) { alive = false; break; }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint8_t* hb = hbuf + c * HBUF;
+                        const uint32_t acc = tmem_base + (uint32_t)((c * NREG + r) * R_HALF);
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const uint32_t wi = it + kb;
+                            const int ws = wi % WST;
+                            if (c == 0) {
+                                if (!r_wait(&full[ws], (wi / WST) & 1, false, RB_WFULL, dbg)) { alive = false; break; }
                                 RTOC(2);
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                const uint64_t d_hhi = g_desc_k_sw128(g_smem_u32(hb + kb * R_HTILE));
-                                const uint64_t d_hmid = g_desc_k_sw128(g_smem_u32(hb + (KB + kb) * R_HTILE));
-                                const uint32_t w_addr = g_smem_u32(wring + ws * R_STAGE);
-                                const uint64_t d_whi = g_desc_k_sw128(w_addr);
-                                const uint64_t d_wmid = g_desc_k_sw128(w_addr + R_WTILE);
-                                if (g_elect_one()) {
-                                    #pragma unroll
-                                    for (int k = 0; k < R_K / 16; ++k) {
-                                        const uint64_t o = (uint64_t)(k * 2);          // 16 bf16 = 32 bytes along the swizzle row
-                                        r_mma_2sm(acc, d_hhi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
-                                        r_mma_2sm(acc, d_hmid + o, d_whi + o, idesc, 1u);
-                                        r_mma_2sm(acc, d_hhi + o, d_wmid + o, idesc, 1u);
-                                    }
-                                    r_commit_2sm(&empty[ws]);                  // stage free in both CTAs
-                                    if (b2 == 1 && kb == KB - 1) r_commit_2sm(&slot_full[c * NSLOT + s]);
-                                }
-                                __syncwarp();
-                                RTOC(3);
                             }
+                            const uint64_t d_hhi = g_desc_k_sw128(g_smem_u32(hb + kb * R_HTILE));
+                            const uint64_t d_hmid = g_desc_k_sw128(g_smem_u32(hb + (KB + kb) * R_HTILE));
+                            const uint32_t w_addr = g_smem_u32(wring + ws * R_STAGE);
+                            const uint64_t d_whi = g_desc_k_sw128(w_addr);
+                            const uint64_t d_wmid = g_desc_k_sw128(w_addr + R_WTILE);
+                            if (g_elect_one()) {
+                                #pragma unroll
+                                for (int k = 0; k < R_K / 16; ++k) {
+                                    const uint64_t o = (uint64_t)(k * 2);          // 16 bf16 = 32 bytes along the swizzle row
+                                    r_mma_2sm(acc, d_hhi + o, d_whi + o, idesc, (kb | k) ? 1u : 0u);
+                                    r_mma_2sm(acc, d_hmid + o, d_whi + o, idesc, 1u);
+                                    r_mma_2sm(acc, d_hhi + o, d_wmid + o, idesc, 1u);
+                                }
+                                if (c == 1) r_commit_2sm(&empty[ws]);      // both chains are through: stage free in both CTAs
+                                if (kb == KB - 1) r_commit_2sm(&acc_full[c * NREG + r]);
+                            }
+                            __syncwarp();
+                            RTOC(3);
                         }
                     }
                 }
@@ -285,14 +288,11 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                 const int s = q % XST;
                 if (!r_wait(&xempty[c * XST + s], ((q / XST) & 1) ^ 1, false, RB_XEMPTY, dbg)) { alive = false; break; }
                 if (g_elect_one()) {
+                    // ONE 4-d box = (64 candidates, 8 units, 2 unit groups 16 rows apart, 3 gates H rows apart): issuing a TMA
+                    // instruction costs the producer ~135 cycles, six 2-d boxes per half-block made it the pace setter
                     g_mbar_expect_tx(&xfull[c * XST + s], R_XSTAGE);
-                    float* st = ring + s * (R_XSTAGE / 4);
-                    #pragma unroll
-                    for (int g = 0; g < 3; ++g)
-                        #pragma unroll
-                        for (int u2 = 0; u2 < 2; ++u2)
-                            g_tma_load_2d(&tma_x, &xfull[c * XST + s], st + (g * 2 + u2) * (8 * R_M), (int)(t * bp) + b0,
-                                          dir * 3 * H + g * H + (hb >> 1) * R_BLK + u2 * 16 + (hb & 1) * 8);
+                    g_tma_load_4d(&tma_x, &xfull[c * XST + s], ring + s * (R_XSTAGE / 4), (int)(t * bp) + b0,
+                                  dir * 3 * H + (hb >> 1) * R_BLK + (hb & 1) * 8, 0, 0);
                 }
                 __syncwarp();
             }
@@ -341,24 +341,21 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
             const int64_t orow = (b * osb + t * ost) * (int64_t)(2 * H) + dir * H;
             #pragma unroll 1
             for (int blk = 0; blk < NB; ++blk) {
-                const int s = blk >> 1;
-                if ((blk & 1) == 0) {                          // first block of a slot: its accumulators have to be complete
-                    if (!r_wait(&slot_full[c * NSLOT + s], step & 1, false, RB_SLOTFULL, dbg)) { alive = false; break; }
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
+                const int r = blk % NREG;
+                // the block's accumulators: second use of the region in this step for blk >= 3
+                if (!r_wait(&acc_full[c * NREG + r], (uint32_t)(step * 2 + blk / NREG) & 1, false, RB_SLOTFULL, dbg)) { alive = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 RTOC(1);
-                // block blk: accumulator columns [48*blk, +48) = r(16) z(16) n(16) of this lane's 16 units, and their state
-                const uint32_t tcol = tmem_base + lanes + (uint32_t)(blk * R_HALF);
+                // region r of this chain: columns [48 * (3c + r), +48) = r(16) z(16) n(16) of this lane's 16 units; and their state
+                const uint32_t tcol = tmem_base + lanes + (uint32_t)((c * NREG + r) * R_HALF);
                 uint32_t acc[48], hs[16];
                 r_tmem_ld32(tcol, acc);
                 r_tmem_ld16(tcol + 32, acc + 32);
                 r_tmem_ld16(state + (uint32_t)(blk * 16), hs);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (blk & 1) {                                 // second block of the slot: hand it to the other chain
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) r_arrive_leader(&slot_free[c * NSLOT + s]);
-                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the region goes back to the MMA warp
+                __syncwarp();
+                if (lane == 0) r_arrive_leader(&acc_free[c * NREG + r]);
                 RTOC(2);
                 uint4 ohi[2], omid[2];
                 #pragma unroll
@@ -369,6 +366,7 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                     const int xs = xq % XST;
                     float xv[24];
                     if (!r_wait(&xfull[c * XST + xs], (xq / XST) & 1, false, RB_XFULL, dbg)) { alive = false; break; }
+                    RTOC(0);
                     const float* xp = ring + xs * (R_XSTAGE / 4) + uhalf * (8 * R_M) + m;
                     #pragma unroll
                     for (int g = 0; g < 3; ++g)
@@ -384,7 +382,7 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                     for (int i = 0; i < 24; ++i) dep |= __float_as_uint(xv[i]);
                     __syncwarp();
                     if (lane == 0) g_mbar_arrive(&xempty[c * XST + xs] + (dep & (uint32_t)zero));
-                    RTOC(0);
+                    RTOC(5);
                     const float4 bn0 = *reinterpret_cast<const float4*>(s_bhn + uu);
                     const float4 bn1 = *reinterpret_cast<const float4*>(s_bhn + uu + 4);
                     const float bnv[8] = {bn0.x, bn0.y, bn0.z, bn0.w, bn1.x, bn1.y, bn1.z, bn1.w};
@@ -401,8 +399,8 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                     r_split2(hv[2], hv[3], hi.y, mid.y);
                     r_split2(hv[4], hv[5], hi.z, mid.z);
                     r_split2(hv[6], hv[7], hi.w, mid.w);
-                    if (s == NSLOT - 1) {
-                        // last slot complete = every MMA of this chain-step has retired: these tiles may be overwritten now
+                    if (blk == NB - 1) {
+                        // last block complete = every MMA of this chain-step has retired: these tiles may be overwritten now
                         const uint32_t to = tile_off(uu);
                         *reinterpret_cast<uint4*>(hb_hi + to) = hi;
                         *reinterpret_cast<uint4*>(hb_mid + to) = mid;
@@ -420,11 +418,11 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                 RTOC(4);
             }
             if (!alive) break;
-            // the h tiles of the first two slots: their gate math ran while later MMAs of the step were still reading
+            // the h tiles of the other blocks: their gate math ran while later MMAs of the step were still reading
             // h_{t-1}; rebuilt now from the state in tensor memory
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             #pragma unroll 1
-            for (int blk = 0; blk < NB - 2; ++blk) {
+            for (int blk = 0; blk < NB - 1; ++blk) {
                 uint32_t hs[16];
                 r_tmem_ld16(state + (uint32_t)(blk * 16), hs);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -473,7 +471,11 @@ int launch_gru4(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_h
     CUtensorMap map_hi, map_mid, map_x;
     if (tc::make_map_bf16(&map_hi, w_hi, 6 * hidden, hidden, hidden, tc::R_HALF)) return 1;
     if (tc::make_map_bf16(&map_mid, w_mid, 6 * hidden, hidden, hidden, tc::R_HALF)) return 1;
-    if (tc::make_map_plain(&map_x, xproj, 6 * hidden, ldx, ldx, 8, tc::R_M)) return 1;          // box: 8 units x 64 candidates
+    {   // projection box: 64 candidates x (8 units, 2 unit groups 16 rows apart, 3 gates `hidden` rows apart) in one instruction
+        const int64_t dim_size[3] = {6 * hidden, 2, 3}, row_stride[3] = {1, 16, hidden};
+        const int box[4] = {tc::R_M, 8, 2, 3};
+        if (tc::make_map_rows_nd(&map_x, xproj, 4, ldx, ldx, dim_size, row_stride, box)) return 1;
+    }
     const int pairs = ceil_div(batch, 256);
     long long* timing = (g_gemm_debug && g_gemm_timing) ? g_gemm_timing + 32 : nullptr;
     cudaLaunchConfig_t cfg = {};
@@ -487,10 +489,10 @@ int launch_gru4(const float* xproj, int64_t ldx, int64_t bp, const uint16_t* w_h
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    // ring depths: 3 projection stages per chain + 4 W stages; 2 + 6 measured the same (profiles/r2_gru4_phase.txt)
-    CTO_CHECK(set_max_dynamic_smem(tc::gru4_kernel<192, 3, 4>, tc::Gru4Smem<192, 3, 4>::TOTAL));
-    cfg.dynamicSmemBytes = tc::Gru4Smem<192, 3, 4>::TOTAL;
-    CTO_CHECK(cudaLaunchKernelEx(&cfg, tc::gru4_kernel<192, 3, 4>, map_hi, map_mid, map_x, bp, bhn, out_hi, out_mid, osb, ost, batch, dbg, timing, 0));
+    // ring depths: 2 projection stages per chain + 6 W stages (a block's three stages serve both chains, three more in flight)
+    CTO_CHECK(set_max_dynamic_smem(tc::gru4_kernel<192, 2, 6>, tc::Gru4Smem<192, 2, 6>::TOTAL));
+    cfg.dynamicSmemBytes = tc::Gru4Smem<192, 2, 6>::TOTAL;
+    CTO_CHECK(cudaLaunchKernelEx(&cfg, tc::gru4_kernel<192, 2, 6>, map_hi, map_mid, map_x, bp, bhn, out_hi, out_mid, osb, ost, batch, dbg, timing, 0));
     CTO_CHECK(cudaGetLastError());
     count_launch();
     return 0;
