@@ -1,26 +1,29 @@
 // GRU recurrence, fourth generation: TWO independent recurrence chains per CTA pair, so that the gate math of one
 // chain runs while the tensor cores work on the other.
 //
-// What the phase counters of gru_tc3.cu showed (profiles/r2_gru_phase.txt, H = 192, one chain per CTA pair): per step the
+// What the phase counters of gru_tc3.cu showed (profiles/r2_gru4_phase.txt, H = 192, one chain per CTA pair): per step the
 // MMA warp is busy ~7 000 cycles and then WAITS ~9 000 cycles for the gate math, because h_t must be complete before
-// the products of step t+1 can start -- the tensor pipe idles 56 % of the time, and neither fewer gate instructions nor
-// removing the MUFU work changed that.  The dependency is inherent to ONE chain; two chains interleave perfectly:
-//
-//     tensor pipe :  A.mma(t)   B.mma(t)   A.mma(t+1)   B.mma(t+1)  ...
-//     gate warps  :             A.gate(t)  B.gate(t)    A.gate(t+1) ...      (4 warps per chain)
+// the products of step t+1 can start -- the tensor pipe idles 56 % of the time.  The dependency is inherent to ONE chain.
 //
 // Chain c of a CTA pair owns 128 candidates (64 per CTA; [pair * 256 + c * 128, +128)) of direction blockIdx.y.
-// Resources that made this impossible in round 1, and how they fit now:
-//   * tensor memory: a chain-step needs 288 accumulator columns (6 blocks x 48), two would need 576 > 512.  The
-//     accumulators live in THREE 96-column slots (one per pair of 32-unit blocks) that the chains use alternately:
-//     slot s is handed from chain to chain as soon as the gate warps have loaded it; that frees 192 columns for ...
-//   * ... the fp32 state h itself, kept in tensor memory (96 columns per chain: each thread owns one TMEM lane and
-//     reads / writes its 96 units with tcgen05.ld / st) instead of 96 registers per thread;
-//   * shared memory: h_t tiles (bf16 hi / mid, the A operand) are SINGLE buffered per chain (2 x 48 KB): the new tiles
-//     are written in a short second pass after the chain's last accumulator has arrived, i.e. when every MMA that reads
-//     the old tiles has retired.  W ring (72 KB) and two 2-stage projection rings (48 KB) as before.
+//   * MMA order: per step and 32-unit block, chain 0's products, then chain 1's, on the SAME W stages (the weights belong
+//     to the step, not to the chain): W passes through L2 once per step, and the chains stay one block apart.
+//   * tensor memory: every chain has THREE accumulator regions of 48 columns (one block each), used cyclically for blocks
+//     (0, 3), (1, 4), (2, 5); a region goes back to the MMA warp as soon as the chain's gate warps have loaded it.  That
+//     leaves 192 columns for the fp32 state h itself (96 per chain: each thread owns one TMEM lane and reads / writes its
+//     96 units with tcgen05.ld / st) instead of 96 registers per thread;
+//   * shared memory: h_t tiles (bf16 hi / mid, the A operand) are SINGLE buffered per chain (2 x 48 KB): the tiles of the
+//     last block are written directly (all MMAs of the chain-step have retired by then), the others in a short second
+//     pass from the state in tensor memory.  W ring 6 x 12 KB, projection ring 2 x 12 KB per chain, filled by one 4-d TMA
+//     box per half-block (a TMA instruction costs its issuing warp ~135 cycles);
+//   * the projection stage goes back to its producer with an arrive that is DATA DEPENDENT on the loaded values
+//     (profiles/r2_gru4_race.txt).
+// Measured: the kernel is bound by shared-memory bandwidth (per step, in 128-byte wavefronts: MMA operands 12 k, W stages
+// 1.7 k, projection in 2.3 k + out 2.3 k, h tiles 0.8 k against a step of ~20 k cycles).  Reading the projection with
+// per-thread global loads instead (no shared memory at all) was built and is slower: one half-block of register
+// look-ahead does not cover the latency, two do not fit in 168 registers.
 // Arithmetic, the weight / projection layouts, the thread <-> (candidate, unit) mapping and the output planes are those
-// of gru_tc3.cu (torch.nn.GRU semantics, clairs/model.py:412-417); see there.
+// of gru_tc3.cu (torch.nn.GRU semantics, clairs/model.py:412-417); the two kernels are bit-identical (tests/test_gpu_gru.py).
 #include "gru_ptx.cuh"
 
 namespace cto {
@@ -366,7 +369,6 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                     const int xs = xq % XST;
                     float xv[24];
                     if (!r_wait(&xfull[c * XST + xs], (xq / XST) & 1, false, RB_XFULL, dbg)) { alive = false; break; }
-                    RTOC(0);
                     const float* xp = ring + xs * (R_XSTAGE / 4) + uhalf * (8 * R_M) + m;
                     #pragma unroll
                     for (int g = 0; g < 3; ++g)
@@ -382,7 +384,7 @@ gru4_kernel(const __grid_constant__ CUtensorMap tma_whi, const __grid_constant__
                     for (int i = 0; i < 24; ++i) dep |= __float_as_uint(xv[i]);
                     __syncwarp();
                     if (lane == 0) g_mbar_arrive(&xempty[c * XST + xs] + (dep & (uint32_t)zero));
-                    RTOC(5);
+                    RTOC(0);
                     const float4 bn0 = *reinterpret_cast<const float4*>(s_bhn + uu);
                     const float4 bn1 = *reinterpret_cast<const float4*>(s_bhn + uu + 4);
                     const float bnv[8] = {bn0.x, bn0.y, bn0.z, bn0.w, bn1.x, bn1.y, bn1.z, bn1.w};
