@@ -41,7 +41,7 @@ for n in (1000, 4096, 33334):
                     print("   candidate", c0, "dir", d, "first wrong t", first, "units at that t", np.unique(u[ds & (t == first)] % H)[:24],
                           "pair", c0 // 256, "chain", (c0 // 128) & 1, "cta", (c0 // 64) & 1, "m", c0 % 64)
     print("n", n, "reps", reps, "bad reps", nbad, "status", eng.fused_status())
-buf = torch.zeros(64, dtype=torch.int64, device='cuda')
+buf = torch.zeros(128, dtype=torch.int64, device='cuda')
 lib.cto_debug_timing(C.c_void_p(buf.data_ptr())); lib.cto_debug_set(1)
 for two in (0, 1):
     for _ in range(2): eng.neg_recurrence(xp, n, two_chains=two)

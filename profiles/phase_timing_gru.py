@@ -7,7 +7,7 @@ from oracle import nn_oracle
 The last kernel launched before the read is GRU-2 (H=192) of the last chunk."""
 lib = _lib.lib()
 lib.cto_debug_timing.argtypes = [C.c_void_p]
-buf = torch.zeros(64, dtype=torch.int64, device='cuda')      # [0,32) GEMM kernels, [32,64) GRU kernel
+buf = torch.zeros(128, dtype=torch.int64, device='cuda')      # [0,32) GEMM kernels, [32,64) GRU kernel
 aff_sd = nn_oracle.synth_state_dict(nn_oracle.aff_state_dict_shapes(4), 104)
 neg_sd = nn_oracle.synth_state_dict(nn_oracle.neg_state_dict_shapes(4), 204)
 n = 37888

@@ -6,7 +6,7 @@ from clairs_to_b200 import _lib
 from clairs_to_b200.engine import gemm_nt
 lib = _lib.lib()
 lib.cto_debug_timing.argtypes = [C.c_void_p]
-buf = torch.zeros(64, dtype=torch.int64, device='cuda')
+buf = torch.zeros(128, dtype=torch.int64, device='cuda')
 lib.cto_debug_timing(C.c_void_p(buf.data_ptr()))
 names = ["prod.wait_empty","prod.issue","-","-","mma.wait_acc_empty","mma.wait_full","mma.wait_conv","mma.issue+commit",
          "conv.wait_full","conv.math","conv.fence","-","epi.wait_acc_full","epi.tmem_ld","epi.waitgrp+bar","epi.math+sts","epi.fence","epi.bar2"]
