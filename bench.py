@@ -103,7 +103,7 @@ class ClockSampler:
 
 
 TRAFFIC_KERNEL = {"neg_gru2_recurrent": "gru4_kernel<192", "neg_gru1_recurrent": "gru1_fused_kernel",
-                  "encoder": "encode_pileup_kernel", "aff_stage1_fused": "aff_stage1_kernel", "aff_layers_fused": "aff_layers_kernel<128",
+                  "encoder": "encode_pileup_kernel", "aff_stage1_fused": "aff_stage1_kernel", "aff_layers_fused": "aff_layers_kernel<64", "aff_layers_fused_last": "aff_layers_kernel<128",
                   "neg_proj2_gemm": "gemm_pair_kernel"}
 
 
@@ -450,6 +450,9 @@ def main():
         enc["traffic"] = enc_tr
         enc["algorithmic_bytes_per_launch"] = enc_bytes / n_enc_launches
     tensor_fams = [f for f in fam if f["flop_per_candidate"] > 0]
+    for f in tensor_fams:                                # algorithmic rate of every contraction family, against the same peak
+        f["tflops"] = f["flop_per_candidate"] * f["candidates_per_step"] / (f["ms_per_step"] * 1e-3) / 1e12
+        f["frac"] = f["tflops"] / peaks["tensor_sustained"]
     top = max(tensor_fams, key=lambda f: f["ms_per_step"])
     per_launch_ms = top["ms_per_step"] / top["launches_per_step"]
     cand_per_launch = top["candidates_per_step"] / top["launches_per_step"]

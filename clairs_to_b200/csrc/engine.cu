@@ -271,30 +271,30 @@ void engine_free(Engine& e) {
 }
 
 const char* prof_kind_name(int kind) {
-    static const char* names[PK_COUNT] = {"aff_forward", "aff_stage1_fused", "aff_gemm_1x1", "aff_embed_conv", "aff_channel_ln", "aff_dwconv", "aff_attention", "aff_layers_fused",
+    static const char* names[PK_COUNT] = {"aff_forward", "aff_stage1_fused", "aff_gemm_1x1", "aff_embed_conv", "aff_channel_ln", "aff_dwconv", "aff_attention", "aff_layers_fused", "aff_layers_fused_last",
                                           "aff_heads", "neg_proj1_gemm", "neg_gru1_recurrent", "neg_proj2_gemm",
                                           "neg_gru2_recurrent", "neg_fc1_gemm", "neg_heads"};
     return (kind >= 0 && kind < PK_COUNT) ? names[kind] : "?";
 }
 
 // AFF FLOP per candidate (multiply-add = 2 FLOP, 3-tap convolutions, attention products included):
-// part 0 = everything, 1 = the transformer layers of the stages that run in the fused kernel, 2 = first stage when it
-// runs in the CUDA-core fused kernel, 3 = heads
+// part 0 = everything, 1 = the transformer layers of the stages that run in the fused kernel (4 = those of the LAST stage, which
+// is a different kernel instantiation and reported apart), 2 = first stage when it runs in the CUDA-core fused kernel, 3 = heads
 static double aff_flops(const Engine& e, int part) {
     const AffModel& m = e.aff;
-    double total = 0.0, layers_fused = 0.0, stage1 = 0.0;
+    double total = 0.0, layers_fused = 0.0, layers_last = 0.0, stage1 = 0.0;
     for (int s = 0; s < m.n_stages; ++s) {
         const CvtStage& st = m.st[s];
         const double c = st.c, inner = st.heads * DIM_HEAD, w = st.wout, wkv = st.wkv;
         const double embed = 2.0 * w * 3 * st.cin * c;
         const double layer = 2.0 * (w * c * inner + wkv * c * 2 * inner + 2.0 * st.heads * w * wkv * DIM_HEAD + w * inner * c + 2.0 * w * c * 4 * c);
         total += embed + st.depth * layer;
-        if (st.fused_stream) layers_fused += st.depth * layer;
+        if (st.fused_stream) (s == m.n_stages - 1 ? layers_last : layers_fused) += st.depth * layer;
         if (s == 0 && aff_stage1_fused_supported(st)) stage1 = embed + st.depth * layer;
     }
     const double heads = 2.0 * (m.feat * FC_DIM + m.n_heads * (FC_DIM * FC_DIM + 2 * FC_DIM));
     total += heads;
-    return part == 0 ? total : (part == 1 ? layers_fused : (part == 2 ? stage1 : heads));
+    return part == 0 ? total : (part == 1 ? layers_fused : (part == 2 ? stage1 : (part == 4 ? layers_last : heads)));
 }
 
 // multiply-add = 2 FLOP; matches SURVEY.md section 8(d) accounting
@@ -304,9 +304,10 @@ double prof_kind_flops_per_candidate(const Engine& e, int kind) {
     switch (kind) {
         case PK_AFF: return aff_flops(e, 0);
         case PK_AFF_LAYERS: return e.use_tc && e.use_fused ? aff_flops(e, 1) : 0.0;
+        case PK_AFF_LAYERS_LAST: return e.use_tc && e.use_fused ? aff_flops(e, 4) : 0.0;
         case PK_AFF_STAGE1: return aff_flops(e, 2);
         case PK_AFF_HEADS: return aff_flops(e, 3);
-        case PK_NEG_PROJ1: return 2.0 * t * l[0].in_dim * 6 * l[0].hidden;
+        case PK_NEG_PROJ1: return (e.neg.fuse_l1 && e.use_tc) ? 0.0 : 2.0 * t * l[0].in_dim * 6 * l[0].hidden;   // fused: counted under PK_NEG_GRU1, this family is the input split
         case PK_NEG_GRU1: return 2.0 * t * l[0].hidden * 6 * l[0].hidden + (e.neg.fuse_l1 && e.use_tc ? 2.0 * t * l[0].in_dim * 6 * l[0].hidden : 0.0);
         case PK_NEG_PROJ2: return 2.0 * t * l[1].in_dim * 6 * l[1].hidden;
         case PK_NEG_GRU2: return 2.0 * t * l[1].hidden * 6 * l[1].hidden;
@@ -409,7 +410,7 @@ static int aff_stage_layers(Engine& e, const CvtStage& st, int64_t n, cudaStream
     // kernels that only feed a GEMM travel as bf16 hi / mid planes (no converter pass in the GEMM)
     if (e.use_tc && e.use_fused && st.fused_stream) {
         // every transformer layer of the stage in one tcgen05 kernel, x stays in tensor memory (aff_fused.cu)
-        TIMED(PK_AFF_LAYERS, launch_aff_layers(st, e.a_xs, n, e.fused_dbg, s));
+        TIMED((&st == &m.st[m.n_stages - 1]) ? PK_AFF_LAYERS_LAST : PK_AFF_LAYERS, launch_aff_layers(st, e.a_xs, n, e.fused_dbg, s));
         return 0;
     }
     const bool planes = e.use_tc && c % 64 == 0;

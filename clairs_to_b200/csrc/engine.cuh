@@ -104,7 +104,7 @@ struct Engine {
     std::vector<cudaEvent_t> ev_free;
 };
 
-enum ProfKind { PK_AFF = 0, PK_AFF_STAGE1, PK_AFF_GEMM, PK_AFF_EMBED, PK_AFF_LN, PK_AFF_DWCONV, PK_AFF_ATTENTION, PK_AFF_LAYERS, PK_AFF_HEADS, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
+enum ProfKind { PK_AFF = 0, PK_AFF_STAGE1, PK_AFF_GEMM, PK_AFF_EMBED, PK_AFF_LN, PK_AFF_DWCONV, PK_AFF_ATTENTION, PK_AFF_LAYERS, PK_AFF_LAYERS_LAST, PK_AFF_HEADS, PK_NEG_PROJ1, PK_NEG_GRU1, PK_NEG_PROJ2, PK_NEG_GRU2, PK_NEG_FC1, PK_NEG_HEADS, PK_COUNT };
 const char* prof_kind_name(int kind);
 double prof_kind_flops_per_candidate(const Engine& e, int kind);
 int prof_begin(Engine& e, int kind, cudaStream_t s);
