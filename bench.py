@@ -232,6 +232,107 @@ def cli_leg(n_chunk, n_heads, likelihood, host_threads):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def scan_leg(raw, peaks, dev, steps=5):
+    """the STEP-1 candidate scan (src/extract_candidates_calling.py:55-169, 335-377) over whole-chunk
+    mpileup text.  Device resident (text in HBM: row index + scan kernels, CUDA events), end to end from pinned host text
+    (cto_scan_candidates_host: 32 MB pieces, copy under compute) and the CPU port on a bounded sample of the same rows."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from clairs_to_b200 import _lib, synth
+    from clairs_to_b200 import extract_candidates_calling as ecc
+    lib = _lib.lib()
+    aff, aff_aux, neg, neg_aux = raw
+    text = synth.render_mpileup_text(neg, neg_aux)
+    reference = ''.join("ACGT"[c] for c in neg.ref_code)
+    n_bytes = len(text)
+    host = torch.frombuffer(bytearray(text), dtype=torch.uint8).pin_memory()
+    d_text = torch.zeros(n_bytes + 32, dtype=torch.uint8, device=dev)
+    d_text[:n_bytes].copy_(host)
+    cap = text.count(b"\n") + 1
+    row_off = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+    ref = torch.frombuffer(bytearray(reference.encode()), dtype=torch.uint8).to(dev)
+    pos = torch.empty(cap, dtype=torch.int32, device=dev)
+    depth = torch.empty(cap, dtype=torch.int32, device=dev)
+    flags = torch.empty(cap, dtype=torch.uint8, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n = C.c_int64()
+    over = C.c_int32()
+    kw = dict(min_coverage=4.0, snv_min_af=0.05, indel_min_af=0.05, alt=3, select_indel=1)
+    p = lambda t: C.c_void_p(t.data_ptr())
+
+    def index():
+        _lib.check(lib.cto_index_rows(p(d_text), n_bytes, p(row_off), cap, C.byref(n), stream), "cto_index_rows")
+
+    def scan():
+        _lib.check(lib.cto_scan_candidates(p(d_text), n_bytes, p(row_off), n.value, p(ref), 1001, len(reference), kw["min_coverage"],
+                                           kw["snv_min_af"], kw["indel_min_af"], kw["alt"], kw["select_indel"], p(pos), p(depth), p(flags),
+                                           C.byref(over), stream), "cto_scan_candidates")
+
+    for _ in range(2):
+        index()
+        scan()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_idx = t_scan = 0.0
+    for _ in range(steps):
+        ev[0].record()
+        index()
+        ev[1].record()
+        scan()
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_idx += ev[0].elapsed_time(ev[1])
+        t_scan += ev[1].elapsed_time(ev[2])
+    t_idx, t_scan = t_idx / steps, t_scan / steps
+    n_rows = n.value
+    dev_flags = flags[:n_rows].cpu().numpy()
+    # end to end from pinned host text
+    out = ecc.scan_mpileup(host, reference, 1001, 4.0, 0.05, 0.05, 3, True)
+    assert np.array_equal(out[2], dev_flags)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hp, hd, hf = (np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.uint8))
+    hn, hov = C.c_int64(), C.c_int64()
+    refb = reference.encode()
+
+    def host_call():
+        _lib.check(lib.cto_scan_candidates_host(C.c_void_p(host.data_ptr()), n_bytes, C.cast(C.c_char_p(refb), C.c_void_p), 1001, len(refb),
+                                                4.0, 0.05, 0.05, 3, 1, cap, C.c_void_p(hp.ctypes.data), C.c_void_p(hd.ctypes.data),
+                                                C.c_void_p(hf.ctypes.data), C.byref(hn), C.byref(hov), stream), "cto_scan_candidates_host")
+
+    host_call()
+    e0.record()
+    for _ in range(steps):
+        host_call()
+    e1.record()
+    torch.cuda.synchronize()
+    t_host = e0.elapsed_time(e1) / steps
+    # CPU port on a bounded sample of the same rows
+    from oracle import candidates_oracle as co
+    sample_rows = 12000
+    cut = 0
+    for _ in range(sample_rows):
+        cut = text.index(b"\n", cut) + 1
+    rows = text[:cut].decode().splitlines(keepends=True)
+    t0 = time.perf_counter()
+    sites = co.scan_rows(rows, reference, 1001, min_coverage=4.0, snv_min_af=0.05, indel_min_af=0.05, alternative_base_num=3,
+                         select_indel_candidates=True)
+    t_cpu = time.perf_counter() - t0
+    want = np.array([1 | (2 if v[1] else 0) | (4 if v[2] else 0) | (8 if v[3] else 0) for v in sites.values()], np.uint8)
+    assert np.array_equal(want, dev_flags[:sample_rows]), "candidate scan differs from the oracle on the bench sample"
+    gbs = n_bytes / (t_scan * 1e-3) / 1e9
+    return dict(workload="%d mpileup rows (%.0f MB of text, ONT-shape, --min-BQ 0 stream of the same sites)" % (n_rows, n_bytes / 1e6),
+                rows_per_s=n_rows / ((t_idx + t_scan) * 1e-3), ms_row_index=t_idx, ms_scan=t_scan,
+                roofline=dict(bound="hbm", kernel="scan_kernel", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                              algorithmic_bytes_per_launch=n_bytes, note="algorithmic bytes = the mpileup text, read once"),
+                row_index_gbs=n_bytes / (t_idx * 1e-3) / 1e9,
+                e2e=dict(rows_per_s=n_rows / (t_host * 1e-3), gb_per_s=n_bytes / (t_host * 1e-3) / 1e9, h2d_bytes_per_step=n_bytes,
+                         d2h_bytes_per_step=9 * n_rows, api="cto_scan_candidates_host (pinned host text)"),
+                cpu_baseline=dict(rows_per_s=sample_rows / t_cpu, cores=1, kind="port", sample="%d rows, oracle/candidates_oracle.py" % sample_rows),
+                candidates=dict(pass_af=int((dev_flags & 2).astype(bool).sum()), snv=int((dev_flags & 4).astype(bool).sum()),
+                                indel=int((dev_flags & 8).astype(bool).sum())),
+                parity="flags equal the oracle on the CPU sample; host call equals the device call")
+
+
 def cpu_mix(cfg):
     total = float(sum(n for _, n in cfg["parts"]))
     return [(h, n / total) for h, n in cfg["parts"]]
@@ -286,6 +387,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-text", action="store_true", help="skip the mpileup-text end-to-end leg (config 1)")
     ap.add_argument("--no-cli", action="store_true", help="skip the chunk-file level leg (config 1, one GPU)")
+    ap.add_argument("--no-scan", action="store_true", help="skip the STEP-1 candidate-scan leg (config 1, one GPU)")
     ap.add_argument("--cli-candidates", type=int, default=2000, help="candidates of the synthetic chunk of the chunk-file leg")
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: allow fewer warm-up steps "
                                                        "(numbers printed in this mode are NOT bench values)")
@@ -553,6 +655,12 @@ def main():
     if rank == 0 and world == 1 and args.config == 1 and not args.no_cli:
         cli = cli_leg(args.cli_candidates, 4, synthetic_likelihood(4), host_threads)
 
+    scan = None
+    if rank == 0 and world == 1 and args.config == 1 and not args.no_scan and parts[0]["raw"] is not None and parts[0]["raw"][3] is not None:
+        launches_scan0 = lib.cto_launch_count()
+        scan = scan_leg(parts[0]["raw"], peaks, dev)
+        scan["gpu_launches"] = int(lib.cto_launch_count() - launches_scan0)
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="strong" if cfg["total"] else "weak",
@@ -562,7 +670,7 @@ def main():
                                 l2_policy="inputs (%.0f MB per step and GPU) larger than the 126 MB L2" % (sum(p["h2d"] for p in parts) / 1e6),
                                 parallelism="candidates sharded x%d, one gather of probabilities" % world,
                                 host_cores_bound_to_gpu_numa_node=numa, datagen_s=round(t_gen, 1)),
-                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, cli=cli, gpu_launches=int(launches), clocks=clocks)
+                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, cli=cli, candidate_scan=scan, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
     for eng_k, _ in engines:
         eng_k.close()

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcto_b200.so")
 
 _lib = None
-ABI_VERSION = 2       # include/clairs_to_b200.h CTO_ABI_VERSION
+ABI_VERSION = 3       # include/clairs_to_b200.h CTO_ABI_VERSION
 
 
 class HostStream(C.Structure):
@@ -65,6 +65,9 @@ SIGNATURES = {
     "cto_format_tensor_can_rows": (I64, [C.c_char_p, I64, I64, P, C.c_char_p, P, C.c_char_p, P, P, P, I64]),
     "cto_format_predict_rows": (I64, [C.c_char_p, P, I64, P, P, P, INT, P, I64]),
     "cto_parse_predict_file": (INT, [C.c_char_p, I64, INT, I64, P, P, P, P]),
+    "cto_index_rows": (INT, [P, I64, P, I64, P, P]),
+    "cto_scan_candidates": (INT, [P, I64, P, I64, P, I64, I64, C.c_double, C.c_double, C.c_double, INT, INT, P, P, P, P, P]),
+    "cto_scan_candidates_host": (INT, [P, I64, P, I64, I64, C.c_double, C.c_double, C.c_double, INT, INT, I64, P, P, P, P, P, P]),
 }
 
 

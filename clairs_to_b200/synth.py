@@ -274,3 +274,74 @@ def synth_pair_tiled(n_candidates, seed, platform='ont', base=50000, **kw):
     aff = take_candidates(concat_streams([a] * reps), n_candidates)
     neg = take_candidates(concat_streams([g] * reps), n_candidates)
     return (aff, None), (neg, None)
+
+
+def scan_rows_text(n_rows, seed, ctg='chr20', first_pos=1001, depth_mean=40, weird=0.0):
+    """Whole-chunk mpileup rows for the candidate scan (STEP 1, ``samtools mpileup`` WITHOUT ``--output-MQ``: six columns
+    ``ctg pos N depth bases BQ``), with planted SNVs / insertions / deletions at a range of allele fractions around the
+    thresholds, strand case, ``*`` / ``#`` / N reads, ``^<q>`` read starts whose quality character is a structural
+    character (``+ - ^ $`` digits, letters), ``$`` read ends and ``< >`` reference skips.  ``weird`` > 0 adds the
+    tokenizer's corner cases with that probability per row (``+0``, a second suffix on one read, a suffix on ``*``/N).
+    Returns (rows, reference) where reference[i] is the base of position first_pos + i (some are N / lower case).
+    Small inputs only (a Python loop per read)."""
+    rng = np.random.default_rng(seed)
+    ref = rng.choice(list("ACGT"), size=n_rows)
+    ref[rng.random(n_rows) < 0.01] = 'N'
+    lower = rng.random(n_rows) < 0.05
+    reference = ''.join(b.lower() if l else b for b, l in zip(ref, lower))
+    quals_special = "+-^$0123456789ACGTNacgtn*#<>!~"
+    rows = []
+    for r in range(n_rows):
+        mode = rng.random()
+        depth = int(rng.poisson(depth_mean)) if rng.random() > 0.08 else int(rng.integers(0, 7))
+        rb = ref[r] if ref[r] in "ACGT" else 'A'
+        alt = "ACGT".replace(rb, "")[int(rng.integers(0, 3))]
+        af = float(rng.choice([0.0, 0.02, 0.045, 0.05, 0.055, 0.08, 0.2, 0.5, 1.0]))
+        n_alleles = int(rng.integers(1, 4))
+        ins_alleles = [''.join(rng.choice(list("ACGT"), size=int(rng.integers(1, 7)))) for _ in range(n_alleles)]
+        del_alleles = [int(rng.integers(1, 12)) for _ in range(n_alleles)]
+        parts = []
+        for read in range(depth):
+            rev = rng.random() < 0.5
+            u = rng.random()
+            base = rb
+            if u < 0.01:
+                base = "ACGT"[int(rng.integers(0, 4))]
+            elif u < 0.02:
+                base = '*' if not rev else '#'
+            elif u < 0.023:
+                base = 'N'
+            suffix = ""
+            if mode < 0.10 and rng.random() < af:
+                base = alt
+            elif 0.10 <= mode < 0.17 and rng.random() < af:
+                seq = ins_alleles[int(rng.integers(0, n_alleles))]
+                suffix = "+%d%s" % (len(seq), seq.lower() if rev else seq)
+            elif 0.17 <= mode < 0.24 and rng.random() < af:
+                ln = del_alleles[int(rng.integers(0, n_alleles))]
+                suffix = "-%d%s" % (ln, ('n' if rev else 'N') * ln)
+            elif rng.random() < 0.004:
+                seq = ''.join(rng.choice(list("ACGT"), size=int(rng.integers(1, 4))))
+                suffix = "+%d%s" % (len(seq), seq.lower() if rev else seq)
+            tok = (base.lower() if rev and base in "ACGTN" else base) + suffix
+            if weird and read + 1 < depth and rng.random() < weird:     # never last: a trailing '+0' raises in the reference
+                k = int(rng.integers(0, 4))
+                if k == 0:
+                    tok += "+0"
+                elif k == 1:
+                    tok += "-2nn"                               # a second suffix replaces the first (EC:86)
+                elif k == 2:
+                    tok = "*+1A"
+                else:
+                    tok = "N-1n"
+            if rng.random() < 0.04:
+                tok = '^' + quals_special[int(rng.integers(0, len(quals_special)))] + tok
+            if rng.random() < 0.04:
+                tok += '$'
+            if rng.random() < 0.005:
+                tok += '<' if rev else '>'
+            parts.append(tok)
+        bases = ''.join(parts) if parts else '*'
+        quals = ''.join(chr(33 + int(q)) for q in rng.integers(1, 50, size=max(depth, 1)))
+        rows.append("%s\t%d\tN\t%d\t%s\t%s\n" % (ctg, first_pos + r, depth, bases, quals))
+    return rows, reference

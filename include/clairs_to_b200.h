@@ -28,7 +28,7 @@ extern "C" {
 
 #define CTO_N_POS 33       /* shared/param.py:60 */
 #define CTO_N_CH 34        /* shared/param.py:56 */
-#define CTO_ABI_VERSION 2
+#define CTO_ABI_VERSION 3
 
 typedef struct cto_engine cto_engine;
 
@@ -296,6 +296,51 @@ int64_t cto_format_predict_rows(const char* text, const int64_t* fields, int64_t
  */
 int cto_parse_predict_file(const char* text, int64_t len, int n_heads, int64_t max_rows, double* p_aff, double* p_neg,
                            int64_t* fields, int64_t* n_rows);
+
+/*
+ * Candidate scan -- STEP 1 of the pipeline, SURVEY.md section 8 row f3.  Replaces the per-row work of
+ * src/extract_candidates_calling.py: the tokenizer and counters of decode_pileup_bases (ibid. 73-120), its allele-frequency /
+ * coverage tests (122-144) and the SNV / indel candidate rules of extract_pair_candidates (335-377), for EVERY row of a
+ * chunk's `samtools mpileup` text, on the GPU (one thread per row, text staged in shared memory).
+ *
+ * cto_index_rows: byte offsets of the rows of a '\n'-separated text in device memory.  row_off_dev int64 [cap_rows + 1]
+ * receives row_off[0 .. n_rows] (row_off[n_rows] = text_len; a last row without '\n' counts); NULL = count only.
+ * Synchronises the stream (the row count comes back to the host).
+ *
+ * cto_scan_candidates: per row r, pos_dev[r] = column 2, depth_dev[r] = the reference's `depth` (ibid. 104-109), flags_dev[r]:
+ *   CTO_CAND_VALID     the reference base of the row is A/C/G/T (ibid. 341-342; other rows are skipped)
+ *   CTO_CAND_PASS_AF   pass_af (ibid. 144): the position enters candidates_set / the .bed file
+ *   CTO_CAND_SNV       member of snv_candidates_set (ibid. 366-371)
+ *   CTO_CAND_INDEL     member of indel_candidates_set (ibid. 372-377; only with select_indel_candidates)
+ *   CTO_CAND_MALFORMED fewer than five columns, CTO_CAND_BAD_REF position outside [ref_start, ref_start + ref_len),
+ *   CTO_CAND_OVERFLOW  more than 8192 distinct indel alleles in one row (the reference would raise / cannot happen with
+ *                      samtools' --max-depth 8000) -- the three are errors for the caller.
+ * ref_dev: upper- or lower-case reference bases of positions ref_start .. ref_start + ref_len - 1 (1-based, the
+ * `reference_sequence` / `reference_start` of ibid. 286-297).  alternative_base_num < 0 stands for None (ibid. 134-137).
+ * Rows with more than 24 distinct indel alleles take a second launch; *n_overflow (nullable) reports how many did.
+ * Contract: text_dev 16-byte aligned and ALLOCATED up to the next multiple of 16 bytes beyond text_len (an unaligned
+ * pointer takes the slower in-place path); text_len < 4 GiB per call.  Synchronises the stream.
+ *
+ * cto_scan_candidates_host: the same from HOST memory (text as samtools wrote it, preferably pinned): the text is cut
+ * into 32 MB pieces at row ends, piece k + 1 is copied while piece k is indexed and scanned; outputs are host arrays of
+ * cap_rows entries, *n_rows the rows found.
+ */
+#define CTO_CAND_VALID 1
+#define CTO_CAND_PASS_AF 2
+#define CTO_CAND_SNV 4
+#define CTO_CAND_INDEL 8
+#define CTO_CAND_MALFORMED 32
+#define CTO_CAND_BAD_REF 64
+#define CTO_CAND_OVERFLOW 128
+int cto_index_rows(const uint8_t* text_dev, int64_t text_len, int64_t* row_off_dev, int64_t cap_rows, int64_t* n_rows, void* stream);
+int cto_scan_candidates(const uint8_t* text_dev, int64_t text_len, const int64_t* row_off_dev, int64_t n_rows, const uint8_t* ref_dev,
+                        int64_t ref_start, int64_t ref_len, double min_coverage, double snv_min_af, double indel_min_af,
+                        int alternative_base_num, int select_indel_candidates, int32_t* pos_dev, int32_t* depth_dev,
+                        uint8_t* flags_dev, int32_t* n_overflow, void* stream);
+int cto_scan_candidates_host(const char* text, int64_t text_len, const char* ref, int64_t ref_start, int64_t ref_len,
+                             double min_coverage, double snv_min_af, double indel_min_af, int alternative_base_num,
+                             int select_indel_candidates, int64_t cap_rows, int32_t* pos, int32_t* depth, uint8_t* flags,
+                             int64_t* n_rows, int64_t* n_overflow, void* stream);
 
 #ifdef __cplusplus
 }

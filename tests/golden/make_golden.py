@@ -274,6 +274,118 @@ def create_tensor_golden():
         print("create_tensor golden (%s): %d rows" % (name, n))
 
 
+def candidates_golden():
+    """Unmodified reference `extract_candidates_calling` (STEP 1) through tests/fake_samtools.py:
+    one chunk with SNV + indel selection and an indel BED, one SNV-only chunk of a 2-chunk split, one chunk with a
+    confident BED (--bed_fn) and --bed_fn_source set (no indel BED filter)."""
+    import shutil
+    work = os.path.join(HERE, "candidates")
+    shutil.rmtree(work, ignore_errors=True)
+    os.makedirs(work)
+    ctg, length, first = "chr20", 4000, 41
+    rows, reference = synth.scan_rows_text(3900, 2024, ctg=ctg, first_pos=first, depth_mean=35, weird=0.004)
+    rng = np.random.default_rng(9)
+    seq = list(rng.choice(list("ACGT"), size=length))
+    seq[first - 1:first - 1 + len(reference)] = list(reference)
+    seq = "".join(seq)
+    fa = os.path.join(work, "ref.fa")
+    with open(fa, "w") as f:
+        f.write(">%s\n" % ctg)
+        for i in range(0, length, 60):
+            f.write(seq[i:i + 60] + "\n")
+    with open(fa + ".fai", "w") as f:
+        f.write("%s\t%d\t%d\t60\t61\n" % (ctg, length, len(ctg) + 2))
+    bam = os.path.join(work, "tumor.bam")
+    open(bam, "w").close()
+    with open(bam + ".minbq20.mpileup", "w") as f:
+        f.writelines(rows)
+    indel_bed = os.path.join(work, "indel_regions.bed")
+    with open(indel_bed, "w") as f:
+        f.write("# indel calling regions\n%s\t100\t900\n%s\t1500\t1500\n%s\t2000\t3500\nchr21\t0\t5000\n" % (ctg, ctg, ctg))
+    conf_bed = os.path.join(work, "confident.bed")
+    with open(conf_bed, "w") as f:
+        f.write("%s\t500\t1800\n%s\t2200\t3000\n" % (ctg, ctg))
+    shim = os.path.join(ROOT, "tests", "fake_samtools.py")
+    env = dict(os.environ, PYTHONPATH=REF)
+    common = [sys.executable, os.path.join(REF, "clairs_to.py"), "extract_candidates_calling", "--tumor_bam_fn", bam, "--ref_fn", fa,
+              "--samtools", shim, "--ctg_name", ctg, "--platform", "ont_r10_dorado_sup_5khz", "--min_coverage", "4", "--min_bq", "20",
+              "--output_depth", "True", "--genotyping_mode_vcf_fn", "None", "--hybrid_mode_vcf_fn", "None"]
+    cases = {
+        "snv_indel": ["--snv_min_af", "0.05", "--indel_min_af", "0.05", "--chunk_id", "1", "--chunk_num", "1", "--bed_fn_source", "None",
+                      "--call_indels_only_in_these_regions", indel_bed, "--select_indel_candidates", "True"],
+        "snv_only": ["--snv_min_af", "0.08", "--indel_min_af", "0.1", "--chunk_id", "2", "--chunk_num", "2", "--bed_fn_source", "None"],
+        "bed": ["--snv_min_af", "0.05", "--indel_min_af", "0.1", "--chunk_id", "1", "--chunk_num", "2", "--bed_fn_source", conf_bed,
+                "--bed_fn", conf_bed, "--call_indels_only_in_these_regions", indel_bed, "--select_indel_candidates", "True"],
+    }
+    for name, extra in cases.items():
+        folder = os.path.join(work, name)
+        os.makedirs(folder)
+        res = subprocess.run(common + extra + ["--candidates_folder", folder], check=True, env=env, stdout=subprocess.PIPE, text=True)
+        # the list files hold absolute paths of the build container: keep them relative to the candidates folder
+        for fn in os.listdir(folder):
+            if fn.startswith(("SNV_CANDIDATES_FILE_", "INDEL_CANDIDATES_FILE_")):
+                path = os.path.join(folder, fn)
+                with open(path) as f:
+                    text = f.read().replace(folder + "/", "<candidates_folder>/")
+                with open(path, "w") as f:
+                    f.write(text)
+        with open(os.path.join(folder, "stdout.txt"), "w") as f:
+            f.write(res.stdout)
+        with open(os.path.join(folder, "args.json"), "w") as f:
+            json.dump([a.replace(work + "/", "") for a in extra], f)
+        print("candidates golden (%s):" % name, res.stdout.strip(), sorted(os.listdir(folder)))
+
+
+def indel_call_golden():
+    """Unmodified reference `call_variants` on a HAND-WRITTEN predict file whose probabilities drive insertion and deletion
+    calls (the synthetic-weight pipeline golden never produced an I/D ALT row): '#'-anchored insertions,
+    multi-base deletions, competing alleles, depth-0 and low-AF rows."""
+    work = os.path.join(HERE, "pipeline")
+    src = os.path.join(work, "predict_indel")
+    rows = [r.rstrip("\n").split("\t") for r in gzip.open(src, "rt")]
+    rng = np.random.default_rng(31)
+    alt_infos = [                                 # (reference base, alt_info as create_tensor writes it, CT:158-209)
+        ("A", "40-IAGT 21 RA 10 XT 3-"),                   # insertion
+        ("C", "55-DCAC 31 RC 20-"),                        # deletion of two bases
+        ("G", "60-IGT 6 IGTT 16 RG 30 XA 2-"),             # competing insertion alleles
+        ("T", "48-DTA 9 DTACGT 20 RT 15-"),                # competing deletion lengths
+        ("A", "35-I#A 9 RA 20-"),                          # insertion anchored on a deleted base (CV:360)
+        ("A", "30-RA 25 XC 5-"),                           # no indel support at all
+        ("G", "0-"),                                       # empty pileup
+        ("A", "80-IAACGTACGTAC 55 RA 20-"),                # long insertion
+        ("C", "44-DCACGTACGTACGT 38 RC 6-"),               # long deletion
+        ("G", "52-IGC 3 DGA 3 RG 40 XT 6-"),               # weak insertion and deletion plus a SNV allele
+        ("T", "20-XA 10 ITA 10-"),                         # tie between a SNV and an insertion
+    ]
+    out_rows = []
+    for k in range(60):
+        cols = list(rows[k % len(rows)])
+        cols[1] = str(7000 + 50 * k)
+        cols[2], cols[3] = alt_infos[k % len(alt_infos)]
+        probs = []
+        hot = int(rng.integers(0, 6)) if k % 7 else 4 + (k // 7) % 2      # heads 4 / 5 = I / D
+        for net in range(2):
+            for h in range(6):
+                p1 = float(rng.uniform(0.75, 0.999)) if h == hot else float(rng.uniform(0.001, 0.3))
+                probs.append("%0.8f %0.8f" % (1.0 - p1, p1))
+        n_fixed = len(cols) - 12
+        out_rows.append("\t".join(cols[:n_fixed] + probs) + "\n")
+    predict_fn = os.path.join(work, "predict_indel_hand")
+    with gzip.open(predict_fn, "wt") as f:
+        f.writelines(out_rows)
+    env = dict(os.environ, PYTHONPATH=REF)
+    for show_ref in (False, True):
+        vcf = os.path.join(work, "call_indel_hand%s.vcf" % ("_showref" if show_ref else ""))
+        cmd = [sys.executable, os.path.join(REF, "clairs_to.py"), "call_variants", "--predict_fn", predict_fn, "--call_fn", vcf,
+               "--ref_fn", os.path.join(work, "ref.fa"), "--platform", "ont_r10_dorado_sup_5khz",
+               "--likelihood_matrix_data", os.path.join(work, "likelihood_indel.txt"), "--disable_indel_calling", "False"]
+        if show_ref:
+            cmd.append("--show_ref")
+        subprocess.run(cmd, check=True, env=env)
+        n_indel = sum(1 for r in open(vcf) if r[0] != '#' and (len(r.split("\t")[3]) > 1 or len(r.split("\t")[4]) > 1))
+        print("indel call golden:", vcf, "rows with an insertion / deletion ALT:", n_indel)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -287,3 +399,7 @@ if __name__ == "__main__":
         pipeline_golden()
     if a.only in (None, "create_tensor"):
         create_tensor_golden()
+    if a.only in (None, "candidates"):
+        candidates_golden()
+    if a.only in (None, "indel_call"):
+        indel_call_golden()

@@ -150,14 +150,18 @@ def test_predict_cli_against_reference_predict_file(golden_dir, tmp_path, tag, n
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag,n_heads,show_ref", [("snv", 4, False), ("snv", 4, True), ("indel", 6, False), ("indel", 6, True)])
+@pytest.mark.parametrize("tag,n_heads,show_ref", [("snv", 4, False), ("snv", 4, True), ("indel", 6, False), ("indel", 6, True),
+                                                  ("indel_hand", 6, False), ("indel_hand", 6, True)])
 def test_call_variants_cli_identical_vcf(golden_dir, tmp_path, tag, n_heads, show_ref):
+    """``indel_hand``: a hand-written predict file whose probabilities drive insertion / deletion calls ('#'-anchored
+    insertions, multi-base deletions, competing alleles; tests/golden/make_golden.py:indel_call_golden) -- the seeded-weight
+    pipeline golden holds no I/D ALT row."""
     from clairs_to_b200 import call_variants as cv
     pdir = os.path.join(golden_dir, "pipeline")
     out = str(tmp_path / "out" / ("call_%s.vcf" % tag))
     argv = ["--predict_fn", os.path.join(pdir, "predict_" + tag), "--call_fn", out,
             "--ref_fn", os.path.join(pdir, "ref.fa"), "--platform", "ont_r10_dorado_sup_5khz",
-            "--likelihood_matrix_data", os.path.join(pdir, "likelihood_%s.txt" % tag),
+            "--likelihood_matrix_data", os.path.join(pdir, "likelihood_%s.txt" % tag.split("_")[0]),
             "--disable_indel_calling", "True" if n_heads == 4 else "False"]
     if show_ref:
         argv.append("--show_ref")
@@ -167,6 +171,9 @@ def test_call_variants_cli_identical_vcf(golden_dir, tmp_path, tag, n_heads, sho
         assert not os.path.exists(out)              # the reference removed its empty VCF, so must we
         return
     assert open(out).read() == open(ref_vcf).read()
+    if tag == "indel_hand":
+        rows = [r.split("\t") for r in open(out) if r[0] != '#']
+        assert sum(len(r[3]) > 1 for r in rows) >= 3 and sum(len(r[4]) > 1 for r in rows) >= 3
 
 
 def test_vcf_header_matches_reference_fixture(golden_dir):

@@ -117,3 +117,60 @@ def test_posterior_oracle_matches_reference_calls(golden_dir, tag, n_heads):
             assert not is_variant
         checked += 1
     assert checked > 5
+
+
+# ---- STEP 1 candidate extraction ----------------------------------------------------------------
+def _candidates_case(golden_dir, name):
+    """Inputs of one golden run of the reference `extract_candidates_calling` (tests/golden/make_golden.py:candidates_golden)."""
+    import fake_samtools
+    work = os.path.join(golden_dir, "candidates")
+    argv = json.load(open(os.path.join(work, name, "args.json")))
+    opt = {argv[i][2:]: argv[i + 1] for i in range(0, len(argv), 2)}
+    ctg = "chr20"
+    seq = fake_samtools.read_fasta(os.path.join(work, "ref.fa"))[ctg]
+    contig_length = int(open(os.path.join(work, "ref.fa.fai")).read().split("\t")[1])
+    return work, opt, ctg, seq, contig_length
+
+
+def _bed(path, ctg):
+    out = []
+    for row in open(path):
+        if row[0] == '#':
+            continue
+        c = row.split()
+        if c[0] == ctg:
+            out.append((int(c[1]), int(c[2]) + (1 if c[1] == c[2] else 0)))
+    return out
+
+
+@pytest.mark.parametrize("name", ["snv_indel", "snv_only", "bed"])
+def test_candidates_oracle_matches_reference_files(golden_dir, name):
+    """oracle/candidates_oracle.py against the files the unmodified reference wrote (bed, region files, [INFO] line)."""
+    from oracle import candidates_oracle as co
+    work, opt, ctg, seq, contig_length = _candidates_case(golden_dir, name)
+    chunk_id, chunk_num = int(opt["chunk_id"]) - 1, int(opt["chunk_num"])
+    bed_range = None
+    if "bed_fn" in opt:
+        iv = _bed(os.path.join(work, opt["bed_fn"]), ctg)
+        bed_range = (min(s for s, _ in iv), max(e for _, e in iv))
+    ctg_start, ctg_end = co.chunk_range(chunk_id, chunk_num, contig_length, bed_range)
+    lo, hi = co.reads_region(ctg_start, ctg_end)
+    rows = [r for r in open(os.path.join(work, "tumor.bam.minbq20.mpileup")) if lo <= int(r.split("\t", 2)[1]) <= hi]
+    reference_start = max(ctg_start - 1000, 1)
+    select_indel = opt.get("select_indel_candidates") == "True"
+    intervals = None
+    if select_indel and opt["bed_fn_source"] == "None":
+        intervals = _bed(os.path.join(work, opt["call_indels_only_in_these_regions"]), ctg)
+    every, snv, indel = co.candidate_lists(
+        rows, seq[reference_start - 1:ctg_end + 1000], reference_start, indel_intervals=intervals, min_coverage=4.0,
+        snv_min_af=float(opt["snv_min_af"]), indel_min_af=float(opt["indel_min_af"]), alternative_base_num=3,
+        select_indel_candidates=select_indel)
+    folder = os.path.join(work, name)
+    bed_rows = open(os.path.join(folder, "bed", "%s_%d.bed" % (ctg, chunk_id))).read().splitlines()
+    assert bed_rows == ["%s\t%d\t%d" % (ctg, p - 1, p) for p in every]
+    assert open(os.path.join(folder, "%s.%d_0_1_snv" % (ctg, chunk_id))).read().splitlines() == co.region_rows(ctg, snv)
+    if select_indel:
+        assert open(os.path.join(folder, "%s.%d_0_1_indel" % (ctg, chunk_id))).read().splitlines() == co.region_rows(ctg, indel)
+        assert "Total SNV candidates found: %d, total Indel candidates found: %d" % (len(snv), len(indel)) in \
+            open(os.path.join(folder, "stdout.txt")).read()
+    assert len(snv) > 20

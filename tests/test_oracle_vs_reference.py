@@ -135,3 +135,38 @@ for path, key, sd_path, export in ((%r, 'model_acgt', %r, export_aff), (%r, 'mod
     assert out.returncode == 0, out.stderr[-2000:]
     assert "model_acgt" in out.stdout and "[4, 3, 16, 1, 1, 64, 3, 2, 128, 4, 3]" in out.stdout
     assert "model_nacgt" in out.stdout and "[4, 34, 128, 192]" in out.stdout
+
+
+def test_candidates_oracle_fuzz():
+    """oracle/candidates_oracle.site_decision against the reference's decode_pileup_bases of STEP 1
+    (src/extract_candidates_calling.py:55-169) + the set rules of ibid. 355-377, on 4000 synthetic rows incl. the
+    tokenizer's corner cases, for both --select_indel_candidates settings and thresholds on and off the planted AFs."""
+    sys.path.insert(0, REF)
+    try:
+        import src.extract_candidates_calling as ec
+        from oracle import candidates_oracle as co
+        rows, reference = synth.scan_rows_text(4000, 77, first_pos=1, depth_mean=30, weird=0.02)
+        checked = 0
+        for k, row in enumerate(rows):
+            cols = row.strip().split('\t')
+            rb = reference[int(cols[1]) - 1].upper()
+            if rb not in "ACGT":
+                continue
+            select = bool(k & 1)
+            kw = dict(min_coverage=(4, 0, 10)[k % 3], snv_min_af=(0.05, 0.08, 0.0)[k % 3], indel_min_af=(0.05, 0.1, 1.0)[(k // 2) % 3],
+                      alternative_base_num=(3, None, 1)[(k // 3) % 3], select_indel_candidates=select)
+            got = co.site_decision(cols[4], rb, **kw)
+            base_list, depth, pass_af, af, af_infos, pileup_infos, tumor_infos, alt_list, pass_snv_af, pass_indel_af, pileup_list = \
+                ec.decode_pileup_bases(pileup_bases=cols[4], reference_base=rb, min_coverage=kw["min_coverage"],
+                                       minimum_snv_af_for_candidate=kw["snv_min_af"], minimum_indel_af_for_candidate=kw["indel_min_af"],
+                                       alternative_base_num=kw["alternative_base_num"], has_pileup_candidates=False, read_name_list=[],
+                                       is_tumor=False, select_indel_candidates=select)
+            snv = bool(pass_af and pass_snv_af and len([i for i in alt_list if i[0] in "ACGT"]) > 0)          # EC:366-371
+            indel = bool(select and pass_af and pass_indel_af and len([i for i in alt_list if '+' in i[0] or '-' in i[0]]) > 0)
+            assert got == (depth, bool(pass_af), snv, indel), (k, cols[4], kw)
+            checked += 1
+        assert checked > 3500
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k.split('.')[0] in ("clairs", "shared", "src")]:
+            del sys.modules[k]
