@@ -109,7 +109,10 @@ def test_scan_matches_oracle_fuzz(kw, misalign):
     assert np.array_equal(pos, wp)
     assert np.array_equal(flags, wf), np.flatnonzero(flags != wf)[:10]
     assert np.array_equal(depth, wd)
-    assert (wf & 4).sum() > 30 and (not kw["select_indel_candidates"] or kw["alternative_base_num"] is None or (wf & 8).sum() > 30)
+    if kw["alternative_base_num"] is None:                     # EC:131-137: "is not None and count >= ..." never holds
+        assert not (wf & 14).any()
+    else:
+        assert (wf & 4).sum() > 30 and (not kw["select_indel_candidates"] or (wf & 8).sum() > 30)
 
 
 def test_scan_deep_rows_and_allele_table_overflow():
