@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcto_b200.so")
 
 _lib = None
-ABI_VERSION = 3       # include/clairs_to_b200.h CTO_ABI_VERSION
+ABI_VERSION = 4       # include/clairs_to_b200.h CTO_ABI_VERSION
 
 
 class HostStream(C.Structure):
@@ -67,6 +67,11 @@ SIGNATURES = {
     "cto_parse_predict_file": (INT, [C.c_char_p, I64, INT, I64, P, P, P, P]),
     "cto_index_rows": (INT, [P, I64, P, I64, P, P]),
     "cto_scan_candidates": (INT, [P, I64, P, I64, P, I64, I64, C.c_double, C.c_double, C.c_double, INT, INT, P, P, P, P, P]),
+    "cto_hf_parse": (INT, [C.c_char_p, I64, INT, C.c_char_p, I64, I64, P]),
+    "cto_hf_sizes": (INT, [P, P]),
+    "cto_hf_export": (INT, [P] * 15),
+    "cto_hf_free": (None, [P]),
+    "cto_hard_filter_sites": (INT, [P, P, INT, INT, INT, INT, P, C.c_double, C.c_double, P, P, P, P, P]),
     "cto_scan_candidates_host": (INT, [P, I64, P, I64, I64, C.c_double, C.c_double, C.c_double, INT, INT, I64, P, P, P, P, P, P]),
 }
 

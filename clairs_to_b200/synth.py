@@ -345,3 +345,195 @@ def scan_rows_text(n_rows, seed, ctg='chr20', first_pos=1001, depth_mean=40, wei
         quals = ''.join(chr(33 + int(q)) for q in rng.integers(1, 50, size=max(depth, 1)))
         rows.append("%s\t%d\tN\t%d\t%s\t%s\n" % (ctg, first_pos + r, depth, bases, quals))
     return rows, reference
+
+
+def hard_filter_chunk(n_sites, seed, ctg='chr20', region_lo=5001, depth=40, read_len=(120, 900), flanking=100, spacing=90,
+                      with_phasing=True):
+    """A phased tumour pileup chunk for the per-site hard filters: mpileup rows as printed by
+    ``samtools mpileup --output-MQ --output-QNAME [--output-extra HP]`` (src/haplotype_filtering.py:303-311,
+    src/postfilter_variants.py:262-268) over one region holding ``n_sites`` called variants.
+
+    Reads are simulated (start, length, strand, haplotype tag, mapping quality); planted on them are heterozygous and
+    homozygous germline variants (SNVs and insertions), the called somatic variants themselves (SNV / insertion / deletion, some
+    strand biased, some only on reads that start or end nearby, some with poor base quality, some inside low-complexity
+    sequence), passenger variants carried by the same reads (variant cluster) and sequencing noise.
+    Returns (rows, chunk_ref, region_lo, sites) with sites = [(pos, ref_base, alt_base, af, hetero_info, homo_info)]."""
+    rng = np.random.default_rng(seed)
+    span = max(n_sites * spacing, 1) + 2 * flanking + 40
+    ref = rng.integers(0, 4, span + 80)
+    for _ in range(max(1, span // 400)):                              # low-complexity stretches (sequence entropy filter)
+        at = int(rng.integers(0, span))
+        unit = rng.integers(0, 4, int(rng.integers(1, 4)))
+        n = int(rng.integers(20, 60))
+        ref[at:at + n] = np.resize(unit, n)[:len(ref[at:at + n])]
+    ref_s = ''.join("ACGT"[b] for b in ref)
+    region_hi = region_lo + span - 1
+
+    # variants: position (absolute) -> kind, payload
+    site_pos = sorted(set(int(region_lo + flanking + 10 + k * spacing + rng.integers(0, spacing // 3)) for k in range(n_sites)))
+    taken = set(site_pos)
+    variants = {}                                                      # pos -> dict(kind, alt, length, who)
+
+    def other_base(p):
+        return "ACGT"[(ref[p - region_lo] + int(rng.integers(1, 4))) % 4]
+
+    def rand_seq(n):
+        return ''.join("ACGT"[b] for b in rng.integers(0, 4, n))
+
+    germline = []
+    for _ in range(max(2, n_sites)):
+        p = int(rng.integers(region_lo + 5, region_hi - 5))
+        if any(abs(p - q) < 3 for q in taken):
+            continue
+        taken.add(p)
+        zyg = 'hom' if rng.random() < 0.35 else 'het'
+        kind = 'ins' if rng.random() < 0.2 else 'snv'
+        hap = int(rng.integers(1, 3))
+        alt = other_base(p) if kind == 'snv' else ref_s[p - region_lo] + rand_seq(int(rng.integers(1, 5)))
+        variants[p] = dict(kind=kind, alt=alt, zyg=zyg, hap=hap, origin='germline')
+        germline.append((p, alt, zyg))
+    for p in site_pos:
+        u = rng.random()
+        kind = 'snv' if u < 0.6 else 'ins' if u < 0.8 else 'del'
+        length = int(rng.integers(1, 6))
+        alt = other_base(p) if kind == 'snv' else ref_s[p - region_lo] + rand_seq(length) if kind == 'ins' else ref_s[p - region_lo]
+        variants[p] = dict(kind=kind, alt=alt, length=length, origin='somatic', af=float(rng.uniform(0.04, 0.6)),
+                           hap=int(rng.integers(0, 4)),              # 0: any read, 1/2: one haplotype, 3: both tagged haplotypes
+                           style=('strand', 'ends', 'lowbq', 'lowmq', 'cluster', 'paralog', 'plain', 'plain', 'plain')[int(rng.integers(0, 9))])
+        if variants[p]['style'] == 'cluster':                          # passenger variants travelling with the alt reads
+            for d in (-7, 9, 23):
+                q = p + d
+                if q not in taken and region_lo < q < region_hi:
+                    taken.add(q)
+                    variants[q] = dict(kind='snv', alt=other_base(q), origin='passenger', of=p)
+
+    # reads
+    n_reads = int(depth * span / ((read_len[0] + read_len[1]) / 2.0)) + 4
+    starts = rng.integers(region_lo - read_len[1] // 2, region_hi, n_reads)
+    lens = rng.integers(read_len[0], read_len[1], n_reads)
+    snap = rng.random(n_reads)                                         # piles of read starts / ends (read start/end filter)
+    ends = starts + lens - 1
+    starts = np.where(snap < 0.25, starts // 61 * 61, starts)
+    ends = np.where(snap > 0.75, ends // 67 * 67, ends)
+    lens = np.maximum(ends - starts + 1, 30)
+    bundle_of = np.zeros(n_reads, np.int64)
+    for p in site_pos:                                                 # a pile of reads that all begin just before the site
+        if variants[p]['style'] == 'ends':
+            k = max(3, int(depth * 0.4))
+            starts = np.concatenate([starts, np.full(k, p - 2)])
+            lens = np.concatenate([lens, rng.integers(read_len[0], read_len[1], k)])
+            bundle_of = np.concatenate([bundle_of, np.full(k, p)])
+    n_reads = len(starts)
+    order = np.argsort(starts, kind='stable')
+    starts, lens, bundle_of = starts[order], lens[order], bundle_of[order]
+    reads = []
+    for k in range(n_reads):
+        reads.append(dict(name="read%05d/%d" % (k, seed % 97), lo=int(starts[k]), hi=int(starts[k] + lens[k] - 1),
+                          rev=bool(rng.random() < 0.5), hap=int(rng.choice([0, 1, 2], p=[0.25, 0.4, 0.35])),
+                          mq=int(60 if rng.random() < 0.85 else rng.integers(0, 60)), carries={}, bundle=int(bundle_of[k])))
+    longest = int(lens.max()) if n_reads else 0
+
+    def covering(p):                                                   # reads are sorted by start
+        for r in reads[int(np.searchsorted(starts, p - longest)):int(np.searchsorted(starts, p, 'right'))]:
+            if r['lo'] <= p <= r['hi']:
+                yield r
+
+    for p, v in variants.items():
+        for r in covering(p):
+            if v['origin'] == 'germline':
+                hap = r['hap'] if r['hap'] else int(rng.integers(1, 3))
+                on = v['zyg'] == 'hom' or hap == v['hap']
+                on = on and rng.random() < 0.97
+            elif v['origin'] == 'somatic':
+                ok_hap = v['hap'] == 0 or (v['hap'] == 3 and r['hap'] > 0) or r['hap'] == v['hap']
+                on = ok_hap and rng.random() < v['af'] * (1.6 if v['hap'] in (1, 2) else 1.0)
+                if v['style'] == 'strand':
+                    on = on and not r['rev']
+                if v['style'] == 'ends':
+                    on = rng.random() < (0.9 if r['bundle'] == p else 0.03)
+                if v['style'] == 'lowmq':
+                    on = ok_hap and rng.random() < (0.9 if r['mq'] < 30 else 0.01)
+            else:
+                continue
+            if on:
+                r['carries'][p] = v
+    for p, v in variants.items():
+        if v['origin'] == 'somatic' and v['style'] == 'paralog':       # alt reads from elsewhere: they lack the germline alleles
+            for r in covering(p):
+                if p in r['carries']:
+                    r['carries'] = {q: w for q, w in r['carries'].items() if w['origin'] != 'germline'}
+    for p, v in variants.items():
+        if v['origin'] == 'passenger':
+            for r in covering(p):
+                if v['of'] in r['carries'] and rng.random() < 0.95:
+                    r['carries'][p] = v
+
+    sites = []
+    for p in site_pos:
+        v = variants[p]
+        near = [(g, alt, z) for g, alt, z in germline if p - flanking < g <= p + flanking and g != p]
+        het = ','.join("%d-%s" % (g, alt) for g, alt, z in near if z == 'het')
+        hom = ','.join("%d-%s" % (g, alt) for g, alt, z in near if z == 'hom')
+        rb = ref_s[p - region_lo] if v['kind'] != 'del' else ref_s[p - region_lo: p - region_lo + 1 + v['length']]
+        sites.append((p, rb, v['alt'], round(v['af'] * float(rng.uniform(0.5, 1.2)), 4), het, hom))
+
+    # rows
+    rows = []
+    deleted_until = {}                                                 # read index -> last deleted position
+    active = []
+    nxt = 0
+    for p in range(region_lo, region_hi + 1):
+        while nxt < n_reads and reads[nxt]['lo'] <= p:
+            active.append(nxt)
+            nxt += 1
+        active = [k for k in active if reads[k]['hi'] >= p]
+        if not active:
+            continue
+        bases, bqs, mqs, names, hps = [], [], [], [], []
+        rb = ref_s[p - region_lo]
+        for k in active:
+            r = reads[k]
+            tok = ''
+            if r['lo'] == p:
+                tok += '^' + chr(min(r['mq'], 60) + 33)
+            bq = int(np.clip(np.rint(rng.normal(28, 9)), 1, 60))
+            if deleted_until.get(k, 0) >= p:
+                sym = '*'
+            else:
+                v = r['carries'].get(p)
+                sym = rb
+                if v is not None and v['kind'] == 'snv':
+                    sym = v['alt']
+                    if v.get('style') == 'lowbq':
+                        bq = int(rng.integers(3, 19))
+                elif rng.random() < 0.008:
+                    sym = "ACGTN"[int(rng.integers(0, 5))]
+                suffix = ''
+                if v is not None and v['kind'] == 'ins':
+                    suffix = '+%d%s' % (len(v['alt']) - 1, v['alt'][1:])
+                elif v is not None and v['kind'] == 'del' and p + v['length'] <= r['hi']:
+                    suffix = '-%d%s' % (v['length'], ref_s[p - region_lo + 1: p - region_lo + 1 + v['length']])
+                    deleted_until[k] = p + v['length']
+                elif rng.random() < 0.004 and p + 12 <= r['hi']:
+                    n = int(rng.integers(1, 9))
+                    if rng.random() < 0.5:
+                        suffix = '+%d%s' % (n, rand_seq(n))
+                    else:
+                        suffix = '-%d%s' % (n, ref_s[p - region_lo + 1: p - region_lo + 1 + n])
+                        deleted_until[k] = p + n
+                sym += suffix
+            if r['rev']:
+                sym = sym.lower().replace('*', '#')
+            tok += sym
+            if r['hi'] == p:
+                tok += '$'
+            bases.append(tok)
+            bqs.append(chr(bq + 33))
+            mqs.append(chr(min(r['mq'], 60) + 33))
+            names.append(r['name'])
+            hps.append(str(r['hap']) if r['hap'] else ('0' if rng.random() < 0.5 else '*'))
+        cols = [ctg, str(p), 'N', str(len(active)), ''.join(bases), ''.join(bqs), ''.join(mqs), ','.join(names)]
+        if with_phasing:
+            cols.append(','.join(hps))
+        rows.append('\t'.join(cols) + '\n')
+    return rows, ref_s[:span], region_lo, sites

@@ -28,7 +28,7 @@ extern "C" {
 
 #define CTO_N_POS 33       /* shared/param.py:60 */
 #define CTO_N_CH 34        /* shared/param.py:56 */
-#define CTO_ABI_VERSION 3
+#define CTO_ABI_VERSION 4
 
 typedef struct cto_engine cto_engine;
 
@@ -341,6 +341,101 @@ int cto_scan_candidates_host(const char* text, int64_t text_len, const char* ref
                              double min_coverage, double snv_min_af, double indel_min_af, int alternative_base_num,
                              int select_indel_candidates, int64_t cap_rows, int32_t* pos, int32_t* depth, uint8_t* flags,
                              int64_t* n_rows, int64_t* n_overflow, void* stream);
+
+/*
+ * Per-site hard filters -- SURVEY.md section 8 row f4.  Replaces, per called variant ("site"), the reference's
+ * _haplotype_build_state_and_line + _haplotype_finalize_line (src/haplotype_filtering.py:570-703, 344-565, cited as HF; long
+ * reads, phased) and _postfilter_build_state_and_line + _postfilter_finalize_line (src/postfilter_variants.py:368-446, 278-365,
+ * PV; short reads): read start/end, variant cluster ("co-exist"), strand bias (Fisher exact, HF:60-98), sequence entropy
+ * (HF:101-151), low alt BQ / MQ, and the haplotype consistency tests against nearby germline variants.
+ *
+ * Two stages.  (1) cto_hf_parse (host): the chunk's `samtools mpileup --output-MQ --output-QNAME [--output-extra HP]` text
+ * (HF:303-311, PV:262-268) -> integer arrays: every string of the reference (read key, upper-cased token, raw indel suffix)
+ * becomes a dense id.  Rows must be in increasing position order (samtools' order).  (2) cto_hard_filter_sites (device): one
+ * thread block per site walks the rows of the site's window (pos - flanking .. pos + flanking) and evaluates every test with
+ * integer counters; the Fisher p-value reproduces the reference's arithmetic (exact big-integer quotient, correctly rounded,
+ * then the multiply / divide walk in double precision) and the entropy its order of additions.
+ *
+ * cto_hf_parse: `ref` = upper-case reference bases of positions region_lo .. region_lo + ref_len - 1 (the chunk_ref of
+ * HF:1096-1099).  with_phasing: the text has the ninth (HP) column.  cto_hf_sizes: sizes[8] = rows, entries, start/end
+ * entries, reads, tokens, token bytes, suffixes, suffix bytes.  cto_hf_export: copies the arrays out (any pointer may be NULL):
+ *   row_pos[rows], row_off[rows + 1] (entry range of a row), row_flags[rows] (CTO_HF_ROW_*), rse_off[rows + 1] / rse_ent[]
+ *   (entry indices of the row's read start/end set), per entry rid / tok / sfx (ids), info (CTO_HF_* bits, haplotype tag in
+ *   bits 0-1, suffix length incl. its sign in bits 8-23), qual (bq | mq << 8); tok_off[tokens + 1] + tok_blob and
+ *   sfx_off[suffixes + 1] + sfx_blob = the interned strings (suffix 0 = none).
+ */
+#define CTO_HF_HAP_MASK 3u      /* HP tag of the read in this row: 0 (none), 1, 2 */
+#define CTO_HF_REV 4u           /* reverse strand (read key ends in '_1') */
+#define CTO_HF_STAR 8u          /* token is '*' or '#' */
+#define CTO_HF_IS_REF 16u       /* token equals the reference base of the row */
+#define CTO_HF_PLUS 32u         /* suffix starts with '+' */
+#define CTO_HF_MINUS 64u        /* '-' occurs in the suffix */
+#define CTO_HF_SHADOW 128u      /* an earlier entry of a read key that occurs again in the row (dict(zip()) keeps the last) */
+#define CTO_HF_LEN_SHIFT 8
+#define CTO_HF_ROW_REF_OK 1     /* the row's position lies inside the reference passed to cto_hf_parse */
+#define CTO_HF_ROW_RSE 2        /* len(read_start_end_set) >= len(base_list) * 0.2 (HF:627) */
+#define CTO_HF_ROW_COUNTER 4    /* the row's Counter is kept for the variant-cluster test (HF:690-696) */
+typedef struct cto_hf_chunk cto_hf_chunk;
+int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* ref, int64_t ref_len, int64_t region_lo,
+                 cto_hf_chunk** out);
+int cto_hf_sizes(const cto_hf_chunk* chunk, int64_t* sizes);
+int cto_hf_export(const cto_hf_chunk* chunk, int32_t* row_pos, int32_t* row_off, uint8_t* row_flags, int32_t* rse_off,
+                  int32_t* rse_ent, int32_t* rid, int32_t* tok, int32_t* sfx, uint32_t* info, uint16_t* qual, int32_t* tok_off,
+                  char* tok_blob, int32_t* sfx_off, char* sfx_blob);
+void cto_hf_free(cto_hf_chunk* chunk);
+
+/*
+ * cto_hard_filter_sites: every pointer is DEVICE memory.  `chunk` = the arrays of cto_hf_export; `sites` = per site:
+ *   row_lo / row_hi   rows [row_lo, row_hi) of the chunk lie in the site's window; centre_row = the row of the site (-1: none)
+ *   kind              0 SNV, 1 insertion, 2 deletion, 3 other (HF:357-359); alt_tok = token id the alt reads carry (SNV: the
+ *                     alt base; insertion: alt[0] + '+' + alt[1:]; -1 = no such token in the chunk); del_len = len(ref_base)
+ *   low_af            af < 0.1 (SNV) / 0.3 (indel), HF:380-385, evaluated by the caller on the VCF's AF
+ *   rid_min / rid_span  the read ids of the window's rows lie in [rid_min, rid_min + rid_span)
+ *   seq_off / seq_len  the site's entropy sequence (HF:147-148: 33 reference bases, IUPAC codes 0-3) inside `seq`
+ *   ph_off            rows (ascending) whose HP tags define the reads' haplotypes: the site's row and the heterozygous
+ *                     germline positions of the window (HF:621-625): ph_row[ph_off[s] .. ph_off[s + 1])
+ *   het_off / hom_off  germline records of the site: het_idx[het_off[s] ..), hom_idx[hom_off[s] ..)
+ * germline record g: g_row[g] = its row (-1: position not in the chunk), g_match[g_off[g] + k] for entry k of that row:
+ * bit 0 = the read carries the allele by the heterozygous rule (HF:444-451), bit 1 by the homozygous rule (HF:473-481).
+ * mode 1 = haplotype filtering (HF), 0 = post filtering (PV).  entropy_tab[35] = e * log(e), e = i / 33 (HF:106-109),
+ * entropy_mul = -1 / log(33): computed by the CALLER with the host's libm, so that the sum matches the reference bit for bit.
+ * Outputs: out_flags[s] = CTO_HFO_* bits, out_p[s] = the Fisher p-value, out_counts[s][8] = a0, r0, a1, r1 (HF:536-541),
+ * match_count, ins_length, depth, |alt read set|.  scratch: uint32 words for sites whose rid_span exceeds the shared-memory table
+ * (scratch_off[s] = word offset, -1 = none needed).
+ */
+#define CTO_HFO_VERDICT 1u
+#define CTO_HFO_PHASEABLE 2u
+#define CTO_HFO_HETERO 4u
+#define CTO_HFO_HOMO 8u
+#define CTO_HFO_READ_START_END 16u
+#define CTO_HFO_BQ 32u
+#define CTO_HFO_MQ 64u
+#define CTO_HFO_CO_EXIST 128u
+#define CTO_HFO_BOTH_SIDE 256u
+#define CTO_HFO_STRAND_BIAS 512u
+#define CTO_HFO_ENTROPY 1024u
+#define CTO_HF_SMEM_READS 16384  /* reads of one window whose state fits the shared-memory table */
+typedef struct {
+    int64_t n_rows, n_entries;
+    const int32_t *row_pos, *row_off, *rse_off, *rse_ent, *rid, *tok;
+    const uint8_t* row_flags;
+    const uint32_t* info;
+    const uint16_t* qual;
+} cto_hf_chunk_arrays;
+typedef struct {
+    int64_t n_sites;
+    const int32_t *row_lo, *row_hi, *centre_row, *alt_tok, *del_len, *rid_min, *rid_span, *seq_off, *ph_off, *ph_row, *het_off,
+        *het_idx, *hom_off, *hom_idx;
+    const uint8_t *kind, *low_af, *seq_len, *seq;
+    const int64_t* scratch_off;
+    int64_t n_germline;
+    const int32_t *g_row, *g_off;
+    const uint8_t* g_match;
+} cto_hf_site_arrays;
+int cto_hard_filter_sites(const cto_hf_chunk_arrays* chunk, const cto_hf_site_arrays* sites, int mode, int flanking,
+                          int disable_read_start_end_filtering, int max_co_exist_read_num, const double* entropy_tab,
+                          double entropy_mul, double entropy_threshold, uint32_t* scratch, uint32_t* out_flags, double* out_p,
+                          int32_t* out_counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -386,6 +386,51 @@ def indel_call_golden():
         print("indel call golden:", vcf, "rows with an insertion / deletion ALT:", n_indel)
 
 
+def hard_filter_golden():
+    """Per-site hard filters: the lines the UNMODIFIED reference functions
+    ``_haplotype_build_state_and_line`` (src/haplotype_filtering.py:570-703) and ``_postfilter_build_state_and_line``
+    (src/postfilter_variants.py:368-446) return for the sites of two synthetic phased chunks
+    (clairs_to_b200.synth.hard_filter_chunk), plus Fisher p-values (repr) and sequence entropies of the reference's helpers."""
+    import gzip
+    import random
+    sys.path.insert(0, os.path.join(REF, "src"))
+    import src.haplotype_filtering as HF
+    import src.postfilter_variants as PV
+    from clairs_to_b200 import synth
+    out = os.path.join(HERE, "hard_filter")
+    os.makedirs(out, exist_ok=True)
+    meta = {}
+    for name, phased, seed, kw in (("phased_long", True, 11, dict(depth=45, read_len=(150, 1200))),
+                                   ("phased_short", True, 12, dict(depth=30, read_len=(60, 300))),
+                                   ("unphased_short", False, 13, dict(depth=60, read_len=(60, 260)))):
+        rows, ref, lo, sites = synth.hard_filter_chunk(24, seed, with_phasing=phased, **kw)
+        with gzip.open(os.path.join(out, name + ".mpileup.gz"), "wt") as f:
+            f.writelines(rows)
+        chunk_rows = HF._parse_mpileup_to_chunk_dict(rows) if phased else PV._parse_mpileup_postfilter_chunk_dict(rows)
+        lines = {}
+        for disable in (False, True):
+            for max_co in (3, 1):
+                got = []
+                for pos, rb, ab, af, het, hom in sites:
+                    if phased:
+                        got.append(HF._haplotype_build_state_and_line("chr20", pos, rb, ab, 100, chunk_rows, ref, lo, het, hom, disable, max_co, af, 50.0))
+                    else:
+                        got.append(PV._postfilter_build_state_and_line("chr20", pos, rb, ab, 100, chunk_rows, ref, lo, disable, max_co))
+                lines["disable=%d,max_co=%d" % (disable, max_co)] = got
+        meta[name] = dict(phased=phased, ref=ref, region_lo=lo, sites=sites, lines=lines)
+    rnd = random.Random(7)
+    tables = [(0, 0, 0, 0), (1, 1, 1, 1), (3, 1, 1, 3), (1, 3, 3, 1), (10, 0, 0, 10), (5, 5, 5, 6), (7, 30, 2, 41), (0, 12, 9, 3)]
+    tables += [tuple(rnd.randint(0, 40) for _ in range(4)) for _ in range(150)]
+    tables += [(k, k + d, k + d, k) for k in range(1, 30) for d in (0, 1, 2)]                       # mirror tables: `<=` ties
+    tables += [tuple(rnd.randint(0, 2500) for _ in range(4)) for _ in range(25)] + [(1800, 1700, 1650, 1900), (4000, 3, 2, 3900)]
+    meta["fisher"] = [[list(t), repr(HF.fisher_exact([[t[0], t[1]], [t[2], t[3]]]))] for t in tables]
+    seqs = ["".join(rnd.choice("ACGT") for _ in range(33)) for _ in range(20)] + ["A" * 33, "AC" * 16 + "A", "ACGTN" * 6 + "RYK", "ACG" * 5]
+    meta["entropy"] = [[q, repr(HF.calculate_sequence_entropy(q, entropy_window=33))] for q in seqs]
+    with open(os.path.join(out, "golden.json"), "w") as f:
+        json.dump(meta, f)
+    print("hard filter golden:", {k: len(v["sites"]) for k, v in meta.items() if isinstance(v, dict)}, len(meta["fisher"]), "tables")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -403,3 +448,5 @@ if __name__ == "__main__":
         candidates_golden()
     if a.only in (None, "indel_call"):
         indel_call_golden()
+    if a.only in (None, "hard_filter"):
+        hard_filter_golden()

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(handle, name), "missing export " + name
     assert set(_lib.SIGNATURES) == declared
-    assert _lib.lib().cto_abi_version() == 3
+    assert _lib.lib().cto_abi_version() == 4
 
 
 def test_tokenizer_matches_oracle_on_golden_rows(golden_dir):

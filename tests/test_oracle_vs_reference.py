@@ -170,3 +170,45 @@ def test_candidates_oracle_fuzz():
         sys.path.remove(REF)
         for k in [k for k in sys.modules if k.split('.')[0] in ("clairs", "shared", "src")]:
             del sys.modules[k]
+
+
+def test_hard_filter_oracle_fuzz():
+    """oracle/hard_filter_oracle.site_line against the reference's per-site functions:
+    _haplotype_build_state_and_line (src/haplotype_filtering.py:570-703) on phased chunks and _postfilter_build_state_and_line
+    (src/postfilter_variants.py:368-446) on unphased ones, plus fisher_exact and calculate_sequence_entropy on their own."""
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, "src"))
+    try:
+        import src.haplotype_filtering as HF
+        import src.postfilter_variants as PV
+        from oracle import hard_filter_oracle as ho
+        checked = failing = 0
+        for seed in range(4):
+            for phased in (True, False):
+                rows, ref, lo, sites = synth.hard_filter_chunk(10, 100 + seed, with_phasing=phased, depth=(20, 40, 80)[seed % 3],
+                                                               read_len=((120, 900), (60, 300))[seed % 2])
+                theirs = HF._parse_mpileup_to_chunk_dict(rows) if phased else PV._parse_mpileup_postfilter_chunk_dict(rows)
+                mine = ho.parse_chunk(rows, phased)
+                for pos, rb, ab, af, het, hom in sites:
+                    for disable, max_co in ((False, 3), (True, 2)):
+                        if phased:
+                            want = HF._haplotype_build_state_and_line("chr20", pos, rb, ab, 100, theirs, ref, lo, het, hom, disable, max_co, af, 50.0)
+                            got = ho.site_line('haplotype', "chr20", pos, rb, ab, 100, mine, ref, lo, het, hom, disable, max_co, af)
+                        else:
+                            want = PV._postfilter_build_state_and_line("chr20", pos, rb, ab, 100, theirs, ref, lo, disable, max_co)
+                            got = ho.site_line('postfilter', "chr20", pos, rb, ab, 100, mine, ref, lo, None, None, disable, max_co, None)
+                        assert got == want, (seed, phased, pos, rb, ab)
+                        checked += 1
+                        failing += want.split()[2] == "False"
+        assert checked >= 150 and failing > 20
+        rng = np.random.default_rng(5)
+        for t in [tuple(int(x) for x in rng.integers(0, 60, 4)) for _ in range(300)] + [(k, k + 1, k + 1, k) for k in range(40)]:
+            assert ho.fisher_exact(*t) == HF.fisher_exact([[t[0], t[1]], [t[2], t[3]]]), t
+        for _ in range(50):
+            q = ''.join("ACGT"[b] for b in rng.integers(0, 4, 33))
+            assert ho.entropy_of(q) == PV.calculate_sequence_entropy(q, entropy_window=33)
+    finally:
+        sys.path.remove(REF)
+        sys.path.remove(os.path.join(REF, "src"))
+        for k in [k for k in sys.modules if k.split('.')[0] in ("clairs", "shared", "src", "haplotype_filtering", "postfilter_variants")]:
+            del sys.modules[k]
