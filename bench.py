@@ -232,6 +232,89 @@ def cli_leg(n_chunk, n_heads, likelihood, host_threads):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def hard_filter_leg(peaks, dev, n_sites=200, replicas=8, steps=5):
+    """the per-site hard filters (src/haplotype_filtering.py:344-703) on one phased chunk of `n_sites`
+    called variants (the reference's chunk size, HF:188).  Device resident: the chunk's integer arrays in HBM, the site list
+    repeated `replicas` times in one launch (CUDA events).  End to end: mpileup text in host memory -> cto_hf_parse -> site
+    tables -> copies -> kernel -> result lines.  CPU: the oracle port on a bounded sample of the same sites (one core)."""
+    import numpy as np
+    import torch
+    from clairs_to_b200 import hard_filters as hf
+    from clairs_to_b200 import synth
+    rows, ref, lo, sites = synth.hard_filter_chunk(n_sites, 2025, depth=50, read_len=(400, 4000))
+    text = "".join(rows).encode()
+    t0 = time.perf_counter()
+    chunk = hf.parse_chunk(text, True, ref, lo)
+    t_parse = time.perf_counter() - t0
+    many = sites * replicas
+    tables, _ = hf._site_tables(chunk, 1, sites, 100)
+    window_entries = int(sum(int(chunk.row_off[h]) - int(chunk.row_off[l]) for l, h in zip(tables["row_lo"], tables["row_hi"])))
+    for _ in range(2):
+        hf.run_sites(chunk, 1, many)
+    # device time of the kernel alone: the host mirror prepares the tables, the launch is bracketed by events inside run_sites' stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    import ctypes as C
+    from clairs_to_b200 import _lib
+    lib = _lib.lib()
+    tab, mul = hf.entropy_table()
+    tt, _ = hf._site_tables(chunk, 1, many, 100)
+    devc = hf.chunk_to_device(chunk, dev)
+    sd = {k: hf._to_device(tt[k], dev) for k in hf.SITE_FIELDS}
+    ca = hf.ChunkArrays(chunk.n_rows, chunk.n_entries, *[C.c_void_p(devc[k].data_ptr()) for k in hf.CHUNK_FIELDS])
+    sa = hf.SiteArrays(len(many), *[C.c_void_p(sd[k].data_ptr()) for k in hf.SITE_FIELDS[:19]], len(tt["g_row"]),
+                       *[C.c_void_p(sd[k].data_ptr()) for k in hf.SITE_FIELDS[19:]])
+    flags = torch.empty(len(many), dtype=torch.int32, device=dev)
+    pval = torch.empty(len(many), dtype=torch.float64, device=dev)
+    scratch = torch.empty(1, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch():
+        _lib.check(lib.cto_hard_filter_sites(C.byref(ca), C.byref(sa), 1, 100, 0, 3, tab, mul, hf.SEQUENCE_ENTROPY_THRESHOLD,
+                                             C.c_void_p(scratch.data_ptr()), C.c_void_p(flags.data_ptr()), C.c_void_p(pval.data_ptr()), None,
+                                             stream), "cto_hard_filter_sites")
+    launch()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(steps):
+        launch()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    dev_flags = flags.cpu().numpy().view(np.uint32)[:len(sites)]
+    # end to end from the text
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lines = hf.haplotype_filter_chunk("chr20", sites, text, ref, lo)
+    t_e2e = (time.perf_counter() - t0) / steps
+    # CPU port on a sample of the sites (parse included, like the reference's chunk mode)
+    from oracle import hard_filter_oracle as ho
+    sample = sites[:40]
+    t0 = time.perf_counter()
+    parsed = ho.parse_chunk(rows, True)
+    t_cpu_parse = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    want = [ho.site_line('haplotype', "chr20", p, rb, ab, 100, parsed, ref, lo, het, hom, False, 3, af) for p, rb, ab, af, het, hom in sample]
+    t_cpu = time.perf_counter() - t0
+    assert lines[:len(sample)] == want, "hard filter lines differ from the oracle on the bench sample"
+    assert (dev_flags == hf.run_sites(chunk, 1, sites)[0]).all()
+    bytes_per_launch = 14.0 * window_entries * replicas
+    gbs = bytes_per_launch / (ms * 1e-3) / 1e9
+    return dict(workload="%d called variants in one phased chunk (%d pileup rows, %.1f MB of mpileup text with QNAME + HP, depth 50), "
+                         "haplotype-filter mode, flanking 100" % (len(sites), chunk.n_rows, len(text) / 1e6),
+                sites_per_s=len(many) / (ms * 1e-3), ms_per_launch=ms, sites_per_launch=len(many),
+                roofline=dict(bound="hbm", kernel="hard_filter_kernel", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                              algorithmic_bytes_per_launch=bytes_per_launch,
+                              note="algorithmic bytes = 14 B (read id, token id, info, qualities) per pileup entry of every site's window, "
+                                   "read once; the %d replicas of the site list share one chunk, so the reads come from L2" % replicas),
+                e2e=dict(sites_per_s=len(sites) / t_e2e, seconds=t_e2e, host_parse_s=t_parse, host_parse_mb_per_s=len(text) / 1e6 / t_parse,
+                         api="hard_filters.haplotype_filter_chunk: mpileup text -> cto_hf_parse (one host thread) -> site tables -> "
+                             "cto_hard_filter_sites -> lines"),
+                cpu_baseline=dict(sites_per_s=len(sample) / (t_cpu + t_cpu_parse * len(sample) / len(sites)), cores=1, kind="port",
+                                  sample="%d sites, oracle/hard_filter_oracle.py (parse time pro rata)" % len(sample)),
+                failing=int((~(dev_flags & 1).astype(bool)).sum()),
+                parity="lines equal the oracle on the CPU sample")
+
+
 def scan_leg(raw, peaks, dev, steps=5):
     """the STEP-1 candidate scan (src/extract_candidates_calling.py:55-169, 335-377) over whole-chunk
     mpileup text.  Device resident (text in HBM: row index + scan kernels, CUDA events), end to end from pinned host text
@@ -388,6 +471,7 @@ def main():
     ap.add_argument("--no-text", action="store_true", help="skip the mpileup-text end-to-end leg (config 1)")
     ap.add_argument("--no-cli", action="store_true", help="skip the chunk-file level leg (config 1, one GPU)")
     ap.add_argument("--no-scan", action="store_true", help="skip the STEP-1 candidate-scan leg (config 1, one GPU)")
+    ap.add_argument("--no-filters", action="store_true", help="skip the per-site hard-filter leg (config 1, one GPU)")
     ap.add_argument("--cli-candidates", type=int, default=2000, help="candidates of the synthetic chunk of the chunk-file leg")
     ap.add_argument("--ncu", action="store_true", help="profiling run under ncu: allow fewer warm-up steps "
                                                        "(numbers printed in this mode are NOT bench values)")
@@ -661,6 +745,12 @@ def main():
         scan = scan_leg(parts[0]["raw"], peaks, dev)
         scan["gpu_launches"] = int(lib.cto_launch_count() - launches_scan0)
 
+    filters = None
+    if rank == 0 and world == 1 and args.config == 1 and not args.no_filters:
+        launches_f0 = lib.cto_launch_count()
+        filters = hard_filter_leg(peaks, dev)
+        filters["gpu_launches"] = int(lib.cto_launch_count() - launches_f0)
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="strong" if cfg["total"] else "weak",
@@ -670,7 +760,7 @@ def main():
                                 l2_policy="inputs (%.0f MB per step and GPU) larger than the 126 MB L2" % (sum(p["h2d"] for p in parts) / 1e6),
                                 parallelism="candidates sharded x%d, one gather of probabilities" % world,
                                 host_cores_bound_to_gpu_numa_node=numa, datagen_s=round(t_gen, 1)),
-                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, cli=cli, candidate_scan=scan, gpu_launches=int(launches), clocks=clocks)
+                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, cli=cli, candidate_scan=scan, hard_filters=filters, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
     for eng_k, _ in engines:
         eng_k.close()
