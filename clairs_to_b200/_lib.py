@@ -36,6 +36,7 @@ SIGNATURES = {
     "cto_softmax_posterior": (INT, [P, P, P, I64, P, P, P, P, P, P]),
     "cto_engine_set_qual_thresholds": (INT, [P, C.c_double, C.c_double, C.c_double]),
     "cto_engine_set_tensor_cores": (INT, [P, INT]),
+    "cto_engine_set_overlap": (INT, [P, INT]),
     "cto_engine_fused_status": (INT, [P, P]),
     "cto_aff_stage_layers": (INT, [P, INT, P, I64, P]),
     "cto_neg_recurrence": (INT, [P, P, I64, P, P, INT, P]),

@@ -239,6 +239,12 @@ void cto_debug_set(int flags) {
 }
 void cto_debug_timing(long long* dev_buf) { cto::g_gemm_timing = dev_buf; }
 void cto_debug_timing_fused(long long* dev_buf) { cto::g_fused_timing = dev_buf; }
+int cto_engine_set_overlap(cto_engine* h, int enable) {
+    CTO_REQUIRE(h, "engine_set_overlap: NULL engine");
+    h->e.overlap_networks = enable != 0;
+    return 0;
+}
+
 int cto_engine_set_tensor_cores(cto_engine* h, int mode) {
     CTO_REQUIRE(h, "engine_set_tensor_cores: NULL engine");
     CTO_REQUIRE(mode >= 0 && mode <= 2, "engine_set_tensor_cores: mode %d (0 exact fp32, 1 tensor cores, 2 tensor cores with the round-1 per-op kernels: no fused AFF layers, one-chain GRU)", mode);
@@ -359,12 +365,30 @@ int cto_predict(cto_engine* h, const int16_t* x_aff, const int32_t* depth_aff, c
     cudaStream_t s = (cudaStream_t)stream;
     const int nh = e.aff.n_heads;
     const int64_t xin = (int64_t)N_POS * N_CH;
+    // The two networks share nothing but their inputs until the posterior.  With profiling off AFF runs on a second stream
+    // beside NEG (fork / join events around every engine chunk); with profiling on they run back to back on the caller's
+    // stream so that the per-kernel events time one kernel at a time.
+    const bool overlap = e.overlap_networks && !e.profile && n > 0;
+    if (overlap && !e.aux_stream) {
+        CTO_CHECK(cudaStreamCreateWithFlags(&e.aux_stream, cudaStreamNonBlocking));
+        CTO_CHECK(cudaEventCreateWithFlags(&e.fork_ev, cudaEventDisableTiming));
+        CTO_CHECK(cudaEventCreateWithFlags(&e.join_ev, cudaEventDisableTiming));
+    }
     for (int64_t o = 0; o < n; o += e.max_batch) {
         const int64_t nb = std::min(e.max_batch, n - o);
-        // both networks saturate the GPU on their own, so they run back to back on the caller's stream
+        cudaStream_t sa = s;
+        if (overlap) {
+            sa = e.aux_stream;
+            CTO_CHECK(cudaEventRecord(e.fork_ev, s));
+            CTO_CHECK(cudaStreamWaitEvent(sa, e.fork_ev, 0));
+        }
         if (int rc = neg_forward_from_counts(e, x_neg + o * xin, depth_neg + o, nb, logits_neg + o * nh * 2, s)) return rc;
-        if (int rc = launch_rescale(x_aff + o * xin, depth_aff + o, nb, e.x_aff, N_CH, s)) return rc;
-        if (int rc = aff_forward(e, e.x_aff, nb, logits_aff + o * nh * 2, s)) return rc;
+        if (int rc = launch_rescale(x_aff + o * xin, depth_aff + o, nb, e.x_aff, N_CH, sa)) return rc;
+        if (int rc = aff_forward(e, e.x_aff, nb, logits_aff + o * nh * 2, sa)) return rc;
+        if (overlap) {
+            CTO_CHECK(cudaEventRecord(e.join_ev, sa));
+            CTO_CHECK(cudaStreamWaitEvent(s, e.join_ev, 0));
+        }
     }
     if (fwd && rev)
         if (int rc = launch_strand_counts(x_aff, n, fwd, rev, s)) return rc;

@@ -254,6 +254,10 @@ void engine_free(Engine& e) {
     e.allocs.clear();
     if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
     e.copy_stream = nullptr;
+    if (e.aux_stream) cudaStreamDestroy(e.aux_stream);
+    if (e.fork_ev) cudaEventDestroy(e.fork_ev);
+    if (e.join_ev) cudaEventDestroy(e.join_ev);
+    e.aux_stream = nullptr; e.fork_ev = e.join_ev = nullptr;
     if (e.pool) cudaMemPoolDestroy(e.pool);
     e.pool = nullptr;
     for (int s = 0; s < 3; ++s) aff_fused_release(e.aff.st[s]);

@@ -92,6 +92,12 @@ struct Engine {
     std::vector<void*> allocs;
     cudaStream_t copy_stream = nullptr;                        // H2D spans of cto_run_sites_host overlap the kernels
     cudaMemPool_t pool = nullptr;                              // private stream-ordered pool of cto_run_sites_host
+    // AFF and NEG of a chunk only meet at the posterior: cto_predict runs AFF on `aux_stream` beside NEG on the caller's
+    // stream (each fills the other's tail waves; profiles/two_stream_overlap.py: 3-7 % per chunk, identical results).  Off
+    // while per-kernel profiling is on, so that every timed kernel runs alone.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    bool overlap_networks = true;
     bool use_tc = true;                                        // dense contractions on tcgen05 (bf16x3)
     bool use_fused = true;                                     // AFF transformer layers in the fused kernel (aff_fused.cu)
     bool use_two_chains = true;                                // GRU layer 2 with two chains per CTA pair (gru_tc4.cu)

@@ -67,6 +67,13 @@ int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* re
     cto_hf_chunk* ck = new cto_hf_chunk();
     ck->sfxs.get(std::string());                                 // suffix id 0 = no suffix
     std::vector<int32_t> last_row_of_read, last_entry_of_read;
+    // Consecutive pileup rows list mostly the same reads in the same order: the read keys of the previous row (text offset,
+    // length, strand, id) are tried first, the hash map only for reads that are new or moved.  Single-character tokens
+    // (no indel suffix) bypass the token map.
+    struct Seen { int64_t off; int32_t len; int32_t rid; bool rev; };
+    std::vector<Seen> prev_row, this_row;
+    int32_t single_tok[256];
+    for (int k = 0; k < 256; ++k) single_tok[k] = -1;
     struct Tok { char sym; int64_t s_off; int64_t s_len; char sign; };
     std::vector<Tok> row_toks;
     std::string key, token, suffix;
@@ -84,13 +91,13 @@ int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* re
         // columns (split('\t') of the whole line, line feed included in the last one)
         int64_t c_lo[10], c_hi[10];
         int n_col = 0;
-        int64_t a = i;
-        for (int64_t k = i; k <= line_end && n_col < 10; ++k) {
-            if (k == line_end || text[k] == '\t') {
-                c_lo[n_col] = a; c_hi[n_col] = k; ++n_col;
-                a = k + 1;
-                if (k == line_end) break;
-            }
+        for (int64_t a = i; n_col < 10;) {
+            const char* tab = a < line_end ? (const char*)memchr(text + a, '\t', (size_t)(line_end - a)) : nullptr;
+            c_lo[n_col] = a;
+            c_hi[n_col] = tab ? tab - text : line_end;
+            ++n_col;
+            if (!tab) break;
+            a = (tab - text) + 1;
         }
         const int64_t next = line_end;
         if (n_col < (with_phasing ? 9 : 8)) { i = next; continue; }            // HF:250-251 / PV:241-242
@@ -148,14 +155,28 @@ int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* re
         }
         int32_t first_tok = -1;
         bool single = true;
+        size_t hint = 0;
+        this_row.clear();
         for (int32_t e = 0; e < n; ++e) {
             if (nm > c_hi[7]) return fail("fewer read names than reads", line_no);
-            int64_t q = nm;
-            while (q < c_hi[7] && text[q] != ',') ++q;
             const Tok& t = row_toks[e];
             const bool rev = t.sym == '#' || (t.sym >= 'a' && t.sym <= 'z');
-            key.assign(text + nm, (size_t)(q - nm));
-            key += rev ? "_1" : "_0";
+            int64_t q = nm;
+            int32_t rid = -1;
+            if (hint < prev_row.size()) {                         // the same read as in the previous row, at the expected place?
+                const Seen& p = prev_row[hint];
+                const int64_t end = nm + p.len;
+                if (p.rev == rev && end <= c_hi[7] && (end == c_hi[7] || text[end] == ',') &&
+                    memcmp(text + p.off, text + nm, (size_t)p.len) == 0 && !memchr(text + nm, ',', (size_t)p.len)) {
+                    rid = p.rid;
+                    q = end;
+                    ++hint;
+                }
+            }
+            if (rid < 0)
+                while (q < c_hi[7] && text[q] != ',') ++q;
+            const int64_t name_off = nm;
+            const int32_t name_len = (int32_t)(q - nm);
             nm = q + 1;
             uint32_t hap = 0;
             if (with_phasing) {
@@ -167,11 +188,36 @@ int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* re
                     return fail("empty or '12' haplotype tag (the reference's `hap in '12'` raises on it)", line_no);
                 hp = h + 1;
             }
+            for (size_t j = hint, tries = 0; rid < 0 && j < prev_row.size() && tries < 4; ++j, ++tries) {
+                const Seen& p = prev_row[j];
+                if (p.len == name_len && p.rev == rev && memcmp(text + p.off, text + name_off, (size_t)name_len) == 0) {
+                    rid = p.rid;
+                    hint = j + 1;
+                    break;
+                }
+            }
+            if (rid < 0) {
+                key.assign(text + name_off, (size_t)name_len);
+                key += rev ? "_1" : "_0";
+                rid = ck->reads.get(key);
+            }
+            this_row.push_back(Seen{name_off, name_len, rid, rev});
             suffix.clear();
-            if (t.sign) { suffix += t.sign; suffix.append(text + t.s_off, (size_t)t.s_len); }
-            token.assign(1, up(t.sym));
-            for (char ch : suffix) token += up(ch);
-            const int32_t rid = ck->reads.get(key), tok = ck->toks.get(token), sfx = ck->sfxs.get(suffix);
+            int32_t tok, sfx = 0;
+            const char sym_up = up(t.sym);
+            if (!t.sign) {
+                int32_t& cached = single_tok[(uint8_t)sym_up];
+                if (cached < 0) { token.assign(1, sym_up); cached = ck->toks.get(token); }
+                tok = cached;
+                token.assign(1, sym_up);
+            } else {
+                suffix += t.sign;
+                suffix.append(text + t.s_off, (size_t)t.s_len);
+                token.assign(1, sym_up);
+                for (char ch : suffix) token += up(ch);
+                tok = ck->toks.get(token);
+                sfx = ck->sfxs.get(suffix);
+            }
             if ((size_t)rid >= last_row_of_read.size()) { last_row_of_read.resize(rid + 1, -1); last_entry_of_read.resize(rid + 1, -1); }
             uint32_t info = hap | (rev ? CTO_HF_REV : 0);
             if (token.size() == 1 && (token[0] == '#' || token[0] == '*')) info |= CTO_HF_STAR;
@@ -202,6 +248,7 @@ int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* re
             if (n == 0) return fail("read start / end marker in a row without reads", line_no);
             ck->rse_ent.push_back(e0 + (idx < 0 ? n - 1 : idx));
         }
+        prev_row.swap(this_row);
         ck->rse_off.push_back((int32_t)ck->rse_ent.size());
         ck->row_pos.push_back((int32_t)pos);
         ck->row_off.push_back((int32_t)ck->rid.size());

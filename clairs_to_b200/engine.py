@@ -147,6 +147,10 @@ class Engine:
         AFF transformer kernel; 2: tcgen05 contractions with one kernel per op (round-1 layers, kept for A/B tests)."""
         _lib.check(self.lib.cto_engine_set_tensor_cores(self.handle, int(mode)), "set_tensor_cores")
 
+    def set_overlap(self, enable=True):
+        """AFF on a second stream beside NEG inside predict / run_sites (default on; identical results)."""
+        _lib.check(self.lib.cto_engine_set_overlap(self.handle, int(bool(enable))), "set_overlap")
+
     def neg_recurrence(self, xproj, n, two_chains=True):
         """Layer-2 GRU recurrence alone (kernel-level hook, cto_neg_recurrence): xproj fp32 [6H, 33 * bp] on the device ->
         (out_hi, out_mid) int16 views of the bf16 planes [n, 33, 2H]."""

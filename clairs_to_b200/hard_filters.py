@@ -146,7 +146,11 @@ def _site_tables(chunk: PhasedChunk, mode: int, sites, flanking: int):
     if len(nonempty):
         row_min[nonempty] = np.minimum.reduceat(chunk.rid, row_off[nonempty])
         row_max[nonempty] = np.maximum.reduceat(chunk.rid, row_off[nonempty])
-    ins_tokens = [(tk, k) for k, tk in enumerate(chunk.tokens) if '+' in tk]
+    ins_by_text = {}                                            # token text without '+' -> ids of the insertion tokens spelling it
+    for k, tk in enumerate(chunk.tokens):
+        if '+' in tk:
+            ins_by_text.setdefault(tk.replace('+', ''), []).append(k)
+    sfx_tables = {}                                             # (ab[:2], ab[1:2]) -> match bits per distinct raw suffix
     scratch_words = 0
 
     def record(gp, ab):
@@ -161,9 +165,11 @@ def _site_tables(chunk: PhasedChunk, mode: int, sites, flanking: int):
             if len(ab) == 1:                                    # HF:444-445 / 473-474: symbol + raw suffix == alt
                 m = (chunk.tok[lo:hi] == chunk.tok_ids.get(ab, -1)).astype(np.uint8) * 3
             elif len(ab) > 1:                                   # HF:446-448 (ab[:2]) / 475-477 (ab[1:2]): substring of the raw suffix
-                by_sfx = np.array([(1 if len(x) > 1 and ab[:2] in x[1:] else 0) | (2 if len(x) > 1 and ab[1:2] in x[1:] else 0)
-                                   for x in chunk.suffixes], np.uint8)
-                m = by_sfx[chunk.sfx[lo:hi]]
+                keys = (ab[:2], ab[1:2])
+                if keys not in sfx_tables:
+                    sfx_tables[keys] = np.array([(1 if len(x) > 1 and keys[0] in x[1:] else 0) | (2 if len(x) > 1 and keys[1] in x[1:] else 0)
+                                                 for x in chunk.suffixes], np.uint8)
+                m = sfx_tables[keys][chunk.sfx[lo:hi]]
             else:
                 m = np.zeros(hi - lo, np.uint8)
             g_match.append(m)
@@ -192,7 +198,7 @@ def _site_tables(chunk: PhasedChunk, mode: int, sites, flanking: int):
         if kind == 0:                                           # HF:639-642: symbol + suffix == alt
             t["alt_tok"][s] = chunk.tok_ids.get(alt_base, -1)
         elif kind == 1:                                         # HF:643-647: '+' in it and the upper-cased text without '+' == alt
-            hits = [k for tk, k in ins_tokens if tk.replace('+', '') == alt_base]
+            hits = ins_by_text.get(alt_base, [])
             if len(hits) > 1:
                 raise ValueError("site %d: several pileup tokens spell the insertion %r" % (pos, alt_base))
             t["alt_tok"][s] = hits[0] if hits else -1

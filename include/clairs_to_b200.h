@@ -134,6 +134,9 @@ int cto_posterior_from_probs(const double* tables_host, int n_heads, const doubl
  * k <= 256) = CTA pairs with A resident in shared memory (csrc/gemm_pair.cu; ignored when the shape does not fit).
  */
 int cto_engine_set_tensor_cores(cto_engine* e, int mode);
+/* cto_predict / cto_run_sites_host run the AFF network on a second stream beside NEG (default on; always off while
+ * cto_engine_profile is on).  enable = 0: both on the caller's stream, back to back.  Results are identical. */
+int cto_engine_set_overlap(cto_engine* e, int enable);
 /*
  * mode 1 (default) additionally runs all transformer layers of a CvT stage (clairs/model.py:134-147) in ONE tcgen05
  * kernel that keeps the stage's residual stream in tensor memory (csrc/aff_fused.cu); mode 2 = tensor cores with the
