@@ -73,6 +73,7 @@ int tokenize_range(const char* text, int64_t text_len, const char* ref_seq, int6
         t->ref_code.reserve(rows); t->row_pos.reserve(rows); t->pos_off.reserve(rows); t->ind_off.reserve(rows); t->alt_off.reserve(rows);
     }
     std::vector<Entry> entries;
+    std::string key;
     std::unordered_map<std::string, uint32_t> allele_ids;
     std::vector<std::pair<std::string, int>> main_counts;          // first-occurrence ordered Counter
     std::unordered_map<std::string, size_t> main_index;
@@ -134,16 +135,15 @@ int tokenize_range(const char* text, int64_t text_len, const char* ref_seq, int6
         }
 
         const int n_mq = col_len[6], n_bq = col_len[5];
-        allele_ids.clear();
+        if (!allele_ids.empty()) allele_ids.clear();             // clear() walks the whole bucket array even when the map is empty
         main_counts.clear();
-        main_index.clear();
+        if (!main_index.empty()) main_index.clear();
         const bool is_cand = cand.count(pos) != 0;
         for (size_t k = 0; k < entries.size(); ++k) {
             const Entry& e = entries[k];
             const uint8_t mqv = (int)k < n_mq ? (uint8_t)(col[6][k] - 33) : QUAL_ABSENT;
             const uint8_t bqv = (int)k < n_bq ? (uint8_t)(col[5][k] - 33) : QUAL_ABSENT;
             uint8_t c = (uint8_t)symbol_index(e.sym);
-            std::string key;
             if (e.sign || is_cand) key.assign(1, e.sym);
             if (e.sign) {
                 const bool is_del = e.sign == '-';
