@@ -68,6 +68,9 @@ SIGNATURES = {
     "cto_parse_predict_file": (INT, [C.c_char_p, I64, INT, I64, P, P, P, P]),
     "cto_index_rows": (INT, [P, I64, P, I64, P, P]),
     "cto_scan_candidates": (INT, [P, I64, P, I64, P, I64, I64, C.c_double, C.c_double, C.c_double, INT, INT, P, P, P, P, P]),
+    "cto_tokenize_count": (INT, [P, I64, P, I64, P, I64, I64, P, P, P, P, P, P, P]),
+    "cto_tokenize_write": (INT, [P, I64, P, I64, P, I64, I64, INT, INT, P, P, P, P, P]),
+    "cto_window_table": (INT, [P, I64, P, I64, P, P]),
     "cto_hf_parse": (INT, [C.c_char_p, I64, INT, C.c_char_p, I64, I64, P]),
     "cto_hf_sizes": (INT, [P, P]),
     "cto_hf_export": (INT, [P] * 15),

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libcto_b200.so")
-SOURCES = ["api.cu", "encoder.cu", "candidates.cu", "hard_filter.cu", "hard_filter_host.cpp", "nn_kernels.cu", "engine.cu", "gemm_tc.cu", "gemm_pair.cu", "gru_tc3.cu", "gru_tc4.cu", "gru_in_tc.cu", "aff_stage1.cu", "aff_fused.cu", "host_codec.cpp"]
+SOURCES = ["api.cu", "encoder.cu", "candidates.cu", "tokenize_dev.cu", "hard_filter.cu", "hard_filter_host.cpp", "nn_kernels.cu", "engine.cu", "gemm_tc.cu", "gemm_pair.cu", "gru_tc3.cu", "gru_tc4.cu", "gru_in_tc.cu", "aff_stage1.cu", "aff_fused.cu", "host_codec.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--use_fast_math=false",

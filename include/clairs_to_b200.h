@@ -346,6 +346,32 @@ int cto_scan_candidates_host(const char* text, int64_t text_len, const char* ref
                              int64_t* n_rows, int64_t* n_overflow, void* stream);
 
 /*
+ * Device tokenizer -- SURVEY.md section 8 row f2: `samtools mpileup` text in DEVICE memory -> the encoder's packed input,
+ * without the host tokenizer.  Replaces the row split and the tokenizer of src/create_tensor_pileup_calling.py:472-497,
+ * 120-144 like cto_tokenize_mpileup + cto_pack_reads do on host threads, with identical output arrays (tests compare them
+ * byte for byte); the alt_info strings (ibid. 158-209) are NOT produced here -- callers that write tensor_can files keep the
+ * host tokenizer for the candidate rows.
+ *
+ * cto_tokenize_count: per row position (row_pos_dev int32 [n_rows]), reference code (ref_code_dev uint8 [n_rows], A for every
+ * non-ACGT base like evc_base_from), and the offsets grp_off_dev / ind_off_dev (int32 [n_rows + 1]: groups of eight reads,
+ * indel-carrying reads).  *n_groups / *n_ind = the totals the caller sizes planes (8 * n_groups bytes, allocated up to a
+ * multiple of 16) and ind_entry (n_ind uint32) with.  row_off_dev from cto_index_rows.  Synchronises the stream.
+ * cto_tokenize_write: fills planes_dev and ind_entry_dev (layout: clairs_to_b200/pileup_format.py, PackedStream).
+ * Errors (non-zero return, message names the first row): fewer than 7 columns, position outside [ref_start, ref_start +
+ * ref_len), an empty line, more than 8192 distinct indel alleles in one row.
+ * cto_window_table: win_pos_dev[c * 33 + s] = index of the row at position cand_pos[c] - 16 + s, -1 if samtools printed none
+ * (ibid. 461, 513-516); row_pos_dev ascending.
+ */
+int cto_tokenize_count(const uint8_t* text_dev, int64_t text_len, const int64_t* row_off_dev, int64_t n_rows, const uint8_t* ref_dev,
+                       int64_t ref_start, int64_t ref_len, int32_t* row_pos_dev, uint8_t* ref_code_dev, int32_t* grp_off_dev,
+                       int32_t* ind_off_dev, int64_t* n_groups, int64_t* n_ind, void* stream);
+int cto_tokenize_write(const uint8_t* text_dev, int64_t text_len, const int64_t* row_off_dev, int64_t n_rows, const uint8_t* ref_dev,
+                       int64_t ref_start, int64_t ref_len, int low_bq_cut, int max_indel_length, const int32_t* grp_off_dev,
+                       const int32_t* ind_off_dev, uint8_t* planes_dev, uint32_t* ind_entry_dev, void* stream);
+int cto_window_table(const int32_t* row_pos_dev, int64_t n_rows, const int64_t* cand_pos_dev, int64_t n_candidates,
+                     int32_t* win_pos_dev, void* stream);
+
+/*
  * Per-site hard filters -- SURVEY.md section 8 row f4.  Replaces, per called variant ("site"), the reference's
  * _haplotype_build_state_and_line + _haplotype_finalize_line (src/haplotype_filtering.py:570-703, 344-565, cited as HF; long
  * reads, phased) and _postfilter_build_state_and_line + _postfilter_finalize_line (src/postfilter_variants.py:368-446, 278-365,
