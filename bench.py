@@ -722,12 +722,39 @@ def main():
             if world > 1:
                 dist.all_reduce(w, op=dist.ReduceOp.MAX)
             text_bytes = sum(len(t) for t in texts)
-            e2e["text"] = dict(value=p0["n"] * world * k_txt / float(w.item()), unit=UNIT, steps=k_txt,
-                               text_bytes_per_step=text_bytes, host_threads=host_threads,
-                               tokenize_pack_s=sum(a for a, _ in tt) / k_txt, gpu_call_s=sum(b for _, b in tt) / k_txt,
-                               tokenizer_gb_per_s=text_bytes / 1e9 / (sum(a for a, _ in tt) / k_txt),
-                               api="mpileup text (host memory) -> cto_tokenize_mpileup + cto_pack_reads -> cto_run_sites_host; "
-                                   "tokenisation is not yet overlapped with the GPU call")
+            host_tok = dict(value=p0["n"] * world * k_txt / float(w.item()), unit=UNIT, steps=k_txt,
+                            text_bytes_per_step=text_bytes, host_threads=host_threads,
+                            tokenize_pack_s=sum(a for a, _ in tt) / k_txt, gpu_call_s=sum(b for _, b in tt) / k_txt,
+                            tokenizer_gb_per_s=text_bytes / 1e9 / (sum(a for a, _ in tt) / k_txt),
+                            api="mpileup text (host memory) -> cto_tokenize_mpileup + cto_pack_reads (host threads) -> cto_run_sites_host")
+            # ---- and with the DEVICE tokenizer: the host only copies the text (pinned), rows are indexed and tokenized in HBM --------
+            pinned = [torch.frombuffer(bytearray(t), dtype=torch.uint8).pin_memory() for t in texts]
+            refb = ref.encode()
+            out_txt = {k: torch.empty_like(v).pin_memory() for k, v in outs[0].items()}
+
+            def dev_text_step():
+                return p0["eng"].run_sites_text(pinned[0], pinned[1], refb, 1001, cands, cut, out=out_txt, pieces=4)
+
+            got = dev_text_step()                                # outs[0]: what the host-tokenizer path just produced for the same sites
+            torch.cuda.synchronize()
+            for k, v in outs[0].items():
+                assert torch.equal(got[k], v), "device-tokenized %s differ from the host-tokenized ones" % k
+            barrier()
+            k_dev = 5
+            w0 = time.perf_counter()
+            for _ in range(k_dev):
+                dev_text_step()
+            torch.cuda.synchronize()
+            w = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(w, op=dist.ReduceOp.MAX)
+            e2e["text"] = dict(value=p0["n"] * world * k_dev / float(w.item()), unit=UNIT, steps=k_dev, text_bytes_per_step=text_bytes,
+                               h2d_bytes_per_step=text_bytes + len(refb) + 8 * len(cands), d2h_bytes_per_step=sum(t.numel() * t.element_size() for t in out_txt.values()),
+                               text_gb_per_s=text_bytes / 1e9 * k_dev / float(w.item()),
+                               api="Engine.run_sites_text: mpileup text (pinned host memory) -> H2D in 4 pieces on a side stream -> "
+                                   "cto_index_rows + cto_tokenize_count / _write + cto_window_table (device) -> encoder -> AFF + NEG -> "
+                                   "probabilities D2H; bit-identical to the host-tokenizer path",
+                               host_tokenizer=host_tok)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

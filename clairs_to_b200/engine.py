@@ -268,6 +268,10 @@ class Engine:
         hs.n_ind = len(s.ind_entry)
         return hs, keep
 
+    def run_sites_text(self, text_aff, text_neg, ref, ref_start, cand_pos, low_bq_cut, out=None, pieces=4):
+        """mpileup text (pinned host tensors) -> host results; tokenized on the device (see ``run_sites_text`` below)."""
+        return run_sites_text(self, text_aff, text_neg, ref, ref_start, cand_pos, low_bq_cut, out, pieces)
+
     def run_sites_host(self, aff, neg, low_bq_cut: int = None, out=None, want_tensors=False):
         """Host arrays in -> host results out through ``cto_run_sites_host`` (H2D + D2H inside).  ``aff`` / ``neg``:
         PackedStream (host, ideally pinned), or PileupStream, which is packed here first (``low_bq_cut`` required).
@@ -297,6 +301,107 @@ class Engine:
                                                _ptr(out.get('tensor_aff')),
                                                _ptr(out.get('tensor_neg')), _stream_ptr()), "cto_run_sites_host")
         return out
+
+
+def _row_start_at_or_after(text: torch.Tensor, n: int, pos: int) -> int:
+    """Byte offset of the first mpileup row whose position (column 2) is >= ``pos``; rows are position sorted.  Bisection on
+    byte offsets: jump to the next row start behind the probe and read its position."""
+    view = text.numpy()
+
+    def row_after(b):                                           # start of the first row that begins at or behind byte b
+        if b <= 0:
+            return 0
+        k = b - 1
+        while k < n:
+            hit = np.flatnonzero(view[k:k + 65536] == 10)
+            if len(hit):
+                return min(k + int(hit[0]) + 1, n)
+            k += 65536
+        return n
+
+    def position(start):
+        cols = view[start:start + 256].tobytes().split(b"\t", 2)
+        digits = cols[1] if len(cols) > 1 else b""
+        k = 0
+        while k < len(digits) and 48 <= digits[k] <= 57:
+            k += 1
+        return int(digits[:k] or b"0")
+
+    lo, hi = 0, n                                               # invariant: rows starting before lo are < pos; rows from hi on are >= pos
+    while lo < hi:
+        mid = (lo + hi) // 2
+        start = row_after(mid)
+        if start >= n or position(start) >= pos:
+            hi = mid
+        else:
+            lo = start + 1
+    return row_after(lo)
+
+
+def run_sites_text(eng: "Engine", text_aff, text_neg, ref: bytes, ref_start: int, cand_pos, low_bq_cut: int, out=None, pieces: int = 4,
+                   max_indel_length: int = 60):
+    """mpileup TEXT in host memory (pinned uint8 tensors, one per stream, rows position sorted) -> probabilities (and posterior,
+    QUAL, FILTER when the engine has likelihood tables) in host memory.  The host only copies: rows are indexed and tokenized on
+    the device (device_tokenizer), then encoded and run through both networks.  The candidate list is cut into ``pieces``; the
+    text of piece k + 1 is copied on a side stream while piece k is being processed.  ``text_neg`` None: one stream feeds both
+    networks (Illumina, run_clairs_to:1248-1252)."""
+    from .device_tokenizer import tokenize_text_device
+    dev = eng.device
+    cand = np.ascontiguousarray(cand_pos, dtype=np.int64)
+    n = len(cand)
+    h = eng.n_heads
+    out = dict(out or {})
+    if 'probs' not in out:
+        out['probs'] = torch.empty((n, 2 * h, 2), dtype=torch.float32).pin_memory()
+    if eng.has_likelihood:
+        for key, shape, dt in (('post', (n, h), torch.float64), ('call', (n,), torch.int32), ('qual', (n,), torch.float64), ('filter', (n,), torch.int32)):
+            if key not in out:
+                out[key] = torch.empty(shape, dtype=dt).pin_memory()
+    if n == 0:
+        return out
+    if not hasattr(eng, "_text_copy_stream"):
+        eng._text_copy_stream = torch.cuda.Stream(device=dev)
+    cs, main = eng._text_copy_stream, torch.cuda.current_stream()
+    ref_dev = torch.frombuffer(bytearray(ref), dtype=torch.uint8).to(dev, non_blocking=True)
+    texts = [t for t in (text_aff, text_neg) if t is not None]
+    pieces = max(1, min(int(pieces), n))
+    bounds = [n * k // pieces for k in range(pieces + 1)]
+    spans = []                                                  # per piece and stream: byte range of the rows its windows touch
+    for k in range(pieces):
+        lo_pos, hi_pos = int(cand[bounds[k]]) - 16, int(cand[bounds[k + 1] - 1]) + 16
+        spans.append([(_row_start_at_or_after(t, t.numel(), lo_pos), _row_start_at_or_after(t, t.numel(), hi_pos + 1)) for t in texts])
+
+    def issue_copy(k):
+        bufs = []
+        with torch.cuda.stream(cs):
+            for t, (a, b) in zip(texts, spans[k]):
+                buf = torch.empty(b - a + 32, dtype=torch.uint8, device=dev)
+                buf[b - a:].zero_()
+                if b > a:
+                    buf[:b - a].copy_(t[a:b], non_blocking=True)
+                bufs.append((buf, b - a))
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        return bufs, ev
+
+    nxt = issue_copy(0)
+    for k in range(pieces):
+        bufs, ev = nxt
+        if k + 1 < pieces:
+            nxt = issue_copy(k + 1)
+        main.wait_event(ev)
+        c0, c1 = bounds[k], bounds[k + 1]
+        cand_dev = torch.from_numpy(cand[c0:c1]).to(dev, non_blocking=True)
+        packed = [tokenize_text_device(buf, nb, ref_dev, ref_start, low_bq_cut, cand_dev, max_indel_length)[0] for buf, nb in bufs]
+        for buf, _ in bufs:
+            buf.record_stream(main)
+        res = eng.run_sites(packed[0], packed[1] if len(packed) > 1 else None, low_bq_cut)
+        out['probs'][c0:c1].copy_(res['probs'], non_blocking=True)
+        for key in ('post', 'call', 'qual', 'filter'):
+            if key in out and res.get(key) is not None:
+                out[key][c0:c1].copy_(res[key], non_blocking=True)
+    main.synchronize()
+    return out
 
 
 def gemm_nt(a, w, bias=None, residual=None, act=0, tensor_cores=True):

@@ -118,3 +118,30 @@ def test_errors_and_empty_text():
         buf, n = text_to_device(bad, "cuda")
         with pytest.raises(_lib.CtoError):
             tokenize_text_device(buf, n, ref_dev, 1, 10)
+
+
+def test_run_sites_text_equals_host_tokenized_call():
+    """Engine.run_sites_text (text copied in pieces, tokenized on the device) against Engine.run_sites_host on the host-tokenized,
+    host-packed streams of the same sites: probabilities, posteriors, calls, QUAL and FILTER bit-identical, for one piece and
+    for pieces whose row spans overlap."""
+    from clairs_to_b200 import synth_weights as sw
+    from clairs_to_b200.engine import Engine
+    aff_sd = sw.synth_state_dict(sw.aff_state_dict_shapes(4), 104)
+    neg_sd = sw.synth_state_dict(sw.neg_state_dict_shapes(4), 204)
+    rng = np.random.default_rng(3)
+    likelihood = np.concatenate([rng.uniform(0.05, 0.95, size=(40, 10)), np.sort(rng.uniform(0.02, 0.98, size=(8, 10)), axis=1)])
+    eng = Engine(aff_sd, neg_sd, max_batch=256, likelihood=likelihood)
+    (aff, aff_aux), (neg, neg_aux) = synth.synth_pair(700, 31, 'ont')
+    texts = [synth.render_mpileup_text(s, a) for s, a in ((aff, aff_aux), (neg, neg_aux))]
+    ref = ''.join("ACGT"[c] for c in neg.ref_code)
+    cands = np.arange(1001 + 16, 1001 + neg.n_rows, 33, dtype=np.int64)
+    packed = [host_packed(t, ref, 1001, cands, 30)[0] for t in texts]
+    want = eng.run_sites_host(packed[0], packed[1])
+    pinned = [torch.frombuffer(bytearray(t), dtype=torch.uint8).pin_memory() for t in texts]
+    for pieces in (1, 3, 7):
+        got = eng.run_sites_text(pinned[0], pinned[1], ref.encode(), 1001, cands, 30, pieces=pieces)
+        for k in ("probs", "post", "call", "qual", "filter"):
+            assert torch.equal(got[k], want[k]), (pieces, k)
+    one = eng.run_sites_text(pinned[1], None, ref.encode(), 1001, cands, 30, pieces=2)     # one stream feeds both networks
+    assert torch.equal(one["probs"], eng.run_sites_host(packed[1], None)["probs"])
+    eng.close()
