@@ -6,6 +6,7 @@
 #include <new>
 #include <vector>
 #include <climits>
+#include <mutex>
 
 namespace cto {
 
@@ -33,6 +34,36 @@ int device_sm_count() {
         __atomic_store_n(&cached[dev], v, __ATOMIC_RELAXED);
     }
     return v;
+}
+
+// Scratch memory of the stand-alone entry points (row index, candidate scan, device tokenizer): a private stream-ordered pool
+// per device that KEEPS its memory.  cudaMallocAsync on the default pool hands everything back to the driver at the next
+// stream synchronisation (release threshold 0), and these entry points synchronise several times per call: the re-allocation
+// cost 5-50 ms per call, at random (profiles/debug_device_tokenizer.py).  The application's default pool is left alone.
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
+    static cudaMemPool_t pools[64] = {nullptr};
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            e = cudaMemPoolCreate(&pools[dev], &props);
+            if (e != cudaSuccess) return e;
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool = pools[dev];
+    }
+    return cudaMallocFromPoolAsync(p, bytes > 16 ? bytes : 16, pool, s);
 }
 
 int launch_encode_pileup(const uint8_t* planes, const int32_t* grp_off, const uint8_t* ref_code, const int32_t* ind_off,

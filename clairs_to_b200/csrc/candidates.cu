@@ -371,7 +371,7 @@ int launch_scan_candidates(const uint8_t* text_dev, const int64_t* row_off_dev, 
     if (n_over > 0) {                                           // in batches: 160 KB of allele table per row
         const int batch = n_over < 256 ? n_over : 256;
         cand::Allele* scratch = nullptr;
-        CTO_CHECK(cudaMallocAsync((void**)&scratch, sizeof(cand::Allele) * (size_t)cand::BIG_TABLE * batch, s));
+        CTO_CHECK(scratch_alloc((void**)&scratch, sizeof(cand::Allele) * (size_t)cand::BIG_TABLE * batch, s));
         for (int b0 = 0; b0 < n_over; b0 += batch) {
             const int nb = n_over - b0 < batch ? n_over - b0 : batch;
             cand::scan_big_kernel<<<ceil_div(nb, cand::TB), cand::TB, 0, s>>>(text_dev, row_off_dev, overflow_dev + 1 + b0, nb, ref_dev,
@@ -403,7 +403,7 @@ int cto_index_rows(const uint8_t* text_dev, int64_t text_len, int64_t* row_off_d
     }
     const int n_tiles = ceil_div(text_len, cand::IDX_TILE);
     int32_t* tiles = nullptr;
-    CTO_CHECK(cudaMallocAsync((void**)&tiles, sizeof(int32_t) * (size_t)n_tiles + 16, s));
+    CTO_CHECK(scratch_alloc((void**)&tiles, sizeof(int32_t) * (size_t)n_tiles + 16, s));
     int64_t* total = reinterpret_cast<int64_t*>(tiles + ((n_tiles + 1) & ~1));
     int rc = launch_count_rows(text_dev, text_len, tiles, total, n_rows, s);
     if (!rc && row_off_dev) {
@@ -429,7 +429,7 @@ int cto_scan_candidates(const uint8_t* text_dev, int64_t text_len, const int64_t
     CTO_REQUIRE(text_len < (1ll << 32), "scan_candidates: %lld bytes of text in one call (limit 4 GiB)", (long long)text_len);
     cudaStream_t s = (cudaStream_t)stream;
     int32_t* over = nullptr;
-    CTO_CHECK(cudaMallocAsync((void**)&over, sizeof(int32_t) * (size_t)(n_rows + 1), s));
+    CTO_CHECK(scratch_alloc((void**)&over, sizeof(int32_t) * (size_t)(n_rows + 1), s));
     int n_over = 0;
     const int rc = launch_scan_candidates(text_dev, row_off_dev, n_rows, text_len, ref_dev, ref_start, ref_len, min_coverage, snv_min_af,
                                           indel_min_af, alternative_base_num, select_indel_candidates, pos_dev, depth_dev, flags_dev, over,
@@ -477,7 +477,7 @@ int cto_scan_candidates_host(const char* text, int64_t text_len, const char* ref
     const int64_t u8_b = up(rows_cap);
     const int64_t slot_b = text_b + tiles_b + off_b + 3 * i32_b + u8_b;
     uint8_t* arena = nullptr;
-    CTO_CHECK(cudaMallocAsync((void**)&arena, (size_t)(slot_b * n_slots + up(ref_len)), s));
+    CTO_CHECK(scratch_alloc((void**)&arena, (size_t)(slot_b * n_slots + up(ref_len)), s));
     uint8_t* ref_dev = arena + slot_b * n_slots;
     cudaStream_t cs = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};

@@ -47,6 +47,9 @@ static inline cudaError_t set_max_dynamic_smem(F* kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
+// stream-ordered scratch allocation from a private per-device pool that keeps its memory (free with cudaFreeAsync)
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s);
+
 // number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
 int64_t launches();

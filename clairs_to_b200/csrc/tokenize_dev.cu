@@ -292,7 +292,7 @@ int cto_tokenize_count(const uint8_t* text_dev, int64_t text_len, const int64_t*
     size_t tmp_bytes = 0;
     CTO_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, grp_off_dev, grp_off_dev, (int)(n_rows + 1), s));
     uint8_t* scratch = nullptr;
-    CTO_CHECK(cudaMallocAsync((void**)&scratch, tmp_bytes + 256, s));
+    CTO_CHECK(scratch_alloc((void**)&scratch, tmp_bytes + 256, s));
     err = reinterpret_cast<int32_t*>(scratch);
     const int32_t err_init[2] = {0, INT32_MAX};
     CTO_CHECK(cudaMemcpyAsync(err, err_init, sizeof(err_init), cudaMemcpyHostToDevice, s));
@@ -328,7 +328,7 @@ int cto_tokenize_write(const uint8_t* text_dev, int64_t text_len, const int64_t*
     CTO_REQUIRE((reinterpret_cast<uintptr_t>(planes_dev) & 7) == 0, "tokenize_write: planes must be 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     int32_t* over = nullptr;                                     // [0] counter, [1..2] error words, [4..] overflow row list
-    CTO_CHECK(cudaMallocAsync((void**)&over, sizeof(int32_t) * (size_t)(n_rows + 4), s));
+    CTO_CHECK(scratch_alloc((void**)&over, sizeof(int32_t) * (size_t)(n_rows + 4), s));
     const int32_t init[3] = {0, 0, INT32_MAX};
     CTO_CHECK(cudaMemcpyAsync(over, init, sizeof(init), cudaMemcpyHostToDevice, s));
     const int stage = tokd::stage_bytes_for(text_len, n_rows);
@@ -347,7 +347,7 @@ int cto_tokenize_write(const uint8_t* text_dev, int64_t text_len, const int64_t*
         const int n_over = head[0];
         const int batch = n_over < 256 ? n_over : 256;
         tokd::Allele* scratch = nullptr;
-        CTO_CHECK(cudaMallocAsync((void**)&scratch, sizeof(tokd::Allele) * (size_t)tokd::BIG_TABLE * batch, s));
+        CTO_CHECK(scratch_alloc((void**)&scratch, sizeof(tokd::Allele) * (size_t)tokd::BIG_TABLE * batch, s));
         for (int b0 = 0; b0 < n_over; b0 += batch) {
             const int nb = n_over - b0 < batch ? n_over - b0 : batch;
             tokd::tok_big_rows_kernel<<<ceil_div(nb, tokd::TB), tokd::TB, 0, s>>>(text_dev, row_off_dev, over + 4 + b0, nb, ref_dev, ref_start,
