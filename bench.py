@@ -733,7 +733,7 @@ def main():
             out_txt = {k: torch.empty_like(v).pin_memory() for k, v in outs[0].items()}
 
             def dev_text_step():
-                return p0["eng"].run_sites_text(pinned[0], pinned[1], refb, 1001, cands, cut, out=out_txt, pieces=4)
+                return p0["eng"].run_sites_text(pinned[0], pinned[1], refb, 1001, cands, cut, out=out_txt)
 
             got = dev_text_step()                                # outs[0]: what the host-tokenizer path just produced for the same sites
             torch.cuda.synchronize()
@@ -751,7 +751,7 @@ def main():
             e2e["text"] = dict(value=p0["n"] * world * k_dev / float(w.item()), unit=UNIT, steps=k_dev, text_bytes_per_step=text_bytes,
                                h2d_bytes_per_step=text_bytes + len(refb) + 8 * len(cands), d2h_bytes_per_step=sum(t.numel() * t.element_size() for t in out_txt.values()),
                                text_gb_per_s=text_bytes / 1e9 * k_dev / float(w.item()),
-                               api="Engine.run_sites_text: mpileup text (pinned host memory) -> H2D in 4 pieces on a side stream -> "
+                               api="Engine.run_sites_text: mpileup text (pinned host memory) -> H2D per engine chunk on a side stream -> "
                                    "cto_index_rows + cto_tokenize_count / _write + cto_window_table (device) -> encoder -> AFF + NEG -> "
                                    "probabilities D2H; bit-identical to the host-tokenizer path",
                                host_tokenizer=host_tok)

@@ -268,7 +268,7 @@ class Engine:
         hs.n_ind = len(s.ind_entry)
         return hs, keep
 
-    def run_sites_text(self, text_aff, text_neg, ref, ref_start, cand_pos, low_bq_cut, out=None, pieces=4):
+    def run_sites_text(self, text_aff, text_neg, ref, ref_start, cand_pos, low_bq_cut, out=None, pieces=None):
         """mpileup text (pinned host tensors) -> host results; tokenized on the device (see ``run_sites_text`` below)."""
         return run_sites_text(self, text_aff, text_neg, ref, ref_start, cand_pos, low_bq_cut, out, pieces)
 
@@ -339,12 +339,13 @@ def _row_start_at_or_after(text: torch.Tensor, n: int, pos: int) -> int:
     return row_after(lo)
 
 
-def run_sites_text(eng: "Engine", text_aff, text_neg, ref: bytes, ref_start: int, cand_pos, low_bq_cut: int, out=None, pieces: int = 4,
+def run_sites_text(eng: "Engine", text_aff, text_neg, ref: bytes, ref_start: int, cand_pos, low_bq_cut: int, out=None, pieces: int = None,
                    max_indel_length: int = 60):
     """mpileup TEXT in host memory (pinned uint8 tensors, one per stream, rows position sorted) -> probabilities (and posterior,
     QUAL, FILTER when the engine has likelihood tables) in host memory.  The host only copies: rows are indexed and tokenized on
-    the device (device_tokenizer), then encoded and run through both networks.  The candidate list is cut into ``pieces``; the
-    text of piece k + 1 is copied on a side stream while piece k is being processed.  ``text_neg`` None: one stream feeds both
+    the device (device_tokenizer), then encoded and run through both networks.  The candidate list is cut into ``pieces`` (default: one per engine chunk): while
+    the networks of piece k run on the caller's stream, piece k + 1 is tokenized on a second stream and the text of piece k + 2
+    is copied on a third.  ``text_neg`` None: one stream feeds both
     networks (Illumina, run_clairs_to:1248-1252)."""
     from .device_tokenizer import tokenize_text_device
     dev = eng.device
@@ -365,8 +366,13 @@ def run_sites_text(eng: "Engine", text_aff, text_neg, ref: bytes, ref_start: int
     cs, main = eng._text_copy_stream, torch.cuda.current_stream()
     ref_dev = torch.frombuffer(bytearray(ref), dtype=torch.uint8).to(dev, non_blocking=True)
     texts = [t for t in (text_aff, text_neg) if t is not None]
-    pieces = max(1, min(int(pieces), n))
-    bounds = [n * k // pieces for k in range(pieces + 1)]
+    if pieces is None:                                          # one piece per engine chunk: every network pass runs full waves
+        step = int(eng.max_batch)
+        bounds = list(range(0, n, step)) + [n]
+        pieces = len(bounds) - 1
+    else:
+        pieces = max(1, min(int(pieces), n))
+        bounds = [n * k // pieces for k in range(pieces + 1)]
     spans = []                                                  # per piece and stream: byte range of the rows its windows touch
     for k in range(pieces):
         lo_pos, hi_pos = int(cand[bounds[k]]) - 16, int(cand[bounds[k + 1] - 1]) + 16
@@ -397,18 +403,43 @@ def run_sites_text(eng: "Engine", text_aff, text_neg, ref: bytes, ref_start: int
             ev.record(cs)
         return bufs, ev
 
-    nxt = issue_copy(0)
+    if not hasattr(eng, "_text_tok_stream"):
+        eng._text_tok_stream = torch.cuda.Stream(device=dev)
+    ts = eng._text_tok_stream
+    ready = torch.cuda.Event()
+    ready.record(main)                                          # ref_dev and the slots are ready for the side streams after this
+    cs.wait_event(ready)
+    ts.wait_event(ready)
+
+    def tokenize(k, copied):
+        """Piece k on the tokenizer stream: the host waits for ITS row / group counts only, the networks of the previous piece
+        keep running on the caller's stream meanwhile."""
+        bufs, ev = copied
+        with torch.cuda.stream(ts):
+            ts.wait_event(ev)
+            cand_dev = torch.from_numpy(cand[bounds[k]:bounds[k + 1]]).to(dev, non_blocking=True)
+            packed = [tokenize_text_device(buf, nb, ref_dev, ref_start, low_bq_cut, cand_dev, max_indel_length)[0] for buf, nb in bufs]
+            done = torch.cuda.Event()
+            done.record(ts)
+        consumed[k & 1] = done
+        for ps in packed:
+            for a in ps.arrays():
+                a.record_stream(main)
+        return packed, done
+
+    copies = {0: issue_copy(0)}
+    if pieces > 1:
+        copies[1] = issue_copy(1)
+    tok = tokenize(0, copies.pop(0))
     for k in range(pieces):
-        bufs, ev = nxt
-        main.wait_event(ev)
+        packed, done = tok
+        main.wait_event(done)
         c0, c1 = bounds[k], bounds[k + 1]
-        cand_dev = torch.from_numpy(cand[c0:c1]).to(dev, non_blocking=True)
-        packed = [tokenize_text_device(buf, nb, ref_dev, ref_start, low_bq_cut, cand_dev, max_indel_length)[0] for buf, nb in bufs]
-        consumed[k & 1] = torch.cuda.Event()
-        consumed[k & 1].record(main)
-        if k + 1 < pieces:                                      # the copy of the next piece runs beside the networks of this one
-            nxt = issue_copy(k + 1)
         res = eng.run_sites(packed[0], packed[1] if len(packed) > 1 else None, low_bq_cut)
+        if k + 2 < pieces:                                      # slot k & 1 is free again: piece k has been tokenized
+            copies[k + 2] = issue_copy(k + 2)
+        if k + 1 < pieces:                                      # tokenize the next piece beside the networks of this one
+            tok = tokenize(k + 1, copies.pop(k + 1))
         out['probs'][c0:c1].copy_(res['probs'], non_blocking=True)
         for key in ('post', 'call', 'qual', 'filter'):
             if key in out and res.get(key) is not None:

@@ -54,5 +54,5 @@ for k, name in ((0, "AFF stream"), (1, "NEG stream")):
 packed = [tokenize_text_device(b, t.numel(), ref_dev, 1001, 30, cand_dev)[0] for b, t in zip(bufs, pinned)]
 timed("tokenize_text_device x2 (all of the above + window table)", lambda: [tokenize_text_device(b, t.numel(), ref_dev, 1001, 30, cand_dev)[0] for b, t in zip(bufs, pinned)])
 timed("run_sites (encode x2 + AFF + NEG)", lambda: eng.run_sites(packed[0], packed[1], 30))
-for pieces in (1, 2, 4, 8):
-    timed("run_sites_text, %d piece(s)" % pieces, lambda: eng.run_sites_text(pinned[0], pinned[1], ref, 1001, cands, 30, pieces=pieces))
+for pieces in (1, 2, 4, 8, None):
+    timed("run_sites_text, %s piece(s)" % (pieces if pieces else "one per engine chunk (3)"), lambda: eng.run_sites_text(pinned[0], pinned[1], ref, 1001, cands, 30, pieces=pieces))

@@ -138,7 +138,7 @@ def test_run_sites_text_equals_host_tokenized_call():
     packed = [host_packed(t, ref, 1001, cands, 30)[0] for t in texts]
     want = eng.run_sites_host(packed[0], packed[1])
     pinned = [torch.frombuffer(bytearray(t), dtype=torch.uint8).pin_memory() for t in texts]
-    for pieces in (1, 3, 7):
+    for pieces in (1, 3, 7, None):
         got = eng.run_sites_text(pinned[0], pinned[1], ref.encode(), 1001, cands, 30, pieces=pieces)
         for k in ("probs", "post", "call", "qual", "filter"):
             assert torch.equal(got[k], want[k]), (pieces, k)
