@@ -162,3 +162,21 @@ def test_oracle_fisher_and_entropy_equal_reference_golden():
         assert repr(ho.fisher_exact(a, b, c, d)) == want
     for seq, want in g["entropy"]:
         assert repr(ho.entropy_of(seq)) == want
+
+
+def test_row_bisection_of_the_text_path():
+    """engine._row_start_at_or_after (host side of Engine.run_sites_text): byte offset of the first mpileup row at or behind a
+    position, by bisection on byte offsets of position-sorted rows."""
+    import torch
+    from clairs_to_b200.engine import _row_start_at_or_after
+    positions = list(range(100, 200)) + list(range(250, 300)) + [100000, 100001]
+    rows = [b"chr1\t%d\tN\t%d\t%s\tI\t]\n" % (p, 1 + p % 3, b"A" * (1 + 37 * (p % 5))) for p in positions]
+    text = b"".join(rows)
+    t = torch.frombuffer(bytearray(text), dtype=torch.uint8)
+    starts = np.cumsum([0] + [len(r) for r in rows])
+    for q in (0, 100, 101, 150, 199, 200, 220, 250, 299, 300, 99999, 100001, 100002):
+        want = next((int(starts[i]) for i, p in enumerate(positions) if p >= q), len(text))
+        assert _row_start_at_or_after(t, len(text), q) == want, q
+    assert _row_start_at_or_after(t[:0], 0, 5) == 0
+    one = torch.frombuffer(bytearray(rows[0][:-1]), dtype=torch.uint8)            # a single row without a line feed
+    assert _row_start_at_or_after(one, one.numel(), 100) == 0 and _row_start_at_or_after(one, one.numel(), 101) == one.numel()
