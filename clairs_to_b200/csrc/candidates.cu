@@ -50,6 +50,33 @@ struct Allele {
 __device__ __forceinline__ uint8_t upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
 __device__ __forceinline__ int base_index(uint8_t up) { return up == 'A' ? 0 : up == 'C' ? 1 : up == 'G' ? 2 : up == 'T' ? 3 : -1; }
 
+// EC:110-120: one counter per distinct indel allele of the row ('I' + base + sequence in upper case, 'D' + length).  Rare
+// (1-2 % of the reads), so it is kept out of the hot loop.
+template <typename TextPtr>
+__device__ __noinline__ void note_allele(TextPtr t, Allele* table, int cap, int& n_alleles, bool& overflow, uint8_t cur, uint8_t sign,
+                                         int64_t seq_off, uint32_t seq_len) {
+    const uint8_t up = upper(cur);
+    const bool del = sign == '-';
+    uint32_t h = del ? 0x9E3779B9u * (seq_len + 1) : 2166136261u ^ up;
+    if (!del)
+        for (uint32_t k = 0; k < seq_len; ++k) h = (h ^ upper(t[seq_off + k])) * 16777619u;
+    int e = 0;
+    for (; e < n_alleles; ++e) {
+        const Allele& a = table[e];
+        if (a.hash != h || a.del != (uint8_t)del || a.len != seq_len) continue;
+        if (del) break;                                         // 'D' + 'N' * length: the length is the key
+        if (a.sym != up) continue;
+        uint32_t k = 0;
+        while (k < seq_len && upper(t[a.off + k]) == upper(t[seq_off + k])) ++k;
+        if (k == seq_len) break;
+    }
+    if (e < n_alleles) ++table[e].count;
+    else if (n_alleles < cap) {
+        Allele& a = table[n_alleles++];
+        a.off = (uint32_t)seq_off; a.len = seq_len; a.hash = h; a.count = 1; a.del = (uint8_t)del; a.sym = up;
+    } else overflow = true;
+}
+
 // One row.  `t` indexes the chunk text (shared-memory copy or global memory, same offsets).
 template <typename TextPtr>
 __device__ void scan_row(TextPtr t, int64_t lo, int64_t hi, const uint8_t* __restrict__ ref, int64_t ref_start, int64_t ref_len,
@@ -72,44 +99,18 @@ __device__ void scan_row(TextPtr t, int64_t lo, int64_t hi, const uint8_t* __res
     const int ref_b = base_index(ref_up);
     if (ref_b < 0) { *flag_out = 0; return; }                   // EC:341-342: reference base not in ACGT, row skipped
 
-    int cnt[4] = {0, 0, 0, 0};
+    // Hot loop: one byte per iteration, the common characters (read symbols) handled by straight-line code so that the lanes
+    // of a warp stay together; the rare indel suffix is parsed in a branch and its allele bookkeeping is OUT OF LINE
+    // (note_allele).  A first version kept the four base counters in an indexed array (local memory) and inlined the allele
+    // code at both flush sites: ncu showed the symbol path executing with 6 of 32 lanes (profiles/r2_ncu_metrics_scan.txt).
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     int depth = 0, n_alleles = 0;
     bool plain_alt = false, overflow = false;
-    // the read being assembled: its symbol and the LAST indel suffix attached to it (EC:86 overwrites)
+    // the read being assembled: its symbol, whether it is a plain alt base, and the LAST indel suffix attached to it (EC:86 overwrites)
     uint8_t cur = 0, sign = 0;
+    bool cur_alt = false;
     int64_t seq_off = 0;
     uint32_t seq_len = 0;
-    auto commit = [&]() {
-        if (!cur) return;
-        const uint8_t up = upper(cur);
-        const int b = base_index(up);
-        if (b >= 0) { ++cnt[b]; ++depth; }                      // EC:105-107 (reads carrying an indel count too)
-        else if (cur == '#' || cur == '*') ++depth;             // EC:108-109
-        if (!sign) {
-            if (b >= 0 && b != ref_b) plain_alt = true;         // an alt_list key that is a single base (EC:369, 146-148)
-        } else if (p.select_indel) {                            // EC:110-120: one counter per allele
-            const bool del = sign == '-';
-            uint32_t h = del ? 0x9E3779B9u * (seq_len + 1) : 2166136261u ^ up;
-            if (!del)
-                for (uint32_t k = 0; k < seq_len; ++k) h = (h ^ upper(t[seq_off + k])) * 16777619u;
-            int e = 0;
-            for (; e < n_alleles; ++e) {
-                const Allele& a = table[e];
-                if (a.hash != h || a.del != (uint8_t)del || a.len != seq_len) continue;
-                if (del) break;                                 // 'D' + 'N' * length: the length is the key
-                if (a.sym != up) continue;
-                uint32_t k = 0;
-                while (k < seq_len && upper(t[a.off + k]) == upper(t[seq_off + k])) ++k;
-                if (k == seq_len) break;
-            }
-            if (e < n_alleles) ++table[e].count;
-            else if (n_alleles < cap) {
-                Allele& a = table[n_alleles++];
-                a.off = (uint32_t)seq_off; a.len = seq_len; a.hash = h; a.count = 1; a.del = (uint8_t)del; a.sym = up;
-            } else overflow = true;
-        }
-        cur = 0; sign = 0;
-    };
     while (i < hi) {
         const uint8_t c = t[i];
         if (c == '\t' || c == '\n' || c == '\r') break;          // end of column 5 (row.strip().split('\t'))
@@ -121,16 +122,31 @@ __device__ void scan_row(TextPtr t, int64_t lo, int64_t hi, const uint8_t* __res
             i += adv;                                           // EC:87 + 93 net effect; adv == 0 re-reads the character
             continue;
         }
-        const uint8_t up = upper(c);
-        if (up == 'A' || up == 'C' || up == 'G' || up == 'T' || up == 'N' || c == '#' || c == '*') {   // EC:89-90
-            commit();
-            cur = c;
+        const uint32_t lc = c | 0x20u;                           // 'A' and 'a' -> 'a' (no other byte maps onto a letter)
+        const int b = lc == 'a' ? 0 : lc == 'c' ? 1 : lc == 'g' ? 2 : lc == 't' ? 3 : -1;
+        const bool gap = c == '#' || c == '*';
+        if (b >= 0 || lc == 'n' || gap) {                        // EC:89-90: a new read; the previous one is complete
+            if (sign) {
+                if (p.select_indel) note_allele(t, table, cap, n_alleles, overflow, cur, sign, seq_off, seq_len);   // EC:110-120
+            } else {
+                plain_alt |= cur_alt;                            // an alt_list key that is a single base (EC:369, 146-148)
+            }
+            c0 += b == 0; c1 += b == 1; c2 += b == 2; c3 += b == 3;
+            depth += (b >= 0) | gap;                             // EC:105-109 (reads carrying an indel count too)
+            cur = c; cur_alt = b >= 0 && b != ref_b; sign = 0;
         } else if (c == '^') {                                   // EC:91-92
             ++i;
         }
         ++i;
     }
-    commit();
+    if (cur) {
+        if (sign) {
+            if (p.select_indel) note_allele(t, table, cap, n_alleles, overflow, cur, sign, seq_off, seq_len);
+        } else {
+            plain_alt |= cur_alt;
+        }
+    }
+    const int cnt[4] = {c0, c1, c2, c3};
 
     const double denom = depth > 0 ? (double)depth : 1.0;      // EC:121
     const bool pass_depth = (double)depth > p.min_coverage;     // EC:127

@@ -43,13 +43,15 @@ struct StagedText {
     __device__ __forceinline__ uint8_t operator[](int64_t i) const { return s[i - bias]; }
 };
 
-__device__ __forceinline__ int symbol_code(uint8_t c) {       // packed order: ACGT acgt * # N n (host_codec.cpp RECODE)
-    switch (c) {
-        case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
-        case 'a': return 4; case 'c': return 5; case 'g': return 6; case 't': return 7;
-        case '*': return 8; case '#': return 9; case 'N': return 10; case 'n': return 11;
-        default: return -1;
-    }
+__device__ __forceinline__ int symbol_code(uint8_t c) {       // packed order: ACGT acgt * # N n (host_codec.cpp RECODE); -1: no read
+    const uint32_t lc = c | 0x20u;                             // selects, no branches: the lanes of a warp stay together
+    const int base = lc == 'a' ? 0 : lc == 'c' ? 1 : lc == 'g' ? 2 : lc == 't' ? 3 : -1;
+    const int other = c == '*' ? 8 : c == '#' ? 9 : c == 'N' ? 10 : c == 'n' ? 11 : -1;
+    return base >= 0 ? base + ((c & 0x20u) ? 4 : 0) : other;
+}
+__device__ __forceinline__ bool is_symbol(uint8_t c) {         // one of ACGTNacgtn*# (CT:140)
+    const uint32_t k = (c | 0x20u) - 'a';                      // a = 0, c = 2, g = 6, n = 13, t = 19
+    return (k < 26u && ((0x82045u >> k) & 1u)) || c == '*' || c == '#';
 }
 __device__ __forceinline__ uint64_t transpose8x8(uint64_t x) {
     uint64_t t;
@@ -68,6 +70,33 @@ struct Out {
     uint32_t* ind_entry;     // WRITE
     int32_t* error;          // [2]: flag bits, first failing row
 };
+
+// Id of the indel allele (symbol, sign, exact sequence) within its row, in order of first appearance (host_codec.cpp:
+// allele_ids).  Alleles are compared on the text itself.  Rare, hence out of line: the hot loop stays small and converged.
+template <typename TextPtr>
+__device__ __noinline__ int allele_id(TextPtr t, Allele* table, int cap, int& n_alleles, int& err, uint8_t cur, uint8_t sign, int64_t seq_off,
+                                      int64_t seq_len) {
+    uint32_t h = 2166136261u ^ cur;
+    h = (h ^ sign) * 16777619u;
+    for (int64_t z = 0; z < seq_len; ++z) h = (h ^ t[seq_off + z]) * 16777619u;
+    int e = 0;
+    for (; e < n_alleles; ++e) {
+        const Allele& a = table[e];
+        if (a.hash != h || a.len != (uint32_t)seq_len || a.sym != cur || a.sign != sign) continue;
+        int64_t z = 0;
+        while (z < seq_len && t[(int64_t)a.off + z] == t[seq_off + z]) ++z;
+        if (z == seq_len) break;
+    }
+    if (e == n_alleles) {
+        if (n_alleles < cap) {
+            Allele& a = table[n_alleles++];
+            a.off = (uint32_t)seq_off; a.len = (uint32_t)seq_len; a.hash = h; a.sym = cur; a.sign = sign;
+        } else {
+            err |= E_OVERFLOW;
+        }
+    }
+    return e;
+}
 
 // One row.  WRITE = false: counts only.  Returns error bits.
 template <bool WRITE, typename TextPtr>
@@ -101,6 +130,7 @@ __device__ int tok_row(TextPtr t, int64_t lo, int64_t hi, int64_t r, const uint8
     int64_t k = -1;                                             // index of the read being assembled
     int n_ind = 0, n_alleles = 0, err = 0;
     uint8_t cur = 0, sign = 0;
+    int cur_code = 0;
     int64_t seq_off = 0, seq_len = 0;
     uint64_t x = 0;
     const int64_t g0 = WRITE ? o.grp_off[r] : 0;
@@ -110,7 +140,7 @@ __device__ int tok_row(TextPtr t, int64_t lo, int64_t hi, int64_t r, const uint8
         if (!WRITE) { n_ind += sign != 0; return; }
         const uint8_t m = k < n_mq ? (uint8_t)(t[c_lo[6] + k] - 33) : QUAL_ABSENT;
         const uint8_t q = k < n_bq ? (uint8_t)(t[c_lo[5] + k] - 33) : QUAL_ABSENT;
-        uint8_t b = (uint8_t)symbol_code(cur);
+        uint8_t b = (uint8_t)cur_code;
         if (!sign) b |= 0x10;
         if (m != QUAL_ABSENT) b |= (m >= 20) ? 0x20 : 0x40;     // CT:147-148
         if (q != QUAL_ABSENT && (int)q < low_bq_cut) b |= 0x80;  // CT:149
@@ -120,25 +150,7 @@ __device__ int tok_row(TextPtr t, int64_t lo, int64_t hi, int64_t r, const uint8
             x = 0;
         }
         if (sign) {                                             // side list entry: allele id within the row, mq, flags
-            uint32_t h = 2166136261u ^ cur;
-            h = (h ^ sign) * 16777619u;
-            for (int64_t z = 0; z < seq_len; ++z) h = (h ^ t[seq_off + z]) * 16777619u;
-            int e = 0;
-            for (; e < n_alleles; ++e) {
-                const Allele& a = table[e];
-                if (a.hash != h || a.len != (uint32_t)seq_len || a.sym != cur || a.sign != sign) continue;
-                int64_t z = 0;
-                while (z < seq_len && t[(int64_t)a.off + z] == t[seq_off + z]) ++z;
-                if (z == seq_len) break;
-            }
-            if (e == n_alleles) {
-                if (n_alleles < cap) {
-                    Allele& a = table[n_alleles++];
-                    a.off = (uint32_t)seq_off; a.len = (uint32_t)seq_len; a.hash = h; a.sym = cur; a.sign = sign;
-                } else {
-                    err |= E_OVERFLOW;
-                }
-            }
+            const int e = allele_id(t, table, cap, n_alleles, err, cur, sign, seq_off, seq_len);
             uint32_t ent = ((uint32_t)e & 0xFFFFu) | ((uint32_t)m << 16);
             const bool is_del = sign == '-';
             if (is_del) ent |= IND_DEL;
@@ -149,9 +161,12 @@ __device__ int tok_row(TextPtr t, int64_t lo, int64_t hi, int64_t r, const uint8
             ++n_ind;
         }
     };
-    for (int64_t i = 0; i < nb;) {                              // CT:120-144
-        const uint8_t ch = t[b0 + i];
-        if (ch == '+' || ch == '-') {
+    // CT:120-144.  One more iteration than the column has characters: the virtual character behind it completes the last read,
+    // so that finish() is inlined ONCE and the loop body stays small.
+    for (int64_t i = 0; i <= nb;) {
+        const bool at_end = i == nb;
+        const uint8_t ch = at_end ? (uint8_t)'A' : t[b0 + i];
+        if ((ch == '+' || ch == '-') && !at_end) {
             int64_t j = i + 1, len = 0;
             while (j < nb && t[b0 + j] >= '0' && t[b0 + j] <= '9') { len = len * 10 + (t[b0 + j] - '0'); ++j; }
             if (k >= 0) {
@@ -159,17 +174,20 @@ __device__ int tok_row(TextPtr t, int64_t lo, int64_t hi, int64_t r, const uint8
                 sign = ch; seq_off = b0 + j; seq_len = len < avail ? len : avail;
             }
             i = j + len;
+            if (i > nb) i = nb;                                 // a length that runs past the column: the column ends here
             continue;
         }
-        if (symbol_code(ch) >= 0) {
+        if (is_symbol(ch)) {
             finish();
+            if (at_end) break;
             ++k; cur = ch; sign = 0;
+            if (WRITE) cur_code = symbol_code(ch);
         } else if (ch == '^') {
             ++i;
+            if (i >= nb) i = nb - 1;                            // `^` as the last character: nothing behind it to skip
         }
         ++i;
     }
-    finish();
     const int64_t n = k + 1;
     if (!WRITE) {
         o.grp_off[r] = (int32_t)((n + 7) >> 3);
