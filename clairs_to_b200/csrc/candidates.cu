@@ -111,41 +111,82 @@ __device__ void scan_row(TextPtr t, int64_t lo, int64_t hi, const uint8_t* __res
     bool cur_alt = false;
     int64_t seq_off = 0;
     uint32_t seq_len = 0;
-    while (i < hi) {
-        const uint8_t c = t[i];
-        if (c == '\t' || c == '\n' || c == '\r') break;          // end of column 5 (row.strip().split('\t'))
-        if (c == '+' || c == '-') {                              // EC:76-87
-            ++i;
-            uint32_t adv = 0;
-            while (i < hi && t[i] >= '0' && t[i] <= '9') { adv = adv * 10 + (t[i] - '0'); ++i; }
-            if (cur) { sign = c; seq_off = i; seq_len = adv < (uint32_t)(hi - i) ? adv : (uint32_t)(hi - i); }
-            i += adv;                                           // EC:87 + 93 net effect; adv == 0 re-reads the character
-            continue;
+    // One character per iteration for every lane, whatever it is: `skip` swallows the characters of an indel sequence and the
+    // one behind `^`, `digits` collects the length behind a sign.  No inner loops and no `continue`, so the rows of a warp
+    // advance in lockstep and only the per-character work is predicated.
+    // Indel-carrying reads are rare per row (1-2 %) but a warp of 32 rows meets one every few characters, and each used to be
+    // handled where it occurred, by ONE lane (31 % of the issued instructions ran with 0-3 lanes).  They are queued instead and
+    // counted behind the loop, where every lane works on its own queue at the same time.
+    constexpr int QUEUE = 8;
+    uint32_t q_off[QUEUE], q_len[QUEUE];
+    uint16_t q_meta[QUEUE];
+    int n_q = 0;
+    auto queue_allele = [&]() {
+        if (n_q < QUEUE) {
+            q_off[n_q] = (uint32_t)(seq_off - lo); q_len[n_q] = seq_len; q_meta[n_q] = (uint16_t)(cur | (sign << 8));
+            ++n_q;
+        } else {
+            note_allele(t, table, cap, n_alleles, overflow, cur, sign, seq_off, seq_len);      // a deep row: count it right away
         }
-        const uint32_t lc = c | 0x20u;                           // 'A' and 'a' -> 'a' (no other byte maps onto a letter)
-        const int b = lc == 'a' ? 0 : lc == 'c' ? 1 : lc == 'g' ? 2 : lc == 't' ? 3 : -1;
-        const bool gap = c == '#' || c == '*';
-        if (b >= 0 || lc == 'n' || gap) {                        // EC:89-90: a new read; the previous one is complete
-            if (sign) {
-                if (p.select_indel) note_allele(t, table, cap, n_alleles, overflow, cur, sign, seq_off, seq_len);   // EC:110-120
+    };
+    uint32_t skip = 0, adv = 0;
+    bool digits = false, done = false;
+    uint8_t pend = 0;                                           // the sign whose length is being read
+    while (i < hi && !done) {
+        const uint8_t c = t[i];
+        bool normal = true;
+        if (skip) {
+            --skip;
+            normal = false;
+        } else if (digits) {                                     // EC:76-87
+            if (c >= '0' && c <= '9') {
+                adv = adv * 10 + (c - '0');
+                normal = false;
             } else {
-                plain_alt |= cur_alt;                            // an alt_list key that is a single base (EC:369, 146-148)
+                digits = false;
+                if (cur) { sign = pend; seq_off = i; seq_len = adv < (uint32_t)(hi - i) ? adv : (uint32_t)(hi - i); }
+                if (adv) { skip = adv - 1; normal = false; }     // this character is the first of the sequence; adv == 0 re-reads it
             }
-            c0 += b == 0; c1 += b == 1; c2 += b == 2; c3 += b == 3;
-            depth += (b >= 0) | gap;                             // EC:105-109 (reads carrying an indel count too)
-            cur = c; cur_alt = b >= 0 && b != ref_b; sign = 0;
-        } else if (c == '^') {                                   // EC:91-92
-            ++i;
+        }
+        if (normal) {
+            // character class by arithmetic only: a `lc == 'a' ? 0 : lc == 'c' ? 1 : ...` chain is compiled into a branch tree with
+            // one path per base, which splits the lanes of a warp by base identity (6 of 32 lanes per path, ncu source page)
+            const uint32_t lc = c | 0x20u;                       // 'A' and 'a' -> 'a' (no other byte maps onto a letter)
+            const uint32_t k5 = lc - 'a';
+            const uint32_t is_base = k5 < 26u ? (0x80045u >> k5) & 1u : 0u;      // a, c, g, t = bits 0, 2, 6, 19
+            const uint32_t code = (lc >> 1) & 3u;                // a 0, c 1, t 2, g 3
+            const int b = is_base ? (int)(code ^ (code >> 1)) : -1;             // -> A 0, C 1, G 2, T 3
+            const bool gap = c == '#' || c == '*';
+            if (is_base || lc == 'n' || gap) {                   // EC:89-90: a new read; the previous one is complete
+                if (sign) {
+                    if (p.select_indel) queue_allele();   // EC:110-120
+                } else {
+                    plain_alt |= cur_alt;                        // an alt_list key that is a single base (EC:369, 146-148)
+                }
+                c0 += is_base & (uint32_t)(b == 0); c1 += is_base & (uint32_t)(b == 1);
+                c2 += is_base & (uint32_t)(b == 2); c3 += is_base & (uint32_t)(b == 3);
+                depth += is_base | (uint32_t)gap;                // EC:105-109 (reads carrying an indel count too)
+                cur = c; cur_alt = is_base && b != ref_b; sign = 0;
+            } else if (c == '+' || c == '-') {
+                digits = true; adv = 0; pend = c;
+            } else if (c == '^') {                               // EC:91-92
+                skip = 1;
+            } else if (c == '\t' || c == '\n' || c == '\r') {    // end of column 5 (row.strip().split('\t'))
+                done = true;
+            }
         }
         ++i;
     }
+    if (digits && cur) { sign = pend; seq_off = hi; seq_len = 0; }   // a length that runs into the end of the row
     if (cur) {
         if (sign) {
-            if (p.select_indel) note_allele(t, table, cap, n_alleles, overflow, cur, sign, seq_off, seq_len);
+            if (p.select_indel) queue_allele();
         } else {
             plain_alt |= cur_alt;
         }
     }
+    for (int e = 0; e < n_q; ++e)
+        note_allele(t, table, cap, n_alleles, overflow, (uint8_t)(q_meta[e] & 0xff), (uint8_t)(q_meta[e] >> 8), lo + q_off[e], q_len[e]);
     const int cnt[4] = {c0, c1, c2, c3};
 
     const double denom = depth > 0 ? (double)depth : 1.0;      // EC:121
