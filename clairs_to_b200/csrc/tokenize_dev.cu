@@ -43,11 +43,15 @@ struct StagedText {
     __device__ __forceinline__ uint8_t operator[](int64_t i) const { return s[i - bias]; }
 };
 
-__device__ __forceinline__ int symbol_code(uint8_t c) {       // packed order: ACGT acgt * # N n (host_codec.cpp RECODE); -1: no read
-    const uint32_t lc = c | 0x20u;                             // selects, no branches: the lanes of a warp stay together
-    const int base = lc == 'a' ? 0 : lc == 'c' ? 1 : lc == 'g' ? 2 : lc == 't' ? 3 : -1;
-    const int other = c == '*' ? 8 : c == '#' ? 9 : c == 'N' ? 10 : c == 'n' ? 11 : -1;
-    return base >= 0 ? base + ((c & 0x20u) ? 4 : 0) : other;
+__device__ __forceinline__ int symbol_code(uint8_t c) {       // packed order: ACGT acgt * # N n (host_codec.cpp RECODE); c is a read symbol
+    // arithmetic, not a chain of `c == 'A' ? 0 : ...`: the compiler turns such a chain into one branch per base, which splits the
+    // lanes of a warp by base identity (measured on scan_kernel)
+    const uint32_t lc = c | 0x20u, k5 = lc - 'a';
+    const uint32_t is_base = k5 < 26u ? (0x80045u >> k5) & 1u : 0u;              // a, c, g, t
+    const uint32_t code = (lc >> 1) & 3u;                                        // a 0, c 1, t 2, g 3
+    const int base = (int)((code ^ (code >> 1)) + ((c & 0x20u) >> 3));           // A 0 C 1 G 2 T 3, lower case + 4
+    const int other = c == '*' ? 8 : c == '#' ? 9 : c == 'N' ? 10 : 11;
+    return is_base ? base : other;
 }
 __device__ __forceinline__ bool is_symbol(uint8_t c) {         // one of ACGTNacgtn*# (CT:140)
     const uint32_t k = (c | 0x20u) - 'a';                      // a = 0, c = 2, g = 6, n = 13, t = 19
@@ -135,6 +139,28 @@ __device__ int tok_row(TextPtr t, int64_t lo, int64_t hi, int64_t r, const uint8
     uint64_t x = 0;
     const int64_t g0 = WRITE ? o.grp_off[r] : 0;
     const int64_t i0 = WRITE ? o.ind_off[r] : 0;
+    // Indel-carrying reads are rare per row but frequent per warp; handled where they occur they run on ONE lane.  They are
+    // queued (in read order: allele ids count first appearances) and turned into side-list entries behind the loop, where all
+    // lanes work on their queues at the same time; a deep row drains its queue whenever it is full.
+    constexpr int QUEUE = 8;
+    uint32_t q_off[QUEUE], q_len[QUEUE], q_meta[QUEUE];
+    int n_q = 0;
+    auto drain = [&]() {
+        for (int e = 0; e < n_q; ++e) {
+            const uint8_t sym = (uint8_t)(q_meta[e] & 0xff), sg = (uint8_t)((q_meta[e] >> 8) & 0xff), m = (uint8_t)(q_meta[e] >> 16);
+            const int64_t off = lo + q_off[e], len = q_len[e];
+            const int id = allele_id(t, table, cap, n_alleles, err, sym, sg, off, len);
+            uint32_t ent = ((uint32_t)id & 0xFFFFu) | ((uint32_t)m << 16);
+            const bool is_del = sg == '-';
+            if (is_del) ent |= IND_DEL;
+            const bool fwd = sym == 'A' || sym == 'C' || sym == 'G' || sym == 'T' || sym == 'N' || sym == '*';   // CT:182, 199
+            if (!fwd) ent |= IND_REV;
+            if ((is_del ? len + 1 : len) > max_indel_length) ent |= IND_LONG;                                    // CT:174, 189
+            o.ind_entry[i0 + n_ind] = ent;
+            ++n_ind;
+        }
+        n_q = 0;
+    };
     auto finish = [&]() {                                       // the read `k` is complete: its suffix cannot change any more
         if (k < 0) return;
         if (!WRITE) { n_ind += sign != 0; return; }
@@ -149,16 +175,10 @@ __device__ int tok_row(TextPtr t, int64_t lo, int64_t hi, int64_t r, const uint8
             *reinterpret_cast<uint64_t*>(o.planes + (g0 + (k >> 3)) * 8) = transpose8x8(x);
             x = 0;
         }
-        if (sign) {                                             // side list entry: allele id within the row, mq, flags
-            const int e = allele_id(t, table, cap, n_alleles, err, cur, sign, seq_off, seq_len);
-            uint32_t ent = ((uint32_t)e & 0xFFFFu) | ((uint32_t)m << 16);
-            const bool is_del = sign == '-';
-            if (is_del) ent |= IND_DEL;
-            const bool fwd = cur == 'A' || cur == 'C' || cur == 'G' || cur == 'T' || cur == 'N' || cur == '*';   // CT:182, 199
-            if (!fwd) ent |= IND_REV;
-            if ((is_del ? seq_len + 1 : seq_len) > max_indel_length) ent |= IND_LONG;                            // CT:174, 189
-            o.ind_entry[i0 + n_ind] = ent;
-            ++n_ind;
+        if (sign) {                                             // side list entry: queued, written behind the loop (see below)
+            if (n_q == QUEUE) drain();
+            q_off[n_q] = (uint32_t)(seq_off - lo); q_len[n_q] = (uint32_t)seq_len; q_meta[n_q] = (uint32_t)cur | ((uint32_t)sign << 8) | ((uint32_t)m << 16);
+            ++n_q;
         }
     };
     // CT:120-144.  One more iteration than the column has characters: the virtual character behind it completes the last read,
@@ -188,6 +208,7 @@ __device__ int tok_row(TextPtr t, int64_t lo, int64_t hi, int64_t r, const uint8
         }
         ++i;
     }
+    if (WRITE) drain();
     const int64_t n = k + 1;
     if (!WRITE) {
         o.grp_off[r] = (int32_t)((n + 7) >> 3);
