@@ -786,6 +786,8 @@ def main():
                                 heads=[h for h, _ in cfg["parts"]], engine_chunk=args.max_batch, weights="seeded random init",
                                 l2_policy="inputs (%.0f MB per step and GPU) larger than the 126 MB L2" % (sum(p["h2d"] for p in parts) / 1e6),
                                 parallelism="candidates sharded x%d, one gather of probabilities" % world,
+                                streams="value: AFF and NEG back to back on one stream with the per-kernel events of the roofline on; "
+                                        "e2e: AFF on a second stream beside NEG (cto_engine_set_overlap, bit-identical)",
                                 host_cores_bound_to_gpu_numa_node=numa, datagen_s=round(t_gen, 1)),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, cli=cli, candidate_scan=scan, hard_filters=filters, gpu_launches=int(launches), clocks=clocks)
         print(json.dumps(line))
