@@ -6,12 +6,12 @@
 // position of a chunk; it is byte work with a few integer counters per row, so here it is one THREAD per mpileup row:
 //
 //   * the text of a chunk lies in device memory as it came out of samtools; row r is text[row_off[r], row_off[r + 1]);
-//   * a block of 128 consecutive rows stages its span of the text in shared memory with coalesced 16-byte loads (rows are
-//     ~3 bytes per read, so a block's span is ~20 KB at 50x; a span that does not fit is read in place);
-//   * every thread walks its row: column 2 = position, column 5 = the bases string; read symbols, `+N<seq>` / `-N<seq>`
-//     suffixes (attached to the previous read, EC:76-87), `^x` (two characters) and everything else skipped -- exactly the
-//     reference's state machine, including its corner cases (a `+0` suffix, a second suffix replacing the first, an N read
-//     carrying an indel);
+//   * every thread walks its row in place (byte loads through L1; a shared-memory stage was measured slower, see scan_kernel):
+//     column 2 = position, column 5 = the bases string; read symbols, `+N<seq>` / `-N<seq>` suffixes (attached to the previous
+//     read, EC:76-87), `^x` (two characters) and everything else skipped -- exactly the reference's state machine, including
+//     its corner cases (a `+0` suffix, a second suffix replacing the first, an N read carrying an indel); one character per
+//     loop iteration, character classes by arithmetic, so that the 32 rows of a warp advance together;
+//   * indel-carrying reads are queued per thread and counted behind the loop (all lanes at once instead of one at a time);
 //   * with --select_indel_candidates the reference counts every distinct indel allele ('I' + base + sequence in upper case,
 //     'D' + length, EC:111-120): a per-thread table of 24 alleles, compared on the text itself; a row with more distinct
 //     alleles is flagged and re-run by a second launch whose tables live in global memory (8192 alleles per row);
@@ -27,7 +27,6 @@ namespace cto {
 namespace cand {
 
 constexpr int TB = 128;                  // rows per block
-constexpr int MAX_STAGE = 96 * 1024;     // staged text bytes per block, upper bound (chosen per launch from the mean row length)
 constexpr int TABLE = 24;                // distinct indel alleles per row in the first pass
 constexpr int BIG_TABLE = 8192;          // ... in the second pass (global memory)
 
@@ -213,38 +212,19 @@ struct GlobalText {
     const uint8_t* p;
     __device__ __forceinline__ uint8_t operator[](int64_t i) const { return __ldg(p + i); }
 };
-struct StagedText {
-    const uint8_t* s;                    // shared-memory copy of text[bias, ...)
-    int64_t bias;
-    __device__ __forceinline__ uint8_t operator[](int64_t i) const { return s[i - bias]; }
-};
 
+// The text is read in place (byte loads through L1): staging a block's span in shared memory first was measured 10 % SLOWER
+// (1.16 against 1.06 ms per 572 MB) -- two thirds of a row are the quality columns, which this scan never looks at, and the
+// stage limited the SM to 6 blocks.  (The tokenizer kernels, which read every column, keep their stage.)
 __global__ void __launch_bounds__(TB)
 scan_kernel(const uint8_t* __restrict__ text, const int64_t* __restrict__ row_off, int64_t n_rows, const uint8_t* __restrict__ ref,
-            int64_t ref_start, int64_t ref_len, Params p, int stage_bytes, int32_t* __restrict__ pos_out,
-            int32_t* __restrict__ depth_out, uint8_t* __restrict__ flags_out, int32_t* __restrict__ overflow_rows,
-            int32_t* __restrict__ overflow_count) {
-    extern __shared__ __align__(16) uint8_t stage[];
-    const int64_t r0 = (int64_t)blockIdx.x * TB;
-    const int64_t r1 = r0 + TB < n_rows ? r0 + TB : n_rows;
-    const int64_t span_lo = row_off[r0] & ~int64_t(15), span_hi = row_off[r1];
-    const bool staged = span_hi - span_lo <= stage_bytes && (reinterpret_cast<uintptr_t>(text) & 15) == 0;
-    if (staged) {
-        const uint4* src = reinterpret_cast<const uint4*>(text + span_lo);
-        const int64_t n16 = (span_hi - span_lo + 15) >> 4;      // may read up to 15 bytes past the text: the buffer is padded
-        for (int64_t k = threadIdx.x; k < n16; k += TB) reinterpret_cast<uint4*>(stage)[k] = __ldg(src + k);
-    }
-    __syncthreads();
-    const int64_t r = r0 + threadIdx.x;
-    if (r >= r1) return;
+            int64_t ref_start, int64_t ref_len, Params p, int32_t* __restrict__ pos_out, int32_t* __restrict__ depth_out,
+            uint8_t* __restrict__ flags_out, int32_t* __restrict__ overflow_rows, int32_t* __restrict__ overflow_count) {
+    const int64_t r = (int64_t)blockIdx.x * TB + threadIdx.x;
+    if (r >= n_rows) return;
     Allele table[TABLE];
     uint8_t flag;
-    if (staged)
-        scan_row(StagedText{stage, span_lo}, row_off[r], row_off[r + 1], ref, ref_start, ref_len, p, table, TABLE, pos_out + r,
-                 depth_out + r, &flag);
-    else
-        scan_row(GlobalText{text}, row_off[r], row_off[r + 1], ref, ref_start, ref_len, p, table, TABLE, pos_out + r, depth_out + r,
-                 &flag);
+    scan_row(GlobalText{text}, row_off[r], row_off[r + 1], ref, ref_start, ref_len, p, table, TABLE, pos_out + r, depth_out + r, &flag);
     flags_out[r] = flag;
     if (flag & F_OVERFLOW) overflow_rows[atomicAdd(overflow_count, 1)] = (int32_t)r;
 }
@@ -411,15 +391,9 @@ int launch_scan_candidates(const uint8_t* text_dev, const int64_t* row_off_dev, 
     CTO_REQUIRE(n_rows < (1ll << 31), "scan_candidates: %lld rows in one call", (long long)n_rows);
     cand::Params p{min_coverage, snv_min_af, indel_min_af, alt_num, select_indel};
     CTO_CHECK(cudaMemsetAsync(overflow_dev, 0, sizeof(int32_t), s));
-    // staging buffer: 1.5x the mean span of 128 rows (a block whose span is larger reads the text in place)
-    int64_t stage = (text_len / n_rows + 1) * cand::TB * 3 / 2 + 1024;
-    stage = (stage + 1023) & ~int64_t(1023);
-    if (stage < 8 * 1024) stage = 8 * 1024;
-    if (stage > cand::MAX_STAGE) stage = cand::MAX_STAGE;
-    CTO_CHECK(set_max_dynamic_smem(cand::scan_kernel, cand::MAX_STAGE));
     const unsigned blocks = (unsigned)ceil_div(n_rows, cand::TB);
-    cand::scan_kernel<<<blocks, cand::TB, stage, s>>>(text_dev, row_off_dev, n_rows, ref_dev, ref_start, ref_len, p, (int)stage, pos_dev,
-                                                      depth_dev, flags_dev, overflow_dev + 1, overflow_dev);
+    cand::scan_kernel<<<blocks, cand::TB, 0, s>>>(text_dev, row_off_dev, n_rows, ref_dev, ref_start, ref_len, p, pos_dev, depth_dev, flags_dev,
+                                                  overflow_dev + 1, overflow_dev);
     CTO_CHECK(cudaGetLastError());
     count_launch();
     int32_t n_over = 0;

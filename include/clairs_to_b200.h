@@ -304,7 +304,7 @@ int cto_parse_predict_file(const char* text, int64_t len, int n_heads, int64_t m
  * Candidate scan -- STEP 1 of the pipeline, SURVEY.md section 8 row f3.  Replaces the per-row work of
  * src/extract_candidates_calling.py: the tokenizer and counters of decode_pileup_bases (ibid. 73-120), its allele-frequency /
  * coverage tests (122-144) and the SNV / indel candidate rules of extract_pair_candidates (335-377), for EVERY row of a
- * chunk's `samtools mpileup` text, on the GPU (one thread per row, text staged in shared memory).
+ * chunk's `samtools mpileup` text, on the GPU (one thread per row).
  *
  * cto_index_rows: byte offsets of the rows of a '\n'-separated text in device memory.  row_off_dev int64 [cap_rows + 1]
  * receives row_off[0 .. n_rows] (row_off[n_rows] = text_len; a last row without '\n' counts); NULL = count only.
@@ -321,8 +321,8 @@ int cto_parse_predict_file(const char* text, int64_t len, int n_heads, int64_t m
  * ref_dev: upper- or lower-case reference bases of positions ref_start .. ref_start + ref_len - 1 (1-based, the
  * `reference_sequence` / `reference_start` of ibid. 286-297).  alternative_base_num < 0 stands for None (ibid. 134-137).
  * Rows with more than 24 distinct indel alleles take a second launch; *n_overflow (nullable) reports how many did.
- * Contract: text_dev 16-byte aligned and ALLOCATED up to the next multiple of 16 bytes beyond text_len (an unaligned
- * pointer takes the slower in-place path); text_len < 4 GiB per call.  Synchronises the stream.
+ * Contract: text_len < 4 GiB per call; cto_index_rows reads 16-byte blocks, so text_dev should be ALLOCATED up to the next
+ * multiple of 16 bytes beyond text_len (any alignment works).  Synchronises the stream.
  *
  * cto_scan_candidates_host: the same from HOST memory (text as samtools wrote it, preferably pinned): the text is cut
  * into 32 MB pieces at row ends, piece k + 1 is copied while piece k is indexed and scanned; outputs are host arrays of
