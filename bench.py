@@ -243,6 +243,7 @@ def hard_filter_leg(peaks, dev, n_sites=200, replicas=8, steps=5):
     from clairs_to_b200 import synth
     rows, ref, lo, sites = synth.hard_filter_chunk(n_sites, 2025, depth=50, read_len=(400, 4000))
     text = "".join(rows).encode()
+    hf.parse_chunk(text, True, ref, lo)
     t0 = time.perf_counter()
     chunk = hf.parse_chunk(text, True, ref, lo)
     t_parse = time.perf_counter() - t0
@@ -291,9 +292,9 @@ def hard_filter_leg(peaks, dev, n_sites=200, replicas=8, steps=5):
     from concurrent.futures import ThreadPoolExecutor
     n_thr = max(1, min(8, len(os.sched_getaffinity(0))))
     with ThreadPoolExecutor(max_workers=n_thr) as ex:
-        list(ex.map(lambda _: hf.haplotype_filter_chunk("chr20", sites, text, ref, lo), range(n_thr)))
+        list(ex.map(lambda _: hf.haplotype_filter_chunk("chr20", sites, text, ref, lo, n_threads=1), range(n_thr)))
         t0 = time.perf_counter()
-        res = list(ex.map(lambda _: hf.haplotype_filter_chunk("chr20", sites, text, ref, lo), range(2 * n_thr)))
+        res = list(ex.map(lambda _: hf.haplotype_filter_chunk("chr20", sites, text, ref, lo, n_threads=1), range(2 * n_thr)))
         t_pool = time.perf_counter() - t0
     assert all(r == lines for r in res)
     # CPU port on a sample of the sites (parse included, like the reference's chunk mode)
@@ -317,10 +318,10 @@ def hard_filter_leg(peaks, dev, n_sites=200, replicas=8, steps=5):
                               note="algorithmic bytes = 14 B (read id, token id, info, qualities) per pileup entry of every site's window, "
                                    "read once; the %d replicas of the site list share one chunk, so the reads come from L2" % replicas),
                 e2e=dict(sites_per_s=len(sites) / t_e2e, seconds=t_e2e, host_parse_s=t_parse, host_parse_mb_per_s=len(text) / 1e6 / t_parse,
-                         api="hard_filters.haplotype_filter_chunk: mpileup text -> cto_hf_parse (one host thread) -> site tables -> "
+                         api="hard_filters.haplotype_filter_chunk: mpileup text -> cto_hf_parse_mt (up to 8 host threads) -> site tables -> "
                              "cto_hard_filter_sites -> lines",
                          chunks_on_a_thread_pool=dict(sites_per_s=2 * n_thr * len(sites) / t_pool, threads=n_thr, chunks=2 * n_thr,
-                                                      note="one chunk per thread, like the reference's ThreadPoolExecutor over chunk jobs")),
+                                                      note="one chunk per thread (tokenizer on one thread each), like the reference's ThreadPoolExecutor over chunk jobs")),
                 cpu_baseline=dict(sites_per_s=len(sample) / (t_cpu + t_cpu_parse * len(sample) / len(sites)), cores=1, kind="port",
                                   sample="%d sites, oracle/hard_filter_oracle.py (parse time pro rata)" % len(sample)),
                 failing=int((~(dev_flags & 1).astype(bool)).sum()),

@@ -72,6 +72,7 @@ SIGNATURES = {
     "cto_tokenize_write": (INT, [P, I64, P, I64, P, I64, I64, INT, INT, P, P, P, P, P]),
     "cto_window_table": (INT, [P, I64, P, I64, P, P]),
     "cto_hf_parse": (INT, [C.c_char_p, I64, INT, C.c_char_p, I64, I64, P]),
+    "cto_hf_parse_mt": (INT, [C.c_char_p, I64, INT, C.c_char_p, I64, I64, INT, P]),
     "cto_hf_sizes": (INT, [P, P]),
     "cto_hf_export": (INT, [P] * 15),
     "cto_hf_free": (None, [P]),

@@ -17,6 +17,7 @@
 #include <string.h>
 #include <set>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -57,15 +58,14 @@ struct cto_hf_chunk {
 
 using cto::set_error;
 
-extern "C" {
+namespace {
 
-int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* ref, int64_t ref_len, int64_t region_lo, cto_hf_chunk** out) {
-    CTO_REQUIRE(out, "hf_parse: NULL out");
-    *out = nullptr;
-    CTO_REQUIRE(len >= 0 && (len == 0 || text), "hf_parse: bad text");
-    CTO_REQUIRE(ref_len >= 0 && (ref_len == 0 || ref), "hf_parse: bad reference");
-    cto_hf_chunk* ck = new cto_hf_chunk();
+// Rows of text[begin, len) (whole rows) -> `ck`, with ids local to this range.  On failure: `err` = what, *err_line = the
+// 1-based row within the range.  *first_pos / *last_pos: positions of the first and last row taken (-1: none).
+int parse_range(const char* text, int64_t begin, int64_t len, int with_phasing, const char* ref, int64_t ref_len, int64_t region_lo,
+                cto_hf_chunk* ck, std::string& err, int64_t* err_line, int64_t* first_pos, int64_t* last_pos_out) {
     ck->sfxs.get(std::string());                                 // suffix id 0 = no suffix
+    *first_pos = *last_pos_out = -1;
     std::vector<int32_t> last_row_of_read, last_entry_of_read;
     // Consecutive pileup rows list mostly the same reads in the same order: the read keys of the previous row (text offset,
     // length, strand, id) are tried first, the hash map only for reads that are new or moved.  Single-character tokens
@@ -78,11 +78,11 @@ int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* re
     std::vector<Tok> row_toks;
     std::string key, token, suffix;
     auto fail = [&](const char* what, int64_t line) {
-        set_error("hf_parse: %s (row %lld)", what, (long long)line);
-        delete ck;
+        err = what;
+        *err_line = line;
         return 2;
     };
-    int64_t i = 0, line_no = 0;
+    int64_t i = begin, line_no = 0;
     int64_t last_pos = -1;
     while (i < len) {
         const char* nl = (const char*)memchr(text + i, '\n', (size_t)(len - i));
@@ -108,8 +108,9 @@ int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* re
             pos = pos * 10 + (text[k] - '0');
         }
         if (pos <= last_pos) return fail("rows are not in strictly increasing position order", line_no);
-        CTO_REQUIRE(pos < (1ll << 31), "hf_parse: position %lld", (long long)pos);
+        if (pos >= (1ll << 31)) return fail("position beyond 2^31", line_no);
         last_pos = pos;
+        if (*first_pos < 0) *first_pos = pos;
         // the bases column: HF:154-185
         row_toks.clear();
         std::set<int32_t> starts, ends;
@@ -253,11 +254,145 @@ int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* re
         ck->row_pos.push_back((int32_t)pos);
         ck->row_off.push_back((int32_t)ck->rid.size());
         ck->row_flags.push_back(flags);
-        CTO_REQUIRE(ck->rid.size() < (1ull << 31), "hf_parse: more than 2^31 pileup entries in one chunk");
+        if (ck->rid.size() >= (1ull << 31)) return fail("more than 2^31 pileup entries in one chunk", line_no);
         i = next;
     }
+    *last_pos_out = last_pos;
+    return 0;
+}
+
+// ids of `part`'s strings in `all` (interned in the part's own order, which keeps "order of first appearance" overall)
+std::vector<int32_t> remap(Interner& all, const Interner& part) {
+    std::vector<int32_t> m(part.ids.size());
+    for (size_t k = 0; k < m.size(); ++k) m[k] = all.get(part.blob.substr((size_t)part.off[k], (size_t)(part.off[k + 1] - part.off[k])));
+    return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+// n_threads: 0 = as many as the machine has, at most 8, and one for texts under 8 MB.  The text is cut at row ends into
+// n_threads ranges parsed side by side with local ids; the ranges are then appended in order and their ids translated, which
+// gives the very arrays the single-threaded parse gives (tests/test_hard_filter_host.py).
+int cto_hf_parse_mt(const char* text, int64_t len, int with_phasing, const char* ref, int64_t ref_len, int64_t region_lo, int n_threads,
+                    cto_hf_chunk** out) {
+    CTO_REQUIRE(out, "hf_parse: NULL out");
+    *out = nullptr;
+    CTO_REQUIRE(len >= 0 && (len == 0 || text), "hf_parse: bad text");
+    CTO_REQUIRE(ref_len >= 0 && (ref_len == 0 || ref), "hf_parse: bad reference");
+    int nt = n_threads;
+    if (nt <= 0) {
+        nt = (int)std::thread::hardware_concurrency();
+        if (nt > 8) nt = 8;
+        if (len < (8ll << 20)) nt = 1;
+    }
+    if (nt < 1) nt = 1;
+    std::vector<int64_t> cut{0};                                 // range boundaries on row starts
+    for (int k = 1; k < nt; ++k) {
+        int64_t at = len * k / nt;
+        if (at <= cut.back()) continue;
+        const void* nl = memchr(text + at, '\n', (size_t)(len - at));
+        at = nl ? (const char*)nl - text + 1 : len;
+        if (at > cut.back() && at < len) cut.push_back(at);
+    }
+    cut.push_back(len);
+    const int n_parts = (int)cut.size() - 1;
+    std::vector<cto_hf_chunk*> parts(n_parts, nullptr);
+    std::vector<std::string> errs(n_parts);
+    std::vector<int64_t> err_line(n_parts, 0), first(n_parts, -1), last(n_parts, -1);
+    std::vector<int> rcs(n_parts, 0);
+    auto work = [&](int k) {
+        parts[k] = new cto_hf_chunk();
+        rcs[k] = parse_range(text, cut[k], cut[k + 1], with_phasing, ref, ref_len, region_lo, parts[k], errs[k], &err_line[k], &first[k], &last[k]);
+    };
+    if (n_parts == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_parts; ++k) th.emplace_back(work, k);
+        for (auto& t : th) t.join();
+    }
+    auto cleanup = [&]() { for (auto* p : parts) delete p; };
+    int64_t prev_last = -1;
+    for (int k = 0; k < n_parts; ++k) {
+        if (!rcs[k] && first[k] >= 0 && first[k] <= prev_last) {
+            rcs[k] = 2; errs[k] = "rows are not in strictly increasing position order"; err_line[k] = 1;
+        }
+        if (rcs[k]) {
+            int64_t before = 0;                                  // rows in front of this range
+            for (int64_t b = 0; b < cut[k];) {
+                const void* nl = memchr(text + b, '\n', (size_t)(cut[k] - b));
+                if (!nl) break;
+                ++before;
+                b = (const char*)nl - text + 1;
+            }
+            set_error("hf_parse: %s (row %lld)", errs[k].c_str(), (long long)(before + err_line[k]));
+            cleanup();
+            return 2;
+        }
+        if (last[k] >= 0) prev_last = last[k];
+    }
+    if (n_parts == 1) {
+        *out = parts[0];
+        return 0;
+    }
+    cto_hf_chunk* ck = new cto_hf_chunk();
+    ck->sfxs.get(std::string());
+    size_t n_rows = 0, n_ent = 0, n_rse = 0;
+    for (auto* p : parts) { n_rows += p->row_pos.size(); n_ent += p->rid.size(); n_rse += p->rse_ent.size(); }
+    if (n_ent >= (1ull << 31)) {
+        set_error("hf_parse: more than 2^31 pileup entries in one chunk");
+        cleanup();
+        delete ck;
+        return 2;
+    }
+    ck->row_pos.resize(n_rows); ck->row_off.resize(n_rows + 1); ck->rse_off.resize(n_rows + 1); ck->row_flags.resize(n_rows);
+    ck->rse_ent.resize(n_rse);
+    ck->rid.resize(n_ent); ck->tok.resize(n_ent); ck->sfx.resize(n_ent); ck->info.resize(n_ent); ck->qual.resize(n_ent);
+    ck->row_off[0] = 0; ck->rse_off[0] = 0;
+    // the id translation tables are built in range order (that IS the order of first appearance); the arrays are then filled
+    // by the ranges side by side
+    std::vector<std::vector<int32_t>> mr(n_parts), mt(n_parts), ms(n_parts);
+    std::vector<size_t> e_base(n_parts), r_base(n_parts), s_base(n_parts);
+    size_t eb = 0, rb = 0, sb = 0;
+    for (int k = 0; k < n_parts; ++k) {
+        mr[k] = remap(ck->reads, parts[k]->reads); mt[k] = remap(ck->toks, parts[k]->toks); ms[k] = remap(ck->sfxs, parts[k]->sfxs);
+        e_base[k] = eb; r_base[k] = rb; s_base[k] = sb;
+        eb += parts[k]->rid.size(); rb += parts[k]->row_pos.size(); sb += parts[k]->rse_ent.size();
+    }
+    auto fill = [&](int k) {
+        const cto_hf_chunk* p = parts[k];
+        const size_t e0 = e_base[k], r0 = r_base[k], s0 = s_base[k];
+        for (size_t e = 0; e < p->rid.size(); ++e) {
+            ck->rid[e0 + e] = mr[k][p->rid[e]];
+            ck->tok[e0 + e] = mt[k][p->tok[e]];
+            ck->sfx[e0 + e] = ms[k][p->sfx[e]];
+        }
+        if (!p->info.empty()) {
+            memcpy(ck->info.data() + e0, p->info.data(), p->info.size() * sizeof(uint32_t));
+            memcpy(ck->qual.data() + e0, p->qual.data(), p->qual.size() * sizeof(uint16_t));
+        }
+        for (size_t j = 0; j < p->rse_ent.size(); ++j) ck->rse_ent[s0 + j] = p->rse_ent[j] + (int32_t)e0;
+        for (size_t r = 0; r < p->row_pos.size(); ++r) {
+            ck->row_pos[r0 + r] = p->row_pos[r];
+            ck->row_flags[r0 + r] = p->row_flags[r];
+            ck->row_off[r0 + r + 1] = p->row_off[r + 1] + (int32_t)e0;
+            ck->rse_off[r0 + r + 1] = p->rse_off[r + 1] + (int32_t)s0;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_parts; ++k) th.emplace_back(fill, k);
+        for (auto& t : th) t.join();
+    }
+    cleanup();
     *out = ck;
     return 0;
+}
+
+int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* ref, int64_t ref_len, int64_t region_lo, cto_hf_chunk** out) {
+    return cto_hf_parse_mt(text, len, with_phasing, ref, ref_len, region_lo, 0, out);
 }
 
 int cto_hf_sizes(const cto_hf_chunk* ck, int64_t* sizes) {

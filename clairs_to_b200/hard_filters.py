@@ -88,13 +88,15 @@ def entropy_table():
     return (C.c_double * 35)(*tab), -1 / math.log(ENTROPY_WINDOW)
 
 
-def parse_chunk(text: bytes, with_phasing: bool, chunk_ref: str, region_lo: int) -> PhasedChunk:
-    """HF:246-275 / PV:237-259 over the whole chunk: ``text`` is what samtools wrote."""
+def parse_chunk(text: bytes, with_phasing: bool, chunk_ref: str, region_lo: int, n_threads: int = 0) -> PhasedChunk:
+    """HF:246-275 / PV:237-259 over the whole chunk: ``text`` is what samtools wrote.  ``n_threads``: host threads of the
+    tokenizer (0 = up to 8 for texts of 8 MB and more; pass 1 when chunks already run on a thread pool)."""
     lib = _lib.lib()
     chunk_ref = chunk_ref or ""
     refb = chunk_ref.encode()
     handle = C.c_void_p()
-    _lib.check(lib.cto_hf_parse(text, len(text), int(bool(with_phasing)), refb, len(refb), int(region_lo), C.byref(handle)), "cto_hf_parse")
+    _lib.check(lib.cto_hf_parse_mt(text, len(text), int(bool(with_phasing)), refb, len(refb), int(region_lo), int(n_threads), C.byref(handle)),
+               "cto_hf_parse")
     try:
         sizes = (C.c_int64 * 8)()
         _lib.check(lib.cto_hf_sizes(handle, sizes), "cto_hf_sizes")
@@ -300,18 +302,18 @@ def format_lines(mode, ctg_name, sites, flags, pval):
 
 
 def haplotype_filter_chunk(ctg_name, sites, mpileup_text, chunk_ref, region_lo, flanking=100, disable_read_start_end_filtering=False,
-                           max_co_exist_read_num=3, device="cuda"):
+                           max_co_exist_read_num=3, device="cuda", n_threads=0):
     """The site loop of ``_run_haplotype_chunk`` (HF:1078-1125): ``sites`` = [(pos, ref_base, alt_base, af, hetero_info,
     homo_info)] as in HAP_INFO (HF:1023-1030); returns the lines ``_haplotype_build_state_and_line`` would."""
-    chunk = parse_chunk(mpileup_text, True, chunk_ref, region_lo)
+    chunk = parse_chunk(mpileup_text, True, chunk_ref, region_lo, n_threads)
     flags, pval = run_sites(chunk, 1, sites, flanking, disable_read_start_end_filtering, max_co_exist_read_num, device)
     return format_lines(1, ctg_name, sites, flags, pval)
 
 
 def postfilter_chunk(ctg_name, sites, mpileup_text, chunk_ref, region_lo, flanking=100, disable_read_start_end_filtering=False,
-                     max_co_exist_read_num=3, device="cuda"):
+                     max_co_exist_read_num=3, device="cuda", n_threads=0):
     """The site loop of the post-filter chunk mode: ``sites`` = [(pos, ref_base, alt_base)]; returns the lines
     ``_postfilter_build_state_and_line`` (PV:368-446) would."""
-    chunk = parse_chunk(mpileup_text, False, chunk_ref, region_lo)
+    chunk = parse_chunk(mpileup_text, False, chunk_ref, region_lo, n_threads)
     flags, pval = run_sites(chunk, 0, sites, flanking, disable_read_start_end_filtering, max_co_exist_read_num, device)
     return format_lines(0, ctg_name, sites, flags, pval)

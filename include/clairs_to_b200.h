@@ -407,6 +407,10 @@ int cto_window_table(const int32_t* row_pos_dev, int64_t n_rows, const int64_t* 
 typedef struct cto_hf_chunk cto_hf_chunk;
 int cto_hf_parse(const char* text, int64_t len, int with_phasing, const char* ref, int64_t ref_len, int64_t region_lo,
                  cto_hf_chunk** out);
+/* the same on n_threads host threads (0 = up to 8, one for texts under 8 MB): row ranges parsed side by side, ids translated when
+ * the ranges are appended -- the arrays are identical to the single-threaded ones */
+int cto_hf_parse_mt(const char* text, int64_t len, int with_phasing, const char* ref, int64_t ref_len, int64_t region_lo,
+                    int n_threads, cto_hf_chunk** out);
 int cto_hf_sizes(const cto_hf_chunk* chunk, int64_t* sizes);
 int cto_hf_export(const cto_hf_chunk* chunk, int32_t* row_pos, int32_t* row_off, uint8_t* row_flags, int32_t* rse_off,
                   int32_t* rse_ent, int32_t* rid, int32_t* tok, int32_t* sfx, uint32_t* info, uint16_t* qual, int32_t* tok_off,

@@ -180,3 +180,28 @@ def test_row_bisection_of_the_text_path():
     assert _row_start_at_or_after(t[:0], 0, 5) == 0
     one = torch.frombuffer(bytearray(rows[0][:-1]), dtype=torch.uint8)            # a single row without a line feed
     assert _row_start_at_or_after(one, one.numel(), 100) == 0 and _row_start_at_or_after(one, one.numel(), 101) == one.numel()
+
+
+@pytest.mark.parametrize("phased", [True, False])
+def test_threaded_parse_equals_single_threaded(phased):
+    """cto_hf_parse_mt: row ranges parsed on several threads with local ids, translated when appended -> the same arrays and
+    the same interned strings in the same order as one thread gives; errors name the same row."""
+    rows, ref, lo, sites = synth.hard_filter_chunk(30, 77, with_phasing=phased, depth=35, read_len=(60, 400))
+    text = "".join(rows).encode()
+    one = hf.parse_chunk(text, phased, ref, lo, n_threads=1)
+    for nt in (2, 3, 7, 64):
+        many = hf.parse_chunk(text, phased, ref, lo, n_threads=nt)
+        for name in ("row_pos", "row_off", "row_flags", "rse_off", "rse_ent", "rid", "tok", "sfx", "info", "qual"):
+            assert np.array_equal(getattr(one, name), getattr(many, name)), (nt, name)
+        assert one.tokens == many.tokens and one.suffixes == many.suffixes and one.n_reads == many.n_reads
+    bad = rows[:400] + [rows[100]] + rows[400:]                               # a position out of order deep inside the text
+    for nt in (1, 4):
+        with pytest.raises(_lib.CtoError, match="row 401"):
+            hf.parse_chunk("".join(bad).encode(), phased, ref, lo, n_threads=nt)
+    cut = rows[:250] + ["\t".join(rows[250].split("\t")[:7] + ["a,b"] + (["0"] if phased else [])) + "\n"] + rows[251:]
+    msgs = []
+    for nt in (1, 5):
+        with pytest.raises(_lib.CtoError) as e:
+            hf.parse_chunk("".join(cut).encode(), phased, ref, lo, n_threads=nt)
+        msgs.append(str(e.value))
+    assert msgs[0] == msgs[1] and "row 251" in msgs[0]
