@@ -152,7 +152,13 @@ def _site_tables(chunk: PhasedChunk, mode: int, sites, flanking: int):
     for k, tk in enumerate(chunk.tokens):
         if '+' in tk:
             ins_by_text.setdefault(tk.replace('+', ''), []).append(k)
-    sfx_tables = {}                                             # (ab[:2], ab[1:2]) -> match bits per distinct raw suffix
+    bodies = [x[1:] if len(x) > 1 else None for x in chunk.suffixes]     # `value[1][1:]` of HF:447, only for len(value[1]) > 1
+    key_hits = {}                                               # substring -> uint8 [suffixes]: the substring occurs in the body
+
+    def suffix_hits(key):
+        if key not in key_hits:
+            key_hits[key] = np.fromiter((b is not None and key in b for b in bodies), np.uint8, len(bodies))
+        return key_hits[key]
     scratch_words = 0
 
     def record(gp, ab):
@@ -167,11 +173,7 @@ def _site_tables(chunk: PhasedChunk, mode: int, sites, flanking: int):
             if len(ab) == 1:                                    # HF:444-445 / 473-474: symbol + raw suffix == alt
                 m = (chunk.tok[lo:hi] == chunk.tok_ids.get(ab, -1)).astype(np.uint8) * 3
             elif len(ab) > 1:                                   # HF:446-448 (ab[:2]) / 475-477 (ab[1:2]): substring of the raw suffix
-                keys = (ab[:2], ab[1:2])
-                if keys not in sfx_tables:
-                    sfx_tables[keys] = np.array([(1 if len(x) > 1 and keys[0] in x[1:] else 0) | (2 if len(x) > 1 and keys[1] in x[1:] else 0)
-                                                 for x in chunk.suffixes], np.uint8)
-                m = sfx_tables[keys][chunk.sfx[lo:hi]]
+                m = (suffix_hits(ab[:2]) | (suffix_hits(ab[1:2]) << 1))[chunk.sfx[lo:hi]]
             else:
                 m = np.zeros(hi - lo, np.uint8)
             g_match.append(m)
@@ -181,6 +183,11 @@ def _site_tables(chunk: PhasedChunk, mode: int, sites, flanking: int):
         germline[key] = len(g_row) - 1
         return germline[key]
 
+    site_pos = np.array([int(site[0]) for site in sites], np.int64)
+    anchors = np.maximum(site_pos - flanking, 1)
+    lo_all = np.searchsorted(row_pos, anchors, 'left')
+    hi_all = np.searchsorted(row_pos, site_pos + flanking, 'right')
+    c_all = np.searchsorted(row_pos, site_pos)
     for s, site in enumerate(sites):
         pos, ref_base, alt_base = int(site[0]), site[1], site[2]
         af = site[3] if len(site) > 3 and site[3] is not None else 1.0
@@ -189,9 +196,7 @@ def _site_tables(chunk: PhasedChunk, mode: int, sites, flanking: int):
         anchor = max(pos - flanking, 1)
         if anchor < chunk.region_lo:
             raise ValueError("site %d: its window starts before the chunk's reference (%d)" % (pos, chunk.region_lo))
-        lo = int(np.searchsorted(row_pos, anchor, 'left'))
-        hi = int(np.searchsorted(row_pos, pos + flanking, 'right'))
-        c = int(np.searchsorted(row_pos, pos))
+        lo, hi, c = int(lo_all[s]), int(hi_all[s]), int(c_all[s])
         t["row_lo"][s], t["row_hi"][s] = lo, hi
         t["centre_row"][s] = c if c < chunk.n_rows and row_pos[c] == pos else -1
         is_snp = len(ref_base) == 1 and len(alt_base) == 1
