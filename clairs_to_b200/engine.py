@@ -351,6 +351,8 @@ def run_sites_text(eng: "Engine", text_aff, text_neg, ref: bytes, ref_start: int
     dev = eng.device
     cand = np.ascontiguousarray(cand_pos, dtype=np.int64)
     n = len(cand)
+    if n > 1 and bool(np.any(cand[1:] < cand[:-1])):
+        raise ValueError("run_sites_text: candidate positions must be in ascending order (the text is cut by position)")
     h = eng.n_heads
     out = dict(out or {})
     if 'probs' not in out:
