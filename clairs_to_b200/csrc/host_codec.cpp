@@ -24,14 +24,16 @@ constexpr uint8_t HAS_INDEL = 0x10;
 constexpr uint8_t QUAL_ABSENT = 254;
 constexpr uint32_t IND_DEL = 1u << 24, IND_REV = 1u << 25, IND_LONG = 1u << 26;
 
-inline int symbol_index(char c) {
-    switch (c) {
-        case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; case 'N': return 4;
-        case 'a': return 5; case 'c': return 6; case 'g': return 7; case 't': return 8; case 'n': return 9;
-        case '*': return 10; case '#': return 11;
-        default: return -1;
+struct SymbolTable {
+    int8_t idx[256];
+    SymbolTable() {
+        for (int k = 0; k < 256; ++k) idx[k] = -1;
+        const char* order = "ACGTNacgtn*#";
+        for (int k = 0; order[k]; ++k) idx[(uint8_t)order[k]] = (int8_t)k;
     }
-}
+};
+const SymbolTable SYMBOLS;
+inline int symbol_index(char c) { return SYMBOLS.idx[(uint8_t)c]; }
 
 inline char upper(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
 
@@ -139,6 +141,13 @@ int tokenize_range(const char* text, int64_t text_len, const char* ref_seq, int6
         main_counts.clear();
         if (!main_index.empty()) main_index.clear();
         const bool is_cand = cand.count(pos) != 0;
+        const size_t read_base = t->code.size();
+        t->code.resize(read_base + entries.size());
+        t->mq.resize(read_base + entries.size());
+        t->bq.resize(read_base + entries.size());
+        uint8_t* out_code = t->code.data() + read_base;
+        uint8_t* out_mq = t->mq.data() + read_base;
+        uint8_t* out_bq = t->bq.data() + read_base;
         for (size_t k = 0; k < entries.size(); ++k) {
             const Entry& e = entries[k];
             const uint8_t mqv = (int)k < n_mq ? (uint8_t)(col[6][k] - 33) : QUAL_ABSENT;
@@ -168,9 +177,9 @@ int tokenize_range(const char* text, int64_t text_len, const char* ref_seq, int6
                 if (span > max_indel_length) ent |= IND_LONG;
                 t->ind_entry.push_back(ent);
             }
-            t->code.push_back(c);
-            t->mq.push_back(mqv);
-            t->bq.push_back(bqv);
+            out_code[k] = c;
+            out_mq[k] = mqv;
+            out_bq[k] = bqv;
             if (is_cand && mqv != QUAL_ABSENT && mqv >= 20) {        // base_counter, CT:147
                 auto it = main_index.find(key);
                 if (it == main_index.end()) {
