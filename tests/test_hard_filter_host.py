@@ -205,3 +205,23 @@ def test_threaded_parse_equals_single_threaded(phased):
             hf.parse_chunk("".join(cut).encode(), phased, ref, lo, n_threads=nt)
         msgs.append(str(e.value))
     assert msgs[0] == msgs[1] and "row 251" in msgs[0]
+
+
+def test_result_lines_and_no_cpu_fallback():
+    """format_lines spells the reference's result line (HF:560-565 / PV:362-365) from the flag bits; without a CUDA device
+    the filters refuse to run instead of falling back to anything (here: the build container has no GPU)."""
+    import torch
+    f = hf.O_VERDICT | hf.O_HETERO | hf.O_HOMO | hf.O_RSE | hf.O_BQ | hf.O_MQ | hf.O_CO_EXIST | hf.O_BOTH | hf.O_SB | hf.O_ENTROPY
+    lines = hf.format_lines(1, "chr7", [(140753336, "A", "T")], np.array([f], np.uint32), np.array([0.123456789]))
+    assert lines == ["chr7 140753336 True False True True True True True True True True 0.12346 True"]
+    lines = hf.format_lines(1, "chr7", [(5,)], np.array([hf.O_PHASEABLE], np.uint32), np.array([1e-9]))
+    assert lines == ["chr7 5 False True False False False False False False False False 0.0 False"]
+    lines = hf.format_lines(0, "chr7", [(5,)], np.array([hf.O_VERDICT | hf.O_RSE | hf.O_CO_EXIST | hf.O_SB | hf.O_ENTROPY], np.uint32), np.array([1.0]))
+    assert lines == ["chr7 5 True True True True 1.0 True"]
+    assert hf._split_germline("12-A,15-ACG,12-A") == {(12, "A"), (15, "ACG")} and hf._split_germline("") == set() and hf._split_germline(None) == set()
+    with pytest.raises(ValueError):
+        hf._split_germline("12-A-C")
+    if not torch.cuda.is_available():
+        chunk = hf.parse_chunk(b"c\t3\tN\t1\tG\tI\t]\tr9\t1\n", True, "ACGTACGT", 1)
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            hf.run_sites(chunk, 1, [(3, "A", "G", 0.5, "", "")])
